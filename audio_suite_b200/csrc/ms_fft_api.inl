@@ -1,0 +1,119 @@
+// ms_fft_api.inl -- C-ABI entry points of the spectral stage (include/microsound_b200.h).
+// Included by ms_lib.cu (nvcc, product) and by tests/host_emul (g++, block emulator).
+#include "ms_fft_host.h"
+#include "../../include/microsound_b200.h"
+
+static_assert(sizeof(ms_band_edge) == sizeof(BandEdge), "ABI mirror of BandEdge");
+
+static inline size_t ms_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void copy_edge(BandEdge& d, const ms_band_edge& s) {
+    d.lo_f0 = s.lo_f0; d.lo_f1 = s.lo_f1; d.hi_f0 = s.hi_f0; d.hi_f1 = s.hi_f1;
+    d.lo_mode = s.lo_mode; d.hi_mode = s.hi_mode; d.zero = s.zero; d._pad = 0;
+}
+
+struct SpecLayout { size_t jobs_off, z_off, work_off, total; std::vector<size_t> z_at, work_at; };
+
+// geometry only (no buffers); fills `out` in input order
+static int spec_prepare(const ms_spec_job* in, int njobs, std::vector<FftJob>& out, SpecLayout& lay, ms_stream_t st) {
+    out.resize(njobs);
+    lay.z_at.resize(njobs); lay.work_at.resize(njobs);
+    size_t z = 0, w = 0;
+    for (int i = 0; i < njobs; ++i) {
+        FftJob& J = out[i];
+        memset(&J, 0, sizeof J);
+        if (FftEngine::get().prepare(J, in[i].n, st)) return -1;
+        lay.z_at[i] = z; z += (size_t)J.n;
+        lay.work_at[i] = w; if (J.F1 > 1) w += (size_t)J.M;
+    }
+    lay.jobs_off = 0;
+    lay.z_off = ms_align256(sizeof(FftJob) * (size_t)njobs);
+    lay.work_off = lay.z_off + ms_align256(sizeof(float2) * z);
+    lay.total = lay.work_off + ms_align256(sizeof(float2) * w);
+    return 0;
+}
+
+extern "C" size_t ms_spectral_workspace_bytes(const ms_spec_job* jobs, int njobs) {
+    std::vector<FftJob> tmp; SpecLayout lay;
+    if (njobs <= 0) return 256;
+    if (spec_prepare(jobs, njobs, tmp, lay, (ms_stream_t)0)) return 0;
+    return lay.total;
+}
+
+struct SpectralPlan { std::vector<FftJob> jobs; FftJob* jobs_dev; };
+
+extern "C" int ms_spectral_create(const ms_spec_job* in, int njobs, const float* src, float* dst,
+                                  void* ws, size_t ws_bytes, void* stream, void** handle) {
+    *handle = nullptr;
+    ms_stream_t st = (ms_stream_t)stream;
+    SpectralPlan* P = new SpectralPlan();
+    P->jobs_dev = nullptr;
+    if (njobs <= 0) { *handle = P; return 0; }
+    std::vector<FftJob>& jobs = P->jobs; SpecLayout lay;
+    if (spec_prepare(in, njobs, jobs, lay, st)) { delete P; return -1; }
+    if (ws_bytes < lay.total) { delete P; MS_FAIL("ms_spectral_create: workspace %zu < required %zu", ws_bytes, lay.total); }
+    char* base = (char*)ws;
+    for (int i = 0; i < njobs; ++i) {
+        FftJob& J = jobs[i];
+        const ms_spec_job& s = in[i];
+        J.in_a = src + s.in_a; J.in_b = s.in_b >= 0 ? src + s.in_b : nullptr;
+        J.out_a = dst + s.out_a; J.out_b = s.out_b >= 0 ? dst + s.out_b : nullptr;
+        J.Z = (float2*)(base + lay.z_off) + lay.z_at[i];
+        J.work = J.F1 > 1 ? (float2*)(base + lay.work_off) + lay.work_at[i] : nullptr;
+        J.out_scale = 1.0f / (float)J.n;
+        for (int w = 0; w < 2; ++w) {
+            SpecOp& op = J.op[w];
+            const ms_spec_op& so = s.op[w];
+            op.kind = so.kind; op.n_bands = so.n_bands; op.lp_on = so.lp_on; op.stretch_on = so.stretch_on;
+            op.df = so.df; op.factor = so.factor; op.alpha = so.alpha;
+            copy_edge(op.lp, so.lp);
+            for (int b = 0; b < 3; ++b) copy_edge(op.mb[b], so.mb[b]);
+        }
+    }
+    std::stable_sort(jobs.begin(), jobs.end(), [](const FftJob& a, const FftJob& b) {
+        return FftEngine::job_class(a) < FftEngine::job_class(b); });
+    P->jobs_dev = (FftJob*)(base + lay.jobs_off);
+    if (ms_h2d(P->jobs_dev, jobs.data(), sizeof(FftJob) * jobs.size(), st)) { delete P; return -1; }
+    *handle = P;
+    return 0;
+}
+extern "C" int ms_spectral_run(void* handle, void* stream) {
+    SpectralPlan* P = (SpectralPlan*)handle;
+    if (!P) MS_FAIL("ms_spectral_run: null handle");
+    if (P->jobs.empty()) return 0;
+    ms_stream_t st = (ms_stream_t)stream;
+    if (FftEngine::get().forward(P->jobs, P->jobs_dev, st)) return -1;
+    return FftEngine::get().inverse(P->jobs, P->jobs_dev, st);
+}
+extern "C" void ms_spectral_destroy(void* handle) { delete (SpectralPlan*)handle; }
+
+extern "C" int ms_spectral_apply(const ms_spec_job* in, int njobs, const float* src, float* dst,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    if (njobs <= 0) return 0;
+    void* h = nullptr;
+    if (ms_spectral_create(in, njobs, src, dst, ws, ws_bytes, stream, &h)) return -1;
+    const int rc = ms_spectral_run(h, stream);
+    ms_spectral_destroy(h);
+    return rc;
+}
+
+extern "C" size_t ms_fft_pair_workspace_bytes(int n) {
+    ms_spec_job j; memset(&j, 0, sizeof j); j.n = n;
+    return ms_spectral_workspace_bytes(&j, 1);
+}
+
+extern "C" int ms_fft_pair_forward(const float* a, const float* b, int n, float* z_out,
+                                   void* ws, size_t ws_bytes, void* stream) {
+    ms_stream_t st = (ms_stream_t)stream;
+    ms_spec_job s; memset(&s, 0, sizeof s); s.n = n;
+    std::vector<FftJob> jobs; SpecLayout lay;
+    if (spec_prepare(&s, 1, jobs, lay, st)) return -1;
+    if (ws_bytes < lay.total) MS_FAIL("ms_fft_pair_forward: workspace %zu < required %zu", ws_bytes, lay.total);
+    char* base = (char*)ws;
+    FftJob& J = jobs[0];
+    J.in_a = a; J.in_b = b; J.Z = (float2*)z_out;
+    J.work = J.F1 > 1 ? (float2*)(base + lay.work_off) : nullptr;
+    FftJob* jd = (FftJob*)(base + lay.jobs_off);
+    if (ms_h2d(jd, jobs.data(), sizeof(FftJob), st)) return -1;
+    return FftEngine::get().forward(jobs, jd, st);
+}

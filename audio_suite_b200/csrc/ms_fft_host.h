@@ -1,0 +1,288 @@
+// ms_fft_host.h -- host side of the spectral engine: geometry planning, twiddle / chirp / Bluestein
+// filter caches, and the kernel sequences.  Compiled by nvcc into the product and by g++ into the
+// block emulator used by the CPU tests (same source, see ms_rt.cuh).
+#pragma once
+#include "ms_fft_kernels.cuh"
+#include "ms_launch.cuh"
+#include <map>
+#include <mutex>
+#include <vector>
+#include <algorithm>
+#include <utility>
+
+#define MS_SMALL_MAX 8192       // largest vector one CTA transforms in shared memory
+#define MS_TILE_MAX 8192        // largest tile (complex elements) a CTA holds
+
+// ---- kernel structs ----------------------------------------------------------------------------------
+template <int LD, int ST, int TWID> struct ColsK {
+    static constexpr int MAXT = 512;
+    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_body<LD, ST, TWID>(jobs, c); }
+};
+template <int LD, int MODE, int ST> struct RowsK {
+    static constexpr int MAXT = 512;
+    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_rows_body<LD, MODE, ST>(jobs, c); }
+};
+struct GenTableK {
+    static constexpr int MAXT = 256;
+    static MS_DEV void run(float2* out, int count, long long mul, long long N, const Ctx& c) {
+        gen_table_body(out, count, mul, N, c, c.nthr * 64, c.bx * c.nthr + c.tid);
+    }
+};
+
+static inline bool ms_is_smooth(long long n) {
+    if (n < 1) return false;
+    while (n % 2 == 0) n /= 2;
+    while (n % 3 == 0) n /= 3;
+    while (n % 5 == 0) n /= 5;
+    return n == 1;
+}
+static inline int ms_round32(int x) { return (x + 31) / 32 * 32; }
+
+struct LaunchShape { int ept, nthr; size_t smem; unsigned gx; };
+
+static inline int cols_tile_elems(const FftJob& J) { return J.T * J.F1; }
+static inline int rows_tile_elems(const FftJob& J) { return J.G * J.F2; }
+static inline size_t cols_smem(const FftJob& J) { return 2 * sizeof(float2) * (size_t)(ms_pad((J.F1 - 1) * J.T + J.T - 1) + 2); }
+static inline size_t rows_smem(const FftJob& J) { return 2 * sizeof(float2) * (size_t)(J.G * ((ms_pad(J.F2) + 1) | 1) + 2); }
+
+static inline void shape_for(int tile, LaunchShape* s) {
+    s->ept = 0;
+    s->nthr = std::min(512, std::max(64, ms_round32((tile + 15) / 16)));
+}
+
+class FftEngine {
+public:
+    static FftEngine& get() { static FftEngine e; return e; }
+
+    // Fill geometry + table pointers of J for logical length n.  Returns 0 / -1.
+    int prepare(FftJob& J, int n, ms_stream_t st) {
+        std::lock_guard<std::mutex> lk(mu_);
+        return prepare_locked(J, n, st);
+    }
+
+    // jobs_dev: device copy of `jobs` (same order).  Jobs must be sorted by job_class().
+    static int job_class(const FftJob& J) { return (J.ch_hi ? 2 : 0) + (J.F1 > 1 ? 1 : 0); }
+
+    // forward: pair (in_a,in_b) -> Z ;  inverse: spec op on Z -> (out_a,out_b)
+    int forward(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 0); }
+    int inverse(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 1); }
+    // complex natural-order transform cin -> cout (direct lengths only; test entry)
+    int c2c(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 2); }
+    // filter spectrum: real taps at in_a (n of them) -> FFT_M / M in [k1][k2] layout at `work`
+    int filter_spectrum(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 3); }
+    // overlap-save: two blocks per job, multiplied by `bspec`, valid outputs stored
+    int overlap_save(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 4); }
+
+private:
+    std::mutex mu_;
+    std::map<int, float2*> wtab_;                                  // F -> w_F^i
+    std::map<long long, std::pair<float2*, float2*>> two_level_;   // modulus N -> (hi, lo)
+    std::map<int, float2*> bspec_;                                 // n -> Bluestein filter spectrum
+    std::map<int, FftJob> geom_;                                   // n -> prepared geometry template
+
+    template <class K, class... A>
+    static int L(unsigned gx, unsigned gy, int nthr, size_t smem, ms_stream_t st, A... a) {
+        MsDim g; g.x = gx; g.y = gy;
+        return ms_launch<K>(g, nthr, smem, st, a...);
+    }
+
+    int get_wtab(int F, ms_stream_t st, const float2** out) {
+        auto it = wtab_.find(F);
+        if (it == wtab_.end()) {
+            float2* p = (float2*)ms_dev_alloc(sizeof(float2) * (size_t)F);
+            if (!p) MS_FAIL("out of device memory for twiddle table F=%d", F);
+            if (L<GenTableK>(64, 1, 256, 0, st, p, F, 1ll, (long long)F)) return -1;
+            it = wtab_.emplace(F, p).first;
+        }
+        *out = it->second;
+        return 0;
+    }
+    int get_two_level(long long N, ms_stream_t st, const float2** hi, const float2** lo) {
+        auto it = two_level_.find(N);
+        if (it == two_level_.end()) {
+            int nhi = (int)((N + 1023) / 1024) + 1;
+            float2* ph = (float2*)ms_dev_alloc(sizeof(float2) * (size_t)nhi);
+            float2* pl = (float2*)ms_dev_alloc(sizeof(float2) * 1024);
+            if (!ph || !pl) MS_FAIL("out of device memory for two-level table N=%lld", N);
+            if (L<GenTableK>(64, 1, 256, 0, st, ph, nhi, 1024ll, N)) return -1;
+            if (L<GenTableK>(64, 1, 256, 0, st, pl, 1024, 1ll, N)) return -1;
+            it = two_level_.emplace(N, std::make_pair(ph, pl)).first;
+        }
+        *hi = it->second.first; *lo = it->second.second;
+        return 0;
+    }
+
+    static bool plan_direct(int n, FftJob& J) {
+        if (!ms_is_smooth(n)) return false;
+        J.M = n;
+        if (n <= MS_SMALL_MAX) { J.F1 = 1; J.F2 = n; J.T = 1; J.G = 1; return true; }
+        int best = 0; long long best_cost = -1;
+        for (int f1 = 2; f1 <= 2048 && f1 < n; ++f1) {
+            if (n % f1) continue;
+            int f2 = n / f1;
+            if (f2 > 2048 || f2 < 2) continue;
+            long long cost = (long long)std::max(f1, f2) + ((f1 > 512 || f2 > 512) ? 100000 : 0)
+                           + ((f1 > 1024 || f2 > 1024) ? 1000000 : 0);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = f1; }
+        }
+        if (!best) return false;
+        J.F1 = best; J.F2 = n / best;
+        J.T = 16; J.G = 16;
+        while (J.T > 1 && J.T * J.F1 > MS_TILE_MAX) J.T /= 2;
+        while (J.G > 1 && J.G * J.F2 > MS_TILE_MAX) J.G /= 2;
+        return true;
+    }
+    static bool plan_bluestein(int n, FftJob& J) {
+        long long need = 2ll * n - 1, M = 1; int lg = 0;
+        while (M < need) { M <<= 1; ++lg; }
+        if (M > (1ll << 22)) return false;
+        J.M = (int)M;
+        if (M <= MS_SMALL_MAX) { J.F1 = 1; J.F2 = (int)M; J.T = 1; J.G = 1; return true; }
+        int l1 = std::min(lg / 2, 9);
+        J.F1 = 1 << l1; J.F2 = (int)(M >> l1);
+        if (J.F2 > MS_TILE_MAX) return false;
+        J.T = 16;
+        while (J.T > 1 && J.T * J.F1 > MS_TILE_MAX / 2) J.T /= 2;
+        J.G = std::max(1, std::min(16, (MS_TILE_MAX / 2) / J.F2));
+        return true;
+    }
+
+    int prepare_locked(FftJob& J, int n, ms_stream_t st) {
+        if (n < 1) MS_FAIL("fft: bad length %d", n);
+        auto it = geom_.find(n);
+        if (it == geom_.end()) {
+            FftJob g; memset(&g, 0, sizeof g);
+            g.n = n;
+            bool blu = false;
+            if (!plan_direct(n, g)) { blu = true; if (!plan_bluestein(n, g)) MS_FAIL("fft: length %d unsupported", n); }
+            if (!ms_make_radix_plan(g.F2, &g.p2)) MS_FAIL("fft: cannot factor %d", g.F2);
+            if (get_wtab(g.F2, st, &g.tw2)) return -1;
+            if (g.F1 > 1) {
+                if (!ms_make_radix_plan(g.F1, &g.p1)) MS_FAIL("fft: cannot factor %d", g.F1);
+                if (get_wtab(g.F1, st, &g.tw1)) return -1;
+                if (get_two_level(g.M, st, &g.twM_hi, &g.twM_lo)) return -1;
+            }
+            if (blu) {
+                if (get_two_level(2ll * n, st, &g.ch_hi, &g.ch_lo)) return -1;
+                if (make_bspec(g, st)) return -1;
+            }
+            it = geom_.emplace(n, g).first;
+        }
+        const FftJob& g = it->second;
+        J.n = g.n; J.M = g.M; J.F1 = g.F1; J.F2 = g.F2; J.T = g.T; J.G = g.G;
+        J.p1 = g.p1; J.p2 = g.p2; J.tw1 = g.tw1; J.tw2 = g.tw2; J.twM_hi = g.twM_hi; J.twM_lo = g.twM_lo;
+        J.ch_hi = g.ch_hi; J.ch_lo = g.ch_lo; J.bspec = g.bspec;
+        return 0;
+    }
+
+    int make_bspec(FftJob& g, ms_stream_t st) {
+        float2* spec = (float2*)ms_dev_alloc(sizeof(float2) * (size_t)g.M);
+        FftJob* jd = (FftJob*)ms_dev_alloc(sizeof(FftJob));
+        if (!spec || !jd) MS_FAIL("out of device memory for Bluestein spectrum n=%d M=%d", g.n, g.M);
+        FftJob t = g; t.work = spec; t.bspec = nullptr;
+        if (ms_h2d(jd, &t, sizeof t, st)) return -1;
+        LaunchShape s;
+        if (g.F1 == 1) {
+            shape_for(rows_tile_elems(t), &s);
+            if (launch_rows<LD_BW, MODE_RAW, ST_WORK>(s.ept, 1, 1, s.nthr, rows_smem(t), st, jd)) return -1;
+        } else {
+            shape_for(cols_tile_elems(t), &s);
+            if (launch_cols<LD_BW, ST_WORK, 1>(s.ept, (t.F2 + t.T - 1) / t.T, 1, s.nthr, cols_smem(t), st, jd)) return -1;
+            shape_for(rows_tile_elems(t), &s);
+            if (launch_rows<LD_WORK, MODE_RAW, ST_WORK>(s.ept, (t.F1 + t.G - 1) / t.G, 1, s.nthr, rows_smem(t), st, jd)) return -1;
+        }
+#ifndef MS_HOST_EMUL
+        MS_CUDA_OK(cudaStreamSynchronize(st));
+#endif
+        ms_dev_free(jd);
+        g.bspec = spec;
+        bspec_[g.n] = spec;
+        return 0;
+    }
+
+    template <int LD, int ST, int TWID>
+    static int launch_cols(int ept, unsigned gx, unsigned gy, int nthr, size_t smem, ms_stream_t st, const FftJob* jd) {
+        return L<ColsK<LD, ST, TWID>>(gx, gy, nthr, smem, st, jd);
+    }
+    template <int LD, int MODE, int ST>
+    static int launch_rows(int ept, unsigned gx, unsigned gy, int nthr, size_t smem, ms_stream_t st, const FftJob* jd) {
+        return L<RowsK<LD, MODE, ST>>(gx, gy, nthr, smem, st, jd);
+    }
+
+    struct ClassShape { LaunchShape cols, rows; };
+    static ClassShape class_shape(const std::vector<FftJob>& jobs, size_t b, size_t e) {
+        ClassShape cs; int tc = 0, tr = 0; size_t sc = 0, sr = 0; unsigned gc = 0, gr = 0;
+        for (size_t i = b; i < e; ++i) {
+            const FftJob& J = jobs[i];
+            tr = std::max(tr, rows_tile_elems(J)); sr = std::max(sr, rows_smem(J));
+            gr = std::max(gr, (unsigned)((J.F1 + J.G - 1) / J.G));
+            if (J.F1 > 1) {
+                tc = std::max(tc, cols_tile_elems(J)); sc = std::max(sc, cols_smem(J));
+                gc = std::max(gc, (unsigned)((J.F2 + J.T - 1) / J.T));
+            }
+        }
+        shape_for(std::max(tc, 1), &cs.cols); cs.cols.smem = sc; cs.cols.gx = gc;
+        shape_for(std::max(tr, 1), &cs.rows); cs.rows.smem = sr; cs.rows.gx = gr;
+        return cs;
+    }
+
+    // what: 0 forward (pair -> Z), 1 inverse (spec(Z) -> pair), 2 c2c test path
+    int run(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, int what) {
+        size_t b = 0;
+        while (b < jobs.size()) {
+            const int cls = job_class(jobs[b]);
+            size_t e = b;
+            while (e < jobs.size() && job_class(jobs[e]) == cls && e - b < 32768) ++e;
+            const ClassShape cs = class_shape(jobs, b, e);
+            const unsigned gy = (unsigned)(e - b);
+            const FftJob* jd = jobs_dev + b;
+            const LaunchShape &C = cs.cols, &R = cs.rows;
+            int rc = 0;
+            if (what == 3) {
+                if (cls == 0) rc = launch_rows<LD_REALPAD, MODE_RAW, ST_WORK>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                else if (cls == 1) {
+                    rc = launch_cols<LD_REALPAD, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    if (!rc) rc = launch_rows<LD_WORK, MODE_RAW, ST_WORK>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                } else MS_FAIL("filter spectrum needs a direct length");
+            } else if (what == 4) {
+                if (cls == 0) rc = launch_rows<LD_OLS, MODE_CONV, ST_OLS>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                else if (cls == 1) {
+                    rc = launch_cols<LD_OLS, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    if (!rc) rc = launch_rows<LD_WORK, MODE_CONV, ST_WORK>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                    if (!rc) rc = launch_cols<LD_WORK, ST_OLS, 0>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                } else MS_FAIL("overlap-save needs a direct length");
+            } else if (what == 2) {
+                if (cls == 0) rc = launch_rows<LD_CPX, MODE_NAT, ST_CPX>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                else if (cls == 1) {
+                    rc = launch_cols<LD_CPX, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    if (!rc) rc = launch_rows<LD_WORK, MODE_NAT, ST_CPX>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                } else MS_FAIL("c2c test path supports direct lengths only");
+            } else if (cls == 0) {
+                rc = what == 0 ? launch_rows<LD_PAIR, MODE_NAT, ST_Z>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd)
+                               : launch_rows<LD_SPEC, MODE_NAT, ST_PAIR>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+            } else if (cls == 1) {
+                if (what == 0) {
+                    rc = launch_cols<LD_PAIR, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    if (!rc) rc = launch_rows<LD_WORK, MODE_NAT, ST_Z>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                } else {
+                    rc = launch_cols<LD_SPEC, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    if (!rc) rc = launch_rows<LD_WORK, MODE_NAT, ST_PAIR>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                }
+            } else if (cls == 2) {
+                rc = what == 0 ? launch_rows<LD_PAIR_CHIRP, MODE_CONV, ST_Z_CHIRP>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd)
+                               : launch_rows<LD_SPEC_CHIRP, MODE_CONV, ST_PAIR_CHIRP>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+            } else {
+                if (what == 0) rc = launch_cols<LD_PAIR_CHIRP, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                else rc = launch_cols<LD_SPEC_CHIRP, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                if (!rc) rc = launch_rows<LD_WORK, MODE_CONV, ST_WORK>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                if (!rc) {
+                    if (what == 0) rc = launch_cols<LD_WORK, ST_Z_CHIRP, 0>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    else rc = launch_cols<LD_WORK, ST_PAIR_CHIRP, 0>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                }
+            }
+            if (rc) return rc;
+            b = e;
+        }
+        return 0;
+    }
+};

@@ -1,0 +1,318 @@
+// ms_fft_kernels.cuh -- batched, variable-length spectral jobs on pairs of real signals.
+//
+// One "job" = two real signals a, b of the same length n packed as z = a + i b (b may be absent).
+// Everything the render path does in the frequency domain is linear with real coefficients, so the
+// pair never has to be separated: a real-symmetric mask acts on Z = A + iB directly and the
+// spectral stretch (a two-point gather, reference main_v2.py:117-128) acts on the upper half through
+// mirrored indices (see spec_value()).
+//
+// Transform lengths:  n with only factors 2,3,5 -> direct mixed-radix;  any other n -> Bluestein
+// (chirp-z) on a power-of-two length M >= 2n-1.  A transform of executed length M = F1*F2 runs
+//   F1 == 1 : one kernel, whole vector in shared memory                      (rows kernel, G = 1)
+//   F1  > 1 : columns kernel (T adjacent columns, length-F1 FFTs, twiddle W_M^{k1 n2})
+//             then rows kernel (G adjacent rows, length-F2 FFTs).
+// Rows kernel modes:  NAT  -> scatter to natural order k = k1 + F1 k2 through the tile transpose
+//                     CONV -> multiply by the Bluestein filter spectrum, swap, FFT again, twiddle,
+//                             leave in place; a final columns kernel (no twiddle) finishes the
+//                             inverse and applies the output chirp.
+//                     RAW  -> leave the [k1][k2] spectrum in place (used to build filter spectra).
+#pragma once
+#include "ms_fft_core.cuh"
+
+enum { LD_WORK = 0, LD_CPX, LD_PAIR, LD_PAIR_CHIRP, LD_SPEC, LD_SPEC_CHIRP, LD_BW, LD_OLS, LD_REALPAD };
+enum { ST_WORK = 0, ST_CPX, ST_Z, ST_Z_CHIRP, ST_PAIR, ST_PAIR_CHIRP, ST_OLS };
+enum { MODE_NAT = 0, MODE_CONV, MODE_RAW };
+enum { OP_NONE = 0, OP_GRAIN = 1, OP_TILT = 2, OP_ROT = 3 };
+
+// Raised-cosine / brick-wall edges in Hz, evaluated at f = k * df in float64 exactly the way
+// numpy's rfftfreq-based masks do (reference main_v2.py:47-58, 67-100).
+struct BandEdge {
+    double lo_f0, lo_f1;   // rising skirt  [f0, f1]; lo_mode 0: none, 1: brick (zero f < lo_f1), 2: cosine
+    double hi_f0, hi_f1;   // falling skirt [f0, f1]; hi_mode 0: none, 1: brick (zero f > hi_f0), 2: cosine
+    int lo_mode, hi_mode;
+    int zero;              // band contributes nothing (hi <= 0)
+    int _pad;
+};
+
+struct SpecOp {
+    int kind;              // OP_*
+    int n_bands;           // 0: no multiband stage; else 3
+    int lp_on;             // low-pass stage present
+    int stretch_on;        // spectral stretch present
+    double df;             // bin spacing in Hz: 1.0 / (n * (1.0 / sr))
+    double factor;         // stretch factor
+    BandEdge lp;           // low-pass described as a band with only a falling skirt
+    BandEdge mb[3];
+    double alpha;          // OP_TILT: shape = max(k,1)^alpha ;  OP_ROT: theta (0.9 * width)
+};
+
+struct FftJob {
+    int n, M, F1, F2;
+    int T, G;                    // column-tile width, row-group height
+    RadixPlan p1, p2;
+    const float2* tw1;           // w_F1^i
+    const float2* tw2;           // w_F2^i
+    const float2* twM_hi;        // W_M^(1024 i)
+    const float2* twM_lo;        // W_M^i, i < 1024
+    const float2* ch_hi;         // W_2n^(1024 i)   (Bluestein chirp), null for direct
+    const float2* ch_lo;         // W_2n^i, i < 1024
+    const float2* bspec;         // FFT_M(conj chirp, wrapped)/M in [k1][k2] layout
+    const float* in_a; const float* in_b;
+    float* out_a; float* out_b;
+    const float2* cin; float2* cout;   // LD_CPX / ST_CPX
+    float2* Z;                   // natural-order spectrum, n entries
+    float2* work;                // M entries
+    float out_scale;
+    int ols_n;                   // overlap-save: signal length (LD_OLS / ST_OLS)
+    long long p0_a, p0_b;        // overlap-save: first input sample position of block a / b (may be negative)
+    int ols_skip;                // overlap-save: taps - 1 (leading outputs of a block that are discarded)
+    int _pad;
+    SpecOp op[2];                // per packed signal (a, b)
+};
+
+// ---- twiddles ------------------------------------------------------------------------------------
+MS_DEV float2 tw2level(const float2* MS_RESTRICT hi, const float2* MS_RESTRICT lo, unsigned e) {
+    return c_mul(__ldg(&hi[e >> 10]), __ldg(&lo[e & 1023u]));
+}
+// chirp c[j] = exp(-i pi j^2 / n) = W_{2n}^(j^2 mod 2n)
+MS_DEV float2 chirp(const FftJob& J, int j) {
+    const long long jj = (long long)j * (long long)j;
+    const long long m2 = 2ll * J.n;
+    long long q = (long long)((double)jj / (double)m2);
+    long long r = jj - q * m2;
+    if (r < 0) r += m2;
+    if (r >= m2) r -= m2;
+    return tw2level(J.ch_hi, J.ch_lo, (unsigned)r);
+}
+
+// ---- spectral operators --------------------------------------------------------------------------
+MS_DEV float edge_weight(const BandEdge& b, double f) {
+    if (b.zero) return 0.f;
+    float w = 1.f;
+    if (b.lo_mode == 1) { if (f < b.lo_f1) return 0.f; }
+    else if (b.lo_mode == 2) {
+        if (f < b.lo_f0) return 0.f;
+        if (f <= b.lo_f1) {
+            double t = (f - b.lo_f0) / fmax(1e-12, b.lo_f1 - b.lo_f0);
+            w *= 0.5f * (1.f - cospif((float)t));
+        }
+    }
+    if (b.hi_mode == 1) { if (f > b.hi_f0) return 0.f; }
+    else if (b.hi_mode == 2) {
+        if (f > b.hi_f1) return 0.f;
+        if (f >= b.hi_f0) {
+            double t = (f - b.hi_f0) / fmax(1e-12, b.hi_f1 - b.hi_f0);
+            w *= 0.5f * (1.f + cospif((float)t));
+        }
+    }
+    return w;
+}
+MS_DEV float lp_weight(const SpecOp& op, int kk) { return op.lp_on ? edge_weight(op.lp, (double)kk * op.df) : 1.f; }
+MS_DEV float mb_weight(const SpecOp& op, int kk) {
+    if (op.n_bands == 0) return 1.f;
+    const double f = (double)kk * op.df;
+    float w = 0.f;
+    for (int b = 0; b < op.n_bands; ++b) w += edge_weight(op.mb[b], f);
+    return w;
+}
+// One packed signal's spectrum out of Z = A + iB:  A[i] = (Z[i] + conj Z[n-i]) / 2,
+// B[i] = (Z[i] - conj Z[n-i]) / (2i)   (0 <= i <= n/2).
+MS_DEV float2 split_bin(const float2* MS_RESTRICT Z, int n, int i, int sel, int paired) {
+    const float2 p = __ldg(&Z[i]);
+    if (!paired) return p;                    // b absent: Z is already A
+    const float2 q = __ldg(&Z[i == 0 ? 0 : n - i]);
+    if (sel == 0) return make_float2(0.5f * (p.x + q.x), 0.5f * (p.y - q.y));
+    return make_float2(0.5f * (p.y + q.y), 0.5f * (q.x - p.x));
+}
+// What irfft() would be handed for one signal at folded bin kk (0 <= kk <= n/2):
+// low-pass -> stretch (two-point gather at kk/factor, zero beyond the last bin) -> multiband weights,
+// or the tilt / rotation multipliers.
+MS_DEV float2 op_value(const SpecOp& op, const float2* MS_RESTRICT Z, int n, int kk, int sel, int paired) {
+    const int kmax = n >> 1;
+    if (op.kind == OP_NONE) return split_bin(Z, n, kk, sel, paired);
+    if (op.kind == OP_TILT) {
+        float s = (float)pow((double)(kk < 1 ? 1 : kk), op.alpha);
+        return c_scale(split_bin(Z, n, kk, sel, paired), s);
+    }
+    if (op.kind == OP_ROT) {   // exp(i theta sin(2 pi kk / kmax))
+        if (kk == 0) return split_bin(Z, n, kk, sel, paired);
+        float sn, cs, rs, rc;
+        sincospif(2.0f * (float)((double)kk / (double)(kmax < 1 ? 1 : kmax)), &sn, &cs);
+        sincosf((float)op.alpha * sn, &rs, &rc);
+        return c_mul(split_bin(Z, n, kk, sel, paired), make_float2(rc, rs));
+    }
+    float2 y;
+    if (!op.stretch_on) {
+        y = c_scale(split_bin(Z, n, kk, sel, paired), lp_weight(op, kk));
+    } else {
+        const double pos = (double)kk / fmax(1e-12, op.factor);
+        if (pos > (double)kmax) return c_zero();
+        int i0 = (int)pos;
+        float fr = (float)(pos - (double)i0);
+        if (i0 >= kmax) { i0 = kmax; fr = 0.f; }
+        y = c_scale(split_bin(Z, n, i0, sel, paired), lp_weight(op, i0));
+        if (fr != 0.f) {
+            float2 v1 = c_scale(split_bin(Z, n, i0 + 1, sel, paired), lp_weight(op, i0 + 1));
+            y = make_float2(y.x + (v1.x - y.x) * fr, y.y + (v1.y - y.y) * fr);
+        }
+    }
+    return c_scale(y, mb_weight(op, kk));
+}
+// Y[k] for natural k in [0, n): both packed signals at once, Hermitian-extended the way irfft does
+// (imaginary part of DC and, for even n, of the Nyquist bin is dropped).
+MS_DEV float2 spec_value(const FftJob& J, const float2* MS_RESTRICT Z, int k) {
+    const int n = J.n, kmax = n >> 1;
+    const int upper = k > kmax;
+    const int kk = upper ? n - k : k;
+    const int paired = J.in_b != nullptr;
+    float2 ya = op_value(J.op[0], Z, n, kk, 0, paired);
+    float2 yb = paired ? op_value(J.op[1], Z, n, kk, 1, paired) : c_zero();
+    if (kk == 0 || (!(n & 1) && kk == kmax)) { ya.y = 0.f; yb.y = 0.f; }
+    if (upper) { ya.y = -ya.y; yb.y = -yb.y; }
+    return make_float2(ya.x - yb.y, ya.y + yb.x);
+}
+
+// ---- load / store functors -----------------------------------------------------------------------
+template <int LD>
+MS_DEV float2 job_load(const FftJob& J, int idx) {
+    if (LD == LD_WORK) return J.work[idx];
+    if (LD == LD_CPX) return idx < J.n ? __ldg(&J.cin[idx]) : c_zero();
+    if (LD == LD_PAIR || LD == LD_PAIR_CHIRP) {
+        if (idx >= J.n) return c_zero();
+        float2 v = make_float2(__ldg(&J.in_a[idx]), J.in_b ? __ldg(&J.in_b[idx]) : 0.f);
+        if (LD == LD_PAIR_CHIRP) v = c_mul(v, chirp(J, idx));
+        return v;
+    }
+    if (LD == LD_SPEC) {            // inverse direct: feed swap(Y)
+        if (idx >= J.n) return c_zero();
+        return c_swap(spec_value(J, J.Z, idx));
+    }
+    if (LD == LD_SPEC_CHIRP) {      // inverse Bluestein: conj(Y) * chirp
+        if (idx >= J.n) return c_zero();
+        return c_mul(c_conj(spec_value(J, J.Z, idx)), chirp(J, idx));
+    }
+    if (LD == LD_OLS) {             // two blocks of one signal as re / im; zero outside [0, ols_n)
+        const long long pa = J.p0_a + idx, pb = J.p0_b + idx;
+        const float a = (pa >= 0 && pa < J.ols_n) ? __ldg(&J.in_a[pa]) : 0.f;
+        const float b = (J.in_b && pb >= 0 && pb < J.ols_n) ? __ldg(&J.in_b[pb]) : 0.f;
+        return make_float2(a, b);
+    }
+    if (LD == LD_REALPAD) {         // real taps, zero padded, pre-scaled by 1/M
+        return idx < J.n ? make_float2(__ldg(&J.in_a[idx]) * J.out_scale, 0.f) : c_zero();
+    }
+    if (LD == LD_BW) {              // wrapped conjugate chirp, scaled by 1/M
+        int d;
+        if (idx < J.n) d = idx; else if (idx > J.M - J.n) d = J.M - idx; else return c_zero();
+        return c_scale(c_conj(chirp(J, d)), 1.0f / (float)J.M);
+    }
+    return c_zero();
+}
+template <int ST>
+MS_DEV void job_store(const FftJob& J, int idx, float2 v) {
+    if (ST == ST_WORK) { J.work[idx] = v; return; }
+    if (ST == ST_OLS) {             // valid part of the circular convolution; un-swap the inverse half
+        if (idx < J.ols_skip) return;
+        const long long qa = J.p0_a + idx, qb = J.p0_b + idx;
+        if (qa < J.ols_n) J.out_a[qa] = v.y;
+        if (J.out_b && qb < J.ols_n) J.out_b[qb] = v.x;
+        return;
+    }
+    if (idx >= J.n) return;
+    if (ST == ST_CPX) { J.cout[idx] = c_scale(v, J.out_scale); return; }
+    if (ST == ST_Z) { J.Z[idx] = v; return; }
+    if (ST == ST_Z_CHIRP) { J.Z[idx] = c_mul(c_swap(v), chirp(J, idx)); return; }     // un-swap the inverse half of the convolution
+    if (ST == ST_PAIR) {            // y = swap(FFT(swap(Y))) / n
+        J.out_a[idx] = v.y * J.out_scale;
+        if (J.out_b) J.out_b[idx] = v.x * J.out_scale;
+        return;
+    }
+    if (ST == ST_PAIR_CHIRP) {      // r = chirp * conv ; y = conj(r) / n
+        float2 r = c_mul(c_swap(v), chirp(J, idx));
+        J.out_a[idx] = r.x * J.out_scale;
+        if (J.out_b) J.out_b[idx] = -r.y * J.out_scale;
+        return;
+    }
+}
+
+// ---- columns kernel --------------------------------------------------------------------------------
+template <int LD, int ST, int TWID>
+MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
+    const FftJob& J = jobs[c.by];
+    const int T = J.T, F1 = J.F1, F2 = J.F2;
+    const int col0 = c.bx * T;
+    if (col0 >= F2) return;
+    const int cnt = (F2 - col0) < T ? (F2 - col0) : T;
+    float2* s = (float2*)c.smem;
+    float2* s2 = s + (ms_pad((F1 - 1) * T + T - 1) + 2);
+    TileGeom g; g.cnt = cnt; g.vs = 1; g.es = T; g.colmajor = 1;
+    const int total = F1 * cnt;
+    for (int e = c.tid; e < total; e += c.nthr) {
+        const int i = e / cnt, v = e - i * cnt;
+        s[tile_addr(g, v, i)] = job_load<LD>(J, i * F2 + col0 + v);
+    }
+    c.sync();
+    s = tile_fft(s, s2, g, J.p1, J.tw1, c);
+    for (int e = c.tid; e < total; e += c.nthr) {
+        const int k1 = e / cnt, v = e - k1 * cnt;
+        float2 val = s[tile_addr(g, v, k1)];
+        if (TWID) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)k1 * (unsigned)(col0 + v)));
+        job_store<ST>(J, k1 * F2 + col0 + v, val);
+    }
+}
+
+// ---- rows kernel -----------------------------------------------------------------------------------
+template <int LD, int MODE, int ST>
+MS_DEV void fft_rows_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
+    const FftJob& J = jobs[c.by];
+    const int G = J.G, F1 = J.F1, F2 = J.F2;
+    const int row0 = c.bx * G;
+    if (row0 >= F1) return;
+    const int cnt = (F1 - row0) < G ? (F1 - row0) : G;
+    float2* s = (float2*)c.smem;
+    TileGeom g; g.cnt = cnt; g.vs = (ms_pad(F2) + 1) | 1; g.es = 1; g.colmajor = 0;
+    float2* s2 = s + (G * g.vs + 2);
+    const int total = F2 * cnt;
+    for (int e = c.tid; e < total; e += c.nthr) {
+        const int r = e / F2, i = e - r * F2;
+        s[tile_addr(g, r, i)] = job_load<LD>(J, (row0 + r) * F2 + i);
+    }
+    c.sync();
+    s = tile_fft(s, s2, g, J.p2, J.tw2, c);
+    if (MODE == MODE_NAT) {
+        for (int e = c.tid; e < total; e += c.nthr) {
+            const int k2 = e / cnt, r = e - k2 * cnt;
+            job_store<ST>(J, (row0 + r) + F1 * k2, s[tile_addr(g, r, k2)]);
+        }
+    } else if (MODE == MODE_RAW) {
+        for (int e = c.tid; e < total; e += c.nthr) {
+            const int r = e / F2, i = e - r * F2;
+            job_store<ST>(J, (row0 + r) * F2 + i, s[tile_addr(g, r, i)]);
+        }
+    } else {   // MODE_CONV
+        for (int e = c.tid; e < total; e += c.nthr) {
+            const int r = e / F2, i = e - r * F2;
+            const int a = tile_addr(g, r, i);
+            s[a] = c_swap(c_mul(s[a], __ldg(&J.bspec[(row0 + r) * F2 + i])));
+        }
+        c.sync();
+        float2* other = (s == (float2*)c.smem) ? s2 : (float2*)c.smem;
+        s = tile_fft(s, other, g, J.p2, J.tw2, c);
+        for (int e = c.tid; e < total; e += c.nthr) {
+            const int r = e / F2, i = e - r * F2;
+            float2 val = s[tile_addr(g, r, i)];
+            if (F1 > 1) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)(row0 + r) * (unsigned)i));
+            job_store<ST>(J, (row0 + r) * F2 + i, val);
+        }
+    }
+}
+
+// ---- table generators (float64 angles, rounded once) -------------------------------------------------
+// out[i] = exp(-2 pi i * ((i * mul) mod N) / N),  i < count
+MS_DEV void gen_table_body(float2* out, int count, long long mul, long long N, const Ctx& c, int grid_threads, int gtid) {
+    for (int i = gtid; i < count; i += grid_threads) {
+        long long e = ((long long)i * mul) % N;
+        double sn, cs;
+        sincospi(2.0 * (double)e / (double)N, &sn, &cs);
+        out[i] = make_float2((float)cs, (float)(-sn));
+    }
+}

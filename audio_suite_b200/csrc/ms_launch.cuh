@@ -1,0 +1,64 @@
+// ms_launch.cuh -- one launcher for both builds (see ms_rt.cuh).  A kernel is a struct K with
+//   static constexpr int MAXT;                    // __launch_bounds__
+//   static MS_DEV void run(args..., const Ctx&);   // the body
+#pragma once
+#include "ms_rt.cuh"
+#include <stddef.h>
+#include <stdio.h>
+#include <string>
+
+struct MsDim { unsigned x, y; };
+
+// thread-local last error (C-ABI: ms_last_error)
+std::string& ms_err_slot();
+#define MS_FAIL(...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); ms_err_slot() = _b; return -1; } while (0)
+
+#ifdef MS_HOST_EMUL
+#include <functional>
+#include <cstdlib>
+typedef void* ms_stream_t;
+namespace msemu {
+    void run(MsDim grid, int block, size_t smem, const std::function<void(const Ctx&)>& body);
+}
+template <class K, class... Args>
+int ms_launch(MsDim grid, int block, size_t smem, ms_stream_t, Args... args) {
+    msemu::run(grid, block, smem, [&](const Ctx& c) { K::run(args..., c); });
+    return 0;
+}
+static inline void* ms_dev_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
+static inline void ms_dev_free(void* p) { free(p); }
+static inline int ms_h2d(void* dst, const void* src, size_t bytes, ms_stream_t) { memcpy(dst, src, bytes); return 0; }
+static inline int ms_memset(void* dst, int v, size_t bytes, ms_stream_t) { memset(dst, v, bytes); return 0; }
+#else
+typedef cudaStream_t ms_stream_t;
+template <class K, class... Args>
+__global__ void __launch_bounds__(K::MAXT) ms_kernel(Args... args) {
+    extern __shared__ float4 ms_dyn_smem[];
+    Ctx c;
+    c.tid = threadIdx.x; c.nthr = blockDim.x; c.bx = blockIdx.x; c.by = blockIdx.y;
+    c.smem = (char*)ms_dyn_smem;
+    K::run(args..., c);
+}
+#define MS_CUDA_OK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) MS_FAIL("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); } while (0)
+template <class K, class... Args>
+int ms_launch(MsDim grid, int block, size_t smem, ms_stream_t st, Args... args) {
+    static size_t configured = 0;          // per instantiation
+    if (block > K::MAXT) MS_FAIL("launch: block %d exceeds kernel bound %d", block, K::MAXT);
+    if (smem > 48 * 1024 && smem > configured) {
+        MS_CUDA_OK(cudaFuncSetAttribute(ms_kernel<K, Args...>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    if (grid.x == 0 || grid.y == 0) return 0;
+    ms_kernel<K, Args...><<<dim3(grid.x, grid.y, 1), block, smem, st>>>(args...);
+    MS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+static inline void* ms_dev_alloc(size_t bytes) { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; return p; }
+static inline void ms_dev_free(void* p) { cudaFree(p); }
+static inline int ms_h2d(void* dst, const void* src, size_t bytes, ms_stream_t st) {
+    MS_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)); return 0;
+}
+static inline int ms_memset(void* dst, int v, size_t bytes, ms_stream_t st) {
+    MS_CUDA_OK(cudaMemsetAsync(dst, v, bytes, st)); return 0;
+}
+#endif

@@ -1,0 +1,319 @@
+// ms_synth.cuh -- transient synthesis: the five gen_basic modes of the reference
+// (main_v2.py:219-269) with numpy's exact random stream generated on the device.
+//
+// numpy's default_rng(seed).standard_normal(n) is PCG64 (128-bit LCG, XSL-RR output) feeding a
+// 256-layer ziggurat.  About 1-2 % of the normals consume more than one 64-bit word (wedge test: one
+// extra word; tail: two extra words per attempt), so "output j" is not "word j".  One CTA renders one
+// event: every thread jumps the LCG to its own run of C consecutive words, classifies them, and the
+// block resolves who-starts-in-which-state with a prefix scan over 6-state transition maps
+// (S0 = fresh word, W = wedge test pending, T1+-/T2+- = tail loop).  Accepted normals go to a
+// shared staging buffer in stream order; the mode's closed-form terms (sine with float64 phase,
+// exponentials, fades) are applied on the way out with coalesced stores.
+#pragma once
+#include "ms_rt.cuh"
+#include "ms_zig_tables.h"
+#include "../../include/microsound_b200.h"
+#ifdef MS_HOST_EMUL
+#define MS_POPC(x) __builtin_popcount(x)
+#else
+#define MS_POPC(x) __popc(x)
+#endif
+
+enum { SY_GAUSS = 0, SY_DUST = 1, SY_NOISE = 2, SY_SKEW = 3, SY_RES = 4, SY_PLAIN = 5 };
+
+#define SY_C 8            // words per thread per round
+#define SY_NTHR 256
+#define SY_W (SY_C * SY_NTHR)
+
+typedef ms_synth_evt SynthEvt;
+
+struct u128 { unsigned long long hi, lo; };
+
+MS_DEV unsigned long long ms_mulhi64(unsigned long long a, unsigned long long b) {
+#ifdef MS_HOST_EMUL
+    return (unsigned long long)(((unsigned __int128)a * b) >> 64);
+#else
+    return __umul64hi(a, b);
+#endif
+}
+MS_DEV u128 u128_mul(u128 a, u128 b) {
+    u128 r;
+    r.lo = a.lo * b.lo;
+    r.hi = ms_mulhi64(a.lo, b.lo) + a.lo * b.hi + a.hi * b.lo;
+    return r;
+}
+MS_DEV u128 u128_add(u128 a, u128 b) {
+    u128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+    return r;
+}
+#define PCG_MULT_HI 0x2360ED051FC65DA4ull
+#define PCG_MULT_LO 0x4385DF649FCCF645ull
+MS_DEV u128 pcg_step(u128 s, u128 inc) {
+    u128 m; m.hi = PCG_MULT_HI; m.lo = PCG_MULT_LO;
+    return u128_add(u128_mul(s, m), inc);
+}
+MS_DEV unsigned long long pcg_output(u128 s) {
+    const unsigned long long x = s.hi ^ s.lo;
+    const unsigned rot = (unsigned)(s.hi >> 58);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+// (mult, plus) such that state_{k+delta} = mult * state_k + plus
+MS_DEV void pcg_jump_consts(u128 inc, unsigned long long delta, u128* mult, u128* plus) {
+    u128 am, ap, cm, cp;
+    am.hi = 0; am.lo = 1; ap.hi = 0; ap.lo = 0;
+    cm.hi = PCG_MULT_HI; cm.lo = PCG_MULT_LO; cp = inc;
+    while (delta) {
+        if (delta & 1ull) { am = u128_mul(am, cm); ap = u128_add(u128_mul(ap, cm), cp); }
+        u128 one; one.hi = 0; one.lo = 1;
+        cp = u128_mul(u128_add(cm, one), cp);
+        cm = u128_mul(cm, cm);
+        delta >>= 1;
+    }
+    *mult = am; *plus = ap;
+}
+
+// ---- ziggurat state machine ------------------------------------------------------------------------
+enum { ZS_S0 = 0, ZS_W = 1, ZS_T1P = 2, ZS_T1N = 3, ZS_T2P = 4, ZS_T2N = 5 };
+#define ZIG_R 3.6541528853610087963519472518
+#define ZIG_INV_R 0.27366123732975827203338247596
+
+struct ZigTables { const unsigned long long* ki; const double* wi; const double* fi; };
+
+MS_DEV double word_to_double(unsigned long long w) { return (double)(w >> 11) * (1.0 / 9007199254740992.0); }
+
+// One step of the machine on word `cur` (with `prev` = the word before it).  Returns the next state;
+// *emit = 1 and *val = the normal when this word completes one.
+MS_DEV int zig_step(int s, unsigned long long prev, unsigned long long cur, const ZigTables& T, int* emit, double* val) {
+    *emit = 0;
+    if (s == ZS_S0) {
+        unsigned long long r = cur;
+        const int idx = (int)(r & 0xff);
+        r >>= 8;
+        const int sign = (int)(r & 1);
+        const unsigned long long rabs = (r >> 1) & 0x000fffffffffffffull;
+        if (rabs < T.ki[idx]) {
+            double x = (double)rabs * T.wi[idx];
+            *val = sign ? -x : x; *emit = 1;
+            return ZS_S0;
+        }
+        if (idx == 0) return ((rabs >> 8) & 1) ? ZS_T1N : ZS_T1P;
+        return ZS_W;
+    }
+    if (s == ZS_W) {
+        unsigned long long r = prev;
+        const int idx = (int)(r & 0xff);
+        r >>= 8;
+        const int sign = (int)(r & 1);
+        const unsigned long long rabs = (r >> 1) & 0x000fffffffffffffull;
+        double x = (double)rabs * T.wi[idx];
+        if (sign) x = -x;
+        const double u = word_to_double(cur);
+        if ((T.fi[idx - 1] - T.fi[idx]) * u + T.fi[idx] < exp(-0.5 * x * x)) { *val = x; *emit = 1; }
+        return ZS_S0;
+    }
+    if (s == ZS_T1P) return ZS_T2P;
+    if (s == ZS_T1N) return ZS_T2N;
+    // T2: prev word gave xx, this one gives yy
+    const double xx = -ZIG_INV_R * log1p(-word_to_double(prev));
+    const double yy = -log1p(-word_to_double(cur));
+    if (yy + yy > xx * xx) {
+        *val = (s == ZS_T2N) ? -(ZIG_R + xx) : (ZIG_R + xx);
+        *emit = 1;
+        return ZS_S0;
+    }
+    return s == ZS_T2N ? ZS_T1N : ZS_T1P;
+}
+
+// transition map of a run of words: per start state, 16 bits = next state (3) | emitted count (13)
+struct ZigMap { unsigned w[3]; };
+MS_DEV unsigned zm_get(const ZigMap& m, int s) { return (m.w[s >> 1] >> ((s & 1) * 16)) & 0xffffu; }
+MS_DEV void zm_set(ZigMap& m, int s, unsigned v) {
+    const int sh = (s & 1) * 16;
+    m.w[s >> 1] = (m.w[s >> 1] & ~(0xffffu << sh)) | (v << sh);
+}
+// f first, then g
+MS_DEV ZigMap zm_compose(const ZigMap& f, const ZigMap& g) {
+    ZigMap h; h.w[0] = h.w[1] = h.w[2] = 0;
+    for (int s = 0; s < 6; ++s) {
+        const unsigned a = zm_get(f, s), b = zm_get(g, a & 7u);
+        zm_set(h, s, (b & 7u) | (((a >> 3) + (b >> 3)) << 3));
+    }
+    return h;
+}
+
+MS_DEV float fade_gain(int j, int n, int fade, double inv_fade) {
+    float w = 1.f;
+    if (j < fade) w *= (float)((double)j * inv_fade);
+    const int t = j - (n - fade);
+    if (t >= 0) w *= (float)(1.0 - (double)t * inv_fade);
+    return w;
+}
+
+// shared-memory carve-up of the synthesis kernel
+struct SynthSmem {
+    unsigned long long ki[256];
+    double wi[256];
+    double fi[256];
+    unsigned long long words[SY_W + 1];     // [0] = word before the round, then i-major: 1 + i*NTHR + t
+    ZigMap scan[2][SY_NTHR];
+    float stage[SY_W + 8];
+    int carry_state, round_total, round_end_state, _pad;
+};
+MS_DEV unsigned long long sy_word(const SynthSmem* S, int p) {   // p in [-1, SY_W)
+    if (p < 0) return S->words[0];
+    const int t = p / SY_C, i = p - t * SY_C;
+    return S->words[1 + i * SY_NTHR + t];
+}
+
+// mode-specific sample from normal z at index j
+MS_DEV float synth_sample(const SynthEvt& E, int j, float z) {
+    const float fj = (float)j;
+    float x;
+    if (E.mode == SY_GAUSS) {
+        const float q = fj / (float)E.sigma;
+        x = expf(-0.5f * q * q) * (z * 0.12f + 1.0f);
+    } else if (E.mode == SY_RES) {
+        double cyc = (double)j * E.f_over_sr;
+        cyc -= floor(cyc);
+        const float tone = sinpif(2.0f * (float)cyc) * expf(-fj * E.ring_decay);
+        x = 0.9f * tone + 0.25f * z * expf(-fj * E.env_decay);
+    } else if (E.mode == SY_PLAIN) {
+        x = z * 0.1f;
+    } else {
+        return z;           // SY_NOISE / SY_SKEW: raw normals, shaped later
+    }
+    return x * fade_gain(j, E.n, E.fade, E.inv_fade);
+}
+
+// One CTA per event.  blockDim.x must be SY_NTHR.
+MS_DEV void synth_normal_body(const SynthEvt* MS_RESTRICT evts, float* MS_RESTRICT pool, const Ctx& c) {
+    const SynthEvt E = evts[c.bx];
+    if (E.mode == SY_DUST) return;
+    SynthSmem* S = (SynthSmem*)c.smem;
+    for (int i = c.tid; i < 256; i += c.nthr) {
+        S->ki[i] = MS_ZIG_KI[i];
+        union { unsigned long long u; double d; } cv;
+        cv.u = MS_ZIG_WI_BITS[i]; S->wi[i] = cv.d;
+        cv.u = MS_ZIG_FI_BITS[i]; S->fi[i] = cv.d;
+    }
+    if (c.tid == 0) S->carry_state = ZS_S0;
+    ZigTables T; T.ki = S->ki; T.wi = S->wi; T.fi = S->fi;
+    u128 inc; inc.hi = E.i_hi; inc.lo = E.i_lo;
+    u128 st; st.hi = E.s_hi; st.lo = E.s_lo;
+    u128 jm, jp;
+    pcg_jump_consts(inc, (unsigned long long)(c.tid * SY_C), &jm, &jp);
+    st = u128_add(u128_mul(st, jm), jp);
+    pcg_jump_consts(inc, (unsigned long long)(SY_W - SY_C), &jm, &jp);
+    float* out = pool + E.out;
+    int out_base = 0;
+    c.sync();
+    const int max_rounds = (int)((2ll * E.n) / SY_W) + 64;
+    for (int round = 0; round < max_rounds && out_base < E.n; ++round) {
+        // ---- generate this thread's words
+        if (c.tid == 0) S->words[0] = pcg_output(st);
+        for (int i = 0; i < SY_C; ++i) { st = pcg_step(st, inc); S->words[1 + i * SY_NTHR + c.tid] = pcg_output(st); }
+        st = u128_add(u128_mul(st, jm), jp);
+        c.sync();
+        // ---- transition map of this thread's run
+        const int p0 = c.tid * SY_C;
+        unsigned mstates = 0, mask = 0;        // main path (start S0): state before word i in bits 3i..3i+2
+        int s = ZS_S0, em; double val;
+        for (int i = 0; i < SY_C; ++i) {
+            mstates |= (unsigned)s << (3 * i);
+            s = zig_step(s, sy_word(S, p0 + i - 1), sy_word(S, p0 + i), T, &em, &val);
+            mask |= (unsigned)em << i;
+        }
+        const int main_end = s;
+        const int main_cnt = MS_POPC(mask);
+        ZigMap mine; mine.w[0] = mine.w[1] = mine.w[2] = 0;
+        zm_set(mine, ZS_S0, (unsigned)main_end | ((unsigned)main_cnt << 3));
+        for (int a = 1; a < 6; ++a) {
+            int t = a, i = 0, cnt = 0;
+            while (i < SY_C && t != (int)((mstates >> (3 * i)) & 7u)) {
+                t = zig_step(t, sy_word(S, p0 + i - 1), sy_word(S, p0 + i), T, &em, &val);
+                cnt += em; ++i;
+            }
+            if (i < SY_C) { cnt += MS_POPC(mask >> i); t = main_end; }
+            zm_set(mine, a, (unsigned)t | ((unsigned)cnt << 3));
+        }
+        // ---- inclusive scan of the maps (Hillis-Steele, double buffered)
+        int cur = 0;
+        S->scan[0][c.tid] = mine;
+        c.sync();
+        for (int d = 1; d < c.nthr; d <<= 1) {
+            ZigMap v = S->scan[cur][c.tid];
+            if (c.tid >= d) v = zm_compose(S->scan[cur][c.tid - d], v);
+            S->scan[cur ^ 1][c.tid] = v;
+            cur ^= 1;
+            c.sync();
+        }
+        const int carry = S->carry_state;
+        int my_state = carry, my_off = 0;
+        if (c.tid > 0) {
+            const unsigned e = zm_get(S->scan[cur][c.tid - 1], carry);
+            my_state = (int)(e & 7u); my_off = (int)(e >> 3);
+        }
+        if (c.tid == c.nthr - 1) {
+            const unsigned e = zm_get(S->scan[cur][c.tid], carry);
+            S->round_end_state = (int)(e & 7u); S->round_total = (int)(e >> 3);
+        }
+        // ---- emit in stream order
+        s = my_state;
+        for (int i = 0; i < SY_C; ++i) {
+            s = zig_step(s, sy_word(S, p0 + i - 1), sy_word(S, p0 + i), T, &em, &val);
+            if (em) S->stage[my_off++] = (float)val;
+        }
+        c.sync();
+        const int total = S->round_total;
+        const int take = (E.n - out_base) < total ? (E.n - out_base) : total;
+        for (int i = c.tid; i < take; i += c.nthr) out[out_base + i] = synth_sample(E, out_base + i, S->stage[i]);
+        out_base += total;
+        c.sync();
+        if (c.tid == 0) S->carry_state = S->round_end_state;
+        c.sync();
+    }
+}
+
+// Finalize for the tilted-noise modes (main_v2.py:246-255): one thread per sample.
+MS_DEV void synth_tilt_finish_body(const SynthEvt* MS_RESTRICT evts, float* MS_RESTRICT pool, const Ctx& c) {
+    const SynthEvt E = evts[c.by];
+    if (E.mode != SY_NOISE && E.mode != SY_SKEW) return;
+    const float* t = pool + E.aux;
+    float* out = pool + E.out;
+    for (int j = c.bx * c.nthr + c.tid; j < E.n; j += c.nthr * 64) {   // gridDim.x == 64
+        float v = t[j];
+        if (E.mode == SY_SKEW) {
+            const float a = v > 0.f ? v : 0.f;
+            const float pv = j > 0 ? t[j - 1] : v;
+            const float b = pv > 0.f ? pv : 0.f;
+            v = a - b;
+        }
+        out[j] = v * expf(-(float)j * E.env_decay) * fade_gain(j, E.n, E.fade, E.inv_fade);
+    }
+}
+
+// Dust impulses (main_v2.py:239-245): sparse impulses convolved ("same") with exp(-linspace(0,6,K)).
+MS_DEV void synth_dust_body(const SynthEvt* MS_RESTRICT evts, const int* MS_RESTRICT dpos, const float* MS_RESTRICT dval,
+                            float* MS_RESTRICT pool, const Ctx& c) {
+    const SynthEvt E = evts[c.by];
+    if (E.mode != SY_DUST) return;
+    const int* pos = dpos + E.dust_begin;
+    const float* val = dval + E.dust_begin;
+    float* out = pool + E.out;
+    const int K = E.ker_len, ctr = (K - 1) / 2;
+    const float rate = 6.0f / (float)(K - 1);
+    for (int j = c.bx * c.nthr + c.tid; j < E.n; j += c.nthr * 64) {
+        const int hi = j + ctr;            // impulses p with hi-K < p <= hi contribute ker[hi-p]
+        int lo_i = 0, hi_i = E.dust_count; // first index with pos > hi - K
+        while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (__ldg(&pos[mid]) > hi - K) hi_i = mid; else lo_i = mid + 1; }
+        float acc = 0.f;
+        for (int q = lo_i; q < E.dust_count; ++q) {
+            const int p = __ldg(&pos[q]);
+            if (p > hi) break;
+            acc += __ldg(&val[q]) * expf(-rate * (float)(hi - p));
+        }
+        out[j] = acc * fade_gain(j, E.n, E.fade, E.inv_fade);
+    }
+}

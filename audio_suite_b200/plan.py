@@ -1,0 +1,368 @@
+"""Host planner: turns a Microsound parameter dict into the flat, integer-exact plan the kernels consume.
+
+Everything `render()` decides with Python scalars stays on the host and is decided the same way
+the reference decides it: Python `round()` (half-to-even) for every index,
+numpy's own PCG64 Generators for every scalar draw (event times, amplitudes, grain offsets,
+reflection taps, dust impulses), float64 for every threshold that selects a branch.  The bulk
+arithmetic (normal noise, FFTs, overlap-add, convolution) is what goes to the GPU.
+
+Reference lines are cited as M:<line> = microsound_0.2.1/main_v2.py.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _abi
+from .configs import BASIC_MODES
+
+DESIGN_SR_CAP = 30_000_000          # M:597, M:646
+IR_TAP_CAP = 8192                   # M:443
+
+MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN = range(6)
+_MODE_ID = {m: i for i, m in enumerate(BASIC_MODES)}
+
+_NEXT_ROW_FLAGS = ("nl_warp_on", "cep_warp_on", "partial_lock_on", "res_bank_on", "wg_on",
+                   "event_feedback_on", "spectral_imprint_on")
+_NEXT_ROW_MODES = ("Crackle / corona", "Stick–slip friction", "Micro-chaos", "Wavelet atoms",
+                   "IR fragment", "Image scanline")
+
+
+# --------------------------------------------------------------------------- breakpoint lanes (M:452-482)
+def parse_breakpoints(text):
+    pts = []
+    for part in (text or "").strip().split(","):
+        part = part.strip()
+        if not part or ":" not in part:
+            continue
+        try:
+            t, v = part.split(":")
+            pts.append((float(t.strip()), float(v.strip())))
+        except Exception:
+            continue
+    pts.sort(key=lambda p: p[0])
+    return pts
+
+
+def eval_breakpoints(pts, t, default):
+    if not pts:
+        return default
+    if t <= pts[0][0]:
+        return pts[0][1]
+    if t >= pts[-1][0]:
+        return pts[-1][1]
+    for (t0, v0), (t1, v1) in zip(pts[:-1], pts[1:]):
+        if t0 <= t <= t1:
+            a = (t - t0) / max(1e-12, t1 - t0)
+            return (1 - a) * v0 + a * v1
+    return default
+
+
+# --------------------------------------------------------------------------- event field (M:507-558)
+def generate_event_times(process, dur_s, rate, seed, cluster_size=6, cluster_spread_ms=25.0,
+                         hawkes_gain=0.6, hawkes_decay_s=0.25):
+    rng = np.random.default_rng(int(seed) + 9999)
+    if process == "Single" or rate <= 0:
+        return [0.0]
+    times = []
+    if process == "Poisson":
+        t = 0.0
+        while t < dur_s:
+            t += rng.exponential(1.0 / rate)
+            if t < dur_s:
+                times.append(t)
+    elif process == "Clustered":
+        parents, t = [], 0.0
+        parent_rate = max(0.1, rate / max(1, cluster_size))
+        while t < dur_s:
+            t += rng.exponential(1.0 / parent_rate)
+            if t < dur_s:
+                parents.append(t)
+        spread = cluster_spread_ms / 1000.0
+        for p in parents:
+            k = int(max(1, round(rng.uniform(0.6, 1.4) * cluster_size)))
+            for _ in range(k):
+                tt = p + rng.normal(0.0, spread)
+                if 0.0 <= tt < dur_s:
+                    times.append(tt)
+        times.sort()
+    elif process == "Hawkes":
+        dt, activity = 0.002, 0.0
+        decay = math.exp(-dt / max(1e-6, hawkes_decay_s))
+        for i in range(int(math.ceil(dur_s / dt))):
+            activity *= decay
+            p = min(0.95, (rate + hawkes_gain * activity * rate) * dt)
+            if rng.random() < p:
+                times.append(i * dt + rng.uniform(0, dt))
+                activity += 1.0
+    return times
+
+
+# --------------------------------------------------------------------------- spectral masks
+def _edge():
+    return _abi.BandEdge(0.0, 0.0, 0.0, 0.0, 0, 0, 0, 0)
+
+
+def lowpass_edge(sr, cutoff, roll):
+    """Mask of lowpass_fft (M:43-58) as a falling skirt."""
+    nyq = 0.5 * sr
+    fc = float(np.clip(cutoff, 1.0, nyq))
+    width = float(max(0.0, roll))
+    e = _edge()
+    if width <= 0:
+        e.hi_mode, e.hi_f0, e.hi_f1 = 1, fc, fc
+    else:
+        e.hi_mode, e.hi_f0, e.hi_f1 = 2, fc, min(nyq, fc + width)
+    return e
+
+
+def bandpass_edge(sr, lo, hi, roll):
+    """Mask of bandpass_fft (M:64-100)."""
+    lo = max(0.0, float(lo))
+    hi = max(lo, float(hi))
+    nyq = 0.5 * sr
+    hi = min(hi, nyq)
+    e = _edge()
+    if hi <= 0:
+        e.zero = 1
+        return e
+    width = float(max(0.0, roll))
+    if lo > 0:
+        if width <= 0:
+            e.lo_mode, e.lo_f0, e.lo_f1 = 1, lo, lo
+        else:
+            e.lo_mode, e.lo_f0, e.lo_f1 = 2, max(0.0, lo - width), lo
+    if hi < nyq:
+        if width <= 0:
+            e.hi_mode, e.hi_f0, e.hi_f1 = 1, hi, hi
+        else:
+            e.hi_mode, e.hi_f0, e.hi_f1 = 2, hi, min(nyq, hi + width)
+    return e
+
+
+def bin_spacing(n, sr):
+    """np.fft.rfftfreq(n, d=1/sr)[k] == k * bin_spacing (numpy computes val = 1.0/(n*d))."""
+    return 1.0 / (n * (1.0 / sr))
+
+
+def grain_spec_op(params, gen_sr, n, cutoff_gen, stretch):
+    """Spectral operator of one event: lowpass_fft -> fft_partial_stretch -> unfold_multiband
+    (M:690-727), or None when every stage is an identity."""
+    op = _abi.SpecOp()
+    op.kind = _abi.OP_GRAIN
+    op.df = bin_spacing(n, gen_sr)
+    op.factor = 1.0
+    if params["bandlimit_on"] and n >= 8:
+        op.lp_on = 1
+        op.lp = lowpass_edge(gen_sr, cutoff_gen, float(params["bandlimit_roll_hz"]))
+    stretch = float(stretch)
+    if n >= 16 and not abs(stretch - 1.0) < 1e-9:
+        op.stretch_on = 1
+        op.factor = stretch
+    if params["unfold_mode"] != "Classic reinterpret" and n >= 8:
+        b1, b2, b3 = float(params["mb_b1"]), float(params["mb_b2"]), float(params["mb_b3"])
+        us = [float(params["mb_u1"]), float(params["mb_u2"]), float(params["mb_u3"])]
+        roll = float(params["mb_roll"])
+        op.n_bands = 3
+        for i, ((lo, hi), u) in enumerate(zip([(0.0, b1), (b1, b2), (b2, b3)], us)):
+            op.mb[i] = bandpass_edge(gen_sr, lo * u, hi * u, roll)
+    if not (op.lp_on or op.stretch_on or op.n_bands):
+        return None
+    return op
+
+
+def tilt_spec_op(n, gen_sr, tilt_db_per_oct):
+    """Spectral shaping of tilted_noise (M:227-232): (f/f[1])**alpha with f[0] := f[1]."""
+    op = _abi.SpecOp()
+    op.kind = _abi.OP_TILT
+    op.df = bin_spacing(n, gen_sr)
+    op.alpha = math.log(10.0 ** (tilt_db_per_oct / 20.0), 2.0)
+    return op
+
+
+# --------------------------------------------------------------------------- plan records
+@dataclass
+class EventPlan:
+    index: int
+    t0: float
+    amp: float
+    ufac: float
+    gen_sr: int
+    n: int
+    seed: int
+    mode: int
+    cutoff_gen: float
+    stretch: float
+    start: int
+    offset: int = 0
+    length: int = 0
+    placed: bool = False
+    spec: Optional[object] = None           # _abi.SpecOp or None
+    tilt: Optional[object] = None           # _abi.SpecOp for the tilted-noise modes
+    dust_pos: Optional[np.ndarray] = None   # sorted unique impulse positions (int32)
+    dust_val: Optional[np.ndarray] = None   # float32 values (last write wins, M:243)
+    # mode constants (float64)
+    f_over_sr: float = 0.0
+    ring_decay: float = 0.0                 # 1 / (tau * gen_sr)
+    env_decay: float = 0.0                  # 1 / (T * gen_sr) for the mode's exponential envelope
+    sigma: int = 1
+    fade: int = 8
+    ker_len: int = 8
+
+
+@dataclass
+class RenderPlan:
+    base_sr: int
+    out_n: int
+    design_sr_base: int
+    events: List[EventPlan] = field(default_factory=list)
+    adsr: tuple = (0, 0, 0, 1.0, 1.0)       # A, D, R samples, sustain, curve
+    er_offs: Optional[np.ndarray] = None    # int32 tap delays (0 < off < out_n)
+    er_gains: Optional[np.ndarray] = None   # float64
+    ir: Optional[np.ndarray] = None         # float64 mono taps (<= 8192) or None
+    stereo_on: bool = False
+    stereo_dl: int = 0
+    stereo_dr: int = 0
+    stereo_theta: float = 0.0
+    drive: float = 1.0
+    peak: float = 0.98
+    progress_msgs: list = field(default_factory=list)
+
+
+def design_rate(base_sr, unfold):
+    return int(np.clip(int(round(base_sr * unfold)), base_sr, DESIGN_SR_CAP))
+
+
+def grain_length(gen_sr, micro_ms):
+    return int(max(16, round(gen_sr * micro_ms / 1000.0)))      # M:221
+
+
+def check_supported(params):
+    for flag in _NEXT_ROW_FLAGS:
+        if params[flag]:
+            raise NotImplementedError(f"microsound_b200: '{flag}' is not on the accelerated path yet (SURVEY 8f)")
+    if params["gen_mode"] in _NEXT_ROW_MODES:
+        raise NotImplementedError(f"microsound_b200: generator '{params['gen_mode']}' is not on the accelerated path yet (SURVEY 8f)")
+
+
+def plan_render(params) -> RenderPlan:
+    """Scalar half of render() (M:589-646, 742-753, 760-781)."""
+    check_supported(params)
+    base_sr = int(params["base_sr"])
+    out_dur = float(params["out_dur_s"])
+    out_n = int(max(1, round(out_dur * base_sr)))
+    base_unfold = max(1.0, float(params["time_unfold"]))
+    rp = RenderPlan(base_sr=base_sr, out_n=out_n, design_sr_base=design_rate(base_sr, base_unfold))
+
+    lanes = [parse_breakpoints(params[k]) for k in ("bp_density", "bp_unfold", "bp_cutoff", "bp_stretch")]
+    rate = float(params["grains_per_sec"])
+    times = generate_event_times(params["event_process"], out_dur, rate, int(params["seed"]),
+                                 int(params["cluster_size"]), float(params["cluster_spread_ms"]),
+                                 float(params["hawkes_gain"]), float(params["hawkes_decay_s"]))
+    times = times[:int(params["max_grains"])]
+    rng = np.random.default_rng(int(params["seed"]) + 123456)
+    seed = int(params["seed"])
+    micro_ms = float(params["micro_ms"])
+    micro_s = micro_ms / 1000.0
+    spread = float(params["grain_amp_rand"])
+    gmode = params["gen_mode"]
+    if gmode in _MODE_ID:
+        mode = _MODE_ID[gmode]
+        dust_density, tilt = float(params["dust_density"]), float(params["noise_tilt"])
+        ring_hz, ring_decay_ms = float(params["ring_hz"]), float(params["ring_decay_ms"])
+    else:       # unknown generator string: M:686
+        mode, dust_density, tilt, ring_hz, ring_decay_ms = MODE_NOISE, 0.01, -3.0, 4000.0, 12.0
+    offset_on = bool(params["grain_offset_on"])
+    max_off = int(round((float(params["grain_offset_max_ms"]) / 1000.0) * base_sr)) if offset_on else 0
+    bl_default = float(params["bandlimit_out_hz"])
+    st_default = float(params["partial_stretch"])
+
+    for i, t0 in enumerate(times):
+        dens = eval_breakpoints(lanes[0], t0, rate)
+        ufac = eval_breakpoints(lanes[1], t0, base_unfold)
+        cutoff_out = eval_breakpoints(lanes[2], t0, bl_default)
+        stretch = eval_breakpoints(lanes[3], t0, st_default)
+        amp = 1.0
+        if rate > 0:
+            amp *= np.clip(dens / max(1e-6, rate), 0.15, 4.0)
+        amp *= rng.uniform(1.0 - spread, 1.0 + spread)
+        ufac = max(1.0, float(ufac))
+        sr_evt = design_rate(base_sr, ufac)
+        n = grain_length(sr_evt, micro_ms)
+        ev = EventPlan(index=i, t0=t0, amp=float(amp), ufac=ufac, gen_sr=sr_evt, n=n, seed=seed + i, mode=mode,
+                       cutoff_gen=cutoff_out * ufac, stretch=float(stretch), start=int(round(t0 * base_sr)))
+        if ev.start < out_n:
+            if offset_on and max_off > 0:
+                ev.offset = int(rng.integers(0, max(1, min(max_off, n))))
+            ev.length = max(0, min(out_n - ev.start, n - ev.offset))
+            ev.placed = ev.length > 0
+        ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, ev.stretch)
+        ev.fade = max(8, int(0.01 * n))
+        if mode == MODE_GAUSS:
+            ev.sigma = max(1, int(0.0025 * n))
+        elif mode == MODE_DUST:
+            _plan_dust(ev, dust_density)
+        elif mode in (MODE_NOISE, MODE_SKEW):
+            ev.tilt = tilt_spec_op(n, sr_evt, tilt)
+            T = max(1e-6, micro_s * (0.25 if mode == MODE_NOISE else 0.2))
+            ev.env_decay = 1.0 / (T * sr_evt)
+        elif mode == MODE_RES:
+            ev.f_over_sr = max(10.0, ring_hz) / sr_evt
+            ev.ring_decay = 1.0 / (max(1e-6, ring_decay_ms / 1000.0) * sr_evt)
+            ev.env_decay = 1.0 / (max(1e-6, micro_s * 0.15) * sr_evt)
+        rp.events.append(ev)
+
+    a = max(0, int(round(base_sr * float(params["env_a"]) / 1000.0)))
+    d = max(0, int(round(base_sr * float(params["env_d"]) / 1000.0)))
+    r = max(0, int(round(base_sr * float(params["env_r"]) / 1000.0)))
+    rp.adsr = (a, d, r, float(np.clip(float(params["env_s"]), 0, 1)), float(max(1e-6, float(params["env_curve"]))))
+
+    if params["er_cloud_on"]:
+        offs, gains = reflection_taps(base_sr, int(params["er_taps"]), float(params["er_max_ms"]), seed)
+        keep = (offs > 0) & (offs < out_n)
+        rp.er_offs, rp.er_gains = offs[keep].astype(np.int32), gains[keep]
+    ir = params.get("_ir_audio")
+    if params["space_ir_on"] and ir is not None:
+        h = np.asarray(ir)[:int(params["space_ir_max_samps"])]
+        if h.size >= 8:                       # M:439 (size counts both channels of a 2-D IR)
+            h = h.astype(np.float64)
+            if h.ndim > 1:
+                h = h.mean(axis=1)
+            rp.ir = h[:min(h.size, IR_TAP_CAP)]
+    if params["stereo_on"] and out_n >= 64:   # M:426: shorter outputs are duplicated
+        w = float(np.clip(float(params["stereo_width"]), 0.0, 1.0))
+        rp.stereo_on = True
+        rp.stereo_dl = int(round((1 + 7 * w) * 0.0005 * base_sr))
+        rp.stereo_dr = int(round((1 + 9 * w) * 0.0007 * base_sr))
+        rp.stereo_theta = w * 0.9
+    rp.drive = float(params["sat_drive"])
+    rp.peak = float(params["peak"])
+    return rp
+
+
+def reflection_taps(sr, taps, max_ms, seed):
+    """Delays in samples and gains of early_reflection_cloud (M:410-417)."""
+    rng = np.random.default_rng(int(seed) + 202)
+    delays = rng.uniform(0.3, max_ms, size=int(max(1, taps))) / 1000.0
+    gains = rng.uniform(-1.0, 1.0, size=delays.size)
+    gains *= np.exp(-delays * 42.0)
+    offs = np.array([int(round(d * sr)) for d in delays.tolist()], dtype=np.int64)
+    return offs, gains
+
+
+def _plan_dust(ev, density):
+    """Dust impulses (M:240-244): the index/value draws happen on the host so the stream is numpy's."""
+    rng = np.random.default_rng(int(ev.seed))
+    n = ev.n
+    k = int(max(1, round(density * n)))
+    where = rng.integers(0, n, size=k)
+    vals = rng.uniform(-1, 1, size=k)
+    dense = np.zeros(n, dtype=np.float64)
+    dense[where] = vals                                  # duplicates: last write wins
+    pos = np.unique(where)
+    ev.dust_pos = pos.astype(np.int32)
+    ev.dust_val = dense[pos].astype(np.float32)
+    ev.ker_len = max(8, int(0.01 * n))

@@ -1,0 +1,162 @@
+/* microsound_b200.h -- C ABI of the B200-native Microsound render kernels.
+ *
+ * The reference (maetyu-d/audio-suite, microsound_0.2.1/main_v2.py) is pure Python/numpy and has no
+ * FFI of its own; its boundary for this path is the Python function
+ *     render(params: dict, progress=None) -> (float64[out_n, 2], meta)        main_v2.py:588-792
+ * which audio_suite_b200.render() reproduces.  This header is the layer *below* that function:
+ * what the Python host binds with ctypes (audio_suite_b200/_abi.py), one entry point per stage of
+ * render(), each citing the reference lines it replaces.
+ *
+ * Conventions: every function returns 0 on success and a negative value on error (message from
+ * ms_last_error(), thread-local).  No function throws.  All data pointers are DEVICE pointers owned
+ * by the caller (torch tensors: tensor.data_ptr()) unless the name says host.  `stream` is a
+ * cudaStream_t passed as void*.  Offsets are in elements of the pointed-to type.  The library keeps
+ * only internal plan caches (twiddle / chirp tables); it never returns memory it allocated.
+ */
+#ifndef MICROSOUND_B200_H
+#define MICROSOUND_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_ABI_VERSION 1
+
+int ms_version(void);
+const char* ms_last_error(void);
+/* 1 when the library was built from the CUDA sources for sm_100a (always, for the shipped .so). */
+int ms_is_cuda_build(void);
+
+/* ---- spectral stage: lowpass_fft (main_v2.py:39-59), fft_partial_stretch (:117-128),
+ *      unfold_multiband / bandpass_fft (:492-500, :61-101), tilted_noise shaping (:224-233),
+ *      spectral_diffusion_stereo's rotation (:432-435; odd lengths only, even lengths use ms_stereo_post).
+ * One job = two real signals of equal length n packed into one complex transform. */
+enum { MS_OP_NONE = 0, MS_OP_GRAIN = 1, MS_OP_TILT = 2, MS_OP_ROT = 3 };
+
+typedef struct {
+    double lo_f0, lo_f1;     /* rising skirt, Hz   */
+    double hi_f0, hi_f1;     /* falling skirt, Hz  */
+    int32_t lo_mode, hi_mode;/* 0 none, 1 brick wall, 2 raised cosine */
+    int32_t zero;            /* band contributes nothing */
+    int32_t _pad;
+} ms_band_edge;
+
+typedef struct {
+    int32_t kind;            /* MS_OP_* */
+    int32_t n_bands;         /* 0 or 3 (multiband unfold) */
+    int32_t lp_on;           /* low-pass present */
+    int32_t stretch_on;      /* spectral stretch present */
+    double df;               /* bin spacing, Hz: 1.0 / (n * (1.0 / sr)) */
+    double factor;           /* stretch factor */
+    double alpha;            /* MS_OP_TILT exponent, MS_OP_ROT angle */
+    ms_band_edge lp;
+    ms_band_edge mb[3];
+} ms_spec_op;
+
+typedef struct {
+    int32_t n;               /* signal length (any n >= 1) */
+    int32_t _pad;
+    int64_t in_a, in_b;      /* offsets into src; in_b < 0: no second signal */
+    int64_t out_a, out_b;    /* offsets into dst; out_b < 0: discard second signal */
+    ms_spec_op op[2];        /* operator for signal a and for signal b */
+} ms_spec_job;
+
+/* One-shot: plan + run + release. */
+size_t ms_spectral_workspace_bytes(const ms_spec_job* host_jobs, int njobs);
+int ms_spectral_apply(const ms_spec_job* host_jobs, int njobs, const float* src, float* dst,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* Planned: job descriptors are uploaded into `workspace` once; ms_spectral_run() only launches kernels
+ * (CUDA-graph capturable).  src/dst/workspace must stay valid for the life of the handle. */
+int ms_spectral_create(const ms_spec_job* host_jobs, int njobs, const float* src, float* dst,
+                       void* workspace, size_t workspace_bytes, void* stream, void** handle);
+int ms_spectral_run(void* handle, void* stream);
+void ms_spectral_destroy(void* handle);
+/* test entry: Z[k] = sum_j (a[j] + i b[j]) exp(-2 pi i jk/n), interleaved re/im, natural order */
+int ms_fft_pair_forward(const float* a, const float* b, int n, float* z_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+size_t ms_fft_pair_workspace_bytes(int n);
+
+/* ---- transient synthesis: gen_basic (main_v2.py:219-269).  One record per event; the array lives in
+ *      DEVICE memory.  The PCG64 state is numpy's `PCG64(seed).state` right after seeding. */
+enum { MS_SY_GAUSS = 0, MS_SY_DUST = 1, MS_SY_NOISE = 2, MS_SY_SKEW = 3, MS_SY_RES = 4, MS_SY_PLAIN = 5 };
+typedef struct {
+    uint64_t s_hi, s_lo, i_hi, i_lo;
+    int32_t n, mode;
+    int32_t fade, sigma;      /* max(8,int(.01n)) ; max(1,int(.0025n)) */
+    int64_t out;              /* offset into the float pool where this event's signal is written */
+    double f_over_sr;         /* MS_SY_RES: max(10, ring_hz) / gen_sr */
+    double inv_fade;          /* 1 / fade */
+    float ring_decay;         /* MS_SY_RES: 1 / (tau * gen_sr) */
+    float env_decay;          /* 1 / (T * gen_sr) of the mode's exponential envelope */
+    int64_t dust_begin;       /* MS_SY_DUST: range in the impulse arrays */
+    int32_t dust_count, ker_len;
+    int64_t aux;              /* MS_SY_NOISE / MS_SY_SKEW: pool offset of the tilted noise */
+} ms_synth_evt;
+/* normals + closed-form modes (GAUSS, RES, PLAIN) and raw normals for NOISE/SKEW (written at `out`) */
+int ms_synth_normal(const ms_synth_evt* dev_evts, int n_evts, float* pool, void* stream);
+int ms_synth_dust(const ms_synth_evt* dev_evts, int n_evts, const int32_t* dust_pos, const float* dust_val,
+                  float* pool, void* stream);
+/* NOISE / SKEW: envelope, rectified difference and fades applied to the tilted noise at `aux` */
+int ms_synth_tilt_finish(const ms_synth_evt* dev_evts, int n_evts, float* pool, void* stream);
+
+/* ---- overlap-add placement + ADSR (main_v2.py:742-764, 172-195) ---- */
+typedef struct {
+    int64_t out;              /* offset of the render's mono buffer */
+    int32_t out_n;
+    int32_t ev_begin, ev_end; /* placed events, ascending */
+    int32_t max_len;
+    int32_t A, D_end, sus_end;
+    int32_t has_release;
+    double inv_A, inv_D, inv_R;
+    float S, curve;
+} ms_ola_render;
+typedef struct {
+    int64_t grain;            /* pool offset of grain[offset] */
+    int32_t start, len;
+    float amp;
+    int32_t _pad;
+} ms_ola_evt;
+int ms_overlap_add(const ms_ola_render* dev_renders, int n_renders, int max_out_n, const ms_ola_evt* dev_evts,
+                   const float* pool, float* mono, void* stream);
+
+/* ---- early-reflection cloud + short IR as one FIR (main_v2.py:409-421, 438-445), applied by
+ *      FFT overlap-save ---- */
+typedef struct {
+    int64_t ir;               /* offset of the IR taps in irpool */
+    int32_t ir_len;
+    int32_t h_len;            /* ir_len + max tap delay */
+    int64_t h;                /* offset of the combined taps in hpool */
+    int32_t tap_begin, tap_end;
+    int64_t x, y;             /* offsets of the render's mono input / output */
+    int32_t out_n, _pad;
+} ms_fir_render;
+int ms_fir_build(const ms_fir_render* dev_renders, int n_renders, int max_h_len, const int32_t* tap_off,
+                 const float* tap_gain, const float* irpool, float* hpool, void* stream);
+size_t ms_fir_workspace_bytes(const ms_fir_render* host_renders, int n_renders);
+int ms_fir_create(const ms_fir_render* host_renders, int n_renders, const float* hpool, const float* mono_in,
+                  float* mono_out, void* workspace, size_t workspace_bytes, void* stream, void** handle);
+int ms_fir_run(void* handle, void* stream);
+void ms_fir_destroy(void* handle);
+
+/* ---- stereo diffusion + soft clip + normalise (main_v2.py:423-436, 31-34, 26-29) ---- */
+#define MS_POST_K 10
+typedef struct {
+    int64_t y;                /* mono input offset */
+    int64_t out;              /* output offset in frames */
+    int64_t rbuf;             /* stereo_mode 2: offset of the precomputed right channel in `mono` */
+    int32_t n;
+    int32_t stereo_mode;      /* 0 duplicate, 1 Bessel FIR (even n), 2 precomputed */
+    int32_t dl, dr;
+    float drive, inv_tanh_drive, peak, _pad;
+    float coef[2 * MS_POST_K + 1];
+    float _pad2;
+} ms_post_render;
+int ms_post(const ms_post_render* dev_renders, int n_renders, int max_n, const float* mono, uint32_t* maxbits,
+            float* out, void* stream);
+int ms_roll(const float* src, float* dst, int n, int shift, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
