@@ -32,14 +32,14 @@ class SpecJob(C.Structure):
 
 
 OP_NONE, OP_GRAIN, OP_TILT, OP_ROT = 0, 1, 2, 3
-POST_K = 10
+POST_K = 12
 
 
 class SynthEvt(C.Structure):
     _fields_ = [("s_hi", C.c_uint64), ("s_lo", C.c_uint64), ("i_hi", C.c_uint64), ("i_lo", C.c_uint64),
                 ("n", C.c_int32), ("mode", C.c_int32), ("fade", C.c_int32), ("sigma", C.c_int32),
                 ("out", C.c_int64), ("f_over_sr", C.c_double), ("inv_fade", C.c_double),
-                ("ring_decay", C.c_float), ("env_decay", C.c_float),
+                ("ring_decay", C.c_double), ("env_decay", C.c_double),
                 ("dust_begin", C.c_int64), ("dust_count", C.c_int32), ("ker_len", C.c_int32), ("aux", C.c_int64)]
 
 
@@ -47,11 +47,11 @@ class OlaRender(C.Structure):
     _fields_ = [("out", C.c_int64), ("out_n", C.c_int32), ("ev_begin", C.c_int32), ("ev_end", C.c_int32),
                 ("max_len", C.c_int32), ("A", C.c_int32), ("D_end", C.c_int32), ("sus_end", C.c_int32),
                 ("has_release", C.c_int32), ("inv_A", C.c_double), ("inv_D", C.c_double), ("inv_R", C.c_double),
-                ("S", C.c_float), ("curve", C.c_float)]
+                ("S", C.c_double), ("curve", C.c_double)]
 
 
 class OlaEvt(C.Structure):
-    _fields_ = [("grain", C.c_int64), ("start", C.c_int32), ("len", C.c_int32), ("amp", C.c_float), ("_pad", C.c_int32)]
+    _fields_ = [("grain", C.c_int64), ("start", C.c_int32), ("len", C.c_int32), ("amp", C.c_double)]
 
 
 class FirRender(C.Structure):
@@ -63,15 +63,18 @@ class FirRender(C.Structure):
 class PostRender(C.Structure):
     _fields_ = [("y", C.c_int64), ("out", C.c_int64), ("rbuf", C.c_int64), ("n", C.c_int32),
                 ("stereo_mode", C.c_int32), ("dl", C.c_int32), ("dr", C.c_int32),
-                ("drive", C.c_float), ("inv_tanh_drive", C.c_float), ("peak", C.c_float), ("_pad", C.c_float),
-                ("coef", C.c_float * (2 * POST_K + 1)), ("_pad2", C.c_float)]
+                ("drive", C.c_double), ("inv_tanh_drive", C.c_double), ("peak", C.c_double),
+                ("coef", C.c_double * (2 * POST_K + 1))]
 
 
 _P, _I, _Z = C.c_void_p, C.c_int, C.c_size_t
-_SIGNATURES = {
+_COMMON = {
     "ms_version": (C.c_int, []),
     "ms_last_error": (C.c_char_p, []),
     "ms_is_cuda_build": (C.c_int, []),
+}
+# every stage exists as <name>_f32 and <name>_f64 (include/microsound_b200.h, MS_DECLARE_API)
+_STAGES = {
     "ms_spectral_workspace_bytes": (_Z, [_P, _I]),
     "ms_spectral_apply": (_I, [_P, _I, _P, _P, _P, _Z, _P]),
     "ms_spectral_create": (_I, [_P, _I, _P, _P, _P, _Z, _P, C.POINTER(C.c_void_p)]),
@@ -91,6 +94,7 @@ _SIGNATURES = {
     "ms_post": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "ms_roll": (_I, [_P, _P, _I, _I, _P]),
 }
+PRECISIONS = ("f32", "f64")
 
 
 class MicrosoundLibraryError(RuntimeError):
@@ -99,7 +103,7 @@ class MicrosoundLibraryError(RuntimeError):
 
 def exported_symbols():
     """Names include/microsound_b200.h declares (checked by tests/test_abi_symbols.py)."""
-    return sorted(_SIGNATURES)
+    return sorted(list(_COMMON) + [f"{n}_{p}" for n in _STAGES for p in PRECISIONS])
 
 
 def load_library(path):
@@ -108,11 +112,27 @@ def load_library(path):
             f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). There is no CPU fallback.")
     lib = C.CDLL(path)
-    for name, (res, args) in _SIGNATURES.items():
+    for name, (res, args) in _COMMON.items():
         fn = getattr(lib, name)      # AttributeError here = header/library mismatch
-        fn.restype = res
-        fn.argtypes = args
+        fn.restype, fn.argtypes = res, args
+    for name, (res, args) in _STAGES.items():
+        for p in PRECISIONS:
+            fn = getattr(lib, f"{name}_{p}")
+            fn.restype, fn.argtypes = res, args
     return lib
+
+
+class Api:
+    """View of the library for one precision: api.ms_post -> lib.ms_post_f64 etc."""
+
+    def __init__(self, lib, precision):
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        self.lib, self.precision = lib, precision
+        for name in _COMMON:
+            setattr(self, name, getattr(lib, name))
+        for name in _STAGES:
+            setattr(self, name, getattr(lib, f"{name}_{precision}"))
 
 
 _lib = None

@@ -1,7 +1,5 @@
 // ms_fft_api.inl -- C-ABI entry points of the spectral stage (include/microsound_b200.h).
 // Included by ms_lib.cu (nvcc, product) and by tests/host_emul (g++, block emulator).
-#include "ms_fft_host.h"
-#include "../../include/microsound_b200.h"
 
 static_assert(sizeof(ms_band_edge) == sizeof(BandEdge), "ABI mirror of BandEdge");
 
@@ -28,12 +26,12 @@ static int spec_prepare(const ms_spec_job* in, int njobs, std::vector<FftJob>& o
     }
     lay.jobs_off = 0;
     lay.z_off = ms_align256(sizeof(FftJob) * (size_t)njobs);
-    lay.work_off = lay.z_off + ms_align256(sizeof(float2) * z);
-    lay.total = lay.work_off + ms_align256(sizeof(float2) * w);
+    lay.work_off = lay.z_off + ms_align256(sizeof(cpx) * z);
+    lay.total = lay.work_off + ms_align256(sizeof(cpx) * w);
     return 0;
 }
 
-extern "C" size_t ms_spectral_workspace_bytes(const ms_spec_job* jobs, int njobs) {
+extern "C" size_t MS_API(ms_spectral_workspace_bytes)(const ms_spec_job* jobs, int njobs) {
     std::vector<FftJob> tmp; SpecLayout lay;
     if (njobs <= 0) return 256;
     if (spec_prepare(jobs, njobs, tmp, lay, (ms_stream_t)0)) return 0;
@@ -42,7 +40,7 @@ extern "C" size_t ms_spectral_workspace_bytes(const ms_spec_job* jobs, int njobs
 
 struct SpectralPlan { std::vector<FftJob> jobs; FftJob* jobs_dev; };
 
-extern "C" int ms_spectral_create(const ms_spec_job* in, int njobs, const float* src, float* dst,
+extern "C" int MS_API(ms_spectral_create)(const ms_spec_job* in, int njobs, const real* src, real* dst,
                                   void* ws, size_t ws_bytes, void* stream, void** handle) {
     *handle = nullptr;
     ms_stream_t st = (ms_stream_t)stream;
@@ -58,9 +56,9 @@ extern "C" int ms_spectral_create(const ms_spec_job* in, int njobs, const float*
         const ms_spec_job& s = in[i];
         J.in_a = src + s.in_a; J.in_b = s.in_b >= 0 ? src + s.in_b : nullptr;
         J.out_a = dst + s.out_a; J.out_b = s.out_b >= 0 ? dst + s.out_b : nullptr;
-        J.Z = (float2*)(base + lay.z_off) + lay.z_at[i];
-        J.work = J.F1 > 1 ? (float2*)(base + lay.work_off) + lay.work_at[i] : nullptr;
-        J.out_scale = 1.0f / (float)J.n;
+        J.Z = (cpx*)(base + lay.z_off) + lay.z_at[i];
+        J.work = J.F1 > 1 ? (cpx*)(base + lay.work_off) + lay.work_at[i] : nullptr;
+        J.out_scale = (real)1.0 / (real)J.n;
         for (int w = 0; w < 2; ++w) {
             SpecOp& op = J.op[w];
             const ms_spec_op& so = s.op[w];
@@ -77,7 +75,7 @@ extern "C" int ms_spectral_create(const ms_spec_job* in, int njobs, const float*
     *handle = P;
     return 0;
 }
-extern "C" int ms_spectral_run(void* handle, void* stream) {
+extern "C" int MS_API(ms_spectral_run)(void* handle, void* stream) {
     SpectralPlan* P = (SpectralPlan*)handle;
     if (!P) MS_FAIL("ms_spectral_run: null handle");
     if (P->jobs.empty()) return 0;
@@ -85,24 +83,24 @@ extern "C" int ms_spectral_run(void* handle, void* stream) {
     if (FftEngine::get().forward(P->jobs, P->jobs_dev, st)) return -1;
     return FftEngine::get().inverse(P->jobs, P->jobs_dev, st);
 }
-extern "C" void ms_spectral_destroy(void* handle) { delete (SpectralPlan*)handle; }
+extern "C" void MS_API(ms_spectral_destroy)(void* handle) { delete (SpectralPlan*)handle; }
 
-extern "C" int ms_spectral_apply(const ms_spec_job* in, int njobs, const float* src, float* dst,
+extern "C" int MS_API(ms_spectral_apply)(const ms_spec_job* in, int njobs, const real* src, real* dst,
                                  void* ws, size_t ws_bytes, void* stream) {
     if (njobs <= 0) return 0;
     void* h = nullptr;
-    if (ms_spectral_create(in, njobs, src, dst, ws, ws_bytes, stream, &h)) return -1;
-    const int rc = ms_spectral_run(h, stream);
-    ms_spectral_destroy(h);
+    if (MS_API(ms_spectral_create)(in, njobs, src, dst, ws, ws_bytes, stream, &h)) return -1;
+    const int rc = MS_API(ms_spectral_run)(h, stream);
+    MS_API(ms_spectral_destroy)(h);
     return rc;
 }
 
-extern "C" size_t ms_fft_pair_workspace_bytes(int n) {
+extern "C" size_t MS_API(ms_fft_pair_workspace_bytes)(int n) {
     ms_spec_job j; memset(&j, 0, sizeof j); j.n = n;
-    return ms_spectral_workspace_bytes(&j, 1);
+    return MS_API(ms_spectral_workspace_bytes)(&j, 1);
 }
 
-extern "C" int ms_fft_pair_forward(const float* a, const float* b, int n, float* z_out,
+extern "C" int MS_API(ms_fft_pair_forward)(const real* a, const real* b, int n, real* z_out,
                                    void* ws, size_t ws_bytes, void* stream) {
     ms_stream_t st = (ms_stream_t)stream;
     ms_spec_job s; memset(&s, 0, sizeof s); s.n = n;
@@ -111,8 +109,8 @@ extern "C" int ms_fft_pair_forward(const float* a, const float* b, int n, float*
     if (ws_bytes < lay.total) MS_FAIL("ms_fft_pair_forward: workspace %zu < required %zu", ws_bytes, lay.total);
     char* base = (char*)ws;
     FftJob& J = jobs[0];
-    J.in_a = a; J.in_b = b; J.Z = (float2*)z_out;
-    J.work = J.F1 > 1 ? (float2*)(base + lay.work_off) : nullptr;
+    J.in_a = a; J.in_b = b; J.Z = (cpx*)z_out;
+    J.work = J.F1 > 1 ? (cpx*)(base + lay.work_off) : nullptr;
     FftJob* jd = (FftJob*)(base + lay.jobs_off);
     if (ms_h2d(jd, jobs.data(), sizeof(FftJob), st)) return -1;
     return FftEngine::get().forward(jobs, jd, st);

@@ -9,8 +9,6 @@
 // the autosort Stockham step: butterfly j (0 <= j < F/R) reads x[j + q*F/R], q < R, multiplies by
 // w_{Ns*R}^{q*(j mod Ns)}, takes a length-R DFT and writes to (j - j mod Ns)*R + (j mod Ns) + q*Ns.
 // Passes ping-pong between two shared-memory buffers.  Natural order in, natural order out.
-#pragma once
-#include "ms_rt.cuh"
 
 #define MS_MAX_RADICES 12
 
@@ -49,62 +47,63 @@ static inline int ms_make_radix_plan(int F, RadixPlan* p) {
     return m == 1;
 }
 
+
 // ---- length-R forward DFTs in registers ---------------------------------------------------------
 template <int R> struct Bfly;
 
 template <> struct Bfly<2> {
-    static MS_DEV void run(float2* a) {
-        float2 t = a[0];
+    static MS_DEV void run(cpx* a) {
+        cpx t = a[0];
         a[0] = c_add(t, a[1]);
         a[1] = c_sub(t, a[1]);
     }
 };
 template <> struct Bfly<4> {
-    static MS_DEV void run(float2* a) {
-        float2 t0 = c_add(a[0], a[2]), t1 = c_sub(a[0], a[2]);
-        float2 t2 = c_add(a[1], a[3]), t3 = c_mul_mi(c_sub(a[1], a[3]));
+    static MS_DEV void run(cpx* a) {
+        cpx t0 = c_add(a[0], a[2]), t1 = c_sub(a[0], a[2]);
+        cpx t2 = c_add(a[1], a[3]), t3 = c_mul_mi(c_sub(a[1], a[3]));
         a[0] = c_add(t0, t2); a[1] = c_add(t1, t3);
         a[2] = c_sub(t0, t2); a[3] = c_sub(t1, t3);
     }
 };
 template <> struct Bfly<3> {
-    static MS_DEV void run(float2* a) {
-        const float h = 0.86602540378443864676f;   // sin(2 pi / 3)
-        float2 s = c_add(a[1], a[2]), d = c_sub(a[1], a[2]);
-        float2 m = make_float2(a[0].x - 0.5f * s.x, a[0].y - 0.5f * s.y);
-        float2 r = make_float2(h * d.y, -h * d.x);   // (-i h) * d
+    static MS_DEV void run(cpx* a) {
+        const real h = (real)0.86602540378443864676;   // sin(2 pi / 3)
+        cpx s = c_add(a[1], a[2]), d = c_sub(a[1], a[2]);
+        cpx m = mk(a[0].x - (real)0.5 * s.x, a[0].y - (real)0.5 * s.y);
+        cpx r = mk(h * d.y, -h * d.x);   // (-i h) * d
         a[0] = c_add(a[0], s);
         a[1] = c_add(m, r);
         a[2] = c_sub(m, r);
     }
 };
 template <> struct Bfly<5> {
-    static MS_DEV void run(float2* a) {
-        const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
-        const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
-        float2 p1 = c_add(a[1], a[4]), m1 = c_sub(a[1], a[4]);
-        float2 p2 = c_add(a[2], a[3]), m2 = c_sub(a[2], a[3]);
-        float2 a0 = a[0];
-        float2 e1 = make_float2(a0.x + c1 * p1.x + c2 * p2.x, a0.y + c1 * p1.y + c2 * p2.y);
-        float2 e2 = make_float2(a0.x + c2 * p1.x + c1 * p2.x, a0.y + c2 * p1.y + c1 * p2.y);
-        float2 u1 = make_float2(s1 * m1.x + s2 * m2.x, s1 * m1.y + s2 * m2.y);
-        float2 u2 = make_float2(s2 * m1.x - s1 * m2.x, s2 * m1.y - s1 * m2.y);
-        float2 r1 = c_mul_mi(u1), r2 = c_mul_mi(u2);  // -i * u
-        a[0] = make_float2(a0.x + p1.x + p2.x, a0.y + p1.y + p2.y);
+    static MS_DEV void run(cpx* a) {
+        const real c1 = (real)0.30901699437494742410, c2 = -(real)0.80901699437494742410;
+        const real s1 = (real)0.95105651629515357212, s2 = (real)0.58778525229247312917;
+        cpx p1 = c_add(a[1], a[4]), m1 = c_sub(a[1], a[4]);
+        cpx p2 = c_add(a[2], a[3]), m2 = c_sub(a[2], a[3]);
+        cpx a0 = a[0];
+        cpx e1 = mk(a0.x + c1 * p1.x + c2 * p2.x, a0.y + c1 * p1.y + c2 * p2.y);
+        cpx e2 = mk(a0.x + c2 * p1.x + c1 * p2.x, a0.y + c2 * p1.y + c1 * p2.y);
+        cpx u1 = mk(s1 * m1.x + s2 * m2.x, s1 * m1.y + s2 * m2.y);
+        cpx u2 = mk(s2 * m1.x - s1 * m2.x, s2 * m1.y - s1 * m2.y);
+        cpx r1 = c_mul_mi(u1), r2 = c_mul_mi(u2);  // -i * u
+        a[0] = mk(a0.x + p1.x + p2.x, a0.y + p1.y + p2.y);
         a[1] = c_add(e1, r1); a[4] = c_sub(e1, r1);
         a[2] = c_add(e2, r2); a[3] = c_sub(e2, r2);
     }
 };
 template <> struct Bfly<8> {
-    static MS_DEV void run(float2* a) {
-        const float h = 0.70710678118654752440f;
-        float2 e[4] = {a[0], a[2], a[4], a[6]};
-        float2 o[4] = {a[1], a[3], a[5], a[7]};
+    static MS_DEV void run(cpx* a) {
+        const real h = (real)0.70710678118654752440;
+        cpx e[4] = {a[0], a[2], a[4], a[6]};
+        cpx o[4] = {a[1], a[3], a[5], a[7]};
         Bfly<4>::run(e);
         Bfly<4>::run(o);
-        float2 o1 = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));      // * (1 - i)/sqrt2
-        float2 o2 = c_mul_mi(o[2]);                                                // * -i
-        float2 o3 = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));     // * (-1 - i)/sqrt2
+        cpx o1 = mk(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));      // * (1 - i)/sqrt2
+        cpx o2 = c_mul_mi(o[2]);                                                // * -i
+        cpx o3 = mk(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));     // * (-1 - i)/sqrt2
         a[0] = c_add(e[0], o[0]); a[4] = c_sub(e[0], o[0]);
         a[1] = c_add(e[1], o1);   a[5] = c_sub(e[1], o1);
         a[2] = c_add(e[2], o2);   a[6] = c_sub(e[2], o2);
@@ -117,8 +116,8 @@ template <> struct Bfly<8> {
 // before it starts the next, so nothing but the R values of a butterfly lives in registers and one
 // barrier per pass suffices.  tw = table of w_F^i (i < F), forward sign.
 template <int R>
-MS_DEV void stockham_pass(const float2* MS_RESTRICT src, float2* MS_RESTRICT dst, const TileGeom& g, int F, int Ns,
-                          const float2* MS_RESTRICT tw, const Ctx& c) {
+MS_DEV void stockham_pass(const cpx* MS_RESTRICT src, cpx* MS_RESTRICT dst, const TileGeom& g, int F, int Ns,
+                          const cpx* MS_RESTRICT tw, const Ctx& c) {
     const int per_vec = F / R;
     const int nb = per_vec * g.cnt;
     const int tws = F / (Ns * R);
@@ -127,7 +126,7 @@ MS_DEV void stockham_pass(const float2* MS_RESTRICT src, float2* MS_RESTRICT dst
         int vec, j;
         if (g.colmajor) { j = b / g.cnt; vec = b - j * g.cnt; } else { vec = b / per_vec; j = b - vec * per_vec; }
         const int k = (Ns == 1) ? 0 : (j % Ns);
-        float2 v[R];
+        cpx v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = src[tile_addr(g, vec, j + q * per_vec)];
         if (k != 0) {
@@ -144,7 +143,7 @@ MS_DEV void stockham_pass(const float2* MS_RESTRICT src, float2* MS_RESTRICT dst
 
 // Full forward FFT of every vector of the tile.  `a` holds the input (caller synchronised after
 // filling it), `b` is the second buffer of the same size.  Returns the buffer that holds the result.
-MS_DEV float2* tile_fft(float2* a, float2* b, const TileGeom& g, const RadixPlan& p, const float2* MS_RESTRICT tw, const Ctx& c) {
+MS_DEV cpx* tile_fft(cpx* a, cpx* b, const TileGeom& g, const RadixPlan& p, const cpx* MS_RESTRICT tw, const Ctx& c) {
     int Ns = 1;
     for (int i = 0; i < p.nrad; ++i) {
         const int r = p.rad[i];
@@ -155,7 +154,7 @@ MS_DEV float2* tile_fft(float2* a, float2* b, const TileGeom& g, const RadixPlan
             case 3: stockham_pass<3>(a, b, g, p.F, Ns, tw, c); break;
             default: stockham_pass<5>(a, b, g, p.F, Ns, tw, c); break;
         }
-        float2* t = a; a = b; b = t;
+        cpx* t = a; a = b; b = t;
         Ns *= r;
     }
     return a;

@@ -1,17 +1,10 @@
 // ms_fft_host.h -- host side of the spectral engine: geometry planning, twiddle / chirp / Bluestein
 // filter caches, and the kernel sequences.  Compiled by nvcc into the product and by g++ into the
 // block emulator used by the CPU tests (same source, see ms_rt.cuh).
-#pragma once
-#include "ms_fft_kernels.cuh"
-#include "ms_launch.cuh"
-#include <map>
-#include <mutex>
-#include <vector>
-#include <algorithm>
-#include <utility>
 
-#define MS_SMALL_MAX 8192       // largest vector one CTA transforms in shared memory
-#define MS_TILE_MAX 8192        // largest tile (complex elements) a CTA holds
+// largest vector one CTA transforms in shared memory / largest tile a CTA holds (two ping-pong buffers)
+static const int MS_SMALL_MAX = sizeof(real) == 4 ? 8192 : 4096;
+static const int MS_TILE_MAX = sizeof(real) == 4 ? 8192 : 4096;
 
 // ---- kernel structs ----------------------------------------------------------------------------------
 template <int LD, int ST, int TWID> struct ColsK {
@@ -24,7 +17,7 @@ template <int LD, int MODE, int ST> struct RowsK {
 };
 struct GenTableK {
     static constexpr int MAXT = 256;
-    static MS_DEV void run(float2* out, int count, long long mul, long long N, const Ctx& c) {
+    static MS_DEV void run(cpx* out, int count, long long mul, long long N, const Ctx& c) {
         gen_table_body(out, count, mul, N, c, c.nthr * 64, c.bx * c.nthr + c.tid);
     }
 };
@@ -42,8 +35,8 @@ struct LaunchShape { int ept, nthr; size_t smem; unsigned gx; };
 
 static inline int cols_tile_elems(const FftJob& J) { return J.T * J.F1; }
 static inline int rows_tile_elems(const FftJob& J) { return J.G * J.F2; }
-static inline size_t cols_smem(const FftJob& J) { return 2 * sizeof(float2) * (size_t)(ms_pad((J.F1 - 1) * J.T + J.T - 1) + 2); }
-static inline size_t rows_smem(const FftJob& J) { return 2 * sizeof(float2) * (size_t)(J.G * ((ms_pad(J.F2) + 1) | 1) + 2); }
+static inline size_t cols_smem(const FftJob& J) { return 2 * sizeof(cpx) * (size_t)(ms_pad((J.F1 - 1) * J.T + J.T - 1) + 2); }
+static inline size_t rows_smem(const FftJob& J) { return 2 * sizeof(cpx) * (size_t)(J.G * ((ms_pad(J.F2) + 1) | 1) + 2); }
 
 static inline void shape_for(int tile, LaunchShape* s) {
     s->ept = 0;
@@ -75,9 +68,9 @@ public:
 
 private:
     std::mutex mu_;
-    std::map<int, float2*> wtab_;                                  // F -> w_F^i
-    std::map<long long, std::pair<float2*, float2*>> two_level_;   // modulus N -> (hi, lo)
-    std::map<int, float2*> bspec_;                                 // n -> Bluestein filter spectrum
+    std::map<int, cpx*> wtab_;                                  // F -> w_F^i
+    std::map<long long, std::pair<cpx*, cpx*>> two_level_;   // modulus N -> (hi, lo)
+    std::map<int, cpx*> bspec_;                                 // n -> Bluestein filter spectrum
     std::map<int, FftJob> geom_;                                   // n -> prepared geometry template
 
     template <class K, class... A>
@@ -86,10 +79,10 @@ private:
         return ms_launch<K>(g, nthr, smem, st, a...);
     }
 
-    int get_wtab(int F, ms_stream_t st, const float2** out) {
+    int get_wtab(int F, ms_stream_t st, const cpx** out) {
         auto it = wtab_.find(F);
         if (it == wtab_.end()) {
-            float2* p = (float2*)ms_dev_alloc(sizeof(float2) * (size_t)F);
+            cpx* p = (cpx*)ms_dev_alloc(sizeof(cpx) * (size_t)F);
             if (!p) MS_FAIL("out of device memory for twiddle table F=%d", F);
             if (L<GenTableK>(64, 1, 256, 0, st, p, F, 1ll, (long long)F)) return -1;
             it = wtab_.emplace(F, p).first;
@@ -97,12 +90,12 @@ private:
         *out = it->second;
         return 0;
     }
-    int get_two_level(long long N, ms_stream_t st, const float2** hi, const float2** lo) {
+    int get_two_level(long long N, ms_stream_t st, const cpx** hi, const cpx** lo) {
         auto it = two_level_.find(N);
         if (it == two_level_.end()) {
             int nhi = (int)((N + 1023) / 1024) + 1;
-            float2* ph = (float2*)ms_dev_alloc(sizeof(float2) * (size_t)nhi);
-            float2* pl = (float2*)ms_dev_alloc(sizeof(float2) * 1024);
+            cpx* ph = (cpx*)ms_dev_alloc(sizeof(cpx) * (size_t)nhi);
+            cpx* pl = (cpx*)ms_dev_alloc(sizeof(cpx) * 1024);
             if (!ph || !pl) MS_FAIL("out of device memory for two-level table N=%lld", N);
             if (L<GenTableK>(64, 1, 256, 0, st, ph, nhi, 1024ll, N)) return -1;
             if (L<GenTableK>(64, 1, 256, 0, st, pl, 1024, 1ll, N)) return -1;
@@ -176,7 +169,7 @@ private:
     }
 
     int make_bspec(FftJob& g, ms_stream_t st) {
-        float2* spec = (float2*)ms_dev_alloc(sizeof(float2) * (size_t)g.M);
+        cpx* spec = (cpx*)ms_dev_alloc(sizeof(cpx) * (size_t)g.M);
         FftJob* jd = (FftJob*)ms_dev_alloc(sizeof(FftJob));
         if (!spec || !jd) MS_FAIL("out of device memory for Bluestein spectrum n=%d M=%d", g.n, g.M);
         FftJob t = g; t.work = spec; t.bspec = nullptr;

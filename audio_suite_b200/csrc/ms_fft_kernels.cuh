@@ -16,8 +16,6 @@
 //                             leave in place; a final columns kernel (no twiddle) finishes the
 //                             inverse and applies the output chirp.
 //                     RAW  -> leave the [k1][k2] spectrum in place (used to build filter spectra).
-#pragma once
-#include "ms_fft_core.cuh"
 
 enum { LD_WORK = 0, LD_CPX, LD_PAIR, LD_PAIR_CHIRP, LD_SPEC, LD_SPEC_CHIRP, LD_BW, LD_OLS, LD_REALPAD };
 enum { ST_WORK = 0, ST_CPX, ST_Z, ST_Z_CHIRP, ST_PAIR, ST_PAIR_CHIRP, ST_OLS };
@@ -46,23 +44,24 @@ struct SpecOp {
     double alpha;          // OP_TILT: shape = max(k,1)^alpha ;  OP_ROT: theta (0.9 * width)
 };
 
+
 struct FftJob {
     int n, M, F1, F2;
     int T, G;                    // column-tile width, row-group height
     RadixPlan p1, p2;
-    const float2* tw1;           // w_F1^i
-    const float2* tw2;           // w_F2^i
-    const float2* twM_hi;        // W_M^(1024 i)
-    const float2* twM_lo;        // W_M^i, i < 1024
-    const float2* ch_hi;         // W_2n^(1024 i)   (Bluestein chirp), null for direct
-    const float2* ch_lo;         // W_2n^i, i < 1024
-    const float2* bspec;         // FFT_M(conj chirp, wrapped)/M in [k1][k2] layout
-    const float* in_a; const float* in_b;
-    float* out_a; float* out_b;
-    const float2* cin; float2* cout;   // LD_CPX / ST_CPX
-    float2* Z;                   // natural-order spectrum, n entries
-    float2* work;                // M entries
-    float out_scale;
+    const cpx* tw1;           // w_F1^i
+    const cpx* tw2;           // w_F2^i
+    const cpx* twM_hi;        // W_M^(1024 i)
+    const cpx* twM_lo;        // W_M^i, i < 1024
+    const cpx* ch_hi;         // W_2n^(1024 i)   (Bluestein chirp), null for direct
+    const cpx* ch_lo;         // W_2n^i, i < 1024
+    const cpx* bspec;         // FFT_M(conj chirp, wrapped)/M in [k1][k2] layout
+    const real* in_a; const real* in_b;
+    real* out_a; real* out_b;
+    const cpx* cin; cpx* cout;   // LD_CPX / ST_CPX
+    cpx* Z;                   // natural-order spectrum, n entries
+    cpx* work;                // M entries
+    real out_scale;
     int ols_n;                   // overlap-save: signal length (LD_OLS / ST_OLS)
     long long p0_a, p0_b;        // overlap-save: first input sample position of block a / b (may be negative)
     int ols_skip;                // overlap-save: taps - 1 (leading outputs of a block that are discarded)
@@ -71,11 +70,11 @@ struct FftJob {
 };
 
 // ---- twiddles ------------------------------------------------------------------------------------
-MS_DEV float2 tw2level(const float2* MS_RESTRICT hi, const float2* MS_RESTRICT lo, unsigned e) {
+MS_DEV cpx tw2level(const cpx* MS_RESTRICT hi, const cpx* MS_RESTRICT lo, unsigned e) {
     return c_mul(__ldg(&hi[e >> 10]), __ldg(&lo[e & 1023u]));
 }
 // chirp c[j] = exp(-i pi j^2 / n) = W_{2n}^(j^2 mod 2n)
-MS_DEV float2 chirp(const FftJob& J, int j) {
+MS_DEV cpx chirp(const FftJob& J, int j) {
     const long long jj = (long long)j * (long long)j;
     const long long m2 = 2ll * J.n;
     long long q = (long long)((double)jj / (double)m2);
@@ -86,100 +85,100 @@ MS_DEV float2 chirp(const FftJob& J, int j) {
 }
 
 // ---- spectral operators --------------------------------------------------------------------------
-MS_DEV float edge_weight(const BandEdge& b, double f) {
-    if (b.zero) return 0.f;
-    float w = 1.f;
-    if (b.lo_mode == 1) { if (f < b.lo_f1) return 0.f; }
+MS_DEV real edge_weight(const BandEdge& b, double f) {
+    if (b.zero) return (real)0.;
+    real w = (real)1.;
+    if (b.lo_mode == 1) { if (f < b.lo_f1) return (real)0.; }
     else if (b.lo_mode == 2) {
-        if (f < b.lo_f0) return 0.f;
+        if (f < b.lo_f0) return (real)0.;
         if (f <= b.lo_f1) {
             double t = (f - b.lo_f0) / fmax(1e-12, b.lo_f1 - b.lo_f0);
-            w *= 0.5f * (1.f - cospif((float)t));
+            w *= (real)0.5 * ((real)1. - r_cospi((real)t));
         }
     }
-    if (b.hi_mode == 1) { if (f > b.hi_f0) return 0.f; }
+    if (b.hi_mode == 1) { if (f > b.hi_f0) return (real)0.; }
     else if (b.hi_mode == 2) {
-        if (f > b.hi_f1) return 0.f;
+        if (f > b.hi_f1) return (real)0.;
         if (f >= b.hi_f0) {
             double t = (f - b.hi_f0) / fmax(1e-12, b.hi_f1 - b.hi_f0);
-            w *= 0.5f * (1.f + cospif((float)t));
+            w *= (real)0.5 * ((real)1. + r_cospi((real)t));
         }
     }
     return w;
 }
-MS_DEV float lp_weight(const SpecOp& op, int kk) { return op.lp_on ? edge_weight(op.lp, (double)kk * op.df) : 1.f; }
-MS_DEV float mb_weight(const SpecOp& op, int kk) {
-    if (op.n_bands == 0) return 1.f;
+MS_DEV real lp_weight(const SpecOp& op, int kk) { return op.lp_on ? edge_weight(op.lp, (double)kk * op.df) : (real)1.; }
+MS_DEV real mb_weight(const SpecOp& op, int kk) {
+    if (op.n_bands == 0) return (real)1.;
     const double f = (double)kk * op.df;
-    float w = 0.f;
+    real w = (real)0.;
     for (int b = 0; b < op.n_bands; ++b) w += edge_weight(op.mb[b], f);
     return w;
 }
 // One packed signal's spectrum out of Z = A + iB:  A[i] = (Z[i] + conj Z[n-i]) / 2,
 // B[i] = (Z[i] - conj Z[n-i]) / (2i)   (0 <= i <= n/2).
-MS_DEV float2 split_bin(const float2* MS_RESTRICT Z, int n, int i, int sel, int paired) {
-    const float2 p = __ldg(&Z[i]);
+MS_DEV cpx split_bin(const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired) {
+    const cpx p = __ldg(&Z[i]);
     if (!paired) return p;                    // b absent: Z is already A
-    const float2 q = __ldg(&Z[i == 0 ? 0 : n - i]);
-    if (sel == 0) return make_float2(0.5f * (p.x + q.x), 0.5f * (p.y - q.y));
-    return make_float2(0.5f * (p.y + q.y), 0.5f * (q.x - p.x));
+    const cpx q = __ldg(&Z[i == 0 ? 0 : n - i]);
+    if (sel == 0) return mk((real)0.5 * (p.x + q.x), (real)0.5 * (p.y - q.y));
+    return mk((real)0.5 * (p.y + q.y), (real)0.5 * (q.x - p.x));
 }
 // What irfft() would be handed for one signal at folded bin kk (0 <= kk <= n/2):
 // low-pass -> stretch (two-point gather at kk/factor, zero beyond the last bin) -> multiband weights,
 // or the tilt / rotation multipliers.
-MS_DEV float2 op_value(const SpecOp& op, const float2* MS_RESTRICT Z, int n, int kk, int sel, int paired) {
+MS_DEV cpx op_value(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int kk, int sel, int paired) {
     const int kmax = n >> 1;
     if (op.kind == OP_NONE) return split_bin(Z, n, kk, sel, paired);
     if (op.kind == OP_TILT) {
-        float s = (float)pow((double)(kk < 1 ? 1 : kk), op.alpha);
+        real s = (real)pow((double)(kk < 1 ? 1 : kk), op.alpha);
         return c_scale(split_bin(Z, n, kk, sel, paired), s);
     }
     if (op.kind == OP_ROT) {   // exp(i theta sin(2 pi kk / kmax))
         if (kk == 0) return split_bin(Z, n, kk, sel, paired);
-        float sn, cs, rs, rc;
-        sincospif(2.0f * (float)((double)kk / (double)(kmax < 1 ? 1 : kmax)), &sn, &cs);
-        sincosf((float)op.alpha * sn, &rs, &rc);
-        return c_mul(split_bin(Z, n, kk, sel, paired), make_float2(rc, rs));
+        real sn, cs, rs, rc;
+        r_sincospi((real)2.0 * (real)((double)kk / (double)(kmax < 1 ? 1 : kmax)), &sn, &cs);
+        r_sincos((real)op.alpha * sn, &rs, &rc);
+        return c_mul(split_bin(Z, n, kk, sel, paired), mk(rc, rs));
     }
-    float2 y;
+    cpx y;
     if (!op.stretch_on) {
         y = c_scale(split_bin(Z, n, kk, sel, paired), lp_weight(op, kk));
     } else {
         const double pos = (double)kk / fmax(1e-12, op.factor);
         if (pos > (double)kmax) return c_zero();
         int i0 = (int)pos;
-        float fr = (float)(pos - (double)i0);
-        if (i0 >= kmax) { i0 = kmax; fr = 0.f; }
+        real fr = (real)(pos - (double)i0);
+        if (i0 >= kmax) { i0 = kmax; fr = (real)0.; }
         y = c_scale(split_bin(Z, n, i0, sel, paired), lp_weight(op, i0));
-        if (fr != 0.f) {
-            float2 v1 = c_scale(split_bin(Z, n, i0 + 1, sel, paired), lp_weight(op, i0 + 1));
-            y = make_float2(y.x + (v1.x - y.x) * fr, y.y + (v1.y - y.y) * fr);
+        if (fr != (real)0.) {
+            cpx v1 = c_scale(split_bin(Z, n, i0 + 1, sel, paired), lp_weight(op, i0 + 1));
+            y = mk(y.x + (v1.x - y.x) * fr, y.y + (v1.y - y.y) * fr);
         }
     }
     return c_scale(y, mb_weight(op, kk));
 }
 // Y[k] for natural k in [0, n): both packed signals at once, Hermitian-extended the way irfft does
 // (imaginary part of DC and, for even n, of the Nyquist bin is dropped).
-MS_DEV float2 spec_value(const FftJob& J, const float2* MS_RESTRICT Z, int k) {
+MS_DEV cpx spec_value(const FftJob& J, const cpx* MS_RESTRICT Z, int k) {
     const int n = J.n, kmax = n >> 1;
     const int upper = k > kmax;
     const int kk = upper ? n - k : k;
     const int paired = J.in_b != nullptr;
-    float2 ya = op_value(J.op[0], Z, n, kk, 0, paired);
-    float2 yb = paired ? op_value(J.op[1], Z, n, kk, 1, paired) : c_zero();
-    if (kk == 0 || (!(n & 1) && kk == kmax)) { ya.y = 0.f; yb.y = 0.f; }
+    cpx ya = op_value(J.op[0], Z, n, kk, 0, paired);
+    cpx yb = paired ? op_value(J.op[1], Z, n, kk, 1, paired) : c_zero();
+    if (kk == 0 || (!(n & 1) && kk == kmax)) { ya.y = (real)0.; yb.y = (real)0.; }
     if (upper) { ya.y = -ya.y; yb.y = -yb.y; }
-    return make_float2(ya.x - yb.y, ya.y + yb.x);
+    return mk(ya.x - yb.y, ya.y + yb.x);
 }
 
 // ---- load / store functors -----------------------------------------------------------------------
 template <int LD>
-MS_DEV float2 job_load(const FftJob& J, int idx) {
+MS_DEV cpx job_load(const FftJob& J, int idx) {
     if (LD == LD_WORK) return J.work[idx];
     if (LD == LD_CPX) return idx < J.n ? __ldg(&J.cin[idx]) : c_zero();
     if (LD == LD_PAIR || LD == LD_PAIR_CHIRP) {
         if (idx >= J.n) return c_zero();
-        float2 v = make_float2(__ldg(&J.in_a[idx]), J.in_b ? __ldg(&J.in_b[idx]) : 0.f);
+        cpx v = mk(__ldg(&J.in_a[idx]), J.in_b ? __ldg(&J.in_b[idx]) : (real)0.);
         if (LD == LD_PAIR_CHIRP) v = c_mul(v, chirp(J, idx));
         return v;
     }
@@ -193,22 +192,22 @@ MS_DEV float2 job_load(const FftJob& J, int idx) {
     }
     if (LD == LD_OLS) {             // two blocks of one signal as re / im; zero outside [0, ols_n)
         const long long pa = J.p0_a + idx, pb = J.p0_b + idx;
-        const float a = (pa >= 0 && pa < J.ols_n) ? __ldg(&J.in_a[pa]) : 0.f;
-        const float b = (J.in_b && pb >= 0 && pb < J.ols_n) ? __ldg(&J.in_b[pb]) : 0.f;
-        return make_float2(a, b);
+        const real a = (pa >= 0 && pa < J.ols_n) ? __ldg(&J.in_a[pa]) : (real)0.;
+        const real b = (J.in_b && pb >= 0 && pb < J.ols_n) ? __ldg(&J.in_b[pb]) : (real)0.;
+        return mk(a, b);
     }
     if (LD == LD_REALPAD) {         // real taps, zero padded, pre-scaled by 1/M
-        return idx < J.n ? make_float2(__ldg(&J.in_a[idx]) * J.out_scale, 0.f) : c_zero();
+        return idx < J.n ? mk(__ldg(&J.in_a[idx]) * J.out_scale, (real)0.) : c_zero();
     }
     if (LD == LD_BW) {              // wrapped conjugate chirp, scaled by 1/M
         int d;
         if (idx < J.n) d = idx; else if (idx > J.M - J.n) d = J.M - idx; else return c_zero();
-        return c_scale(c_conj(chirp(J, d)), 1.0f / (float)J.M);
+        return c_scale(c_conj(chirp(J, d)), (real)1.0 / (real)J.M);
     }
     return c_zero();
 }
 template <int ST>
-MS_DEV void job_store(const FftJob& J, int idx, float2 v) {
+MS_DEV void job_store(const FftJob& J, int idx, cpx v) {
     if (ST == ST_WORK) { J.work[idx] = v; return; }
     if (ST == ST_OLS) {             // valid part of the circular convolution; un-swap the inverse half
         if (idx < J.ols_skip) return;
@@ -227,7 +226,7 @@ MS_DEV void job_store(const FftJob& J, int idx, float2 v) {
         return;
     }
     if (ST == ST_PAIR_CHIRP) {      // r = chirp * conv ; y = conj(r) / n
-        float2 r = c_mul(c_swap(v), chirp(J, idx));
+        cpx r = c_mul(c_swap(v), chirp(J, idx));
         J.out_a[idx] = r.x * J.out_scale;
         if (J.out_b) J.out_b[idx] = -r.y * J.out_scale;
         return;
@@ -242,8 +241,8 @@ MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
     const int col0 = c.bx * T;
     if (col0 >= F2) return;
     const int cnt = (F2 - col0) < T ? (F2 - col0) : T;
-    float2* s = (float2*)c.smem;
-    float2* s2 = s + (ms_pad((F1 - 1) * T + T - 1) + 2);
+    cpx* s = (cpx*)c.smem;
+    cpx* s2 = s + (ms_pad((F1 - 1) * T + T - 1) + 2);
     TileGeom g; g.cnt = cnt; g.vs = 1; g.es = T; g.colmajor = 1;
     const int total = F1 * cnt;
     for (int e = c.tid; e < total; e += c.nthr) {
@@ -254,7 +253,7 @@ MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
     s = tile_fft(s, s2, g, J.p1, J.tw1, c);
     for (int e = c.tid; e < total; e += c.nthr) {
         const int k1 = e / cnt, v = e - k1 * cnt;
-        float2 val = s[tile_addr(g, v, k1)];
+        cpx val = s[tile_addr(g, v, k1)];
         if (TWID) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)k1 * (unsigned)(col0 + v)));
         job_store<ST>(J, k1 * F2 + col0 + v, val);
     }
@@ -268,9 +267,9 @@ MS_DEV void fft_rows_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
     const int row0 = c.bx * G;
     if (row0 >= F1) return;
     const int cnt = (F1 - row0) < G ? (F1 - row0) : G;
-    float2* s = (float2*)c.smem;
+    cpx* s = (cpx*)c.smem;
     TileGeom g; g.cnt = cnt; g.vs = (ms_pad(F2) + 1) | 1; g.es = 1; g.colmajor = 0;
-    float2* s2 = s + (G * g.vs + 2);
+    cpx* s2 = s + (G * g.vs + 2);
     const int total = F2 * cnt;
     for (int e = c.tid; e < total; e += c.nthr) {
         const int r = e / F2, i = e - r * F2;
@@ -295,11 +294,11 @@ MS_DEV void fft_rows_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
             s[a] = c_swap(c_mul(s[a], __ldg(&J.bspec[(row0 + r) * F2 + i])));
         }
         c.sync();
-        float2* other = (s == (float2*)c.smem) ? s2 : (float2*)c.smem;
+        cpx* other = (s == (cpx*)c.smem) ? s2 : (cpx*)c.smem;
         s = tile_fft(s, other, g, J.p2, J.tw2, c);
         for (int e = c.tid; e < total; e += c.nthr) {
             const int r = e / F2, i = e - r * F2;
-            float2 val = s[tile_addr(g, r, i)];
+            cpx val = s[tile_addr(g, r, i)];
             if (F1 > 1) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)(row0 + r) * (unsigned)i));
             job_store<ST>(J, (row0 + r) * F2 + i, val);
         }
@@ -308,11 +307,11 @@ MS_DEV void fft_rows_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
 
 // ---- table generators (float64 angles, rounded once) -------------------------------------------------
 // out[i] = exp(-2 pi i * ((i * mul) mod N) / N),  i < count
-MS_DEV void gen_table_body(float2* out, int count, long long mul, long long N, const Ctx& c, int grid_threads, int gtid) {
+MS_DEV void gen_table_body(cpx* out, int count, long long mul, long long N, const Ctx& c, int grid_threads, int gtid) {
     for (int i = gtid; i < count; i += grid_threads) {
         long long e = ((long long)i * mul) % N;
         double sn, cs;
-        sincospi(2.0 * (double)e / (double)N, &sn, &cs);
-        out[i] = make_float2((float)cs, (float)(-sn));
+        r_sincospi(2.0 * (double)e / (double)N, &sn, &cs);
+        out[i] = mk((real)cs, (real)(-sn));
     }
 }

@@ -25,11 +25,6 @@
   static inline double __ldg(const double* p) { return *p; }
   static inline float2 __ldg(const float2* p) { return *p; }
   static inline int __ldg(const int* p) { return *p; }
-  static inline void sincospi(double a, double* s, double* c) { *s = std::sin(M_PI * a); *c = std::cos(M_PI * a); }
-  static inline void sincospif(float a, float* s, float* c) { *s = (float)std::sin(M_PI * (double)a); *c = (float)std::cos(M_PI * (double)a); }
-  static inline float cospif(float a) { return (float)std::cos(M_PI * (double)a); }
-  static inline float sinpif(float a) { return (float)std::sin(M_PI * (double)a); }
-  static inline double cospi(double a) { return std::cos(M_PI * a); }
   static inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
   namespace msemu { void yield_barrier(); }
   struct Ctx {
@@ -49,14 +44,49 @@
   };
 #endif
 
-// ---- complex helpers (float2 = re, im) -------------------------------------------------------
-MS_DEV float2 c_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-MS_DEV float2 c_mulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
-MS_DEV float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-MS_DEV float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-MS_DEV float2 c_scale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
-MS_DEV float2 c_swap(float2 a) { return make_float2(a.y, a.x); }
-MS_DEV float2 c_conj(float2 a) { return make_float2(a.x, -a.y); }
-MS_DEV float2 c_zero() { return make_float2(0.f, 0.f); }
-// multiply by -i (forward-FFT quarter turn): (x+iy)(-i) = y - ix
-MS_DEV float2 c_mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+// ---- complex helpers, stamped for float2 and double2 -----------------------------------------------
+#define MS_STAMP_CPX(C, T, MK) \
+MS_DEV C c_mul(C a, C b) { return MK(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); } \
+MS_DEV C c_mulc(C a, C b) { return MK(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); } \
+MS_DEV C c_add(C a, C b) { return MK(a.x + b.x, a.y + b.y); } \
+MS_DEV C c_sub(C a, C b) { return MK(a.x - b.x, a.y - b.y); } \
+MS_DEV C c_scale(C a, T s) { return MK(a.x * s, a.y * s); } \
+MS_DEV C c_swap(C a) { return MK(a.y, a.x); } \
+MS_DEV C c_conj(C a) { return MK(a.x, -a.y); } \
+MS_DEV C c_mul_mi(C a) { return MK(a.y, -a.x); }
+MS_STAMP_CPX(float2, float, make_float2)
+MS_STAMP_CPX(double2, double, make_double2)
+#ifdef MS_HOST_EMUL
+static inline double2 __ldg(const double2* p) { return *p; }
+#endif
+
+// ---- math wrappers overloaded on precision ---------------------------------------------------------------
+#ifdef MS_HOST_EMUL
+MS_DEV void r_sincospi(float a, float* s, float* c) { *s = (float)std::sin(M_PI * (double)a); *c = (float)std::cos(M_PI * (double)a); }
+MS_DEV void r_sincospi(double a, double* s, double* c) { *s = std::sin(M_PI * a); *c = std::cos(M_PI * a); }
+MS_DEV float r_cospi(float a) { return (float)std::cos(M_PI * (double)a); }
+MS_DEV double r_cospi(double a) { return std::cos(M_PI * a); }
+MS_DEV float r_sinpi(float a) { return (float)std::sin(M_PI * (double)a); }
+MS_DEV double r_sinpi(double a) { return std::sin(M_PI * a); }
+MS_DEV void r_sincos(float a, float* s, float* c) { *s = std::sin(a); *c = std::cos(a); }
+MS_DEV void r_sincos(double a, double* s, double* c) { *s = std::sin(a); *c = std::cos(a); }
+#else
+MS_DEV void r_sincospi(float a, float* s, float* c) { sincospif(a, s, c); }
+MS_DEV void r_sincospi(double a, double* s, double* c) { sincospi(a, s, c); }
+MS_DEV float r_cospi(float a) { return cospif(a); }
+MS_DEV double r_cospi(double a) { return cospi(a); }
+MS_DEV float r_sinpi(float a) { return sinpif(a); }
+MS_DEV double r_sinpi(double a) { return sinpi(a); }
+MS_DEV void r_sincos(float a, float* s, float* c) { sincosf(a, s, c); }
+MS_DEV void r_sincos(double a, double* s, double* c) { sincos(a, s, c); }
+#endif
+MS_DEV float r_exp(float a) { return expf(a); }
+MS_DEV double r_exp(double a) { return exp(a); }
+MS_DEV float r_pow(float a, float b) { return powf(a, b); }
+MS_DEV double r_pow(double a, double b) { return pow(a, b); }
+MS_DEV float r_tanh(float a) { return tanhf(a); }
+MS_DEV double r_tanh(double a) { return tanh(a); }
+MS_DEV float r_abs(float a) { return fabsf(a); }
+MS_DEV double r_abs(double a) { return fabs(a); }
+MS_DEV float r_max(float a, float b) { return fmaxf(a, b); }
+MS_DEV double r_max(double a, double b) { return fmax(a, b); }

@@ -1,67 +1,64 @@
 // ms_stage_api.inl -- C-ABI entry points of the non-spectral stages (include/microsound_b200.h).
-#include "ms_synth.cuh"
-#include "ms_time.cuh"
-#include "ms_fft_host.h"
 
 struct SynthNormalK { static constexpr int MAXT = SY_NTHR;
-    static MS_DEV void run(const SynthEvt* e, float* pool, const Ctx& c) { synth_normal_body(e, pool, c); } };
+    static MS_DEV void run(const SynthEvt* e, real* pool, const Ctx& c) { synth_normal_body(e, pool, c); } };
 struct SynthTiltK { static constexpr int MAXT = 256;
-    static MS_DEV void run(const SynthEvt* e, float* pool, const Ctx& c) { synth_tilt_finish_body(e, pool, c); } };
+    static MS_DEV void run(const SynthEvt* e, real* pool, const Ctx& c) { synth_tilt_finish_body(e, pool, c); } };
 struct SynthDustK { static constexpr int MAXT = 256;
-    static MS_DEV void run(const SynthEvt* e, const int* dp, const float* dv, float* pool, const Ctx& c) { synth_dust_body(e, dp, dv, pool, c); } };
+    static MS_DEV void run(const SynthEvt* e, const int* dp, const real* dv, real* pool, const Ctx& c) { synth_dust_body(e, dp, dv, pool, c); } };
 struct OlaK { static constexpr int MAXT = OLA_NTHR;
-    static MS_DEV void run(const OlaRender* r, const OlaEvt* e, const float* pool, float* mono, const Ctx& c) { ola_adsr_body(r, e, pool, mono, c); } };
+    static MS_DEV void run(const OlaRender* r, const OlaEvt* e, const real* pool, real* mono, const Ctx& c) { ola_adsr_body(r, e, pool, mono, c); } };
 struct FirBuildK { static constexpr int MAXT = OLA_NTHR;
-    static MS_DEV void run(const FirRender* r, const int* to, const float* tg, const float* ir, float* h, const Ctx& c) { fir_build_body(r, to, tg, ir, h, c); } };
+    static MS_DEV void run(const FirRender* r, const int* to, const real* tg, const real* ir, real* h, const Ctx& c) { fir_build_body(r, to, tg, ir, h, c); } };
 struct PostMaxK { static constexpr int MAXT = OLA_NTHR;
-    static MS_DEV void run(const PostRender* r, const float* mono, unsigned* mb, const Ctx& c) { post_max_body(r, mono, mb, c); } };
+    static MS_DEV void run(const PostRender* r, const real* mono, unsigned long long* mb, const Ctx& c) { post_max_body(r, mono, mb, c); } };
 struct PostWriteK { static constexpr int MAXT = OLA_NTHR;
-    static MS_DEV void run(const PostRender* r, const float* mono, const unsigned* mb, float2* out, const Ctx& c) { post_write_body(r, mono, mb, out, c); } };
+    static MS_DEV void run(const PostRender* r, const real* mono, const unsigned long long* mb, float2* out, const Ctx& c) { post_write_body(r, mono, mb, out, c); } };
 struct RollK { static constexpr int MAXT = 256;
-    static MS_DEV void run(const float* src, float* dst, int n, int shift, const Ctx& c) { roll_body(src, dst, n, shift, c); } };
+    static MS_DEV void run(const real* src, real* dst, int n, int shift, const Ctx& c) { roll_body(src, dst, n, shift, c); } };
 
 static inline MsDim mk_dim(unsigned x, unsigned y) { MsDim d; d.x = x; d.y = y; return d; }
 #define MS_FOR_Y_CHUNKS(total, body) for (int _y0 = 0; _y0 < (total); _y0 += 32768) { const int _yc = std::min(32768, (total) - _y0); body }
 
-extern "C" int ms_synth_normal(const ms_synth_evt* evts, int n, float* pool, void* stream) {
+extern "C" int MS_API(ms_synth_normal)(const ms_synth_evt* evts, int n, real* pool, void* stream) {
     for (int x0 = 0; x0 < n; x0 += 1 << 20) {
         const int cnt = std::min(1 << 20, n - x0);
         if (ms_launch<SynthNormalK>(mk_dim((unsigned)cnt, 1), SY_NTHR, sizeof(SynthSmem), (ms_stream_t)stream, evts + x0, pool)) return -1;
     }
     return 0;
 }
-extern "C" int ms_synth_tilt_finish(const ms_synth_evt* evts, int n, float* pool, void* stream) {
+extern "C" int MS_API(ms_synth_tilt_finish)(const ms_synth_evt* evts, int n, real* pool, void* stream) {
     MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthTiltK>(mk_dim(64, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, pool)) return -1; })
     return 0;
 }
-extern "C" int ms_synth_dust(const ms_synth_evt* evts, int n, const int32_t* dpos, const float* dval, float* pool, void* stream) {
+extern "C" int MS_API(ms_synth_dust)(const ms_synth_evt* evts, int n, const int32_t* dpos, const real* dval, real* pool, void* stream) {
     MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthDustK>(mk_dim(64, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, (const int*)dpos, dval, pool)) return -1; })
     return 0;
 }
-extern "C" int ms_overlap_add(const ms_ola_render* renders, int n_renders, int max_out_n, const ms_ola_evt* evts,
-                              const float* pool, float* mono, void* stream) {
+extern "C" int MS_API(ms_overlap_add)(const ms_ola_render* renders, int n_renders, int max_out_n, const ms_ola_evt* evts,
+                              const real* pool, real* mono, void* stream) {
     const unsigned gx = (unsigned)((max_out_n + OLA_TILE - 1) / OLA_TILE);
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<OlaK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream, renders + _y0, evts, pool, mono)) return -1; })
     return 0;
 }
-extern "C" int ms_fir_build(const ms_fir_render* renders, int n_renders, int max_h_len, const int32_t* tap_off,
-                            const float* tap_gain, const float* irpool, float* hpool, void* stream) {
+extern "C" int MS_API(ms_fir_build)(const ms_fir_render* renders, int n_renders, int max_h_len, const int32_t* tap_off,
+                            const real* tap_gain, const real* irpool, real* hpool, void* stream) {
     const unsigned gx = (unsigned)((max_h_len + OLA_TILE - 1) / OLA_TILE);
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<FirBuildK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, FIR_MAX_TAPS * 8, (ms_stream_t)stream,
                                    renders + _y0, (const int*)tap_off, tap_gain, irpool, hpool)) return -1; })
     return 0;
 }
-extern "C" int ms_post(const ms_post_render* renders, int n_renders, int max_n, const float* mono, uint32_t* maxbits,
+extern "C" int MS_API(ms_post)(const ms_post_render* renders, int n_renders, int max_n, const real* mono, uint64_t* maxbits,
                        float* out, void* stream) {
     const unsigned gx = (unsigned)((max_n + OLA_TILE - 1) / OLA_TILE);
-    if (ms_memset(maxbits, 0, sizeof(uint32_t) * (size_t)n_renders, (ms_stream_t)stream)) return -1;
-    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, OLA_NTHR * 4, (ms_stream_t)stream,
-                                   renders + _y0, mono, (unsigned*)maxbits + _y0)) return -1; })
+    if (ms_memset(maxbits, 0, sizeof(uint64_t) * (size_t)n_renders, (ms_stream_t)stream)) return -1;
+    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, OLA_NTHR * sizeof(real), (ms_stream_t)stream,
+                                   renders + _y0, mono, (unsigned long long*)maxbits + _y0)) return -1; })
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostWriteK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream,
-                                   renders + _y0, mono, (const unsigned*)maxbits + _y0, (float2*)out)) return -1; })
+                                   renders + _y0, mono, (const unsigned long long*)maxbits + _y0, (float2*)out)) return -1; })
     return 0;
 }
-extern "C" int ms_roll(const float* src, float* dst, int n, int shift, void* stream) {
+extern "C" int MS_API(ms_roll)(const real* src, real* dst, int n, int shift, void* stream) {
     return ms_launch<RollK>(mk_dim(64, 1), 256, 0, (ms_stream_t)stream, src, dst, n, shift);
 }
 
@@ -92,17 +89,17 @@ static int fir_layout(const ms_fir_render* r, int n, FirLayout& L) {
     L.hjobs_off = 0;
     L.cjobs_off = ms_align256(sizeof(FftJob) * (size_t)n);
     L.hspec_off = L.cjobs_off + ms_align256(sizeof(FftJob) * (size_t)ncj);
-    L.work_off = L.hspec_off + ms_align256(sizeof(float2) * hs);
-    L.total = L.work_off + ms_align256(sizeof(float2) * wk);
+    L.work_off = L.hspec_off + ms_align256(sizeof(cpx) * hs);
+    L.total = L.work_off + ms_align256(sizeof(cpx) * wk);
     return 0;
 }
-extern "C" size_t ms_fir_workspace_bytes(const ms_fir_render* r, int n) {
+extern "C" size_t MS_API(ms_fir_workspace_bytes)(const ms_fir_render* r, int n) {
     FirLayout L;
     if (n <= 0) return 256;
     if (fir_layout(r, n, L)) return 0;
     return L.total;
 }
-extern "C" int ms_fir_create(const ms_fir_render* r, int n, const float* hpool, const float* mono_in, float* mono_out,
+extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* hpool, const real* mono_in, real* mono_out,
                              void* ws, size_t ws_bytes, void* stream, void** handle) {
     *handle = nullptr;
     ms_stream_t st = (ms_stream_t)stream;
@@ -113,14 +110,14 @@ extern "C" int ms_fir_create(const ms_fir_render* r, int n, const float* hpool, 
     if (fir_layout(r, n, L)) { delete P; return -1; }
     if (ws_bytes < L.total) { delete P; MS_FAIL("ms_fir_create: workspace %zu < required %zu", ws_bytes, L.total); }
     char* base = (char*)ws;
-    float2* hspec = (float2*)(base + L.hspec_off);
-    float2* work = (float2*)(base + L.work_off);
+    cpx* hspec = (cpx*)(base + L.hspec_off);
+    cpx* work = (cpx*)(base + L.work_off);
     size_t wk = 0;
     for (int i = 0; i < n; ++i) {
         FftJob H; memset(&H, 0, sizeof H);
         if (FftEngine::get().prepare(H, L.B[i], st)) { delete P; return -1; }
         FftJob Cj = H;
-        H.n = r[i].h_len; H.in_a = hpool + r[i].h; H.work = hspec + L.hspec_at[i]; H.out_scale = 1.0f / (float)L.B[i];
+        H.n = r[i].h_len; H.in_a = hpool + r[i].h; H.work = hspec + L.hspec_at[i]; H.out_scale = (real)1.0 / (real)L.B[i];
         P->hjobs.push_back(H);
         const int hop = L.B[i] - r[i].h_len + 1;
         const int nblk = (r[i].out_n + hop - 1) / hop;
@@ -147,11 +144,11 @@ extern "C" int ms_fir_create(const ms_fir_render* r, int n, const float* hpool, 
     *handle = P;
     return 0;
 }
-extern "C" int ms_fir_run(void* handle, void* stream) {
+extern "C" int MS_API(ms_fir_run)(void* handle, void* stream) {
     FirPlan* P = (FirPlan*)handle;
     if (!P) MS_FAIL("ms_fir_run: null handle");
     if (P->hjobs.empty()) return 0;
     if (FftEngine::get().filter_spectrum(P->hjobs, P->hjobs_dev, (ms_stream_t)stream)) return -1;
     return FftEngine::get().overlap_save(P->cjobs, P->cjobs_dev, (ms_stream_t)stream);
 }
-extern "C" void ms_fir_destroy(void* handle) { delete (FirPlan*)handle; }
+extern "C" void MS_API(ms_fir_destroy)(void* handle) { delete (FirPlan*)handle; }

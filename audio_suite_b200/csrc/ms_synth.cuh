@@ -9,15 +9,6 @@
 // (S0 = fresh word, W = wedge test pending, T1+-/T2+- = tail loop).  Accepted normals go to a
 // shared staging buffer in stream order; the mode's closed-form terms (sine with float64 phase,
 // exponentials, fades) are applied on the way out with coalesced stores.
-#pragma once
-#include "ms_rt.cuh"
-#include "ms_zig_tables.h"
-#include "../../include/microsound_b200.h"
-#ifdef MS_HOST_EMUL
-#define MS_POPC(x) __builtin_popcount(x)
-#else
-#define MS_POPC(x) __popc(x)
-#endif
 
 enum { SY_GAUSS = 0, SY_DUST = 1, SY_NOISE = 2, SY_SKEW = 3, SY_RES = 4, SY_PLAIN = 5 };
 
@@ -143,11 +134,11 @@ MS_DEV ZigMap zm_compose(const ZigMap& f, const ZigMap& g) {
     return h;
 }
 
-MS_DEV float fade_gain(int j, int n, int fade, double inv_fade) {
-    float w = 1.f;
-    if (j < fade) w *= (float)((double)j * inv_fade);
+MS_DEV real fade_gain(int j, int n, int fade, double inv_fade) {
+    real w = (real)1.;
+    if (j < fade) w *= (real)((double)j * inv_fade);
     const int t = j - (n - fade);
-    if (t >= 0) w *= (float)(1.0 - (double)t * inv_fade);
+    if (t >= 0) w *= (real)(1.0 - (double)t * inv_fade);
     return w;
 }
 
@@ -158,7 +149,7 @@ struct SynthSmem {
     double fi[256];
     unsigned long long words[SY_W + 1];     // [0] = word before the round, then i-major: 1 + i*NTHR + t
     ZigMap scan[2][SY_NTHR];
-    float stage[SY_W + 8];
+    real stage[SY_W + 8];
     int carry_state, round_total, round_end_state, _pad;
 };
 MS_DEV unsigned long long sy_word(const SynthSmem* S, int p) {   // p in [-1, SY_W)
@@ -168,19 +159,19 @@ MS_DEV unsigned long long sy_word(const SynthSmem* S, int p) {   // p in [-1, SY
 }
 
 // mode-specific sample from normal z at index j
-MS_DEV float synth_sample(const SynthEvt& E, int j, float z) {
-    const float fj = (float)j;
-    float x;
+MS_DEV real synth_sample(const SynthEvt& E, int j, real z) {
+    const real fj = (real)j;
+    real x;
     if (E.mode == SY_GAUSS) {
-        const float q = fj / (float)E.sigma;
-        x = expf(-0.5f * q * q) * (z * 0.12f + 1.0f);
+        const real q = fj / (real)E.sigma;
+        x = r_exp(-(real)0.5 * q * q) * (z * (real)0.12 + (real)1.0);
     } else if (E.mode == SY_RES) {
         double cyc = (double)j * E.f_over_sr;
         cyc -= floor(cyc);
-        const float tone = sinpif(2.0f * (float)cyc) * expf(-fj * E.ring_decay);
-        x = 0.9f * tone + 0.25f * z * expf(-fj * E.env_decay);
+        const real tone = r_sinpi((real)2.0 * (real)cyc) * r_exp(-fj * (real)E.ring_decay);
+        x = (real)0.9 * tone + (real)0.25 * z * r_exp(-fj * (real)E.env_decay);
     } else if (E.mode == SY_PLAIN) {
-        x = z * 0.1f;
+        x = z * (real)0.1;
     } else {
         return z;           // SY_NOISE / SY_SKEW: raw normals, shaped later
     }
@@ -188,7 +179,7 @@ MS_DEV float synth_sample(const SynthEvt& E, int j, float z) {
 }
 
 // One CTA per event.  blockDim.x must be SY_NTHR.
-MS_DEV void synth_normal_body(const SynthEvt* MS_RESTRICT evts, float* MS_RESTRICT pool, const Ctx& c) {
+MS_DEV void synth_normal_body(const SynthEvt* MS_RESTRICT evts, real* MS_RESTRICT pool, const Ctx& c) {
     const SynthEvt E = evts[c.bx];
     if (E.mode == SY_DUST) return;
     SynthSmem* S = (SynthSmem*)c.smem;
@@ -206,7 +197,7 @@ MS_DEV void synth_normal_body(const SynthEvt* MS_RESTRICT evts, float* MS_RESTRI
     pcg_jump_consts(inc, (unsigned long long)(c.tid * SY_C), &jm, &jp);
     st = u128_add(u128_mul(st, jm), jp);
     pcg_jump_consts(inc, (unsigned long long)(SY_W - SY_C), &jm, &jp);
-    float* out = pool + E.out;
+    real* out = pool + E.out;
     int out_base = 0;
     c.sync();
     const int max_rounds = (int)((2ll * E.n) / SY_W) + 64;
@@ -263,7 +254,7 @@ MS_DEV void synth_normal_body(const SynthEvt* MS_RESTRICT evts, float* MS_RESTRI
         s = my_state;
         for (int i = 0; i < SY_C; ++i) {
             s = zig_step(s, sy_word(S, p0 + i - 1), sy_word(S, p0 + i), T, &em, &val);
-            if (em) S->stage[my_off++] = (float)val;
+            if (em) S->stage[my_off++] = (real)val;
         }
         c.sync();
         const int total = S->round_total;
@@ -277,42 +268,42 @@ MS_DEV void synth_normal_body(const SynthEvt* MS_RESTRICT evts, float* MS_RESTRI
 }
 
 // Finalize for the tilted-noise modes (main_v2.py:246-255): one thread per sample.
-MS_DEV void synth_tilt_finish_body(const SynthEvt* MS_RESTRICT evts, float* MS_RESTRICT pool, const Ctx& c) {
+MS_DEV void synth_tilt_finish_body(const SynthEvt* MS_RESTRICT evts, real* MS_RESTRICT pool, const Ctx& c) {
     const SynthEvt E = evts[c.by];
     if (E.mode != SY_NOISE && E.mode != SY_SKEW) return;
-    const float* t = pool + E.aux;
-    float* out = pool + E.out;
+    const real* t = pool + E.aux;
+    real* out = pool + E.out;
     for (int j = c.bx * c.nthr + c.tid; j < E.n; j += c.nthr * 64) {   // gridDim.x == 64
-        float v = t[j];
+        real v = t[j];
         if (E.mode == SY_SKEW) {
-            const float a = v > 0.f ? v : 0.f;
-            const float pv = j > 0 ? t[j - 1] : v;
-            const float b = pv > 0.f ? pv : 0.f;
+            const real a = v > (real)0. ? v : (real)0.;
+            const real pv = j > 0 ? t[j - 1] : v;
+            const real b = pv > (real)0. ? pv : (real)0.;
             v = a - b;
         }
-        out[j] = v * expf(-(float)j * E.env_decay) * fade_gain(j, E.n, E.fade, E.inv_fade);
+        out[j] = v * r_exp(-(real)j * (real)E.env_decay) * fade_gain(j, E.n, E.fade, E.inv_fade);
     }
 }
 
 // Dust impulses (main_v2.py:239-245): sparse impulses convolved ("same") with exp(-linspace(0,6,K)).
-MS_DEV void synth_dust_body(const SynthEvt* MS_RESTRICT evts, const int* MS_RESTRICT dpos, const float* MS_RESTRICT dval,
-                            float* MS_RESTRICT pool, const Ctx& c) {
+MS_DEV void synth_dust_body(const SynthEvt* MS_RESTRICT evts, const int* MS_RESTRICT dpos, const real* MS_RESTRICT dval,
+                            real* MS_RESTRICT pool, const Ctx& c) {
     const SynthEvt E = evts[c.by];
     if (E.mode != SY_DUST) return;
     const int* pos = dpos + E.dust_begin;
-    const float* val = dval + E.dust_begin;
-    float* out = pool + E.out;
+    const real* val = dval + E.dust_begin;
+    real* out = pool + E.out;
     const int K = E.ker_len, ctr = (K - 1) / 2;
-    const float rate = 6.0f / (float)(K - 1);
+    const real rate = (real)6.0 / (real)(K - 1);
     for (int j = c.bx * c.nthr + c.tid; j < E.n; j += c.nthr * 64) {
         const int hi = j + ctr;            // impulses p with hi-K < p <= hi contribute ker[hi-p]
         int lo_i = 0, hi_i = E.dust_count; // first index with pos > hi - K
         while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (__ldg(&pos[mid]) > hi - K) hi_i = mid; else lo_i = mid + 1; }
-        float acc = 0.f;
+        real acc = (real)0.;
         for (int q = lo_i; q < E.dust_count; ++q) {
             const int p = __ldg(&pos[q]);
             if (p > hi) break;
-            acc += __ldg(&val[q]) * expf(-rate * (float)(hi - p));
+            acc += __ldg(&val[q]) * r_exp(-rate * (real)(hi - p));
         }
         out[j] = acc * fade_gain(j, E.n, E.fade, E.inv_fade);
     }

@@ -1,9 +1,6 @@
 // ms_time.cuh -- time-domain stages of render(): overlap-add placement + ADSR (main_v2.py:742-764,
 // 172-195), the reflection-cloud / impulse-response FIR builder (main_v2.py:409-421, 438-445), and the
 // stereo / soft-clip / normalise tail (main_v2.py:423-436, 31-34, 26-29, 775-781).
-#pragma once
-#include "ms_rt.cuh"
-#include "../../include/microsound_b200.h"
 
 #define OLA_TILE 1024
 #define OLA_NTHR 256
@@ -14,18 +11,20 @@
 typedef ms_ola_render OlaRender;
 typedef ms_ola_evt OlaEvt;
 
-MS_DEV float adsr_gain(const OlaRender& R, int i) {
-    if (i < R.A) return powf((float)((double)i * R.inv_A), R.curve);
-    if (i < R.D_end) return 1.0f - (1.0f - R.S) * powf((float)((double)(i - R.A) * R.inv_D), R.curve);
-    if (i < R.sus_end || !R.has_release) return R.S;
-    const float r = (i == R.out_n - 1 && R.out_n - R.sus_end > 1) ? 1.0f : (float)((double)(i - R.sus_end) * R.inv_R);
-    return R.S * (1.0f - powf(r, R.curve));
+
+MS_DEV real adsr_gain(const OlaRender& R, int i) {
+    const real S = (real)R.S, curve = (real)R.curve;
+    if (i < R.A) return r_pow((real)((double)i * R.inv_A), curve);
+    if (i < R.D_end) return (real)1.0 - ((real)1.0 - S) * r_pow((real)((double)(i - R.A) * R.inv_D), curve);
+    if (i < R.sus_end || !R.has_release) return S;
+    const real r = (i == R.out_n - 1 && R.out_n - R.sus_end > 1) ? (real)1.0 : (real)((double)(i - R.sus_end) * R.inv_R);
+    return S * ((real)1.0 - r_pow(r, curve));
 }
 
 // grid = (ceil(max out_n / OLA_TILE), renders), block = OLA_NTHR.  Gather form: every output sample
 // sums the events that cover it, in event order, so no atomics and each output is written once.
 MS_DEV void ola_adsr_body(const OlaRender* MS_RESTRICT renders, const OlaEvt* MS_RESTRICT evts,
-                          const float* MS_RESTRICT pool, float* MS_RESTRICT mono, const Ctx& c) {
+                          const real* MS_RESTRICT pool, real* MS_RESTRICT mono, const Ctx& c) {
     const OlaRender R = renders[c.by];
     const int t0 = c.bx * OLA_TILE;
     if (t0 >= R.out_n) return;
@@ -37,13 +36,13 @@ MS_DEV void ola_adsr_body(const OlaRender* MS_RESTRICT renders, const OlaEvt* MS
     lo = R.ev_begin; hi = eb;
     while (lo < hi) { const int m = (lo + hi) >> 1; if (evts[m].start > t0 - R.max_len) hi = m; else lo = m + 1; }
     const int ea = lo;
-    float* out = mono + R.out;
+    real* out = mono + R.out;
     for (int i = t0 + c.tid; i < t1; i += c.nthr) {
-        float acc = 0.f;
+        real acc = (real)0.;
         for (int e = ea; e < eb; ++e) {
             const int st = __ldg(&evts[e].start), ln = __ldg(&evts[e].len);
             const int k = i - st;
-            if (k >= 0 && k < ln) acc += __ldg(&evts[e].amp) * __ldg(&pool[evts[e].grain + k]);
+            if (k >= 0 && k < ln) acc += (real)__ldg(&evts[e].amp) * __ldg(&pool[evts[e].grain + k]);
         }
         out[i] = acc * adsr_gain(R, i);
     }
@@ -52,21 +51,21 @@ MS_DEV void ola_adsr_body(const OlaRender* MS_RESTRICT renders, const OlaEvt* MS
 // ---- FIR builder: h = ir + sum_t g_t * delay(ir, off_t)   (reflection cloud folded into the IR) ------
 typedef ms_fir_render FirRender;
 #define FIR_MAX_TAPS 4096
-MS_DEV void fir_build_body(const FirRender* MS_RESTRICT renders, const int* MS_RESTRICT tap_off, const float* MS_RESTRICT tap_gain,
-                           const float* MS_RESTRICT irpool, float* MS_RESTRICT hpool, const Ctx& c) {
+MS_DEV void fir_build_body(const FirRender* MS_RESTRICT renders, const int* MS_RESTRICT tap_off, const real* MS_RESTRICT tap_gain,
+                           const real* MS_RESTRICT irpool, real* MS_RESTRICT hpool, const Ctx& c) {
     const FirRender R = renders[c.by];
     const int m0 = c.bx * OLA_TILE;
     if (m0 >= R.h_len) return;
     int* s_off = (int*)c.smem;
-    float* s_gain = (float*)(s_off + FIR_MAX_TAPS);
+    real* s_gain = (real*)(s_off + FIR_MAX_TAPS);
     const int ntap = R.tap_end - R.tap_begin;
     for (int t = c.tid; t < ntap; t += c.nthr) { s_off[t] = tap_off[R.tap_begin + t]; s_gain[t] = tap_gain[R.tap_begin + t]; }
     c.sync();
-    const float* ir = irpool + R.ir;
-    float* h = hpool + R.h;
+    const real* ir = irpool + R.ir;
+    real* h = hpool + R.h;
     const int m1 = (m0 + OLA_TILE) < R.h_len ? (m0 + OLA_TILE) : R.h_len;
     for (int m = m0 + c.tid; m < m1; m += c.nthr) {
-        float acc = m < R.ir_len ? __ldg(&ir[m]) : 0.f;
+        real acc = m < R.ir_len ? __ldg(&ir[m]) : (real)0.;
         for (int t = 0; t < ntap; ++t) {
             const int k = m - s_off[t];
             if (k >= 0 && k < R.ir_len) acc += s_gain[t] * __ldg(&ir[k]);
@@ -78,67 +77,68 @@ MS_DEV void fir_build_body(const FirRender* MS_RESTRICT renders, const int* MS_R
 // ---- stereo diffusion + soft clip + normalise -----------------------------------------------------------
 typedef ms_post_render PostRender;
 MS_DEV int wrap_idx(long long i, int n) { long long r = i % n; if (r < 0) r += n; return (int)r; }
-MS_DEV float right_sample(const PostRender& R, const float* MS_RESTRICT y, const float* MS_RESTRICT mono, int i) {
+MS_DEV real right_sample(const PostRender& R, const real* MS_RESTRICT y, const real* MS_RESTRICT mono, int i) {
     if (R.stereo_mode == 0) return y[i];
     if (R.stereo_mode == 2) return mono[R.rbuf + i];
-    float acc = 0.f;
+    real acc = (real)0.;
     int idx = wrap_idx((long long)i + R.dr - 2 * POST_K, R.n);
 #pragma unroll
     for (int m = 0; m < POST_NC; ++m) {
-        acc += R.coef[m] * __ldg(&y[idx]);
+        acc += (real)R.coef[m] * __ldg(&y[idx]);
         idx += 2; if (idx >= R.n) idx -= R.n;
     }
     return acc;
 }
-MS_DEV float soft_clip(float v, float drive, float inv_t) { return drive > 0.f ? tanhf(v * drive) * inv_t : v; }
+MS_DEV real soft_clip(real v, real drive, real inv_t) { return drive > (real)0. ? r_tanh(v * drive) * inv_t : v; }
 
 // pass 1: per-render max(|L|, |R|) before the clip (tanh is monotonic, so the clipped max follows)
-MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, const float* MS_RESTRICT mono, unsigned* MS_RESTRICT maxbits, const Ctx& c) {
+MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, const real* MS_RESTRICT mono, unsigned long long* MS_RESTRICT maxbits, const Ctx& c) {
     const PostRender R = renders[c.by];
     const int t0 = c.bx * OLA_TILE;
     if (t0 >= R.n) return;
     const int t1 = (t0 + OLA_TILE) < R.n ? (t0 + OLA_TILE) : R.n;
-    const float* y = mono + R.y;
-    float m = 0.f;
+    const real* y = mono + R.y;
+    real m = (real)0.;
     for (int i = t0 + c.tid; i < t1; i += c.nthr) {
-        m = fmaxf(m, fabsf(y[i]));
-        if (R.stereo_mode) m = fmaxf(m, fabsf(right_sample(R, y, mono, i)));
+        m = r_max(m, r_abs(y[i]));
+        if (R.stereo_mode) m = r_max(m, r_abs(right_sample(R, y, mono, i)));
     }
-    float* red = (float*)c.smem;
+    real* red = (real*)c.smem;
     red[c.tid] = m;
     c.sync();
     for (int s = c.nthr >> 1; s > 0; s >>= 1) {
-        if (c.tid < s) red[c.tid] = fmaxf(red[c.tid], red[c.tid + s]);
+        if (c.tid < s) red[c.tid] = r_max(red[c.tid], red[c.tid + s]);
         c.sync();
     }
     if (c.tid == 0) {
-        union { float f; unsigned u; } cv; cv.f = red[0];
+        union { double f; unsigned long long u; } cv; cv.f = (double)red[0];
 #ifdef MS_HOST_EMUL
         if (cv.u > maxbits[c.by]) maxbits[c.by] = cv.u;
 #else
-        atomicMax(&maxbits[c.by], cv.u);       // non-negative floats order like their bit patterns
+        atomicMax(&maxbits[c.by], cv.u);       // non-negative doubles order like their bit patterns
 #endif
     }
 }
 // pass 2: write interleaved stereo, clipped and scaled to the requested peak
-MS_DEV void post_write_body(const PostRender* MS_RESTRICT renders, const float* MS_RESTRICT mono, const unsigned* MS_RESTRICT maxbits,
+MS_DEV void post_write_body(const PostRender* MS_RESTRICT renders, const real* MS_RESTRICT mono, const unsigned long long* MS_RESTRICT maxbits,
                             float2* MS_RESTRICT out, const Ctx& c) {
     const PostRender R = renders[c.by];
     const int t0 = c.bx * OLA_TILE;
     if (t0 >= R.n) return;
     const int t1 = (t0 + OLA_TILE) < R.n ? (t0 + OLA_TILE) : R.n;
-    const float* y = mono + R.y;
-    union { float f; unsigned u; } cv; cv.u = maxbits[c.by];
-    const float top = soft_clip(cv.f, R.drive, R.inv_tanh_drive);
-    const float scale = top > 0.f ? R.peak / top : 1.0f;
+    const real* y = mono + R.y;
+    union { double f; unsigned long long u; } cv; cv.u = maxbits[c.by];
+    const real drive = (real)R.drive, inv_t = (real)R.inv_tanh_drive;
+    const real top = soft_clip((real)cv.f, drive, inv_t);
+    const real scale = top > (real)0. ? (real)R.peak / top : (real)1.0;
     float2* o = out + R.out;
     for (int i = t0 + c.tid; i < t1; i += c.nthr) {
-        const float l = R.stereo_mode ? y[wrap_idx((long long)i - R.dl, R.n)] : y[i];
-        const float r = right_sample(R, y, mono, i);
-        o[i] = make_float2(soft_clip(l, R.drive, R.inv_tanh_drive) * scale, soft_clip(r, R.drive, R.inv_tanh_drive) * scale);
+        const real l = R.stereo_mode ? y[wrap_idx((long long)i - R.dl, R.n)] : y[i];
+        const real r = right_sample(R, y, mono, i);
+        o[i] = make_float2((float)(soft_clip(l, drive, inv_t) * scale), (float)(soft_clip(r, drive, inv_t) * scale));
     }
 }
 // circular shift used by the odd-length stereo path: dst[i] = src[(i + shift) mod n]
-MS_DEV void roll_body(const float* MS_RESTRICT src, float* MS_RESTRICT dst, int n, int shift, const Ctx& c) {
+MS_DEV void roll_body(const real* MS_RESTRICT src, real* MS_RESTRICT dst, int n, int shift, const Ctx& c) {
     for (int i = c.bx * c.nthr + c.tid; i < n; i += c.nthr * 64) dst[i] = src[wrap_idx((long long)i + shift, n)];
 }

@@ -41,8 +41,8 @@ class CudaDevice:
         return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
 
     def empty(self, n, dtype):
-        t = {np.float32: self.torch.float32, np.uint8: self.torch.uint8, np.int32: self.torch.int32,
-             np.uint32: self.torch.int32}[dtype]
+        t = {np.float32: self.torch.float32, np.float64: self.torch.float64, np.uint8: self.torch.uint8,
+             np.int32: self.torch.int32, np.uint64: self.torch.int64}[dtype]
         return self.torch.empty(max(1, int(n)), dtype=t, device=self.dev)
 
     def zeros(self, n, dtype):
@@ -60,7 +60,7 @@ class CudaDevice:
         return C.c_void_p(buf.data_ptr())
 
     def download(self, buf, offset, count):
-        """float32 slice -> numpy"""
+        """slice of a device buffer -> numpy"""
         return buf[offset:offset + count].cpu().numpy()
 
     def synchronize(self):
@@ -70,6 +70,18 @@ class CudaDevice:
 def _check(dev, rc):
     if rc != 0:
         raise RuntimeError("microsound_b200: " + (dev.lib.ms_last_error() or b"unknown error").decode())
+
+
+def choose_precision(plans):
+    """'auto' precision rule.  The soft clip (main_v2.py:31-34) follows the FIR stage; with an impulse
+    response or a reflection cloud the pre-clip peak is routinely 10^2..10^3, and tanh's unit slope at
+    every zero crossing turns float32's ~3e-7 relative-to-peak error into 1e-5..1e-4 absolute error.
+    Renders with a FIR stage and a soft clip therefore run the float64 build; the rest run float32."""
+    for rp in plans:
+        has_fir = rp.ir is not None or (rp.er_offs is not None and rp.er_offs.size > 0)
+        if has_fir and rp.drive > 0:
+            return "f64"
+    return "f32"
 
 
 def _recs(ctype, n):
@@ -118,25 +130,25 @@ def _pair_jobs(items):
 
 
 class _SpectralStage:
-    def __init__(self, dev, jobs, src, dst):
-        self.dev, self.handle, self.njobs = dev, C.c_void_p(None), len(jobs)
+    def __init__(self, dev, api, jobs, src, dst):
+        self.dev, self.api, self.handle, self.njobs = dev, api, C.c_void_p(None), len(jobs)
         if not jobs:
             return
         arr = (_abi.SpecJob * len(jobs))(*jobs)
-        need = dev.lib.ms_spectral_workspace_bytes(C.addressof(arr), len(jobs))
+        need = api.ms_spectral_workspace_bytes(C.addressof(arr), len(jobs))
         if need == 0:
             _check(dev, -1)
         self.ws = dev.empty(need, np.uint8)
-        _check(dev, dev.lib.ms_spectral_create(C.addressof(arr), len(jobs), dev.ptr(src), dev.ptr(dst),
-                                               dev.ptr(self.ws), need, dev.stream_ptr(), C.byref(self.handle)))
+        _check(dev, api.ms_spectral_create(C.addressof(arr), len(jobs), dev.ptr(src), dev.ptr(dst),
+                                           dev.ptr(self.ws), need, dev.stream_ptr(), C.byref(self.handle)))
 
     def run(self):
         if self.njobs:
-            _check(self.dev, self.dev.lib.ms_spectral_run(self.handle, self.dev.stream_ptr()))
+            _check(self.dev, self.api.ms_spectral_run(self.handle, self.dev.stream_ptr()))
 
     def close(self):
         if self.handle:
-            self.dev.lib.ms_spectral_destroy(self.handle)
+            self.api.ms_spectral_destroy(self.handle)
             self.handle = C.c_void_p(None)
 
 
@@ -144,14 +156,17 @@ class BatchRenderer:
     """Plans a batch of independent renders once, keeps every table resident on the device and
     re-runs the kernel sequence on demand (`run()`), e.g. for benchmarking or repeated renders."""
 
-    def __init__(self, params_list, device=None, keep_micro=True):
+    def __init__(self, params_list, device=None, precision="auto"):
         self.dev = device or CudaDevice()
         self.plans = [P.plan_render(p) for p in params_list]
+        self.precision = choose_precision(self.plans) if precision == "auto" else precision
+        self.api = _abi.Api(self.dev.lib, self.precision)
+        self.real = np.float32 if self.precision == "f32" else np.float64
         self._pack()
 
     # ---- layout + tables ---------------------------------------------------------------------------
     def _pack(self):
-        dev, plans = self.dev, self.plans
+        dev, plans, real = self.dev, self.plans, self.real
         n_evt = sum(len(rp.events) for rp in plans)
         R = len(plans)
         sy1 = _recs(_abi.SynthEvt, n_evt)            # stage 1 (normals / closed form / dust)
@@ -237,13 +252,13 @@ class BatchRenderer:
                     key = rp.ir.tobytes()
                     if key not in ir_index:
                         ir_index[key] = (sum(len(x) for x in ir_chunks), rp.ir.size)
-                        ir_chunks.append(rp.ir.astype(np.float32))
+                        ir_chunks.append(rp.ir.astype(real))
                     ir_at, ir_len = ir_index[key]
                 else:
                     key = b"delta"
                     if key not in ir_index:
                         ir_index[key] = (sum(len(x) for x in ir_chunks), 1)
-                        ir_chunks.append(np.ones(1, np.float32))
+                        ir_chunks.append(np.ones(1, real))
                     ir_at, ir_len = ir_index[key]
                 f = _abi.FirRender()
                 f.ir, f.ir_len = ir_at, ir_len
@@ -252,7 +267,7 @@ class BatchRenderer:
                     if rp.er_offs.size > 4096:
                         raise ValueError("er_taps > 4096 is outside the accelerated path")
                     tap_off.append(rp.er_offs)
-                    tap_gain.append(rp.er_gains.astype(np.float32))
+                    tap_gain.append(rp.er_gains.astype(real))
                     f.h_len = ir_len + int(rp.er_offs.max())
                 else:
                     f.h_len = ir_len
@@ -280,7 +295,7 @@ class BatchRenderer:
                 pr["dl"], pr["dr"] = rp.stereo_dl, rp.stereo_dr
                 if n % 2 == 0:
                     pr["stereo_mode"] = 1
-                    pr["coef"] = _bessel_coeffs(rp.stereo_theta).astype(np.float32)
+                    pr["coef"] = _bessel_coeffs(rp.stereo_theta)
                 else:
                     pr["stereo_mode"] = 2
                     pr["rbuf"] = 2 * plane + extra + n          # [rolled copy | right channel]
@@ -299,10 +314,10 @@ class BatchRenderer:
         self.pool_n, self.mono_n = pool_n, 2 * plane + extra
 
         # ---- device buffers
-        self.pool = dev.empty(pool_n, np.float32)
-        self.mono = dev.zeros(self.mono_n, np.float32)
+        self.pool = dev.empty(pool_n, real)
+        self.mono = dev.zeros(self.mono_n, real)
         self.out = dev.empty(2 * frames, np.float32)
-        self.maxbits = dev.zeros(R, np.uint32)
+        self.maxbits = dev.zeros(R, np.uint64)
         self.d_sy1, self.d_sy2 = dev.upload(sy1), dev.upload(sy2)
         ola_e_arr = _recs(_abi.OlaEvt, len(ola_e))
         for i, (g, s, ln, amp) in enumerate(ola_e):
@@ -311,10 +326,10 @@ class BatchRenderer:
         self.d_post = dev.upload(post_r)
         if any_dust:
             self.d_dpos = dev.upload(np.concatenate(dust_pos).astype(np.int32))
-            self.d_dval = dev.upload(np.concatenate(dust_val).astype(np.float32))
+            self.d_dval = dev.upload(np.concatenate(dust_val).astype(real))
         # spectral stages
-        self.tilt_stage = _SpectralStage(dev, _pair_jobs(tilt_items), self.pool, self.pool)
-        self.grain_stage = _SpectralStage(dev, _pair_jobs(grain_items), self.pool, self.pool)
+        self.tilt_stage = _SpectralStage(dev, self.api, _pair_jobs(tilt_items), self.pool, self.pool)
+        self.grain_stage = _SpectralStage(dev, self.api, _pair_jobs(grain_items), self.pool, self.pool)
         # FIR
         self.fir_handle = C.c_void_p(None)
         self.n_fir = len(fir_r)
@@ -323,15 +338,15 @@ class BatchRenderer:
             self.fir_arr = arr
             self.d_fir = dev.upload(np.frombuffer(bytes(arr), dtype=np.uint8))
             self.d_tap_off = dev.upload(np.concatenate(tap_off).astype(np.int32) if tap_off else np.zeros(1, np.int32))
-            self.d_tap_gain = dev.upload(np.concatenate(tap_gain).astype(np.float32) if tap_gain else np.zeros(1, np.float32))
-            self.d_ir = dev.upload(np.concatenate(ir_chunks).astype(np.float32))
-            self.hpool = dev.empty(h_total, np.float32)
+            self.d_tap_gain = dev.upload(np.concatenate(tap_gain).astype(real) if tap_gain else np.zeros(1, real))
+            self.d_ir = dev.upload(np.concatenate(ir_chunks).astype(real))
+            self.hpool = dev.empty(h_total, real)
             self.max_h = max_h
-            need = dev.lib.ms_fir_workspace_bytes(C.addressof(arr), len(fir_r))
+            need = self.api.ms_fir_workspace_bytes(C.addressof(arr), len(fir_r))
             if need == 0:
                 _check(dev, -1)
             self.fir_ws = dev.empty(need, np.uint8)
-            _check(dev, dev.lib.ms_fir_create(C.addressof(arr), len(fir_r), dev.ptr(self.hpool), dev.ptr(self.mono),
+            _check(dev, self.api.ms_fir_create(C.addressof(arr), len(fir_r), dev.ptr(self.hpool), dev.ptr(self.mono),
                                               dev.ptr(self.mono), dev.ptr(self.fir_ws), need, dev.stream_ptr(),
                                               C.byref(self.fir_handle)))
         # odd-length stereo: rolled copy -> rotation through the spectral engine -> right channel
@@ -340,11 +355,11 @@ class BatchRenderer:
             op = _abi.SpecOp()
             op.kind, op.alpha = _abi.OP_ROT, theta
             rot_items.append((n, scratch, scratch + n, op))
-        self.rot_stage = _SpectralStage(dev, _pair_jobs(rot_items), self.mono, self.mono)
+        self.rot_stage = _SpectralStage(dev, self.api, _pair_jobs(rot_items), self.mono, self.mono)
 
     # ---- execution -------------------------------------------------------------------------------------
     def run(self):
-        dev, lib = self.dev, self.dev.lib
+        dev, lib = self.dev, self.api
         st = dev.stream_ptr()
         if self.n_evt:
             _check(dev, lib.ms_synth_normal(dev.ptr(self.d_sy1), self.n_evt, dev.ptr(self.pool), st))
@@ -362,9 +377,9 @@ class BatchRenderer:
                                          dev.ptr(self.d_tap_gain), dev.ptr(self.d_ir), dev.ptr(self.hpool), st))
             _check(dev, lib.ms_fir_run(self.fir_handle, st))
         if self.odd_stereo:
-            base = dev.ptr(self.mono).value
+            base, isz = dev.ptr(self.mono).value, np.dtype(self.real).itemsize
             for (r, scratch, n, dr, theta) in self.odd_stereo:
-                _check(dev, lib.ms_roll(C.c_void_p(base + 4 * self.y_at[r]), C.c_void_p(base + 4 * scratch), n, dr, st))
+                _check(dev, lib.ms_roll(C.c_void_p(base + isz * self.y_at[r]), C.c_void_p(base + isz * scratch), n, dr, st))
             self.rot_stage.run()
         _check(dev, lib.ms_post(dev.ptr(self.d_post), self.n_renders, self.max_out_n, dev.ptr(self.mono),
                                 dev.ptr(self.maxbits), dev.ptr(self.out), st))
@@ -392,7 +407,7 @@ class BatchRenderer:
         for s in (self.tilt_stage, self.grain_stage, self.rot_stage):
             s.close()
         if self.fir_handle:
-            self.dev.lib.ms_fir_destroy(self.fir_handle)
+            self.api.ms_fir_destroy(self.fir_handle)
             self.fir_handle = C.c_void_p(None)
 
     def __del__(self):
@@ -402,9 +417,9 @@ class BatchRenderer:
             pass
 
 
-def render(params, progress=None, device=None):
+def render(params, progress=None, device=None, precision="auto"):
     """Drop-in for reference render() (main_v2.py:588-792)."""
-    br = BatchRenderer([params], device=device)
+    br = BatchRenderer([params], device=device, precision=precision)
     rp = br.plans[0]
     if progress:
         progress(0, f"Output SR {rp.base_sr} Hz | Design SR {rp.design_sr_base} Hz")
@@ -422,9 +437,9 @@ def render(params, progress=None, device=None):
     return audio, meta
 
 
-def render_batch(params_list, device=None):
+def render_batch(params_list, device=None, precision="auto"):
     """Independent renders as one batched launch sequence.  Returns a list of float32 [out_n, 2]."""
-    br = BatchRenderer(params_list, device=device)
+    br = BatchRenderer(params_list, device=device, precision=precision)
     br.run()
     outs = [br.output(r) for r in range(br.n_renders)]
     br.close()

@@ -203,7 +203,7 @@ class EventPlan:
     spec: Optional[object] = None           # _abi.SpecOp or None
     tilt: Optional[object] = None           # _abi.SpecOp for the tilted-noise modes
     dust_pos: Optional[np.ndarray] = None   # sorted unique impulse positions (int32)
-    dust_val: Optional[np.ndarray] = None   # float32 values (last write wins, M:243)
+    dust_val: Optional[np.ndarray] = None   # float64 values (last write wins, M:243)
     # mode constants (float64)
     f_over_sr: float = 0.0
     ring_decay: float = 0.0                 # 1 / (tau * gen_sr)
@@ -364,5 +364,5 @@ def _plan_dust(ev, density):
     dense[where] = vals                                  # duplicates: last write wins
     pos = np.unique(where)
     ev.dust_pos = pos.astype(np.int32)
-    ev.dust_val = dense[pos].astype(np.float32)
+    ev.dust_val = dense[pos]
     ev.ker_len = max(8, int(0.01 * n))

@@ -63,19 +63,16 @@ typedef struct {
 } ms_spec_job;
 
 /* One-shot: plan + run + release. */
-size_t ms_spectral_workspace_bytes(const ms_spec_job* host_jobs, int njobs);
-int ms_spectral_apply(const ms_spec_job* host_jobs, int njobs, const float* src, float* dst,
-                      void* workspace, size_t workspace_bytes, void* stream);
+/* ms_spectral_workspace_bytes_f32 / ms_spectral_workspace_bytes_f64: declared below by MS_DECLARE_API */
+/* ms_spectral_apply_f32 / ms_spectral_apply_f64: declared below by MS_DECLARE_API */
 /* Planned: job descriptors are uploaded into `workspace` once; ms_spectral_run() only launches kernels
  * (CUDA-graph capturable).  src/dst/workspace must stay valid for the life of the handle. */
-int ms_spectral_create(const ms_spec_job* host_jobs, int njobs, const float* src, float* dst,
-                       void* workspace, size_t workspace_bytes, void* stream, void** handle);
-int ms_spectral_run(void* handle, void* stream);
-void ms_spectral_destroy(void* handle);
+/* ms_spectral_create_f32 / ms_spectral_create_f64: declared below by MS_DECLARE_API */
+/* ms_spectral_run_f32 / ms_spectral_run_f64: declared below by MS_DECLARE_API */
+/* ms_spectral_destroy_f32 / ms_spectral_destroy_f64: declared below by MS_DECLARE_API */
 /* test entry: Z[k] = sum_j (a[j] + i b[j]) exp(-2 pi i jk/n), interleaved re/im, natural order */
-int ms_fft_pair_forward(const float* a, const float* b, int n, float* z_out,
-                        void* workspace, size_t workspace_bytes, void* stream);
-size_t ms_fft_pair_workspace_bytes(int n);
+/* ms_fft_pair_forward_f32 / ms_fft_pair_forward_f64: declared below by MS_DECLARE_API */
+/* ms_fft_pair_workspace_bytes_f32 / ms_fft_pair_workspace_bytes_f64: declared below by MS_DECLARE_API */
 
 /* ---- transient synthesis: gen_basic (main_v2.py:219-269).  One record per event; the array lives in
  *      DEVICE memory.  The PCG64 state is numpy's `PCG64(seed).state` right after seeding. */
@@ -87,18 +84,17 @@ typedef struct {
     int64_t out;              /* offset into the float pool where this event's signal is written */
     double f_over_sr;         /* MS_SY_RES: max(10, ring_hz) / gen_sr */
     double inv_fade;          /* 1 / fade */
-    float ring_decay;         /* MS_SY_RES: 1 / (tau * gen_sr) */
-    float env_decay;          /* 1 / (T * gen_sr) of the mode's exponential envelope */
+    double ring_decay;        /* MS_SY_RES: 1 / (tau * gen_sr) */
+    double env_decay;         /* 1 / (T * gen_sr) of the mode's exponential envelope */
     int64_t dust_begin;       /* MS_SY_DUST: range in the impulse arrays */
     int32_t dust_count, ker_len;
     int64_t aux;              /* MS_SY_NOISE / MS_SY_SKEW: pool offset of the tilted noise */
 } ms_synth_evt;
 /* normals + closed-form modes (GAUSS, RES, PLAIN) and raw normals for NOISE/SKEW (written at `out`) */
-int ms_synth_normal(const ms_synth_evt* dev_evts, int n_evts, float* pool, void* stream);
-int ms_synth_dust(const ms_synth_evt* dev_evts, int n_evts, const int32_t* dust_pos, const float* dust_val,
-                  float* pool, void* stream);
+/* ms_synth_normal_f32 / ms_synth_normal_f64: declared below by MS_DECLARE_API */
+/* ms_synth_dust_f32 / ms_synth_dust_f64: declared below by MS_DECLARE_API */
 /* NOISE / SKEW: envelope, rectified difference and fades applied to the tilted noise at `aux` */
-int ms_synth_tilt_finish(const ms_synth_evt* dev_evts, int n_evts, float* pool, void* stream);
+/* ms_synth_tilt_finish_f32 / ms_synth_tilt_finish_f64: declared below by MS_DECLARE_API */
 
 /* ---- overlap-add placement + ADSR (main_v2.py:742-764, 172-195) ---- */
 typedef struct {
@@ -109,16 +105,14 @@ typedef struct {
     int32_t A, D_end, sus_end;
     int32_t has_release;
     double inv_A, inv_D, inv_R;
-    float S, curve;
+    double S, curve;
 } ms_ola_render;
 typedef struct {
     int64_t grain;            /* pool offset of grain[offset] */
     int32_t start, len;
-    float amp;
-    int32_t _pad;
+    double amp;
 } ms_ola_evt;
-int ms_overlap_add(const ms_ola_render* dev_renders, int n_renders, int max_out_n, const ms_ola_evt* dev_evts,
-                   const float* pool, float* mono, void* stream);
+/* ms_overlap_add_f32 / ms_overlap_add_f64: declared below by MS_DECLARE_API */
 
 /* ---- early-reflection cloud + short IR as one FIR (main_v2.py:409-421, 438-445), applied by
  *      FFT overlap-save ---- */
@@ -131,16 +125,14 @@ typedef struct {
     int64_t x, y;             /* offsets of the render's mono input / output */
     int32_t out_n, _pad;
 } ms_fir_render;
-int ms_fir_build(const ms_fir_render* dev_renders, int n_renders, int max_h_len, const int32_t* tap_off,
-                 const float* tap_gain, const float* irpool, float* hpool, void* stream);
-size_t ms_fir_workspace_bytes(const ms_fir_render* host_renders, int n_renders);
-int ms_fir_create(const ms_fir_render* host_renders, int n_renders, const float* hpool, const float* mono_in,
-                  float* mono_out, void* workspace, size_t workspace_bytes, void* stream, void** handle);
-int ms_fir_run(void* handle, void* stream);
-void ms_fir_destroy(void* handle);
+/* ms_fir_build_f32 / ms_fir_build_f64: declared below by MS_DECLARE_API */
+/* ms_fir_workspace_bytes_f32 / ms_fir_workspace_bytes_f64: declared below by MS_DECLARE_API */
+/* ms_fir_create_f32 / ms_fir_create_f64: declared below by MS_DECLARE_API */
+/* ms_fir_run_f32 / ms_fir_run_f64: declared below by MS_DECLARE_API */
+/* ms_fir_destroy_f32 / ms_fir_destroy_f64: declared below by MS_DECLARE_API */
 
 /* ---- stereo diffusion + soft clip + normalise (main_v2.py:423-436, 31-34, 26-29) ---- */
-#define MS_POST_K 10
+#define MS_POST_K 12
 typedef struct {
     int64_t y;                /* mono input offset */
     int64_t out;              /* output offset in frames */
@@ -148,13 +140,44 @@ typedef struct {
     int32_t n;
     int32_t stereo_mode;      /* 0 duplicate, 1 Bessel FIR (even n), 2 precomputed */
     int32_t dl, dr;
-    float drive, inv_tanh_drive, peak, _pad;
-    float coef[2 * MS_POST_K + 1];
-    float _pad2;
+    double drive, inv_tanh_drive, peak;
+    double coef[2 * MS_POST_K + 1];  /* J_m(theta), m = -K..K */
 } ms_post_render;
-int ms_post(const ms_post_render* dev_renders, int n_renders, int max_n, const float* mono, uint32_t* maxbits,
-            float* out, void* stream);
-int ms_roll(const float* src, float* dst, int n, int shift, void* stream);
+/* ms_post_f32 / ms_post_f64: declared below by MS_DECLARE_API */
+/* ms_roll_f32 / ms_roll_f64: declared below by MS_DECLARE_API */
+
+/* ---- entry points.  Every stage exists in two precisions with identical signatures except for the
+ *      element type of the signal buffers: suffix _f32 (float) and _f64 (double).  The interleaved stereo
+ *      output of ms_post is float in both. ---- */
+#define MS_DECLARE_API(SFX, REAL) \
+    size_t ms_spectral_workspace_bytes##SFX(const ms_spec_job* host_jobs, int njobs); \
+    int ms_spectral_apply##SFX(const ms_spec_job* host_jobs, int njobs, const REAL* src, REAL* dst, \
+    void* workspace, size_t workspace_bytes, void* stream); \
+    int ms_spectral_create##SFX(const ms_spec_job* host_jobs, int njobs, const REAL* src, REAL* dst, \
+    void* workspace, size_t workspace_bytes, void* stream, void** handle); \
+    int ms_spectral_run##SFX(void* handle, void* stream); \
+    void ms_spectral_destroy##SFX(void* handle); \
+    int ms_fft_pair_forward##SFX(const REAL* a, const REAL* b, int n, REAL* z_out, \
+    void* workspace, size_t workspace_bytes, void* stream); \
+    size_t ms_fft_pair_workspace_bytes##SFX(int n); \
+    int ms_synth_normal##SFX(const ms_synth_evt* dev_evts, int n_evts, REAL* pool, void* stream); \
+    int ms_synth_dust##SFX(const ms_synth_evt* dev_evts, int n_evts, const int32_t* dust_pos, const REAL* dust_val, \
+    REAL* pool, void* stream); \
+    int ms_synth_tilt_finish##SFX(const ms_synth_evt* dev_evts, int n_evts, REAL* pool, void* stream); \
+    int ms_overlap_add##SFX(const ms_ola_render* dev_renders, int n_renders, int max_out_n, const ms_ola_evt* dev_evts, \
+    const REAL* pool, REAL* mono, void* stream); \
+    int ms_fir_build##SFX(const ms_fir_render* dev_renders, int n_renders, int max_h_len, const int32_t* tap_off, \
+    const REAL* tap_gain, const REAL* irpool, REAL* hpool, void* stream); \
+    size_t ms_fir_workspace_bytes##SFX(const ms_fir_render* host_renders, int n_renders); \
+    int ms_fir_create##SFX(const ms_fir_render* host_renders, int n_renders, const REAL* hpool, const REAL* mono_in, \
+    REAL* mono_out, void* workspace, size_t workspace_bytes, void* stream, void** handle); \
+    int ms_fir_run##SFX(void* handle, void* stream); \
+    void ms_fir_destroy##SFX(void* handle); \
+    int ms_post##SFX(const ms_post_render* dev_renders, int n_renders, int max_n, const REAL* mono, uint64_t* maxbits, \
+    float* out, void* stream); \
+    int ms_roll##SFX(const REAL* src, REAL* dst, int n, int shift, void* stream);
+MS_DECLARE_API(_f32, float)
+MS_DECLARE_API(_f64, double)
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,187 @@
+"""Kernel-level checks shared by the CPU (block emulator) and GPU test files: the same assertions run
+against the same C ABI; only the device differs."""
+import ctypes as C
+
+import numpy as np
+
+from audio_suite_b200 import _abi, configs, engine, plan
+from oracle import microsound_np as O
+
+
+def _api(dev, precision):
+    return _abi.Api(dev.lib, precision)
+
+
+def _real(precision):
+    return np.float32 if precision == "f32" else np.float64
+
+
+def _to_host(dev, buf, n, dtype):
+    out = dev.download(buf, 0, n)
+    return np.asarray(out).view(dtype) if np.asarray(out).dtype != dtype else np.asarray(out)
+
+
+def fft_pair(dev, precision, a, b):
+    api, real = _api(dev, precision), _real(precision)
+    n = len(a)
+    need = api.ms_fft_pair_workspace_bytes(n)
+    assert need > 0, dev.lib.ms_last_error()
+    ws = dev.empty(need, np.uint8)
+    da, db = dev.upload(np.asarray(a, real)), dev.upload(np.asarray(b, real))
+    z = dev.empty(2 * n, real)
+    rc = api.ms_fft_pair_forward(dev.ptr(da), dev.ptr(db), n, dev.ptr(z), dev.ptr(ws), need, dev.stream_ptr())
+    assert rc == 0, dev.lib.ms_last_error()
+    dev.synchronize()
+    zz = np.asarray(dev.download(z, 0, 2 * n), dtype=np.float64)
+    return zz[0::2] + 1j * zz[1::2]
+
+
+def check_fft_lengths(dev, precision, lengths, tol):
+    rng = np.random.default_rng(0)
+    real = _real(precision)
+    for n in lengths:
+        a, b = rng.standard_normal(n).astype(real), rng.standard_normal(n).astype(real)
+        got = fft_pair(dev, precision, a, b)
+        want = np.fft.fft(a.astype(np.float64) + 1j * b.astype(np.float64))
+        err = np.max(np.abs(got - want)) / np.max(np.abs(want))
+        assert err < tol, (n, err)
+
+
+def spectral_apply(dev, precision, jobs, src, dst_len):
+    api, real = _api(dev, precision), _real(precision)
+    arr = (_abi.SpecJob * len(jobs))(*jobs)
+    need = api.ms_spectral_workspace_bytes(C.addressof(arr), len(jobs))
+    assert need > 0, dev.lib.ms_last_error()
+    ws = dev.empty(need, np.uint8)
+    dsrc = dev.upload(np.asarray(src, real))
+    dst = dev.zeros(dst_len, real)
+    rc = api.ms_spectral_apply(C.addressof(arr), len(jobs), dev.ptr(dsrc), dev.ptr(dst), dev.ptr(ws), need, dev.stream_ptr())
+    assert rc == 0, dev.lib.ms_last_error()
+    dev.synchronize()
+    return np.asarray(dev.download(dst, 0, dst_len), dtype=np.float64)
+
+
+def _ref_grain(x, sr, p):
+    g = x
+    if p["bandlimit_on"]:
+        g = O.fft_lowpass(g, sr, p["cut"], roll=p["bandlimit_roll_hz"])
+    g = O.spectrum_stretch(g, p["st"])
+    if p["unfold_mode"] != "Classic reinterpret":
+        b1, b2, b3 = p["mb_b1"], p["mb_b2"], p["mb_b3"]
+        g = O.multiband_unfold(g, sr, [(0, b1), (b1, b2), (b2, b3)], [p["mb_u1"], p["mb_u2"], p["mb_u3"]], p["mb_roll"])
+    return g
+
+
+def check_spectral_ops(dev, precision, tol, big=True):
+    """Pairs of signals with *different* operators in one complex transform, against the oracle."""
+    rng = np.random.default_rng(5)
+    real = _real(precision)
+    base = configs.with_defaults()
+
+    def Pm(**kw):
+        p = dict(base)
+        p.update(kw)
+        return p
+    cases = [
+        (7680, 768000, Pm(cut=18000 * 16, st=1.0), Pm(cut=18000 * 16, st=2.5)),
+        (3301, 48000 * 30, Pm(cut=18000 * 30., st=1.3, unfold_mode="Multi-band unfold"),
+         Pm(cut=9000 * 30., st=1.0, unfold_mode="Multi-band unfold", mb_roll=0.0)),
+        (1690, 48000 * 30, Pm(cut=18000 * 30., st=0.3), Pm(cut=1e9, st=1.0)),
+        (4001, 48000 * 30, Pm(cut=18000 * 30., st=2.0), Pm(cut=1e9, st=0.9)),
+        (999, 48000 * 30, Pm(cut=18000 * 30., st=4.0, bandlimit_roll_hz=0.0), Pm(cut=5e5, st=0.25)),
+    ]
+    if big:
+        cases += [
+            (48000, 4800000, Pm(cut=1.8e6, st=4.0), Pm(cut=0.9e6, st=0.5, bandlimit_roll_hz=0.0)),
+            (12480, 48000 * 26, Pm(cut=18000 * 26, st=3.36), Pm(cut=18000 * 26, st=0.77, bandlimit_on=False)),
+            (30000, 3000000, Pm(cut=1e6, st=2.5), Pm(cut=1e6, st=2.5)),
+        ]
+    for n, sr, pa, pb in cases:
+        a = rng.standard_normal(n).astype(real).astype(np.float64)
+        b = rng.standard_normal(n).astype(real).astype(np.float64)
+        j = _abi.SpecJob()
+        j.n, j.in_a, j.in_b, j.out_a, j.out_b = n, 0, n, 0, n
+        oa = plan.grain_spec_op(pa, sr, n, pa["cut"], pa["st"])
+        ob = plan.grain_spec_op(pb, sr, n, pb["cut"], pb["st"])
+        j.op[0] = oa if oa is not None else _abi.SpecOp()
+        j.op[1] = ob if ob is not None else _abi.SpecOp()
+        out = spectral_apply(dev, precision, [j], np.concatenate([a, b]), 2 * n)
+        ra, rb = _ref_grain(a, sr, pa), _ref_grain(b, sr, pb)
+        sc = max(np.max(np.abs(ra)), np.max(np.abs(rb)))
+        assert np.max(np.abs(out[:n] - ra)) / sc < tol, (n, "a")
+        assert np.max(np.abs(out[n:] - rb)) / sc < tol, (n, "b")
+        j2 = _abi.SpecJob()
+        j2.n, j2.in_a, j2.in_b, j2.out_a, j2.out_b = n, 0, -1, 0, -1
+        j2.op[0] = j.op[0]
+        out2 = spectral_apply(dev, precision, [j2], a, n)
+        assert np.max(np.abs(out2 - ra)) / sc < tol, (n, "single")
+
+
+def check_identity_ops(dev, precision, tol):
+    """OP_NONE round trip is the identity for direct, two-pass and Bluestein lengths."""
+    rng = np.random.default_rng(9)
+    real = _real(precision)
+    jobs, src, off = [], [], 0
+    for n in (16, 17, 480, 625, 1000, 4099, 9000, 12345):
+        a, b = rng.standard_normal(n).astype(real), rng.standard_normal(n).astype(real)
+        j = _abi.SpecJob()
+        j.n, j.in_a, j.in_b, j.out_a, j.out_b = n, off, off + n, off, off + n
+        jobs.append(j)
+        src += [a, b]
+        off += 2 * n
+    src = np.concatenate(src)
+    out = spectral_apply(dev, precision, jobs, src, off)
+    assert np.max(np.abs(out - src.astype(np.float64))) < tol * 10
+
+
+def synth_plain(dev, precision, seed, n):
+    """Raw normals * 0.1 with fades (gen_basic's fallback branch, main_v2.py:263-269)."""
+    p = configs.with_defaults(gen_mode="Noise burst")     # planner needs a valid mode; we override below
+    rp = plan.plan_render(p)
+    api, real = _api(dev, precision), _real(precision)
+    rec = np.zeros(1, dtype=np.dtype(_abi.SynthEvt))
+    st = np.random.PCG64(seed).state["state"]
+    rec[0]["s_hi"], rec[0]["s_lo"] = st["state"] >> 64, st["state"] & 0xFFFFFFFFFFFFFFFF
+    rec[0]["i_hi"], rec[0]["i_lo"] = st["inc"] >> 64, st["inc"] & 0xFFFFFFFFFFFFFFFF
+    rec[0]["n"], rec[0]["mode"] = n, plan.MODE_NOISE     # NOISE writes the raw normals
+    rec[0]["fade"], rec[0]["inv_fade"], rec[0]["sigma"] = 8, 1.0 / 8, 1
+    d = dev.upload(rec)
+    pool = dev.zeros(n, real)
+    rc = api.ms_synth_normal(dev.ptr(d), 1, dev.ptr(pool), dev.stream_ptr())
+    assert rc == 0, dev.lib.ms_last_error()
+    dev.synchronize()
+    return np.asarray(dev.download(pool, 0, n))
+
+
+def check_normals_bit_exact(dev, precision, cases):
+    real = _real(precision)
+    for seed, n in cases:
+        got = synth_plain(dev, precision, seed, n)
+        want = np.random.default_rng(seed).standard_normal(n).astype(real)
+        assert got.dtype == want.dtype
+        assert np.array_equal(got, want), (seed, n, int(np.argmax(got != want)))
+
+
+def render_error(dev, params, precision):
+    ref, mref = O.render(params)
+    out, meta = engine.render(params, device=dev, precision=precision)
+    assert out.dtype == np.float64 and out.shape == ref.shape
+    assert meta["out_sr"] == mref["out_sr"] and meta["design_sr_base"] == mref["design_sr_base"]
+    err = float(np.max(np.abs(out - ref)))
+    rms_db = 20 * np.log10(max(1e-30, float(np.sqrt(np.mean((out - ref) ** 2)))))
+    gm = np.max(np.abs(meta["grain_last"] - mref["grain_last"])) / max(1e-30, np.max(np.abs(mref["grain_last"])))
+    mm = np.max(np.abs(meta["micro_last"] - mref["micro_last"])) / max(1e-30, np.max(np.abs(mref["micro_last"])))
+    return err, rms_db, float(gm), float(mm)
+
+
+# tolerance north_star states: 1e-5 max-abs and -100 dBFS RMS residual against the numpy path
+MAX_ABS_TOL = 1e-5
+RMS_DB_TOL = -100.0
+
+
+def check_render(dev, params, precision="auto"):
+    err, rms_db, gm, mm = render_error(dev, params, precision)
+    assert err < MAX_ABS_TOL, err
+    assert rms_db < RMS_DB_TOL, rms_db
+    assert gm < 2e-6 and mm < 2e-6, (gm, mm)
+    return err

@@ -1,0 +1,94 @@
+"""CPU tests of the *kernel bodies* through the block emulator (tests/host_emul): same C ABI, same
+engine, CUDA threads emulated by fibres.  Sizes are kept small; the GPU tests repeat these at full size."""
+import numpy as np
+import pytest
+
+import kernel_checks as K
+from audio_suite_b200 import configs
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 2e-6), ("f64", 1e-13)])
+def test_fft_direct_twopass_bluestein(emul, precision, tol):
+    K.check_fft_lengths(emul, precision, [16, 60, 125, 243, 480, 1000, 7680, 8192, 17, 97, 1690, 3301, 4097,
+                                           9000, 12480, 20011], tol)
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 3e-6), ("f64", 1e-12)])
+def test_spectral_ops_on_packed_pairs(emul, precision, tol):
+    K.check_spectral_ops(emul, precision, tol, big=False)
+
+
+@pytest.mark.parametrize("precision,tol", [("f32", 1e-6), ("f64", 1e-13)])
+def test_identity_round_trip(emul, precision, tol):
+    K.check_identity_ops(emul, precision, tol)
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_normals_bit_exact_vs_numpy(emul, precision):
+    # 40000 normals cross ~20 rounds of the block scan and contain wedge rejections and tail draws
+    K.check_normals_bit_exact(emul, precision, [(12345, 16), (1, 2047), (7, 2049), (2026, 40000)])
+
+
+@pytest.mark.parametrize("name,precision", [("C1b", "f32"), ("C1b", "f64"), ("C2", "f32")])
+def test_render_small_configs(emul, name, precision):
+    K.check_render(emul, configs.canonical(name), precision)
+
+
+def test_render_c3_auto_precision(emul):
+    p = configs.canonical("C3")
+    p["out_dur_s"] = 0.25
+    K.check_render(emul, p, "auto")
+
+
+@pytest.mark.parametrize("mode", configs.BASIC_MODES)
+def test_render_every_generator(emul, mode):
+    p = configs.with_defaults(gen_mode=mode, event_process="Poisson", out_dur_s=0.4, grains_per_sec=25.0,
+                              time_unfold=40.0, micro_ms=2.0, partial_stretch=1.7, space_ir_on=True,
+                              _ir_audio=configs.synth_ir(0.05, 48000, 3))
+    K.check_render(emul, p, "auto")
+
+
+def test_render_lanes_multiband_odd_stereo(emul):
+    p = configs.with_defaults(event_process="Clustered", out_dur_s=0.30003, base_sr=44100, grains_per_sec=30.0,
+                              bp_unfold="0:20, 0.2:33.3", bp_stretch="0:0.5, 0.3:2", bp_cutoff="0:9000,0.3:18000",
+                              unfold_mode="Multi-band unfold", gen_mode="Resonant strike")
+    assert int(round(p["out_dur_s"] * p["base_sr"])) % 2 == 1        # odd length: FFT rotation path
+    K.check_render(emul, p, "auto")
+
+
+def test_identities_from_the_reference_code(emul):
+    from audio_suite_b200 import engine
+    base = dict(out_dur_s=0.1, event_process="Single", er_cloud_on=False, gen_mode="Gaussian click")
+    # stereo_on False -> L == R (M:778); final max|out| == peak (M:781)
+    out, meta = engine.render(configs.with_defaults(base, stereo_on=False, peak=0.5), device=emul)
+    assert np.array_equal(out[:, 0], out[:, 1]) and abs(np.max(np.abs(out)) - 0.5) < 1e-6
+    # bandlimit off and stretch 1 -> grain_last == micro_last (M:688-729)
+    out, meta = engine.render(configs.with_defaults(base, bandlimit_on=False, partial_stretch=1.0), device=emul)
+    assert np.array_equal(meta["grain_last"], meta["micro_last"])
+    assert meta["micro_last"][0] == 0.0                                  # fade-in starts at exactly 0 (M:267)
+    # unit-impulse IR leaves the output unchanged; an IR shorter than 8 samples is skipped (M:439)
+    ref, _ = engine.render(configs.with_defaults(base), device=emul, precision="f64")
+    imp = np.zeros(64); imp[0] = 1.0
+    a, _ = engine.render(configs.with_defaults(base, space_ir_on=True, _ir_audio=imp), device=emul, precision="f64")
+    b, _ = engine.render(configs.with_defaults(base, space_ir_on=True, _ir_audio=np.ones(7)), device=emul, precision="f64")
+    assert np.max(np.abs(a - ref)) < 1e-6 and np.array_equal(b, ref)
+
+
+def test_progress_call_shapes(emul):
+    from audio_suite_b200 import engine
+    from oracle import microsound_np as O
+    p = configs.with_defaults(event_process="Poisson", out_dur_s=0.5, grains_per_sec=300.0, micro_ms=0.5)
+    a, b = [], []
+    engine.render(p, progress=lambda pct, msg: a.append((pct, msg)), device=emul)
+    O.render(p, progress=lambda pct, msg: b.append((pct, msg)))
+    assert a == b and a[0][0] == 0 and a[-1] == (100, "Done.")
+
+
+def test_batch_equals_single_renders(emul):
+    from audio_suite_b200 import engine
+    ps = [configs.with_defaults(seed=s, out_dur_s=0.1, gen_mode=m, time_unfold=u)
+          for s, m, u in ((1, "Gaussian click", 25.0), (2, "Noise burst", 30.0), (3, "Gaussian click", 25.0))]
+    batch = engine.render_batch(ps, device=emul, precision="f64")
+    for p, got in zip(ps, batch):
+        one, _ = engine.render(p, device=emul, precision="f64")
+        assert np.max(np.abs(got.astype(np.float64) - one)) < 1e-6     # pairing changes rounding only
