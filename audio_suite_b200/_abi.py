@@ -57,7 +57,7 @@ class OlaEvt(C.Structure):
 class FirRender(C.Structure):
     _fields_ = [("ir", C.c_int64), ("ir_len", C.c_int32), ("h_len", C.c_int32), ("h", C.c_int64),
                 ("tap_begin", C.c_int32), ("tap_end", C.c_int32), ("x", C.c_int64), ("y", C.c_int64),
-                ("out_n", C.c_int32), ("_pad", C.c_int32)]
+                ("out_n", C.c_int32), ("x_begin", C.c_int32), ("x_end", C.c_int32), ("_pad", C.c_int32)]
 
 
 class PostRender(C.Structure):
@@ -72,6 +72,8 @@ _COMMON = {
     "ms_version": (C.c_int, []),
     "ms_last_error": (C.c_char_p, []),
     "ms_is_cuda_build": (C.c_int, []),
+    "ms_launch_count": (C.c_ulonglong, []),
+    "ms_h2d_bytes": (C.c_ulonglong, []),
 }
 # every stage exists as <name>_f32 and <name>_f64 (include/microsound_b200.h, MS_DECLARE_API)
 _STAGES = {

@@ -65,6 +65,7 @@ struct FftJob {
     int ols_n;                   // overlap-save: signal length (LD_OLS / ST_OLS)
     long long p0_a, p0_b;        // overlap-save: first input sample position of block a / b (may be negative)
     int ols_skip;                // overlap-save: taps - 1 (leading outputs of a block that are discarded)
+    int live_lo, live_hi;        // overlap-save: outputs outside [live_lo, live_hi) are exactly zero (input support + taps)
     int _pad;
     SpecOp op[2];                // per packed signal (a, b)
 };
@@ -212,8 +213,8 @@ MS_DEV void job_store(const FftJob& J, int idx, cpx v) {
     if (ST == ST_OLS) {             // valid part of the circular convolution; un-swap the inverse half
         if (idx < J.ols_skip) return;
         const long long qa = J.p0_a + idx, qb = J.p0_b + idx;
-        if (qa < J.ols_n) J.out_a[qa] = v.y;
-        if (J.out_b && qb < J.ols_n) J.out_b[qb] = v.x;
+        if (qa < J.ols_n) J.out_a[qa] = (qa >= J.live_lo && qa < J.live_hi) ? v.y : (real)0;
+        if (J.out_b && qb < J.ols_n) J.out_b[qb] = (qb >= J.live_lo && qb < J.live_hi) ? v.x : (real)0;
         return;
     }
     if (idx >= J.n) return;

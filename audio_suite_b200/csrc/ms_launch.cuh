@@ -11,6 +11,10 @@ struct MsDim { unsigned x, y; };
 
 // thread-local last error (C-ABI: ms_last_error)
 std::string& ms_err_slot();
+// kernels launched by this library since it was loaded (C-ABI: ms_launch_count)
+unsigned long long& ms_launch_counter();
+// bytes of job tables this library has copied host->device itself (C-ABI: ms_h2d_bytes)
+unsigned long long& ms_h2d_counter();
 #define MS_FAIL(...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); ms_err_slot() = _b; return -1; } while (0)
 
 #ifdef MS_HOST_EMUL
@@ -23,11 +27,12 @@ namespace msemu {
 template <class K, class... Args>
 int ms_launch(MsDim grid, int block, size_t smem, ms_stream_t, Args... args) {
     msemu::run(grid, block, smem, [&](const Ctx& c) { K::run(args..., c); });
+    ++ms_launch_counter();
     return 0;
 }
 static inline void* ms_dev_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
 static inline void ms_dev_free(void* p) { free(p); }
-static inline int ms_h2d(void* dst, const void* src, size_t bytes, ms_stream_t) { memcpy(dst, src, bytes); return 0; }
+static inline int ms_h2d(void* dst, const void* src, size_t bytes, ms_stream_t) { ms_h2d_counter() += bytes; memcpy(dst, src, bytes); return 0; }
 static inline int ms_memset(void* dst, int v, size_t bytes, ms_stream_t) { memset(dst, v, bytes); return 0; }
 #else
 typedef cudaStream_t ms_stream_t;
@@ -50,12 +55,14 @@ int ms_launch(MsDim grid, int block, size_t smem, ms_stream_t st, Args... args) 
     }
     if (grid.x == 0 || grid.y == 0) return 0;
     ms_kernel<K, Args...><<<dim3(grid.x, grid.y, 1), block, smem, st>>>(args...);
+    ++ms_launch_counter();
     MS_CUDA_OK(cudaGetLastError());
     return 0;
 }
 static inline void* ms_dev_alloc(size_t bytes) { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; return p; }
 static inline void ms_dev_free(void* p) { cudaFree(p); }
 static inline int ms_h2d(void* dst, const void* src, size_t bytes, ms_stream_t st) {
+    ms_h2d_counter() += bytes;
     MS_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)); return 0;
 }
 static inline int ms_memset(void* dst, int v, size_t bytes, ms_stream_t st) {

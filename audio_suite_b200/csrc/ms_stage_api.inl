@@ -129,6 +129,8 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
             J.p0_a = (long long)ba * hop - (r[i].h_len - 1);
             if (bb < nblk) { J.in_b = J.in_a; J.out_b = J.out_a; J.p0_b = (long long)bb * hop - (r[i].h_len - 1); }
             J.ols_n = r[i].out_n; J.ols_skip = r[i].h_len - 1;
+            J.live_lo = r[i].x_begin;
+            J.live_hi = (int)std::min<long long>(r[i].out_n, (long long)r[i].x_end + r[i].h_len - 1);
             J.bspec = hspec + L.hspec_at[i];
             if (L.B[i] > MS_SMALL_MAX) { J.work = work + wk; wk += (size_t)L.B[i]; }
             P->cjobs.push_back(J);

@@ -36,6 +36,7 @@ class CudaDevice:
         self.index = torch.cuda.current_device() if index is None else int(index)
         self.dev = torch.device("cuda", self.index)
         self.lib = _abi.lib()
+        self.uploaded = 0
 
     def stream_ptr(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
@@ -52,7 +53,8 @@ class CudaDevice:
 
     def upload(self, arr):
         """numpy array (any dtype) -> device bytes."""
-        a = np.ascontiguousarray(arr)
+        a = np.array(arr, copy=True, order="C")
+        self.uploaded += a.nbytes
         host = self.torch.from_numpy(a.view(np.uint8).reshape(-1) if a.size else np.zeros(1, np.uint8))
         return host.pin_memory().to(self.dev, non_blocking=True)
 
@@ -162,7 +164,9 @@ class BatchRenderer:
         self.precision = choose_precision(self.plans) if precision == "auto" else precision
         self.api = _abi.Api(self.dev.lib, self.precision)
         self.real = np.float32 if self.precision == "f32" else np.float64
+        up0 = getattr(self.dev, "uploaded", 0) + self.dev.lib.ms_h2d_bytes()
         self._pack()
+        self.h2d_bytes = getattr(self.dev, "uploaded", 0) + self.dev.lib.ms_h2d_bytes() - up0
 
     # ---- layout + tables ---------------------------------------------------------------------------
     def _pack(self):
@@ -203,6 +207,7 @@ class BatchRenderer:
             o["S"], o["curve"] = S, curve
             o["ev_begin"] = len(ola_e)
             max_len = 0
+            x_begin, x_end = n, 0
             last_micro = last_grain = None
             for ev in rp.events:
                 rec1, rec2 = sy1[e], sy2[e]
@@ -240,6 +245,10 @@ class BatchRenderer:
                 if ev.placed:
                     ola_e.append((grain + ev.offset, ev.start, ev.length, ev.amp))
                     max_len = max(max_len, ev.length)
+                    # grain[0] is exactly 0 (fade-in starts at 0, main_v2.py:267), so with no offset the
+                    # first placed sample is an exact zero
+                    x_begin = min(x_begin, ev.start + (1 if ev.offset == 0 else 0))
+                    x_end = max(x_end, ev.start + ev.length)
                 e += 1
             o["ev_end"], o["max_len"] = len(ola_e), max_len
             self.micro_at.append(last_micro)
@@ -276,6 +285,9 @@ class BatchRenderer:
                 h_total += f.h_len
                 max_h = max(max_h, f.h_len)
                 f.x, f.out_n = mono_n, n
+                if x_begin == 0 and a > 0:
+                    x_begin = 1                      # env[0] = 0 ** curve = 0 (main_v2.py:181-182)
+                f.x_begin, f.x_end = min(x_begin, x_end), x_end
                 fir_r.append((r, f))
             self.mono_at.append(mono_n)
             mono_n += n
@@ -358,24 +370,33 @@ class BatchRenderer:
         self.rot_stage = _SpectralStage(dev, self.api, _pair_jobs(rot_items), self.mono, self.mono)
 
     # ---- execution -------------------------------------------------------------------------------------
-    def run(self):
+    def run(self, mark=None):
+        """Launch the whole kernel sequence on the current stream.  `mark(name)` (optional) is called
+        after each stage has been enqueued (bench.py records a CUDA event there)."""
         dev, lib = self.dev, self.api
         st = dev.stream_ptr()
+        mark = mark or (lambda name: None)
         if self.n_evt:
             _check(dev, lib.ms_synth_normal(dev.ptr(self.d_sy1), self.n_evt, dev.ptr(self.pool), st))
             if self.any_dust:
                 _check(dev, lib.ms_synth_dust(dev.ptr(self.d_sy1), self.n_evt, dev.ptr(self.d_dpos), dev.ptr(self.d_dval),
                                               dev.ptr(self.pool), st))
+            mark("synth")
             if self.any_tilt:
                 self.tilt_stage.run()
                 _check(dev, lib.ms_synth_tilt_finish(dev.ptr(self.d_sy2), self.n_evt, dev.ptr(self.pool), st))
+                mark("tilt_spectral")
             self.grain_stage.run()
+            mark("grain_spectral")
         _check(dev, lib.ms_overlap_add(dev.ptr(self.d_ola_r), self.n_renders, self.max_out_n, dev.ptr(self.d_ola_e),
                                        dev.ptr(self.pool), dev.ptr(self.mono), st))
+        mark("overlap_add")
         if self.n_fir:
             _check(dev, lib.ms_fir_build(dev.ptr(self.d_fir), self.n_fir, self.max_h, dev.ptr(self.d_tap_off),
                                          dev.ptr(self.d_tap_gain), dev.ptr(self.d_ir), dev.ptr(self.hpool), st))
+            mark("fir_build")
             _check(dev, lib.ms_fir_run(self.fir_handle, st))
+            mark("fir_overlap_save")
         if self.odd_stereo:
             base, isz = dev.ptr(self.mono).value, np.dtype(self.real).itemsize
             for (r, scratch, n, dr, theta) in self.odd_stereo:
@@ -383,6 +404,7 @@ class BatchRenderer:
             self.rot_stage.run()
         _check(dev, lib.ms_post(dev.ptr(self.d_post), self.n_renders, self.max_out_n, dev.ptr(self.mono),
                                 dev.ptr(self.maxbits), dev.ptr(self.out), st))
+        mark("post")
 
     # ---- results ---------------------------------------------------------------------------------------
     def output(self, r):

@@ -1,0 +1,57 @@
+"""Sharding a batch of independent renders over the GPUs of one box.
+
+The reference's batch render is a serial loop of independent `render(p)` calls
+(main_v2.py:1578-1593): no state is shared and nothing is exchanged, so the partition is by render
+index, one process per GPU, identical kernel sequences, and the only collective is the final
+collection of the rendered buffers on rank 0 (NCCL `gather`; `gloo` in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def partition(n_items: int, world: int, rank: int):
+    """Contiguous block of render indices owned by `rank`: sizes differ by at most one."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad world/rank")
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def balanced_partition(costs, world: int):
+    """Greedy longest-processing-time assignment; returns a list of index lists, one per rank.
+    Cost model of one render: grain FFT work n log n plus the per-output-frame tail."""
+    order = np.argsort(-np.asarray(costs, dtype=np.float64), kind="stable")
+    loads = np.zeros(world)
+    owners = [[] for _ in range(world)]
+    for i in order.tolist():
+        r = int(np.argmin(loads))
+        owners[r].append(i)
+        loads[r] += costs[i]
+    return [sorted(o) for o in owners]
+
+
+def render_cost(plan):
+    c = 56.0 * plan.out_n
+    for ev in plan.events:
+        c += ev.n * (20.0 + 8.0 * np.log2(max(2, ev.n)))
+    return c
+
+
+def gather_frames(local, frames_per_rank, dist, rank, world, dst=0):
+    """Collect per-rank interleaved stereo buffers (`local`: 1-D tensor of 2*frames floats) on rank
+    `dst`.  Ranks may own different frame counts; buffers are padded to the largest.  Returns the list of
+    per-rank tensors on `dst` (views trimmed to the true size) and None elsewhere."""
+    import torch
+    longest = 2 * max(frames_per_rank)
+    if local.numel() < longest:
+        pad = torch.zeros(longest, dtype=local.dtype, device=local.device)
+        pad[:local.numel()] = local
+        local = pad
+    if rank == dst:
+        bufs = [torch.empty(longest, dtype=local.dtype, device=local.device) for _ in range(world)]
+        dist.gather(local, gather_list=bufs, dst=dst)
+        return [b[:2 * f] for b, f in zip(bufs, frames_per_rank)]
+    dist.gather(local, gather_list=None, dst=dst)
+    return None

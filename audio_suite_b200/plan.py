@@ -328,10 +328,10 @@ def plan_render(params) -> RenderPlan:
     if params["space_ir_on"] and ir is not None:
         h = np.asarray(ir)[:int(params["space_ir_max_samps"])]
         if h.size >= 8:                       # M:439 (size counts both channels of a 2-D IR)
-            h = h.astype(np.float64)
+            h = h[:IR_TAP_CAP].astype(np.float64)     # the mono mix is row-wise, so cut to 8192 rows first
             if h.ndim > 1:
                 h = h.mean(axis=1)
-            rp.ir = h[:min(h.size, IR_TAP_CAP)]
+            rp.ir = h
     if params["stereo_on"] and out_n >= 64:   # M:426: shorter outputs are duplicated
         w = float(np.clip(float(params["stereo_width"]), 0.0, 1.0))
         rp.stereo_on = True
@@ -349,7 +349,7 @@ def reflection_taps(sr, taps, max_ms, seed):
     delays = rng.uniform(0.3, max_ms, size=int(max(1, taps))) / 1000.0
     gains = rng.uniform(-1.0, 1.0, size=delays.size)
     gains *= np.exp(-delays * 42.0)
-    offs = np.array([int(round(d * sr)) for d in delays.tolist()], dtype=np.int64)
+    offs = np.rint(delays * sr).astype(np.int64)      # np.rint is half-to-even like Python round()
     return offs, gains
 
 

@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- Microsound batched preset sweep (BASELINE.json configs[4], "C5"): 4096 randomised-parameter
+renders (2 s stereo @ 48 kHz each, design SR 1.2-9.6 MHz, five generator modes, band-limit, spectral
+stretch, reflection cloud + 8192-tap IR, stereo diffusion, soft clip, normalise), partitioned by render
+index over the GPUs of one box.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores
+
+One step = one pass of the whole render pipeline over the batch.  `value` = rendered stereo samples
+per second (2 x output frames) with all plan tables resident in HBM; `e2e` = the same through the
+public API from host parameter dicts to host float32 audio (planning, H2D, kernels, D2H all timed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FRAMES_PER_RENDER = 96000
+METRIC = "microsound_rendered_samples_per_s"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--renders", type=int, default=4096, help="renders in the sweep (total, all GPUs)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "f32", "f64"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=48, help="renders timed for cpu_baseline (rank 0, N=1)")
+    ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather of rendered buffers (N>1)")
+    return ap.parse_args()
+
+
+def workload_config(args, extra=None):
+    cfg = {"workload": "C5 batched preset sweep: %d renders x 2.0 s stereo @48 kHz (BASELINE.json configs[4])" % args.renders,
+           "renders": args.renders, "frames_per_render": FRAMES_PER_RENDER, "taps": "8192 IR + 320-tap reflection cloud",
+           "parallelism": "renders partitioned by index, %d rank(s)" % args.gpus,
+           "l2": "working set (GBs) exceeds the 126 MB L2; no flush needed"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for t, line in self.rows:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                mx = max(mx, float(parts[2]))
+                if t0 <= t <= t1:
+                    sm.append(float(parts[1]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def _ref_worker(idx):
+    from audio_suite_b200 import configs
+    from oracle import microsound_np as O
+    out, _ = O.render(configs.c5_params(idx))
+    return out.shape[0]
+
+
+def cpu_pool_throughput(indices, procs):
+    """samples/s of the numpy restatement of the reference over `indices`, `procs` worker processes."""
+    import multiprocessing as mp
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    if procs <= 1:
+        t = time.perf_counter()
+        frames = sum(_ref_worker(i) for i in indices)
+        return 2.0 * frames / (time.perf_counter() - t)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        pool.map(_ref_worker, list(indices[:procs]))          # spin the workers up (imports, IR synthesis)
+        t = time.perf_counter()
+        frames = sum(pool.map(_ref_worker, list(indices), chunksize=1))
+        dt = time.perf_counter() - t
+    return 2.0 * frames / dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    per_step = max(cores, min(2 * cores, 256))
+    vals = []
+    for s in range(args.warmup + args.steps):
+        idx = [(s * per_step + i) % args.renders for i in range(per_step)]
+        v = cpu_pool_throughput(idx, cores)
+        if s >= args.warmup:
+            vals.append(v)
+        if s >= args.warmup and sum(per_step * FRAMES_PER_RENDER * 2 / x for x in vals) > 150:
+            break
+    value = float(np.mean(vals))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": args.warmup, "ms_per_step": 1e3 * per_step * FRAMES_PER_RENDER * 2 / value, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, {"sample_renders_per_step": per_step}),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d renders of the sweep per step, one worker process per core "
+                                       "(oracle/microsound_np.py, verified <=2e-13 against the reference)" % per_step},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def algorithmic_bytes(br):
+    """Compulsory traffic per stage, element size = the precision actually used."""
+    es = 4 if br.precision == "f32" else 8
+    grain = tilt = synth = 0
+    sum_l = 0
+    fir = 0
+    n_total = 0
+    for rp in br.plans:
+        n_total += rp.out_n
+        for ev in rp.events:
+            synth += es * ev.n
+            if ev.tilt is not None:
+                tilt += 2 * es * ev.n
+            if ev.spec is not None:
+                grain += 2 * es * ev.n * ((1 if ev.spec.lp_on else 0) + (1 if ev.spec.stretch_on else 0) + (1 if ev.spec.n_bands else 0))
+            sum_l += ev.length
+        has_er = rp.er_offs is not None and rp.er_offs.size > 0
+        if has_er:
+            fir += 2 * es * rp.out_n
+        if rp.ir is not None:
+            fir += 2 * es * rp.out_n + es * rp.ir.size
+    return {"synth": synth, "tilt_spectral": tilt, "grain_spectral": grain, "overlap_add": es * (sum_l + n_total),
+            "fir_build": 0, "fir_overlap_save": fir, "post": es * n_total + 2 * 4 * n_total + 6 * 4 * n_total}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from audio_suite_b200 import configs, engine, parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = engine.CudaDevice(local)
+    mine = list(parallel.partition(args.renders, world, rank))
+    frames_per_rank = [len(parallel.partition(args.renders, world, r)) * FRAMES_PER_RENDER for r in range(world)]
+    ir = configs.synth_ir(5.0, 48000, 303)
+    params = [configs.c5_params(i, shared_ir=ir) for i in mine]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident plan: kernels only
+    br = engine.BatchRenderer(params, device=dev, precision=args.precision)
+    gather = world > 1 and not args.no_gather
+
+    def step(mark=None):
+        br.run(mark)
+        if gather:
+            parallel.gather_frames(br.outputs_device(), frames_per_rank, dist, rank, world)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    stage_names, stage_ev = [], []
+    launches0 = dev.lib.ms_launch_count()
+    barrier()
+    wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        evs = [torch.cuda.Event(enable_timing=True)]
+        evs[0].record()
+        names = []
+
+        def mark(name, evs=evs, names=names):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            evs.append(ev)
+            names.append(name)
+        step(mark)
+        stage_names, _ = names, stage_ev.append(evs)
+    e1.record()
+    barrier()
+    wall1 = time.time()
+    launches = (dev.lib.ms_launch_count() - launches0) // args.steps
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device=dev.dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    stage_ms = {}
+    for evs in stage_ev:
+        for name, a, b in zip(stage_names, evs[:-1], evs[1:]):
+            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / args.steps
+
+    # ---- end to end through the public API: host dicts -> host float32 audio
+    h2d = d2h = 0
+    e2e_ms = []
+    host_out = torch.empty(2 * len(mine) * FRAMES_PER_RENDER, dtype=torch.float32).pin_memory()
+    for s in range(1 + args.e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        br2 = engine.BatchRenderer(params, device=dev, precision=args.precision)
+        br2.run()
+        host_out.copy_(br2.outputs_device(), non_blocking=True)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        h2d, d2h = br2.h2d_bytes, host_out.numel() * 4
+        br2.close()
+        del br2
+        if s > 0:
+            e2e_ms.append(dt)
+    t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev.dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(t.item())
+
+    if rank == 0:
+        total_samples = 2.0 * args.renders * FRAMES_PER_RENDER
+        value = total_samples / (ms_max * 1e-3)
+        alg = algorithmic_bytes(br)
+        dom = max(stage_ms, key=stage_ms.get)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        stages = {k: {"ms": round(v, 4), "algorithmic_GB": round(alg.get(k, 0) / 1e9, 4),
+                      "GBps": round(alg.get(k, 0) / 1e9 / (v * 1e-3), 1) if v > 0 else None,
+                      "frac_of_hbm": round(alg.get(k, 0) / 1e9 / (v * 1e-3) / peak, 4) if v > 0 else None}
+                  for k, v in stage_ms.items()}
+        ach = alg.get(dom, 0) / 1e9 / (stage_ms[dom] * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": br.precision, "data": "synthetic",
+                "config": workload_config(args, {"precision_rule": "auto: f64 when a FIR stage feeds the soft clip" if args.precision == "auto" else args.precision,
+                                                 "gather": "NCCL gather of rendered buffers to rank 0 inside the step" if gather else "none"}),
+                "frames_per_s": value / 2.0,
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "e2e": {"value": total_samples / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "includes": "host planning (numpy RNG draws, job tables), pinned H2D of tables, all kernels, D2H of float32 audio"},
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                             "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                             "note": "stage = consecutive launches of one pipeline stage, CUDA events on the launch stream; "
+                                     "see profiles/ for the per-kernel ncu launch list"},
+                "stages": stages}
+        if world == 1 and args.cpu_sample > 0:
+            idx = list(range(args.cpu_sample))
+            v = cpu_pool_throughput(idx, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "first %d renders of the sweep, serial like the reference's batch loop "
+                                              "(main_v2.py:1578-1593), oracle/microsound_np.py" % args.cpu_sample}
+        print(json.dumps(line))
+    br.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,10 @@ int ms_version(void);
 const char* ms_last_error(void);
 /* 1 when the library was built from the CUDA sources for sm_100a (always, for the shipped .so). */
 int ms_is_cuda_build(void);
+/* kernels this library has launched since it was loaded (bench.py reports the delta per step). */
+unsigned long long ms_launch_count(void);
+/* bytes of job descriptors the library itself has copied host->device since it was loaded. */
+unsigned long long ms_h2d_bytes(void);
 
 /* ---- spectral stage: lowpass_fft (main_v2.py:39-59), fft_partial_stretch (:117-128),
  *      unfold_multiband / bandpass_fft (:492-500, :61-101), tilted_noise shaping (:224-233),
@@ -123,7 +127,9 @@ typedef struct {
     int64_t h;                /* offset of the combined taps in hpool */
     int32_t tap_begin, tap_end;
     int64_t x, y;             /* offsets of the render's mono input / output */
-    int32_t out_n, _pad;
+    int32_t out_n;
+    int32_t x_begin, x_end;   /* support of the input: samples outside [x_begin, x_end) are exactly zero */
+    int32_t _pad;
 } ms_fir_render;
 /* ms_fir_build_f32 / ms_fir_build_f64: declared below by MS_DECLARE_API */
 /* ms_fir_workspace_bytes_f32 / ms_fir_workspace_bytes_f64: declared below by MS_DECLARE_API */

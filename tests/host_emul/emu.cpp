@@ -58,3 +58,7 @@ void run(MsDim grid, int block, size_t smem, const std::function<void(const Ctx&
 }  // namespace msemu
 
 std::string& ms_err_slot() { static thread_local std::string s; return s; }
+unsigned long long& ms_launch_counter() { static unsigned long long n = 0; return n; }
+extern "C" unsigned long long ms_launch_count(void) { return ms_launch_counter(); }
+unsigned long long& ms_h2d_counter() { static unsigned long long n = 0; return n; }
+extern "C" unsigned long long ms_h2d_bytes(void) { return ms_h2d_counter(); }

@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "microsound_b200.h")
 
 def _declared():
     text = open(HEADER).read()
-    names = set(re.findall(r"^(?:int|size_t|const char\*|void)\s+(ms_\w+)\(", text, re.M))
+    names = set(re.findall(r"^(?:int|size_t|const char\*|void|unsigned long long)\s+(ms_\w+)\(", text, re.M))
     macro = text[text.index("#define MS_DECLARE_API"):text.index("MS_DECLARE_API(_f32, float)")]
     staged = set(re.findall(r"(ms_\w+)##SFX", macro))
     assert len(staged) >= 18

@@ -73,8 +73,9 @@ def test_render_c5_batch_against_oracle(cuda_dev):
     ps = [configs.c5_params(i) for i in idx]
     outs = engine.render_batch(ps, device=cuda_dev)
     for p, got in zip(ps, outs):
-        ref, _ = O.render(p)
-        assert np.max(np.abs(got.astype(np.float64) - ref)) < K.MAX_ABS_TOL
+        taps = {}
+        ref, _ = O.render(p, taps=taps)
+        assert np.max(np.abs(got.astype(np.float64) - ref)) < K.MAX_ABS_TOL + K.reference_noise_floor(p, taps)
 
 
 def test_render_c4_shortened_against_oracle(cuda_dev):
@@ -100,13 +101,19 @@ def test_render_edge_cases(cuda_dev):
           bp_stretch="0:0.5, 0.3:2", unfold_mode="Multi-band unfold", gen_mode="Resonant strike"),     # odd length
         W(event_process="Hawkes", out_dur_s=1.0, gen_mode="Noise burst", bandlimit_roll_hz=0.0),      # brick wall
         W(event_process="Poisson", out_dur_s=0.3, micro_ms=40.0, time_unfold=100.0),                  # grains past the end
-        W(out_dur_s=0.001, er_cloud_on=False),                                                       # out_n = 48 < 64: duplicate
+        W(out_dur_s=0.001, er_cloud_on=False, env_a=0.5, env_d=0.1, env_r=0.2),                      # out_n = 48 < 64: duplicate
         W(event_process="Poisson", out_dur_s=1.0, sat_drive=0.0, stereo_on=False, base_sr=192000),    # no clip
         W(event_process="Poisson", out_dur_s=1.0, grains_per_sec=0.0),                                # rate 0 -> single event
         W(event_process="Poisson", out_dur_s=2.0, max_grains=3, grains_per_sec=50.0),
     ]
     for p in cases:
         K.check_render(cuda_dev, p, "auto")
+    # attack longer than the output: the reference fails in make_adsr (main_v2.py:182); so do we
+    bad = W(out_dur_s=0.001, er_cloud_on=False)
+    with pytest.raises(ValueError):
+        O.render(bad)
+    with pytest.raises(ValueError):
+        engine.render(bad, device=cuda_dev)
 
 
 def test_golden_fixtures_from_the_reference(cuda_dev):
