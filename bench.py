@@ -290,7 +290,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": br.precision, "data": "synthetic",
-                "config": workload_config(args, {"precision_rule": "auto: f64 when a FIR stage feeds the soft clip" if args.precision == "auto" else args.precision,
+                "config": workload_config(args, {"precision_rule": "auto = f64 (engine.choose_precision)" if args.precision == "auto" else args.precision,
                                                  "gather": "NCCL gather of rendered buffers to rank 0 inside the step" if gather else "none"}),
                 "frames_per_s": value / 2.0,
                 "gpu_launches": int(launches),
