@@ -15,6 +15,10 @@ template <int LD, int MODE, int ST> struct RowsK {
     static constexpr int MAXT = 512;
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_rows_body<LD, MODE, ST>(jobs, c); }
 };
+struct GenChirpK {
+    static constexpr int MAXT = 256;
+    static MS_DEV void run(cpx* out, int n, const Ctx& c) { gen_chirp_body(out, n, c, c.nthr * 64, c.bx * c.nthr + c.tid); }
+};
 struct GenTableK {
     static constexpr int MAXT = 256;
     static MS_DEV void run(cpx* out, int count, long long mul, long long N, const Ctx& c) {
@@ -33,14 +37,15 @@ static inline int ms_round32(int x) { return (x + 31) / 32 * 32; }
 
 struct LaunchShape { int ept, nthr; size_t smem; unsigned gx; };
 
-static inline int cols_tile_elems(const FftJob& J) { return J.T * J.F1; }
+static inline int cols_tile_elems(const FftJob& J) { return J.T * (J.B1 ? J.B1 : J.F1); }
 static inline int rows_tile_elems(const FftJob& J) { return J.G * J.F2; }
-static inline size_t cols_smem(const FftJob& J) { return 2 * sizeof(cpx) * (size_t)(ms_pad((J.F1 - 1) * J.T + J.T - 1) + 2); }
+static inline int cols_rows(const FftJob& J) { return J.B1 ? J.B1 : J.F1; }
+static inline size_t cols_smem(const FftJob& J) { return 2 * sizeof(cpx) * (size_t)(ms_pad((cols_rows(J) - 1) * J.T + J.T - 1) + 2); }
 static inline size_t rows_smem(const FftJob& J) { return 2 * sizeof(cpx) * (size_t)(J.G * ((ms_pad(J.F2) + 1) | 1) + 2); }
 
 static inline void shape_for(int tile, LaunchShape* s) {
     s->ept = 0;
-    s->nthr = std::min(512, std::max(64, ms_round32((tile + 15) / 16)));
+    s->nthr = std::min(512, std::max(64, ms_round32((tile + 7) / 8)));     // one radix-8 butterfly per thread per pass
 }
 
 class FftEngine {
@@ -121,8 +126,36 @@ private:
         if (!best) return false;
         J.F1 = best; J.F2 = n / best;
         J.T = 16; J.G = 16;
+        while (J.T > 8 && J.T * J.F1 > MS_TILE_MAX / 2) J.T /= 2;       // prefer half tiles: 2-3 CTAs per SM
+        while (J.G > 8 && J.G * J.F2 > MS_TILE_MAX / 2) J.G /= 2;
         while (J.T > 1 && J.T * J.F1 > MS_TILE_MAX) J.T /= 2;
         while (J.G > 1 && J.G * J.F2 > MS_TILE_MAX) J.G /= 2;
+        return true;
+    }
+    // n = F1 * F2 with F2 smooth (rows kernel) and F1 arbitrary, done in the columns kernel as an in-tile
+    // Bluestein of length B1 = pow2 >= 2 F1 - 1.  Same global traffic as the direct two-pass transform.
+    static bool plan_mixed(int n, FftJob& J) {
+        const int tile_target = MS_TILE_MAX / 2;
+        int best = 0; double best_cost = 0;
+        for (int f2 = 16; f2 <= MS_TILE_MAX && f2 < n; ++f2) {
+            if (n % f2 || !ms_is_smooth(f2)) continue;
+            const int f1 = n / f2;
+            if (f1 < 2 || ms_is_smooth(f1)) continue;
+            int b1 = 1; while (b1 < 2 * f1 - 1) b1 <<= 1;
+            if (b1 * 4 > MS_TILE_MAX) continue;
+            const int T = std::max(1, std::min(16, tile_target / b1)), G = std::max(1, std::min(16, tile_target / f2));
+            double lg2 = 0, lgb = 0;
+            for (int t = f2; t > 1; t >>= 1) lg2 += 1;
+            for (int t = b1; t > 1; t >>= 1) lgb += 1;
+            double cost = lg2 + 2.0 * lgb * (double)b1 / (double)f1 + (T < 8 ? 16.0 / T : 0) + (G < 8 ? 16.0 / G : 0);
+            if (!best || cost < best_cost) { best = f2; best_cost = cost; }
+        }
+        if (!best) return false;
+        J.M = n; J.F2 = best; J.F1 = n / best;
+        int b1 = 1; while (b1 < 2 * J.F1 - 1) b1 <<= 1;
+        J.B1 = b1;
+        J.T = std::max(1, std::min(16, tile_target / b1));
+        J.G = std::max(1, std::min(16, tile_target / J.F2));
         return true;
     }
     static bool plan_bluestein(int n, FftJob& J) {
@@ -146,11 +179,25 @@ private:
         if (it == geom_.end()) {
             FftJob g; memset(&g, 0, sizeof g);
             g.n = n;
-            bool blu = false;
-            if (!plan_direct(n, g)) { blu = true; if (!plan_bluestein(n, g)) MS_FAIL("fft: length %d unsupported", n); }
+            bool blu = false, mixed = false;
+            if (!plan_direct(n, g)) {
+                if (n > MS_SMALL_MAX / 2 && plan_mixed(n, g)) mixed = true;
+                else { blu = true; if (!plan_bluestein(n, g)) MS_FAIL("fft: length %d unsupported", n); }
+            }
             if (!ms_make_radix_plan(g.F2, &g.p2)) MS_FAIL("fft: cannot factor %d", g.F2);
             if (get_wtab(g.F2, st, &g.tw2)) return -1;
-            if (g.F1 > 1) {
+            if (mixed) {
+                // borrow the small Bluestein plan of length F1: its filter spectrum (natural order) and radix plan
+                FftJob sub; memset(&sub, 0, sizeof sub);
+                if (prepare_locked(sub, g.F1, st)) return -1;
+                if (!sub.ch_hi || sub.F1 != 1 || sub.M != g.B1) MS_FAIL("fft: internal: sub-plan of %d is not a small Bluestein", g.F1);
+                g.pb = sub.p2; g.twb = sub.tw2; g.b1_spec = sub.bspec;
+                cpx* ch = (cpx*)ms_dev_alloc(sizeof(cpx) * (size_t)g.F1);
+                if (!ch) MS_FAIL("out of device memory for chirp table");
+                if (L<GenChirpK>(64, 1, 256, 0, st, ch, g.F1)) return -1;
+                g.b1_chirp = ch;
+                if (get_two_level(g.M, st, &g.twM_hi, &g.twM_lo)) return -1;
+            } else if (g.F1 > 1) {
                 if (!ms_make_radix_plan(g.F1, &g.p1)) MS_FAIL("fft: cannot factor %d", g.F1);
                 if (get_wtab(g.F1, st, &g.tw1)) return -1;
                 if (get_two_level(g.M, st, &g.twM_hi, &g.twM_lo)) return -1;
@@ -165,6 +212,7 @@ private:
         J.n = g.n; J.M = g.M; J.F1 = g.F1; J.F2 = g.F2; J.T = g.T; J.G = g.G;
         J.p1 = g.p1; J.p2 = g.p2; J.tw1 = g.tw1; J.tw2 = g.tw2; J.twM_hi = g.twM_hi; J.twM_lo = g.twM_lo;
         J.ch_hi = g.ch_hi; J.ch_lo = g.ch_lo; J.bspec = g.bspec;
+        J.B1 = g.B1; J.pb = g.pb; J.twb = g.twb; J.b1_chirp = g.b1_chirp; J.b1_spec = g.b1_spec;
         return 0;
     }
 

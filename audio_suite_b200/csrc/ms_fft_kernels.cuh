@@ -56,6 +56,13 @@ struct FftJob {
     const cpx* ch_hi;         // W_2n^(1024 i)   (Bluestein chirp), null for direct
     const cpx* ch_lo;         // W_2n^i, i < 1024
     const cpx* bspec;         // FFT_M(conj chirp, wrapped)/M in [k1][k2] layout
+    // columns pass by in-tile Bluestein (F1 has a prime factor > 5): length-F1 DFT as a length-B1 circular
+    // convolution held entirely in shared memory.  B1 == 0: plain mixed-radix columns.
+    int B1, _padb;
+    RadixPlan pb;                // radices of B1
+    const cpx* twb;              // w_B1^i
+    const cpx* b1_chirp;         // exp(-i pi j^2 / F1), j < F1
+    const cpx* b1_spec;          // FFT_B1(conj chirp, wrapped) / B1, natural order
     const real* in_a; const real* in_b;
     real* out_a; real* out_b;
     const cpx* cin; cpx* cout;   // LD_CPX / ST_CPX
@@ -242,10 +249,38 @@ MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
     const int col0 = c.bx * T;
     if (col0 >= F2) return;
     const int cnt = (F2 - col0) < T ? (F2 - col0) : T;
+    const int rows = J.B1 ? J.B1 : F1;           // vector length held in the tile
     cpx* s = (cpx*)c.smem;
-    cpx* s2 = s + (ms_pad((F1 - 1) * T + T - 1) + 2);
+    cpx* s2 = s + (ms_pad((rows - 1) * T + T - 1) + 2);
     TileGeom g; g.cnt = cnt; g.vs = 1; g.es = T; g.colmajor = 1;
     const int total = F1 * cnt;
+    if (J.B1) {
+        // length-F1 DFT of every column as chirp * IFFT_B1(FFT_B1(x * chirp) * spec)
+        const int all = rows * cnt;
+        for (int e = c.tid; e < all; e += c.nthr) {
+            const int i = e / cnt, v = e - i * cnt;
+            cpx val = c_zero();
+            if (i < F1) val = c_mul(job_load<LD>(J, i * F2 + col0 + v), __ldg(&J.b1_chirp[i]));
+            s[tile_addr(g, v, i)] = val;
+        }
+        c.sync();
+        s = tile_fft(s, s2, g, J.pb, J.twb, c);
+        for (int e = c.tid; e < all; e += c.nthr) {
+            const int i = e / cnt, v = e - i * cnt;
+            const int a = tile_addr(g, v, i);
+            s[a] = c_swap(c_mul(s[a], __ldg(&J.b1_spec[i])));
+        }
+        c.sync();
+        cpx* other = (s == (cpx*)c.smem) ? s2 : (cpx*)c.smem;
+        s = tile_fft(s, other, g, J.pb, J.twb, c);
+        for (int e = c.tid; e < total; e += c.nthr) {
+            const int k1 = e / cnt, v = e - k1 * cnt;
+            cpx val = c_mul(c_swap(s[tile_addr(g, v, k1)]), __ldg(&J.b1_chirp[k1]));
+            if (TWID) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)k1 * (unsigned)(col0 + v)));
+            job_store<ST>(J, k1 * F2 + col0 + v, val);
+        }
+        return;
+    }
     for (int e = c.tid; e < total; e += c.nthr) {
         const int i = e / cnt, v = e - i * cnt;
         s[tile_addr(g, v, i)] = job_load<LD>(J, i * F2 + col0 + v);
@@ -303,6 +338,16 @@ MS_DEV void fft_rows_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
             if (F1 > 1) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)(row0 + r) * (unsigned)i));
             job_store<ST>(J, (row0 + r) * F2 + i, val);
         }
+    }
+}
+
+// out[j] = exp(-i pi j^2 / n), j < n
+MS_DEV void gen_chirp_body(cpx* out, int n, const Ctx& c, int grid_threads, int gtid) {
+    for (int j = gtid; j < n; j += grid_threads) {
+        const long long e = ((long long)j * (long long)j) % (2ll * n);
+        double sn, cs;
+        r_sincospi((double)e / (double)n, &sn, &cs);
+        out[j] = mk((real)cs, (real)(-sn));
     }
 }
 

@@ -89,7 +89,8 @@ MS_DEV real right_sample(const PostRender& R, const real* MS_RESTRICT y, const r
     }
     return acc;
 }
-MS_DEV real soft_clip(real v, real drive, real inv_t) { return drive > (real)0. ? r_tanh(v * drive) * inv_t : v; }
+// the clipped value is stored as float32, so tanh is evaluated in float32 (argument rounded once: 6e-8 relative)
+MS_DEV real soft_clip(real v, real drive, real inv_t) { return drive > (real)0. ? (real)tanhf((float)(v * drive)) * inv_t : v; }
 
 // pass 1: per-render max(|L|, |R|) before the clip (tanh is monotonic, so the clipped max follows)
 MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, const real* MS_RESTRICT mono, unsigned long long* MS_RESTRICT maxbits, const Ctx& c) {

@@ -218,6 +218,7 @@ def run_ours(args):
     stage_names, stage_ev = [], []
     launches0 = dev.lib.ms_launch_count()
     barrier()
+    torch.cuda.profiler.start()          # ncu --profile-from-start off captures exactly the timed steps
     wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -235,6 +236,7 @@ def run_ours(args):
         stage_names, _ = names, stage_ev.append(evs)
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     wall1 = time.time()
     launches = (dev.lib.ms_launch_count() - launches0) // args.steps
     ms = e0.elapsed_time(e1) / args.steps
