@@ -11,7 +11,7 @@ struct OlaK { static constexpr int MAXT = OLA_NTHR;
 struct FirBuildK { static constexpr int MAXT = OLA_NTHR;
     static MS_DEV void run(const FirRender* r, const int* to, const real* tg, const real* ir, real* h, const Ctx& c) { fir_build_body(r, to, tg, ir, h, c); } };
 struct PostMaxK { static constexpr int MAXT = OLA_NTHR;
-    static MS_DEV void run(const PostRender* r, const real* mono, unsigned long long* mb, const Ctx& c) { post_max_body(r, mono, mb, c); } };
+    static MS_DEV void run(const PostRender* r, real* mono, unsigned long long* mb, const Ctx& c) { post_max_body(r, mono, mb, c); } };
 struct PostWriteK { static constexpr int MAXT = OLA_NTHR;
     static MS_DEV void run(const PostRender* r, const real* mono, const unsigned long long* mb, float2* out, const Ctx& c) { post_write_body(r, mono, mb, out, c); } };
 struct RollK { static constexpr int MAXT = 256;
@@ -48,14 +48,14 @@ extern "C" int MS_API(ms_fir_build)(const ms_fir_render* renders, int n_renders,
                                    renders + _y0, (const int*)tap_off, tap_gain, irpool, hpool)) return -1; })
     return 0;
 }
-extern "C" int MS_API(ms_post)(const ms_post_render* renders, int n_renders, int max_n, const real* mono, uint64_t* maxbits,
+extern "C" int MS_API(ms_post)(const ms_post_render* renders, int n_renders, int max_n, real* mono, uint64_t* maxbits,
                        float* out, void* stream) {
     const unsigned gx = (unsigned)((max_n + OLA_TILE - 1) / OLA_TILE);
     if (ms_memset(maxbits, 0, sizeof(uint64_t) * (size_t)n_renders, (ms_stream_t)stream)) return -1;
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, OLA_NTHR * sizeof(real), (ms_stream_t)stream,
                                    renders + _y0, mono, (unsigned long long*)maxbits + _y0)) return -1; })
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostWriteK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream,
-                                   renders + _y0, mono, (const unsigned long long*)maxbits + _y0, (float2*)out)) return -1; })
+                                   renders + _y0, (const real*)mono, (const unsigned long long*)maxbits + _y0, (float2*)out)) return -1; })
     return 0;
 }
 extern "C" int MS_API(ms_roll)(const real* src, real* dst, int n, int shift, void* stream) {

@@ -77,9 +77,8 @@ MS_DEV void fir_build_body(const FirRender* MS_RESTRICT renders, const int* MS_R
 // ---- stereo diffusion + soft clip + normalise -----------------------------------------------------------
 typedef ms_post_render PostRender;
 MS_DEV int wrap_idx(long long i, int n) { long long r = i % n; if (r < 0) r += n; return (int)r; }
-MS_DEV real right_sample(const PostRender& R, const real* MS_RESTRICT y, const real* MS_RESTRICT mono, int i) {
-    if (R.stereo_mode == 0) return y[i];
-    if (R.stereo_mode == 2) return mono[R.rbuf + i];
+// right channel by the Bessel taps (even lengths): R[i] = sum_m J_m(theta) y[(i + dr + 2m) mod n]
+MS_DEV real right_taps(const PostRender& R, const real* MS_RESTRICT y, int i) {
     real acc = (real)0.;
     int idx = wrap_idx((long long)i + R.dr - 2 * POST_K, R.n);
 #pragma unroll
@@ -92,8 +91,9 @@ MS_DEV real right_sample(const PostRender& R, const real* MS_RESTRICT y, const r
 // the clipped value is stored as float32, so tanh is evaluated in float32 (argument rounded once: 6e-8 relative)
 MS_DEV real soft_clip(real v, real drive, real inv_t) { return drive > (real)0. ? (real)tanhf((float)(v * drive)) * inv_t : v; }
 
-// pass 1: per-render max(|L|, |R|) before the clip (tanh is monotonic, so the clipped max follows)
-MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, const real* MS_RESTRICT mono, unsigned long long* MS_RESTRICT maxbits, const Ctx& c) {
+// pass 1: per-render max(|L|, |R|) before the clip (tanh is monotonic, so the clipped max follows).
+// stereo_mode 1 also materialises the right channel at rbuf so that pass 2 does not redo the 25 taps.
+MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, unsigned long long* MS_RESTRICT maxbits, const Ctx& c) {
     const PostRender R = renders[c.by];
     const int t0 = c.bx * OLA_TILE;
     if (t0 >= R.n) return;
@@ -102,7 +102,13 @@ MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, const real* MS_
     real m = (real)0.;
     for (int i = t0 + c.tid; i < t1; i += c.nthr) {
         m = r_max(m, r_abs(y[i]));
-        if (R.stereo_mode) m = r_max(m, r_abs(right_sample(R, y, mono, i)));
+        if (R.stereo_mode == 1) {
+            const real r = right_taps(R, y, i);
+            mono[R.rbuf + i] = r;
+            m = r_max(m, r_abs(r));
+        } else if (R.stereo_mode == 2) {
+            m = r_max(m, r_abs(mono[R.rbuf + i]));
+        }
     }
     real* red = (real*)c.smem;
     red[c.tid] = m;
@@ -135,7 +141,7 @@ MS_DEV void post_write_body(const PostRender* MS_RESTRICT renders, const real* M
     float2* o = out + R.out;
     for (int i = t0 + c.tid; i < t1; i += c.nthr) {
         const real l = R.stereo_mode ? y[wrap_idx((long long)i - R.dl, R.n)] : y[i];
-        const real r = right_sample(R, y, mono, i);
+        const real r = R.stereo_mode ? mono[R.rbuf + i] : y[i];
         o[i] = make_float2((float)(soft_clip(l, drive, inv_t) * scale), (float)(soft_clip(r, drive, inv_t) * scale));
     }
 }

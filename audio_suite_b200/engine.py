@@ -162,13 +162,18 @@ class BatchRenderer:
     re-runs the kernel sequence on demand (`run()`), e.g. for benchmarking or repeated renders."""
 
     def __init__(self, params_list, device=None, precision="auto"):
+        import time as _time
         self.dev = device or CudaDevice()
-        self.plans = [P.plan_render(p) for p in params_list]
+        t0 = _time.perf_counter()
+        self.plans = P.plan_many(params_list)
+        self.t_plan = _time.perf_counter() - t0
         self.precision = choose_precision(self.plans) if precision == "auto" else precision
         self.api = _abi.Api(self.dev.lib, self.precision)
         self.real = np.float32 if self.precision == "f32" else np.float64
         up0 = getattr(self.dev, "uploaded", 0) + self.dev.lib.ms_h2d_bytes()
+        t0 = _time.perf_counter()
         self._pack()
+        self.t_pack = _time.perf_counter() - t0
         self.h2d_bytes = getattr(self.dev, "uploaded", 0) + self.dev.lib.ms_h2d_bytes() - up0
 
     # ---- layout + tables ---------------------------------------------------------------------------
@@ -311,6 +316,8 @@ class BatchRenderer:
                 if n % 2 == 0:
                     pr["stereo_mode"] = 1
                     pr["coef"] = _bessel_coeffs(rp.stereo_theta)
+                    pr["rbuf"] = 2 * plane + extra               # right channel, written by the max pass
+                    extra += n
                 else:
                     pr["stereo_mode"] = 2
                     pr["rbuf"] = 2 * plane + extra + n          # [rolled copy | right channel]

@@ -64,9 +64,9 @@ def eval_breakpoints(pts, t, default):
 # --------------------------------------------------------------------------- event field (M:507-558)
 def generate_event_times(process, dur_s, rate, seed, cluster_size=6, cluster_spread_ms=25.0,
                          hawkes_gain=0.6, hawkes_decay_s=0.25):
-    rng = np.random.default_rng(int(seed) + 9999)
     if process == "Single" or rate <= 0:
-        return [0.0]
+        return [0.0]                      # (the reference seeds a generator first; it is never drawn from)
+    rng = np.random.default_rng(int(seed) + 9999)
     times = []
     if process == "Poisson":
         t = 0.0
@@ -109,7 +109,7 @@ def _edge():
 def lowpass_edge(sr, cutoff, roll):
     """Mask of lowpass_fft (M:43-58) as a falling skirt."""
     nyq = 0.5 * sr
-    fc = float(np.clip(cutoff, 1.0, nyq))
+    fc = float(min(max(cutoff, 1.0), nyq))            # np.clip (M:44)
     width = float(max(0.0, roll))
     e = _edge()
     if width <= 0:
@@ -233,7 +233,7 @@ class RenderPlan:
 
 
 def design_rate(base_sr, unfold):
-    return int(np.clip(int(round(base_sr * unfold)), base_sr, DESIGN_SR_CAP))
+    return int(min(max(int(round(base_sr * unfold)), base_sr), DESIGN_SR_CAP))     # np.clip on scalars (M:597, M:646)
 
 
 def grain_length(gen_sr, micro_ms):
@@ -287,7 +287,7 @@ def plan_render(params) -> RenderPlan:
         stretch = eval_breakpoints(lanes[3], t0, st_default)
         amp = 1.0
         if rate > 0:
-            amp *= np.clip(dens / max(1e-6, rate), 0.15, 4.0)
+            amp *= min(max(dens / max(1e-6, rate), 0.15), 4.0)          # np.clip (M:641)
         amp *= rng.uniform(1.0 - spread, 1.0 + spread)
         ufac = max(1.0, float(ufac))
         sr_evt = design_rate(base_sr, ufac)
@@ -318,7 +318,7 @@ def plan_render(params) -> RenderPlan:
     a = max(0, int(round(base_sr * float(params["env_a"]) / 1000.0)))
     d = max(0, int(round(base_sr * float(params["env_d"]) / 1000.0)))
     r = max(0, int(round(base_sr * float(params["env_r"]) / 1000.0)))
-    rp.adsr = (a, d, r, float(np.clip(float(params["env_s"]), 0, 1)), float(max(1e-6, float(params["env_curve"]))))
+    rp.adsr = (a, d, r, float(min(max(float(params["env_s"]), 0.0), 1.0)), float(max(1e-6, float(params["env_curve"]))))
 
     if params["er_cloud_on"]:
         offs, gains = reflection_taps(base_sr, int(params["er_taps"]), float(params["er_max_ms"]), seed)
@@ -326,14 +326,9 @@ def plan_render(params) -> RenderPlan:
         rp.er_offs, rp.er_gains = offs[keep].astype(np.int32), gains[keep]
     ir = params.get("_ir_audio")
     if params["space_ir_on"] and ir is not None:
-        h = np.asarray(ir)[:int(params["space_ir_max_samps"])]
-        if h.size >= 8:                       # M:439 (size counts both channels of a 2-D IR)
-            h = h[:IR_TAP_CAP].astype(np.float64)     # the mono mix is row-wise, so cut to 8192 rows first
-            if h.ndim > 1:
-                h = h.mean(axis=1)
-            rp.ir = h
+        rp.ir = _ir_taps(ir, int(params["space_ir_max_samps"]))
     if params["stereo_on"] and out_n >= 64:   # M:426: shorter outputs are duplicated
-        w = float(np.clip(float(params["stereo_width"]), 0.0, 1.0))
+        w = float(min(max(float(params["stereo_width"]), 0.0), 1.0))
         rp.stereo_on = True
         rp.stereo_dl = int(round((1 + 7 * w) * 0.0005 * base_sr))
         rp.stereo_dr = int(round((1 + 9 * w) * 0.0007 * base_sr))
@@ -341,6 +336,27 @@ def plan_render(params) -> RenderPlan:
     rp.drive = float(params["sat_drive"])
     rp.peak = float(params["peak"])
     return rp
+
+
+_TAPS_CACHE = {}
+
+
+def _ir_taps(ir, max_samps):
+    """convolve_ir_short's view of the IR (M:438-443): None if the slice has fewer than 8 values, else the
+    float64 mono mix of its first 8192 rows.  Cached per IR object: a sweep shares one IR."""
+    key = (id(ir), max_samps)
+    hit = _TAPS_CACHE.get(key)
+    if hit is not None and hit[0] is ir:
+        return hit[1]
+    h = np.asarray(ir)[:max_samps]
+    taps = None
+    if h.size >= 8:                           # size counts both channels of a 2-D IR
+        h = h[:IR_TAP_CAP].astype(np.float64)         # the mono mix is row-wise, so cut to 8192 rows first
+        taps = h.mean(axis=1) if h.ndim > 1 else h
+    if len(_TAPS_CACHE) > 64:
+        _TAPS_CACHE.clear()
+    _TAPS_CACHE[key] = (ir, taps)
+    return taps
 
 
 def reflection_taps(sr, taps, max_ms, seed):
@@ -366,3 +382,61 @@ def _plan_dust(ev, density):
     ev.dust_pos = pos.astype(np.int32)
     ev.dust_val = dense[pos]
     ev.ker_len = max(8, int(0.01 * n))
+
+
+# --------------------------------------------------------------------------- batch planning
+_POOL = None
+_IR_CACHE = {}
+
+
+def _slim_params(p):
+    """Copy of a parameter dict whose impulse response is already reduced to what the planner keeps:
+    the mono mix of the first 8192 rows (M:441-443).  Planning the copy gives the identical plan."""
+    ir = p.get("_ir_audio")
+    if ir is None:
+        return p
+    q = dict(p)
+    a = np.asarray(ir)
+    if a[:int(p["space_ir_max_samps"])].size < 8:          # M:439 is evaluated on the full (2-D) slice
+        q["_ir_audio"] = None
+        return q
+    key = (id(ir), a.shape)
+    hit = _IR_CACHE.get(key)
+    if hit is None or hit[0] is not ir:
+        h = a[:IR_TAP_CAP].astype(np.float64)
+        if h.ndim > 1:
+            h = h.mean(axis=1)
+        if len(_IR_CACHE) > 64:
+            _IR_CACHE.clear()
+        _IR_CACHE[key] = hit = (ir, h)
+    q["_ir_audio"] = hit[1]
+    if hit[1].size < 8:                                    # keep the planner's own size test true
+        q["_ir_audio"] = np.concatenate([hit[1], np.zeros(8 - hit[1].size)]) if False else hit[1]
+    return q
+
+
+def _plan_chunk(chunk):
+    return [plan_render(p) for p in chunk]
+
+
+def plan_many(params_list, workers=None):
+    """Plans of many independent renders.  Planning is pure host work (numpy Generators, Python
+    rounding); large batches are planned by a pool of forked worker processes."""
+    import os
+    n = len(params_list)
+    if workers is None:
+        workers = min(32, len(os.sched_getaffinity(0)))
+    if n < 128 or workers <= 1 or os.environ.get("MS_PLAN_WORKERS", "") == "1":
+        return [plan_render(p) for p in params_list]
+    global _POOL
+    import multiprocessing as mp
+    if _POOL is None or _POOL[1] != workers:
+        _POOL = (mp.get_context("fork").Pool(workers), workers)
+    # one shared IR object per batch would be pickled with every chunk: send it once per chunk only
+    per = max(16, (n + 4 * workers - 1) // (4 * workers))
+    slim = [_slim_params(p) for p in params_list]       # do not pickle multi-MB impulse responses per render
+    chunks = [slim[i:i + per] for i in range(0, n, per)]
+    out = []
+    for part in _POOL[0].map(_plan_chunk, chunks):
+        out.extend(part)
+    return out

@@ -142,7 +142,7 @@ typedef struct {
 typedef struct {
     int64_t y;                /* mono input offset */
     int64_t out;              /* output offset in frames */
-    int64_t rbuf;             /* stereo_mode 2: offset of the precomputed right channel in `mono` */
+    int64_t rbuf;             /* offset in `mono` of the right channel: written by ms_post (mode 1), read (mode 2) */
     int32_t n;
     int32_t stereo_mode;      /* 0 duplicate, 1 Bessel FIR (even n), 2 precomputed */
     int32_t dl, dr;
@@ -179,7 +179,7 @@ typedef struct {
     REAL* mono_out, void* workspace, size_t workspace_bytes, void* stream, void** handle); \
     int ms_fir_run##SFX(void* handle, void* stream); \
     void ms_fir_destroy##SFX(void* handle); \
-    int ms_post##SFX(const ms_post_render* dev_renders, int n_renders, int max_n, const REAL* mono, uint64_t* maxbits, \
+    int ms_post##SFX(const ms_post_render* dev_renders, int n_renders, int max_n, REAL* mono, uint64_t* maxbits, \
     float* out, void* stream); \
     int ms_roll##SFX(const REAL* src, REAL* dst, int n, int shift, void* stream);
 MS_DECLARE_API(_f32, float)
