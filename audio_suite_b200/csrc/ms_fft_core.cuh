@@ -12,23 +12,35 @@
 
 #define MS_MAX_RADICES 12
 
-// Tile geometry: element i of vector v sits at float2 index  v*vs + pad(i*es)  where
-// pad(a) = a + (a >> 4) skews every 16 complex by one slot (kills the stride-R bank conflicts of the
-// early Stockham writes in the contiguous layout; harmless in the column layout).
+// Tile geometry: element i of vector v sits at complex index  v*vs + pad(i*es)  where pad() skews every
+// 128 bytes of complex data (16 float2 / 8 double2 = all 32 banks) by one slot: that kills the stride-R
+// bank conflicts of the early Stockham writes in the contiguous layout and is harmless in the column layout.
 struct TileGeom {
     int cnt;   // vectors in the tile
     int vs;    // stride between vectors (float2 units, already padded)
     int es;    // stride between consecutive elements of one vector before padding
     int colmajor;  // 1: consecutive threads walk vectors (column tiles), 0: walk elements (row tiles)
 };
-MS_HD int ms_pad(int a) { return a + (a >> 4); }
+MS_HD int ms_pad(int a) { return a + (a >> (sizeof(cpx) == 16 ? 3 : 4)); }
 MS_HD int tile_addr(const TileGeom& g, int v, int i) { return v * g.vs + ms_pad(i * g.es); }
 
 struct RadixPlan {
     int F;                       // vector length
     int nrad;                    // number of passes
     unsigned char rad[MS_MAX_RADICES];
+    unsigned mg_ns[MS_MAX_RADICES];   // magic multipliers: x / Ns_i  == umulhi(x, mg_ns[i])  (0: divisor is 1)
+    unsigned mg_pv[MS_MAX_RADICES];   //                    x / (F / rad_i)
 };
+// q = x / d for 0 <= x < 2^16-ish ranges used here (x * d' never overflows): m = floor(2^32 / d) + 1
+static inline unsigned ms_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / d) + 1u; }
+MS_HD unsigned ms_mulhi32(unsigned a, unsigned b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (unsigned)(((unsigned long long)a * b) >> 32);
+#endif
+}
+MS_HD int ms_fastdiv(int x, unsigned magic) { return magic ? (int)ms_mulhi32((unsigned)x, magic) : x; }
 
 // Factor F into radices from {8,4,2,3,5}.  Returns 0 if F has another prime factor.
 static inline int ms_make_radix_plan(int F, RadixPlan* p) {
@@ -44,6 +56,12 @@ static inline int ms_make_radix_plan(int F, RadixPlan* p) {
     for (int i = 0; i < n2; ++i) p->rad[p->nrad++] = 2;
     while (m % 5 == 0) { m /= 5; if (p->nrad >= MS_MAX_RADICES) return 0; p->rad[p->nrad++] = 5; }
     while (m % 3 == 0) { m /= 3; if (p->nrad >= MS_MAX_RADICES) return 0; p->rad[p->nrad++] = 3; }
+    int Ns = 1;
+    for (int i = 0; i < p->nrad; ++i) {
+        p->mg_ns[i] = ms_magic((unsigned)Ns);
+        p->mg_pv[i] = ms_magic((unsigned)(F / p->rad[i]));
+        Ns *= p->rad[i];
+    }
     return m == 1;
 }
 
@@ -114,9 +132,11 @@ template <> struct Bfly<8> {
 // ---- one Stockham pass over a tile ----------------------------------------------------------------
 // Out of place (src -> dst, two shared-memory buffers ping-pong): a thread finishes one butterfly
 // before it starts the next, so nothing but the R values of a butterfly lives in registers and one
-// barrier per pass suffices.  tw = table of w_F^i (i < F), forward sign.
+// barrier per pass suffices.  tw = table of w_F^i (i < F), forward sign.  Integer divisions by the
+// per-pass constants go through host-computed magic multipliers.
 template <int R>
 MS_DEV void stockham_pass(const cpx* MS_RESTRICT src, cpx* MS_RESTRICT dst, const TileGeom& g, int F, int Ns,
+                          unsigned mg_ns, unsigned mg_pv, unsigned mg_cnt,
                           const cpx* MS_RESTRICT tw, const Ctx& c) {
     const int per_vec = F / R;
     const int nb = per_vec * g.cnt;
@@ -124,14 +144,30 @@ MS_DEV void stockham_pass(const cpx* MS_RESTRICT src, cpx* MS_RESTRICT dst, cons
 #pragma unroll 2
     for (int b = c.tid; b < nb; b += c.nthr) {
         int vec, j;
-        if (g.colmajor) { j = b / g.cnt; vec = b - j * g.cnt; } else { vec = b / per_vec; j = b - vec * per_vec; }
-        const int k = (Ns == 1) ? 0 : (j % Ns);
+        if (g.colmajor) { j = ms_fastdiv(b, mg_cnt); vec = b - j * g.cnt; } else { vec = ms_fastdiv(b, mg_pv); j = b - vec * per_vec; }
+        const int k = j - ms_fastdiv(j, mg_ns) * Ns;
         cpx v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = src[tile_addr(g, vec, j + q * per_vec)];
         if (k != 0) {
-#pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = c_mul(v[q], __ldg(&tw[q * k * tws]));
+            // powers of w = w_F^(k*tws): load w, w^2, w^4 (each rounded once), multiply the rest
+            const cpx w1 = __ldg(&tw[k * tws]);
+            if (R == 2) { v[1] = c_mul(v[1], w1); }
+            else {
+                const cpx w2 = __ldg(&tw[2 * k * tws]);
+                if (R == 3) { v[1] = c_mul(v[1], w1); v[2] = c_mul(v[2], w2); }
+                else {
+                    const cpx w3 = c_mul(w1, w2);
+                    if (R == 4) { v[1] = c_mul(v[1], w1); v[2] = c_mul(v[2], w2); v[3] = c_mul(v[3], w3); }
+                    else {
+                        const cpx w4 = __ldg(&tw[4 * k * tws]);
+                        v[1] = c_mul(v[1], w1); v[2] = c_mul(v[2], w2); v[3] = c_mul(v[3], w3); v[4] = c_mul(v[4], w4);
+                        if (R == 8) {
+                            v[5] = c_mul(v[5], c_mul(w4, w1)); v[6] = c_mul(v[6], c_mul(w4, w2)); v[7] = c_mul(v[7], c_mul(w4, w3));
+                        }
+                    }
+                }
+            }
         }
         Bfly<R>::run(v);
         const int base = (j - k) * R + k;
@@ -145,14 +181,16 @@ MS_DEV void stockham_pass(const cpx* MS_RESTRICT src, cpx* MS_RESTRICT dst, cons
 // filling it), `b` is the second buffer of the same size.  Returns the buffer that holds the result.
 MS_DEV cpx* tile_fft(cpx* a, cpx* b, const TileGeom& g, const RadixPlan& p, const cpx* MS_RESTRICT tw, const Ctx& c) {
     int Ns = 1;
+    const unsigned mg_cnt = g.cnt <= 1 ? 0u : (unsigned)(0x100000000ull / (unsigned)g.cnt) + 1u;
     for (int i = 0; i < p.nrad; ++i) {
         const int r = p.rad[i];
+        const unsigned mn = p.mg_ns[i], mp = p.mg_pv[i];
         switch (r) {
-            case 8: stockham_pass<8>(a, b, g, p.F, Ns, tw, c); break;
-            case 4: stockham_pass<4>(a, b, g, p.F, Ns, tw, c); break;
-            case 2: stockham_pass<2>(a, b, g, p.F, Ns, tw, c); break;
-            case 3: stockham_pass<3>(a, b, g, p.F, Ns, tw, c); break;
-            default: stockham_pass<5>(a, b, g, p.F, Ns, tw, c); break;
+            case 8: stockham_pass<8>(a, b, g, p.F, Ns, mn, mp, mg_cnt, tw, c); break;
+            case 4: stockham_pass<4>(a, b, g, p.F, Ns, mn, mp, mg_cnt, tw, c); break;
+            case 2: stockham_pass<2>(a, b, g, p.F, Ns, mn, mp, mg_cnt, tw, c); break;
+            case 3: stockham_pass<3>(a, b, g, p.F, Ns, mn, mp, mg_cnt, tw, c); break;
+            default: stockham_pass<5>(a, b, g, p.F, Ns, mn, mp, mg_cnt, tw, c); break;
         }
         cpx* t = a; a = b; b = t;
         Ns *= r;
