@@ -164,12 +164,12 @@ MS_DEV real synth_sample(const SynthEvt& E, int j, real z) {
     real x;
     if (E.mode == SY_GAUSS) {
         const real q = fj / (real)E.sigma;
-        x = (real)expf((float)(-(real)0.5 * q * q)) * (z * (real)0.12 + (real)1.0);
+        x = r_exp(-(real)0.5 * q * q) * (z * (real)0.12 + (real)1.0);
     } else if (E.mode == SY_RES) {
         double cyc = (double)j * E.f_over_sr;
         cyc -= floor(cyc);
-        const real tone = r_sinpi((real)2.0 * (real)cyc) * (real)expf(-(float)j * (float)E.ring_decay);
-        x = (real)0.9 * tone + (real)0.25 * z * (real)expf(-(float)j * (float)E.env_decay);
+        const real tone = r_sinpi((real)2.0 * (real)cyc) * r_exp(-fj * (real)E.ring_decay);
+        x = (real)0.9 * tone + (real)0.25 * z * r_exp(-(real)j * (real)E.env_decay);
     } else if (E.mode == SY_PLAIN) {
         x = z * (real)0.1;
     } else {
@@ -281,7 +281,7 @@ MS_DEV void synth_tilt_finish_body(const SynthEvt* MS_RESTRICT evts, real* MS_RE
             const real b = pv > (real)0. ? pv : (real)0.;
             v = a - b;
         }
-        out[j] = v * (real)expf(-(float)j * (float)E.env_decay) * fade_gain(j, E.n, E.fade, E.inv_fade);
+        out[j] = v * r_exp(-(real)j * (real)E.env_decay) * fade_gain(j, E.n, E.fade, E.inv_fade);
     }
 }
 
@@ -303,7 +303,7 @@ MS_DEV void synth_dust_body(const SynthEvt* MS_RESTRICT evts, const int* MS_REST
         for (int q = lo_i; q < E.dust_count; ++q) {
             const int p = __ldg(&pos[q]);
             if (p > hi) break;
-            acc += __ldg(&val[q]) * (real)expf(-(float)rate * (float)(hi - p));
+            acc += __ldg(&val[q]) * r_exp(-rate * (real)(hi - p));
         }
         out[j] = acc * fade_gain(j, E.n, E.fade, E.inv_fade);
     }

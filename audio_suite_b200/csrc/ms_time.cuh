@@ -13,14 +13,14 @@ typedef ms_ola_evt OlaEvt;
 
 
 MS_DEV real adsr_gain(const OlaRender& R, int i) {
-    // The envelope multiplies each sample, so its rounding is relative to that sample (not to the peak):
-    // the power curve is evaluated in float32 in both precisions.
-    const float S = (float)R.S, curve = (float)R.curve;
-    if (i < R.A) return (real)powf((float)((double)i * R.inv_A), curve);
-    if (i < R.D_end) return (real)(1.0f - (1.0f - S) * powf((float)((double)(i - R.A) * R.inv_D), curve));
-    if (i < R.sus_end || !R.has_release) return (real)R.S;
-    const float r = (i == R.out_n - 1 && R.out_n - R.sus_end > 1) ? 1.0f : (float)((double)(i - R.sus_end) * R.inv_R);
-    return (real)(S * (1.0f - powf(r, curve)));
+    // Evaluated in the working precision: an error relative to a loud sample is still an error relative
+    // to the peak, and the FIR gain + soft clip downstream turn 1e-7 of that into 1e-5 (precision).
+    const real S = (real)R.S, curve = (real)R.curve;
+    if (i < R.A) return r_pow((real)((double)i * R.inv_A), curve);
+    if (i < R.D_end) return (real)1.0 - ((real)1.0 - S) * r_pow((real)((double)(i - R.A) * R.inv_D), curve);
+    if (i < R.sus_end || !R.has_release) return S;
+    const real r = (i == R.out_n - 1 && R.out_n - R.sus_end > 1) ? (real)1.0 : (real)((double)(i - R.sus_end) * R.inv_R);
+    return S * ((real)1.0 - r_pow(r, curve));
 }
 
 // grid = (ceil(max out_n / OLA_TILE), renders), block = OLA_NTHR.  Gather form: every output sample

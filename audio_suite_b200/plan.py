@@ -385,7 +385,6 @@ def _plan_dust(ev, density):
 
 
 # --------------------------------------------------------------------------- batch planning
-_POOL = None
 _IR_CACHE = {}
 
 
@@ -413,30 +412,3 @@ def _slim_params(p):
     if hit[1].size < 8:                                    # keep the planner's own size test true
         q["_ir_audio"] = np.concatenate([hit[1], np.zeros(8 - hit[1].size)]) if False else hit[1]
     return q
-
-
-def _plan_chunk(chunk):
-    return [plan_render(p) for p in chunk]
-
-
-def plan_many(params_list, workers=None):
-    """Plans of many independent renders.  Planning is pure host work (numpy Generators, Python
-    rounding); large batches are planned by a pool of forked worker processes."""
-    import os
-    n = len(params_list)
-    if workers is None:
-        workers = min(32, len(os.sched_getaffinity(0)))
-    if n < 128 or workers <= 1 or os.environ.get("MS_PLAN_WORKERS", "") == "1":
-        return [plan_render(p) for p in params_list]
-    global _POOL
-    import multiprocessing as mp
-    if _POOL is None or _POOL[1] != workers:
-        _POOL = (mp.get_context("fork").Pool(workers), workers)
-    # one shared IR object per batch would be pickled with every chunk: send it once per chunk only
-    per = max(16, (n + 4 * workers - 1) // (4 * workers))
-    slim = [_slim_params(p) for p in params_list]       # do not pickle multi-MB impulse responses per render
-    chunks = [slim[i:i + per] for i in range(0, n, per)]
-    out = []
-    for part in _POOL[0].map(_plan_chunk, chunks):
-        out.extend(part)
-    return out

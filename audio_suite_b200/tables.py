@@ -1,0 +1,455 @@
+"""Job tables: RenderPlans -> flat, relocatable numpy tables -> one merged batch.
+
+`pack_chunk(plans)` lays a list of render plans out in chunk-local coordinates (every offset starts at
+0) and returns plain numpy arrays, so chunks can be built by worker processes and pickled cheaply;
+`merge_chunks` concatenates them, shifts every offset field by the chunk's base in its buffer, and pairs
+the spectral jobs across the whole batch (two signals of equal length share one complex transform).
+A single in-process chunk goes through exactly the same code.
+
+Buffers (offsets in elements): pool (real; per-event signals), mono (real; per chunk:
+[OLA plane | FIR plane | right channels / odd-length scratch]), out (float32 frames), hpool (real;
+combined FIR taps), taps (reflection delays/gains), irs (deduplicated IR taps), dust (impulses).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _abi, plan as P
+
+_SPEC_OP_BYTES = np.dtype(_abi.SpecOp).itemsize
+_SPEC_JOB = np.dtype(_abi.SpecJob)
+_ZERO_OP = np.zeros(_SPEC_OP_BYTES, np.uint8)
+
+
+def _recs(ctype, n):
+    return np.zeros(n, dtype=np.dtype(ctype))
+
+
+_BESSEL = {}
+
+
+def bessel_coeffs(theta, K=_abi.POST_K):
+    """J_m(theta), m = -K..K by the ascending series (theta <= 0.9 here).  exp(i theta sin(phi)) =
+    sum_m J_m(theta) exp(i m phi): for even n the rotation of spectral_diffusion_stereo (main_v2.py:432-435)
+    is exactly a (2K+1)-tap circular FIR with taps at even lags."""
+    hit = _BESSEL.get(theta)
+    if hit is not None:
+        return hit
+    out = np.zeros(2 * K + 1)
+    for m in range(K + 1):
+        s, k = 0.0, 0
+        while True:
+            term = (-1.0) ** k * (theta / 2.0) ** (2 * k + m) / (math.factorial(k) * math.factorial(k + m))
+            s += term
+            k += 1
+            if abs(term) < 1e-22 or k > 40:
+                break
+        out[K + m] = s
+        out[K - m] = s * (-1.0) ** m
+    if len(_BESSEL) > 256:
+        _BESSEL.clear()
+    _BESSEL[theta] = out
+    return out
+
+
+class _Items:
+    """Spectral work items (n, in, out, operator bytes) of one stage."""
+
+    def __init__(self):
+        self.n, self.src, self.dst, self.ops = [], [], [], []
+
+    def add(self, n, src, dst, op):
+        self.n.append(n)
+        self.src.append(src)
+        self.dst.append(dst)
+        self.ops.append(bytes(op))
+
+    def arrays(self):
+        k = len(self.n)
+        ops = np.frombuffer(b"".join(self.ops), dtype=np.uint8).reshape(k, _SPEC_OP_BYTES) if k else np.zeros((0, _SPEC_OP_BYTES), np.uint8)
+        return (np.asarray(self.n, np.int64), np.asarray(self.src, np.int64), np.asarray(self.dst, np.int64), ops)
+
+
+@dataclass
+class Tables:
+    sy1: np.ndarray = None
+    sy2: np.ndarray = None
+    ola_r: np.ndarray = None
+    ola_e: np.ndarray = None
+    fir: np.ndarray = None
+    post: np.ndarray = None
+    tap_off: np.ndarray = None
+    tap_gain: np.ndarray = None
+    irs: np.ndarray = None
+    dust_pos: np.ndarray = None
+    dust_val: np.ndarray = None
+    tilt: tuple = None          # (n, src, dst, ops)
+    grain: tuple = None
+    rot: tuple = None
+    odd: np.ndarray = None      # rows: y_at, scratch, n, dr   (odd-length stereo)
+    pool_n: int = 0
+    mono_n: int = 0
+    frames: int = 0
+    h_total: int = 0
+    max_h: int = 0
+    max_out_n: int = 0
+    out_at: np.ndarray = None   # per render: first frame
+    out_n: np.ndarray = None
+    y_at: np.ndarray = None
+    last: np.ndarray = None     # per render: micro_at, grain_at, n of the last event (-1 if none)
+    srs: np.ndarray = None      # per render: base_sr, design_sr_base
+    alg: dict = field(default_factory=dict)   # algorithmic element counts per stage
+
+
+def pack_chunk(plans) -> Tables:
+    R = len(plans)
+    n_evt = sum(len(rp.events) for rp in plans)
+    sy1, sy2 = _recs(_abi.SynthEvt, n_evt), _recs(_abi.SynthEvt, n_evt)
+    ola_r, post = _recs(_abi.OlaRender, R), _recs(_abi.PostRender, R)
+    ola_e = []
+    fir = []
+    tilt, grain, rot = _Items(), _Items(), _Items()
+    dust_pos, dust_val, n_dust = [], [], 0
+    tap_off, tap_gain, n_taps = [], [], 0
+    irs, ir_index, n_ir = [], {}, 0
+    pool_n = mono_n = h_total = max_h = 0
+    mono_at, last = [], np.full((R, 3), -1, np.int64)
+    fir_of = {}
+    alg = dict(synth=0, tilt_spectral=0, grain_spectral=0, overlap_add=0, fir_in=0, fir_taps=0, post=0)
+    e = 0
+    for r, rp in enumerate(plans):
+        a, d, rel, S, curve = rp.adsr
+        n = rp.out_n
+        if a > n:
+            raise ValueError(f"could not broadcast input array from shape ({a},) into shape ({n},)")   # main_v2.py:182
+        d_end = min(n, a + d) if d > 0 else a
+        sus_end = max(d_end, n - rel)
+        ev_begin = len(ola_e)
+        max_len = 0
+        x_begin, x_end = n, 0
+        for ev in rp.events:
+            st = np.random.PCG64(ev.seed).state["state"]
+            s_hi, s_lo = st["state"] >> 64, st["state"] & 0xFFFFFFFFFFFFFFFF
+            i_hi, i_lo = st["inc"] >> 64, st["inc"] & 0xFFFFFFFFFFFFFFFF
+            micro = pool_n
+            pool_n += ev.n
+            out1, mode2, aux2, dust_b, dust_c = micro, -1, 0, 0, 0
+            alg["synth"] += ev.n
+            if ev.mode == P.MODE_DUST:
+                dust_b, dust_c = n_dust, len(ev.dust_pos)
+                dust_pos.append(ev.dust_pos)
+                dust_val.append(ev.dust_val)
+                n_dust += dust_c
+            elif ev.mode in (P.MODE_NOISE, P.MODE_SKEW):
+                raw, tilted = pool_n, pool_n + ev.n
+                pool_n += 2 * ev.n
+                out1, mode2, aux2 = raw, ev.mode, tilted
+                tilt.add(ev.n, raw, tilted, ev.tilt)
+                alg["tilt_spectral"] += 2 * ev.n
+            common = (s_hi, s_lo, i_hi, i_lo, ev.n)
+            tail = (ev.fade, ev.sigma)
+            sy1[e] = common + (ev.mode,) + tail + (out1, ev.f_over_sr, 1.0 / ev.fade, ev.ring_decay, ev.env_decay,
+                                                     dust_b, dust_c, ev.ker_len, 0)
+            sy2[e] = common + (mode2,) + tail + (micro, ev.f_over_sr, 1.0 / ev.fade, ev.ring_decay, ev.env_decay,
+                                                  0, 0, ev.ker_len, aux2)
+            g_at = micro
+            if ev.spec is not None:
+                g_at = pool_n
+                pool_n += ev.n
+                grain.add(ev.n, micro, g_at, ev.spec)
+                alg["grain_spectral"] += 2 * ev.n * (int(ev.spec.lp_on) + int(ev.spec.stretch_on) + (1 if ev.spec.n_bands else 0))
+            last[r] = (micro, g_at, ev.n)
+            if ev.placed:
+                ola_e.append((g_at + ev.offset, ev.start, ev.length, ev.amp))
+                max_len = max(max_len, ev.length)
+                # grain[0] is exactly 0 (fade-in starts at 0, main_v2.py:267): with no offset the first placed
+                # sample is an exact zero
+                x_begin = min(x_begin, ev.start + (1 if ev.offset == 0 else 0))
+                x_end = max(x_end, ev.start + ev.length)
+                alg["overlap_add"] += ev.length
+            e += 1
+        ola_r[r] = (mono_n, n, ev_begin, len(ola_e), max_len, a, d_end, sus_end, 1 if (rel > 0 and n > sus_end) else 0,
+                    1.0 / a if a > 0 else 0.0, 1.0 / (d_end - a) if d_end > a else 0.0,
+                    1.0 / (n - sus_end - 1) if n - sus_end > 1 else 0.0, S, curve)
+        alg["overlap_add"] += n
+        # FIR: reflection cloud folded into the impulse response
+        has_er = rp.er_offs is not None and rp.er_offs.size > 0
+        if has_er or rp.ir is not None:
+            if rp.ir is not None:
+                key = rp.ir.ctypes.data if rp.ir.flags.owndata else rp.ir.tobytes()
+                hit = ir_index.get(key)
+                if hit is None or (not isinstance(key, bytes) and hit[2] is not rp.ir):
+                    hit = ir_index[key] = (n_ir, rp.ir.size, rp.ir)
+                    irs.append(rp.ir)
+                    n_ir += rp.ir.size
+                alg["fir_in"] += 2 * n
+                alg["fir_taps"] += rp.ir.size
+            else:
+                hit = ir_index.get(b"delta")
+                if hit is None:
+                    hit = ir_index[b"delta"] = (n_ir, 1, None)
+                    irs.append(np.ones(1))
+                    n_ir += 1
+            ir_at, ir_len = hit[0], hit[1]
+            t0 = n_taps
+            h_len = ir_len
+            if has_er:
+                if rp.er_offs.size > 4096:
+                    raise ValueError("er_taps > 4096 is outside the accelerated path")
+                tap_off.append(rp.er_offs)
+                tap_gain.append(rp.er_gains)
+                n_taps += rp.er_offs.size
+                h_len = ir_len + int(rp.er_offs.max())
+                alg["fir_in"] += 2 * n
+            if x_begin == 0 and a > 0:
+                x_begin = 1                      # env[0] = 0 ** curve = 0 (main_v2.py:181-182)
+            fir_of[r] = len(fir)
+            fir.append((ir_at, ir_len, h_len, h_total, t0, n_taps, mono_n, 0, n, min(x_begin, x_end), x_end, 0))
+            h_total += h_len
+            max_h = max(max_h, h_len)
+        mono_at.append(mono_n)
+        mono_n += n
+    plane = mono_n
+    extra = 0
+    frames = 0
+    odd = []
+    out_at, out_n, y_at = np.zeros(R, np.int64), np.zeros(R, np.int64), np.zeros(R, np.int64)
+    fir_arr = _recs(_abi.FirRender, len(fir))
+    for i, f in enumerate(fir):
+        fir_arr[i] = f
+    for r, rp in enumerate(plans):
+        n = rp.out_n
+        y = mono_at[r]
+        if r in fir_of:
+            y = plane + mono_at[r]
+            fir_arr[fir_of[r]]["y"] = y
+        mode, dl, dr, rbuf = 0, 0, 0, 0
+        coef = np.zeros(2 * _abi.POST_K + 1)
+        if rp.stereo_on:
+            dl, dr = rp.stereo_dl, rp.stereo_dr
+            if n % 2 == 0:
+                mode, coef, rbuf = 1, bessel_coeffs(rp.stereo_theta), 2 * plane + extra     # right channel, written by the max pass
+                extra += n
+            else:
+                mode, rbuf = 2, 2 * plane + extra + n                                        # [rolled copy | right channel]
+                odd.append((y, 2 * plane + extra, n, dr))
+                op = _abi.SpecOp()
+                op.kind, op.alpha = _abi.OP_ROT, rp.stereo_theta
+                rot.add(n, 2 * plane + extra, 2 * plane + extra + n, op)
+                extra += 2 * n
+        post[r] = (y, frames, rbuf, n, mode, dl, dr, rp.drive, 1.0 / math.tanh(rp.drive) if rp.drive > 0 else 1.0, rp.peak, coef)
+        out_at[r], out_n[r], y_at[r] = frames, n, y
+        frames += n
+        alg["post"] += n
+    t = Tables()
+    t.sy1, t.sy2, t.ola_r, t.post, t.fir = sy1, sy2, ola_r, post, fir_arr
+    t.ola_e = _recs(_abi.OlaEvt, len(ola_e))
+    for i, rec in enumerate(ola_e):
+        t.ola_e[i] = rec
+    t.tap_off = np.concatenate(tap_off).astype(np.int32) if tap_off else np.zeros(0, np.int32)
+    t.tap_gain = np.concatenate(tap_gain).astype(np.float64) if tap_gain else np.zeros(0)
+    t.irs = np.concatenate(irs).astype(np.float64) if irs else np.zeros(0)
+    t.dust_pos = np.concatenate(dust_pos).astype(np.int32) if dust_pos else np.zeros(0, np.int32)
+    t.dust_val = np.concatenate(dust_val).astype(np.float64) if dust_val else np.zeros(0)
+    t.tilt, t.grain, t.rot = tilt.arrays(), grain.arrays(), rot.arrays()
+    t.odd = np.asarray(odd, np.int64).reshape(-1, 4)
+    t.pool_n, t.mono_n, t.frames, t.h_total, t.max_h = pool_n, 2 * plane + extra, frames, h_total, max_h
+    t.max_out_n = max((rp.out_n for rp in plans), default=0)
+    t.out_at, t.out_n, t.y_at, t.last = out_at, out_n, y_at, last
+    t.srs = np.asarray([(rp.base_sr, rp.design_sr_base) for rp in plans], np.int64).reshape(-1, 2)
+    t.alg = alg
+    return t
+
+
+def _shift(arr, fields, base):
+    if arr.size and base:
+        for f in fields:
+            arr[f] += base
+
+
+def merge_chunks(chunks) -> Tables:
+    if len(chunks) == 1:
+        return chunks[0]
+    m = Tables()
+    pool_b = mono_b = frame_b = h_b = tap_b = ir_b = dust_b = olae_b = 0
+    parts = {k: [] for k in ("sy1", "sy2", "ola_r", "ola_e", "fir", "post", "tap_off", "tap_gain", "irs", "dust_pos", "dust_val",
+                             "odd", "out_at", "out_n", "y_at", "last", "srs")}
+    items = {k: [[], [], [], []] for k in ("tilt", "grain", "rot")}
+    alg = {}
+    for c in chunks:
+        _shift(c.sy1, ("out",), pool_b)
+        _shift(c.sy1, ("dust_begin",), dust_b)
+        _shift(c.sy2, ("out", "aux"), pool_b)
+        _shift(c.ola_r, ("out",), mono_b)
+        _shift(c.ola_r, ("ev_begin", "ev_end"), olae_b)
+        _shift(c.ola_e, ("grain",), pool_b)
+        _shift(c.fir, ("ir",), ir_b)
+        _shift(c.fir, ("h",), h_b)
+        _shift(c.fir, ("tap_begin", "tap_end"), tap_b)
+        _shift(c.fir, ("x", "y"), mono_b)
+        _shift(c.post, ("y", "rbuf"), mono_b)
+        _shift(c.post, ("out",), frame_b)
+        if c.odd.size:
+            c.odd[:, 0:2] += mono_b
+        c.out_at += frame_b
+        c.y_at += mono_b
+        if c.last.size:
+            c.last[:, 0:2] += np.where(c.last[:, 0:2] >= 0, pool_b, 0)
+        for k in parts:
+            parts[k].append(getattr(c, k))
+        for k, base in (("tilt", pool_b), ("grain", pool_b), ("rot", mono_b)):
+            n, s, d, ops = getattr(c, k)
+            items[k][0].append(n)
+            items[k][1].append(s + base)
+            items[k][2].append(d + base)
+            items[k][3].append(ops)
+        for k, v in c.alg.items():
+            alg[k] = alg.get(k, 0) + v
+        pool_b += c.pool_n
+        mono_b += c.mono_n
+        frame_b += c.frames
+        h_b += c.h_total
+        tap_b += c.tap_off.size
+        ir_b += c.irs.size
+        dust_b += c.dust_pos.size
+        olae_b += c.ola_e.size
+        m.max_h = max(m.max_h, c.max_h)
+        m.max_out_n = max(m.max_out_n, c.max_out_n)
+    for k in parts:
+        setattr(m, k, np.concatenate(parts[k]))
+    for k in items:
+        setattr(m, k, tuple(np.concatenate(x) for x in items[k]))
+    m.pool_n, m.mono_n, m.frames, m.h_total, m.alg = pool_b, mono_b, frame_b, h_b, alg
+    return m
+
+
+def pair_jobs(items):
+    """(n, src, dst, ops) -> SpecJob record array.  Two signals of equal n share one complex transform;
+    the leftover of an odd group rides alone."""
+    n, src, dst, ops = items
+    k = n.size
+    if k == 0:
+        return np.zeros(0, _SPEC_JOB)
+    order = np.argsort(n, kind="stable")
+    n, src, dst, ops = n[order], src[order], dst[order], ops[order]
+    starts = np.flatnonzero(np.r_[True, n[1:] != n[:-1]])
+    pos = np.arange(k) - np.repeat(starts, np.diff(np.r_[starts, k]))      # index inside its equal-n group
+    first = pos % 2 == 0
+    has_partner = np.zeros(k, bool)
+    has_partner[:-1] = first[:-1] & (n[1:] == n[:-1]) & (pos[1:] == pos[:-1] + 1)
+    a = np.flatnonzero(first)
+    b = a + 1
+    paired = has_partner[a]
+    jobs = np.zeros(a.size, _SPEC_JOB)
+    raw = jobs.view(np.uint8).reshape(a.size, _SPEC_JOB.itemsize)
+    jobs["n"] = n[a]
+    jobs["in_a"], jobs["out_a"] = src[a], dst[a]
+    bb = np.where(paired, np.minimum(b, k - 1), 0)
+    jobs["in_b"] = np.where(paired, src[bb], -1)
+    jobs["out_b"] = np.where(paired, dst[bb], -1)
+    op0 = _SPEC_JOB.fields["op"][1]
+    raw[:, op0:op0 + _SPEC_OP_BYTES] = ops[a]
+    raw[:, op0 + _SPEC_OP_BYTES:op0 + 2 * _SPEC_OP_BYTES] = np.where(paired[:, None], ops[bb], _ZERO_OP[None, :])
+    return jobs
+
+
+# --------------------------------------------------------------------------- worker pool
+class _WorkerPool:
+    """Persistent `python -m audio_suite_b200.plan_worker` subprocesses, one feeder thread each."""
+
+    def __init__(self, size):
+        import os
+        import subprocess
+        import sys
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env = dict(os.environ)
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        env["OMP_NUM_THREADS"] = env["OPENBLAS_NUM_THREADS"] = "1"
+        self.size = size
+        self.procs = [subprocess.Popen([sys.executable, "-m", "audio_suite_b200.plan_worker"], stdin=subprocess.PIPE,
+                                       stdout=subprocess.PIPE, env=env) for _ in range(size)]
+
+    def map(self, chunks):
+        import pickle
+        import struct
+        import threading
+        results = [None] * len(chunks)
+        errors = []
+        todo = list(enumerate(chunks))
+        lock = threading.Lock()
+
+        def serve(proc):
+            while True:
+                with lock:
+                    if not todo or errors:
+                        return
+                    i, chunk = todo.pop(0)
+                try:
+                    blob = pickle.dumps(chunk, protocol=pickle.HIGHEST_PROTOCOL)
+                    proc.stdin.write(struct.pack("<Q", len(blob)))
+                    proc.stdin.write(blob)
+                    proc.stdin.flush()
+                    head = proc.stdout.read(8)
+                    if len(head) < 8:
+                        raise RuntimeError("planning worker died")
+                    status, payload = pickle.loads(proc.stdout.read(struct.unpack("<Q", head)[0]))
+                    if status != "ok":
+                        raise payload
+                    results[i] = payload
+                except BaseException as e:
+                    errors.append(e)
+                    return
+        threads = [threading.Thread(target=serve, args=(p,)) for p in self.procs]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            self.close()
+            raise errors[0]
+        return results
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.close()
+                p.terminate()
+            except Exception:
+                pass
+        self.procs = []
+
+
+_POOL = None
+
+
+def shutdown_pool():
+    global _POOL
+    if _POOL is not None:
+        _POOL.close()
+        _POOL = None
+
+
+def plan_and_pack(params_list, workers=None):
+    """Returns (Tables, plans or None).  Small batches are planned in-process (plans kept for progress /
+    inspection); large ones by a persistent pool of worker processes that return packed chunks."""
+    import atexit
+    import os
+    n = len(params_list)
+    if workers is None:
+        workers = int(os.environ.get("MS_PLAN_WORKERS", "0")) or min(32, len(os.sched_getaffinity(0)))
+    min_batch = int(os.environ.get("MS_PLAN_MIN_BATCH", "256"))
+    if n < min_batch or workers <= 1:
+        plans = [P.plan_render(p) for p in params_list]
+        return pack_chunk(plans), plans
+    global _POOL
+    if _POOL is None or _POOL.size != workers or not _POOL.procs:
+        shutdown_pool()
+        _POOL = _WorkerPool(workers)
+        atexit.register(shutdown_pool)
+    slim = [P._slim_params(p) for p in params_list]      # do not pickle multi-MB impulse responses per render
+    per = max(min(32, max(1, n // workers)), (n + 2 * workers - 1) // (2 * workers))
+    chunks = _POOL.map([slim[i:i + per] for i in range(0, n, per)])
+    return merge_chunks(chunks), None

@@ -152,28 +152,13 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------- our arm
 def algorithmic_bytes(br):
-    """Compulsory traffic per stage, element size = the precision actually used."""
+    """Compulsory traffic per stage, element size = the precision actually used.
+    Element counts are accumulated while the job tables are packed (tables.pack_chunk)."""
     es = 4 if br.precision == "f32" else 8
-    grain = tilt = synth = 0
-    sum_l = 0
-    fir = 0
-    n_total = 0
-    for rp in br.plans:
-        n_total += rp.out_n
-        for ev in rp.events:
-            synth += es * ev.n
-            if ev.tilt is not None:
-                tilt += 2 * es * ev.n
-            if ev.spec is not None:
-                grain += 2 * es * ev.n * ((1 if ev.spec.lp_on else 0) + (1 if ev.spec.stretch_on else 0) + (1 if ev.spec.n_bands else 0))
-            sum_l += ev.length
-        has_er = rp.er_offs is not None and rp.er_offs.size > 0
-        if has_er:
-            fir += 2 * es * rp.out_n
-        if rp.ir is not None:
-            fir += 2 * es * rp.out_n + es * rp.ir.size
-    return {"synth": synth, "tilt_spectral": tilt, "grain_spectral": grain, "overlap_add": es * (sum_l + n_total),
-            "fir_build": 0, "fir_overlap_save": fir, "post": es * n_total + 2 * 4 * n_total + 6 * 4 * n_total}
+    a = br.tables.alg
+    return {"synth": es * a["synth"], "tilt_spectral": es * a["tilt_spectral"], "grain_spectral": es * a["grain_spectral"],
+            "overlap_add": es * a["overlap_add"], "fir_build": 0, "fir_overlap_save": es * (a["fir_in"] + a["fir_taps"]),
+            "post": es * a["post"] + 2 * 4 * a["post"] + 6 * 4 * a["post"]}
 
 
 def run_ours(args):

@@ -92,3 +92,21 @@ def test_batch_equals_single_renders(emul):
     for p, got in zip(ps, batch):
         one, _ = engine.render(p, device=emul, precision="f64")
         assert np.max(np.abs(got.astype(np.float64) - one)) < 1e-6     # pairing changes rounding only
+
+
+def test_pooled_planning_matches_in_process(emul, monkeypatch):
+    """Large batches are planned and packed by worker processes in relocatable chunks; the merged tables
+    must render exactly what the single-chunk path renders."""
+    from audio_suite_b200 import engine
+    ps = [configs.with_defaults(seed=10 + s, out_dur_s=0.05 + 0.01 * (s % 2), gen_mode=m, time_unfold=u, space_ir_on=True,
+                                _ir_audio=configs.synth_ir(0.02, 48000, 3))
+          for s, (m, u) in enumerate([("Gaussian click", 25.0), ("Noise burst", 30.0), ("Dust impulses", 25.0),
+                                      ("Resonant strike", 30.0), ("Skewed transient", 25.0), ("Gaussian click", 30.0),
+                                      ("Resonant strike", 25.0)])]
+    ps[3]["base_sr"], ps[3]["out_dur_s"] = 44100, 0.05003          # odd length -> FFT rotation path
+    one = engine.render_batch(ps, device=emul)
+    monkeypatch.setenv("MS_PLAN_MIN_BATCH", "2")
+    monkeypatch.setenv("MS_PLAN_WORKERS", "3")
+    pooled = engine.render_batch(ps, device=emul)
+    for a, b in zip(one, pooled):
+        assert a.shape == b.shape and np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))) < 1e-6

@@ -85,7 +85,7 @@ def test_mask_edges_follow_reference_branching():
 
 
 def test_bessel_taps_reproduce_the_rotation_filter():
-    from audio_suite_b200.engine import _bessel_coeffs
+    from audio_suite_b200.tables import bessel_coeffs as _bessel_coeffs
     rng = np.random.default_rng(1)
     for n, sr, width in ((4800, 48000, 0.65), (960, 96000, 1.0)):
         x = rng.standard_normal(n)
