@@ -38,7 +38,9 @@ extern "C" size_t MS_API(ms_spectral_workspace_bytes)(const ms_spec_job* jobs, i
     return lay.total;
 }
 
-struct SpectralPlan { std::vector<FftJob> jobs; FftJob* jobs_dev; };
+// groups: job index boundaries such that one group's working set (signals, spectrum, scratch) stays in L2
+struct SpectralPlan { std::vector<FftJob> jobs; FftJob* jobs_dev; std::vector<size_t> groups; };
+static const size_t MS_L2_GROUP_BYTES = 56u << 20;
 
 extern "C" int MS_API(ms_spectral_create)(const ms_spec_job* in, int njobs, const real* src, real* dst,
                                   void* ws, size_t ws_bytes, void* stream, void** handle) {
@@ -72,6 +74,17 @@ extern "C" int MS_API(ms_spectral_create)(const ms_spec_job* in, int njobs, cons
         return FftEngine::job_class(a) < FftEngine::job_class(b); });
     P->jobs_dev = (FftJob*)(base + lay.jobs_off);
     if (ms_h2d(P->jobs_dev, jobs.data(), sizeof(FftJob) * jobs.size(), st)) { delete P; return -1; }
+    // forward and inverse of one group run back to back so the spectrum and the two-pass scratch are
+    // still in the 126 MB L2 when the next kernel wants them
+    size_t acc = 0;
+    P->groups.push_back(0);
+    for (size_t i = 0; i < jobs.size(); ++i) {
+        const FftJob& J = jobs[i];
+        const size_t bytes = sizeof(cpx) * ((size_t)J.n + (J.F1 > 1 ? (size_t)J.M : 0)) + 4 * sizeof(real) * (size_t)J.n;
+        if (acc && acc + bytes > MS_L2_GROUP_BYTES) { P->groups.push_back(i); acc = 0; }
+        acc += bytes;
+    }
+    P->groups.push_back(jobs.size());
     *handle = P;
     return 0;
 }
@@ -80,8 +93,11 @@ extern "C" int MS_API(ms_spectral_run)(void* handle, void* stream) {
     if (!P) MS_FAIL("ms_spectral_run: null handle");
     if (P->jobs.empty()) return 0;
     ms_stream_t st = (ms_stream_t)stream;
-    if (FftEngine::get().forward(P->jobs, P->jobs_dev, st)) return -1;
-    return FftEngine::get().inverse(P->jobs, P->jobs_dev, st);
+    for (size_t g = 0; g + 1 < P->groups.size(); ++g) {
+        if (FftEngine::get().forward(P->jobs, P->jobs_dev, st, P->groups[g], P->groups[g + 1])) return -1;
+        if (FftEngine::get().inverse(P->jobs, P->jobs_dev, st, P->groups[g], P->groups[g + 1])) return -1;
+    }
+    return 0;
 }
 extern "C" void MS_API(ms_spectral_destroy)(void* handle) { delete (SpectralPlan*)handle; }
 

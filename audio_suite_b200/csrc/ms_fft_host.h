@@ -62,14 +62,15 @@ public:
     static int job_class(const FftJob& J) { return (J.ch_hi ? 2 : 0) + (J.F1 > 1 ? 1 : 0); }
 
     // forward: pair (in_a,in_b) -> Z ;  inverse: spec op on Z -> (out_a,out_b)
-    int forward(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 0); }
-    int inverse(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 1); }
+    // (all entry points take an optional [lo, hi) job range so callers can walk a batch in L2-sized groups)
+    int forward(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, size_t lo = 0, size_t hi = (size_t)-1) { return run(jobs, jobs_dev, st, 0, lo, hi); }
+    int inverse(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, size_t lo = 0, size_t hi = (size_t)-1) { return run(jobs, jobs_dev, st, 1, lo, hi); }
     // complex natural-order transform cin -> cout (direct lengths only; test entry)
     int c2c(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 2); }
     // filter spectrum: real taps at in_a (n of them) -> FFT_M / M in [k1][k2] layout at `work`
-    int filter_spectrum(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 3); }
+    int filter_spectrum(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, size_t lo = 0, size_t hi = (size_t)-1) { return run(jobs, jobs_dev, st, 3, lo, hi); }
     // overlap-save: two blocks per job, multiplied by `bspec`, valid outputs stored
-    int overlap_save(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 4); }
+    int overlap_save(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, size_t lo = 0, size_t hi = (size_t)-1) { return run(jobs, jobs_dev, st, 4, lo, hi); }
 
 private:
     std::mutex mu_;
@@ -268,12 +269,13 @@ private:
     }
 
     // what: 0 forward (pair -> Z), 1 inverse (spec(Z) -> pair), 2 c2c test path
-    int run(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, int what) {
-        size_t b = 0;
-        while (b < jobs.size()) {
+    int run(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, int what, size_t lo = 0, size_t hi = (size_t)-1) {
+        const size_t end = std::min(hi, jobs.size());
+        size_t b = lo;
+        while (b < end) {
             const int cls = job_class(jobs[b]);
             size_t e = b;
-            while (e < jobs.size() && job_class(jobs[e]) == cls && e - b < 32768) ++e;
+            while (e < end && job_class(jobs[e]) == cls && e - b < 32768) ++e;
             const ClassShape cs = class_shape(jobs, b, e);
             const unsigned gy = (unsigned)(e - b);
             const FftJob* jd = jobs_dev + b;

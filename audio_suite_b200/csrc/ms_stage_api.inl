@@ -69,7 +69,8 @@ static int ols_block_len(int h_len) {
     while (B < 4 * h_len && B < (1 << 20)) B <<= 1;
     return B;
 }
-struct FirPlan { std::vector<FftJob> hjobs, cjobs; FftJob *hjobs_dev, *cjobs_dev; };
+struct FirGroup { size_t h0, h1, c0, c1; };
+struct FirPlan { std::vector<FftJob> hjobs, cjobs; FftJob *hjobs_dev, *cjobs_dev; std::vector<FirGroup> groups; };
 struct FirLayout { size_t hjobs_off, cjobs_off, hspec_off, work_off, total; std::vector<size_t> hspec_at; std::vector<int> B; int ncj; };
 
 static int fir_layout(const ms_fir_render* r, int n, FirLayout& L) {
@@ -113,7 +114,25 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
     cpx* hspec = (cpx*)(base + L.hspec_off);
     cpx* work = (cpx*)(base + L.work_off);
     size_t wk = 0;
-    for (int i = 0; i < n; ++i) {
+    // renders in order of their block length so both job lists come out sorted by launch class and aligned
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (L.B[a] > MS_SMALL_MAX) < (L.B[b] > MS_SMALL_MAX); });
+    size_t acc = 0;
+    FirGroup cur; cur.h0 = cur.c0 = 0;
+    for (int oi = 0; oi < n; ++oi) {
+        const int i = order[oi];
+        {
+            const int hop_i = L.B[i] - r[i].h_len + 1;
+            const int nj_i = ((r[i].out_n + hop_i - 1) / hop_i + 1) / 2;
+            const size_t bytes = sizeof(cpx) * (size_t)L.B[i] * (size_t)(1 + nj_i) + 2 * sizeof(real) * (size_t)r[i].out_n;
+            if (acc && (acc + bytes > MS_L2_GROUP_BYTES || (oi > 0 && (L.B[order[oi - 1]] > MS_SMALL_MAX) != (L.B[i] > MS_SMALL_MAX)))) {
+                cur.h1 = P->hjobs.size(); cur.c1 = P->cjobs.size();
+                P->groups.push_back(cur);
+                cur.h0 = cur.h1; cur.c0 = cur.c1; acc = 0;
+            }
+            acc += bytes;
+        }
         FftJob H; memset(&H, 0, sizeof H);
         if (FftEngine::get().prepare(H, L.B[i], st)) { delete P; return -1; }
         FftJob Cj = H;
@@ -136,9 +155,8 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
             P->cjobs.push_back(J);
         }
     }
-    auto by_class = [](const FftJob& a, const FftJob& b) { return FftEngine::job_class(a) < FftEngine::job_class(b); };
-    std::stable_sort(P->hjobs.begin(), P->hjobs.end(), by_class);
-    std::stable_sort(P->cjobs.begin(), P->cjobs.end(), by_class);
+    cur.h1 = P->hjobs.size(); cur.c1 = P->cjobs.size();
+    P->groups.push_back(cur);
     P->hjobs_dev = (FftJob*)(base + L.hjobs_off);
     P->cjobs_dev = (FftJob*)(base + L.cjobs_off);
     if (ms_h2d(P->hjobs_dev, P->hjobs.data(), sizeof(FftJob) * P->hjobs.size(), st)) { delete P; return -1; }
@@ -150,7 +168,12 @@ extern "C" int MS_API(ms_fir_run)(void* handle, void* stream) {
     FirPlan* P = (FirPlan*)handle;
     if (!P) MS_FAIL("ms_fir_run: null handle");
     if (P->hjobs.empty()) return 0;
-    if (FftEngine::get().filter_spectrum(P->hjobs, P->hjobs_dev, (ms_stream_t)stream)) return -1;
-    return FftEngine::get().overlap_save(P->cjobs, P->cjobs_dev, (ms_stream_t)stream);
+    // filter spectrum and overlap-save of one group back to back: the per-render spectrum (B complex) and the
+    // two-pass scratch are consumed out of L2
+    for (const FirGroup& g : P->groups) {
+        if (FftEngine::get().filter_spectrum(P->hjobs, P->hjobs_dev, (ms_stream_t)stream, g.h0, g.h1)) return -1;
+        if (FftEngine::get().overlap_save(P->cjobs, P->cjobs_dev, (ms_stream_t)stream, g.c0, g.c1)) return -1;
+    }
+    return 0;
 }
 extern "C" void MS_API(ms_fir_destroy)(void* handle) { delete (FirPlan*)handle; }
