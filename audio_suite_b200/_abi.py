@@ -88,9 +88,8 @@ _STAGES = {
     "ms_synth_dust": (_I, [_P, _I, _P, _P, _P, _P]),
     "ms_synth_tilt_finish": (_I, [_P, _I, _P, _P]),
     "ms_overlap_add": (_I, [_P, _I, _I, _P, _P, _P, _P]),
-    "ms_fir_build": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "ms_fir_workspace_bytes": (_Z, [_P, _I]),
-    "ms_fir_create": (_I, [_P, _I, _P, _P, _P, _P, _Z, _P, C.POINTER(C.c_void_p)]),
+    "ms_fir_create": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _Z, _P, C.POINTER(C.c_void_p)]),
     "ms_fir_run": (_I, [_P, _P]),
     "ms_fir_destroy": (None, [_P]),
     "ms_post": (_I, [_P, _I, _I, _P, _P, _P, _P]),

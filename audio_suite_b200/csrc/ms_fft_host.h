@@ -9,18 +9,22 @@ static const int MS_TILE_MAX = sizeof(real) == 4 ? 8192 : 4096;
 // ---- kernel structs ----------------------------------------------------------------------------------
 template <int LD, int ST, int TWID> struct ColsK {
     static constexpr int MAXT = 512;
+    static constexpr int MINB = 2;        // <= 64 registers: three 256..320-thread CTAs per SM
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_body<LD, ST, TWID>(jobs, c); }
 };
 template <int LD, int MODE, int ST> struct RowsK {
     static constexpr int MAXT = 512;
+    static constexpr int MINB = 2;
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_rows_body<LD, MODE, ST>(jobs, c); }
 };
 struct GenChirpK {
     static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
     static MS_DEV void run(cpx* out, int n, const Ctx& c) { gen_chirp_body(out, n, c, c.nthr * 64, c.bx * c.nthr + c.tid); }
 };
 struct GenTableK {
     static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
     static MS_DEV void run(cpx* out, int count, long long mul, long long N, const Ctx& c) {
         gen_table_body(out, count, mul, N, c, c.nthr * 64, c.bx * c.nthr + c.tid);
     }
@@ -69,6 +73,8 @@ public:
     int c2c(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st) { return run(jobs, jobs_dev, st, 2); }
     // filter spectrum: real taps at in_a (n of them) -> FFT_M / M in [k1][k2] layout at `work`
     int filter_spectrum(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, size_t lo = 0, size_t hi = (size_t)-1) { return run(jobs, jobs_dev, st, 3, lo, hi); }
+    // combined filter spectrum: real reflection taps at in_a -> IR spectrum (cin) * (1 + FFT_M(taps)) at `work`
+    int filter_compose(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, size_t lo = 0, size_t hi = (size_t)-1) { return run(jobs, jobs_dev, st, 5, lo, hi); }
     // overlap-save: two blocks per job, multiplied by `bspec`, valid outputs stored
     int overlap_save(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, size_t lo = 0, size_t hi = (size_t)-1) { return run(jobs, jobs_dev, st, 4, lo, hi); }
 
@@ -127,8 +133,8 @@ private:
         if (!best) return false;
         J.F1 = best; J.F2 = n / best;
         J.T = 16; J.G = 16;
-        while (J.T > 8 && J.T * J.F1 > MS_TILE_MAX / 2) J.T /= 2;       // prefer half tiles: 2-3 CTAs per SM
-        while (J.G > 8 && J.G * J.F2 > MS_TILE_MAX / 2) J.G /= 2;
+        while (J.T > 4 && J.T * J.F1 > MS_TILE_MAX / 2) J.T /= 2;       // half tiles (<= 74 KB in f64): three CTAs per SM
+        while (J.G > 4 && J.G * J.F2 > MS_TILE_MAX / 2) J.G /= 2;
         while (J.T > 1 && J.T * J.F1 > MS_TILE_MAX) J.T /= 2;
         while (J.G > 1 && J.G * J.F2 > MS_TILE_MAX) J.G /= 2;
         return true;
@@ -286,6 +292,12 @@ private:
                 else if (cls == 1) {
                     rc = launch_cols<LD_REALPAD, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
                     if (!rc) rc = launch_rows<LD_WORK, MODE_RAW, ST_WORK>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                } else MS_FAIL("filter spectrum needs a direct length");
+            } else if (what == 5) {
+                if (cls == 0) rc = launch_rows<LD_REALPAD, MODE_RAW, ST_HMUL>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                else if (cls == 1) {
+                    rc = launch_cols<LD_REALPAD, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    if (!rc) rc = launch_rows<LD_WORK, MODE_RAW, ST_HMUL>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
                 } else MS_FAIL("filter spectrum needs a direct length");
             } else if (what == 4) {
                 if (cls == 0) rc = launch_rows<LD_OLS, MODE_CONV, ST_OLS>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);

@@ -18,7 +18,7 @@
 //                     RAW  -> leave the [k1][k2] spectrum in place (used to build filter spectra).
 
 enum { LD_WORK = 0, LD_CPX, LD_PAIR, LD_PAIR_CHIRP, LD_SPEC, LD_SPEC_CHIRP, LD_BW, LD_OLS, LD_REALPAD };
-enum { ST_WORK = 0, ST_CPX, ST_Z, ST_Z_CHIRP, ST_PAIR, ST_PAIR_CHIRP, ST_OLS };
+enum { ST_WORK = 0, ST_CPX, ST_Z, ST_Z_CHIRP, ST_PAIR, ST_PAIR_CHIRP, ST_OLS, ST_HMUL };
 enum { MODE_NAT = 0, MODE_CONV, MODE_RAW };
 enum { OP_NONE = 0, OP_GRAIN = 1, OP_TILT = 2, OP_ROT = 3 };
 
@@ -217,6 +217,10 @@ MS_DEV cpx job_load(const FftJob& J, int idx) {
 template <int ST>
 MS_DEV void job_store(const FftJob& J, int idx, cpx v) {
     if (ST == ST_WORK) { J.work[idx] = v; return; }
+    if (ST == ST_HMUL) {            // filter spectrum: IR spectrum (at cin, already / B) times (1 + reflection-cloud spectrum)
+        J.work[idx] = c_mul(__ldg(&J.cin[idx]), mk(v.x + (real)1.0, v.y));
+        return;
+    }
     if (ST == ST_OLS) {             // valid part of the circular convolution; un-swap the inverse half
         if (idx < J.ols_skip) return;
         const long long qa = J.p0_a + idx, qb = J.p0_b + idx;

@@ -37,7 +37,7 @@ static inline int ms_memset(void* dst, int v, size_t bytes, ms_stream_t) { memse
 #else
 typedef cudaStream_t ms_stream_t;
 template <class K, class... Args>
-__global__ void __launch_bounds__(K::MAXT) ms_kernel(Args... args) {
+__global__ void __launch_bounds__(K::MAXT, K::MINB) ms_kernel(Args... args) {
     extern __shared__ float4 ms_dyn_smem[];
     Ctx c;
     c.tid = threadIdx.x; c.nthr = blockDim.x; c.bx = blockIdx.x; c.by = blockIdx.y;

@@ -1,20 +1,28 @@
 // ms_stage_api.inl -- C-ABI entry points of the non-spectral stages (include/microsound_b200.h).
 
 struct SynthNormalK { static constexpr int MAXT = SY_NTHR;
+    static constexpr int MINB = 4;
     static MS_DEV void run(const SynthEvt* e, real* pool, const Ctx& c) { synth_normal_body(e, pool, c); } };
 struct SynthTiltK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
     static MS_DEV void run(const SynthEvt* e, real* pool, const Ctx& c) { synth_tilt_finish_body(e, pool, c); } };
 struct SynthDustK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
     static MS_DEV void run(const SynthEvt* e, const int* dp, const real* dv, real* pool, const Ctx& c) { synth_dust_body(e, dp, dv, pool, c); } };
 struct OlaK { static constexpr int MAXT = OLA_NTHR;
+    static constexpr int MINB = 1;
     static MS_DEV void run(const OlaRender* r, const OlaEvt* e, const real* pool, real* mono, const Ctx& c) { ola_adsr_body(r, e, pool, mono, c); } };
-struct FirBuildK { static constexpr int MAXT = OLA_NTHR;
-    static MS_DEV void run(const FirRender* r, const int* to, const real* tg, const real* ir, real* h, const Ctx& c) { fir_build_body(r, to, tg, ir, h, c); } };
+struct ErScatterK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const ErJob* j, const int* to, const real* tg, real* e, const Ctx& c) { er_scatter_body(j, to, tg, e, c); } };
 struct PostMaxK { static constexpr int MAXT = OLA_NTHR;
+    static constexpr int MINB = 1;
     static MS_DEV void run(const PostRender* r, real* mono, unsigned long long* mb, const Ctx& c) { post_max_body(r, mono, mb, c); } };
 struct PostWriteK { static constexpr int MAXT = OLA_NTHR;
+    static constexpr int MINB = 1;
     static MS_DEV void run(const PostRender* r, const real* mono, const unsigned long long* mb, float2* out, const Ctx& c) { post_write_body(r, mono, mb, out, c); } };
 struct RollK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
     static MS_DEV void run(const real* src, real* dst, int n, int shift, const Ctx& c) { roll_body(src, dst, n, shift, c); } };
 
 static inline MsDim mk_dim(unsigned x, unsigned y) { MsDim d; d.x = x; d.y = y; return d; }
@@ -41,18 +49,11 @@ extern "C" int MS_API(ms_overlap_add)(const ms_ola_render* renders, int n_render
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<OlaK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream, renders + _y0, evts, pool, mono)) return -1; })
     return 0;
 }
-extern "C" int MS_API(ms_fir_build)(const ms_fir_render* renders, int n_renders, int max_h_len, const int32_t* tap_off,
-                            const real* tap_gain, const real* irpool, real* hpool, void* stream) {
-    const unsigned gx = (unsigned)((max_h_len + OLA_TILE - 1) / OLA_TILE);
-    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<FirBuildK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, FIR_MAX_TAPS * 8, (ms_stream_t)stream,
-                                   renders + _y0, (const int*)tap_off, tap_gain, irpool, hpool)) return -1; })
-    return 0;
-}
 extern "C" int MS_API(ms_post)(const ms_post_render* renders, int n_renders, int max_n, real* mono, uint64_t* maxbits,
                        float* out, void* stream) {
     const unsigned gx = (unsigned)((max_n + OLA_TILE - 1) / OLA_TILE);
     if (ms_memset(maxbits, 0, sizeof(uint64_t) * (size_t)n_renders, (ms_stream_t)stream)) return -1;
-    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, OLA_NTHR * sizeof(real), (ms_stream_t)stream,
+    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, (OLA_TILE + 4 * POST_K + POST_NC + 1 + OLA_NTHR) * sizeof(real), (ms_stream_t)stream,
                                    renders + _y0, mono, (unsigned long long*)maxbits + _y0)) return -1; })
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostWriteK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream,
                                    renders + _y0, (const real*)mono, (const unsigned long long*)maxbits + _y0, (float2*)out)) return -1; })
@@ -69,27 +70,52 @@ static int ols_block_len(int h_len) {
     while (B < 4 * h_len && B < (1 << 20)) B <<= 1;
     return B;
 }
-struct FirGroup { size_t h0, h1, c0, c1; };
-struct FirPlan { std::vector<FftJob> hjobs, cjobs; FftJob *hjobs_dev, *cjobs_dev; std::vector<FirGroup> groups; };
-struct FirLayout { size_t hjobs_off, cjobs_off, hspec_off, work_off, total; std::vector<size_t> hspec_at; std::vector<int> B; int ncj; };
+// Plan: (1) at create time, the spectrum of every distinct impulse response (FFT_B(ir)/B, scrambled [k1][k2]
+// layout); (2) per run and per render with reflection taps: scatter the taps into a dense vector, transform it
+// and compose the render's filter spectrum IRspec * (1 + FFT(e)); (3) overlap-save with two blocks per transform.
+struct FirPlan {
+    std::vector<FftJob> ijobs, hjobs, cjobs;
+    FftJob *ijobs_dev, *hjobs_dev, *cjobs_dev;
+    std::vector<ErJob> ejobs; ErJob* ejobs_dev;
+    const int* tap_off; const real* tap_gain; real* ebase;
+};
+struct FirLayout {
+    size_t ijobs_off, hjobs_off, cjobs_off, ejobs_off, ebuf_off, ispec_off, hspec_off, work_off, total;
+    std::vector<size_t> hspec_at, e_at; std::vector<int> B, ispec_of; std::vector<std::pair<long long, std::pair<int, int>>> irs;
+    int ncj, nh;
+};
 
 static int fir_layout(const ms_fir_render* r, int n, FirLayout& L) {
-    L.hspec_at.resize(n); L.B.resize(n);
-    size_t hs = 0, wk = 0; int ncj = 0;
+    L.hspec_at.assign(n, 0); L.e_at.assign(n, 0); L.B.resize(n); L.ispec_of.resize(n); L.irs.clear();
+    size_t hs = 0, wk = 0, is = 0, eb = 0; int ncj = 0, nh = 0;
     for (int i = 0; i < n; ++i) {
         const int B = ols_block_len(r[i].h_len);
-        if (r[i].h_len < 1 || r[i].h_len > B / 2) MS_FAIL("fir: %d taps unsupported", r[i].h_len);
-        L.B[i] = B; L.hspec_at[i] = hs; hs += (size_t)B;
+        if (r[i].h_len < 1 || r[i].h_len > B / 2 || r[i].ir_len < 1) MS_FAIL("fir: %d taps unsupported", r[i].h_len);
+        L.B[i] = B;
+        const std::pair<long long, std::pair<int, int>> key(r[i].ir, std::make_pair(r[i].ir_len, B));
+        int found = -1;
+        for (size_t k = 0; k < L.irs.size(); ++k) if (L.irs[k] == key) { found = (int)k; break; }
+        if (found < 0) { found = (int)L.irs.size(); L.irs.push_back(key); is += (size_t)B; }
+        L.ispec_of[i] = found;
+        if (r[i].tap_end > r[i].tap_begin) {
+            L.hspec_at[i] = hs; hs += (size_t)B;
+            L.e_at[i] = eb; eb += (size_t)(r[i].h_len - r[i].ir_len + 1);
+            ++nh;
+        }
         const int hop = B - r[i].h_len + 1;
         const int nblk = (r[i].out_n + hop - 1) / hop;
         const int nj = (nblk + 1) / 2;
         ncj += nj;
         if (B > MS_SMALL_MAX) wk += (size_t)B * (size_t)nj;
     }
-    L.ncj = ncj;
-    L.hjobs_off = 0;
-    L.cjobs_off = ms_align256(sizeof(FftJob) * (size_t)n);
-    L.hspec_off = L.cjobs_off + ms_align256(sizeof(FftJob) * (size_t)ncj);
+    L.ncj = ncj; L.nh = nh;
+    L.ijobs_off = 0;
+    L.hjobs_off = ms_align256(sizeof(FftJob) * L.irs.size());
+    L.cjobs_off = L.hjobs_off + ms_align256(sizeof(FftJob) * (size_t)nh);
+    L.ejobs_off = L.cjobs_off + ms_align256(sizeof(FftJob) * (size_t)ncj);
+    L.ebuf_off = L.ejobs_off + ms_align256(sizeof(ErJob) * (size_t)nh);
+    L.ispec_off = L.ebuf_off + ms_align256(sizeof(real) * eb);
+    L.hspec_off = L.ispec_off + ms_align256(sizeof(cpx) * is);
     L.work_off = L.hspec_off + ms_align256(sizeof(cpx) * hs);
     L.total = L.work_off + ms_align256(sizeof(cpx) * wk);
     return 0;
@@ -100,49 +126,56 @@ extern "C" size_t MS_API(ms_fir_workspace_bytes)(const ms_fir_render* r, int n) 
     if (fir_layout(r, n, L)) return 0;
     return L.total;
 }
-extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* hpool, const real* mono_in, real* mono_out,
-                             void* ws, size_t ws_bytes, void* stream, void** handle) {
+extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* irpool, const int32_t* tap_off, const real* tap_gain,
+                             const real* mono_in, real* mono_out, void* ws, size_t ws_bytes, void* stream, void** handle) {
     *handle = nullptr;
     ms_stream_t st = (ms_stream_t)stream;
     FirPlan* P = new FirPlan();
-    P->hjobs_dev = P->cjobs_dev = nullptr;
+    P->ijobs_dev = P->hjobs_dev = P->cjobs_dev = nullptr; P->ejobs_dev = nullptr;
     if (n <= 0) { *handle = P; return 0; }
     FirLayout L;
     if (fir_layout(r, n, L)) { delete P; return -1; }
     if (ws_bytes < L.total) { delete P; MS_FAIL("ms_fir_create: workspace %zu < required %zu", ws_bytes, L.total); }
     char* base = (char*)ws;
+    cpx* ispec = (cpx*)(base + L.ispec_off);
     cpx* hspec = (cpx*)(base + L.hspec_off);
     cpx* work = (cpx*)(base + L.work_off);
-    size_t wk = 0;
-    // renders in order of their block length so both job lists come out sorted by launch class and aligned
+    P->ebase = (real*)(base + L.ebuf_off);
+    P->tap_off = (const int*)tap_off; P->tap_gain = tap_gain;
+    // (1) impulse-response spectra
+    std::vector<size_t> ispec_at(L.irs.size());
+    size_t is = 0;
+    for (size_t k = 0; k < L.irs.size(); ++k) {
+        const int B = L.irs[k].second.second;
+        FftJob I; memset(&I, 0, sizeof I);
+        if (FftEngine::get().prepare(I, B, st)) { delete P; return -1; }
+        I.n = L.irs[k].second.first; I.in_a = irpool + L.irs[k].first; I.work = ispec + is; I.out_scale = (real)1.0 / (real)B;
+        ispec_at[k] = is; is += (size_t)B;
+        P->ijobs.push_back(I);
+    }
+    // (2)+(3) per render, in order of launch class
     std::vector<int> order(n);
     for (int i = 0; i < n; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (L.B[a] > MS_SMALL_MAX) < (L.B[b] > MS_SMALL_MAX); });
-    size_t acc = 0;
-    FirGroup cur; cur.h0 = cur.c0 = 0;
+    size_t wk = 0;
     for (int oi = 0; oi < n; ++oi) {
         const int i = order[oi];
-        {
-            const int hop_i = L.B[i] - r[i].h_len + 1;
-            const int nj_i = ((r[i].out_n + hop_i - 1) / hop_i + 1) / 2;
-            const size_t bytes = sizeof(cpx) * (size_t)L.B[i] * (size_t)(1 + nj_i) + 2 * sizeof(real) * (size_t)r[i].out_n;
-            if (acc && (acc + bytes > MS_L2_GROUP_BYTES || (oi > 0 && (L.B[order[oi - 1]] > MS_SMALL_MAX) != (L.B[i] > MS_SMALL_MAX)))) {
-                cur.h1 = P->hjobs.size(); cur.c1 = P->cjobs.size();
-                P->groups.push_back(cur);
-                cur.h0 = cur.h1; cur.c0 = cur.c1; acc = 0;
-            }
-            acc += bytes;
+        FftJob G; memset(&G, 0, sizeof G);
+        if (FftEngine::get().prepare(G, L.B[i], st)) { delete P; return -1; }
+        const cpx* filt = ispec + ispec_at[L.ispec_of[i]];
+        if (r[i].tap_end > r[i].tap_begin) {
+            FftJob H = G;
+            ErJob E; E.e = (long long)L.e_at[i]; E.elen = r[i].h_len - r[i].ir_len + 1; E.tap_begin = r[i].tap_begin; E.tap_end = r[i].tap_end;
+            P->ejobs.push_back(E);
+            H.n = E.elen; H.in_a = P->ebase + E.e; H.cin = filt; H.work = hspec + L.hspec_at[i]; H.out_scale = (real)1.0;
+            P->hjobs.push_back(H);
+            filt = hspec + L.hspec_at[i];
         }
-        FftJob H; memset(&H, 0, sizeof H);
-        if (FftEngine::get().prepare(H, L.B[i], st)) { delete P; return -1; }
-        FftJob Cj = H;
-        H.n = r[i].h_len; H.in_a = hpool + r[i].h; H.work = hspec + L.hspec_at[i]; H.out_scale = (real)1.0 / (real)L.B[i];
-        P->hjobs.push_back(H);
         const int hop = L.B[i] - r[i].h_len + 1;
         const int nblk = (r[i].out_n + hop - 1) / hop;
         const int nj = (nblk + 1) / 2;
         for (int j = 0; j < nj; ++j) {
-            FftJob J = Cj;
+            FftJob J = G;
             const int ba = j, bb = j + nj;                 // pair block j with block j + nj of the same render
             J.in_a = mono_in + r[i].x; J.out_a = mono_out + r[i].y;
             J.p0_a = (long long)ba * hop - (r[i].h_len - 1);
@@ -150,30 +183,39 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
             J.ols_n = r[i].out_n; J.ols_skip = r[i].h_len - 1;
             J.live_lo = r[i].x_begin;
             J.live_hi = (int)std::min<long long>(r[i].out_n, (long long)r[i].x_end + r[i].h_len - 1);
-            J.bspec = hspec + L.hspec_at[i];
+            J.bspec = filt;
             if (L.B[i] > MS_SMALL_MAX) { J.work = work + wk; wk += (size_t)L.B[i]; }
             P->cjobs.push_back(J);
         }
     }
-    cur.h1 = P->hjobs.size(); cur.c1 = P->cjobs.size();
-    P->groups.push_back(cur);
+    auto by_class = [](const FftJob& a, const FftJob& b) { return FftEngine::job_class(a) < FftEngine::job_class(b); };
+    std::stable_sort(P->ijobs.begin(), P->ijobs.end(), by_class);
+    P->ijobs_dev = (FftJob*)(base + L.ijobs_off);
     P->hjobs_dev = (FftJob*)(base + L.hjobs_off);
     P->cjobs_dev = (FftJob*)(base + L.cjobs_off);
-    if (ms_h2d(P->hjobs_dev, P->hjobs.data(), sizeof(FftJob) * P->hjobs.size(), st)) { delete P; return -1; }
+    P->ejobs_dev = (ErJob*)(base + L.ejobs_off);
+    if (ms_h2d(P->ijobs_dev, P->ijobs.data(), sizeof(FftJob) * P->ijobs.size(), st)) { delete P; return -1; }
+    if (!P->hjobs.empty()) {
+        if (ms_h2d(P->hjobs_dev, P->hjobs.data(), sizeof(FftJob) * P->hjobs.size(), st)) { delete P; return -1; }
+        if (ms_h2d(P->ejobs_dev, P->ejobs.data(), sizeof(ErJob) * P->ejobs.size(), st)) { delete P; return -1; }
+    }
     if (ms_h2d(P->cjobs_dev, P->cjobs.data(), sizeof(FftJob) * P->cjobs.size(), st)) { delete P; return -1; }
+    if (FftEngine::get().filter_spectrum(P->ijobs, P->ijobs_dev, st)) { delete P; return -1; }      // once per plan
     *handle = P;
     return 0;
 }
 extern "C" int MS_API(ms_fir_run)(void* handle, void* stream) {
     FirPlan* P = (FirPlan*)handle;
     if (!P) MS_FAIL("ms_fir_run: null handle");
-    if (P->hjobs.empty()) return 0;
-    // filter spectrum and overlap-save of one group back to back: the per-render spectrum (B complex) and the
-    // two-pass scratch are consumed out of L2
-    for (const FirGroup& g : P->groups) {
-        if (FftEngine::get().filter_spectrum(P->hjobs, P->hjobs_dev, (ms_stream_t)stream, g.h0, g.h1)) return -1;
-        if (FftEngine::get().overlap_save(P->cjobs, P->cjobs_dev, (ms_stream_t)stream, g.c0, g.c1)) return -1;
+    if (P->cjobs.empty()) return 0;
+    ms_stream_t st = (ms_stream_t)stream;
+    if (!P->hjobs.empty()) {
+        for (size_t y0 = 0; y0 < P->ejobs.size(); y0 += 32768) {
+            const unsigned yc = (unsigned)std::min<size_t>(32768, P->ejobs.size() - y0);
+            if (ms_launch<ErScatterK>(mk_dim(1, yc), 256, 0, st, (const ErJob*)(P->ejobs_dev + y0), P->tap_off, P->tap_gain, P->ebase)) return -1;
+        }
+        if (FftEngine::get().filter_compose(P->hjobs, P->hjobs_dev, st)) return -1;
     }
-    return 0;
+    return FftEngine::get().overlap_save(P->cjobs, P->cjobs_dev, st);
 }
 extern "C" void MS_API(ms_fir_destroy)(void* handle) { delete (FirPlan*)handle; }

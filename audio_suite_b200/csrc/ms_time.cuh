@@ -50,69 +50,69 @@ MS_DEV void ola_adsr_body(const OlaRender* MS_RESTRICT renders, const OlaEvt* MS
     }
 }
 
-// ---- FIR builder: h = ir + sum_t g_t * delay(ir, off_t)   (reflection cloud folded into the IR) ------
+// ---- reflection cloud as a dense tap vector: e[off_t] += g_t  (early_reflection_cloud, main_v2.py:413-420) ----
+// The cloud and the impulse response are both causal LTI filters, so they are applied as ONE filter whose
+// spectrum is IRspec * (1 + FFT(e)); e is only max_off + 1 samples long.
 typedef ms_fir_render FirRender;
-#define FIR_MAX_TAPS 4096
-MS_DEV void fir_build_body(const FirRender* MS_RESTRICT renders, const int* MS_RESTRICT tap_off, const real* MS_RESTRICT tap_gain,
-                           const real* MS_RESTRICT irpool, real* MS_RESTRICT hpool, const Ctx& c) {
-    const FirRender R = renders[c.by];
-    const int m0 = c.bx * OLA_TILE;
-    if (m0 >= R.h_len) return;
-    int* s_off = (int*)c.smem;
-    real* s_gain = (real*)(s_off + FIR_MAX_TAPS);
-    const int ntap = R.tap_end - R.tap_begin;
-    for (int t = c.tid; t < ntap; t += c.nthr) { s_off[t] = tap_off[R.tap_begin + t]; s_gain[t] = tap_gain[R.tap_begin + t]; }
+struct ErJob { long long e; int elen, tap_begin, tap_end; };
+MS_DEV void er_scatter_body(const ErJob* MS_RESTRICT jobs, const int* MS_RESTRICT tap_off, const real* MS_RESTRICT tap_gain,
+                            real* ebase, const Ctx& c) {
+    const ErJob J = jobs[c.by];
+    real* e = ebase + J.e;
+    for (int i = c.tid; i < J.elen; i += c.nthr) e[i] = (real)0.;
     c.sync();
-    const real* ir = irpool + R.ir;
-    real* h = hpool + R.h;
-    const int m1 = (m0 + OLA_TILE) < R.h_len ? (m0 + OLA_TILE) : R.h_len;
-    for (int m = m0 + c.tid; m < m1; m += c.nthr) {
-        real acc = m < R.ir_len ? __ldg(&ir[m]) : (real)0.;
-        for (int t = 0; t < ntap; ++t) {
-            const int k = m - s_off[t];
-            if (k >= 0 && k < R.ir_len) acc += s_gain[t] * __ldg(&ir[k]);
+    for (int t = J.tap_begin + c.tid; t < J.tap_end; t += c.nthr) {
+        const int off = tap_off[t];
+        if (off >= 0 && off < J.elen) {
+#ifdef MS_HOST_EMUL
+            e[off] += tap_gain[t];
+#else
+            atomicAdd(&e[off], tap_gain[t]);        // several taps may share a delay
+#endif
         }
-        h[m] = acc;
     }
 }
 
 // ---- stereo diffusion + soft clip + normalise -----------------------------------------------------------
 typedef ms_post_render PostRender;
 MS_DEV int wrap_idx(long long i, int n) { long long r = i % n; if (r < 0) r += n; return (int)r; }
-// right channel by the Bessel taps (even lengths): R[i] = sum_m J_m(theta) y[(i + dr + 2m) mod n]
-MS_DEV real right_taps(const PostRender& R, const real* MS_RESTRICT y, int i) {
-    real acc = (real)0.;
-    int idx = wrap_idx((long long)i + R.dr - 2 * POST_K, R.n);
-#pragma unroll
-    for (int m = 0; m < POST_NC; ++m) {
-        acc += (real)R.coef[m] * __ldg(&y[idx]);
-        idx += 2; if (idx >= R.n) idx -= R.n;
-    }
-    return acc;
-}
 // the clipped value is stored as float32, so tanh is evaluated in float32 (argument rounded once: 6e-8 relative)
 MS_DEV real soft_clip(real v, real drive, real inv_t) { return drive > (real)0. ? (real)tanhf((float)(v * drive)) * inv_t : v; }
 
 // pass 1: per-render max(|L|, |R|) before the clip (tanh is monotonic, so the clipped max follows).
 // stereo_mode 1 also materialises the right channel at rbuf so that pass 2 does not redo the 25 taps.
+// The tile's input window (1024 + 4K samples, circular) and the taps are staged in shared memory.
 MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, unsigned long long* MS_RESTRICT maxbits, const Ctx& c) {
-    const PostRender R = renders[c.by];
+    const PostRender& R = renders[c.by];
+    const int n = R.n, mode = R.stereo_mode;
     const int t0 = c.bx * OLA_TILE;
-    if (t0 >= R.n) return;
-    const int t1 = (t0 + OLA_TILE) < R.n ? (t0 + OLA_TILE) : R.n;
+    if (t0 >= n) return;
+    const int t1 = (t0 + OLA_TILE) < n ? (t0 + OLA_TILE) : n;
     const real* y = mono + R.y;
+    real* win = (real*)c.smem;                       // OLA_TILE + 4K
+    real* coef = win + (OLA_TILE + 4 * POST_K);       // POST_NC
+    real* red = coef + POST_NC + 1;                  // nthr
+    if (mode == 1) {
+        const int W = (t1 - t0) + 4 * POST_K;
+        const long long w0 = (long long)t0 + R.dr - 2 * POST_K;
+        for (int j = c.tid; j < W; j += c.nthr) win[j] = y[wrap_idx(w0 + j, n)];
+        for (int j = c.tid; j < POST_NC; j += c.nthr) coef[j] = (real)R.coef[j];
+        c.sync();
+    }
     real m = (real)0.;
     for (int i = t0 + c.tid; i < t1; i += c.nthr) {
         m = r_max(m, r_abs(y[i]));
-        if (R.stereo_mode == 1) {
-            const real r = right_taps(R, y, i);
-            mono[R.rbuf + i] = r;
-            m = r_max(m, r_abs(r));
-        } else if (R.stereo_mode == 2) {
+        if (mode == 1) {
+            real acc = (real)0.;
+            const real* w = win + (i - t0);
+#pragma unroll
+            for (int k = 0; k < POST_NC; ++k) acc += coef[k] * w[2 * k];
+            mono[R.rbuf + i] = acc;
+            m = r_max(m, r_abs(acc));
+        } else if (mode == 2) {
             m = r_max(m, r_abs(mono[R.rbuf + i]));
         }
     }
-    real* red = (real*)c.smem;
     red[c.tid] = m;
     c.sync();
     for (int s = c.nthr >> 1; s > 0; s >>= 1) {

@@ -11,7 +11,7 @@ Stage order (one batched launch sequence for all renders):
   [tilted-noise modes: rfft -> power-law tilt -> irfft, finish]  ms_spectral_* / ms_synth_tilt_finish
   grain spectral op: low-pass -> stretch -> multiband            ms_spectral_*
   overlap-add placement + ADSR                                   ms_overlap_add
-  reflection cloud (+) impulse response as one FIR, overlap-save ms_fir_build / ms_fir_*
+  reflection cloud (+) impulse response as one FIR, overlap-save ms_fir_*
   stereo diffusion, soft clip, normalise                         ms_post
 """
 from __future__ import annotations
@@ -159,14 +159,13 @@ class BatchRenderer:
             self.d_tap_off = dev.upload(t.tap_off if t.tap_off.size else np.zeros(1, np.int32))
             self.d_tap_gain = dev.upload((t.tap_gain if t.tap_gain.size else np.zeros(1)).astype(real))
             self.d_ir = dev.upload(t.irs.astype(real))
-            self.hpool = dev.empty(t.h_total, real)
             need = self.api.ms_fir_workspace_bytes(fir.ctypes.data, len(fir))
             if need == 0:
                 _check(dev, -1)
             self.fir_ws = dev.empty(need, np.uint8)
-            _check(dev, self.api.ms_fir_create(fir.ctypes.data, len(fir), dev.ptr(self.hpool), dev.ptr(self.mono),
-                                               dev.ptr(self.mono), dev.ptr(self.fir_ws), need, dev.stream_ptr(),
-                                               C.byref(self.fir_handle)))
+            _check(dev, self.api.ms_fir_create(fir.ctypes.data, len(fir), dev.ptr(self.d_ir), dev.ptr(self.d_tap_off),
+                                               dev.ptr(self.d_tap_gain), dev.ptr(self.mono), dev.ptr(self.mono),
+                                               dev.ptr(self.fir_ws), need, dev.stream_ptr(), C.byref(self.fir_handle)))
 
     # ---- execution -------------------------------------------------------------------------------------
     def run(self, mark=None):
@@ -191,9 +190,6 @@ class BatchRenderer:
                                        dev.ptr(self.pool), dev.ptr(self.mono), st))
         mark("overlap_add")
         if self.n_fir:
-            _check(dev, lib.ms_fir_build(dev.ptr(self.d_fir), self.n_fir, self.max_h, dev.ptr(self.d_tap_off),
-                                         dev.ptr(self.d_tap_gain), dev.ptr(self.d_ir), dev.ptr(self.hpool), st))
-            mark("fir_build")
             _check(dev, lib.ms_fir_run(self.fir_handle, st))
             mark("fir_overlap_save")
         if len(self.tables.odd):

@@ -124,14 +124,15 @@ typedef struct {
     int64_t ir;               /* offset of the IR taps in irpool */
     int32_t ir_len;
     int32_t h_len;            /* ir_len + max tap delay */
-    int64_t h;                /* offset of the combined taps in hpool */
+    int64_t h;                /* unused (kept for layout stability) */
     int32_t tap_begin, tap_end;
     int64_t x, y;             /* offsets of the render's mono input / output */
     int32_t out_n;
     int32_t x_begin, x_end;   /* support of the input: samples outside [x_begin, x_end) are exactly zero */
     int32_t _pad;
 } ms_fir_render;
-/* ms_fir_build_f32 / ms_fir_build_f64: declared below by MS_DECLARE_API */
+/* The cloud and the IR are both causal LTI filters: the library keeps the spectrum of every distinct IR
+ * (computed once in ms_fir_create) and composes IRspec * (1 + FFT(cloud taps)) per render in ms_fir_run. */
 /* ms_fir_workspace_bytes_f32 / ms_fir_workspace_bytes_f64: declared below by MS_DECLARE_API */
 /* ms_fir_create_f32 / ms_fir_create_f64: declared below by MS_DECLARE_API */
 /* ms_fir_run_f32 / ms_fir_run_f64: declared below by MS_DECLARE_API */
@@ -172,11 +173,10 @@ typedef struct {
     int ms_synth_tilt_finish##SFX(const ms_synth_evt* dev_evts, int n_evts, REAL* pool, void* stream); \
     int ms_overlap_add##SFX(const ms_ola_render* dev_renders, int n_renders, int max_out_n, const ms_ola_evt* dev_evts, \
     const REAL* pool, REAL* mono, void* stream); \
-    int ms_fir_build##SFX(const ms_fir_render* dev_renders, int n_renders, int max_h_len, const int32_t* tap_off, \
-    const REAL* tap_gain, const REAL* irpool, REAL* hpool, void* stream); \
     size_t ms_fir_workspace_bytes##SFX(const ms_fir_render* host_renders, int n_renders); \
-    int ms_fir_create##SFX(const ms_fir_render* host_renders, int n_renders, const REAL* hpool, const REAL* mono_in, \
-    REAL* mono_out, void* workspace, size_t workspace_bytes, void* stream, void** handle); \
+    int ms_fir_create##SFX(const ms_fir_render* host_renders, int n_renders, const REAL* irpool, const int32_t* tap_off, \
+    const REAL* tap_gain, const REAL* mono_in, REAL* mono_out, void* workspace, size_t workspace_bytes, void* stream, \
+    void** handle); \
     int ms_fir_run##SFX(void* handle, void* stream); \
     void ms_fir_destroy##SFX(void* handle); \
     int ms_post##SFX(const ms_post_render* dev_renders, int n_renders, int max_n, REAL* mono, uint64_t* maxbits, \
