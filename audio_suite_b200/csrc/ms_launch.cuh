@@ -6,6 +6,8 @@
 #include <stddef.h>
 #include <stdio.h>
 #include <string>
+#include <string.h>
+#include <mutex>
 
 struct MsDim { unsigned x, y; };
 
@@ -61,9 +63,52 @@ int ms_launch(MsDim grid, int block, size_t smem, ms_stream_t st, Args... args) 
 }
 static inline void* ms_dev_alloc(size_t bytes) { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; return p; }
 static inline void ms_dev_free(void* p) { cudaFree(p); }
+// Job tables are built in pageable host memory (std::vector).  A cudaMemcpyAsync from pageable memory makes
+// the host wait for the stream, which would serialise "build the tables of slice k+1" behind "render slice k".
+// So every upload is staged through a small ring of pinned blocks owned by the library: memcpy into the ring,
+// async DMA from there; a block is reused only after the event recorded behind its last copy has completed.
+struct MsStageRing {
+    static const size_t BLK = (size_t)8 << 20;
+    static const int NB = 6;
+    char* base[NB]; cudaEvent_t ev[NB]; bool used[NB]; cudaStream_t last[NB];
+    int cur; size_t off; std::mutex mu; bool ok;
+    MsStageRing() : cur(0), off(0), ok(true) { for (int i = 0; i < NB; ++i) { base[i] = nullptr; used[i] = false; last[i] = 0; } }
+    int open(int b) {
+        if (!base[b]) {
+            if (cudaHostAlloc((void**)&base[b], BLK, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); base[b] = nullptr; return -1; }
+            if (cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming) != cudaSuccess) return -1;
+        }
+        if (used[b]) { if (cudaEventSynchronize(ev[b]) != cudaSuccess) return -1; used[b] = false; }
+        return 0;
+    }
+    int copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+        std::lock_guard<std::mutex> lk(mu);
+        const char* s = (const char*)src; char* d = (char*)dst;
+        if (!base[cur] && open(cur)) return -1;
+        while (bytes) {
+            if (off >= BLK || (off > 0 && last[cur] != st)) {          // next block (also when the stream changes)
+                cur = (cur + 1) % NB; off = 0;
+                if (open(cur)) return -1;
+            }
+            const size_t c = bytes < BLK - off ? bytes : BLK - off;
+            memcpy(base[cur] + off, s, c);
+            if (cudaMemcpyAsync(d, base[cur] + off, c, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+            if (cudaEventRecord(ev[cur], st) != cudaSuccess) return -1;
+            used[cur] = true; last[cur] = st;
+            off += (c + 255) & ~(size_t)255; s += c; d += c; bytes -= c;
+        }
+        return 0;
+    }
+};
+MsStageRing& ms_stage_ring();
 static inline int ms_h2d(void* dst, const void* src, size_t bytes, ms_stream_t st) {
     ms_h2d_counter() += bytes;
-    MS_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)); return 0;
+    if (bytes == 0) return 0;
+    if (ms_stage_ring().copy(dst, src, bytes, st)) {
+        cudaGetLastError();
+        MS_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));       // pageable fallback (slower, still correct)
+    }
+    return 0;
 }
 static inline int ms_memset(void* dst, int v, size_t bytes, ms_stream_t st) {
     MS_CUDA_OK(cudaMemsetAsync(dst, v, bytes, st)); return 0;

@@ -5,6 +5,7 @@ unsigned long long& ms_launch_counter() { static unsigned long long n = 0; retur
 extern "C" unsigned long long ms_launch_count(void) { return ms_launch_counter(); }
 unsigned long long& ms_h2d_counter() { static unsigned long long n = 0; return n; }
 extern "C" unsigned long long ms_h2d_bytes(void) { return ms_h2d_counter(); }
+MsStageRing& ms_stage_ring() { static MsStageRing r; return r; }
 extern "C" int ms_version(void) { return MS_ABI_VERSION; }
 extern "C" const char* ms_last_error(void) { return ms_err_slot().c_str(); }
 extern "C" int ms_is_cuda_build(void) { return 1; }

@@ -44,7 +44,32 @@ class CudaDevice:
     def empty(self, n, dtype):
         t = {np.float32: self.torch.float32, np.float64: self.torch.float64, np.uint8: self.torch.uint8,
              np.int32: self.torch.int32, np.uint64: self.torch.int64}[dtype]
-        return self.torch.empty(max(1, int(n)), dtype=t, device=self.dev)
+        n = max(1, int(n))
+        s = self._slot
+        if s is not None:                       # carve from the slot's arena (no allocator call on the streamed path)
+            nbytes = n * np.dtype(dtype).itemsize
+            a = (s["off"] + 255) & ~255
+            s["off"] = a + nbytes               # virtual offset: also counts what did not fit, to size the next arena
+            if a + nbytes <= s["cap"]:
+                return s["buf"][a:a + nbytes].view(t)
+        return self.torch.empty(n, dtype=t, device=self.dev)
+
+    # ---- arenas for streamed batches: slot k is one device buffer that the k-th live renderer carves all of
+    #      its tensors from; it is sized from what the previous user of the slot needed and only ever grows.
+    _slot = None
+
+    def slot_begin(self, key):
+        slots = self.__dict__.setdefault("_slots", {})
+        s = slots.setdefault(key, {"buf": None, "cap": 0, "off": 0})
+        if s["off"] > s["cap"]:
+            s["buf"] = None
+            s["cap"] = int(s["off"] * 1.2) + (64 << 20)
+            s["buf"] = self.torch.empty(s["cap"], dtype=self.torch.uint8, device=self.dev)
+        s["off"] = 0
+        self._slot = s
+
+    def slot_end(self):
+        self._slot = None
 
     def zeros(self, n, dtype):
         b = self.empty(n, dtype)
@@ -52,11 +77,37 @@ class CudaDevice:
         return b
 
     def upload(self, arr):
-        """numpy array (any dtype) -> device bytes."""
-        a = np.array(arr, copy=True, order="C")
+        """numpy array (any dtype) -> device bytes, staged through a ring of pinned blocks owned by the device
+        object.  (`tensor.pin_memory()` per upload costs 10-20 ms a call whenever other processes on the box
+        are busy -- measured on the B200 hosts with the planning workers running -- so nothing on the
+        streamed path allocates pinned memory.)"""
+        a = np.ascontiguousarray(arr)
         self.uploaded += a.nbytes
-        host = self.torch.from_numpy(a.view(np.uint8).reshape(-1) if a.size else np.zeros(1, np.uint8))
-        return host.pin_memory().to(self.dev, non_blocking=True)
+        flat = a.view(np.uint8).reshape(-1) if a.size else np.zeros(1, np.uint8)
+        n = flat.size
+        dst = self.empty(n, np.uint8)
+        if n > self._RING_BLOCK:
+            return dst.copy_(self.torch.from_numpy(np.array(flat, copy=True)).pin_memory(), non_blocking=True)
+        if not self._ring:
+            self._ring = [[self.torch.empty(self._RING_BLOCK, dtype=self.torch.uint8).pin_memory(), None] for _ in range(self._RING_N)]
+            self._ring_np = [blk[0].numpy() for blk in self._ring]
+            self._ring_cur, self._ring_off = 0, 0
+        if self._ring_off + n > self._RING_BLOCK:
+            self._ring_cur, self._ring_off = (self._ring_cur + 1) % self._RING_N, 0
+            ev = self._ring[self._ring_cur][1]
+            if ev is not None:
+                ev.synchronize()              # long complete in steady state: the ring holds several slices of tables
+        blk, off = self._ring[self._ring_cur], self._ring_off
+        self._ring_np[self._ring_cur][off:off + n] = flat
+        dst.copy_(blk[0][off:off + n], non_blocking=True)
+        if blk[1] is None:
+            blk[1] = self.torch.cuda.Event()
+        blk[1].record(self.torch.cuda.current_stream(self.dev))
+        self._ring_off = off + ((n + 255) & ~255)
+        return dst
+
+    _RING_BLOCK, _RING_N = 32 << 20, 4
+    _ring = None
 
     def ptr(self, buf):
         return C.c_void_p(buf.data_ptr())
@@ -117,12 +168,15 @@ class BatchRenderer:
     """Plans a batch of independent renders once, keeps every table resident on the device and
     re-runs the kernel sequence on demand (`run()`), e.g. for benchmarking or repeated renders."""
 
-    def __init__(self, params_list, device=None, precision="auto", workers=None):
+    def __init__(self, params_list=None, device=None, precision="auto", workers=None, tables=None):
         import time as _time
         from . import tables as T
         self.dev = device or CudaDevice()
         t0 = _time.perf_counter()
-        self.tables, self.plans = T.plan_and_pack(params_list, workers)      # plans is None for pooled batches
+        if tables is not None:
+            self.tables, self.plans = tables, None                            # already planned (tables.plan_stream)
+        else:
+            self.tables, self.plans = T.plan_and_pack(params_list, workers)  # plans is None for pooled batches
         self.t_plan = _time.perf_counter() - t0
         self.precision = choose_precision(self.plans) if precision == "auto" else precision
         self.api = _abi.Api(self.dev.lib, self.precision)
@@ -135,7 +189,14 @@ class BatchRenderer:
 
     # ---- device buffers + native plans -----------------------------------------------------------------
     def _upload(self, T):
+        import os as _os, time as _time
         dev, t, real = self.dev, self.tables, self.real
+        _tr = [] if _os.environ.get("MS_TRACE") else None
+        _t0 = _time.perf_counter()
+
+        def _mark(name):
+            if _tr is not None:
+                _tr.append((name, _time.perf_counter() - _t0))
         self.n_renders, self.n_evt, self.frames = len(t.post), len(t.sy1), t.frames
         self.max_out_n, self.max_h = t.max_out_n, t.max_h
         self.any_dust, self.any_tilt = t.dust_pos.size > 0, t.tilt[0].size > 0
@@ -144,14 +205,17 @@ class BatchRenderer:
         self.mono = dev.zeros(t.mono_n, real)
         self.out = dev.empty(2 * t.frames, np.float32)
         self.maxbits = dev.zeros(self.n_renders, np.uint64)
+        _mark("alloc")
         self.d_sy1, self.d_sy2 = dev.upload(t.sy1), dev.upload(t.sy2)
         self.d_ola_r, self.d_ola_e = dev.upload(t.ola_r), dev.upload(t.ola_e)
         self.d_post = dev.upload(t.post)
         if self.any_dust:
             self.d_dpos, self.d_dval = dev.upload(t.dust_pos), dev.upload(t.dust_val.astype(real))
+        _mark("uploads")
         self.tilt_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.tilt), self.pool, self.pool)
         self.grain_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.grain), self.pool, self.pool)
         self.rot_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.rot), self.mono, self.mono)
+        _mark("spectral_create")
         self.fir_handle = C.c_void_p(None)
         if self.n_fir:
             fir = np.ascontiguousarray(t.fir)
@@ -166,6 +230,9 @@ class BatchRenderer:
             _check(dev, self.api.ms_fir_create(fir.ctypes.data, len(fir), dev.ptr(self.d_ir), dev.ptr(self.d_tap_off),
                                                dev.ptr(self.d_tap_gain), dev.ptr(self.mono), dev.ptr(self.mono),
                                                dev.ptr(self.fir_ws), need, dev.stream_ptr(), C.byref(self.fir_handle)))
+        _mark("fir_create")
+        if _tr is not None:
+            print("  _upload: " + " ".join("%s %.1f" % (n, 1e3 * v) for n, v in _tr), flush=True)
 
     # ---- execution -------------------------------------------------------------------------------------
     def run(self, mark=None):
@@ -253,10 +320,77 @@ def render(params, progress=None, device=None, precision="auto"):
     return audio, meta
 
 
-def render_batch(params_list, device=None, precision="auto"):
-    """Independent renders as one batched launch sequence.  Returns a list of float32 [out_n, 2]."""
-    br = BatchRenderer(params_list, device=device, precision=precision)
-    br.run()
-    outs = [br.output(r) for r in range(br.n_renders)]
-    br.close()
-    return outs
+def render_batch(params_list, device=None, precision="auto", host_out=None, chunk=512, depth=3, workers=None, piece=32):
+    """Independent renders (the reference's batch loop, main_v2.py:1578-1593) streamed through the GPU.
+
+    The batch is cut into slices of `chunk` renders.  Worker processes plan slice k+1 (numpy Generators,
+    integer segment maps) while the GPU renders slice k and slice k-1 drains to host memory on a copy
+    stream, so planning, kernels and the device->host transfer overlap.  Returns a list of float32
+    [out_n, 2] arrays, one per render, in order -- views into `host_out` (a pinned 1-D float32 torch tensor
+    of at least 2 * total frames) when it is given, else into a pinned buffer allocated here."""
+    from collections import deque
+    from . import tables as T
+    dev = device or CudaDevice()
+    if not hasattr(dev, "torch"):                   # host emulator device (tests): one slice after the other
+        outs = []
+        for tb in T.plan_stream(params_list, chunk, workers=workers or 1, piece=piece):
+            br = BatchRenderer(device=dev, precision=precision, tables=tb)
+            br.run()
+            outs += [br.output(r) for r in range(br.n_renders)]
+            br.close()
+        return outs
+    torch = dev.torch
+    total = sum(int(max(1, round(float(p["out_dur_s"]) * int(p["base_sr"])))) for p in params_list)      # main_v2.py:590
+    if host_out is None:
+        host_out = torch.empty(2 * total, dtype=torch.float32).pin_memory()
+    if host_out.numel() < 2 * total:
+        raise ValueError("host_out is smaller than 2 * total frames")
+    main = torch.cuda.current_stream(dev.dev)
+    copy = torch.cuda.Stream(dev.dev)
+    live, views, at = deque(), [], 0
+    h2d = 0
+    import os as _os, time as _time
+    trace = [] if _os.environ.get("MS_TRACE") else None
+    t_start = t_prev = _time.perf_counter()
+    k = 0
+    for tb in T.plan_stream(params_list, chunk, workers=workers, piece=piece):
+        t_got = _time.perf_counter()
+        dev.slot_begin(k % (depth + 1))        # the previous user of this slot has retired (see below)
+        try:
+            br = BatchRenderer(device=dev, precision=precision, tables=tb)
+        finally:
+            dev.slot_end()
+        k += 1
+        t_ctor = _time.perf_counter()
+        br.run()
+        h2d += br.h2d_bytes
+        rendered = torch.cuda.Event()
+        rendered.record(main)
+        with torch.cuda.stream(copy):
+            copy.wait_event(rendered)
+            host_out[at:at + 2 * tb.frames].copy_(br.out[:2 * tb.frames], non_blocking=True)
+            drained = torch.cuda.Event()
+            drained.record(copy)
+        for a, n in zip(tb.out_at.tolist(), tb.out_n.tolist()):
+            views.append((at + 2 * a, n))
+        at += 2 * tb.frames
+        live.append((br, drained))
+        t_enq = _time.perf_counter()
+        while len(live) >= depth + 1:
+            old, ev = live.popleft()
+            ev.synchronize()
+            old.close()
+        if trace is not None:
+            now = _time.perf_counter()
+            trace.append("  slice %d: wait_plan %.1f ctor %.1f enqueue %.1f retire %.1f | t=%.1f ms" % (
+                k - 1, 1e3 * (t_got - t_prev), 1e3 * (t_ctor - t_got), 1e3 * (t_enq - t_ctor), 1e3 * (now - t_enq), 1e3 * (now - t_start)))
+            t_prev = now
+    while live:
+        old, ev = live.popleft()
+        ev.synchronize()
+        old.close()
+    render_batch.last_h2d_bytes = h2d
+    if trace is not None:
+        print("\n".join(trace) + "\n  drained at t=%.1f ms" % (1e3 * (_time.perf_counter() - t_start)), flush=True)
+    flat = host_out.numpy()
+    return [flat[a:a + 2 * n].reshape(n, 2) for a, n in views]

@@ -32,7 +32,20 @@ _NEXT_ROW_MODES = ("Crackle / corona", "Stick–slip friction", "Micro-chaos", "
 
 
 # --------------------------------------------------------------------------- breakpoint lanes (M:452-482)
+_BP_CACHE = {}
+
+
 def parse_breakpoints(text):
+    """M:452-467.  Cached per text: a sweep repeats the same four lane strings thousands of times."""
+    hit = _BP_CACHE.get(text)
+    if hit is None:
+        if len(_BP_CACHE) > 1024:
+            _BP_CACHE.clear()
+        hit = _BP_CACHE[text] = tuple(_parse_breakpoints(text))
+    return list(hit)
+
+
+def _parse_breakpoints(text):
     pts = []
     for part in (text or "").strip().split(","):
         part = part.strip()
@@ -378,7 +391,9 @@ def _plan_dust(ev, density):
     vals = rng.uniform(-1, 1, size=k)
     dense = np.zeros(n, dtype=np.float64)
     dense[where] = vals                                  # duplicates: last write wins
-    pos = np.unique(where)
+    hit = np.zeros(n, dtype=bool)
+    hit[where] = True
+    pos = np.flatnonzero(hit)                            # sorted unique positions
     ev.dust_pos = pos.astype(np.int32)
     ev.dust_val = dense[pos]
     ev.ker_len = max(8, int(0.01 * n))

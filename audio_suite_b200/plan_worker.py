@@ -18,14 +18,16 @@ def main():
             return
         (size,) = struct.unpack("<Q", head)
         chunk = pickle.loads(inp.read(size))
-        try:
-            reply = ("ok", T.pack_chunk([P.plan_render(p) for p in chunk]))
-        except BaseException as e:                     # the parent re-raises
-            reply = ("err", e)
-        blob = pickle.dumps(reply, protocol=pickle.HIGHEST_PROTOCOL)
-        out.write(struct.pack("<Q", len(blob)))
-        out.write(blob)
-        out.flush()
+        # a dict {"pieces": [[params, ...], ...]} is answered piece by piece (streamed batches); a plain list is one piece
+        for piece in (chunk["pieces"] if isinstance(chunk, dict) else [chunk]):
+            try:
+                reply = ("ok", T.pack_chunk([P.plan_render(p) for p in piece]))
+            except BaseException as e:                     # the parent re-raises
+                reply = ("err", e)
+            blob = pickle.dumps(reply, protocol=pickle.HIGHEST_PROTOCOL)
+            out.write(struct.pack("<Q", len(blob)))
+            out.write(blob)
+            out.flush()
 
 
 if __name__ == "__main__":

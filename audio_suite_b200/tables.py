@@ -357,6 +357,34 @@ def pair_jobs(items):
 
 
 # --------------------------------------------------------------------------- worker pool
+class _Pending:
+    """Results of _WorkerPool.submit, retrievable in any order while the workers are still busy."""
+
+    def __init__(self, n):
+        import threading
+        self.results, self.ready, self.error, self.cv, self.threads = [None] * n, [False] * n, None, threading.Condition(), []
+
+    def put(self, i, value):
+        with self.cv:
+            self.results[i], self.ready[i] = value, True
+            self.cv.notify_all()
+
+    def fail(self, err):
+        with self.cv:
+            if self.error is None:
+                self.error = err
+            self.cv.notify_all()
+
+    def get(self, i):
+        with self.cv:
+            while not self.ready[i] and self.error is None:
+                self.cv.wait()
+            if not self.ready[i]:
+                raise self.error
+            out, self.results[i] = self.results[i], None
+            return out
+
+
 class _WorkerPool:
     """Persistent `python -m audio_suite_b200.plan_worker` subprocesses, one feeder thread each."""
 
@@ -371,46 +399,82 @@ class _WorkerPool:
         self.size = size
         self.procs = [subprocess.Popen([sys.executable, "-m", "audio_suite_b200.plan_worker"], stdin=subprocess.PIPE,
                                        stdout=subprocess.PIPE, env=env) for _ in range(size)]
+        # one worker per core, leaving the first cores of the affinity mask to the parent (kernel launches, table
+        # uploads, the copy stream): measured on the 16-core B200 hosts, workers floating over all cores stall
+        # the parent's CUDA calls for tens of ms at a time
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            spare = int(os.environ.get("MS_PLAN_SPARE_CORES", "2")) if len(cores) >= 8 else 0
+            usable = cores[spare:] or cores
+            if os.environ.get("MS_PLAN_PIN", "1") != "0":
+                for i, p in enumerate(self.procs):
+                    os.sched_setaffinity(p.pid, {usable[i % len(usable)]})
+        except Exception:
+            pass
+        try:                                    # 1 MiB pipes: a request or a packed piece fits without blocking the writer
+            import fcntl
+            for p in self.procs:
+                for f in (p.stdin, p.stdout):
+                    fcntl.fcntl(f.fileno(), 1031, 1 << 20)          # F_SETPIPE_SZ
+        except Exception:
+            pass
 
-    def map(self, chunks):
+    def submit(self, chunks, prep=None):
+        """Start planning `chunks` (lists of parameter dicts); returns a _Pending whose get(i) blocks until
+        chunk i is packed.  Chunks are handed out in order, so early chunks finish first.  `prep` (optional)
+        is applied to a chunk by the feeder thread right before it is sent."""
         import pickle
         import struct
         import threading
-        results = [None] * len(chunks)
-        errors = []
+        pend = _Pending(len(chunks))
         todo = list(enumerate(chunks))
         lock = threading.Lock()
 
         def serve(proc):
-            while True:
+            # two requests in flight per worker: the worker finds its next piece already in the pipe when it
+            # finishes one, instead of waiting for this thread to be scheduled on a box whose cores are all busy
+            from collections import deque
+            inflight = deque()
+
+            def send_next():
                 with lock:
-                    if not todo or errors:
+                    if not todo or pend.error is not None:
                         return
                     i, chunk = todo.pop(0)
-                try:
-                    blob = pickle.dumps(chunk, protocol=pickle.HIGHEST_PROTOCOL)
-                    proc.stdin.write(struct.pack("<Q", len(blob)))
-                    proc.stdin.write(blob)
-                    proc.stdin.flush()
+                if prep is not None:
+                    chunk = prep(chunk)
+                blob = pickle.dumps(chunk, protocol=pickle.HIGHEST_PROTOCOL)
+                proc.stdin.write(struct.pack("<Q", len(blob)))
+                proc.stdin.write(blob)
+                proc.stdin.flush()
+                inflight.append(i)
+            try:
+                send_next()
+                send_next()
+                while inflight:
+                    i = inflight.popleft()
                     head = proc.stdout.read(8)
                     if len(head) < 8:
                         raise RuntimeError("planning worker died")
                     status, payload = pickle.loads(proc.stdout.read(struct.unpack("<Q", head)[0]))
                     if status != "ok":
                         raise payload
-                    results[i] = payload
-                except BaseException as e:
-                    errors.append(e)
-                    return
-        threads = [threading.Thread(target=serve, args=(p,)) for p in self.procs]
-        for t in threads:
+                    pend.put(i, payload)
+                    send_next()
+            except BaseException as e:
+                pend.fail(e)
+        pend.threads = [threading.Thread(target=serve, args=(p,), daemon=True) for p in self.procs]
+        for t in pend.threads:
             t.start()
-        for t in threads:
-            t.join()
-        if errors:
+        return pend
+
+    def map(self, chunks):
+        pend = self.submit(chunks)
+        try:
+            return [pend.get(i) for i in range(len(chunks))]
+        except BaseException:
             self.close()
-            raise errors[0]
-        return results
+            raise
 
     def close(self):
         for p in self.procs:
@@ -432,24 +496,95 @@ def shutdown_pool():
         _POOL = None
 
 
-def plan_and_pack(params_list, workers=None):
-    """Returns (Tables, plans or None).  Small batches are planned in-process (plans kept for progress /
-    inspection); large ones by a persistent pool of worker processes that return packed chunks."""
+def _pool(workers):
     import atexit
-    import os
-    n = len(params_list)
-    if workers is None:
-        workers = int(os.environ.get("MS_PLAN_WORKERS", "0")) or min(32, len(os.sched_getaffinity(0)))
-    min_batch = int(os.environ.get("MS_PLAN_MIN_BATCH", "256"))
-    if n < min_batch or workers <= 1:
-        plans = [P.plan_render(p) for p in params_list]
-        return pack_chunk(plans), plans
     global _POOL
     if _POOL is None or _POOL.size != workers or not _POOL.procs:
         shutdown_pool()
         _POOL = _WorkerPool(workers)
         atexit.register(shutdown_pool)
+    return _POOL
+
+
+def default_workers():
+    import os
+    cores = len(os.sched_getaffinity(0))
+    return int(os.environ.get("MS_PLAN_WORKERS", "0")) or min(32, max(1, cores - 2 if cores >= 8 else cores))
+
+
+def plan_stream(params_list, chunk, workers=None, piece=32):
+    """Generator of packed Tables for consecutive slices of `chunk` renders.  The whole list is handed to the
+    worker pool at once (pieces of `piece` renders, in order); slice k is yielded as soon as its pieces are
+    packed, while the workers carry on with the later ones -- the caller renders slice k meanwhile."""
+    n = len(params_list)
+    workers = default_workers() if workers is None else workers
+    if workers <= 1:
+        for a in range(0, n, chunk):
+            yield pack_chunk([P.plan_render(p) for p in params_list[a:a + chunk]])
+        return
+    bounds = []
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        bounds.append([(i, min(b, i + piece)) for i in range(a, b, piece)])
+    flat = [ab for bs in bounds for ab in bs]
+    # Static round-robin assignment, no threads in the parent: piece i belongs to worker i % W.  Every worker
+    # first gets its piece of the first slice, then ONE message with all of its remaining pieces, and answers
+    # piece by piece; the parent reads the answers in piece order straight from the pipes (1 MiB pipes let a
+    # worker run a few pieces ahead).  Impulse responses are slimmed before pickling (P._slim_params).
+    import pickle
+    import struct
+    pool = _pool(workers)
+    W = len(pool.procs)
+
+    def send(w, obj):
+        blob = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+        f = pool.procs[w].stdin
+        f.write(struct.pack("<Q", len(blob)))
+        f.write(blob)
+        f.flush()
+
+    def slim(i):
+        a, b = flat[i]
+        return [P._slim_params(p) for p in params_list[a:b]]
+
+    def recv(w):
+        f = pool.procs[w].stdout
+        head = f.read(8)
+        if len(head) < 8:
+            raise RuntimeError("planning worker died")
+        status, payload = pickle.loads(f.read(struct.unpack("<Q", head)[0]))
+        if status != "ok":
+            raise payload
+        return payload
+    try:
+        for w in range(min(W, len(flat))):
+            send(w, slim(w))
+        for w in range(W):
+            rest = [slim(i) for i in range(w + W, len(flat), W)]
+            if rest:
+                send(w, {"pieces": rest})
+        k = 0
+        for bs in bounds:
+            parts = [recv((k + t) % W) for t in range(len(bs))]
+            k += len(bs)
+            yield merge_chunks(parts)
+    except BaseException:
+        shutdown_pool()          # pipes may hold unread answers: start from fresh workers next time
+        raise
+
+
+def plan_and_pack(params_list, workers=None):
+    """Returns (Tables, plans or None).  Small batches are planned in-process (plans kept for progress /
+    inspection); large ones by a persistent pool of worker processes that return packed chunks."""
+    import os
+    n = len(params_list)
+    if workers is None:
+        workers = default_workers()
+    min_batch = int(os.environ.get("MS_PLAN_MIN_BATCH", "256"))
+    if n < min_batch or workers <= 1:
+        plans = [P.plan_render(p) for p in params_list]
+        return pack_chunk(plans), plans
     slim = [P._slim_params(p) for p in params_list]      # do not pickle multi-MB impulse responses per render
     per = max(min(32, max(1, n // workers)), (n + 2 * workers - 1) // (2 * workers))
-    chunks = _POOL.map([slim[i:i + per] for i in range(0, n, per)])
+    chunks = _pool(workers).map([slim[i:i + per] for i in range(0, n, per)])
     return merge_chunks(chunks), None

@@ -105,8 +105,14 @@ def test_pooled_planning_matches_in_process(emul, monkeypatch):
                                       ("Resonant strike", 25.0)])]
     ps[3]["base_sr"], ps[3]["out_dur_s"] = 44100, 0.05003          # odd length -> FFT rotation path
     one = engine.render_batch(ps, device=emul)
+    streamed = engine.render_batch(ps, device=emul, chunk=5, workers=3, piece=2)     # slices of 5 = pieces of 2+2+1, 2
     monkeypatch.setenv("MS_PLAN_MIN_BATCH", "2")
     monkeypatch.setenv("MS_PLAN_WORKERS", "3")
-    pooled = engine.render_batch(ps, device=emul)
-    for a, b in zip(one, pooled):
+    br = engine.BatchRenderer(ps, device=emul)                                       # plan_and_pack through the pool
+    assert br.plans is None
+    br.run()
+    pooled = [br.output(r) for r in range(br.n_renders)]
+    br.close()
+    for a, b, c in zip(one, pooled, streamed):
         assert a.shape == b.shape and np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))) < 1e-6
+        assert a.shape == c.shape and np.max(np.abs(a.astype(np.float64) - c.astype(np.float64))) < 1e-6

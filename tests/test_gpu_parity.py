@@ -78,6 +78,21 @@ def test_render_c5_batch_against_oracle(cuda_dev):
         assert np.max(np.abs(got.astype(np.float64) - ref)) < K.MAX_ABS_TOL + K.reference_noise_floor(p, taps)
 
 
+def test_streamed_batch_equals_one_launch_sequence(cuda_dev):
+    """render_batch streams slices through planning workers, the GPU and a copy stream; the audio must be
+    what one BatchRenderer over the whole list produces."""
+    import torch
+    ps = [configs.c5_params(i) for i in range(200, 296)]
+    host = torch.empty(2 * 96 * 96000, dtype=torch.float32).pin_memory()
+    outs = engine.render_batch(ps, device=cuda_dev, host_out=host, chunk=40, piece=16, depth=2)
+    br = engine.BatchRenderer(ps, device=cuda_dev)
+    br.run()
+    for r in (0, 39, 40, 79, 80, 95):
+        want = br.output(r)
+        assert outs[r].shape == want.shape and np.max(np.abs(outs[r] - want)) < 1e-6, r
+    br.close()
+
+
 def test_render_c4_shortened_against_oracle(cuda_dev):
     """C4 with the output cut to 12 s (same 96 kHz, x500 -> 30 MHz clip, n = 300000 grains, x2.5 stretch,
     ER cloud, 10 s IR -> 8192 taps, stereo): the oracle finishes in seconds."""
