@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmicrosound_b200.so")
+# MS_LIB_PATH: A/B-test another build of the same CUDA library (development only; still no CPU fallback)
+LIB_PATH = os.environ.get("MS_LIB_PATH") or os.path.join(_HERE, "csrc", "libmicrosound_b200.so")
 
 
 class BandEdge(C.Structure):
@@ -47,7 +48,7 @@ class OlaRender(C.Structure):
     _fields_ = [("out", C.c_int64), ("out_n", C.c_int32), ("ev_begin", C.c_int32), ("ev_end", C.c_int32),
                 ("max_len", C.c_int32), ("A", C.c_int32), ("D_end", C.c_int32), ("sus_end", C.c_int32),
                 ("has_release", C.c_int32), ("inv_A", C.c_double), ("inv_D", C.c_double), ("inv_R", C.c_double),
-                ("S", C.c_double), ("curve", C.c_double)]
+                ("S", C.c_double), ("curve", C.c_double), ("env", C.c_int64)]
 
 
 class OlaEvt(C.Structure):
@@ -87,7 +88,8 @@ _STAGES = {
     "ms_synth_normal": (_I, [_P, _I, _P, _P]),
     "ms_synth_dust": (_I, [_P, _I, _P, _P, _P, _P]),
     "ms_synth_tilt_finish": (_I, [_P, _I, _P, _P]),
-    "ms_overlap_add": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "ms_adsr_tables": (_I, [_P, _I, _I, _P, _P]),
+    "ms_overlap_add": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "ms_fir_workspace_bytes": (_Z, [_P, _I]),
     "ms_fir_create": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _Z, _P, C.POINTER(C.c_void_p)]),
     "ms_fir_run": (_I, [_P, _P]),

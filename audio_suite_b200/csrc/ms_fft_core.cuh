@@ -30,6 +30,8 @@ struct RadixPlan {
     unsigned char rad[MS_MAX_RADICES];
     unsigned mg_ns[MS_MAX_RADICES];   // magic multipliers: x / Ns_i  == umulhi(x, mg_ns[i])  (0: divisor is 1)
     unsigned mg_pv[MS_MAX_RADICES];   //                    x / (F / rad_i)
+    unsigned short tws[MS_MAX_RADICES];   // twiddle stride of pass i: F / (Ns_i * rad_i)
+    unsigned mg_F;                    //                    x / F
 };
 // q = x / d for 0 <= x < 2^16-ish ranges used here (x * d' never overflows): m = floor(2^32 / d) + 1
 static inline unsigned ms_magic(unsigned d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / d) + 1u; }
@@ -61,7 +63,9 @@ static inline int ms_make_radix_plan(int F, RadixPlan* p) {
         p->mg_ns[i] = ms_magic((unsigned)Ns);
         p->mg_pv[i] = ms_magic((unsigned)(F / p->rad[i]));
         Ns *= p->rad[i];
+        p->tws[i] = (unsigned short)(F / Ns);
     }
+    p->mg_F = ms_magic((unsigned)F);
     return m == 1;
 }
 
@@ -134,17 +138,15 @@ template <> struct Bfly<8> {
 // before it starts the next, so nothing but the R values of a butterfly lives in registers and one
 // barrier per pass suffices.  tw = table of w_F^i (i < F), forward sign.  Integer divisions by the
 // per-pass constants go through host-computed magic multipliers.
-template <int R>
-MS_DEV void stockham_pass(const cpx* MS_RESTRICT src, cpx* MS_RESTRICT dst, const TileGeom& g, int F, int Ns,
+template <int R, int CM>
+MS_DEV void stockham_pass(const cpx* MS_RESTRICT src, cpx* MS_RESTRICT dst, const TileGeom& g, int per_vec, int Ns, int tws,
                           unsigned mg_ns, unsigned mg_pv, unsigned mg_cnt,
                           const cpx* MS_RESTRICT tw, const Ctx& c) {
-    const int per_vec = F / R;
     const int nb = per_vec * g.cnt;
-    const int tws = F / (Ns * R);
 #pragma unroll 2
     for (int b = c.tid; b < nb; b += c.nthr) {
         int vec, j;
-        if (g.colmajor) { j = ms_fastdiv(b, mg_cnt); vec = b - j * g.cnt; } else { vec = ms_fastdiv(b, mg_pv); j = b - vec * per_vec; }
+        if (CM) { j = ms_fastdiv(b, mg_cnt); vec = b - j * g.cnt; } else { vec = ms_fastdiv(b, mg_pv); j = b - vec * per_vec; }
         const int k = j - ms_fastdiv(j, mg_ns) * Ns;
         cpx v[R];
 #pragma unroll
@@ -179,18 +181,23 @@ MS_DEV void stockham_pass(const cpx* MS_RESTRICT src, cpx* MS_RESTRICT dst, cons
 
 // Full forward FFT of every vector of the tile.  `a` holds the input (caller synchronised after
 // filling it), `b` is the second buffer of the same size.  Returns the buffer that holds the result.
+MS_DEV unsigned ms_magic_dev(int d) { return d <= 1 ? 0u : (unsigned)(0x100000000ull / (unsigned)d) + 1u; }
+template <int CM>
 MS_DEV cpx* tile_fft(cpx* a, cpx* b, const TileGeom& g, const RadixPlan& p, const cpx* MS_RESTRICT tw, const Ctx& c) {
     int Ns = 1;
-    const unsigned mg_cnt = g.cnt <= 1 ? 0u : (unsigned)(0x100000000ull / (unsigned)g.cnt) + 1u;
+    const unsigned mg_cnt = CM ? ms_magic_dev(g.cnt) : 0u;
+    int per_vec = p.F;
     for (int i = 0; i < p.nrad; ++i) {
         const int r = p.rad[i];
         const unsigned mn = p.mg_ns[i], mp = p.mg_pv[i];
+        const int tws = p.tws[i];
+        per_vec = tws * Ns;                      // F / r
         switch (r) {
-            case 8: stockham_pass<8>(a, b, g, p.F, Ns, mn, mp, mg_cnt, tw, c); break;
-            case 4: stockham_pass<4>(a, b, g, p.F, Ns, mn, mp, mg_cnt, tw, c); break;
-            case 2: stockham_pass<2>(a, b, g, p.F, Ns, mn, mp, mg_cnt, tw, c); break;
-            case 3: stockham_pass<3>(a, b, g, p.F, Ns, mn, mp, mg_cnt, tw, c); break;
-            default: stockham_pass<5>(a, b, g, p.F, Ns, mn, mp, mg_cnt, tw, c); break;
+            case 8: stockham_pass<8, CM>(a, b, g, per_vec, Ns, tws, mn, mp, mg_cnt, tw, c); break;
+            case 4: stockham_pass<4, CM>(a, b, g, per_vec, Ns, tws, mn, mp, mg_cnt, tw, c); break;
+            case 2: stockham_pass<2, CM>(a, b, g, per_vec, Ns, tws, mn, mp, mg_cnt, tw, c); break;
+            case 3: stockham_pass<3, CM>(a, b, g, per_vec, Ns, tws, mn, mp, mg_cnt, tw, c); break;
+            default: stockham_pass<5, CM>(a, b, g, per_vec, Ns, tws, mn, mp, mg_cnt, tw, c); break;
         }
         cpx* t = a; a = b; b = t;
         Ns *= r;

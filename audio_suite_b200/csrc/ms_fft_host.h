@@ -7,14 +7,17 @@ static const int MS_SMALL_MAX = sizeof(real) == 4 ? 8192 : 4096;
 static const int MS_TILE_MAX = sizeof(real) == 4 ? 8192 : 4096;
 
 // ---- kernel structs ----------------------------------------------------------------------------------
+#ifndef MS_FFT_MINB
+#define MS_FFT_MINB 2
+#endif
 template <int LD, int ST, int TWID> struct ColsK {
     static constexpr int MAXT = 512;
-    static constexpr int MINB = 2;        // <= 64 registers: three 256..320-thread CTAs per SM
+    static constexpr int MINB = MS_FFT_MINB;        // 2: <= 64 registers, three 256..320-thread CTAs per SM
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_body<LD, ST, TWID>(jobs, c); }
 };
 template <int LD, int MODE, int ST> struct RowsK {
     static constexpr int MAXT = 512;
-    static constexpr int MINB = 2;
+    static constexpr int MINB = MS_FFT_MINB;
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_rows_body<LD, MODE, ST>(jobs, c); }
 };
 struct GenChirpK {
@@ -44,8 +47,8 @@ struct LaunchShape { int ept, nthr; size_t smem; unsigned gx; };
 static inline int cols_tile_elems(const FftJob& J) { return J.T * (J.B1 ? J.B1 : J.F1); }
 static inline int rows_tile_elems(const FftJob& J) { return J.G * J.F2; }
 static inline int cols_rows(const FftJob& J) { return J.B1 ? J.B1 : J.F1; }
-static inline size_t cols_smem(const FftJob& J) { return 2 * sizeof(cpx) * (size_t)(ms_pad((cols_rows(J) - 1) * J.T + J.T - 1) + 2); }
-static inline size_t rows_smem(const FftJob& J) { return 2 * sizeof(cpx) * (size_t)(J.G * ((ms_pad(J.F2) + 1) | 1) + 2); }
+static inline size_t cols_smem(const FftJob& J) { return MS_JOB_SMEM + 2 * sizeof(cpx) * (size_t)(ms_pad((cols_rows(J) - 1) * J.T + J.T - 1) + 2); }
+static inline size_t rows_smem(const FftJob& J) { return MS_JOB_SMEM + 2 * sizeof(cpx) * (size_t)(J.G * ((ms_pad(J.F2) + 1) | 1) + 2); }
 
 static inline void shape_for(int tile, LaunchShape* s) {
     s->ept = 0;

@@ -245,54 +245,69 @@ MS_DEV void job_store(const FftJob& J, int idx, cpx v) {
     }
 }
 
+// The job descriptor (geometry, radix plans, table pointers, spectral operators: ~1 KB) is staged in shared
+// memory by the CTA: every later field access is a shared-memory load instead of a global one.
+#define MS_JOB_SMEM ((sizeof(FftJob) + 15) / 16 * 16)
+MS_DEV const FftJob& stage_job(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
+    const unsigned* src = (const unsigned*)(jobs + c.by);
+    unsigned* dst = (unsigned*)c.smem;
+    for (int i = c.tid; i < (int)(sizeof(FftJob) / 4); i += c.nthr) dst[i] = src[i];
+    c.sync();
+    return *(const FftJob*)c.smem;
+}
+
 // ---- columns kernel --------------------------------------------------------------------------------
 template <int LD, int ST, int TWID>
 MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
-    const FftJob& J = jobs[c.by];
+    const FftJob& J = stage_job(jobs, c);
     const int T = J.T, F1 = J.F1, F2 = J.F2;
     const int col0 = c.bx * T;
     if (col0 >= F2) return;
     const int cnt = (F2 - col0) < T ? (F2 - col0) : T;
     const int rows = J.B1 ? J.B1 : F1;           // vector length held in the tile
-    cpx* s = (cpx*)c.smem;
+    cpx* s = (cpx*)(c.smem + MS_JOB_SMEM);
+    cpx* const sA = s;
     cpx* s2 = s + (ms_pad((rows - 1) * T + T - 1) + 2);
     TileGeom g; g.cnt = cnt; g.vs = 1; g.es = T; g.colmajor = 1;
     const int total = F1 * cnt;
+    const unsigned mgc = ms_magic_dev(cnt);
     if (J.B1) {
         // length-F1 DFT of every column as chirp * IFFT_B1(FFT_B1(x * chirp) * spec)
         const int all = rows * cnt;
+#pragma unroll 2
         for (int e = c.tid; e < all; e += c.nthr) {
-            const int i = e / cnt, v = e - i * cnt;
+            const int i = ms_fastdiv(e, mgc), v = e - i * cnt;
             cpx val = c_zero();
             if (i < F1) val = c_mul(job_load<LD>(J, i * F2 + col0 + v), __ldg(&J.b1_chirp[i]));
             s[tile_addr(g, v, i)] = val;
         }
         c.sync();
-        s = tile_fft(s, s2, g, J.pb, J.twb, c);
+        s = tile_fft<1>(s, s2, g, J.pb, J.twb, c);
         for (int e = c.tid; e < all; e += c.nthr) {
-            const int i = e / cnt, v = e - i * cnt;
+            const int i = ms_fastdiv(e, mgc), v = e - i * cnt;
             const int a = tile_addr(g, v, i);
             s[a] = c_swap(c_mul(s[a], __ldg(&J.b1_spec[i])));
         }
         c.sync();
-        cpx* other = (s == (cpx*)c.smem) ? s2 : (cpx*)c.smem;
-        s = tile_fft(s, other, g, J.pb, J.twb, c);
+        cpx* other = (s == sA) ? s2 : sA;
+        s = tile_fft<1>(s, other, g, J.pb, J.twb, c);
         for (int e = c.tid; e < total; e += c.nthr) {
-            const int k1 = e / cnt, v = e - k1 * cnt;
+            const int k1 = ms_fastdiv(e, mgc), v = e - k1 * cnt;
             cpx val = c_mul(c_swap(s[tile_addr(g, v, k1)]), __ldg(&J.b1_chirp[k1]));
             if (TWID) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)k1 * (unsigned)(col0 + v)));
             job_store<ST>(J, k1 * F2 + col0 + v, val);
         }
         return;
     }
+#pragma unroll 4
     for (int e = c.tid; e < total; e += c.nthr) {
-        const int i = e / cnt, v = e - i * cnt;
+        const int i = ms_fastdiv(e, mgc), v = e - i * cnt;
         s[tile_addr(g, v, i)] = job_load<LD>(J, i * F2 + col0 + v);
     }
     c.sync();
-    s = tile_fft(s, s2, g, J.p1, J.tw1, c);
+    s = tile_fft<1>(s, s2, g, J.p1, J.tw1, c);
     for (int e = c.tid; e < total; e += c.nthr) {
-        const int k1 = e / cnt, v = e - k1 * cnt;
+        const int k1 = ms_fastdiv(e, mgc), v = e - k1 * cnt;
         cpx val = s[tile_addr(g, v, k1)];
         if (TWID) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)k1 * (unsigned)(col0 + v)));
         job_store<ST>(J, k1 * F2 + col0 + v, val);
@@ -302,42 +317,46 @@ MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
 // ---- rows kernel -----------------------------------------------------------------------------------
 template <int LD, int MODE, int ST>
 MS_DEV void fft_rows_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
-    const FftJob& J = jobs[c.by];
+    const FftJob& J = stage_job(jobs, c);
     const int G = J.G, F1 = J.F1, F2 = J.F2;
     const int row0 = c.bx * G;
     if (row0 >= F1) return;
     const int cnt = (F1 - row0) < G ? (F1 - row0) : G;
-    cpx* s = (cpx*)c.smem;
+    cpx* s = (cpx*)(c.smem + MS_JOB_SMEM);
+    cpx* const sA = s;
     TileGeom g; g.cnt = cnt; g.vs = (ms_pad(F2) + 1) | 1; g.es = 1; g.colmajor = 0;
     cpx* s2 = s + (G * g.vs + 2);
     const int total = F2 * cnt;
+    const unsigned mgF = J.p2.mg_F, mgc = ms_magic_dev(cnt);
+#pragma unroll 4
     for (int e = c.tid; e < total; e += c.nthr) {
-        const int r = e / F2, i = e - r * F2;
+        const int r = ms_fastdiv(e, mgF), i = e - r * F2;
         s[tile_addr(g, r, i)] = job_load<LD>(J, (row0 + r) * F2 + i);
     }
     c.sync();
-    s = tile_fft(s, s2, g, J.p2, J.tw2, c);
+    s = tile_fft<0>(s, s2, g, J.p2, J.tw2, c);
     if (MODE == MODE_NAT) {
         for (int e = c.tid; e < total; e += c.nthr) {
-            const int k2 = e / cnt, r = e - k2 * cnt;
+            const int k2 = ms_fastdiv(e, mgc), r = e - k2 * cnt;
             job_store<ST>(J, (row0 + r) + F1 * k2, s[tile_addr(g, r, k2)]);
         }
     } else if (MODE == MODE_RAW) {
         for (int e = c.tid; e < total; e += c.nthr) {
-            const int r = e / F2, i = e - r * F2;
+            const int r = ms_fastdiv(e, mgF), i = e - r * F2;
             job_store<ST>(J, (row0 + r) * F2 + i, s[tile_addr(g, r, i)]);
         }
     } else {   // MODE_CONV
+#pragma unroll 4
         for (int e = c.tid; e < total; e += c.nthr) {
-            const int r = e / F2, i = e - r * F2;
+            const int r = ms_fastdiv(e, mgF), i = e - r * F2;
             const int a = tile_addr(g, r, i);
             s[a] = c_swap(c_mul(s[a], __ldg(&J.bspec[(row0 + r) * F2 + i])));
         }
         c.sync();
-        cpx* other = (s == (cpx*)c.smem) ? s2 : (cpx*)c.smem;
-        s = tile_fft(s, other, g, J.p2, J.tw2, c);
+        cpx* other = (s == sA) ? s2 : sA;
+        s = tile_fft<0>(s, other, g, J.p2, J.tw2, c);
         for (int e = c.tid; e < total; e += c.nthr) {
-            const int r = e / F2, i = e - r * F2;
+            const int r = ms_fastdiv(e, mgF), i = e - r * F2;
             cpx val = s[tile_addr(g, r, i)];
             if (F1 > 1) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)(row0 + r) * (unsigned)i));
             job_store<ST>(J, (row0 + r) * F2 + i, val);

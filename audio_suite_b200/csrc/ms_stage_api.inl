@@ -11,7 +11,10 @@ struct SynthDustK { static constexpr int MAXT = 256;
     static MS_DEV void run(const SynthEvt* e, const int* dp, const real* dv, real* pool, const Ctx& c) { synth_dust_body(e, dp, dv, pool, c); } };
 struct OlaK { static constexpr int MAXT = OLA_NTHR;
     static constexpr int MINB = 1;
-    static MS_DEV void run(const OlaRender* r, const OlaEvt* e, const real* pool, real* mono, const Ctx& c) { ola_adsr_body(r, e, pool, mono, c); } };
+    static MS_DEV void run(const OlaRender* r, const OlaEvt* e, const real* pool, const real* env, real* mono, const Ctx& c) { ola_adsr_body(r, e, pool, env, mono, c); } };
+struct AdsrTableK { static constexpr int MAXT = OLA_NTHR;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const OlaRender* r, real* env, const Ctx& c) { adsr_table_body(r, env, c); } };
 struct ErScatterK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const ErJob* j, const int* to, const real* tg, real* e, const Ctx& c) { er_scatter_body(j, to, tg, e, c); } };
@@ -43,17 +46,22 @@ extern "C" int MS_API(ms_synth_dust)(const ms_synth_evt* evts, int n, const int3
     MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthDustK>(mk_dim(64, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, (const int*)dpos, dval, pool)) return -1; })
     return 0;
 }
-extern "C" int MS_API(ms_overlap_add)(const ms_ola_render* renders, int n_renders, int max_out_n, const ms_ola_evt* evts,
-                              const real* pool, real* mono, void* stream) {
+extern "C" int MS_API(ms_adsr_tables)(const ms_ola_render* reps, int n_tables, int max_out_n, real* envpool, void* stream) {
     const unsigned gx = (unsigned)((max_out_n + OLA_TILE - 1) / OLA_TILE);
-    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<OlaK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream, renders + _y0, evts, pool, mono)) return -1; })
+    MS_FOR_Y_CHUNKS(n_tables, { if (ms_launch<AdsrTableK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream, reps + _y0, envpool)) return -1; })
+    return 0;
+}
+extern "C" int MS_API(ms_overlap_add)(const ms_ola_render* renders, int n_renders, int max_out_n, const ms_ola_evt* evts,
+                              const real* pool, const real* envpool, real* mono, void* stream) {
+    const unsigned gx = (unsigned)((max_out_n + OLA_TILE - 1) / OLA_TILE);
+    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<OlaK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream, renders + _y0, evts, pool, envpool, mono)) return -1; })
     return 0;
 }
 extern "C" int MS_API(ms_post)(const ms_post_render* renders, int n_renders, int max_n, real* mono, uint64_t* maxbits,
                        float* out, void* stream) {
     const unsigned gx = (unsigned)((max_n + OLA_TILE - 1) / OLA_TILE);
     if (ms_memset(maxbits, 0, sizeof(uint64_t) * (size_t)n_renders, (ms_stream_t)stream)) return -1;
-    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, (OLA_TILE + 4 * POST_K + POST_NC + 1 + OLA_NTHR) * sizeof(real), (ms_stream_t)stream,
+    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, (2 * POST_PAR + POST_NC + 1 + OLA_NTHR + OLA_TILE) * sizeof(real), (ms_stream_t)stream,
                                    renders + _y0, mono, (unsigned long long*)maxbits + _y0)) return -1; })
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostWriteK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream,
                                    renders + _y0, (const real*)mono, (const unsigned long long*)maxbits + _y0, (float2*)out)) return -1; })

@@ -117,23 +117,6 @@ MS_DEV int zig_step(int s, unsigned long long prev, unsigned long long cur, cons
     return s == ZS_T2N ? ZS_T1N : ZS_T1P;
 }
 
-// transition map of a run of words: per start state, 16 bits = next state (3) | emitted count (13)
-struct ZigMap { unsigned w[3]; };
-MS_DEV unsigned zm_get(const ZigMap& m, int s) { return (m.w[s >> 1] >> ((s & 1) * 16)) & 0xffffu; }
-MS_DEV void zm_set(ZigMap& m, int s, unsigned v) {
-    const int sh = (s & 1) * 16;
-    m.w[s >> 1] = (m.w[s >> 1] & ~(0xffffu << sh)) | (v << sh);
-}
-// f first, then g
-MS_DEV ZigMap zm_compose(const ZigMap& f, const ZigMap& g) {
-    ZigMap h; h.w[0] = h.w[1] = h.w[2] = 0;
-    for (int s = 0; s < 6; ++s) {
-        const unsigned a = zm_get(f, s), b = zm_get(g, a & 7u);
-        zm_set(h, s, (b & 7u) | (((a >> 3) + (b >> 3)) << 3));
-    }
-    return h;
-}
-
 MS_DEV real fade_gain(int j, int n, int fade, double inv_fade) {
     real w = (real)1.;
     if (j < fade) w *= (real)((double)j * inv_fade);
@@ -148,14 +131,30 @@ struct SynthSmem {
     double wi[256];
     double fi[256];
     unsigned long long words[SY_W + 1];     // [0] = word before the round, then i-major: 1 + i*NTHR + t
-    ZigMap scan[2][SY_NTHR];
     real stage[SY_W + 8];
-    int carry_state, round_total, round_end_state, _pad;
+    int endst[SY_NTHR];                     // state each thread's run ends in
+    int scan[2][SY_NTHR];                   // prefix sums of the per-thread output counts
+    int flag[3];                            // "some thread changed its start state" (rotating, see below)
+    int carry_state, _pad;
 };
 MS_DEV unsigned long long sy_word(const SynthSmem* S, int p) {   // p in [-1, SY_W)
     if (p < 0) return S->words[0];
     const int t = p / SY_C, i = p - t * SY_C;
     return S->words[1 + i * SY_NTHR + t];
+}
+// One thread's run of SY_C consecutive words from state `s`: vals[i] = the normal completed by word i when bit i
+// of *mask is set (static indices: the array stays in registers).  Returns the end state.
+MS_DEV int zig_run(int s, const SynthSmem* S, int p0, const ZigTables& T, double* vals, unsigned* mask) {
+    unsigned m = 0; int em;
+#pragma unroll
+    for (int i = 0; i < SY_C; ++i) {
+        double v = 0.0;
+        s = zig_step(s, sy_word(S, p0 + i - 1), sy_word(S, p0 + i), T, &em, &v);
+        vals[i] = v;
+        m |= (unsigned)em << i;
+    }
+    *mask = m;
+    return s;
 }
 
 // mode-specific sample from normal z at index j
@@ -203,66 +202,54 @@ MS_DEV void synth_normal_body(const SynthEvt* MS_RESTRICT evts, real* MS_RESTRIC
     const int max_rounds = (int)((2ll * E.n) / SY_W) + 64;
     for (int round = 0; round < max_rounds && out_base < E.n; ++round) {
         // ---- generate this thread's words
-        if (c.tid == 0) S->words[0] = pcg_output(st);
+        if (c.tid == 0) { S->words[0] = pcg_output(st); S->flag[0] = 0; }
         for (int i = 0; i < SY_C; ++i) { st = pcg_step(st, inc); S->words[1 + i * SY_NTHR + c.tid] = pcg_output(st); }
         st = u128_add(u128_mul(st, jm), jp);
         c.sync();
-        // ---- transition map of this thread's run
+        // ---- every run is first walked as if it began on a fresh word (true for ~99 % of them: a run inherits a
+        //      pending wedge / tail state only when the previous run ended inside a multi-word draw).  Then the
+        //      end states are published and any thread whose neighbour says otherwise re-walks its run from the
+        //      state it really starts in; repeat until nobody changes (normally one check, rarely two).
         const int p0 = c.tid * SY_C;
-        unsigned mstates = 0, mask = 0;        // main path (start S0): state before word i in bits 3i..3i+2
-        int s = ZS_S0, em; double val;
-        for (int i = 0; i < SY_C; ++i) {
-            mstates |= (unsigned)s << (3 * i);
-            s = zig_step(s, sy_word(S, p0 + i - 1), sy_word(S, p0 + i), T, &em, &val);
-            mask |= (unsigned)em << i;
-        }
-        const int main_end = s;
-        const int main_cnt = MS_POPC(mask);
-        ZigMap mine; mine.w[0] = mine.w[1] = mine.w[2] = 0;
-        zm_set(mine, ZS_S0, (unsigned)main_end | ((unsigned)main_cnt << 3));
-        for (int a = 1; a < 6; ++a) {
-            int t = a, i = 0, cnt = 0;
-            while (i < SY_C && t != (int)((mstates >> (3 * i)) & 7u)) {
-                t = zig_step(t, sy_word(S, p0 + i - 1), sy_word(S, p0 + i), T, &em, &val);
-                cnt += em; ++i;
+        const int first = c.tid == 0 ? S->carry_state : ZS_S0;
+        int start = first;
+        unsigned mask;
+        double vals[SY_C];
+        int end = zig_run(start, S, p0, T, vals, &mask);
+        for (int it = 0;; ++it) {
+            S->endst[c.tid] = end;
+            if (c.tid == 0) S->flag[(it + 1) % 3] = 0;
+            c.sync();
+            const int want = c.tid == 0 ? first : S->endst[c.tid - 1];
+            if (want != start) {
+                start = want;
+                end = zig_run(start, S, p0, T, vals, &mask);
+                S->flag[it % 3] = 1;
             }
-            if (i < SY_C) { cnt += MS_POPC(mask >> i); t = main_end; }
-            zm_set(mine, a, (unsigned)t | ((unsigned)cnt << 3));
+            c.sync();
+            if (!S->flag[it % 3]) break;
         }
-        // ---- inclusive scan of the maps (Hillis-Steele, double buffered)
+        // ---- where each run's normals go: exclusive prefix sum of the counts (Hillis-Steele over the block)
         int cur = 0;
-        S->scan[0][c.tid] = mine;
+        const int cnt = MS_POPC(mask);
+        S->scan[0][c.tid] = cnt;
         c.sync();
         for (int d = 1; d < c.nthr; d <<= 1) {
-            ZigMap v = S->scan[cur][c.tid];
-            if (c.tid >= d) v = zm_compose(S->scan[cur][c.tid - d], v);
+            int v = S->scan[cur][c.tid];
+            if (c.tid >= d) v += S->scan[cur][c.tid - d];
             S->scan[cur ^ 1][c.tid] = v;
             cur ^= 1;
             c.sync();
         }
-        const int carry = S->carry_state;
-        int my_state = carry, my_off = 0;
-        if (c.tid > 0) {
-            const unsigned e = zm_get(S->scan[cur][c.tid - 1], carry);
-            my_state = (int)(e & 7u); my_off = (int)(e >> 3);
-        }
-        if (c.tid == c.nthr - 1) {
-            const unsigned e = zm_get(S->scan[cur][c.tid], carry);
-            S->round_end_state = (int)(e & 7u); S->round_total = (int)(e >> 3);
-        }
-        // ---- emit in stream order
-        s = my_state;
-        for (int i = 0; i < SY_C; ++i) {
-            s = zig_step(s, sy_word(S, p0 + i - 1), sy_word(S, p0 + i), T, &em, &val);
-            if (em) S->stage[my_off++] = (real)val;
-        }
+        const int total = S->scan[cur][c.nthr - 1];
+        int my_off = S->scan[cur][c.tid] - cnt;
+#pragma unroll
+        for (int i = 0; i < SY_C; ++i) if ((mask >> i) & 1u) S->stage[my_off++] = (real)vals[i];
+        if (c.tid == c.nthr - 1) S->carry_state = end;
         c.sync();
-        const int total = S->round_total;
         const int take = (E.n - out_base) < total ? (E.n - out_base) : total;
         for (int i = c.tid; i < take; i += c.nthr) out[out_base + i] = synth_sample(E, out_base + i, S->stage[i]);
         out_base += total;
-        c.sync();
-        if (c.tid == 0) S->carry_state = S->round_end_state;
         c.sync();
     }
 }

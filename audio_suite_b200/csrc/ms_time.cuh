@@ -6,6 +6,8 @@
 #define OLA_NTHR 256
 #define POST_K MS_POST_K          // Bessel taps -K..K of the stereo rotation
 #define POST_NC (2 * POST_K + 1)
+#define POST_HALF (OLA_TILE / 2 + 2 * POST_K + 4)            // samples of one parity in a tile's window (+ quad slack)
+#define POST_PAR (POST_HALF + POST_HALF / 4 + 2)             // ... with the one-in-four skew
 
 // ---- overlap-add ("unfold" placement) + ADSR --------------------------------------------------------
 typedef ms_ola_render OlaRender;
@@ -25,8 +27,16 @@ MS_DEV real adsr_gain(const OlaRender& R, int i) {
 
 // grid = (ceil(max out_n / OLA_TILE), renders), block = OLA_NTHR.  Gather form: every output sample
 // sums the events that cover it, in event order, so no atomics and each output is written once.
+// envelope tables: one per distinct ADSR description that several renders of the batch share
+MS_DEV void adsr_table_body(const OlaRender* MS_RESTRICT reps, real* MS_RESTRICT envpool, const Ctx& c) {
+    const OlaRender R = reps[c.by];
+    const int t0 = c.bx * OLA_TILE;
+    const int t1 = (t0 + OLA_TILE) < R.out_n ? (t0 + OLA_TILE) : R.out_n;
+    for (int i = t0 + c.tid; i < t1; i += c.nthr) envpool[R.env + i] = adsr_gain(R, i);
+}
+
 MS_DEV void ola_adsr_body(const OlaRender* MS_RESTRICT renders, const OlaEvt* MS_RESTRICT evts,
-                          const real* MS_RESTRICT pool, real* MS_RESTRICT mono, const Ctx& c) {
+                          const real* MS_RESTRICT pool, const real* MS_RESTRICT envpool, real* MS_RESTRICT mono, const Ctx& c) {
     const OlaRender R = renders[c.by];
     const int t0 = c.bx * OLA_TILE;
     if (t0 >= R.out_n) return;
@@ -39,14 +49,26 @@ MS_DEV void ola_adsr_body(const OlaRender* MS_RESTRICT renders, const OlaEvt* MS
     while (lo < hi) { const int m = (lo + hi) >> 1; if (evts[m].start > t0 - R.max_len) hi = m; else lo = m + 1; }
     const int ea = lo;
     real* out = mono + R.out;
-    for (int i = t0 + c.tid; i < t1; i += c.nthr) {
-        real acc = (real)0.;
-        for (int e = ea; e < eb; ++e) {
-            const int st = __ldg(&evts[e].start), ln = __ldg(&evts[e].len);
-            const int k = i - st;
-            if (k >= 0 && k < ln) acc += (real)__ldg(&evts[e].amp) * __ldg(&pool[evts[e].grain + k]);
+    // every thread owns OLA_TILE / OLA_NTHR samples (i = t0 + tid + q * nthr) and keeps their sums in registers;
+    // events are the outer loop (one descriptor fetch per event, not per sample) and are added in event order,
+    // so each output sample sees the same sequence of additions as out[start:start+L] += amp * g (main_v2.py:755)
+    real acc[OLA_TILE / OLA_NTHR];
+#pragma unroll
+    for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) acc[q] = (real)0.;
+    for (int e = ea; e < eb; ++e) {
+        const int st = __ldg(&evts[e].start), ln = __ldg(&evts[e].len);
+        const real amp = (real)__ldg(&evts[e].amp);
+        const real* g = pool + evts[e].grain;
+#pragma unroll
+        for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) {
+            const int k = t0 + c.tid + q * OLA_NTHR - st;
+            if (k >= 0 && k < ln) acc[q] += amp * __ldg(&g[k]);
         }
-        out[i] = acc * adsr_gain(R, i);
+    }
+#pragma unroll
+    for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) {
+        const int i = t0 + c.tid + q * OLA_NTHR;
+        if (i < t1) out[i] = acc[q] * (R.env >= 0 ? __ldg(&envpool[R.env + i]) : adsr_gain(R, i));
     }
 }
 
@@ -89,28 +111,53 @@ MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, uns
     if (t0 >= n) return;
     const int t1 = (t0 + OLA_TILE) < n ? (t0 + OLA_TILE) : n;
     const real* y = mono + R.y;
-    real* win = (real*)c.smem;                       // OLA_TILE + 4K
-    real* coef = win + (OLA_TILE + 4 * POST_K);       // POST_NC
+    // shared memory: the tile's input window (1024 + 4K samples, circular) de-interleaved into its even and odd
+    // samples (the Bessel taps sit at even lags, so each parity is a dense 25-tap FIR of its own), every four
+    // samples skewed by one slot so that threads working on quads of outputs hit distinct banks.
+    real* win = (real*)c.smem;                       // 2 * POST_PAR
+    real* coef = win + 2 * POST_PAR;                  // POST_NC (+1)
     real* red = coef + POST_NC + 1;                  // nthr
+    real* res = red + OLA_NTHR;                      // OLA_TILE results, stream order
+    const int len = t1 - t0;
+    real m = (real)0.;
     if (mode == 1) {
-        const int W = (t1 - t0) + 4 * POST_K;
-        const long long w0 = (long long)t0 + R.dr - 2 * POST_K;
-        for (int j = c.tid; j < W; j += c.nthr) win[j] = y[wrap_idx(w0 + j, n)];
+        const int W = len + 4 * POST_K;
+        const int w0 = wrap_idx((long long)t0 + R.dr - 2 * POST_K, n);          // one 64-bit modulo per thread
+        for (int j = c.tid; j < W; j += c.nthr) {
+            const int mm = j >> 1;
+            int idx = w0 + j;
+            if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }                  // second wrap only for n < tile
+            win[(j & 1) * POST_PAR + mm + (mm >> 2)] = y[idx];
+        }
         for (int j = c.tid; j < POST_NC; j += c.nthr) coef[j] = (real)R.coef[j];
         c.sync();
-    }
-    real m = (real)0.;
-    for (int i = t0 + c.tid; i < t1; i += c.nthr) {
-        m = r_max(m, r_abs(y[i]));
-        if (mode == 1) {
-            real acc = (real)0.;
-            const real* w = win + (i - t0);
+        // thread -> parity (warp-uniform) and a quad of consecutive outputs of that parity: 28 loads per 4 outputs
+        for (int u = c.tid; u < OLA_TILE / 4; u += c.nthr) {
+            const int par = u / (OLA_TILE / 8), t = u - par * (OLA_TILE / 8);
+            if (8 * t + par >= len) continue;
+            const real* w = win + par * POST_PAR + 5 * t;     // slot of sample m0 = 4t: 4t + t
+            real a0 = (real)0., a1 = (real)0., a2 = (real)0., a3 = (real)0.;
+            real x0 = w[0], x1 = w[1], x2 = w[2];
 #pragma unroll
-            for (int k = 0; k < POST_NC; ++k) acc += coef[k] * w[2 * k];
-            mono[R.rbuf + i] = acc;
-            m = r_max(m, r_abs(acc));
-        } else if (mode == 2) {
-            m = r_max(m, r_abs(mono[R.rbuf + i]));
+            for (int k = 0; k < POST_NC; ++k) {
+                const real x3 = w[(k + 3) + ((k + 3) >> 2)];
+                const real ck = coef[k];
+                a0 += ck * x0; a1 += ck * x1; a2 += ck * x2; a3 += ck * x3;
+                x0 = x1; x1 = x2; x2 = x3;
+            }
+            const int j0 = 8 * t + par;
+            res[j0] = a0; res[j0 + 2] = a1; res[j0 + 4] = a2; res[j0 + 6] = a3;
+        }
+        c.sync();
+        for (int j = c.tid; j < len; j += c.nthr) {
+            const real r = res[j];
+            mono[R.rbuf + t0 + j] = r;
+            m = r_max(m, r_max(r_abs(r), r_abs(y[t0 + j])));
+        }
+    } else {
+        for (int i = t0 + c.tid; i < t1; i += c.nthr) {
+            m = r_max(m, r_abs(y[i]));
+            if (mode == 2) m = r_max(m, r_abs(mono[R.rbuf + i]));
         }
     }
     red[c.tid] = m;
@@ -141,8 +188,10 @@ MS_DEV void post_write_body(const PostRender* MS_RESTRICT renders, const real* M
     const real top = soft_clip((real)cv.f, drive, inv_t);
     const real scale = top > (real)0. ? (real)R.peak / top : (real)1.0;
     float2* o = out + R.out;
+    const int dlm = R.stereo_mode ? wrap_idx((long long)R.dl, R.n) : 0;          // left channel = roll(y, dl)
     for (int i = t0 + c.tid; i < t1; i += c.nthr) {
-        const real l = R.stereo_mode ? y[wrap_idx((long long)i - R.dl, R.n)] : y[i];
+        int li = i - dlm; if (li < 0) li += R.n;
+        const real l = y[li];
         const real r = R.stereo_mode ? mono[R.rbuf + i] : y[i];
         o[i] = make_float2((float)(soft_clip(l, drive, inv_t) * scale), (float)(soft_clip(r, drive, inv_t) * scale));
     }

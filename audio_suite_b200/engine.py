@@ -206,8 +206,13 @@ class BatchRenderer:
         self.out = dev.empty(2 * t.frames, np.float32)
         self.maxbits = dev.zeros(self.n_renders, np.uint64)
         _mark("alloc")
-        self.d_sy1, self.d_sy2 = dev.upload(t.sy1), dev.upload(t.sy2)
+        # one CTA per event, dispatched in table order: longest events first, so the tail of the launch is short ones
+        sy1 = t.sy1[np.argsort(-t.sy1["n"].astype(np.int64), kind="stable")] if len(t.sy1) > 1 else t.sy1
+        self.d_sy1, self.d_sy2 = dev.upload(sy1), dev.upload(t.sy2)
         self.d_ola_r, self.d_ola_e = dev.upload(t.ola_r), dev.upload(t.ola_e)
+        self.n_env = len(t.env_reps)
+        self.envpool = dev.empty(max(1, t.env_n), real)
+        self.d_env_reps = dev.upload(t.env_reps) if self.n_env else None
         self.d_post = dev.upload(t.post)
         if self.any_dust:
             self.d_dpos, self.d_dval = dev.upload(t.dust_pos), dev.upload(t.dust_val.astype(real))
@@ -253,8 +258,10 @@ class BatchRenderer:
                 mark("tilt_spectral")
             self.grain_stage.run()
             mark("grain_spectral")
+        if self.n_env:
+            _check(dev, lib.ms_adsr_tables(dev.ptr(self.d_env_reps), self.n_env, self.max_out_n, dev.ptr(self.envpool), st))
         _check(dev, lib.ms_overlap_add(dev.ptr(self.d_ola_r), self.n_renders, self.max_out_n, dev.ptr(self.d_ola_e),
-                                       dev.ptr(self.pool), dev.ptr(self.mono), st))
+                                       dev.ptr(self.pool), dev.ptr(self.envpool), dev.ptr(self.mono), st))
         mark("overlap_add")
         if self.n_fir:
             _check(dev, lib.ms_fir_run(self.fir_handle, st))

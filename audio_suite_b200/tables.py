@@ -78,6 +78,8 @@ class Tables:
     sy1: np.ndarray = None
     sy2: np.ndarray = None
     ola_r: np.ndarray = None
+    env_reps: np.ndarray = None     # one OlaRender per shared envelope table (its .env = table offset)
+    env_n: int = 0
     ola_e: np.ndarray = None
     fir: np.ndarray = None
     post: np.ndarray = None
@@ -173,7 +175,7 @@ def pack_chunk(plans) -> Tables:
             e += 1
         ola_r[r] = (mono_n, n, ev_begin, len(ola_e), max_len, a, d_end, sus_end, 1 if (rel > 0 and n > sus_end) else 0,
                     1.0 / a if a > 0 else 0.0, 1.0 / (d_end - a) if d_end > a else 0.0,
-                    1.0 / (n - sus_end - 1) if n - sus_end > 1 else 0.0, S, curve)
+                    1.0 / (n - sus_end - 1) if n - sus_end > 1 else 0.0, S, curve, -1)
         alg["overlap_add"] += n
         # FIR: reflection cloud folded into the impulse response
         has_er = rp.er_offs is not None and rp.er_offs.size > 0
@@ -244,7 +246,20 @@ def pack_chunk(plans) -> Tables:
         out_at[r], out_n[r], y_at[r] = frames, n, y
         frames += n
         alg["post"] += n
+    # envelopes shared by several renders are tabulated once (ms_adsr_tables) instead of one pow() per sample
+    env_fields = ["out_n", "A", "D_end", "sus_end", "has_release", "inv_A", "inv_D", "inv_R", "S", "curve"]
+    seen, env_n = {}, 0
+    for r in range(R):
+        seen.setdefault(tuple(ola_r[r][f].item() for f in env_fields), []).append(r)
+    reps = []
+    for key, members in seen.items():
+        if len(members) >= 2:
+            ola_r["env"][members] = env_n
+            reps.append(ola_r[members[0]].copy())
+            env_n += int(key[0])
+    env_reps = np.array(reps, dtype=ola_r.dtype) if reps else np.zeros(0, dtype=ola_r.dtype)
     t = Tables()
+    t.env_reps, t.env_n = env_reps, env_n
     t.sy1, t.sy2, t.ola_r, t.post, t.fir = sy1, sy2, ola_r, post, fir_arr
     t.ola_e = _recs(_abi.OlaEvt, len(ola_e))
     for i, rec in enumerate(ola_e):
@@ -274,8 +289,8 @@ def merge_chunks(chunks) -> Tables:
     if len(chunks) == 1:
         return chunks[0]
     m = Tables()
-    pool_b = mono_b = frame_b = h_b = tap_b = ir_b = dust_b = olae_b = 0
-    parts = {k: [] for k in ("sy1", "sy2", "ola_r", "ola_e", "fir", "post", "tap_off", "tap_gain", "irs", "dust_pos", "dust_val",
+    pool_b = mono_b = frame_b = h_b = tap_b = ir_b = dust_b = olae_b = env_b = 0
+    parts = {k: [] for k in ("sy1", "sy2", "ola_r", "env_reps", "ola_e", "fir", "post", "tap_off", "tap_gain", "irs", "dust_pos", "dust_val",
                              "odd", "out_at", "out_n", "y_at", "last", "srs")}
     items = {k: [[], [], [], []] for k in ("tilt", "grain", "rot")}
     alg = {}
@@ -285,6 +300,9 @@ def merge_chunks(chunks) -> Tables:
         _shift(c.sy2, ("out", "aux"), pool_b)
         _shift(c.ola_r, ("out",), mono_b)
         _shift(c.ola_r, ("ev_begin", "ev_end"), olae_b)
+        if env_b:
+            c.ola_r["env"] += np.where(c.ola_r["env"] >= 0, env_b, 0)
+            c.env_reps["env"] += env_b
         _shift(c.ola_e, ("grain",), pool_b)
         _shift(c.fir, ("ir",), ir_b)
         _shift(c.fir, ("h",), h_b)
@@ -316,13 +334,14 @@ def merge_chunks(chunks) -> Tables:
         ir_b += c.irs.size
         dust_b += c.dust_pos.size
         olae_b += c.ola_e.size
+        env_b += c.env_n
         m.max_h = max(m.max_h, c.max_h)
         m.max_out_n = max(m.max_out_n, c.max_out_n)
     for k in parts:
         setattr(m, k, np.concatenate(parts[k]))
     for k in items:
         setattr(m, k, tuple(np.concatenate(x) for x in items[k]))
-    m.pool_n, m.mono_n, m.frames, m.h_total, m.alg = pool_b, mono_b, frame_b, h_b, alg
+    m.pool_n, m.mono_n, m.frames, m.h_total, m.alg, m.env_n = pool_b, mono_b, frame_b, h_b, alg, env_b
     return m
 
 

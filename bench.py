@@ -240,7 +240,7 @@ def run_ours(args):
     h2d = d2h = 0
     e2e_ms = []
     host_out = torch.empty(2 * len(mine) * FRAMES_PER_RENDER, dtype=torch.float32).pin_memory()
-    for s in range(1 + args.e2e_steps):
+    for s in range(1 + args.e2e_steps if args.e2e_steps > 0 else 0):
         barrier()
         t0 = time.perf_counter()
         # public API: host parameter dicts in, host float32 audio out; planning (worker processes), table
@@ -252,7 +252,7 @@ def run_ours(args):
         h2d, d2h = engine.render_batch.last_h2d_bytes, host_out.numel() * 4
         if s > 0:
             e2e_ms.append(dt)
-    t = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device=dev.dev)
+    t = torch.tensor([float(np.mean(e2e_ms)) if e2e_ms else float('nan')], dtype=torch.float64, device=dev.dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms_max = float(t.item())

@@ -110,12 +110,17 @@ typedef struct {
     int32_t has_release;
     double inv_A, inv_D, inv_R;
     double S, curve;
+    int64_t env;              /* >= 0: offset in envpool of a precomputed envelope shared by several renders
+                                 (ms_adsr_tables); < 0: evaluate make_adsr in closed form per sample */
 } ms_ola_render;
 typedef struct {
     int64_t grain;            /* pool offset of grain[offset] */
     int32_t start, len;
     double amp;
 } ms_ola_evt;
+/* ms_adsr_tables: make_adsr (main_v2.py:172-195) evaluated once per distinct envelope of the batch (a preset
+ * sweep shares one); dev_reps[i].env is where table i goes, its other fields describe the envelope. */
+/* ms_adsr_tables_f32 / ms_adsr_tables_f64: declared below by MS_DECLARE_API */
 /* ms_overlap_add_f32 / ms_overlap_add_f64: declared below by MS_DECLARE_API */
 
 /* ---- early-reflection cloud + short IR as one FIR (main_v2.py:409-421, 438-445), applied by
@@ -171,8 +176,9 @@ typedef struct {
     int ms_synth_dust##SFX(const ms_synth_evt* dev_evts, int n_evts, const int32_t* dust_pos, const REAL* dust_val, \
     REAL* pool, void* stream); \
     int ms_synth_tilt_finish##SFX(const ms_synth_evt* dev_evts, int n_evts, REAL* pool, void* stream); \
+    int ms_adsr_tables##SFX(const ms_ola_render* dev_reps, int n_tables, int max_out_n, REAL* envpool, void* stream); \
     int ms_overlap_add##SFX(const ms_ola_render* dev_renders, int n_renders, int max_out_n, const ms_ola_evt* dev_evts, \
-    const REAL* pool, REAL* mono, void* stream); \
+    const REAL* pool, const REAL* envpool, REAL* mono, void* stream); \
     size_t ms_fir_workspace_bytes##SFX(const ms_fir_render* host_renders, int n_renders); \
     int ms_fir_create##SFX(const ms_fir_render* host_renders, int n_renders, const REAL* irpool, const int32_t* tap_off, \
     const REAL* tap_gain, const REAL* mono_in, REAL* mono_out, void* workspace, size_t workspace_bytes, void* stream, \
