@@ -75,7 +75,9 @@ _COMMON = {
     "ms_is_cuda_build": (C.c_int, []),
     "ms_launch_count": (C.c_ulonglong, []),
     "ms_h2d_bytes": (C.c_ulonglong, []),
+    "ms_set_launch_hook": (None, [C.c_void_p]),
 }
+LAUNCH_HOOK = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
 # every stage exists as <name>_f32 and <name>_f64 (include/microsound_b200.h, MS_DECLARE_API)
 _STAGES = {
     "ms_spectral_workspace_bytes": (_Z, [_P, _I]),

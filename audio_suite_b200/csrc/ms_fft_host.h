@@ -41,6 +41,14 @@ static inline bool ms_is_smooth(long long n) {
     return n == 1;
 }
 static inline int ms_round32(int x) { return (x + 31) / 32 * 32; }
+// Length of the circular convolution that carries a Bluestein transform.  Any 2-3-5-smooth M >= need would do,
+// but measured on B200 (C5 sweep, f64) smooth lengths lose to the next power of two even at equal pass count
+// (270 in five passes: grain stage 17.1 -> 22.5 ms; 320 = 8*8*5 in three: 22.7 ms): radix-8 passes over 2^k tiles
+// are the cheapest per element here.  So: the next power of two.
+static inline int ms_conv_len(int need) {
+    int p2 = 1; while (p2 < need) p2 <<= 1;
+    return p2;
+}
 
 struct LaunchShape { int ept, nthr; size_t smem; unsigned gx; };
 
@@ -151,7 +159,7 @@ private:
             if (n % f2 || !ms_is_smooth(f2)) continue;
             const int f1 = n / f2;
             if (f1 < 2 || ms_is_smooth(f1)) continue;
-            int b1 = 1; while (b1 < 2 * f1 - 1) b1 <<= 1;
+            const int b1 = ms_conv_len(2 * f1 - 1);
             if (b1 * 4 > MS_TILE_MAX) continue;
             const int T = std::max(1, std::min(16, tile_target / b1)), G = std::max(1, std::min(16, tile_target / f2));
             double lg2 = 0, lgb = 0;
@@ -162,7 +170,7 @@ private:
         }
         if (!best) return false;
         J.M = n; J.F2 = best; J.F1 = n / best;
-        int b1 = 1; while (b1 < 2 * J.F1 - 1) b1 <<= 1;
+        const int b1 = ms_conv_len(2 * J.F1 - 1);
         J.B1 = b1;
         J.T = std::max(1, std::min(16, tile_target / b1));
         J.G = std::max(1, std::min(16, tile_target / J.F2));
@@ -173,7 +181,7 @@ private:
         while (M < need) { M <<= 1; ++lg; }
         if (M > (1ll << 22)) return false;
         J.M = (int)M;
-        if (M <= MS_SMALL_MAX) { J.F1 = 1; J.F2 = (int)M; J.T = 1; J.G = 1; return true; }
+        if (M <= MS_SMALL_MAX) { J.M = ms_conv_len((int)need); J.F1 = 1; J.F2 = J.M; J.T = 1; J.G = 1; return true; }
         int l1 = std::min(lg / 2, 9);
         J.F1 = 1 << l1; J.F2 = (int)(M >> l1);
         if (J.F2 > MS_TILE_MAX) return false;

@@ -17,6 +17,10 @@ std::string& ms_err_slot();
 unsigned long long& ms_launch_counter();
 // bytes of job tables this library has copied host->device itself (C-ABI: ms_h2d_bytes)
 unsigned long long& ms_h2d_counter();
+// optional observer called after every kernel launch with the kernel's type name and the stream (C-ABI:
+// ms_set_launch_hook; bench.py records a CUDA event there to time individual kernels inside a step)
+typedef void (*ms_launch_hook_t)(const char* kernel, void* stream);
+ms_launch_hook_t& ms_launch_hook();
 #define MS_FAIL(...) do { char _b[512]; snprintf(_b, sizeof _b, __VA_ARGS__); ms_err_slot() = _b; return -1; } while (0)
 
 #ifdef MS_HOST_EMUL
@@ -30,6 +34,7 @@ template <class K, class... Args>
 int ms_launch(MsDim grid, int block, size_t smem, ms_stream_t, Args... args) {
     msemu::run(grid, block, smem, [&](const Ctx& c) { K::run(args..., c); });
     ++ms_launch_counter();
+    if (ms_launch_hook()) ms_launch_hook()(__PRETTY_FUNCTION__, nullptr);
     return 0;
 }
 static inline void* ms_dev_alloc(size_t bytes) { return calloc(1, bytes ? bytes : 1); }
@@ -59,6 +64,7 @@ int ms_launch(MsDim grid, int block, size_t smem, ms_stream_t st, Args... args) 
     ms_kernel<K, Args...><<<dim3(grid.x, grid.y, 1), block, smem, st>>>(args...);
     ++ms_launch_counter();
     MS_CUDA_OK(cudaGetLastError());
+    if (ms_launch_hook()) ms_launch_hook()(__PRETTY_FUNCTION__, (void*)st);
     return 0;
 }
 static inline void* ms_dev_alloc(size_t bytes) { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr; return p; }

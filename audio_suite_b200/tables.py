@@ -425,7 +425,8 @@ class _WorkerPool:
             cores = sorted(os.sched_getaffinity(0))
             spare = int(os.environ.get("MS_PLAN_SPARE_CORES", "2")) if len(cores) >= 8 else 0
             usable = cores[spare:] or cores
-            if os.environ.get("MS_PLAN_PIN", "1") != "0":
+            # (pinning only helps when this process owns the box; ranks of a torchrun job share it unpinned)
+            if os.environ.get("MS_PLAN_PIN", "0") == "1":
                 for i, p in enumerate(self.procs):
                     os.sched_setaffinity(p.pid, {usable[i % len(usable)]})
         except Exception:
@@ -526,9 +527,16 @@ def _pool(workers):
 
 
 def default_workers():
+    """Planning worker processes per rank: the cores this process may run on, shared between the ranks of the box
+    (torchrun sets LOCAL_WORLD_SIZE), minus two per rank for the parent (kernel launches, uploads, copy stream)."""
     import os
+    forced = int(os.environ.get("MS_PLAN_WORKERS", "0"))
+    if forced:
+        return forced
     cores = len(os.sched_getaffinity(0))
-    return int(os.environ.get("MS_PLAN_WORKERS", "0")) or min(32, max(1, cores - 2 if cores >= 8 else cores))
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    share = cores // ranks
+    return min(32, max(1, share - 2 if share >= 8 else share - 1 if share >= 3 else share))
 
 
 def plan_stream(params_list, chunk, workers=None, piece=32):

@@ -236,6 +236,41 @@ def run_ours(args):
         for name, a, b in zip(stage_names, evs[:-1], evs[1:]):
             stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / args.steps
 
+    # ---- individual kernels of one step: the library calls a hook after every launch, a CUDA event is recorded
+    #      there (on the launching stream), consecutive events bracket one kernel.  Separate untimed steps, so
+    #      the headline timing above carries no hook overhead.
+    kernel_ms = {}
+    if rank == 0:
+        import re
+        from audio_suite_b200 import _abi
+        rec = []
+
+        def _hook(name, stream):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            rec.append((name.decode(), ev))
+        cb = _abi.LAUNCH_HOOK(_hook)
+        import ctypes
+        reps = max(1, min(3, args.steps))
+        order = []
+        for s in range(reps):
+            rec.clear()
+            first = torch.cuda.Event(enable_timing=True)
+            first.record()
+            dev.lib.ms_set_launch_hook(ctypes.cast(cb, ctypes.c_void_p))
+            br.run()
+            dev.lib.ms_set_launch_hook(None)
+            torch.cuda.synchronize()
+            prev = first
+            for i, (name, ev) in enumerate(rec):
+                m = re.search(r"K = (?:ms[fd]::)?([^;\]]+)", name)
+                key = "%02d %s" % (i, m.group(1).strip() if m else name[-40:])
+                if s == 0:
+                    order.append(key)
+                kernel_ms[key] = kernel_ms.get(key, 0.0) + prev.elapsed_time(ev) / reps
+                prev = ev
+        kernel_ms = {k: round(kernel_ms[k], 4) for k in order}
+
     # ---- end to end through the public API: host dicts -> host float32 audio
     h2d = d2h = 0
     e2e_ms = []
@@ -290,7 +325,8 @@ def run_ours(args):
                              "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
                              "note": "stage = consecutive launches of one pipeline stage, CUDA events on the launch stream; "
                                      "see profiles/ for the per-kernel ncu launch list"},
-                "stages": stages}
+                "stages": stages,
+                "kernels_ms": kernel_ms}
         if world == 1 and args.cpu_sample > 0:
             idx = list(range(args.cpu_sample))
             v = cpu_pool_throughput(idx, 1)

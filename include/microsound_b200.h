@@ -31,6 +31,9 @@ int ms_is_cuda_build(void);
 unsigned long long ms_launch_count(void);
 /* bytes of job descriptors the library itself has copied host->device since it was loaded. */
 unsigned long long ms_h2d_bytes(void);
+/* observer called after every kernel launch with the kernel's type name and its stream (NULL: off).  bench.py
+ * records a CUDA event there to time the individual kernels of a step; the product never sets it. */
+void ms_set_launch_hook(void (*hook)(const char* kernel, void* stream));
 
 /* ---- spectral stage: lowpass_fft (main_v2.py:39-59), fft_partial_stretch (:117-128),
  *      unfold_multiband / bandpass_fft (:492-500, :61-101), tilted_noise shaping (:224-233),

@@ -157,10 +157,11 @@ def test_full_size_properties_c5_slab(cuda_dev):
     br.close()
 
 
-def test_full_size_c4_properties(cuda_dev):
-    """The real C4 (600 s, 57.6 M frames, 1222 events): linearity of the pipeline before the clip is
-    checked through the peak normalisation, finiteness, and agreement of a 10 s window re-rendered
-    alone up to the first event that differs (event list is a prefix)."""
+def test_full_size_c4_against_the_reference(cuda_dev):
+    """The real C4 (600 s, 57.6 M frames, 1222 events of 300000 samples, x2.5 stretch, reflection cloud, 8192-tap
+    IR, stereo) against tests/golden/c4_full.npz, which oracle/make_golden_c4.py wrote from the UNMODIFIED
+    reference in the build container (one core, about four minutes): every 997th frame, three 4096-frame
+    windows, the channel sums and the peak."""
     p = configs.canonical("C4")
     br = engine.BatchRenderer([p], device=cuda_dev)
     assert len(br.plans[0].events) == 1222 and br.plans[0].out_n == 57_600_000
@@ -168,4 +169,20 @@ def test_full_size_c4_properties(cuda_dev):
     out = br.outputs_device().view(-1, 2)
     assert bool(out.isfinite().all())
     assert abs(float(out.abs().max()) - 0.98) < 1e-5
+    path = os.path.join(GOLDEN, "c4_full.npz")
+    g = np.load(path)
+    step = int(g["step"])
+    dec = out[::step].cpu().numpy().astype(np.float64)
+    assert dec.shape == g["decimated_f64"].shape
+    err = float(np.max(np.abs(dec - g["decimated_f64"])))
+    rms_db = 20 * np.log10(max(1e-30, float(np.sqrt(np.mean((dec - g["decimated_f64"]) ** 2)))))
+    assert err < K.MAX_ABS_TOL and rms_db < K.RMS_DB_TOL, (err, rms_db)
+    for k in range(3):
+        a = int(g["win%d_at" % k])
+        w = out[a:a + g["win%d" % k].shape[0]].cpu().numpy().astype(np.float64)
+        assert float(np.max(np.abs(w - g["win%d" % k]))) < K.MAX_ABS_TOL, k
+    sums = out.sum(dim=0, dtype=cuda_dev.torch.float64).cpu().numpy()
+    assert np.all(np.abs(sums - g["sums"]) < 1e-5 * 57_600_000 ** 0.5 * 4)          # random-walk bound on 57.6 M float32 roundings
+    meta = br.meta(0)
+    assert meta["design_sr_base"] == int(g["design_sr_base"]) == 30_000_000
     br.close()
