@@ -18,8 +18,11 @@ struct AdsrTableK { static constexpr int MAXT = OLA_NTHR;
 struct ErScatterK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const ErJob* j, const int* to, const real* tg, real* e, const Ctx& c) { er_scatter_body(j, to, tg, e, c); } };
+#ifndef MS_POSTMAX_MINB
+#define MS_POSTMAX_MINB 6          // <= 42 registers: six 256-thread CTAs per SM (measured 3.7 -> 3.0 ms on the C5 sweep)
+#endif
 struct PostMaxK { static constexpr int MAXT = OLA_NTHR;
-    static constexpr int MINB = 1;
+    static constexpr int MINB = MS_POSTMAX_MINB;
     static MS_DEV void run(const PostRender* r, real* mono, unsigned long long* mb, const Ctx& c) { post_max_body(r, mono, mb, c); } };
 struct PostWriteK { static constexpr int MAXT = OLA_NTHR;
     static constexpr int MINB = 1;
@@ -43,7 +46,7 @@ extern "C" int MS_API(ms_synth_tilt_finish)(const ms_synth_evt* evts, int n, rea
     return 0;
 }
 extern "C" int MS_API(ms_synth_dust)(const ms_synth_evt* evts, int n, const int32_t* dpos, const real* dval, real* pool, void* stream) {
-    MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthDustK>(mk_dim(64, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, (const int*)dpos, dval, pool)) return -1; })
+    MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthDustK>(mk_dim(64, (unsigned)_yc), 256, DUST_KER_MAX * sizeof(real), (ms_stream_t)stream, evts + _y0, (const int*)dpos, dval, pool)) return -1; })
     return 0;
 }
 extern "C" int MS_API(ms_adsr_tables)(const ms_ola_render* reps, int n_tables, int max_out_n, real* envpool, void* stream) {

@@ -272,7 +272,10 @@ MS_DEV void synth_tilt_finish_body(const SynthEvt* MS_RESTRICT evts, real* MS_RE
     }
 }
 
-// Dust impulses (main_v2.py:239-245): sparse impulses convolved ("same") with exp(-linspace(0,6,K)).
+// Dust impulses (main_v2.py:239-245): sparse impulses convolved ("same") with ker = exp(-linspace(0,6,K)).
+// ker is tabulated once per CTA in shared memory (K <= 0.01 n entries), so an output costs one table lookup
+// per impulse in reach instead of one exp().  Events longer than the table fall back to exp().
+#define DUST_KER_MAX 4096
 MS_DEV void synth_dust_body(const SynthEvt* MS_RESTRICT evts, const int* MS_RESTRICT dpos, const real* MS_RESTRICT dval,
                             real* MS_RESTRICT pool, const Ctx& c) {
     const SynthEvt E = evts[c.by];
@@ -282,6 +285,12 @@ MS_DEV void synth_dust_body(const SynthEvt* MS_RESTRICT evts, const int* MS_REST
     real* out = pool + E.out;
     const int K = E.ker_len, ctr = (K - 1) / 2;
     const real rate = (real)6.0 / (real)(K - 1);
+    real* ker = (real*)c.smem;
+    const int tab = K <= DUST_KER_MAX;
+    if (tab) {
+        for (int d = c.tid; d < K; d += c.nthr) ker[d] = r_exp(-rate * (real)d);
+        c.sync();
+    }
     for (int j = c.bx * c.nthr + c.tid; j < E.n; j += c.nthr * 64) {
         const int hi = j + ctr;            // impulses p with hi-K < p <= hi contribute ker[hi-p]
         int lo_i = 0, hi_i = E.dust_count; // first index with pos > hi - K
@@ -290,7 +299,7 @@ MS_DEV void synth_dust_body(const SynthEvt* MS_RESTRICT evts, const int* MS_REST
         for (int q = lo_i; q < E.dust_count; ++q) {
             const int p = __ldg(&pos[q]);
             if (p > hi) break;
-            acc += __ldg(&val[q]) * r_exp(-rate * (real)(hi - p));
+            acc += __ldg(&val[q]) * (tab ? ker[hi - p] : r_exp(-rate * (real)(hi - p)));
         }
         out[j] = acc * fade_gain(j, E.n, E.fade, E.inv_fade);
     }

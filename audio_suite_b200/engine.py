@@ -208,7 +208,14 @@ class BatchRenderer:
         _mark("alloc")
         # one CTA per event, dispatched in table order: longest events first, so the tail of the launch is short ones
         sy1 = t.sy1[np.argsort(-t.sy1["n"].astype(np.int64), kind="stable")] if len(t.sy1) > 1 else t.sy1
-        self.d_sy1, self.d_sy2 = dev.upload(sy1), dev.upload(t.sy2)
+        # dust / tilted-noise kernels launch 64 CTAs per table entry: hand them compact tables of just their events
+        dust = sy1[sy1["mode"] == P.MODE_DUST]
+        tilt = t.sy2[(t.sy2["mode"] == P.MODE_NOISE) | (t.sy2["mode"] == P.MODE_SKEW)]
+        self.n_dust_evt, self.n_tilt_evt = len(dust), len(tilt)
+        self.d_sy1 = dev.upload(sy1[sy1["mode"] != P.MODE_DUST]) if self.n_dust_evt < len(sy1) else None
+        self.n_normal_evt = len(sy1) - self.n_dust_evt
+        self.d_sy_dust = dev.upload(dust) if self.n_dust_evt else None
+        self.d_sy_tilt = dev.upload(tilt) if self.n_tilt_evt else None
         self.d_ola_r, self.d_ola_e = dev.upload(t.ola_r), dev.upload(t.ola_e)
         self.n_env = len(t.env_reps)
         self.envpool = dev.empty(max(1, t.env_n), real)
@@ -247,14 +254,15 @@ class BatchRenderer:
         st = dev.stream_ptr()
         mark = mark or (lambda name: None)
         if self.n_evt:
-            _check(dev, lib.ms_synth_normal(dev.ptr(self.d_sy1), self.n_evt, dev.ptr(self.pool), st))
-            if self.any_dust:
-                _check(dev, lib.ms_synth_dust(dev.ptr(self.d_sy1), self.n_evt, dev.ptr(self.d_dpos), dev.ptr(self.d_dval),
+            if self.n_normal_evt:
+                _check(dev, lib.ms_synth_normal(dev.ptr(self.d_sy1), self.n_normal_evt, dev.ptr(self.pool), st))
+            if self.n_dust_evt:
+                _check(dev, lib.ms_synth_dust(dev.ptr(self.d_sy_dust), self.n_dust_evt, dev.ptr(self.d_dpos), dev.ptr(self.d_dval),
                                               dev.ptr(self.pool), st))
             mark("synth")
             if self.any_tilt:
                 self.tilt_stage.run()
-                _check(dev, lib.ms_synth_tilt_finish(dev.ptr(self.d_sy2), self.n_evt, dev.ptr(self.pool), st))
+                _check(dev, lib.ms_synth_tilt_finish(dev.ptr(self.d_sy_tilt), self.n_tilt_evt, dev.ptr(self.pool), st))
                 mark("tilt_spectral")
             self.grain_stage.run()
             mark("grain_spectral")
