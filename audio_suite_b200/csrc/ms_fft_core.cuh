@@ -204,3 +204,77 @@ MS_DEV cpx* tile_fft(cpx* a, cpx* b, const TileGeom& g, const RadixPlan& p, cons
     }
     return a;
 }
+
+// (The generic passes stay ping-pong: run in place, a thread must hold ALL its butterflies of a pass in registers at
+//  once -- 8..10 double-complex values for the radix 4/5/3/2 passes -- and at the 64-register budget that spills:
+//  measured grain stage 17.2 -> 20.8 ms.  The static 256-point tiles are radix 8 (+ one radix-4 pass) and gain.)
+// ---- in-place pass (static 256 x 256 tiles) ---------------------------------------------------------
+// In place: every thread pulls the inputs of its (at most BPT) butterflies into registers and transforms them, the
+// CTA synchronises, then the results go back into the SAME buffer at the autosort positions.  Two barriers per
+// pass, ONE tile buffer: half the shared memory of a ping-pong Stockham, i.e. more CTAs per SM, which is what these
+// latency-bound passes need (measured on the FIR stage: 19.2 -> 15.3 ms).  tw = table of w_F^i (i < F), forward
+// sign.  Integer divisions by the per-pass constants go through host-computed magic multipliers.
+template <int R, int CM, int BPT>
+MS_DEV void stockham_pass_ip(cpx* MS_RESTRICT buf, const TileGeom& g, int per_vec, int Ns, int tws,
+                             unsigned mg_ns, unsigned mg_pv, unsigned mg_cnt, const cpx* MS_RESTRICT tw, const Ctx& c) {
+    const int nb = per_vec * g.cnt;
+    cpx v[BPT][R];
+    int at[BPT], vecs[BPT];
+#pragma unroll
+    for (int u = 0; u < BPT; ++u) {
+        const int b = c.tid + u * c.nthr;
+        vecs[u] = -1;
+        if (b < nb) {
+            int vec, j;
+            if (CM) { j = ms_fastdiv(b, mg_cnt); vec = b - j * g.cnt; } else { vec = ms_fastdiv(b, mg_pv); j = b - vec * per_vec; }
+            const int k = j - ms_fastdiv(j, mg_ns) * Ns;
+#pragma unroll
+            for (int q = 0; q < R; ++q) v[u][q] = buf[tile_addr(g, vec, j + q * per_vec)];
+            if (k != 0) {
+                // powers of w = w_F^(k*tws): load w, w^2, w^4 (each rounded once), multiply the rest
+                const cpx w1 = __ldg(&tw[k * tws]);
+                if (R == 2) { v[u][1] = c_mul(v[u][1], w1); }
+                else {
+                    const cpx w2 = __ldg(&tw[2 * k * tws]);
+                    if (R == 3) { v[u][1] = c_mul(v[u][1], w1); v[u][2] = c_mul(v[u][2], w2); }
+                    else {
+                        const cpx w3 = c_mul(w1, w2);
+                        v[u][1] = c_mul(v[u][1], w1); v[u][2] = c_mul(v[u][2], w2); v[u][3] = c_mul(v[u][3], w3);
+                        if (R > 4) {
+                            const cpx w4 = __ldg(&tw[4 * k * tws]);
+                            v[u][4 % R] = c_mul(v[u][4 % R], w4);
+                            if (R == 8) {
+                                v[u][5 % R] = c_mul(v[u][5 % R], c_mul(w4, w1)); v[u][6 % R] = c_mul(v[u][6 % R], c_mul(w4, w2));
+                                v[u][7 % R] = c_mul(v[u][7 % R], c_mul(w4, w3));
+                            }
+                        }
+                    }
+                }
+            }
+            Bfly<R>::run(v[u]);
+            at[u] = (j - k) * R + k; vecs[u] = vec;
+        }
+    }
+    c.sync();
+#pragma unroll
+    for (int u = 0; u < BPT; ++u) {
+        if (vecs[u] >= 0) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) buf[tile_addr(g, vecs[u], at[u] + q * Ns)] = v[u][q];
+        }
+    }
+    c.sync();
+}
+// Static 256-point transform (radices 8, 8, 4) with literal geometry, so the magic divisions, strides and padded
+// addresses fold into immediates.  Used by the 256 x 256 (65536-point) transforms of the FIR stage, whose tiles are
+// always full: CNT vectors, CNT * 32 threads.
+template <unsigned D> struct MsMagic { static constexpr unsigned v = D <= 1 ? 0u : (unsigned)(0x100000000ull / (D ? D : 1)) + 1u; };
+#define ms_magic_c(D) (MsMagic<(D)>::v)
+template <int CM, int CNT>
+MS_DEV cpx* tile_fft_256(cpx* a, const TileGeom& g, const cpx* MS_RESTRICT tw, const Ctx& c) {
+    constexpr unsigned mc = ms_magic_c(CNT);
+    stockham_pass_ip<8, CM, 1>(a, g, 32, 1, 32, ms_magic_c(1), ms_magic_c(32), mc, tw, c);
+    stockham_pass_ip<8, CM, 1>(a, g, 32, 8, 4, ms_magic_c(8), ms_magic_c(32), mc, tw, c);
+    stockham_pass_ip<4, CM, 2>(a, g, 64, 64, 1, ms_magic_c(64), ms_magic_c(64), mc, tw, c);
+    return a;
+}

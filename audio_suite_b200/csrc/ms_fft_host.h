@@ -10,16 +10,21 @@ static const int MS_TILE_MAX = sizeof(real) == 4 ? 8192 : 4096;
 #ifndef MS_FFT_MINB
 #define MS_FFT_MINB 2
 #endif
-template <int LD, int ST, int TWID> struct ColsK {
-    static constexpr int MAXT = 512;
-    static constexpr int MINB = MS_FFT_MINB;        // 2: <= 64 registers, three 256..320-thread CTAs per SM
-    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_body<LD, ST, TWID>(jobs, c); }
+#ifndef MS_SQ_MINB
+#define MS_SQ_MINB 5
+#endif
+template <int LD, int ST, int TWID, int SQ = 0> struct ColsK {
+    static constexpr int MAXT = (SQ && sizeof(real) == 8) ? 256 : 512;      // static f64 tiles: 2048 elements, 256 threads
+    static constexpr int MINB = (SQ && sizeof(real) == 8) ? MS_SQ_MINB : MS_FFT_MINB;        // 2 x 512: <= 64 registers, three 256..320-thread CTAs per SM
+    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_body<LD, ST, TWID, SQ>(jobs, c); }
 };
-template <int LD, int MODE, int ST> struct RowsK {
-    static constexpr int MAXT = 512;
-    static constexpr int MINB = MS_FFT_MINB;
-    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_rows_body<LD, MODE, ST>(jobs, c); }
+template <int LD, int MODE, int ST, int SQ = 0> struct RowsK {
+    static constexpr int MAXT = (SQ && sizeof(real) == 8) ? 256 : 512;
+    static constexpr int MINB = (SQ && sizeof(real) == 8) ? MS_SQ_MINB : MS_FFT_MINB;
+    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_rows_body<LD, MODE, ST, SQ>(jobs, c); }
 };
+// tile width of the static 256 x 256 kernels: what plan_direct picks for 65536 points in this precision
+static const int MS_SQ = (sizeof(real) == 4 ? 8192 : 4096) / 2 / 256;
 struct GenChirpK {
     static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
@@ -259,13 +264,26 @@ private:
         return 0;
     }
 
-    template <int LD, int ST, int TWID>
+    template <int LD, int ST, int TWID, int SQ = 0>
     static int launch_cols(int ept, unsigned gx, unsigned gy, int nthr, size_t smem, ms_stream_t st, const FftJob* jd) {
-        return L<ColsK<LD, ST, TWID>>(gx, gy, nthr, smem, st, jd);
+        return L<ColsK<LD, ST, TWID, SQ>>(gx, gy, nthr, smem, st, jd);
     }
-    template <int LD, int MODE, int ST>
+    template <int LD, int MODE, int ST, int SQ = 0>
     static int launch_rows(int ept, unsigned gx, unsigned gy, int nthr, size_t smem, ms_stream_t st, const FftJob* jd) {
-        return L<RowsK<LD, MODE, ST>>(gx, gy, nthr, smem, st, jd);
+        return L<RowsK<LD, MODE, ST, SQ>>(gx, gy, nthr, smem, st, jd);
+    }
+    // shared memory of the static kernels: the job + ONE tile (the static passes run in place)
+    static size_t sq_smem(bool cols) {
+        FftJob t; t.T = t.G = MS_SQ; t.F1 = t.F2 = 256; t.B1 = 0;
+        return MS_JOB_SMEM + ((cols ? cols_smem(t) : rows_smem(t)) - MS_JOB_SMEM) / 2;
+    }
+    // every job of [b, e) is a plain 256 x 256 transform with the static tile width: the FIR stage's 65536-point blocks
+    static bool all_square(const std::vector<FftJob>& jobs, size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            const FftJob& J = jobs[i];
+            if (J.F1 != 256 || J.F2 != 256 || J.T != MS_SQ || J.G != MS_SQ || J.B1 || J.ch_hi) return false;
+        }
+        return e > b;
     }
 
     struct ClassShape { LaunchShape cols, rows; };
@@ -309,12 +327,21 @@ private:
                 else if (cls == 1) {
                     // (summing the few non-zero input rows of the tap vector directly in the rows kernel, instead of
                     //  the columns pass, was measured SLOWER on B200: 7.8 ms vs 2.95 + 3.79 ms for the C5 sweep)
+                    if (all_square(jobs, b, e)) {
+                        rc = launch_cols<LD_REALPAD, ST_WORK, 1, MS_SQ>(C.ept, C.gx, gy, C.nthr, sq_smem(true), st, jd);
+                        if (!rc) rc = launch_rows<LD_WORK, MODE_RAW, ST_HMUL, MS_SQ>(R.ept, R.gx, gy, R.nthr, sq_smem(false), st, jd);
+                    } else {
                     rc = launch_cols<LD_REALPAD, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
                     if (!rc) rc = launch_rows<LD_WORK, MODE_RAW, ST_HMUL>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                    }
                 } else MS_FAIL("filter spectrum needs a direct length");
             } else if (what == 4) {
                 if (cls == 0) rc = launch_rows<LD_OLS, MODE_CONV, ST_OLS>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
-                else if (cls == 1) {
+                else if (cls == 1 && all_square(jobs, b, e)) {
+                    rc = launch_cols<LD_OLS, ST_WORK, 1, MS_SQ>(C.ept, C.gx, gy, C.nthr, sq_smem(true), st, jd);
+                    if (!rc) rc = launch_rows<LD_WORK, MODE_CONV, ST_WORK, MS_SQ>(R.ept, R.gx, gy, R.nthr, sq_smem(false), st, jd);
+                    if (!rc) rc = launch_cols<LD_WORK, ST_OLS, 0, MS_SQ>(C.ept, C.gx, gy, C.nthr, sq_smem(true), st, jd);
+                } else if (cls == 1) {
                     rc = launch_cols<LD_OLS, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
                     if (!rc) rc = launch_rows<LD_WORK, MODE_CONV, ST_WORK>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
                     if (!rc) rc = launch_cols<LD_WORK, ST_OLS, 0>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);

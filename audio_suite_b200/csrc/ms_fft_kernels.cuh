@@ -257,21 +257,22 @@ MS_DEV const FftJob& stage_job(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
 }
 
 // ---- columns kernel --------------------------------------------------------------------------------
-template <int LD, int ST, int TWID>
+// SQ != 0: static geometry F1 = F2 = 256, T = G = SQ, plain mixed radix (the 65536-point transforms of the FIR stage)
+template <int LD, int ST, int TWID, int SQ>
 MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
     const FftJob& J = stage_job(jobs, c);
-    const int T = J.T, F1 = J.F1, F2 = J.F2;
+    const int T = SQ ? SQ : J.T, F1 = SQ ? 256 : J.F1, F2 = SQ ? 256 : J.F2;
     const int col0 = c.bx * T;
     if (col0 >= F2) return;
-    const int cnt = (F2 - col0) < T ? (F2 - col0) : T;
-    const int rows = J.B1 ? J.B1 : F1;           // vector length held in the tile
+    const int cnt = SQ ? SQ : ((F2 - col0) < T ? (F2 - col0) : T);
+    const int rows = SQ ? 256 : (J.B1 ? J.B1 : F1);           // vector length held in the tile
     cpx* s = (cpx*)(c.smem + MS_JOB_SMEM);
     cpx* const sA = s;
-    cpx* s2 = s + (ms_pad((rows - 1) * T + T - 1) + 2);
+    cpx* s2 = s + (ms_pad((rows - 1) * T + T - 1) + 2);       // (unused by the static in-place tiles)
     TileGeom g; g.cnt = cnt; g.vs = 1; g.es = T; g.colmajor = 1;
     const int total = F1 * cnt;
-    const unsigned mgc = ms_magic_dev(cnt);
-    if (J.B1) {
+    const unsigned mgc = SQ ? ms_magic_c(SQ ? SQ : 1) : ms_magic_dev(cnt);
+    if (!SQ && J.B1) {
         // length-F1 DFT of every column as chirp * IFFT_B1(FFT_B1(x * chirp) * spec)
         const int all = rows * cnt;
 #pragma unroll 2
@@ -305,7 +306,8 @@ MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
         s[tile_addr(g, v, i)] = job_load<LD>(J, i * F2 + col0 + v);
     }
     c.sync();
-    s = tile_fft<1>(s, s2, g, J.p1, J.tw1, c);
+    s = SQ ? tile_fft_256<1, SQ ? SQ : 1>(s, g, J.tw1, c) : tile_fft<1>(s, s2, g, J.p1, J.tw1, c);
+#pragma unroll 4
     for (int e = c.tid; e < total; e += c.nthr) {
         const int k1 = ms_fastdiv(e, mgc), v = e - k1 * cnt;
         cpx val = s[tile_addr(g, v, k1)];
@@ -315,26 +317,26 @@ MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
 }
 
 // ---- rows kernel -----------------------------------------------------------------------------------
-template <int LD, int MODE, int ST>
+template <int LD, int MODE, int ST, int SQ>
 MS_DEV void fft_rows_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
     const FftJob& J = stage_job(jobs, c);
-    const int G = J.G, F1 = J.F1, F2 = J.F2;
+    const int G = SQ ? SQ : J.G, F1 = SQ ? 256 : J.F1, F2 = SQ ? 256 : J.F2;
     const int row0 = c.bx * G;
     if (row0 >= F1) return;
-    const int cnt = (F1 - row0) < G ? (F1 - row0) : G;
+    const int cnt = SQ ? SQ : ((F1 - row0) < G ? (F1 - row0) : G);
     cpx* s = (cpx*)(c.smem + MS_JOB_SMEM);
     cpx* const sA = s;
     TileGeom g; g.cnt = cnt; g.vs = (ms_pad(F2) + 1) | 1; g.es = 1; g.colmajor = 0;
-    cpx* s2 = s + (G * g.vs + 2);
+    cpx* s2 = s + (G * g.vs + 2);                                 // (unused by the static in-place tiles)
     const int total = F2 * cnt;
-    const unsigned mgF = J.p2.mg_F, mgc = ms_magic_dev(cnt);
+    const unsigned mgF = SQ ? ms_magic_c(256) : J.p2.mg_F, mgc = SQ ? ms_magic_c(SQ ? SQ : 1) : ms_magic_dev(cnt);
 #pragma unroll 4
     for (int e = c.tid; e < total; e += c.nthr) {
         const int r = ms_fastdiv(e, mgF), i = e - r * F2;
         s[tile_addr(g, r, i)] = job_load<LD>(J, (row0 + r) * F2 + i);
     }
     c.sync();
-    s = tile_fft<0>(s, s2, g, J.p2, J.tw2, c);
+    s = SQ ? tile_fft_256<0, SQ ? SQ : 1>(s, g, J.tw2, c) : tile_fft<0>(s, s2, g, J.p2, J.tw2, c);
     if (MODE == MODE_NAT) {
         for (int e = c.tid; e < total; e += c.nthr) {
             const int k2 = ms_fastdiv(e, mgc), r = e - k2 * cnt;
@@ -354,7 +356,8 @@ MS_DEV void fft_rows_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
         }
         c.sync();
         cpx* other = (s == sA) ? s2 : sA;
-        s = tile_fft<0>(s, other, g, J.p2, J.tw2, c);
+        s = SQ ? tile_fft_256<0, SQ ? SQ : 1>(s, g, J.tw2, c) : tile_fft<0>(s, other, g, J.p2, J.tw2, c);
+#pragma unroll 4
         for (int e = c.tid; e < total; e += c.nthr) {
             const int r = ms_fastdiv(e, mgF), i = e - r * F2;
             cpx val = s[tile_addr(g, r, i)];

@@ -121,6 +121,7 @@ def pack_chunk(plans) -> Tables:
     mono_at, last = [], np.full((R, 3), -1, np.int64)
     fir_of = {}
     alg = dict(synth=0, tilt_spectral=0, grain_spectral=0, overlap_add=0, fir_in=0, fir_taps=0, post=0)
+    env_seen = {}
     e = 0
     for r, rp in enumerate(plans):
         a, d, rel, S, curve = rp.adsr
@@ -173,9 +174,11 @@ def pack_chunk(plans) -> Tables:
                 x_end = max(x_end, ev.start + ev.length)
                 alg["overlap_add"] += ev.length
             e += 1
-        ola_r[r] = (mono_n, n, ev_begin, len(ola_e), max_len, a, d_end, sus_end, 1 if (rel > 0 and n > sus_end) else 0,
-                    1.0 / a if a > 0 else 0.0, 1.0 / (d_end - a) if d_end > a else 0.0,
-                    1.0 / (n - sus_end - 1) if n - sus_end > 1 else 0.0, S, curve, -1)
+        env_key = (n, a, d_end, sus_end, 1 if (rel > 0 and n > sus_end) else 0,
+                   1.0 / a if a > 0 else 0.0, 1.0 / (d_end - a) if d_end > a else 0.0,
+                   1.0 / (n - sus_end - 1) if n - sus_end > 1 else 0.0, S, curve)
+        env_seen.setdefault(env_key, []).append(r)
+        ola_r[r] = (mono_n, n, ev_begin, len(ola_e), max_len) + env_key[1:] + (-1,)
         alg["overlap_add"] += n
         # FIR: reflection cloud folded into the impulse response
         has_er = rp.er_offs is not None and rp.er_offs.size > 0
@@ -247,12 +250,9 @@ def pack_chunk(plans) -> Tables:
         frames += n
         alg["post"] += n
     # envelopes shared by several renders are tabulated once (ms_adsr_tables) instead of one pow() per sample
-    env_fields = ["out_n", "A", "D_end", "sus_end", "has_release", "inv_A", "inv_D", "inv_R", "S", "curve"]
-    seen, env_n = {}, 0
-    for r in range(R):
-        seen.setdefault(tuple(ola_r[r][f].item() for f in env_fields), []).append(r)
+    env_n = 0
     reps = []
-    for key, members in seen.items():
+    for key, members in env_seen.items():
         if len(members) >= 2:
             ola_r["env"][members] = env_n
             reps.append(ola_r[members[0]].copy())
