@@ -270,6 +270,29 @@ MS_DEV void stockham_pass_ip(cpx* MS_RESTRICT buf, const TileGeom& g, int per_ve
 // always full: CNT vectors, CNT * 32 threads.
 template <unsigned D> struct MsMagic { static constexpr unsigned v = D <= 1 ? 0u : (unsigned)(0x100000000ull / (D ? D : 1)) + 1u; };
 #define ms_magic_c(D) (MsMagic<(D)>::v)
+// Static power-of-two transforms of CNT vectors of length F, F * CNT elements = 8 per thread (CNT * F / 8 threads),
+// in place: 128 = 8.4.4, 256 = 8.8.4, 512 = 8.8.8, 1024 = 8.8.4.4.  Used by the in-tile Bluestein columns.
+template <int CM, int F, int CNT>
+MS_DEV cpx* tile_fft_pow2(cpx* a, const TileGeom& g, const cpx* MS_RESTRICT tw, const Ctx& c) {
+    constexpr unsigned mc = ms_magic_c(CNT);
+    constexpr int P = F / 8;
+    stockham_pass_ip<8, CM, 1>(a, g, P, 1, P, ms_magic_c(1), ms_magic_c(P), mc, tw, c);
+    if (F == 128) {
+        stockham_pass_ip<4, CM, 2>(a, g, 32, 8, 4, ms_magic_c(8), ms_magic_c(32), mc, tw, c);
+        stockham_pass_ip<4, CM, 2>(a, g, 32, 32, 1, ms_magic_c(32), ms_magic_c(32), mc, tw, c);
+    } else if (F == 256) {
+        stockham_pass_ip<8, CM, 1>(a, g, 32, 8, 4, ms_magic_c(8), ms_magic_c(32), mc, tw, c);
+        stockham_pass_ip<4, CM, 2>(a, g, 64, 64, 1, ms_magic_c(64), ms_magic_c(64), mc, tw, c);
+    } else if (F == 512) {
+        stockham_pass_ip<8, CM, 1>(a, g, 64, 8, 8, ms_magic_c(8), ms_magic_c(64), mc, tw, c);
+        stockham_pass_ip<8, CM, 1>(a, g, 64, 64, 1, ms_magic_c(64), ms_magic_c(64), mc, tw, c);
+    } else {        // 1024
+        stockham_pass_ip<8, CM, 1>(a, g, 128, 8, 16, ms_magic_c(8), ms_magic_c(128), mc, tw, c);
+        stockham_pass_ip<4, CM, 2>(a, g, 256, 64, 4, ms_magic_c(64), ms_magic_c(256), mc, tw, c);
+        stockham_pass_ip<4, CM, 2>(a, g, 256, 256, 1, ms_magic_c(256), ms_magic_c(256), mc, tw, c);
+    }
+    return a;
+}
 template <int CM, int CNT>
 MS_DEV cpx* tile_fft_256(cpx* a, const TileGeom& g, const cpx* MS_RESTRICT tw, const Ctx& c) {
     constexpr unsigned mc = ms_magic_c(CNT);

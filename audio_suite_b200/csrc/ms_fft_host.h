@@ -13,10 +13,13 @@ static const int MS_TILE_MAX = sizeof(real) == 4 ? 8192 : 4096;
 #ifndef MS_SQ_MINB
 #define MS_SQ_MINB 5
 #endif
-template <int LD, int ST, int TWID, int SQ = 0> struct ColsK {
-    static constexpr int MAXT = (SQ && sizeof(real) == 8) ? 256 : 512;      // static f64 tiles: 2048 elements, 256 threads
-    static constexpr int MINB = (SQ && sizeof(real) == 8) ? MS_SQ_MINB : MS_FFT_MINB;        // 2 x 512: <= 64 registers, three 256..320-thread CTAs per SM
-    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_body<LD, ST, TWID, SQ>(jobs, c); }
+#ifndef MS_SB_MINB
+#define MS_SB_MINB 5
+#endif
+template <int LD, int ST, int TWID, int SQ = 0, int SB = 0> struct ColsK {
+    static constexpr int MAXT = ((SQ && sizeof(real) == 8) || SB) ? 256 : 512;      // static tiles: 2048 elements, 256 threads
+    static constexpr int MINB = SB ? MS_SB_MINB : (SQ && sizeof(real) == 8) ? MS_SQ_MINB : MS_FFT_MINB;   // 2 x 512: <= 64 registers
+    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_body<LD, ST, TWID, SQ, SB>(jobs, c); }
 };
 template <int LD, int MODE, int ST, int SQ = 0> struct RowsK {
     static constexpr int MAXT = (SQ && sizeof(real) == 8) ? 256 : 512;
@@ -79,7 +82,12 @@ public:
     }
 
     // jobs_dev: device copy of `jobs` (same order).  Jobs must be sorted by job_class().
-    static int job_class(const FftJob& J) { return (J.ch_hi ? 2 : 0) + (J.F1 > 1 ? 1 : 0); }
+    // + 4 * static Bluestein id (1..4 for B1 = 128, 256, 512, 1024 with 2048-element tiles of full columns)
+    static int sb_id(const FftJob& J) {
+        if (!J.B1 || J.ch_hi || J.T * J.B1 != MS_SB_TILE || J.F2 % J.T) return 0;
+        return J.B1 == 128 ? 1 : J.B1 == 256 ? 2 : J.B1 == 512 ? 3 : J.B1 == 1024 ? 4 : 0;
+    }
+    static int job_class(const FftJob& J) { return (J.ch_hi ? 2 : 0) + (J.F1 > 1 ? 1 : 0) + 4 * sb_id(J); }
 
     // forward: pair (in_a,in_b) -> Z ;  inverse: spec op on Z -> (out_a,out_b)
     // (all entry points take an optional [lo, hi) job range so callers can walk a batch in L2-sized groups)
@@ -268,6 +276,17 @@ private:
     static int launch_cols(int ept, unsigned gx, unsigned gy, int nthr, size_t smem, ms_stream_t st, const FftJob* jd) {
         return L<ColsK<LD, ST, TWID, SQ>>(gx, gy, nthr, smem, st, jd);
     }
+    // in-tile Bluestein columns with static convolution length (sb = sb_id): 256 threads, one tile buffer
+    template <int LD, int ST, int TWID>
+    static int launch_cols_sb(int sb, unsigned gx, unsigned gy, ms_stream_t st, const FftJob* jd) {
+        const size_t smem = MS_JOB_SMEM + sizeof(cpx) * (size_t)(MS_SB_TILE + MS_SB_TILE / 8 + 4);
+        switch (sb) {
+            case 1: return L<ColsK<LD, ST, TWID, 0, 128>>(gx, gy, 256, smem, st, jd);
+            case 2: return L<ColsK<LD, ST, TWID, 0, 256>>(gx, gy, 256, smem, st, jd);
+            case 3: return L<ColsK<LD, ST, TWID, 0, 512>>(gx, gy, 256, smem, st, jd);
+            default: return L<ColsK<LD, ST, TWID, 0, 1024>>(gx, gy, 256, smem, st, jd);
+        }
+    }
     template <int LD, int MODE, int ST, int SQ = 0>
     static int launch_rows(int ept, unsigned gx, unsigned gy, int nthr, size_t smem, ms_stream_t st, const FftJob* jd) {
         return L<RowsK<LD, MODE, ST, SQ>>(gx, gy, nthr, smem, st, jd);
@@ -308,9 +327,10 @@ private:
         const size_t end = std::min(hi, jobs.size());
         size_t b = lo;
         while (b < end) {
-            const int cls = job_class(jobs[b]);
+            const int full_cls = job_class(jobs[b]);
+            const int cls = full_cls & 3, sb = full_cls >> 2;
             size_t e = b;
-            while (e < end && job_class(jobs[e]) == cls && e - b < 32768) ++e;
+            while (e < end && job_class(jobs[e]) == full_cls && e - b < 32768) ++e;
             const ClassShape cs = class_shape(jobs, b, e);
             const unsigned gy = (unsigned)(e - b);
             const FftJob* jd = jobs_dev + b;
@@ -357,10 +377,12 @@ private:
                                : launch_rows<LD_SPEC, MODE_NAT, ST_PAIR>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
             } else if (cls == 1) {
                 if (what == 0) {
-                    rc = launch_cols<LD_PAIR, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    rc = sb ? launch_cols_sb<LD_PAIR, ST_WORK, 1>(sb, C.gx, gy, st, jd)
+                            : launch_cols<LD_PAIR, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
                     if (!rc) rc = launch_rows<LD_WORK, MODE_NAT, ST_Z>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
                 } else {
-                    rc = launch_cols<LD_SPEC, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    rc = sb ? launch_cols_sb<LD_SPEC, ST_WORK, 1>(sb, C.gx, gy, st, jd)
+                            : launch_cols<LD_SPEC, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
                     if (!rc) rc = launch_rows<LD_WORK, MODE_NAT, ST_PAIR>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
                 }
             } else if (cls == 2) {

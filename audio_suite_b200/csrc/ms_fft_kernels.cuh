@@ -258,9 +258,47 @@ MS_DEV const FftJob& stage_job(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
 
 // ---- columns kernel --------------------------------------------------------------------------------
 // SQ != 0: static geometry F1 = F2 = 256, T = G = SQ, plain mixed radix (the 65536-point transforms of the FIR stage)
-template <int LD, int ST, int TWID, int SQ>
+// SB != 0: in-tile Bluestein with static convolution length B1 = SB and T = MS_SB_TILE / SB full columns, in place
+#define MS_SB_TILE 2048
+template <int LD, int ST, int TWID, int SB>
+MS_DEV void fft_cols_bluestein_static(const FftJob& J, const Ctx& c) {
+    constexpr int T = MS_SB_TILE / (SB ? SB : 1);
+    const int F1 = J.F1, F2 = J.F2;
+    const int col0 = c.bx * T;
+    if (col0 >= F2) return;
+    cpx* s = (cpx*)(c.smem + MS_JOB_SMEM);
+    TileGeom g; g.cnt = T; g.vs = 1; g.es = T; g.colmajor = 1;
+    constexpr int all = MS_SB_TILE;
+#pragma unroll 2
+    for (int e = c.tid; e < all; e += c.nthr) {
+        const int i = e / T, v = e - i * T;
+        cpx val = c_zero();
+        if (i < F1) val = c_mul(job_load<LD>(J, i * F2 + col0 + v), __ldg(&J.b1_chirp[i]));
+        s[tile_addr(g, v, i)] = val;
+    }
+    c.sync();
+    tile_fft_pow2<1, SB ? SB : 128, T>(s, g, J.twb, c);
+#pragma unroll 2
+    for (int e = c.tid; e < all; e += c.nthr) {
+        const int i = e / T, v = e - i * T;
+        const int a = tile_addr(g, v, i);
+        s[a] = c_swap(c_mul(s[a], __ldg(&J.b1_spec[i])));
+    }
+    c.sync();
+    tile_fft_pow2<1, SB ? SB : 128, T>(s, g, J.twb, c);
+    const int total = F1 * T;
+#pragma unroll 2
+    for (int e = c.tid; e < total; e += c.nthr) {
+        const int k1 = e / T, v = e - k1 * T;
+        cpx val = c_mul(c_swap(s[tile_addr(g, v, k1)]), __ldg(&J.b1_chirp[k1]));
+        if (TWID) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)k1 * (unsigned)(col0 + v)));
+        job_store<ST>(J, k1 * F2 + col0 + v, val);
+    }
+}
+template <int LD, int ST, int TWID, int SQ, int SB>
 MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
     const FftJob& J = stage_job(jobs, c);
+    if (SB) { fft_cols_bluestein_static<LD, ST, TWID, SB>(J, c); return; }
     const int T = SQ ? SQ : J.T, F1 = SQ ? 256 : J.F1, F2 = SQ ? 256 : J.F2;
     const int col0 = c.bx * T;
     if (col0 >= F2) return;
