@@ -81,8 +81,13 @@ struct MsStageRing {
     MsStageRing() : cur(0), off(0), ok(true) { for (int i = 0; i < NB; ++i) { base[i] = nullptr; used[i] = false; last[i] = 0; } }
     int open(int b) {
         if (!base[b]) {
-            if (cudaHostAlloc((void**)&base[b], BLK, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); base[b] = nullptr; return -1; }
-            if (cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming) != cudaSuccess) return -1;
+            // all blocks at once, on first use: pinning memory later, while planning workers keep the cores busy,
+            // stalls the caller for tens of ms (measured on the B200 hosts)
+            for (int i = 0; i < NB; ++i) {
+                if (base[i]) continue;
+                if (cudaHostAlloc((void**)&base[i], BLK, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); base[i] = nullptr; return -1; }
+                if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return -1;
+            }
         }
         if (used[b]) { if (cudaEventSynchronize(ev[b]) != cudaSuccess) return -1; used[b] = false; }
         return 0;
