@@ -41,7 +41,20 @@ class SynthEvt(C.Structure):
                 ("n", C.c_int32), ("mode", C.c_int32), ("fade", C.c_int32), ("sigma", C.c_int32),
                 ("out", C.c_int64), ("f_over_sr", C.c_double), ("inv_fade", C.c_double),
                 ("ring_decay", C.c_double), ("env_decay", C.c_double),
-                ("dust_begin", C.c_int64), ("dust_count", C.c_int32), ("ker_len", C.c_int32), ("aux", C.c_int64)]
+                ("dust_begin", C.c_int64), ("dust_count", C.c_int32), ("ker_len", C.c_int32), ("aux", C.c_int64),
+                ("atom_begin", C.c_int64), ("atom_count", C.c_int32), ("_pad", C.c_int32)]
+
+
+class ImprintEvt(C.Structure):
+    _fields_ = [("z", C.c_int64), ("n", C.c_int32), ("_pad", C.c_int32)]
+
+
+class ImprintRender(C.Structure):
+    _fields_ = [("ev_begin", C.c_int32), ("ev_end", C.c_int32), ("amount", C.c_double), ("smooth", C.c_double)]
+
+
+class WaveletAtom(C.Structure):
+    _fields_ = [("f0_over_sr", C.c_double), ("inv_sigma", C.c_double), ("phase", C.c_double), ("weight", C.c_double)]
 
 
 class OlaRender(C.Structure):
@@ -84,12 +97,17 @@ _STAGES = {
     "ms_spectral_apply": (_I, [_P, _I, _P, _P, _P, _Z, _P]),
     "ms_spectral_create": (_I, [_P, _I, _P, _P, _P, _Z, _P, C.POINTER(C.c_void_p)]),
     "ms_spectral_run": (_I, [_P, _P]),
+    "ms_spectral_forward": (_I, [_P, _P]),
+    "ms_spectral_inverse": (_I, [_P, _P]),
+    "ms_spectral_z_table": (_I, [_P, _P, C.POINTER(C.c_size_t)]),
+    "ms_imprint": (_I, [_P, _P, _I, _I, _P, _P]),
     "ms_spectral_destroy": (None, [_P]),
     "ms_fft_pair_forward": (_I, [_P, _P, _I, _P, _P, _Z, _P]),
     "ms_fft_pair_workspace_bytes": (_Z, [_I]),
     "ms_synth_normal": (_I, [_P, _I, _P, _P]),
     "ms_synth_dust": (_I, [_P, _I, _P, _P, _P, _P]),
     "ms_synth_tilt_finish": (_I, [_P, _I, _P, _P]),
+    "ms_synth_wavelet": (_I, [_P, _I, _P, _P, _P, _P]),
     "ms_adsr_tables": (_I, [_P, _I, _I, _P, _P]),
     "ms_overlap_add": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "ms_fir_workspace_bytes": (_Z, [_P, _I]),

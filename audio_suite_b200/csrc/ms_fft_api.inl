@@ -39,7 +39,7 @@ extern "C" size_t MS_API(ms_spectral_workspace_bytes)(const ms_spec_job* jobs, i
 }
 
 // groups: job index boundaries such that one group's working set (signals, spectrum, scratch) stays in L2
-struct SpectralPlan { std::vector<FftJob> jobs; FftJob* jobs_dev; std::vector<size_t> groups; };
+struct SpectralPlan { std::vector<FftJob> jobs; FftJob* jobs_dev; std::vector<size_t> groups; std::vector<size_t> z_at; size_t z_off; };
 // Measured on B200 (C5 sweep): walking the batch in 56 MB groups was 14 % SLOWER (2023 small launches, tail
 // effects) than one launch per pass over the whole batch -- these passes are latency-bound, not DRAM-bound --
 // so grouping is off.
@@ -55,6 +55,7 @@ extern "C" int MS_API(ms_spectral_create)(const ms_spec_job* in, int njobs, cons
     std::vector<FftJob>& jobs = P->jobs; SpecLayout lay;
     if (spec_prepare(in, njobs, jobs, lay, st)) { delete P; return -1; }
     if (ws_bytes < lay.total) { delete P; MS_FAIL("ms_spectral_create: workspace %zu < required %zu", ws_bytes, lay.total); }
+    P->z_at = lay.z_at; P->z_off = lay.z_off;
     char* base = (char*)ws;
     for (int i = 0; i < njobs; ++i) {
         FftJob& J = jobs[i];
@@ -100,6 +101,25 @@ extern "C" int MS_API(ms_spectral_run)(void* handle, void* stream) {
         if (FftEngine::get().forward(P->jobs, P->jobs_dev, st, P->groups[g], P->groups[g + 1])) return -1;
         if (FftEngine::get().inverse(P->jobs, P->jobs_dev, st, P->groups[g], P->groups[g + 1])) return -1;
     }
+    return 0;
+}
+extern "C" int MS_API(ms_spectral_forward)(void* handle, void* stream) {
+    SpectralPlan* P = (SpectralPlan*)handle;
+    if (!P) MS_FAIL("ms_spectral_forward: null handle");
+    if (P->jobs.empty()) return 0;
+    return FftEngine::get().forward(P->jobs, P->jobs_dev, (ms_stream_t)stream);
+}
+extern "C" int MS_API(ms_spectral_inverse)(void* handle, void* stream) {
+    SpectralPlan* P = (SpectralPlan*)handle;
+    if (!P) MS_FAIL("ms_spectral_inverse: null handle");
+    if (P->jobs.empty()) return 0;
+    return FftEngine::get().inverse(P->jobs, P->jobs_dev, (ms_stream_t)stream);
+}
+extern "C" int MS_API(ms_spectral_z_table)(void* handle, int64_t* z_offsets, size_t* z_base_bytes) {
+    SpectralPlan* P = (SpectralPlan*)handle;
+    if (!P) MS_FAIL("ms_spectral_z_table: null handle");
+    for (size_t i = 0; i < P->z_at.size(); ++i) z_offsets[i] = (int64_t)P->z_at[i];
+    *z_base_bytes = P->z_off;
     return 0;
 }
 extern "C" void MS_API(ms_spectral_destroy)(void* handle) { delete (SpectralPlan*)handle; }

@@ -26,6 +26,7 @@
   static inline float2 __ldg(const float2* p) { return *p; }
   static inline int __ldg(const int* p) { return *p; }
   static inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
+  static inline double cospi(double a) { return std::cos(M_PI * a); }
   namespace msemu { void yield_barrier(); }
   struct Ctx {
       int tid, nthr, bx, by;

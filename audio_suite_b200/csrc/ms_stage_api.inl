@@ -9,6 +9,12 @@ struct SynthTiltK { static constexpr int MAXT = 256;
 struct SynthDustK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const SynthEvt* e, const int* dp, const real* dv, real* pool, const Ctx& c) { synth_dust_body(e, dp, dv, pool, c); } };
+struct SynthWaveletK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const SynthEvt* e, const WaveletAtom* a, const int* sh, real* pool, const Ctx& c) { synth_wavelet_body(e, a, sh, pool, c); } };
+struct ImprintK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const ImprintEvt* e, const ImprintRender* r, cpx* z, const Ctx& c) { imprint_body(e, r, z, c); } };
 struct OlaK { static constexpr int MAXT = OLA_NTHR;
     static constexpr int MINB = 1;
     static MS_DEV void run(const OlaRender* r, const OlaEvt* e, const real* pool, const real* env, real* mono, const Ctx& c) { ola_adsr_body(r, e, pool, env, mono, c); } };
@@ -52,6 +58,17 @@ extern "C" int MS_API(ms_synth_dust)(const ms_synth_evt* evts, int n, const int3
 extern "C" int MS_API(ms_adsr_tables)(const ms_ola_render* reps, int n_tables, int max_out_n, real* envpool, void* stream) {
     const unsigned gx = (unsigned)((max_out_n + OLA_TILE - 1) / OLA_TILE);
     MS_FOR_Y_CHUNKS(n_tables, { if (ms_launch<AdsrTableK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream, reps + _y0, envpool)) return -1; })
+    return 0;
+}
+extern "C" int MS_API(ms_synth_wavelet)(const ms_synth_evt* evts, int n, const ms_wavelet_atom* atoms, const int32_t* shifts,
+                                real* pool, void* stream) {
+    MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthWaveletK>(mk_dim(64, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, atoms, (const int*)shifts, pool)) return -1; })
+    return 0;
+}
+extern "C" int MS_API(ms_imprint)(const ms_imprint_evt* evts, const ms_imprint_render* renders, int n_renders, int max_bins,
+                          real* z_base, void* stream) {
+    const unsigned gx = (unsigned)((max_bins + 255) / 256);
+    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<ImprintK>(mk_dim(gx, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts, renders + _y0, (cpx*)z_base)) return -1; })
     return 0;
 }
 extern "C" int MS_API(ms_overlap_add)(const ms_ola_render* renders, int n_renders, int max_out_n, const ms_ola_evt* evts,

@@ -10,7 +10,7 @@
 // shared staging buffer in stream order; the mode's closed-form terms (sine with float64 phase,
 // exponentials, fades) are applied on the way out with coalesced stores.
 
-enum { SY_GAUSS = 0, SY_DUST = 1, SY_NOISE = 2, SY_SKEW = 3, SY_RES = 4, SY_PLAIN = 5 };
+enum { SY_GAUSS = 0, SY_DUST = 1, SY_NOISE = 2, SY_SKEW = 3, SY_RES = 4, SY_PLAIN = 5, SY_WAVELET = 6 };
 
 #define SY_C 8            // words per thread per round
 #define SY_NTHR 256
@@ -302,5 +302,34 @@ MS_DEV void synth_dust_body(const SynthEvt* MS_RESTRICT evts, const int* MS_REST
             acc += __ldg(&val[q]) * (tab ? ker[hi - p] : r_exp(-rate * (real)(hi - p)));
         }
         out[j] = acc * fade_gain(j, E.n, E.fade, E.inv_fade);
+    }
+}
+
+// Wavelet atoms (main_v2.py:317-331, morlet_atom :165-170): x[j] = hann(n)[j] * sum_k w_k * atom_k[(j - shift_k) mod n],
+// atom_k[m] = exp(-0.5 (t/sigma)^2) cos(2 pi f0 t + phase), t = (m - n/2) / gen_sr.  The scalar draws (f0, sigma, phase,
+// shift) come from the host planner; phase arithmetic is float64 (f0 t reaches 1e4 cycles).  One thread per sample.
+typedef ms_wavelet_atom WaveletAtom;
+MS_DEV void synth_wavelet_body(const SynthEvt* MS_RESTRICT evts, const WaveletAtom* MS_RESTRICT atoms, const int* MS_RESTRICT shifts,
+                               real* MS_RESTRICT pool, const Ctx& c) {
+    const SynthEvt E = evts[c.by];
+    if (E.mode != SY_WAVELET) return;
+    const WaveletAtom* A = atoms + E.atom_begin;
+    const int* S = shifts + E.atom_begin;
+    real* out = pool + E.out;
+    const int n = E.n;
+    const double half = 0.5 * (double)n;
+    for (int j = c.bx * c.nthr + c.tid; j < n; j += c.nthr * 64) {
+        double acc = 0.0;
+        for (int k = 0; k < E.atom_count; ++k) {
+            int m = j - S[k];                      // np.roll(atom, shift)[j] = atom[(j - shift) mod n]
+            if (m < 0) m += n; else if (m >= n) m -= n;
+            const double d = (double)m - half;
+            const double q = d * A[k].inv_sigma;
+            double cyc = d * A[k].f0_over_sr;
+            cyc -= floor(cyc);
+            acc += A[k].weight * exp(-0.5 * q * q) * cos(6.283185307179586476925286766559 * cyc + A[k].phase);
+        }
+        const double hann = n > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)j / (double)(n - 1)) : 1.0;
+        out[j] = (real)(acc * hann);
     }
 }

@@ -200,3 +200,30 @@ MS_DEV void post_write_body(const PostRender* MS_RESTRICT renders, const real* M
 MS_DEV void roll_body(const real* MS_RESTRICT src, real* MS_RESTRICT dst, int n, int shift, const Ctx& c) {
     for (int i = c.bx * c.nthr + c.tid; i < n; i += c.nthr * 64) dst[i] = src[wrap_idx((long long)i + shift, n)];
 }
+
+// ---- spectral imprint (SpectralImprint.apply, main_v2.py:565-581) ----------------------------------------------
+// grid = (ceil(max_bins / nthr), renders): a thread owns one rfft bin of one render and walks that render's grains
+// in event order, carrying the moving average of the magnitude in a register.  The average restarts whenever the
+// spectrum length differs from the previous imprinted grain's (M:575).  Spectra are those of single-signal jobs
+// (Z = DFT of the real grain); only bins 0..n/2 are rewritten, the inverse transform mirrors them (irfft).
+typedef ms_imprint_evt ImprintEvt;
+typedef ms_imprint_render ImprintRender;
+MS_DEV void imprint_body(const ImprintEvt* MS_RESTRICT evts, const ImprintRender* MS_RESTRICT renders, cpx* zbase, const Ctx& c) {
+    const ImprintRender R = renders[c.by];
+    const int k = c.bx * c.nthr + c.tid;
+    const real amount = (real)R.amount, smooth = (real)R.smooth;
+    real mem = (real)0.;
+    int prev_bins = -1;
+    for (int e = R.ev_begin; e < R.ev_end; ++e) {
+        const int n = evts[e].n, bins = n / 2 + 1;
+        if (k < bins) {
+            cpx* Z = zbase + evts[e].z;
+            const cpx X = Z[k];
+            const real mag = (real)hypot((double)X.x, (double)X.y);
+            mem = (bins != prev_bins) ? mag : smooth * mem + ((real)1.0 - smooth) * mag;
+            const real mag2 = ((real)1.0 - amount) * mag + amount * mem;
+            Z[k] = mag > (real)0. ? c_scale(X, mag2 / mag) : mk(mag2, (real)0.);     // angle(0) = 0
+        }
+        prev_bins = bins;
+    }
+}

@@ -158,6 +158,21 @@ class _SpectralStage:
         if self.njobs:
             _check(self.dev, self.api.ms_spectral_run(self.handle, self.dev.stream_ptr()))
 
+    def forward(self):
+        if self.njobs:
+            _check(self.dev, self.api.ms_spectral_forward(self.handle, self.dev.stream_ptr()))
+
+    def inverse(self):
+        if self.njobs:
+            _check(self.dev, self.api.ms_spectral_inverse(self.handle, self.dev.stream_ptr()))
+
+    def z_table(self):
+        """(byte offset of the spectra inside the workspace, per-job offsets in complex elements, input order)"""
+        offs = np.zeros(self.njobs, np.int64)
+        base = C.c_size_t(0)
+        _check(self.dev, self.api.ms_spectral_z_table(self.handle, offs.ctypes.data, C.byref(base)))
+        return int(base.value), offs
+
     def close(self):
         if self.handle:
             self.api.ms_spectral_destroy(self.handle)
@@ -212,10 +227,16 @@ class BatchRenderer:
         dust = sy1[sy1["mode"] == P.MODE_DUST]
         tilt = t.sy2[(t.sy2["mode"] == P.MODE_NOISE) | (t.sy2["mode"] == P.MODE_SKEW)]
         self.n_dust_evt, self.n_tilt_evt = len(dust), len(tilt)
-        self.d_sy1 = dev.upload(sy1[sy1["mode"] != P.MODE_DUST]) if self.n_dust_evt < len(sy1) else None
-        self.n_normal_evt = len(sy1) - self.n_dust_evt
+        normal = sy1[(sy1["mode"] != P.MODE_DUST) & (sy1["mode"] != P.MODE_WAVELET)]      # the modes that draw normals
+        self.n_normal_evt = len(normal)
+        self.d_sy1 = dev.upload(normal) if self.n_normal_evt else None
         self.d_sy_dust = dev.upload(dust) if self.n_dust_evt else None
         self.d_sy_tilt = dev.upload(tilt) if self.n_tilt_evt else None
+        wav = sy1[sy1["mode"] == P.MODE_WAVELET]
+        self.n_wav_evt = len(wav)
+        if self.n_wav_evt:
+            self.d_sy_wav = dev.upload(wav)
+            self.d_atoms, self.d_atom_shift = dev.upload(t.atoms), dev.upload(t.atom_shift)
         self.d_ola_r, self.d_ola_e = dev.upload(t.ola_r), dev.upload(t.ola_e)
         self.n_env = len(t.env_reps)
         self.envpool = dev.empty(max(1, t.env_n), real)
@@ -227,6 +248,26 @@ class BatchRenderer:
         self.tilt_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.tilt), self.pool, self.pool)
         self.grain_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.grain), self.pool, self.pool)
         self.rot_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.rot), self.mono, self.mono)
+        # spectral imprint: single-signal jobs (Z = the grain's DFT), forward -> per-render moving average -> inverse
+        self.imprint_stage, self.n_imprint_renders = None, 0
+        if len(t.imprint):
+            rows = t.imprint
+            jobs = np.zeros(len(rows), np.dtype(_abi.SpecJob))
+            jobs["n"], jobs["in_a"], jobs["out_a"], jobs["in_b"], jobs["out_b"] = rows[:, 3], rows[:, 1], rows[:, 2], -1, -1
+            self.imprint_stage = _SpectralStage(dev, self.api, jobs, self.pool, self.pool)
+            zbase, zoffs = self.imprint_stage.z_table()
+            ev = np.zeros(len(rows), np.dtype(_abi.ImprintEvt))
+            ev["z"], ev["n"] = zoffs, rows[:, 3]
+            renders = np.unique(rows[:, 0])
+            first = np.searchsorted(rows[:, 0], renders, side="left")
+            last = np.searchsorted(rows[:, 0], renders, side="right")
+            rr = np.zeros(len(renders), np.dtype(_abi.ImprintRender))
+            rr["ev_begin"], rr["ev_end"] = first, last
+            rr["amount"], rr["smooth"] = t.imprint_par[renders, 0], t.imprint_par[renders, 1]
+            self.d_imp_evt, self.d_imp_render = dev.upload(ev), dev.upload(rr)
+            self.n_imprint_renders = len(renders)
+            self.imprint_max_bins = int(rows[:, 3].max()) // 2 + 1
+            self.imprint_zbase = zbase
         _mark("spectral_create")
         self.fir_handle = C.c_void_p(None)
         if self.n_fir:
@@ -259,6 +300,9 @@ class BatchRenderer:
             if self.n_dust_evt:
                 _check(dev, lib.ms_synth_dust(dev.ptr(self.d_sy_dust), self.n_dust_evt, dev.ptr(self.d_dpos), dev.ptr(self.d_dval),
                                               dev.ptr(self.pool), st))
+            if self.n_wav_evt:
+                _check(dev, lib.ms_synth_wavelet(dev.ptr(self.d_sy_wav), self.n_wav_evt, dev.ptr(self.d_atoms),
+                                                 dev.ptr(self.d_atom_shift), dev.ptr(self.pool), st))
             mark("synth")
             if self.any_tilt:
                 self.tilt_stage.run()
@@ -266,6 +310,13 @@ class BatchRenderer:
                 mark("tilt_spectral")
             self.grain_stage.run()
             mark("grain_spectral")
+            if self.imprint_stage is not None:
+                self.imprint_stage.forward()
+                zptr = C.c_void_p(dev.ptr(self.imprint_stage.ws).value + self.imprint_zbase)
+                _check(dev, lib.ms_imprint(dev.ptr(self.d_imp_evt), dev.ptr(self.d_imp_render), self.n_imprint_renders,
+                                           self.imprint_max_bins, zptr, st))
+                self.imprint_stage.inverse()
+                mark("spectral_imprint")
         if self.n_env:
             _check(dev, lib.ms_adsr_tables(dev.ptr(self.d_env_reps), self.n_env, self.max_out_n, dev.ptr(self.envpool), st))
         _check(dev, lib.ms_overlap_add(dev.ptr(self.d_ola_r), self.n_renders, self.max_out_n, dev.ptr(self.d_ola_e),
@@ -302,8 +353,9 @@ class BatchRenderer:
         return m
 
     def close(self):
-        for s in (self.tilt_stage, self.grain_stage, self.rot_stage):
-            s.close()
+        for s in (self.tilt_stage, self.grain_stage, self.rot_stage, self.imprint_stage):
+            if s is not None:
+                s.close()
         if self.fir_handle:
             self.api.ms_fir_destroy(self.fir_handle)
             self.fir_handle = C.c_void_p(None)

@@ -22,13 +22,12 @@ from .configs import BASIC_MODES
 DESIGN_SR_CAP = 30_000_000          # M:597, M:646
 IR_TAP_CAP = 8192                   # M:443
 
-MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN = range(6)
+MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET = range(7)
+WAVELET_FLOOR = 128                 # M:319
 _MODE_ID = {m: i for i, m in enumerate(BASIC_MODES)}
 
-_NEXT_ROW_FLAGS = ("nl_warp_on", "cep_warp_on", "partial_lock_on", "res_bank_on", "wg_on",
-                   "event_feedback_on", "spectral_imprint_on")
-_NEXT_ROW_MODES = ("Crackle / corona", "Stick–slip friction", "Micro-chaos", "Wavelet atoms",
-                   "IR fragment", "Image scanline")
+_NEXT_ROW_FLAGS = ("nl_warp_on", "cep_warp_on", "partial_lock_on", "res_bank_on", "wg_on", "event_feedback_on")
+_NEXT_ROW_MODES = ("Crackle / corona", "Stick–slip friction", "Micro-chaos", "IR fragment", "Image scanline")
 
 
 # --------------------------------------------------------------------------- breakpoint lanes (M:452-482)
@@ -217,6 +216,8 @@ class EventPlan:
     tilt: Optional[object] = None           # _abi.SpecOp for the tilted-noise modes
     dust_pos: Optional[np.ndarray] = None   # sorted unique impulse positions (int32)
     dust_val: Optional[np.ndarray] = None   # float64 values (last write wins, M:243)
+    atoms: Optional[np.ndarray] = None      # wavelet atoms: float64 [count, 4] = f0/sr, 1/(sigma*sr), phase, weight
+    atom_shift: Optional[np.ndarray] = None # int32 [count] circular shifts
     # mode constants (float64)
     f_over_sr: float = 0.0
     ring_decay: float = 0.0                 # 1 / (tau * gen_sr)
@@ -233,6 +234,7 @@ class RenderPlan:
     design_sr_base: int
     events: List[EventPlan] = field(default_factory=list)
     adsr: tuple = (0, 0, 0, 1.0, 1.0)       # A, D, R samples, sustain, curve
+    imprint: Optional[tuple] = None         # (amount, smooth) when SpectralImprint is active (M:625, 736-738)
     er_offs: Optional[np.ndarray] = None    # int32 tap delays (0 < off < out_n)
     er_gains: Optional[np.ndarray] = None   # float64
     ir: Optional[np.ndarray] = None         # float64 mono taps (<= 8192) or None
@@ -249,8 +251,8 @@ def design_rate(base_sr, unfold):
     return int(min(max(int(round(base_sr * unfold)), base_sr), DESIGN_SR_CAP))     # np.clip on scalars (M:597, M:646)
 
 
-def grain_length(gen_sr, micro_ms):
-    return int(max(16, round(gen_sr * micro_ms / 1000.0)))      # M:221
+def grain_length(gen_sr, micro_ms, floor=16):
+    return int(max(floor, round(gen_sr * micro_ms / 1000.0)))      # M:221 (gen_basic, floor 16), M:319 (wavelet atoms, 128)
 
 
 def check_supported(params):
@@ -282,7 +284,10 @@ def plan_render(params) -> RenderPlan:
     micro_s = micro_ms / 1000.0
     spread = float(params["grain_amp_rand"])
     gmode = params["gen_mode"]
-    if gmode in _MODE_ID:
+    dust_density = tilt = ring_hz = ring_decay_ms = 0.0
+    if gmode == "Wavelet atoms":
+        mode = MODE_WAVELET
+    elif gmode in _MODE_ID:
         mode = _MODE_ID[gmode]
         dust_density, tilt = float(params["dust_density"]), float(params["noise_tilt"])
         ring_hz, ring_decay_ms = float(params["ring_hz"]), float(params["ring_decay_ms"])
@@ -304,7 +309,7 @@ def plan_render(params) -> RenderPlan:
         amp *= rng.uniform(1.0 - spread, 1.0 + spread)
         ufac = max(1.0, float(ufac))
         sr_evt = design_rate(base_sr, ufac)
-        n = grain_length(sr_evt, micro_ms)
+        n = grain_length(sr_evt, micro_ms, WAVELET_FLOOR if mode == MODE_WAVELET else 16)
         ev = EventPlan(index=i, t0=t0, amp=float(amp), ufac=ufac, gen_sr=sr_evt, n=n, seed=seed + i, mode=mode,
                        cutoff_gen=cutoff_out * ufac, stretch=float(stretch), start=int(round(t0 * base_sr)))
         if ev.start < out_n:
@@ -322,6 +327,8 @@ def plan_render(params) -> RenderPlan:
             ev.tilt = tilt_spec_op(n, sr_evt, tilt)
             T = max(1e-6, micro_s * (0.25 if mode == MODE_NOISE else 0.2))
             ev.env_decay = 1.0 / (T * sr_evt)
+        elif mode == MODE_WAVELET:
+            _plan_wavelet(ev, micro_ms, float(params["wav_base_hz"]), int(params["wav_count"]), float(params["wav_spread"]))
         elif mode == MODE_RES:
             ev.f_over_sr = max(10.0, ring_hz) / sr_evt
             ev.ring_decay = 1.0 / (max(1e-6, ring_decay_ms / 1000.0) * sr_evt)
@@ -333,6 +340,8 @@ def plan_render(params) -> RenderPlan:
     r = max(0, int(round(base_sr * float(params["env_r"]) / 1000.0)))
     rp.adsr = (a, d, r, float(min(max(float(params["env_s"]), 0.0), 1.0)), float(max(1e-6, float(params["env_curve"]))))
 
+    if params["spectral_imprint_on"]:
+        rp.imprint = (float(params["spectral_imprint_amt"]), float(params["spectral_imprint_smooth"]))
     if params["er_cloud_on"]:
         offs, gains = reflection_taps(base_sr, int(params["er_taps"]), float(params["er_max_ms"]), seed)
         keep = (offs > 0) & (offs < out_n)
@@ -380,6 +389,26 @@ def reflection_taps(sr, taps, max_ms, seed):
     gains *= np.exp(-delays * 42.0)
     offs = np.rint(delays * sr).astype(np.int64)      # np.rint is half-to-even like Python round()
     return offs, gains
+
+
+def _plan_wavelet(ev, micro_ms, base_hz, count, spread):
+    """Scalar draws of gen_wavelet_atoms (M:322-327) in the reference's stream order."""
+    n = ev.n
+    if grain_length(ev.gen_sr, micro_ms, 16) != n:
+        # morlet_atom builds its atoms with gen_basic's length rule (M:166): shorter than the 128-sample grain here
+        raise ValueError(f"operands could not be broadcast together with shapes ({n},) ({grain_length(ev.gen_sr, micro_ms, 16)},)")
+    rng = np.random.default_rng(int(ev.seed))
+    count = int(max(1, count))
+    atoms = np.zeros((count, 4), dtype=np.float64)
+    shifts = np.zeros(count, dtype=np.int32)
+    for k in range(count):
+        f0 = base_hz * (2.0 ** rng.uniform(-spread, spread))
+        sigma_ms = max(0.03, micro_ms * rng.uniform(0.04, 0.18))
+        phase = rng.uniform(0, 2 * np.pi)
+        shifts[k] = int(rng.integers(-n // 8, n // 8))
+        sigma = max(1e-9, sigma_ms / 1000.0)
+        atoms[k] = (f0 / ev.gen_sr, 1.0 / (sigma * ev.gen_sr), phase, 1.0 / (1 + k * 0.6))
+    ev.atoms, ev.atom_shift = atoms, shifts
 
 
 def _plan_dust(ev, density):

@@ -88,6 +88,10 @@ class Tables:
     irs: np.ndarray = None
     dust_pos: np.ndarray = None
     dust_val: np.ndarray = None
+    atoms: np.ndarray = None        # wavelet atoms, float64 [N, 4]
+    atom_shift: np.ndarray = None   # int32 [N]
+    imprint: np.ndarray = None      # rows per imprinted event, in event order per render: render, pool_in, pool_out, n
+    imprint_par: np.ndarray = None  # per render: amount, smooth (nan when off)
     tilt: tuple = None          # (n, src, dst, ops)
     grain: tuple = None
     rot: tuple = None
@@ -115,6 +119,8 @@ def pack_chunk(plans) -> Tables:
     fir = []
     tilt, grain, rot = _Items(), _Items(), _Items()
     dust_pos, dust_val, n_dust = [], [], 0
+    atoms, atom_shift, n_atoms = [], [], 0
+    imprint_rows, imprint_par = [], np.full((R, 2), np.nan)
     tap_off, tap_gain, n_taps = [], [], 0
     irs, ir_index, n_ir = [], {}, 0
     pool_n = mono_n = h_total = max_h = 0
@@ -140,7 +146,13 @@ def pack_chunk(plans) -> Tables:
             micro = pool_n
             pool_n += ev.n
             out1, mode2, aux2, dust_b, dust_c = micro, -1, 0, 0, 0
+            atom_b, atom_c = 0, 0
             alg["synth"] += ev.n
+            if ev.mode == P.MODE_WAVELET:
+                atom_b, atom_c = n_atoms, len(ev.atom_shift)
+                atoms.append(ev.atoms)
+                atom_shift.append(ev.atom_shift)
+                n_atoms += atom_c
             if ev.mode == P.MODE_DUST:
                 dust_b, dust_c = n_dust, len(ev.dust_pos)
                 dust_pos.append(ev.dust_pos)
@@ -155,9 +167,9 @@ def pack_chunk(plans) -> Tables:
             common = (s_hi, s_lo, i_hi, i_lo, ev.n)
             tail = (ev.fade, ev.sigma)
             sy1[e] = common + (ev.mode,) + tail + (out1, ev.f_over_sr, 1.0 / ev.fade, ev.ring_decay, ev.env_decay,
-                                                     dust_b, dust_c, ev.ker_len, 0)
+                                                     dust_b, dust_c, ev.ker_len, 0, atom_b, atom_c, 0)
             sy2[e] = common + (mode2,) + tail + (micro, ev.f_over_sr, 1.0 / ev.fade, ev.ring_decay, ev.env_decay,
-                                                  0, 0, ev.ker_len, aux2)
+                                                  0, 0, ev.ker_len, aux2, 0, 0, 0)
             g_at = micro
             if ev.spec is not None:
                 g_at = pool_n
@@ -165,6 +177,12 @@ def pack_chunk(plans) -> Tables:
                 grain.add(ev.n, micro, g_at, ev.spec)
                 alg["grain_spectral"] += 2 * ev.n * (int(ev.spec.lp_on) + int(ev.spec.stretch_on) + (1 if ev.spec.n_bands else 0))
             last[r] = (micro, g_at, ev.n)
+            if rp.imprint is not None and ev.n >= 64 and rp.imprint[0] > 0:         # M:570: short grains / amount <= 0 pass through
+                src = g_at
+                g_at = pool_n                      # imprinted grain (grain_last keeps the grain before it, M:729)
+                pool_n += ev.n
+                imprint_rows.append((r, src, g_at, ev.n))
+                imprint_par[r] = rp.imprint
             if ev.placed:
                 ola_e.append((g_at + ev.offset, ev.start, ev.length, ev.amp))
                 max_len = max(max_len, ev.length)
@@ -269,6 +287,10 @@ def pack_chunk(plans) -> Tables:
     t.irs = np.concatenate(irs).astype(np.float64) if irs else np.zeros(0)
     t.dust_pos = np.concatenate(dust_pos).astype(np.int32) if dust_pos else np.zeros(0, np.int32)
     t.dust_val = np.concatenate(dust_val).astype(np.float64) if dust_val else np.zeros(0)
+    t.atoms = np.concatenate(atoms).astype(np.float64) if atoms else np.zeros((0, 4))
+    t.atom_shift = np.concatenate(atom_shift).astype(np.int32) if atom_shift else np.zeros(0, np.int32)
+    t.imprint = np.asarray(imprint_rows, np.int64).reshape(-1, 4)
+    t.imprint_par = imprint_par
     t.tilt, t.grain, t.rot = tilt.arrays(), grain.arrays(), rot.arrays()
     t.odd = np.asarray(odd, np.int64).reshape(-1, 4)
     t.pool_n, t.mono_n, t.frames, t.h_total, t.max_h = pool_n, 2 * plane + extra, frames, h_total, max_h
@@ -289,14 +311,18 @@ def merge_chunks(chunks) -> Tables:
     if len(chunks) == 1:
         return chunks[0]
     m = Tables()
-    pool_b = mono_b = frame_b = h_b = tap_b = ir_b = dust_b = olae_b = env_b = 0
+    pool_b = mono_b = frame_b = h_b = tap_b = ir_b = dust_b = olae_b = env_b = atom_b = render_b = 0
     parts = {k: [] for k in ("sy1", "sy2", "ola_r", "env_reps", "ola_e", "fir", "post", "tap_off", "tap_gain", "irs", "dust_pos", "dust_val",
-                             "odd", "out_at", "out_n", "y_at", "last", "srs")}
+                             "atoms", "atom_shift", "imprint", "imprint_par", "odd", "out_at", "out_n", "y_at", "last", "srs")}
     items = {k: [[], [], [], []] for k in ("tilt", "grain", "rot")}
     alg = {}
     for c in chunks:
         _shift(c.sy1, ("out",), pool_b)
         _shift(c.sy1, ("dust_begin",), dust_b)
+        _shift(c.sy1, ("atom_begin",), atom_b)
+        if c.imprint.size:
+            c.imprint[:, 0] += render_b
+            c.imprint[:, 1:3] += pool_b
         _shift(c.sy2, ("out", "aux"), pool_b)
         _shift(c.ola_r, ("out",), mono_b)
         _shift(c.ola_r, ("ev_begin", "ev_end"), olae_b)
@@ -335,6 +361,8 @@ def merge_chunks(chunks) -> Tables:
         dust_b += c.dust_pos.size
         olae_b += c.ola_e.size
         env_b += c.env_n
+        atom_b += c.atom_shift.size
+        render_b += len(c.post)
         m.max_h = max(m.max_h, c.max_h)
         m.max_out_n = max(m.max_out_n, c.max_out_n)
     for k in parts:

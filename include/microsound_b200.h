@@ -77,13 +77,25 @@ typedef struct {
 /* ms_spectral_create_f32 / ms_spectral_create_f64: declared below by MS_DECLARE_API */
 /* ms_spectral_run_f32 / ms_spectral_run_f64: declared below by MS_DECLARE_API */
 /* ms_spectral_destroy_f32 / ms_spectral_destroy_f64: declared below by MS_DECLARE_API */
+/* The two halves of ms_spectral_run, for stages that work on the spectra in between (spectral imprint):
+ * ms_spectral_forward leaves job i's natural-order spectrum (n complex values; for a single-signal job simply the
+ * DFT of the signal) at workspace + z_base_bytes + 2 * sizeof(REAL) * z_offset[i]  (ms_spectral_z_table, offsets in
+ * complex elements, in the order the jobs were given); ms_spectral_inverse applies the jobs' operators to whatever
+ * is there and transforms back. */
+/* ms_spectral_forward_f32/_f64, ms_spectral_inverse_f32/_f64, ms_spectral_z_table_f32/_f64: declared below */
+/* SpectralImprint.apply (main_v2.py:565-581) on the spectra of one render's grains, in event order: an exponential
+ * moving average of |X| per bin (restarted when the spectrum length changes) blended into the magnitudes, phases
+ * kept.  One record per imprinted grain, grouped by render in event order. */
+typedef struct { int64_t z; int32_t n, _pad; } ms_imprint_evt;               /* z: offset of the grain's spectrum, complex elements */
+typedef struct { int32_t ev_begin, ev_end; double amount, smooth; } ms_imprint_render;
+/* ms_imprint_f32 / ms_imprint_f64: declared below by MS_DECLARE_API */
 /* test entry: Z[k] = sum_j (a[j] + i b[j]) exp(-2 pi i jk/n), interleaved re/im, natural order */
 /* ms_fft_pair_forward_f32 / ms_fft_pair_forward_f64: declared below by MS_DECLARE_API */
 /* ms_fft_pair_workspace_bytes_f32 / ms_fft_pair_workspace_bytes_f64: declared below by MS_DECLARE_API */
 
 /* ---- transient synthesis: gen_basic (main_v2.py:219-269).  One record per event; the array lives in
  *      DEVICE memory.  The PCG64 state is numpy's `PCG64(seed).state` right after seeding. */
-enum { MS_SY_GAUSS = 0, MS_SY_DUST = 1, MS_SY_NOISE = 2, MS_SY_SKEW = 3, MS_SY_RES = 4, MS_SY_PLAIN = 5 };
+enum { MS_SY_GAUSS = 0, MS_SY_DUST = 1, MS_SY_NOISE = 2, MS_SY_SKEW = 3, MS_SY_RES = 4, MS_SY_PLAIN = 5, MS_SY_WAVELET = 6 };
 typedef struct {
     uint64_t s_hi, s_lo, i_hi, i_lo;
     int32_t n, mode;
@@ -96,12 +108,19 @@ typedef struct {
     int64_t dust_begin;       /* MS_SY_DUST: range in the impulse arrays */
     int32_t dust_count, ker_len;
     int64_t aux;              /* MS_SY_NOISE / MS_SY_SKEW: pool offset of the tilted noise */
+    int64_t atom_begin;       /* MS_SY_WAVELET: range in the atom arrays */
+    int32_t atom_count, _pad;
 } ms_synth_evt;
+/* gen_wavelet_atoms (main_v2.py:317-331) + morlet_atom (:165-170): per atom the host-drawn scalars, as
+ * (f0 / gen_sr, 1 / (sigma * gen_sr), phase, weight) and the circular shift in samples. */
+typedef struct { double f0_over_sr, inv_sigma, phase, weight; } ms_wavelet_atom;
 /* normals + closed-form modes (GAUSS, RES, PLAIN) and raw normals for NOISE/SKEW (written at `out`) */
 /* ms_synth_normal_f32 / ms_synth_normal_f64: declared below by MS_DECLARE_API */
 /* ms_synth_dust_f32 / ms_synth_dust_f64: declared below by MS_DECLARE_API */
 /* NOISE / SKEW: envelope, rectified difference and fades applied to the tilted noise at `aux` */
 /* ms_synth_tilt_finish_f32 / ms_synth_tilt_finish_f64: declared below by MS_DECLARE_API */
+/* MS_SY_WAVELET events: sum of shifted Gaussian-windowed cosines under a Hann window (float64 phase) */
+/* ms_synth_wavelet_f32 / ms_synth_wavelet_f64: declared below by MS_DECLARE_API */
 
 /* ---- overlap-add placement + ADSR (main_v2.py:742-764, 172-195) ---- */
 typedef struct {
@@ -171,6 +190,11 @@ typedef struct {
     int ms_spectral_create##SFX(const ms_spec_job* host_jobs, int njobs, const REAL* src, REAL* dst, \
     void* workspace, size_t workspace_bytes, void* stream, void** handle); \
     int ms_spectral_run##SFX(void* handle, void* stream); \
+    int ms_spectral_forward##SFX(void* handle, void* stream); \
+    int ms_spectral_inverse##SFX(void* handle, void* stream); \
+    int ms_spectral_z_table##SFX(void* handle, int64_t* host_z_offsets, size_t* z_base_bytes); \
+    int ms_imprint##SFX(const ms_imprint_evt* dev_evts, const ms_imprint_render* dev_renders, int n_renders, int max_bins, \
+    REAL* z_base, void* stream); \
     void ms_spectral_destroy##SFX(void* handle); \
     int ms_fft_pair_forward##SFX(const REAL* a, const REAL* b, int n, REAL* z_out, \
     void* workspace, size_t workspace_bytes, void* stream); \
@@ -179,6 +203,8 @@ typedef struct {
     int ms_synth_dust##SFX(const ms_synth_evt* dev_evts, int n_evts, const int32_t* dust_pos, const REAL* dust_val, \
     REAL* pool, void* stream); \
     int ms_synth_tilt_finish##SFX(const ms_synth_evt* dev_evts, int n_evts, REAL* pool, void* stream); \
+    int ms_synth_wavelet##SFX(const ms_synth_evt* dev_evts, int n_evts, const ms_wavelet_atom* atoms, const int32_t* shifts, \
+    REAL* pool, void* stream); \
     int ms_adsr_tables##SFX(const ms_ola_render* dev_reps, int n_tables, int max_out_n, REAL* envpool, void* stream); \
     int ms_overlap_add##SFX(const ms_ola_render* dev_renders, int n_renders, int max_out_n, const ms_ola_evt* dev_evts, \
     const REAL* pool, const REAL* envpool, REAL* mono, void* stream); \

@@ -365,9 +365,79 @@ def basic_transient(gen_sr, micro_ms, seed, mode, dust_density, tilt_db_per_oct,
     return x * edge_fade(n)
 
 
+def raised_cosine_window(n):
+    """M:17-21 -- symmetric Hann window (ones for n <= 1)."""
+    if n <= 1:
+        return np.ones(n, dtype=np.float64)
+    return 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n, dtype=np.float64) / (n - 1))
+
+
+WAVELET_FLOOR = 128          # M:319: wavelet grains are at least 128 samples (gen_basic: 16)
+
+
+def wavelet_atom_draws(seed, micro_ms, n, base_hz, count, spread):
+    """Scalar draws of gen_wavelet_atoms in stream order (M:322-327): per atom centre frequency, Gaussian width in
+    ms, phase and circular shift.  Shared with the product's planner tests."""
+    rng = np.random.default_rng(int(seed))
+    rows = []
+    for k in range(int(max(1, count))):
+        f0 = base_hz * (2.0 ** rng.uniform(-spread, spread))
+        sigma_ms = max(0.03, micro_ms * rng.uniform(0.04, 0.18))
+        phase = rng.uniform(0, 2 * np.pi)
+        shift = int(rng.integers(-n // 8, n // 8))
+        rows.append((f0, sigma_ms, phase, shift, 1.0 / (1 + k * 0.6)))
+    return rows
+
+
+def wavelet_atoms(gen_sr, micro_ms, seed, base_hz, count, spread):
+    """M:317-331 + morlet_atom M:165-170: a sum of circularly shifted Gaussian-windowed cosines under a Hann
+    window.  The atoms are built with gen_basic's length rule (floor 16, M:166) while the grain uses floor 128
+    (M:319): when they differ the reference's `x += atom[:n]` raises; so does this."""
+    n = grain_length(gen_sr, micro_ms, floor=WAVELET_FLOOR)
+    n_atom = grain_length(gen_sr, micro_ms, floor=16)
+    x = np.zeros(n, dtype=np.float64)
+    t = (np.arange(n_atom, dtype=np.float64) - (n_atom / 2)) / gen_sr
+    for f0, sigma_ms, phase, shift, weight in wavelet_atom_draws(seed, micro_ms, n, base_hz, count, spread):
+        sigma = max(1e-9, sigma_ms / 1000.0)
+        atom = np.exp(-0.5 * (t / sigma) ** 2) * np.cos(2 * np.pi * f0 * t + phase)
+        x += weight * np.roll(atom, shift)[:n]          # ValueError when n_atom < n, like the reference
+    return x * raised_cosine_window(n)
+
+
+class ImprintMemory:
+    """SpectralImprint (M:565-581): an exponential moving average of the grains' magnitude spectra, carried from
+    event to event of one render and restarted whenever the spectrum length changes."""
+
+    def __init__(self):
+        self.mem = None
+
+    def apply(self, x, amount, smooth):
+        n = len(x)
+        if n < 64 or amount <= 0:
+            return x
+        spec = np.fft.rfft(x)
+        mag = np.abs(spec)
+        if self.mem is None or self.mem.size != mag.size:
+            self.mem = mag.copy()
+        else:
+            self.mem = smooth * self.mem + (1.0 - smooth) * mag
+        blended = (1.0 - amount) * mag + amount * self.mem
+        return np.fft.irfft(blended * np.exp(1j * np.angle(spec)), n=n)
+
+
+def imprint_noise_floor(params, reference_audio=None):
+    """max-abs change of the rendered audio under a 1e-15 relative perturbation of the grains entering the spectral
+    imprint: the part of the reference's output that is decided by float64 rounding noise (0.0 without imprint)."""
+    if not params["spectral_imprint_on"]:
+        return 0.0
+    a = reference_audio if reference_audio is not None else render(params)[0]
+    b = render(params, jitter=1e-15)[0]
+    return float(np.max(np.abs(a - b)))
+
+
 # --------------------------------------------------------------------------- render
 _UNSUPPORTED_FLAGS = ("nl_warp_on", "cep_warp_on", "partial_lock_on", "res_bank_on", "wg_on",
-                      "event_feedback_on", "spectral_imprint_on")
+                      "event_feedback_on")
 
 
 def design_rate(base_sr, unfold):
@@ -404,7 +474,7 @@ def plan_events(params):
         amp *= rng.uniform(1.0 - spread, 1.0 + spread)
         ufac = max(1.0, float(ufac))
         sr_evt = design_rate(base_sr, ufac)
-        n = grain_length(sr_evt, micro_ms)
+        n = grain_length(sr_evt, micro_ms, floor=WAVELET_FLOOR if params["gen_mode"] == "Wavelet atoms" else 16)
         start = int(round(t0 * base_sr))
         row = dict(index=i, t0=t0, amp=float(amp), ufac=ufac, gen_sr=sr_evt, n=n,
                    cutoff_gen=cutoff_out * ufac, stretch=float(stretch), start=start,
@@ -420,14 +490,19 @@ def plan_events(params):
     return dict(base_sr=base_sr, out_n=out_n, design_sr_base=design_rate(base_sr, base_unfold), events=rows)
 
 
-def render(params, progress=None, taps=None):
-    """M:588-792.  `taps` (optional dict) receives intermediate buffers for stage-level tests."""
+def render(params, progress=None, taps=None, jitter=None):
+    """M:588-792.  `taps` (optional dict) receives intermediate buffers for stage-level tests.
+
+    `jitter` (tests only): relative size of a seeded perturbation added to every grain right before the spectral
+    imprint.  SpectralImprint keeps the PHASE of every rfft bin and replaces its magnitude by a blend with the
+    moving average; in bins the band-limit has emptied the phase is that of float64 rounding noise, so wherever
+    the average still remembers energy there (a falling `bp_cutoff` lane) the reference's output depends on
+    rounding noise.  Rendering with and without a 1e-15 jitter measures how much (imprint_noise_floor)."""
     for flag in _UNSUPPORTED_FLAGS:
         if params[flag]:
             raise NotImplementedError(f"oracle: '{flag}' is a SURVEY 8(f) 'next' row, not restated yet")
     mode = params["gen_mode"]
-    if mode in ("Crackle / corona", "Stick–slip friction", "Micro-chaos", "Wavelet atoms",
-                "IR fragment", "Image scanline"):
+    if mode in ("Crackle / corona", "Stick–slip friction", "Micro-chaos", "IR fragment", "Image scanline"):
         raise NotImplementedError(f"oracle: generator '{mode}' is a SURVEY 8(f) 'next' row")
     plan = plan_events(params)
     base_sr, out_n = plan["base_sr"], plan["out_n"]
@@ -438,9 +513,13 @@ def render(params, progress=None, taps=None):
     seed = int(params["seed"])
     micro_ms = float(params["micro_ms"])
     n_evt = len(plan["events"])
+    imprint = ImprintMemory() if params["spectral_imprint_on"] else None          # M:625
     for ev in plan["events"]:
         i = ev["index"]
-        if mode in BASIC_MODES:
+        if mode == "Wavelet atoms":
+            g = wavelet_atoms(ev["gen_sr"], micro_ms, seed + i, float(params["wav_base_hz"]), int(params["wav_count"]),
+                              float(params["wav_spread"]))
+        elif mode in BASIC_MODES:
             g = basic_transient(ev["gen_sr"], micro_ms, seed + i, mode, float(params["dust_density"]),
                                 float(params["noise_tilt"]), float(params["ring_hz"]),
                                 float(params["ring_decay_ms"]))
@@ -456,6 +535,10 @@ def render(params, progress=None, taps=None):
                                  [float(params["mb_u1"]), float(params["mb_u2"]), float(params["mb_u3"])],
                                  float(params["mb_roll"]))
         grain_last = g.copy()
+        if imprint is not None:                                                   # M:736-738 (after grain_last)
+            if jitter:
+                g = g + jitter * np.max(np.abs(g)) * np.random.default_rng(777 + i).standard_normal(g.size)
+            g = imprint.apply(g, float(params["spectral_imprint_amt"]), float(params["spectral_imprint_smooth"]))
         if ev["placed"]:
             a, o, ln = ev["start"], ev["offset"], ev["length"]
             mix[a:a + ln] += ev["amp"] * g[o:o + ln]

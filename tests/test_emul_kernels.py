@@ -116,3 +116,18 @@ def test_pooled_planning_matches_in_process(emul, monkeypatch):
     for a, b, c in zip(one, pooled, streamed):
         assert a.shape == b.shape and np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))) < 1e-6
         assert a.shape == c.shape and np.max(np.abs(a.astype(np.float64) - c.astype(np.float64))) < 1e-6
+
+
+@pytest.mark.parametrize("name", list(K.PRESET_LIKE))
+def test_preset_rows_wavelet_atoms_and_imprint(emul, name):
+    """SURVEY 8(f) rows now accelerated: the wavelet-atom generator and the spectral imprint (sequential across the
+    events of a render), on shortened versions of the shipped presets that need nothing else."""
+    p = K.preset_like(name)
+    p["out_dur_s"] = 1.2
+    K.check_render(emul, p, "f64")
+
+
+def test_imprint_restarts_when_the_grain_length_changes(emul):
+    p = K.preset_like("soft_ellipse_memory")
+    p["out_dur_s"], p["bp_unfold"], p["grains_per_sec"] = 1.0, "0:25, 0.5:25, 0.51:31, 1:31", 20.0
+    K.check_render(emul, p, "f64")

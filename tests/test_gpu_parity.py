@@ -109,6 +109,19 @@ def test_render_every_generator_with_events(cuda_dev, mode):
     K.check_render(cuda_dev, p, "auto")
 
 
+@pytest.mark.parametrize("name", list(K.PRESET_LIKE))
+def test_render_preset_rows_wavelet_atoms_and_imprint(cuda_dev, name):
+    """SURVEY 8(f) rows accelerated so far (wavelet-atom generator, spectral imprint): full-length (8 s) versions of
+    the shipped presets that need nothing else, against the oracle and against the reference's golden fixture."""
+    p = K.preset_like(name)
+    K.check_render(cuda_dev, p, "auto")
+    p["out_dur_s"] = 2.0
+    out, _ = engine.render(p, device=cuda_dev)
+    g = np.load(os.path.join(GOLDEN, "next_rows.npz"))
+    floor = O.imprint_noise_floor(p)
+    assert np.max(np.abs(out[::4] - g["render_" + name])) < K.MAX_ABS_TOL + 4.0 * floor, name
+
+
 def test_render_edge_cases(cuda_dev):
     W = configs.with_defaults
     cases = [

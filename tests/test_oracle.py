@@ -120,3 +120,45 @@ def test_ir_loader_matches_shipped_files():
     for f in sorted(os.listdir(d)):
         a = ref_loader.load_ir_wav(os.path.join(d, f))
         assert a.ndim == 1 and abs(np.max(np.abs(a)) - 0.9) < 1e-12
+
+
+# ---------------------------------------------------------------- SURVEY 8(f) rows accelerated so far
+def test_golden_next_rows():
+    import kernel_checks as K
+    g = _g("next_rows.npz")
+    assert np.max(np.abs(O.wavelet_atoms(1_200_000, 1.6, 4242, 1800, 10, 0.9) - g["wavelet"])) < TOL
+    assert np.max(np.abs(O.wavelet_atoms(1_200_000, 0.11, 7, 2400, 3, 0.6) - g["wavelet_floor"])) < TOL
+    imp, at, out = O.ImprintMemory(), 0, []
+    for n in (400, 400, 400, 401, 401, 63, 400):
+        out.append(imp.apply(g["imprint_in"][at:at + n].copy(), 0.35, 0.9))
+        at += n
+    assert np.max(np.abs(np.concatenate(out) - g["imprint_out"])) < TOL
+    for name in K.PRESET_LIKE:
+        p = K.preset_like(name)
+        p["out_dur_s"] = 2.0
+        audio, _ = O.render(p)
+        assert np.max(np.abs(audio[::4] - g["render_" + name])) < TOL, name
+
+
+def test_wavelet_grain_shorter_than_its_atoms_fails_like_the_reference():
+    # 128-sample floor for the grain (main_v2.py:319) but 16 for the atoms (:166): `x += atom[:n]` cannot broadcast
+    with pytest.raises(ValueError):
+        O.wavelet_atoms(48000, 1.0, 1, 2400, 2, 0.5)
+    from audio_suite_b200 import plan as P
+    with pytest.raises(ValueError):
+        P.plan_render(configs.with_defaults(gen_mode="Wavelet atoms", time_unfold=1.0, micro_ms=1.0))
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["opal_airfold", "opal_oval_breath", "basinski_melodic_loop", "basinski_oval_decay",
+                                  "soft_ellipse_memory"])
+def test_oracle_matches_reference_on_shipped_presets(name):
+    """The shipped presets that need only accelerated rows, merged over the factory defaults the way on_load_preset
+    does (main_v2.py:1286-1291), full 8 s renders."""
+    import json
+    ref = ref_loader.load()
+    path = os.path.join(ref_loader.REFERENCE_ROOT, "microsound_0.2.1", "presets", name + ".json")
+    p = configs.with_defaults(json.load(open(path)))
+    a, ma = ref.render(p)
+    b, mb = O.render(p)
+    assert np.max(np.abs(a - b)) < TOL and np.max(np.abs(ma["grain_last"] - mb["grain_last"])) < TOL
