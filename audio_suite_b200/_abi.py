@@ -22,7 +22,7 @@ class BandEdge(C.Structure):
 
 class SpecOp(C.Structure):
     _fields_ = [("kind", C.c_int32), ("n_bands", C.c_int32), ("lp_on", C.c_int32), ("stretch_on", C.c_int32),
-                ("df", C.c_double), ("factor", C.c_double), ("alpha", C.c_double),
+                ("df", C.c_double), ("factor", C.c_double), ("alpha", C.c_double), ("warp_exp", C.c_double),
                 ("lp", BandEdge), ("mb", BandEdge * 3)]
 
 
@@ -43,6 +43,11 @@ class SynthEvt(C.Structure):
                 ("ring_decay", C.c_double), ("env_decay", C.c_double),
                 ("dust_begin", C.c_int64), ("dust_count", C.c_int32), ("ker_len", C.c_int32), ("aux", C.c_int64),
                 ("atom_begin", C.c_int64), ("atom_count", C.c_int32), ("_pad", C.c_int32)]
+
+
+class PlockEvt(C.Structure):
+    _fields_ = [("z", C.c_int64), ("scratch", C.c_int64), ("n", C.c_int32), ("top_n", C.c_int32), ("neigh", C.c_int32),
+                ("_pad", C.c_int32), ("factor", C.c_double), ("pre", SpecOp)]
 
 
 class ImprintEvt(C.Structure):
@@ -101,6 +106,7 @@ _STAGES = {
     "ms_spectral_inverse": (_I, [_P, _P]),
     "ms_spectral_z_table": (_I, [_P, _P, C.POINTER(C.c_size_t)]),
     "ms_imprint": (_I, [_P, _P, _I, _I, _P, _P]),
+    "ms_partial_lock": (_I, [_P, _I, _P, _P, _P]),
     "ms_spectral_destroy": (None, [_P]),
     "ms_fft_pair_forward": (_I, [_P, _P, _I, _P, _P, _Z, _P]),
     "ms_fft_pair_workspace_bytes": (_Z, [_I]),

@@ -2,6 +2,8 @@
 // Included by ms_lib.cu (nvcc, product) and by tests/host_emul (g++, block emulator).
 
 static_assert(sizeof(ms_band_edge) == sizeof(BandEdge), "ABI mirror of BandEdge");
+static_assert(sizeof(ms_spec_op) == sizeof(SpecOp) && offsetof(ms_spec_op, lp) == offsetof(SpecOp, lp) &&
+              offsetof(ms_spec_op, warp_exp) == offsetof(SpecOp, warp_exp), "ABI mirror of SpecOp");
 
 static inline size_t ms_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -69,7 +71,7 @@ extern "C" int MS_API(ms_spectral_create)(const ms_spec_job* in, int njobs, cons
             SpecOp& op = J.op[w];
             const ms_spec_op& so = s.op[w];
             op.kind = so.kind; op.n_bands = so.n_bands; op.lp_on = so.lp_on; op.stretch_on = so.stretch_on;
-            op.df = so.df; op.factor = so.factor; op.alpha = so.alpha;
+            op.df = so.df; op.factor = so.factor; op.alpha = so.alpha; op.warp_exp = so.warp_exp;
             copy_edge(op.lp, so.lp);
             for (int b = 0; b < 3; ++b) copy_edge(op.mb[b], so.mb[b]);
         }

@@ -32,16 +32,17 @@ struct BandEdge {
     int _pad;
 };
 
-struct SpecOp {
+struct SpecOp {             // same layout as ms_spec_op (include/microsound_b200.h); asserted in ms_fft_api.inl
     int kind;              // OP_*
     int n_bands;           // 0: no multiband stage; else 3
     int lp_on;             // low-pass stage present
     int stretch_on;        // spectral stretch present
     double df;             // bin spacing in Hz: 1.0 / (n * (1.0 / sr))
     double factor;         // stretch factor
+    double alpha;          // OP_TILT: shape = max(k,1)^alpha ;  OP_ROT: theta (0.9 * width)
+    double warp_exp;       // OP_GRAIN: 1 / power of fft_warp_power (0: none)
     BandEdge lp;           // low-pass described as a band with only a falling skirt
     BandEdge mb[3];
-    double alpha;          // OP_TILT: shape = max(k,1)^alpha ;  OP_ROT: theta (0.9 * width)
 };
 
 
@@ -131,6 +132,31 @@ MS_DEV cpx split_bin(const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired
     if (sel == 0) return mk((real)0.5 * (p.x + q.x), (real)0.5 * (p.y - q.y));
     return mk((real)0.5 * (p.y + q.y), (real)0.5 * (q.x - p.x));
 }
+// low-passed spectrum at integer bin i, then the optional power warp (fft_warp_power, main_v2.py:103-115): bin i of
+// the warped spectrum is the low-passed one interpolated at (i / kmax) ** (1 / power) * kmax (zero beyond the last bin).
+MS_DEV cpx lp_bin(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired) {
+    return c_scale(split_bin(Z, n, i, sel, paired), lp_weight(op, i));
+}
+// (out of line: the pow() and the second gather stay out of the register budget of the common, unwarped path)
+MS_DEV_NOINLINE cpx warp_bin_on(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired) {
+    const int kmax = n >> 1;
+    const double km = kmax < 1 ? 1.0 : (double)kmax;
+    const double pos = pow((double)i / km, op.warp_exp) * km;
+    if (pos > (double)kmax) return c_zero();
+    int i0 = (int)pos;
+    real fr = (real)(pos - (double)i0);
+    if (i0 >= kmax) { i0 = kmax; fr = (real)0.; }
+    cpx y = lp_bin(op, Z, n, i0, sel, paired);
+    if (fr != (real)0.) {
+        const cpx v1 = lp_bin(op, Z, n, i0 + 1, sel, paired);
+        y = mk(y.x + (v1.x - y.x) * fr, y.y + (v1.y - y.y) * fr);
+    }
+    return y;
+}
+MS_DEV cpx warp_bin(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired) {
+    if (op.warp_exp == 0.0) return lp_bin(op, Z, n, i, sel, paired);
+    return warp_bin_on(op, Z, n, i, sel, paired);
+}
 // What irfft() would be handed for one signal at folded bin kk (0 <= kk <= n/2):
 // low-pass -> stretch (two-point gather at kk/factor, zero beyond the last bin) -> multiband weights,
 // or the tilt / rotation multipliers.
@@ -150,16 +176,16 @@ MS_DEV cpx op_value(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int kk, i
     }
     cpx y;
     if (!op.stretch_on) {
-        y = c_scale(split_bin(Z, n, kk, sel, paired), lp_weight(op, kk));
+        y = warp_bin(op, Z, n, kk, sel, paired);
     } else {
         const double pos = (double)kk / fmax(1e-12, op.factor);
         if (pos > (double)kmax) return c_zero();
         int i0 = (int)pos;
         real fr = (real)(pos - (double)i0);
         if (i0 >= kmax) { i0 = kmax; fr = (real)0.; }
-        y = c_scale(split_bin(Z, n, i0, sel, paired), lp_weight(op, i0));
+        y = warp_bin(op, Z, n, i0, sel, paired);
         if (fr != (real)0.) {
-            cpx v1 = c_scale(split_bin(Z, n, i0 + 1, sel, paired), lp_weight(op, i0 + 1));
+            cpx v1 = warp_bin(op, Z, n, i0 + 1, sel, paired);
             y = mk(y.x + (v1.x - y.x) * fr, y.y + (v1.y - y.y) * fr);
         }
     }

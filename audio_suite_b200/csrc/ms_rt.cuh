@@ -14,6 +14,7 @@
   #include <cstring>
   #include <algorithm>
   #define MS_DEV inline
+  #define MS_DEV_NOINLINE static __attribute__((noinline))
   #define MS_HD inline
   #define MS_RESTRICT
   struct float2 { float x, y; };
@@ -36,6 +37,7 @@
 #else
   #include <cuda_runtime.h>
   #define MS_DEV __device__ __forceinline__
+  #define MS_DEV_NOINLINE static __device__ __noinline__
   #define MS_HD __host__ __device__ __forceinline__
   #define MS_RESTRICT __restrict__
   struct Ctx {

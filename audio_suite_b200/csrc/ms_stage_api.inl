@@ -12,6 +12,9 @@ struct SynthDustK { static constexpr int MAXT = 256;
 struct SynthWaveletK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const SynthEvt* e, const WaveletAtom* a, const int* sh, real* pool, const Ctx& c) { synth_wavelet_body(e, a, sh, pool, c); } };
+struct PartialLockK { static constexpr int MAXT = PLOCK_NTHR;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const PlockEvt* e, cpx* z, real* scratch, const Ctx& c) { partial_lock_body(e, z, scratch, c); } };
 struct ImprintK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const ImprintEvt* e, const ImprintRender* r, cpx* z, const Ctx& c) { imprint_body(e, r, z, c); } };
@@ -63,6 +66,14 @@ extern "C" int MS_API(ms_adsr_tables)(const ms_ola_render* reps, int n_tables, i
 extern "C" int MS_API(ms_synth_wavelet)(const ms_synth_evt* evts, int n, const ms_wavelet_atom* atoms, const int32_t* shifts,
                                 real* pool, void* stream) {
     MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthWaveletK>(mk_dim(64, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, atoms, (const int*)shifts, pool)) return -1; })
+    return 0;
+}
+extern "C" int MS_API(ms_partial_lock)(const ms_plock_evt* evts, int n, real* z_base, real* scratch, void* stream) {
+    for (int x0 = 0; x0 < n; x0 += 1 << 20) {
+        const int cnt = std::min(1 << 20, n - x0);
+        if (ms_launch<PartialLockK>(mk_dim((unsigned)cnt, 1), PLOCK_NTHR, PLOCK_NTHR * sizeof(int), (ms_stream_t)stream,
+                                    evts + x0, (cpx*)z_base, scratch)) return -1;
+    }
     return 0;
 }
 extern "C" int MS_API(ms_imprint)(const ms_imprint_evt* evts, const ms_imprint_render* renders, int n_renders, int max_bins,

@@ -227,3 +227,70 @@ MS_DEV void imprint_body(const ImprintEvt* MS_RESTRICT evts, const ImprintRender
         prev_bins = bins;
     }
 }
+
+// ---- partial lock (partial_lock_stretch, main_v2.py:130-148) ------------------------------------------------------
+// One CTA per grain.  (1) W[k] = low-pass / power-warp of the grain's spectrum and its magnitude, for every rfft bin;
+// (2) the magnitude of the top_n-th strongest bin (k >= 1) by bisection on the bit pattern of the non-negative
+// magnitudes (monotone), a block-wide count per step; (3) Y = 0.12 W, then every selected bin adds
+// W[k] * (1 - |d| / (neigh + 1)) at round-half-even(k * factor) + d; (4) Y replaces the spectrum's bins 0..n/2.
+typedef ms_plock_evt PlockEvt;
+#define PLOCK_NTHR 256
+MS_DEV int plock_block_sum(int v, int* red, const Ctx& c) {
+    red[c.tid] = v;
+    c.sync();
+    for (int s = c.nthr >> 1; s > 0; s >>= 1) {
+        if (c.tid < s) red[c.tid] += red[c.tid + s];
+        c.sync();
+    }
+    const int r = red[0];
+    c.sync();
+    return r;
+}
+MS_DEV void partial_lock_body(const PlockEvt* MS_RESTRICT evts, cpx* zbase, real* scratch, const Ctx& c) {
+    const PlockEvt& E = evts[c.bx];
+    const SpecOp& op = *(const SpecOp*)&E.pre;
+    const int n = E.n, bins = n / 2 + 1;
+    cpx* Z = zbase + E.z;
+    cpx* W = (cpx*)(scratch + E.scratch);
+    real* M = (real*)(W + bins);
+    int* red = (int*)c.smem;
+    for (int k = c.tid; k < bins; k += c.nthr) {
+        const cpx w = warp_bin(op, Z, n, k, 0, 0);
+        W[k] = w;
+        M[k] = (real)hypot((double)w.x, (double)w.y);
+    }
+    c.sync();
+    const int want = E.top_n < bins - 1 ? E.top_n : bins - 1;
+    // largest threshold T (as bits of a double) such that count(M[k] >= T, k >= 1) >= want
+    unsigned long long lo = 0ull, hi = 0x7ff0000000000000ull;          // count(lo) >= want always; hi = +inf: count = 0
+    while (hi - lo > 1ull) {
+        const unsigned long long mid = lo + ((hi - lo) >> 1);
+        union { unsigned long long u; double d; } cv; cv.u = mid;
+        int cnt = 0;
+        for (int k = 1 + c.tid; k < bins; k += c.nthr) cnt += ((double)M[k] >= cv.d) ? 1 : 0;
+        if (plock_block_sum(cnt, red, c) >= want) lo = mid; else hi = mid;
+    }
+    union { unsigned long long u; double d; } th; th.u = lo;
+    for (int k = c.tid; k < bins; k += c.nthr) Z[k] = c_scale(W[k], (real)0.12);
+    c.sync();
+    if (want > 0) {
+        const int nb = E.neigh;
+        const real inv = (real)1.0 / (real)(nb + 1);
+        for (int k = 1 + c.tid; k < bins; k += c.nthr) {
+            if ((double)M[k] < th.d) continue;
+            const int k2 = (int)rint((double)k * E.factor);                 // Python round(): half to even
+            if (k2 < 1 || k2 >= bins) continue;
+            const cpx x = W[k];
+            for (int d = -nb; d <= nb; ++d) {
+                const int kk = k2 + d;
+                if (kk < 1 || kk >= bins) continue;
+                const real w = (real)1.0 - (real)(d < 0 ? -d : d) * inv;
+#ifdef MS_HOST_EMUL
+                Z[kk].x += x.x * w; Z[kk].y += x.y * w;
+#else
+                atomicAdd(&Z[kk].x, x.x * w); atomicAdd(&Z[kk].y, x.y * w);    // several strong bins may land on one
+#endif
+            }
+        }
+    }
+}

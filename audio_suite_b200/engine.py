@@ -248,6 +248,28 @@ class BatchRenderer:
         self.tilt_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.tilt), self.pool, self.pool)
         self.grain_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.grain), self.pool, self.pool)
         self.rot_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.rot), self.mono, self.mono)
+        # partial lock: single-signal jobs from the event's raw transient; low-pass / warp are evaluated by the
+        # lock kernel on the forward spectrum, the inverse applies what follows it (multiband)
+        self.plock_stage = None
+        if t.plock is not None and len(t.plock[0]):
+            rows, factor, pre, post = t.plock
+            jobs = np.zeros(len(rows), np.dtype(_abi.SpecJob))
+            jobs["n"], jobs["in_a"], jobs["out_a"], jobs["in_b"], jobs["out_b"] = rows[:, 2], rows[:, 0], rows[:, 1], -1, -1
+            raw = jobs.view(np.uint8).reshape(len(rows), jobs.dtype.itemsize)
+            op0 = jobs.dtype.fields["op"][1]
+            raw[:, op0:op0 + post.shape[1]] = post
+            self.plock_stage = _SpectralStage(dev, self.api, jobs, self.pool, self.pool)
+            zbase, zoffs = self.plock_stage.z_table()
+            ev = np.zeros(len(rows), np.dtype(_abi.PlockEvt))
+            bins = rows[:, 2] // 2 + 1
+            scr = np.concatenate([[0], np.cumsum((3 * bins + 3) // 4 * 4)])       # 16-byte aligned complex scratch per grain
+            ev["z"], ev["scratch"], ev["n"], ev["top_n"], ev["neigh"], ev["factor"] = zoffs, scr[:-1], rows[:, 2], rows[:, 3], rows[:, 4], factor
+            rawe = ev.view(np.uint8).reshape(len(rows), ev.dtype.itemsize)
+            p0 = ev.dtype.fields["pre"][1]
+            rawe[:, p0:p0 + pre.shape[1]] = pre
+            self.d_plock_evt, self.n_plock = dev.upload(ev), len(rows)
+            self.plock_scratch = dev.empty(int(scr[-1]), real)
+            self.plock_zbase = zbase
         # spectral imprint: single-signal jobs (Z = the grain's DFT), forward -> per-render moving average -> inverse
         self.imprint_stage, self.n_imprint_renders = None, 0
         if len(t.imprint):
@@ -310,6 +332,12 @@ class BatchRenderer:
                 mark("tilt_spectral")
             self.grain_stage.run()
             mark("grain_spectral")
+            if self.plock_stage is not None:
+                self.plock_stage.forward()
+                zptr = C.c_void_p(dev.ptr(self.plock_stage.ws).value + self.plock_zbase)
+                _check(dev, lib.ms_partial_lock(dev.ptr(self.d_plock_evt), self.n_plock, zptr, dev.ptr(self.plock_scratch), st))
+                self.plock_stage.inverse()
+                mark("partial_lock")
             if self.imprint_stage is not None:
                 self.imprint_stage.forward()
                 zptr = C.c_void_p(dev.ptr(self.imprint_stage.ws).value + self.imprint_zbase)
@@ -353,7 +381,7 @@ class BatchRenderer:
         return m
 
     def close(self):
-        for s in (self.tilt_stage, self.grain_stage, self.rot_stage, self.imprint_stage):
+        for s in (self.tilt_stage, self.grain_stage, self.rot_stage, self.imprint_stage, self.plock_stage):
             if s is not None:
                 s.close()
         if self.fir_handle:

@@ -26,7 +26,7 @@ MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET
 WAVELET_FLOOR = 128                 # M:319
 _MODE_ID = {m: i for i, m in enumerate(BASIC_MODES)}
 
-_NEXT_ROW_FLAGS = ("nl_warp_on", "cep_warp_on", "partial_lock_on", "res_bank_on", "wg_on", "event_feedback_on")
+_NEXT_ROW_FLAGS = ("cep_warp_on", "res_bank_on", "wg_on", "event_feedback_on")
 _NEXT_ROW_MODES = ("Crackle / corona", "Stick–slip friction", "Micro-chaos", "IR fragment", "Image scanline")
 
 
@@ -160,16 +160,23 @@ def bin_spacing(n, sr):
     return 1.0 / (n * (1.0 / sr))
 
 
-def grain_spec_op(params, gen_sr, n, cutoff_gen, stretch):
-    """Spectral operator of one event: lowpass_fft -> fft_partial_stretch -> unfold_multiband
-    (M:690-727), or None when every stage is an identity."""
+def grain_spec_op(params, gen_sr, n, cutoff_gen, stretch, pre=True, post=True, keep=False):
+    """Spectral operator of one event: lowpass_fft -> fft_warp_power -> fft_partial_stretch -> unfold_multiband
+    (M:690-727), or None when every stage is an identity (unless `keep`).  `pre` / `post` select the stages before
+    (low-pass, warp) and after (stretch, multiband) the point where partial_lock_stretch sits."""
     op = _abi.SpecOp()
     op.kind = _abi.OP_GRAIN
     op.df = bin_spacing(n, gen_sr)
     op.factor = 1.0
+    if not pre:
+        params = dict(params, bandlimit_on=False, nl_warp_on=False)
+    if not post:
+        params, stretch = dict(params, unfold_mode="Classic reinterpret"), 1.0
     if params["bandlimit_on"] and n >= 8:
         op.lp_on = 1
         op.lp = lowpass_edge(gen_sr, cutoff_gen, float(params["bandlimit_roll_hz"]))
+    if params["nl_warp_on"] and n >= 16:                               # fft_warp_power (M:103-115, called at M:694-695)
+        op.warp_exp = 1.0 / max(1e-6, float(params["nl_warp_power"]))
     stretch = float(stretch)
     if n >= 16 and not abs(stretch - 1.0) < 1e-9:
         op.stretch_on = 1
@@ -181,7 +188,7 @@ def grain_spec_op(params, gen_sr, n, cutoff_gen, stretch):
         op.n_bands = 3
         for i, ((lo, hi), u) in enumerate(zip([(0.0, b1), (b1, b2), (b2, b3)], us)):
             op.mb[i] = bandpass_edge(gen_sr, lo * u, hi * u, roll)
-    if not (op.lp_on or op.stretch_on or op.n_bands):
+    if not (op.lp_on or op.stretch_on or op.n_bands or op.warp_exp) and not keep:
         return None
     return op
 
@@ -213,6 +220,7 @@ class EventPlan:
     length: int = 0
     placed: bool = False
     spec: Optional[object] = None           # _abi.SpecOp or None
+    plock: Optional[tuple] = None           # (factor, top_n, neigh, pre-operator) when partial_lock_stretch is active
     tilt: Optional[object] = None           # _abi.SpecOp for the tilted-noise modes
     dust_pos: Optional[np.ndarray] = None   # sorted unique impulse positions (int32)
     dust_val: Optional[np.ndarray] = None   # float64 values (last write wins, M:243)
@@ -317,7 +325,16 @@ def plan_render(params) -> RenderPlan:
                 ev.offset = int(rng.integers(0, max(1, min(max_off, n))))
             ev.length = max(0, min(out_n - ev.start, n - ev.offset))
             ev.placed = ev.length > 0
-        ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, ev.stretch)
+        if params["partial_lock_on"]:
+            # M:699-702: partial_lock_stretch REPLACES fft_partial_stretch; it is the identity for n < 64 or a factor of 1
+            if n >= 64 and not abs(ev.stretch - 1.0) < 1e-9:
+                ev.plock = (ev.stretch, int(params["pl_top_n"]), int(params["pl_neigh"]),
+                            grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, post=False, keep=True))
+                ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, pre=False, keep=True)
+            else:
+                ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0)
+        else:
+            ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, ev.stretch)
         ev.fade = max(8, int(0.01 * n))
         if mode == MODE_GAUSS:
             ev.sigma = max(1, int(0.0025 * n))

@@ -90,6 +90,7 @@ class Tables:
     dust_val: np.ndarray = None
     atoms: np.ndarray = None        # wavelet atoms, float64 [N, 4]
     atom_shift: np.ndarray = None   # int32 [N]
+    plock: tuple = None             # (rows int64 [N, 5] = src, dst, n, top_n, neigh ; factor [N] ; pre ops [N, B] ; post ops [N, B])
     imprint: np.ndarray = None      # rows per imprinted event, in event order per render: render, pool_in, pool_out, n
     imprint_par: np.ndarray = None  # per render: amount, smooth (nan when off)
     tilt: tuple = None          # (n, src, dst, ops)
@@ -121,6 +122,7 @@ def pack_chunk(plans) -> Tables:
     dust_pos, dust_val, n_dust = [], [], 0
     atoms, atom_shift, n_atoms = [], [], 0
     imprint_rows, imprint_par = [], np.full((R, 2), np.nan)
+    pl_rows, pl_factor, pl_pre, pl_post = [], [], [], []
     tap_off, tap_gain, n_taps = [], [], 0
     irs, ir_index, n_ir = [], {}, 0
     pool_n = mono_n = h_total = max_h = 0
@@ -171,11 +173,20 @@ def pack_chunk(plans) -> Tables:
             sy2[e] = common + (mode2,) + tail + (micro, ev.f_over_sr, 1.0 / ev.fade, ev.ring_decay, ev.env_decay,
                                                   0, 0, ev.ker_len, aux2, 0, 0, 0)
             g_at = micro
-            if ev.spec is not None:
+            if ev.plock is not None:
+                g_at = pool_n
+                pool_n += ev.n
+                pl_rows.append((micro, g_at, ev.n, ev.plock[1], ev.plock[2]))
+                pl_factor.append(ev.plock[0])
+                pl_pre.append(bytes(ev.plock[3]))
+                pl_post.append(bytes(ev.spec))
+                alg["grain_spectral"] += 2 * ev.n * (1 + int(ev.plock[3].lp_on) + (1 if ev.plock[3].warp_exp else 0) + (1 if ev.spec.n_bands else 0))
+            elif ev.spec is not None:
                 g_at = pool_n
                 pool_n += ev.n
                 grain.add(ev.n, micro, g_at, ev.spec)
-                alg["grain_spectral"] += 2 * ev.n * (int(ev.spec.lp_on) + int(ev.spec.stretch_on) + (1 if ev.spec.n_bands else 0))
+                alg["grain_spectral"] += 2 * ev.n * (int(ev.spec.lp_on) + int(ev.spec.stretch_on) + (1 if ev.spec.n_bands else 0)
+                                                     + (1 if ev.spec.warp_exp else 0))
             last[r] = (micro, g_at, ev.n)
             if rp.imprint is not None and ev.n >= 64 and rp.imprint[0] > 0:         # M:570: short grains / amount <= 0 pass through
                 src = g_at
@@ -289,6 +300,10 @@ def pack_chunk(plans) -> Tables:
     t.dust_val = np.concatenate(dust_val).astype(np.float64) if dust_val else np.zeros(0)
     t.atoms = np.concatenate(atoms).astype(np.float64) if atoms else np.zeros((0, 4))
     t.atom_shift = np.concatenate(atom_shift).astype(np.int32) if atom_shift else np.zeros(0, np.int32)
+    npl = len(pl_rows)
+    t.plock = (np.asarray(pl_rows, np.int64).reshape(-1, 5), np.asarray(pl_factor, np.float64),
+               np.frombuffer(b"".join(pl_pre), np.uint8).reshape(npl, _SPEC_OP_BYTES) if npl else np.zeros((0, _SPEC_OP_BYTES), np.uint8),
+               np.frombuffer(b"".join(pl_post), np.uint8).reshape(npl, _SPEC_OP_BYTES) if npl else np.zeros((0, _SPEC_OP_BYTES), np.uint8))
     t.imprint = np.asarray(imprint_rows, np.int64).reshape(-1, 4)
     t.imprint_par = imprint_par
     t.tilt, t.grain, t.rot = tilt.arrays(), grain.arrays(), rot.arrays()
@@ -315,6 +330,7 @@ def merge_chunks(chunks) -> Tables:
     parts = {k: [] for k in ("sy1", "sy2", "ola_r", "env_reps", "ola_e", "fir", "post", "tap_off", "tap_gain", "irs", "dust_pos", "dust_val",
                              "atoms", "atom_shift", "imprint", "imprint_par", "odd", "out_at", "out_n", "y_at", "last", "srs")}
     items = {k: [[], [], [], []] for k in ("tilt", "grain", "rot")}
+    pl_parts = [[], [], [], []]
     alg = {}
     for c in chunks:
         _shift(c.sy1, ("out",), pool_b)
@@ -323,6 +339,10 @@ def merge_chunks(chunks) -> Tables:
         if c.imprint.size:
             c.imprint[:, 0] += render_b
             c.imprint[:, 1:3] += pool_b
+        if c.plock[0].size:
+            c.plock[0][:, 0:2] += pool_b
+        for i in range(4):
+            pl_parts[i].append(c.plock[i])
         _shift(c.sy2, ("out", "aux"), pool_b)
         _shift(c.ola_r, ("out",), mono_b)
         _shift(c.ola_r, ("ev_begin", "ev_end"), olae_b)
@@ -369,6 +389,7 @@ def merge_chunks(chunks) -> Tables:
         setattr(m, k, np.concatenate(parts[k]))
     for k in items:
         setattr(m, k, tuple(np.concatenate(x) for x in items[k]))
+    m.plock = tuple(np.concatenate(x) for x in pl_parts)
     m.pool_n, m.mono_n, m.frames, m.h_total, m.alg, m.env_n = pool_b, mono_b, frame_b, h_b, alg, env_b
     return m
 

@@ -57,6 +57,8 @@ typedef struct {
     double df;               /* bin spacing, Hz: 1.0 / (n * (1.0 / sr)) */
     double factor;           /* stretch factor */
     double alpha;            /* MS_OP_TILT exponent, MS_OP_ROT angle */
+    double warp_exp;         /* fft_warp_power (main_v2.py:103-115): 1 / max(1e-6, power); 0 = no warp.  Order of the
+                                grain operator: low-pass -> power warp -> stretch -> multiband */
     ms_band_edge lp;
     ms_band_edge mb[3];
 } ms_spec_op;
@@ -89,6 +91,19 @@ typedef struct {
 typedef struct { int64_t z; int32_t n, _pad; } ms_imprint_evt;               /* z: offset of the grain's spectrum, complex elements */
 typedef struct { int32_t ev_begin, ev_end; double amount, smooth; } ms_imprint_render;
 /* ms_imprint_f32 / ms_imprint_f64: declared below by MS_DECLARE_API */
+/* partial_lock_stretch (main_v2.py:130-148) on the spectrum of one grain (single-signal job, after
+ * ms_spectral_forward): W = low-pass / power warp of the grain's spectrum (`pre`), the top_n strongest bins of W
+ * (DC excluded) are moved to round(k * factor) with a triangular spread over +-neigh bins on top of 0.12 W, and the
+ * result replaces the spectrum in place; ms_spectral_inverse (operator: multiband only) finishes.  `scratch`:
+ * offset (REAL elements) of 3 * (n/2 + 1) REALs of per-grain scratch in the `scratch` buffer. */
+typedef struct {
+    int64_t z;               /* offset of the grain's spectrum, complex elements */
+    int64_t scratch;
+    int32_t n, top_n, neigh, _pad;
+    double factor;
+    ms_spec_op pre;
+} ms_plock_evt;
+/* ms_partial_lock_f32 / ms_partial_lock_f64: declared below by MS_DECLARE_API */
 /* test entry: Z[k] = sum_j (a[j] + i b[j]) exp(-2 pi i jk/n), interleaved re/im, natural order */
 /* ms_fft_pair_forward_f32 / ms_fft_pair_forward_f64: declared below by MS_DECLARE_API */
 /* ms_fft_pair_workspace_bytes_f32 / ms_fft_pair_workspace_bytes_f64: declared below by MS_DECLARE_API */
@@ -193,6 +208,7 @@ typedef struct {
     int ms_spectral_forward##SFX(void* handle, void* stream); \
     int ms_spectral_inverse##SFX(void* handle, void* stream); \
     int ms_spectral_z_table##SFX(void* handle, int64_t* host_z_offsets, size_t* z_base_bytes); \
+    int ms_partial_lock##SFX(const ms_plock_evt* dev_evts, int n_evts, REAL* z_base, REAL* scratch, void* stream); \
     int ms_imprint##SFX(const ms_imprint_evt* dev_evts, const ms_imprint_render* dev_renders, int n_renders, int max_bins, \
     REAL* z_base, void* stream); \
     void ms_spectral_destroy##SFX(void* handle); \

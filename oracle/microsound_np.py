@@ -144,6 +144,39 @@ def spectrum_stretch(x, factor):
     return np.fft.irfft(y, n=n)
 
 
+def spectrum_power_warp(x, power):
+    """M:103-115 -- bin k of the output spectrum is the input spectrum interpolated (Re and Im separately, zeros
+    outside) at (k / kmax) ** (1 / power) * kmax."""
+    n = len(x)
+    if n < 16:
+        return x
+    spec = np.fft.rfft(x)
+    k = np.arange(spec.size, dtype=np.float64)
+    kmax = max(1.0, k[-1])
+    src = np.power(k / kmax, 1.0 / max(1e-6, float(power))) * kmax
+    warped = np.interp(src, k, spec.real, left=0.0, right=0.0) + 1j * np.interp(src, k, spec.imag, left=0.0, right=0.0)
+    return np.fft.irfft(warped, n=n)
+
+
+def partial_lock(x, factor, top_n=24, neighborhood=4):
+    """M:130-148 -- the top_n strongest rfft bins (DC excluded) are moved to round(k * factor) with a triangular
+    spread over +-neighborhood bins, on top of 12 % of the original spectrum."""
+    n = len(x)
+    factor = float(factor)
+    if n < 64 or abs(factor - 1.0) < 1e-9:
+        return x
+    spec = np.fft.rfft(x)
+    strongest = np.argsort(np.abs(spec)[1:])[-top_n:] + 1
+    moved = np.zeros_like(spec)
+    for k in strongest:
+        centre = int(round(k * factor))
+        if 1 <= centre < moved.size:
+            for d in range(-neighborhood, neighborhood + 1):
+                if 1 <= centre + d < moved.size:
+                    moved[centre + d] += spec[k] * (1.0 - abs(d) / (neighborhood + 1))
+    return np.fft.irfft(moved + 0.12 * spec, n=n)
+
+
 def multiband_unfold(x, gen_sr, bands_out_hz, unfolds, roll_hz):
     """M:492-500 -- sum of band-passed copies, band edges scaled by each band's unfold."""
     acc = None
@@ -436,7 +469,7 @@ def imprint_noise_floor(params, reference_audio=None):
 
 
 # --------------------------------------------------------------------------- render
-_UNSUPPORTED_FLAGS = ("nl_warp_on", "cep_warp_on", "partial_lock_on", "res_bank_on", "wg_on",
+_UNSUPPORTED_FLAGS = ("cep_warp_on", "res_bank_on", "wg_on",
                       "event_feedback_on")
 
 
@@ -528,7 +561,12 @@ def render(params, progress=None, taps=None, jitter=None):
         micro_last = g.copy()
         if params["bandlimit_on"]:
             g = fft_lowpass(g, ev["gen_sr"], ev["cutoff_gen"], roll=float(params["bandlimit_roll_hz"]))
-        g = spectrum_stretch(g, ev["stretch"])
+        if params["nl_warp_on"]:                                                  # M:694-695
+            g = spectrum_power_warp(g, float(params["nl_warp_power"]))
+        if params["partial_lock_on"]:                                             # M:699-702
+            g = partial_lock(g, ev["stretch"], int(params["pl_top_n"]), int(params["pl_neigh"]))
+        else:
+            g = spectrum_stretch(g, ev["stretch"])
         if params["unfold_mode"] != "Classic reinterpret":
             b1, b2, b3 = float(params["mb_b1"]), float(params["mb_b2"]), float(params["mb_b3"])
             g = multiband_unfold(g, ev["gen_sr"], [(0, b1), (b1, b2), (b2, b3)],

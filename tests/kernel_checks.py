@@ -224,6 +224,13 @@ PRESET_LIKE = {
     "basinski_melodic_loop": dict(gen_mode="Gaussian click", micro_ms=3.6, event_process="Poisson", grains_per_sec=4,
                                   spectral_imprint_on=True, spectral_imprint_amt=0.35, spectral_imprint_smooth=0.99,
                                   partial_stretch=0.9, er_cloud_on=False, stereo_width=0.5),
+    "micro_carillon": dict(gen_mode="Wavelet atoms", micro_ms=1.1, wav_base_hz=660, wav_count=6, wav_spread=0.15,
+                           event_process="Clustered", grains_per_sec=18, cluster_size=3, cluster_spread_ms=10,
+                           partial_lock_on=True, er_cloud_on=True, er_taps=200, er_max_ms=32),      # lock at factor 1: identity
+    "oval_glass_orbit": dict(gen_mode="Wavelet atoms", micro_ms=1.9, wav_base_hz=1400, wav_count=6, wav_spread=0.4,
+                             partial_lock_on=True, partial_stretch=1.05, event_process="Poisson", grains_per_sec=7,
+                             bp_unfold="0:28, 6:34, 14:30", bp_density="0:6, 10:9, 18:6", er_cloud_on=True, er_taps=260,
+                             er_max_ms=48, stereo_width=0.7),
     "soft_ellipse_memory": dict(gen_mode="Noise burst", micro_ms=2.2, noise_tilt=-8.0, event_process="Poisson",
                                 grains_per_sec=6, spectral_imprint_on=True, spectral_imprint_amt=0.25,
                                 spectral_imprint_smooth=0.97, partial_stretch=0.95, bp_cutoff="0:14000, 12:9000, 24:6000",

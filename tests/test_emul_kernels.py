@@ -131,3 +131,23 @@ def test_imprint_restarts_when_the_grain_length_changes(emul):
     p = K.preset_like("soft_ellipse_memory")
     p["out_dur_s"], p["bp_unfold"], p["grains_per_sec"] = 1.0, "0:25, 0.5:25, 0.51:31, 1:31", 20.0
     K.check_render(emul, p, "f64")
+
+
+@pytest.mark.parametrize("power,stretch,odd", [(1.25, 1.0, False), (0.6, 2.3, False), (3.0, 0.7, True)])
+def test_power_warp_fused_into_the_grain_operator(emul, power, stretch, odd):
+    """fft_warp_power (main_v2.py:103-115) between the low-pass and the stretch: a gather of a gather."""
+    p = configs.with_defaults(nl_warp_on=True, nl_warp_power=power, partial_stretch=stretch, event_process="Poisson",
+                              out_dur_s=0.6, grains_per_sec=20.0, gen_mode="Resonant strike", er_cloud_on=False,
+                              bp_unfold="0:25, 0.6:25.013" if odd else "")
+    K.check_render(emul, p, "f64")
+
+
+@pytest.mark.parametrize("kw", [dict(partial_stretch=1.05), dict(partial_stretch=1.0),
+                                dict(partial_stretch=0.7, pl_top_n=60, pl_neigh=9, unfold_mode="Multi-band unfold"),
+                                dict(partial_stretch=1.3, nl_warp_on=True, bandlimit_roll_hz=0.0, gen_mode="Noise burst")])
+def test_partial_lock(emul, kw):
+    """partial_lock_stretch (main_v2.py:130-148): top-N bin selection, triangular scatter, 12 % dry spectrum."""
+    base = dict(partial_lock_on=True, event_process="Poisson", out_dur_s=0.6, grains_per_sec=20.0,
+                gen_mode="Resonant strike", er_cloud_on=False)
+    base.update(kw)
+    K.check_render(emul, configs.with_defaults(base), "f64")

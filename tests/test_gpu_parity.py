@@ -122,6 +122,18 @@ def test_render_preset_rows_wavelet_atoms_and_imprint(cuda_dev, name):
     assert np.max(np.abs(out[::4] - g["render_" + name])) < K.MAX_ABS_TOL + 4.0 * floor, name
 
 
+@pytest.mark.parametrize("kw", [dict(nl_warp_on=True, nl_warp_power=1.6, partial_stretch=1.3),
+                                dict(partial_lock_on=True, partial_stretch=0.8, pl_top_n=100, pl_neigh=12),
+                                dict(partial_lock_on=True, partial_stretch=1.7, nl_warp_on=True, unfold_mode="Multi-band unfold",
+                                     spectral_imprint_on=True, gen_mode="Wavelet atoms")])
+def test_render_spectral_extras(cuda_dev, kw):
+    """SURVEY 8(f) rank 1 rows on the GPU: power warp, partial lock, imprint, combined, several events per render."""
+    base = dict(event_process="Poisson", out_dur_s=3.0, grains_per_sec=25.0, time_unfold=60.0, micro_ms=3.0,
+                gen_mode="Resonant strike", space_ir_on=True, _ir_audio=configs.synth_ir(0.2, 48000, 3))
+    base.update(kw)
+    K.check_render(cuda_dev, configs.with_defaults(base), "auto")
+
+
 def test_render_edge_cases(cuda_dev):
     W = configs.with_defaults
     cases = [
