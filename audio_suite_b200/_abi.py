@@ -114,6 +114,7 @@ _STAGES = {
     "ms_synth_dust": (_I, [_P, _I, _P, _P, _P, _P]),
     "ms_synth_tilt_finish": (_I, [_P, _I, _P, _P]),
     "ms_synth_wavelet": (_I, [_P, _I, _P, _P, _P, _P]),
+    "ms_synth_table": (_I, [_P, _I, _P, _P, _P]),
     "ms_adsr_tables": (_I, [_P, _I, _I, _P, _P]),
     "ms_overlap_add": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
     "ms_fir_workspace_bytes": (_Z, [_P, _I]),

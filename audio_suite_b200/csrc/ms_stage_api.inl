@@ -9,6 +9,9 @@ struct SynthTiltK { static constexpr int MAXT = 256;
 struct SynthDustK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const SynthEvt* e, const int* dp, const real* dv, real* pool, const Ctx& c) { synth_dust_body(e, dp, dv, pool, c); } };
+struct SynthTableK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const SynthEvt* e, const real* dv, real* pool, const Ctx& c) { synth_table_body(e, dv, pool, c); } };
 struct SynthWaveletK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const SynthEvt* e, const WaveletAtom* a, const int* sh, real* pool, const Ctx& c) { synth_wavelet_body(e, a, sh, pool, c); } };
@@ -61,6 +64,13 @@ extern "C" int MS_API(ms_synth_dust)(const ms_synth_evt* evts, int n, const int3
 extern "C" int MS_API(ms_adsr_tables)(const ms_ola_render* reps, int n_tables, int max_out_n, real* envpool, void* stream) {
     const unsigned gx = (unsigned)((max_out_n + OLA_TILE - 1) / OLA_TILE);
     MS_FOR_Y_CHUNKS(n_tables, { if (ms_launch<AdsrTableK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream, reps + _y0, envpool)) return -1; })
+    return 0;
+}
+extern "C" int MS_API(ms_synth_table)(const ms_synth_evt* evts, int n, const real* dval, real* pool, void* stream) {
+    for (int x0 = 0; x0 < n; x0 += 1 << 20) {
+        const int cnt = std::min(1 << 20, n - x0);
+        if (ms_launch<SynthTableK>(mk_dim((unsigned)cnt, 1), 256, 256 * sizeof(real), (ms_stream_t)stream, evts + x0, dval, pool)) return -1;
+    }
     return 0;
 }
 extern "C" int MS_API(ms_synth_wavelet)(const ms_synth_evt* evts, int n, const ms_wavelet_atom* atoms, const int32_t* shifts,

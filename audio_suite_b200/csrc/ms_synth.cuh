@@ -10,7 +10,7 @@
 // shared staging buffer in stream order; the mode's closed-form terms (sine with float64 phase,
 // exponentials, fades) are applied on the way out with coalesced stores.
 
-enum { SY_GAUSS = 0, SY_DUST = 1, SY_NOISE = 2, SY_SKEW = 3, SY_RES = 4, SY_PLAIN = 5, SY_WAVELET = 6 };
+enum { SY_GAUSS = 0, SY_DUST = 1, SY_NOISE = 2, SY_SKEW = 3, SY_RES = 4, SY_PLAIN = 5, SY_WAVELET = 6, SY_IRFRAG = 7, SY_SCANLINE = 8, SY_SILENT = 9 };
 
 #define SY_C 8            // words per thread per round
 #define SY_NTHR 256
@@ -331,5 +331,58 @@ MS_DEV void synth_wavelet_body(const SynthEvt* MS_RESTRICT evts, const WaveletAt
         }
         const double hann = n > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)j / (double)(n - 1)) : 1.0;
         out[j] = (real)(acc * hann);
+    }
+}
+
+// Table generators (gen_ir_fragment main_v2.py:333-348, gen_image_scanline :350-362): a host-chosen table of M values is
+// stretched to n samples (np.interp over linspace(0,1,M) -> linspace(0,1,n)) under a Hann window; the IR fragment is then
+// peak-normalised to 0.9, the scan line smoothed ("same") by exp(-linspace(0, 5, K)).  One CTA per event.
+MS_DEV real table_sample(const real* MS_RESTRICT tab, int M, int n, int j) {
+    double v;
+    if (M < 2 || n < 2) v = (double)tab[0];
+    else {
+        const double pos = ((double)j / (double)(n - 1)) * (double)(M - 1);
+        int m = (int)pos;
+        if (m >= M - 1) m = M - 2;
+        const double fr = pos - (double)m;
+        v = (double)tab[m] + ((double)tab[m + 1] - (double)tab[m]) * fr;
+    }
+    const double hann = n > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)j / (double)(n - 1)) : 1.0;
+    return (real)(v * hann);
+}
+MS_DEV void synth_table_body(const SynthEvt* MS_RESTRICT evts, const real* MS_RESTRICT dval, real* pool, const Ctx& c) {
+    const SynthEvt E = evts[c.bx];
+    real* out = pool + E.out;
+    const int n = E.n;
+    if (E.mode == SY_SILENT) { for (int j = c.tid; j < n; j += c.nthr) out[j] = (real)0.; return; }
+    const real* tab = dval + E.dust_begin;
+    const int M = E.dust_count;
+    if (E.mode == SY_IRFRAG) {
+        real* red = (real*)c.smem;
+        real mx = (real)0.;
+        for (int j = c.tid; j < n; j += c.nthr) { const real v = table_sample(tab, M, n, j); out[j] = v; mx = r_max(mx, r_abs(v)); }
+        red[c.tid] = mx;
+        c.sync();
+        for (int s = c.nthr >> 1; s > 0; s >>= 1) { if (c.tid < s) red[c.tid] = r_max(red[c.tid], red[c.tid + s]); c.sync(); }
+        const real peak = red[0];
+        if (peak > (real)0.) {                               // normalize(x, 0.9), main_v2.py:26-29
+            const real g = (real)0.9 / peak;
+            for (int j = c.tid; j < n; j += c.nthr) out[j] *= g;
+        }
+        return;
+    }
+    // SY_SCANLINE
+    real* tmp = pool + E.aux;
+    for (int j = c.tid; j < n; j += c.nthr) tmp[j] = table_sample(tab, M, n, j);
+    c.sync();
+    const int K = E.ker_len, ctr = (K - 1) / 2;
+    const real rate = (real)5.0 / (real)(K - 1);
+    for (int j = c.tid; j < n; j += c.nthr) {
+        real acc = (real)0.;
+        for (int m = 0; m < K; ++m) {                          // np.convolve(x, ker, "same")[j] = sum_m ker[m] x[j + ctr - m]
+            const int i = j + ctr - m;
+            if (i >= 0 && i < n) acc += r_exp(-rate * (real)m) * tmp[i];
+        }
+        out[j] = acc;
     }
 }

@@ -227,7 +227,10 @@ class BatchRenderer:
         dust = sy1[sy1["mode"] == P.MODE_DUST]
         tilt = t.sy2[(t.sy2["mode"] == P.MODE_NOISE) | (t.sy2["mode"] == P.MODE_SKEW)]
         self.n_dust_evt, self.n_tilt_evt = len(dust), len(tilt)
-        normal = sy1[(sy1["mode"] != P.MODE_DUST) & (sy1["mode"] != P.MODE_WAVELET)]      # the modes that draw normals
+        normal = sy1[(sy1["mode"] != P.MODE_DUST) & (sy1["mode"] < P.MODE_WAVELET)]      # the modes that draw normals
+        tab = sy1[sy1["mode"] > P.MODE_WAVELET]                                           # IR fragment / scan line / silence
+        self.n_tab_evt = len(tab)
+        self.d_sy_tab = dev.upload(tab) if self.n_tab_evt else None
         self.n_normal_evt = len(normal)
         self.d_sy1 = dev.upload(normal) if self.n_normal_evt else None
         self.d_sy_dust = dev.upload(dust) if self.n_dust_evt else None
@@ -322,6 +325,9 @@ class BatchRenderer:
             if self.n_dust_evt:
                 _check(dev, lib.ms_synth_dust(dev.ptr(self.d_sy_dust), self.n_dust_evt, dev.ptr(self.d_dpos), dev.ptr(self.d_dval),
                                               dev.ptr(self.pool), st))
+            if self.n_tab_evt:
+                dv = dev.ptr(self.d_dval) if self.any_dust else C.c_void_p(None)
+                _check(dev, lib.ms_synth_table(dev.ptr(self.d_sy_tab), self.n_tab_evt, dv, dev.ptr(self.pool), st))
             if self.n_wav_evt:
                 _check(dev, lib.ms_synth_wavelet(dev.ptr(self.d_sy_wav), self.n_wav_evt, dev.ptr(self.d_atoms),
                                                  dev.ptr(self.d_atom_shift), dev.ptr(self.pool), st))

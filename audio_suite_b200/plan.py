@@ -22,12 +22,12 @@ from .configs import BASIC_MODES
 DESIGN_SR_CAP = 30_000_000          # M:597, M:646
 IR_TAP_CAP = 8192                   # M:443
 
-MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET = range(7)
+MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET, MODE_IRFRAG, MODE_SCANLINE, MODE_SILENT = range(10)
 WAVELET_FLOOR = 128                 # M:319
 _MODE_ID = {m: i for i, m in enumerate(BASIC_MODES)}
 
 _NEXT_ROW_FLAGS = ("cep_warp_on", "res_bank_on", "wg_on", "event_feedback_on")
-_NEXT_ROW_MODES = ("Crackle / corona", "Stick–slip friction", "Micro-chaos", "IR fragment", "Image scanline")
+_NEXT_ROW_MODES = ("Stick–slip friction", "Micro-chaos")
 
 
 # --------------------------------------------------------------------------- breakpoint lanes (M:452-482)
@@ -224,6 +224,7 @@ class EventPlan:
     tilt: Optional[object] = None           # _abi.SpecOp for the tilted-noise modes
     dust_pos: Optional[np.ndarray] = None   # sorted unique impulse positions (int32)
     dust_val: Optional[np.ndarray] = None   # float64 values (last write wins, M:243)
+    table: Optional[np.ndarray] = None      # IR fragment / image row to be resampled to n samples (float64)
     atoms: Optional[np.ndarray] = None      # wavelet atoms: float64 [count, 4] = f0/sr, 1/(sigma*sr), phase, weight
     atom_shift: Optional[np.ndarray] = None # int32 [count] circular shifts
     # mode constants (float64)
@@ -293,8 +294,16 @@ def plan_render(params) -> RenderPlan:
     spread = float(params["grain_amp_rand"])
     gmode = params["gen_mode"]
     dust_density = tilt = ring_hz = ring_decay_ms = 0.0
+    ir_audio, img_gray = params.get("_ir_audio"), params.get("_img_gray")
+    floor = 16
     if gmode == "Wavelet atoms":
-        mode = MODE_WAVELET
+        mode, floor = MODE_WAVELET, WAVELET_FLOOR
+    elif gmode == "Crackle / corona":
+        mode = MODE_DUST                       # same device kernel as the dust mode: sparse impulses * exp kernel, no fades
+    elif gmode == "IR fragment":               # M:335-337: silence of gen_basic's length when no IR is loaded
+        mode, floor = (MODE_SILENT, 16) if (ir_audio is None or np.asarray(ir_audio).size < 32) else (MODE_IRFRAG, 64)
+    elif gmode == "Image scanline":
+        mode, floor = (MODE_SILENT if img_gray is None else MODE_SCANLINE), 64
     elif gmode in _MODE_ID:
         mode = _MODE_ID[gmode]
         dust_density, tilt = float(params["dust_density"]), float(params["noise_tilt"])
@@ -317,7 +326,7 @@ def plan_render(params) -> RenderPlan:
         amp *= rng.uniform(1.0 - spread, 1.0 + spread)
         ufac = max(1.0, float(ufac))
         sr_evt = design_rate(base_sr, ufac)
-        n = grain_length(sr_evt, micro_ms, WAVELET_FLOOR if mode == MODE_WAVELET else 16)
+        n = grain_length(sr_evt, micro_ms, floor)
         ev = EventPlan(index=i, t0=t0, amp=float(amp), ufac=ufac, gen_sr=sr_evt, n=n, seed=seed + i, mode=mode,
                        cutoff_gen=cutoff_out * ufac, stretch=float(stretch), start=int(round(t0 * base_sr)))
         if ev.start < out_n:
@@ -338,8 +347,14 @@ def plan_render(params) -> RenderPlan:
         ev.fade = max(8, int(0.01 * n))
         if mode == MODE_GAUSS:
             ev.sigma = max(1, int(0.0025 * n))
+        elif gmode == "Crackle / corona":
+            _plan_crackle(ev, float(params["crackle_alpha"]), float(params["crackle_density"]), int(params["crackle_kernel"]))
         elif mode == MODE_DUST:
             _plan_dust(ev, dust_density)
+        elif mode == MODE_IRFRAG:
+            _plan_ir_fragment(ev, ir_audio)
+        elif mode == MODE_SCANLINE:
+            _plan_scanline(ev, img_gray)
         elif mode in (MODE_NOISE, MODE_SKEW):
             ev.tilt = tilt_spec_op(n, sr_evt, tilt)
             T = max(1e-6, micro_s * (0.25 if mode == MODE_NOISE else 0.2))
@@ -426,6 +441,53 @@ def _plan_wavelet(ev, micro_ms, base_hz, count, spread):
         sigma = max(1e-9, sigma_ms / 1000.0)
         atoms[k] = (f0 / ev.gen_sr, 1.0 / (sigma * ev.gen_sr), phase, 1.0 / (1 + k * 0.6))
     ev.atoms, ev.atom_shift = atoms, shifts
+
+
+def _plan_crackle(ev, alpha, density, kernel):
+    """Scalar draws of gen_crackle (M:272-279): Pareto gaps -> impulse times; amplitudes on one sample add up."""
+    rng = np.random.default_rng(int(ev.seed))
+    n = ev.n
+    times = np.cumsum(rng.pareto(alpha, int(max(8, density))))
+    times = times[times < n].astype(int)
+    dense = np.zeros(n, dtype=np.float64)
+    for ti in times:
+        dense[ti] += rng.uniform(-1, 1)
+    pos = np.unique(times)
+    ev.dust_pos, ev.dust_val = pos.astype(np.int32), dense[pos]
+    ev.ker_len = max(8, int(kernel))
+    ev.fade = 0                                  # gen_crackle has no fades
+
+
+_MONO_CACHE = {}
+
+
+def _mono64(ir):
+    hit = _MONO_CACHE.get(id(ir))
+    if hit is None or hit[0] is not ir:
+        src = np.asarray(ir).astype(np.float64)
+        if src.ndim > 1:
+            src = src.mean(axis=1)
+        if len(_MONO_CACHE) > 16:
+            _MONO_CACHE.clear()
+        _MONO_CACHE[id(ir)] = hit = (ir, src)
+    return hit[1]
+
+
+def _plan_ir_fragment(ev, ir_audio):
+    """gen_ir_fragment (M:333-348): the host draws the start and hands the 256-sample piece to the device."""
+    rng = np.random.default_rng(int(ev.seed))
+    src = _mono64(ir_audio)
+    start = int(rng.integers(0, max(1, src.size - 256)))
+    ev.table = np.ascontiguousarray(src[start:start + 256])
+
+
+def _plan_scanline(ev, img_gray):
+    """gen_image_scanline (M:350-362): the host draws the row and centres it; the device resamples and smooths."""
+    rng = np.random.default_rng(int(ev.seed))
+    h, w = img_gray.shape
+    row = img_gray[int(rng.integers(0, h)), :].astype(np.float64) / 255.0
+    ev.table = (row - row.mean()) * 2.0
+    ev.ker_len = 48
 
 
 def _plan_dust(ev, density):

@@ -160,6 +160,14 @@ def pack_chunk(plans) -> Tables:
                 dust_pos.append(ev.dust_pos)
                 dust_val.append(ev.dust_val)
                 n_dust += dust_c
+            elif ev.mode in (P.MODE_IRFRAG, P.MODE_SCANLINE):        # table rides in the impulse arrays (positions unused)
+                dust_b, dust_c = n_dust, len(ev.table)
+                dust_pos.append(np.zeros(dust_c, np.int32))
+                dust_val.append(ev.table)
+                n_dust += dust_c
+                if ev.mode == P.MODE_SCANLINE:
+                    aux2 = pool_n                                     # windowed, unsmoothed line
+                    pool_n += ev.n
             elif ev.mode in (P.MODE_NOISE, P.MODE_SKEW):
                 raw, tilted = pool_n, pool_n + ev.n
                 pool_n += 2 * ev.n
@@ -168,9 +176,11 @@ def pack_chunk(plans) -> Tables:
                 alg["tilt_spectral"] += 2 * ev.n
             common = (s_hi, s_lo, i_hi, i_lo, ev.n)
             tail = (ev.fade, ev.sigma)
-            sy1[e] = common + (ev.mode,) + tail + (out1, ev.f_over_sr, 1.0 / ev.fade, ev.ring_decay, ev.env_decay,
-                                                     dust_b, dust_c, ev.ker_len, 0, atom_b, atom_c, 0)
-            sy2[e] = common + (mode2,) + tail + (micro, ev.f_over_sr, 1.0 / ev.fade, ev.ring_decay, ev.env_decay,
+            inv_fade = 1.0 / ev.fade if ev.fade > 0 else 0.0
+            sy1[e] = common + (ev.mode,) + tail + (out1, ev.f_over_sr, inv_fade, ev.ring_decay, ev.env_decay,
+                                                     dust_b, dust_c, ev.ker_len, aux2 if ev.mode == P.MODE_SCANLINE else 0,
+                                                     atom_b, atom_c, 0)
+            sy2[e] = common + (mode2,) + tail + (micro, ev.f_over_sr, inv_fade, ev.ring_decay, ev.env_decay,
                                                   0, 0, ev.ker_len, aux2, 0, 0, 0)
             g_at = micro
             if ev.plock is not None:
@@ -334,6 +344,8 @@ def merge_chunks(chunks) -> Tables:
     alg = {}
     for c in chunks:
         _shift(c.sy1, ("out",), pool_b)
+        if c.sy1.size and pool_b:
+            c.sy1["aux"] += np.where(c.sy1["mode"] == P.MODE_SCANLINE, pool_b, 0)
         _shift(c.sy1, ("dust_begin",), dust_b)
         _shift(c.sy1, ("atom_begin",), atom_b)
         if c.imprint.size:

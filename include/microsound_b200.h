@@ -110,7 +110,8 @@ typedef struct {
 
 /* ---- transient synthesis: gen_basic (main_v2.py:219-269).  One record per event; the array lives in
  *      DEVICE memory.  The PCG64 state is numpy's `PCG64(seed).state` right after seeding. */
-enum { MS_SY_GAUSS = 0, MS_SY_DUST = 1, MS_SY_NOISE = 2, MS_SY_SKEW = 3, MS_SY_RES = 4, MS_SY_PLAIN = 5, MS_SY_WAVELET = 6 };
+enum { MS_SY_GAUSS = 0, MS_SY_DUST = 1, MS_SY_NOISE = 2, MS_SY_SKEW = 3, MS_SY_RES = 4, MS_SY_PLAIN = 5, MS_SY_WAVELET = 6,
+       MS_SY_IRFRAG = 7, MS_SY_SCANLINE = 8, MS_SY_SILENT = 9 };
 typedef struct {
     uint64_t s_hi, s_lo, i_hi, i_lo;
     int32_t n, mode;
@@ -134,6 +135,11 @@ typedef struct { double f0_over_sr, inv_sigma, phase, weight; } ms_wavelet_atom;
 /* ms_synth_dust_f32 / ms_synth_dust_f64: declared below by MS_DECLARE_API */
 /* NOISE / SKEW: envelope, rectified difference and fades applied to the tilted noise at `aux` */
 /* ms_synth_tilt_finish_f32 / ms_synth_tilt_finish_f64: declared below by MS_DECLARE_API */
+/* MS_SY_IRFRAG (gen_ir_fragment, main_v2.py:333-348), MS_SY_SCANLINE (gen_image_scanline, :350-362), MS_SY_SILENT:
+ * a short host-chosen table (dust_val[dust_begin .. +dust_count]) stretched to n samples by linear interpolation
+ * under a Hann window, then peak-normalised to 0.9 (IR fragment) or smoothed by exp(-linspace(0,5,ker_len))
+ * (scanline; `aux` = n samples of scratch in the pool).  One CTA per event. */
+/* ms_synth_table_f32 / ms_synth_table_f64: declared below by MS_DECLARE_API */
 /* MS_SY_WAVELET events: sum of shifted Gaussian-windowed cosines under a Hann window (float64 phase) */
 /* ms_synth_wavelet_f32 / ms_synth_wavelet_f64: declared below by MS_DECLARE_API */
 
@@ -219,6 +225,7 @@ typedef struct {
     int ms_synth_dust##SFX(const ms_synth_evt* dev_evts, int n_evts, const int32_t* dust_pos, const REAL* dust_val, \
     REAL* pool, void* stream); \
     int ms_synth_tilt_finish##SFX(const ms_synth_evt* dev_evts, int n_evts, REAL* pool, void* stream); \
+    int ms_synth_table##SFX(const ms_synth_evt* dev_evts, int n_evts, const REAL* dust_val, REAL* pool, void* stream); \
     int ms_synth_wavelet##SFX(const ms_synth_evt* dev_evts, int n_evts, const ms_wavelet_atom* atoms, const int32_t* shifts, \
     REAL* pool, void* stream); \
     int ms_adsr_tables##SFX(const ms_ola_render* dev_reps, int n_tables, int max_out_n, REAL* envpool, void* stream); \

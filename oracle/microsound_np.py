@@ -437,6 +437,70 @@ def wavelet_atoms(gen_sr, micro_ms, seed, base_hz, count, spread):
     return x * raised_cosine_window(n)
 
 
+def crackle_impulses(seed, n, alpha, density):
+    """Scalar draws of gen_crackle (M:272-279): Pareto-distributed gaps accumulate into impulse times; every time
+    below n gets one uniform amplitude, amplitudes landing on the same sample add up.  Returns (positions, sums)."""
+    rng = np.random.default_rng(int(seed))
+    times = np.cumsum(rng.pareto(alpha, int(max(8, density))))
+    times = times[times < n].astype(int)
+    x = np.zeros(n, dtype=np.float64)
+    for ti in times:
+        x[ti] += rng.uniform(-1, 1)
+    pos = np.unique(times)
+    return pos, x[pos]
+
+
+def crackle(gen_sr, micro_ms, seed, alpha, density, kernel):
+    """M:271-281 -- sparse impulses convolved ("same") with exp(-linspace(0, 6, max(8, kernel)))."""
+    n = grain_length(gen_sr, micro_ms)
+    x = np.zeros(n, dtype=np.float64)
+    pos, val = crackle_impulses(seed, n, alpha, density)
+    x[pos] = val
+    return np.convolve(x, np.exp(-np.linspace(0, 6, max(8, int(kernel)))), mode="same")
+
+
+def ir_fragment(ir_audio, gen_sr, micro_ms, seed):
+    """M:333-348 -- 256 samples of the loaded IR from a random start, stretched to the grain length by linear
+    interpolation, Hann-windowed, peak-normalised to 0.9; silence (gen_basic's length) when no IR is loaded."""
+    rng = np.random.default_rng(int(seed))
+    if ir_audio is None or ir_audio.size < 32:
+        return np.zeros(grain_length(gen_sr, micro_ms))
+    n = grain_length(gen_sr, micro_ms, floor=64)
+    src = ir_audio.astype(np.float64)
+    if src.ndim > 1:
+        src = src.mean(axis=1)
+    start = rng.integers(0, max(1, src.size - 256))
+    piece = src[start:start + 256]
+    x = np.interp(np.linspace(0, 1, n), np.linspace(0, 1, piece.size), piece) * raised_cosine_window(n)
+    return peak_normalize(x, 0.9)
+
+
+def image_scanline(img_gray, gen_sr, micro_ms, seed):
+    """M:350-362 -- one random row of the loaded grey image, centred, stretched to the grain length, Hann-windowed
+    and smoothed by exp(-linspace(0, 5, 48)); silence when no image is loaded."""
+    rng = np.random.default_rng(int(seed))
+    n = grain_length(gen_sr, micro_ms, floor=64)
+    if img_gray is None:
+        return np.zeros(n, dtype=np.float64)
+    h, w = img_gray.shape
+    row = img_gray[int(rng.integers(0, h)), :].astype(np.float64) / 255.0
+    row = (row - row.mean()) * 2.0
+    x = np.interp(np.linspace(0, 1, n), np.linspace(0, 1, w), row) * raised_cosine_window(n)
+    return np.convolve(x, np.exp(-np.linspace(0, 5, 48)), mode="same")
+
+
+def generator_floor(mode, params):
+    """Minimum grain length of each generator (M:221, 273, 319, 337-338, 352)."""
+    if mode == "Wavelet atoms":
+        return WAVELET_FLOOR
+    if mode == "Image scanline":
+        return 64
+    if mode == "IR fragment":
+        ir = params.get("_ir_audio")
+        return 16 if (ir is None or np.asarray(ir).size < 32) else 64
+    return 16
+
+
 class ImprintMemory:
     """SpectralImprint (M:565-581): an exponential moving average of the grains' magnitude spectra, carried from
     event to event of one render and restarted whenever the spectrum length changes."""
@@ -507,7 +571,7 @@ def plan_events(params):
         amp *= rng.uniform(1.0 - spread, 1.0 + spread)
         ufac = max(1.0, float(ufac))
         sr_evt = design_rate(base_sr, ufac)
-        n = grain_length(sr_evt, micro_ms, floor=WAVELET_FLOOR if params["gen_mode"] == "Wavelet atoms" else 16)
+        n = grain_length(sr_evt, micro_ms, floor=generator_floor(params["gen_mode"], params))
         start = int(round(t0 * base_sr))
         row = dict(index=i, t0=t0, amp=float(amp), ufac=ufac, gen_sr=sr_evt, n=n,
                    cutoff_gen=cutoff_out * ufac, stretch=float(stretch), start=start,
@@ -535,7 +599,7 @@ def render(params, progress=None, taps=None, jitter=None):
         if params[flag]:
             raise NotImplementedError(f"oracle: '{flag}' is a SURVEY 8(f) 'next' row, not restated yet")
     mode = params["gen_mode"]
-    if mode in ("Crackle / corona", "Stick–slip friction", "Micro-chaos", "IR fragment", "Image scanline"):
+    if mode in ("Stick–slip friction", "Micro-chaos"):
         raise NotImplementedError(f"oracle: generator '{mode}' is a SURVEY 8(f) 'next' row")
     plan = plan_events(params)
     base_sr, out_n = plan["base_sr"], plan["out_n"]
@@ -552,6 +616,13 @@ def render(params, progress=None, taps=None, jitter=None):
         if mode == "Wavelet atoms":
             g = wavelet_atoms(ev["gen_sr"], micro_ms, seed + i, float(params["wav_base_hz"]), int(params["wav_count"]),
                               float(params["wav_spread"]))
+        elif mode == "Crackle / corona":
+            g = crackle(ev["gen_sr"], micro_ms, seed + i, float(params["crackle_alpha"]), float(params["crackle_density"]),
+                        int(params["crackle_kernel"]))
+        elif mode == "IR fragment":
+            g = ir_fragment(params.get("_ir_audio"), ev["gen_sr"], micro_ms, seed + i)
+        elif mode == "Image scanline":
+            g = image_scanline(params.get("_img_gray"), ev["gen_sr"], micro_ms, seed + i)
         elif mode in BASIC_MODES:
             g = basic_transient(ev["gen_sr"], micro_ms, seed + i, mode, float(params["dust_density"]),
                                 float(params["noise_tilt"]), float(params["ring_hz"]),

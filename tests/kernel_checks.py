@@ -211,7 +211,13 @@ def check_render(dev, params, precision="auto"):
 def preset_like(name):
     """Parameter sets shaped like the shipped presets that need only accelerated rows (values copied from
     microsound_0.2.1/presets/<name>.json; the files themselves stay in the reference)."""
-    return configs.with_defaults(PRESET_LIKE[name])
+    p = configs.with_defaults(PRESET_LIKE[name])
+    if isinstance(p.get("_ir_audio"), str):            # what on_load_ir hands over: mono, peak 0.9 (main_v2.py:1401-1413)
+        ir = configs.synth_ir(0.25, 48000, 11, channels=1)
+        p["_ir_audio"] = ir * (0.9 / np.max(np.abs(ir)))
+    if isinstance(p.get("_img_gray"), str):
+        p["_img_gray"] = np.random.default_rng(5).integers(0, 256, (40, 300)).astype(np.uint8)
+    return p
 
 
 PRESET_LIKE = {
@@ -231,6 +237,30 @@ PRESET_LIKE = {
                              partial_lock_on=True, partial_stretch=1.05, event_process="Poisson", grains_per_sec=7,
                              bp_unfold="0:28, 6:34, 14:30", bp_density="0:6, 10:9, 18:6", er_cloud_on=True, er_taps=260,
                              er_max_ms=48, stereo_width=0.7),
+    "01_corona_glass_fog": dict(stereo_width=0.7, gen_mode="Crackle / corona", micro_ms=1.0, seed=14001, crackle_alpha=1.35,
+                                crackle_density=260.0, crackle_kernel=72, unfold_mode="Multi-band unfold", nl_warp_on=True,
+                                nl_warp_power=1.35, mb_u1=40.0, mb_u2=22.0, mb_u3=12.0, mb_roll=2500.0, event_process="Hawkes",
+                                hawkes_gain=0.8, hawkes_decay_s=0.22, bp_density="0:12, 3:24, 8:14", bp_unfold="0:18, 4:35, 8:20",
+                                spectral_imprint_on=True, spectral_imprint_amt=0.32, spectral_imprint_smooth=0.93,
+                                er_cloud_on=True, er_taps=420, er_max_ms=55.0),
+    "corona_memory_glass": dict(gen_mode="Crackle / corona", micro_ms=0.7, crackle_alpha=1.35, crackle_density=260,
+                                crackle_kernel=48, event_process="Hawkes", grains_per_sec=16, hawkes_gain=0.85,
+                                hawkes_decay_s=0.18, unfold_mode="Multi-band unfold", mb_u1=48, mb_u2=26, mb_u3=14,
+                                partial_lock_on=True, partial_stretch=1.12, spectral_imprint_on=True,
+                                spectral_imprint_amt=0.42, spectral_imprint_smooth=0.94, er_cloud_on=True, er_taps=420, er_max_ms=55),
+    "melodic_dust_chime": dict(gen_mode="Crackle / corona", micro_ms=0.9, crackle_alpha=1.25, crackle_density=120,
+                               partial_lock_on=True, partial_stretch=0.98, event_process="Clustered", grains_per_sec=14,
+                               cluster_size=4, cluster_spread_ms=16, er_cloud_on=False),
+    "glass_harmonic_arc": dict(gen_mode="Wavelet atoms", micro_ms=1.4, wav_base_hz=330, wav_count=8, wav_spread=0.25,
+                               partial_lock_on=True, partial_stretch=1.0, event_process="Poisson", grains_per_sec=9,
+                               spectral_imprint_on=True, spectral_imprint_amt=0.18, er_cloud_on=True, er_taps=240, er_max_ms=45),
+    "oval_room_trace": dict(gen_mode="IR fragment", micro_ms=2.0, event_process="Poisson", grains_per_sec=6,
+                            spectral_imprint_on=True, spectral_imprint_amt=0.28, space_ir_on=True, space_ir_max_samps=11000,
+                            er_cloud_on=False, _ir_audio="synthetic mono 250 ms"),
+    "image_grain_hallucination": dict(gen_mode="Image scanline", micro_ms=0.8, partial_stretch=1.35, event_process="Clustered",
+                                      grains_per_sec=26, cluster_size=10, cluster_spread_ms=12, nl_warp_on=True,
+                                      nl_warp_power=1.9, er_cloud_on=True, er_taps=220, er_max_ms=35,
+                                      _img_gray="synthetic 40 x 300"),
     "soft_ellipse_memory": dict(gen_mode="Noise burst", micro_ms=2.2, noise_tilt=-8.0, event_process="Poisson",
                                 grains_per_sec=6, spectral_imprint_on=True, spectral_imprint_amt=0.25,
                                 spectral_imprint_smooth=0.97, partial_stretch=0.95, bp_cutoff="0:14000, 12:9000, 24:6000",

@@ -151,3 +151,15 @@ def test_partial_lock(emul, kw):
                 gen_mode="Resonant strike", er_cloud_on=False)
     base.update(kw)
     K.check_render(emul, configs.with_defaults(base), "f64")
+
+
+@pytest.mark.parametrize("kw", [dict(gen_mode="Crackle / corona"),
+                                dict(gen_mode="Crackle / corona", crackle_density=900, crackle_kernel=8, micro_ms=4.0),
+                                dict(gen_mode="IR fragment", _ir_audio=configs.synth_ir(0.25, 48000, 11, channels=1)),
+                                dict(gen_mode="IR fragment"),                                     # no IR loaded: silence
+                                dict(gen_mode="Image scanline", _img_gray=np.random.default_rng(5).integers(0, 256, (40, 300)).astype(np.uint8)),
+                                dict(gen_mode="Image scanline")])
+def test_next_row_generators(emul, kw):
+    """gen_crackle (main_v2.py:271-281), gen_ir_fragment (:333-348), gen_image_scanline (:350-362)."""
+    p = configs.with_defaults(event_process="Poisson", out_dur_s=0.6, grains_per_sec=20.0, er_cloud_on=False, **kw)
+    K.check_render(emul, p, "f64")
