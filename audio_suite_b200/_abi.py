@@ -50,6 +50,11 @@ class PlockEvt(C.Structure):
                 ("_pad", C.c_int32), ("factor", C.c_double), ("pre", SpecOp)]
 
 
+class CepEvt(C.Structure):
+    _fields_ = [("z1", C.c_int64), ("z2", C.c_int64), ("z3", C.c_int64), ("xp", C.c_int64), ("cep", C.c_int64),
+                ("cep2", C.c_int64), ("n", C.c_int32), ("_pad", C.c_int32), ("factor", C.c_double), ("pre", SpecOp)]
+
+
 class ImprintEvt(C.Structure):
     _fields_ = [("z", C.c_int64), ("n", C.c_int32), ("_pad", C.c_int32)]
 
@@ -107,6 +112,7 @@ _STAGES = {
     "ms_spectral_z_table": (_I, [_P, _P, C.POINTER(C.c_size_t)]),
     "ms_imprint": (_I, [_P, _P, _I, _I, _P, _P]),
     "ms_partial_lock": (_I, [_P, _I, _P, _P, _P]),
+    "ms_cepstral": (_I, [_I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "ms_spectral_destroy": (None, [_P]),
     "ms_fft_pair_forward": (_I, [_P, _P, _I, _P, _P, _Z, _P]),
     "ms_fft_pair_workspace_bytes": (_Z, [_I]),

@@ -137,8 +137,7 @@ MS_DEV cpx split_bin(const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired
 MS_DEV cpx lp_bin(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired) {
     return c_scale(split_bin(Z, n, i, sel, paired), lp_weight(op, i));
 }
-// (out of line: the pow() and the second gather stay out of the register budget of the common, unwarped path)
-MS_DEV_NOINLINE cpx warp_bin_on(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired) {
+MS_DEV cpx warp_bin_on(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired) {
     const int kmax = n >> 1;
     const double km = kmax < 1 ? 1.0 : (double)kmax;
     const double pos = pow((double)i / km, op.warp_exp) * km;
@@ -153,7 +152,32 @@ MS_DEV_NOINLINE cpx warp_bin_on(const SpecOp& op, const cpx* MS_RESTRICT Z, int 
     }
     return y;
 }
-MS_DEV cpx warp_bin(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired) {
+// low-pass -> [power warp] -> stretch (two-point gather at kk / factor, zero beyond the last bin) -> multiband weights
+template <int WARP>
+MS_DEV cpx grain_value(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int kk, int sel, int paired) {
+    const int kmax = n >> 1;
+    cpx y;
+    if (!op.stretch_on) {
+        y = WARP ? warp_bin_on(op, Z, n, kk, sel, paired) : lp_bin(op, Z, n, kk, sel, paired);
+    } else {
+        const double pos = (double)kk / fmax(1e-12, op.factor);
+        if (pos > (double)kmax) return c_zero();
+        int i0 = (int)pos;
+        real fr = (real)(pos - (double)i0);
+        if (i0 >= kmax) { i0 = kmax; fr = (real)0.; }
+        y = WARP ? warp_bin_on(op, Z, n, i0, sel, paired) : lp_bin(op, Z, n, i0, sel, paired);
+        if (fr != (real)0.) {
+            cpx v1 = WARP ? warp_bin_on(op, Z, n, i0 + 1, sel, paired) : lp_bin(op, Z, n, i0 + 1, sel, paired);
+            y = mk(y.x + (v1.x - y.x) * fr, y.y + (v1.y - y.y) * fr);
+        }
+    }
+    return c_scale(y, mb_weight(op, kk));
+}
+// (the warped variant lives out of line as a whole, so the common path compiles exactly as it did without it)
+MS_DEV_NOINLINE cpx grain_value_warped(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int kk, int sel, int paired) {
+    return grain_value<1>(op, Z, n, kk, sel, paired);
+}
+MS_DEV cpx warp_bin(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int i, int sel, int paired) {      // partial-lock kernel
     if (op.warp_exp == 0.0) return lp_bin(op, Z, n, i, sel, paired);
     return warp_bin_on(op, Z, n, i, sel, paired);
 }
@@ -174,22 +198,8 @@ MS_DEV cpx op_value(const SpecOp& op, const cpx* MS_RESTRICT Z, int n, int kk, i
         r_sincos((real)op.alpha * sn, &rs, &rc);
         return c_mul(split_bin(Z, n, kk, sel, paired), mk(rc, rs));
     }
-    cpx y;
-    if (!op.stretch_on) {
-        y = warp_bin(op, Z, n, kk, sel, paired);
-    } else {
-        const double pos = (double)kk / fmax(1e-12, op.factor);
-        if (pos > (double)kmax) return c_zero();
-        int i0 = (int)pos;
-        real fr = (real)(pos - (double)i0);
-        if (i0 >= kmax) { i0 = kmax; fr = (real)0.; }
-        y = warp_bin(op, Z, n, i0, sel, paired);
-        if (fr != (real)0.) {
-            cpx v1 = warp_bin(op, Z, n, i0 + 1, sel, paired);
-            y = mk(y.x + (v1.x - y.x) * fr, y.y + (v1.y - y.y) * fr);
-        }
-    }
-    return c_scale(y, mb_weight(op, kk));
+    if (op.warp_exp != 0.0) return grain_value_warped(op, Z, n, kk, sel, paired);
+    return grain_value<0>(op, Z, n, kk, sel, paired);
 }
 // Y[k] for natural k in [0, n): both packed signals at once, Hermitian-extended the way irfft does
 // (imaginary part of DC and, for even n, of the Nyquist bin is dropped).

@@ -18,6 +18,9 @@ struct SynthWaveletK { static constexpr int MAXT = 256;
 struct PartialLockK { static constexpr int MAXT = PLOCK_NTHR;
     static constexpr int MINB = 1;
     static MS_DEV void run(const PlockEvt* e, cpx* z, real* scratch, const Ctx& c) { partial_lock_body(e, z, scratch, c); } };
+template <int STEP> struct CepstralK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const CepEvt* e, cpx* z1, cpx* z2, const cpx* z3, real* scratch, const Ctx& c) { cepstral_body<STEP>(e, z1, z2, z3, scratch, c); } };
 struct ImprintK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const ImprintEvt* e, const ImprintRender* r, cpx* z, const Ctx& c) { imprint_body(e, r, z, c); } };
@@ -84,6 +87,18 @@ extern "C" int MS_API(ms_partial_lock)(const ms_plock_evt* evts, int n, real* z_
         if (ms_launch<PartialLockK>(mk_dim((unsigned)cnt, 1), PLOCK_NTHR, PLOCK_NTHR * sizeof(int), (ms_stream_t)stream,
                                     evts + x0, (cpx*)z_base, scratch)) return -1;
     }
+    return 0;
+}
+extern "C" int MS_API(ms_cepstral)(int step, const ms_cep_evt* evts, int n, int max_n, real* z1, real* z2, real* z3, real* scratch,
+                           void* stream) {
+    const unsigned gx = (unsigned)(((step == 1 ? max_n : max_n / 2 + 1) + 255) / 256);
+    MS_FOR_Y_CHUNKS(n, {
+        int rc;
+        if (step == 0) rc = ms_launch<CepstralK<0>>(mk_dim(gx, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, (cpx*)z1, (cpx*)z2, (const cpx*)z3, scratch);
+        else if (step == 1) rc = ms_launch<CepstralK<1>>(mk_dim(gx, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, (cpx*)z1, (cpx*)z2, (const cpx*)z3, scratch);
+        else rc = ms_launch<CepstralK<2>>(mk_dim(gx, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, (cpx*)z1, (cpx*)z2, (const cpx*)z3, scratch);
+        if (rc) return -1;
+    })
     return 0;
 }
 extern "C" int MS_API(ms_imprint)(const ms_imprint_evt* evts, const ms_imprint_render* renders, int n_renders, int max_bins,

@@ -294,3 +294,39 @@ MS_DEV void partial_lock_body(const PlockEvt* MS_RESTRICT evts, cpx* zbase, real
         }
     }
 }
+
+// ---- cepstral warp (cepstral_warp, main_v2.py:150-163): the three elementwise steps between its transforms ---------
+// grid = (ceil(max_n / nthr), grains).  step 0: X = low-pass / warp of the grain's spectrum -> scratch, log(|X| + 1e-12)
+// -> spectrum of the cepstrum transform;  step 1: cepstrum resampled at t / factor (np.interp, zeros to the right);
+// step 2: exp(Re rfft(warped cepstrum)) with the phases of X -> the grain's spectrum.
+typedef ms_cep_evt CepEvt;
+template <int STEP>
+MS_DEV void cepstral_body(const CepEvt* MS_RESTRICT evts, cpx* z1, cpx* z2, const cpx* MS_RESTRICT z3, real* scratch, const Ctx& c) {
+    const CepEvt& E = evts[c.by];
+    const int n = E.n, bins = n / 2 + 1;
+    const int i = c.bx * c.nthr + c.tid;
+    if (STEP == 0) {
+        if (i >= bins) return;
+        const SpecOp& op = *(const SpecOp*)&E.pre;
+        const cpx x = warp_bin(op, z1 + E.z1, n, i, 0, 0);
+        ((cpx*)(scratch + E.xp))[i] = x;
+        z2[E.z2 + i] = mk((real)log(hypot((double)x.x, (double)x.y) + 1e-12), (real)0.);
+    } else if (STEP == 1) {
+        if (i >= n) return;
+        const real* cep = scratch + E.cep;
+        const double pos = (double)i / fmax(1e-12, E.factor);
+        real v = (real)0.;
+        if (pos <= (double)(n - 1)) {
+            int i0 = (int)pos;
+            if (i0 >= n - 1) v = cep[n - 1];
+            else { const real fr = (real)(pos - (double)i0); v = cep[i0] + (cep[i0 + 1] - cep[i0]) * fr; }
+        }
+        scratch[E.cep2 + i] = v;
+    } else {
+        if (i >= bins) return;
+        const cpx x = ((const cpx*)(scratch + E.xp))[i];
+        const double mag = hypot((double)x.x, (double)x.y);
+        const double g = exp((double)z3[E.z3 + i].x);
+        z1[E.z1 + i] = mag > 0.0 ? mk((real)(g * ((double)x.x / mag)), (real)(g * ((double)x.y / mag))) : mk((real)g, (real)0.);
+    }
+}

@@ -251,6 +251,42 @@ class BatchRenderer:
         self.tilt_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.tilt), self.pool, self.pool)
         self.grain_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.grain), self.pool, self.pool)
         self.rot_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.rot), self.mono, self.mono)
+        # cepstral warp: three stages of single-signal jobs around the elementwise steps of ms_cepstral
+        self.cep_stages = None
+        if t.cep is not None and len(t.cep[0]):
+            rows, factor, pre, post = t.cep
+            N = len(rows)
+            n = rows[:, 2]
+            bins = n // 2 + 1
+            xp_len = (2 * bins + 3) // 4 * 4
+            per = xp_len + 2 * ((n + 3) // 4 * 4)
+            base = np.concatenate([[0], np.cumsum(per)])
+            xp, cep, cep2 = base[:-1], base[:-1] + xp_len, base[:-1] + xp_len + (n + 3) // 4 * 4
+            self.cep_scratch = dev.empty(int(base[-1]), real)
+
+            def mk_jobs(in_a, out_a, ops=None):
+                jobs = np.zeros(N, np.dtype(_abi.SpecJob))
+                jobs["n"], jobs["in_a"], jobs["out_a"], jobs["in_b"], jobs["out_b"] = n, in_a, out_a, -1, -1
+                if ops is not None:
+                    raw = jobs.view(np.uint8).reshape(N, jobs.dtype.itemsize)
+                    o0 = jobs.dtype.fields["op"][1]
+                    raw[:, o0:o0 + ops.shape[1]] = ops
+                return jobs
+            s1 = _SpectralStage(dev, self.api, mk_jobs(rows[:, 0], rows[:, 1], post), self.pool, self.pool)
+            s2 = _SpectralStage(dev, self.api, mk_jobs(cep, cep), self.cep_scratch, self.cep_scratch)     # inverse only
+            s3 = _SpectralStage(dev, self.api, mk_jobs(cep2, cep2), self.cep_scratch, self.cep_scratch)   # forward only
+            self.cep_stages = (s1, s2, s3)
+            ev = np.zeros(N, np.dtype(_abi.CepEvt))
+            zb = []
+            for name, st_ in zip(("z1", "z2", "z3"), self.cep_stages):
+                b0, offs = st_.z_table()
+                ev[name] = offs
+                zb.append(b0)
+            ev["xp"], ev["cep"], ev["cep2"], ev["n"], ev["factor"] = xp, cep, cep2, n, factor
+            rawe = ev.view(np.uint8).reshape(N, ev.dtype.itemsize)
+            p0 = ev.dtype.fields["pre"][1]
+            rawe[:, p0:p0 + pre.shape[1]] = pre
+            self.d_cep_evt, self.n_cep, self.cep_max_n, self.cep_zb = dev.upload(ev), N, int(n.max()), zb
         # partial lock: single-signal jobs from the event's raw transient; low-pass / warp are evaluated by the
         # lock kernel on the forward spectrum, the inverse applies what follows it (multiband)
         self.plock_stage = None
@@ -338,6 +374,18 @@ class BatchRenderer:
                 mark("tilt_spectral")
             self.grain_stage.run()
             mark("grain_spectral")
+            if self.cep_stages is not None:
+                s1, s2, s3 = self.cep_stages
+                zp = [C.c_void_p(dev.ptr(s_.ws).value + b0) for s_, b0 in zip(self.cep_stages, self.cep_zb)]
+                args = (dev.ptr(self.d_cep_evt), self.n_cep, self.cep_max_n, zp[0], zp[1], zp[2], dev.ptr(self.cep_scratch), st)
+                s1.forward()
+                _check(dev, lib.ms_cepstral(0, *args))
+                s2.inverse()
+                _check(dev, lib.ms_cepstral(1, *args))
+                s3.forward()
+                _check(dev, lib.ms_cepstral(2, *args))
+                s1.inverse()
+                mark("cepstral_warp")
             if self.plock_stage is not None:
                 self.plock_stage.forward()
                 zptr = C.c_void_p(dev.ptr(self.plock_stage.ws).value + self.plock_zbase)
@@ -387,7 +435,7 @@ class BatchRenderer:
         return m
 
     def close(self):
-        for s in (self.tilt_stage, self.grain_stage, self.rot_stage, self.imprint_stage, self.plock_stage):
+        for s in (self.tilt_stage, self.grain_stage, self.rot_stage, self.imprint_stage, self.plock_stage) + tuple(self.cep_stages or ()):
             if s is not None:
                 s.close()
         if self.fir_handle:

@@ -26,7 +26,7 @@ MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET
 WAVELET_FLOOR = 128                 # M:319
 _MODE_ID = {m: i for i, m in enumerate(BASIC_MODES)}
 
-_NEXT_ROW_FLAGS = ("cep_warp_on", "res_bank_on", "wg_on", "event_feedback_on")
+_NEXT_ROW_FLAGS = ("res_bank_on", "wg_on", "event_feedback_on")
 _NEXT_ROW_MODES = ("Stick–slip friction", "Micro-chaos")
 
 
@@ -221,6 +221,7 @@ class EventPlan:
     placed: bool = False
     spec: Optional[object] = None           # _abi.SpecOp or None
     plock: Optional[tuple] = None           # (factor, top_n, neigh, pre-operator) when partial_lock_stretch is active
+    cep: Optional[tuple] = None             # (factor, pre-operator) when cepstral_warp is active
     tilt: Optional[object] = None           # _abi.SpecOp for the tilted-noise modes
     dust_pos: Optional[np.ndarray] = None   # sorted unique impulse positions (int32)
     dust_val: Optional[np.ndarray] = None   # float64 values (last write wins, M:243)
@@ -334,7 +335,14 @@ def plan_render(params) -> RenderPlan:
                 ev.offset = int(rng.integers(0, max(1, min(max_off, n))))
             ev.length = max(0, min(out_n - ev.start, n - ev.offset))
             ev.placed = ev.length > 0
-        if params["partial_lock_on"]:
+        if params["cep_warp_on"] and n >= 64:
+            # M:696-697: cepstral_warp sits between low-pass / power warp and the stretch; its three elementwise steps
+            # run between transforms of their own, the stage's inverse applies stretch + multiband
+            if params["partial_lock_on"] and not abs(ev.stretch - 1.0) < 1e-9:
+                raise NotImplementedError("microsound_b200: cep_warp_on together with an active partial lock is not on the accelerated path yet")
+            ev.cep = (float(params["cep_factor"]), grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, post=False, keep=True))
+            ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0 if params["partial_lock_on"] else ev.stretch, pre=False, keep=True)
+        elif params["partial_lock_on"]:
             # M:699-702: partial_lock_stretch REPLACES fft_partial_stretch; it is the identity for n < 64 or a factor of 1
             if n >= 64 and not abs(ev.stretch - 1.0) < 1e-9:
                 ev.plock = (ev.stretch, int(params["pl_top_n"]), int(params["pl_neigh"]),

@@ -90,6 +90,7 @@ class Tables:
     dust_val: np.ndarray = None
     atoms: np.ndarray = None        # wavelet atoms, float64 [N, 4]
     atom_shift: np.ndarray = None   # int32 [N]
+    cep: tuple = None               # (rows int64 [N, 3] = src, dst, n ; factor [N] ; pre ops [N, B] ; post ops [N, B])
     plock: tuple = None             # (rows int64 [N, 5] = src, dst, n, top_n, neigh ; factor [N] ; pre ops [N, B] ; post ops [N, B])
     imprint: np.ndarray = None      # rows per imprinted event, in event order per render: render, pool_in, pool_out, n
     imprint_par: np.ndarray = None  # per render: amount, smooth (nan when off)
@@ -123,6 +124,7 @@ def pack_chunk(plans) -> Tables:
     atoms, atom_shift, n_atoms = [], [], 0
     imprint_rows, imprint_par = [], np.full((R, 2), np.nan)
     pl_rows, pl_factor, pl_pre, pl_post = [], [], [], []
+    cp_rows, cp_factor, cp_pre, cp_post = [], [], [], []
     tap_off, tap_gain, n_taps = [], [], 0
     irs, ir_index, n_ir = [], {}, 0
     pool_n = mono_n = h_total = max_h = 0
@@ -183,7 +185,16 @@ def pack_chunk(plans) -> Tables:
             sy2[e] = common + (mode2,) + tail + (micro, ev.f_over_sr, inv_fade, ev.ring_decay, ev.env_decay,
                                                   0, 0, ev.ker_len, aux2, 0, 0, 0)
             g_at = micro
-            if ev.plock is not None:
+            if ev.cep is not None:
+                g_at = pool_n
+                pool_n += ev.n
+                cp_rows.append((micro, g_at, ev.n))
+                cp_factor.append(ev.cep[0])
+                cp_pre.append(bytes(ev.cep[1]))
+                cp_post.append(bytes(ev.spec))
+                alg["grain_spectral"] += 2 * ev.n * (1 + int(ev.cep[1].lp_on) + (1 if ev.cep[1].warp_exp else 0)
+                                                     + int(ev.spec.stretch_on) + (1 if ev.spec.n_bands else 0))
+            elif ev.plock is not None:
                 g_at = pool_n
                 pool_n += ev.n
                 pl_rows.append((micro, g_at, ev.n, ev.plock[1], ev.plock[2]))
@@ -314,6 +325,10 @@ def pack_chunk(plans) -> Tables:
     t.plock = (np.asarray(pl_rows, np.int64).reshape(-1, 5), np.asarray(pl_factor, np.float64),
                np.frombuffer(b"".join(pl_pre), np.uint8).reshape(npl, _SPEC_OP_BYTES) if npl else np.zeros((0, _SPEC_OP_BYTES), np.uint8),
                np.frombuffer(b"".join(pl_post), np.uint8).reshape(npl, _SPEC_OP_BYTES) if npl else np.zeros((0, _SPEC_OP_BYTES), np.uint8))
+    ncp = len(cp_rows)
+    t.cep = (np.asarray(cp_rows, np.int64).reshape(-1, 3), np.asarray(cp_factor, np.float64),
+             np.frombuffer(b"".join(cp_pre), np.uint8).reshape(ncp, _SPEC_OP_BYTES) if ncp else np.zeros((0, _SPEC_OP_BYTES), np.uint8),
+             np.frombuffer(b"".join(cp_post), np.uint8).reshape(ncp, _SPEC_OP_BYTES) if ncp else np.zeros((0, _SPEC_OP_BYTES), np.uint8))
     t.imprint = np.asarray(imprint_rows, np.int64).reshape(-1, 4)
     t.imprint_par = imprint_par
     t.tilt, t.grain, t.rot = tilt.arrays(), grain.arrays(), rot.arrays()
@@ -341,6 +356,7 @@ def merge_chunks(chunks) -> Tables:
                              "atoms", "atom_shift", "imprint", "imprint_par", "odd", "out_at", "out_n", "y_at", "last", "srs")}
     items = {k: [[], [], [], []] for k in ("tilt", "grain", "rot")}
     pl_parts = [[], [], [], []]
+    cp_parts = [[], [], [], []]
     alg = {}
     for c in chunks:
         _shift(c.sy1, ("out",), pool_b)
@@ -353,8 +369,11 @@ def merge_chunks(chunks) -> Tables:
             c.imprint[:, 1:3] += pool_b
         if c.plock[0].size:
             c.plock[0][:, 0:2] += pool_b
+        if c.cep[0].size:
+            c.cep[0][:, 0:2] += pool_b
         for i in range(4):
             pl_parts[i].append(c.plock[i])
+            cp_parts[i].append(c.cep[i])
         _shift(c.sy2, ("out", "aux"), pool_b)
         _shift(c.ola_r, ("out",), mono_b)
         _shift(c.ola_r, ("ev_begin", "ev_end"), olae_b)
@@ -402,6 +421,7 @@ def merge_chunks(chunks) -> Tables:
     for k in items:
         setattr(m, k, tuple(np.concatenate(x) for x in items[k]))
     m.plock = tuple(np.concatenate(x) for x in pl_parts)
+    m.cep = tuple(np.concatenate(x) for x in cp_parts)
     m.pool_n, m.mono_n, m.frames, m.h_total, m.alg, m.env_n = pool_b, mono_b, frame_b, h_b, alg, env_b
     return m
 

@@ -104,6 +104,20 @@ typedef struct {
     ms_spec_op pre;
 } ms_plock_evt;
 /* ms_partial_lock_f32 / ms_partial_lock_f64: declared below by MS_DECLARE_API */
+/* cepstral_warp (main_v2.py:150-163) around three spectral stages of single-signal jobs: (1) forward of the grain;
+ * ms_cepstral(step 0): X = low-pass / power warp of its spectrum (`pre`) is kept in scratch and log(|X| + 1e-12)
+ * becomes the spectrum of stage 2; (2) inverse of stage 2 -> cepstrum; ms_cepstral(step 1): the cepstrum resampled at
+ * t / factor; (3) forward of stage 3; ms_cepstral(step 2): exp(Re Z3) with the phases of X replaces the spectrum of
+ * stage 1, whose inverse (operator: stretch, multiband) finishes.  Offsets z1/z2/z3 in complex elements of the three
+ * stages' spectra, xp/cep/cep2 in REAL elements of `scratch`. */
+typedef struct {
+    int64_t z1, z2, z3;
+    int64_t xp, cep, cep2;
+    int32_t n, _pad;
+    double factor;
+    ms_spec_op pre;
+} ms_cep_evt;
+/* ms_cepstral_f32 / ms_cepstral_f64: declared below by MS_DECLARE_API */
 /* test entry: Z[k] = sum_j (a[j] + i b[j]) exp(-2 pi i jk/n), interleaved re/im, natural order */
 /* ms_fft_pair_forward_f32 / ms_fft_pair_forward_f64: declared below by MS_DECLARE_API */
 /* ms_fft_pair_workspace_bytes_f32 / ms_fft_pair_workspace_bytes_f64: declared below by MS_DECLARE_API */
@@ -215,6 +229,8 @@ typedef struct {
     int ms_spectral_inverse##SFX(void* handle, void* stream); \
     int ms_spectral_z_table##SFX(void* handle, int64_t* host_z_offsets, size_t* z_base_bytes); \
     int ms_partial_lock##SFX(const ms_plock_evt* dev_evts, int n_evts, REAL* z_base, REAL* scratch, void* stream); \
+    int ms_cepstral##SFX(int step, const ms_cep_evt* dev_evts, int n_evts, int max_n, REAL* z1_base, REAL* z2_base, \
+    REAL* z3_base, REAL* scratch, void* stream); \
     int ms_imprint##SFX(const ms_imprint_evt* dev_evts, const ms_imprint_render* dev_renders, int n_renders, int max_bins, \
     REAL* z_base, void* stream); \
     void ms_spectral_destroy##SFX(void* handle); \

@@ -177,6 +177,21 @@ def partial_lock(x, factor, top_n=24, neighborhood=4):
     return np.fft.irfft(moved + 0.12 * spec, n=n)
 
 
+def cepstrum_warp(x, factor):
+    """M:150-163 -- the real cepstrum of the grain (irfft of log(|X| + 1e-12)) is resampled on the quefrency axis
+    (linear interpolation at t / factor, zeros outside), turned back into a log-magnitude (real part of its rfft)
+    and recombined with the original phases."""
+    n = len(x)
+    if n < 64:
+        return x
+    spec = np.fft.rfft(x)
+    cep = np.fft.irfft(np.log(np.abs(spec) + 1e-12), n=n)
+    t = np.arange(n, dtype=np.float64)
+    warped = np.interp(t / max(1e-12, float(factor)), t, cep, left=0.0, right=0.0)
+    mag = np.exp(np.fft.rfft(warped).real)
+    return np.fft.irfft(mag * np.exp(1j * np.angle(spec)), n=n)
+
+
 def multiband_unfold(x, gen_sr, bands_out_hz, unfolds, roll_hz):
     """M:492-500 -- sum of band-passed copies, band edges scaled by each band's unfold."""
     acc = None
@@ -522,18 +537,22 @@ class ImprintMemory:
         return np.fft.irfft(blended * np.exp(1j * np.angle(spec)), n=n)
 
 
-def imprint_noise_floor(params, reference_audio=None):
-    """max-abs change of the rendered audio under a 1e-15 relative perturbation of the grains entering the spectral
-    imprint: the part of the reference's output that is decided by float64 rounding noise (0.0 without imprint)."""
-    if not params["spectral_imprint_on"]:
+def rounding_noise_floor(params, reference_audio=None):
+    """max-abs change of the rendered audio under a 1e-15 relative perturbation of the grains entering the cepstral
+    warp / the spectral imprint: the part of the reference's output that is decided by float64 rounding noise
+    (0.0 when neither is on)."""
+    if not (params["spectral_imprint_on"] or params["cep_warp_on"]):
         return 0.0
     a = reference_audio if reference_audio is not None else render(params)[0]
     b = render(params, jitter=1e-15)[0]
     return float(np.max(np.abs(a - b)))
 
 
+imprint_noise_floor = rounding_noise_floor
+
+
 # --------------------------------------------------------------------------- render
-_UNSUPPORTED_FLAGS = ("cep_warp_on", "res_bank_on", "wg_on",
+_UNSUPPORTED_FLAGS = ( "res_bank_on", "wg_on",
                       "event_feedback_on")
 
 
@@ -590,11 +609,13 @@ def plan_events(params):
 def render(params, progress=None, taps=None, jitter=None):
     """M:588-792.  `taps` (optional dict) receives intermediate buffers for stage-level tests.
 
-    `jitter` (tests only): relative size of a seeded perturbation added to every grain right before the spectral
-    imprint.  SpectralImprint keeps the PHASE of every rfft bin and replaces its magnitude by a blend with the
-    moving average; in bins the band-limit has emptied the phase is that of float64 rounding noise, so wherever
-    the average still remembers energy there (a falling `bp_cutoff` lane) the reference's output depends on
-    rounding noise.  Rendering with and without a 1e-15 jitter measures how much (imprint_noise_floor)."""
+    `jitter` (tests only): relative size of a seeded perturbation added to every grain right before the cepstral
+    warp and before the spectral imprint.  Both keep the PHASE of every rfft bin and give it a new magnitude; in
+    bins the band-limit has emptied, the phase is that of float64 rounding noise (|X| ~ 1e-16).  The imprint's
+    moving average may still remember energy there (a falling `bp_cutoff` lane), and the warped cepstrum of a
+    band-limited grain puts exp(-5..-16) there against an output of 1e-3: a 1e-17 relative perturbation of the
+    input moves cepstral_warp's output by 2.4 %.  Rendering with and without a 1e-15 jitter measures how much of the
+    reference's output is decided by rounding noise (rounding_noise_floor)."""
     for flag in _UNSUPPORTED_FLAGS:
         if params[flag]:
             raise NotImplementedError(f"oracle: '{flag}' is a SURVEY 8(f) 'next' row, not restated yet")
@@ -634,6 +655,10 @@ def render(params, progress=None, taps=None, jitter=None):
             g = fft_lowpass(g, ev["gen_sr"], ev["cutoff_gen"], roll=float(params["bandlimit_roll_hz"]))
         if params["nl_warp_on"]:                                                  # M:694-695
             g = spectrum_power_warp(g, float(params["nl_warp_power"]))
+        if params["cep_warp_on"]:                                                 # M:696-697
+            if jitter:
+                g = g + jitter * np.max(np.abs(g)) * np.random.default_rng(555 + i).standard_normal(g.size)
+            g = cepstrum_warp(g, float(params["cep_factor"]))
         if params["partial_lock_on"]:                                             # M:699-702
             g = partial_lock(g, ev["stretch"], int(params["pl_top_n"]), int(params["pl_neigh"]))
         else:

@@ -118,14 +118,16 @@ def test_render_preset_rows_wavelet_atoms_and_imprint(cuda_dev, name):
     p["out_dur_s"] = 2.0
     out, _ = engine.render(p, device=cuda_dev)
     g = np.load(os.path.join(GOLDEN, "next_rows.npz"))
-    floor = O.imprint_noise_floor(p)
+    floor = O.rounding_noise_floor(p)
     assert np.max(np.abs(out[::4] - g["render_" + name])) < K.MAX_ABS_TOL + 4.0 * floor, name
 
 
 @pytest.mark.parametrize("kw", [dict(nl_warp_on=True, nl_warp_power=1.6, partial_stretch=1.3),
                                 dict(partial_lock_on=True, partial_stretch=0.8, pl_top_n=100, pl_neigh=12),
                                 dict(partial_lock_on=True, partial_stretch=1.7, nl_warp_on=True, unfold_mode="Multi-band unfold",
-                                     spectral_imprint_on=True, gen_mode="Wavelet atoms")])
+                                     spectral_imprint_on=True, gen_mode="Wavelet atoms"),
+                                dict(cep_warp_on=True, cep_factor=1.3, bandlimit_on=False, partial_stretch=1.2, nl_warp_on=True),
+                                dict(cep_warp_on=True, cep_factor=0.7, bandlimit_on=False, gen_mode="Crackle / corona")])
 def test_render_spectral_extras(cuda_dev, kw):
     """SURVEY 8(f) rank 1 rows on the GPU: power warp, partial lock, imprint, combined, several events per render."""
     base = dict(event_process="Poisson", out_dur_s=3.0, grains_per_sec=25.0, time_unfold=60.0, micro_ms=3.0,

@@ -153,7 +153,8 @@ def test_wavelet_grain_shorter_than_its_atoms_fails_like_the_reference():
 @pytest.mark.parametrize("name", ["opal_airfold", "opal_oval_breath", "basinski_melodic_loop", "basinski_oval_decay",
                                   "soft_ellipse_memory", "micro_carillon", "oval_glass_orbit", "glass_harmonic_arc",
                                   "01_corona_glass_fog", "corona_memory_glass", "melodic_dust_chime", "oval_room_trace",
-                                  "room_as_particle", "image_grain_hallucination", "chaotic_dustfield"])
+                                  "room_as_particle", "image_grain_hallucination", "closed_curve_air",
+                                  "drifting_mode_fragments", "ghost_formants", "corona_glass_fog", "chaotic_dustfield"])
 def test_oracle_matches_reference_on_shipped_presets(name):
     """The shipped presets that need only accelerated rows, merged over the factory defaults the way on_load_preset
     does (main_v2.py:1286-1291), first 3 s."""
