@@ -14,4 +14,7 @@ def __getattr__(name):
     if name in ("render", "render_batch", "BatchRenderer"):
         from . import engine
         return getattr(engine, name)
+    if name in ("load_preset", "batch_render", "batch_name", "write_wav_float32"):
+        from . import frontend
+        return getattr(frontend, name)
     raise AttributeError(name)
