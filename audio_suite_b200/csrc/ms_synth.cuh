@@ -10,7 +10,7 @@
 // shared staging buffer in stream order; the mode's closed-form terms (sine with float64 phase,
 // exponentials, fades) are applied on the way out with coalesced stores.
 
-enum { SY_GAUSS = 0, SY_DUST = 1, SY_NOISE = 2, SY_SKEW = 3, SY_RES = 4, SY_PLAIN = 5, SY_WAVELET = 6, SY_IRFRAG = 7, SY_SCANLINE = 8, SY_SILENT = 9 };
+enum { SY_GAUSS = 0, SY_DUST = 1, SY_NOISE = 2, SY_SKEW = 3, SY_RES = 4, SY_PLAIN = 5, SY_WAVELET = 6, SY_IRFRAG = 7, SY_SCANLINE = 8, SY_SILENT = 9, SY_CHAOS = 10 };
 
 #define SY_C 8            // words per thread per round
 #define SY_NTHR 256
@@ -371,10 +371,41 @@ MS_DEV void synth_table_body(const SynthEvt* MS_RESTRICT evts, const real* MS_RE
         }
         return;
     }
-    // SY_SCANLINE
     real* tmp = pool + E.aux;
-    for (int j = c.tid; j < n; j += c.nthr) tmp[j] = table_sample(tab, M, n, j);
-    c.sync();
+    if (E.mode == SY_CHAOS) {
+        // gen_micro_chaos (main_v2.py:303-315).  The gate draws (one uniform per sample: (word >> 11) * 2^-53 < gate) are
+        // position-independent, so every thread jumps the 128-bit LCG to its own samples; the logistic map itself is a
+        // chaotic recurrence and is iterated by ONE thread with the reference's exact float64 operation order
+        // ((r * y) * (1.0 - y), no fused multiply-add), so it stays bit-identical for any grain length.
+        u128 inc; inc.hi = E.i_hi; inc.lo = E.i_lo;
+        u128 st; st.hi = E.s_hi; st.lo = E.s_lo;
+        u128 jm, jp;
+        pcg_jump_consts(inc, (unsigned long long)c.tid + 1ull, &jm, &jp);      // sample j uses word j (state after j + 1 steps)
+        st = u128_add(u128_mul(st, jm), jp);
+        pcg_jump_consts(inc, (unsigned long long)c.nthr, &jm, &jp);
+        const double gate = E.ring_decay;
+        for (int j = c.tid; j < n; j += c.nthr) {
+            tmp[j] = word_to_double(pcg_output(st)) < gate ? (real)1. : (real)0.;
+            st = u128_add(u128_mul(st, jm), jp);
+        }
+        c.sync();
+        if (c.tid == 0) {
+            const double r = E.f_over_sr;
+            double y = E.env_decay;
+            for (int j = 0; j < n; ++j) {
+#ifdef MS_HOST_EMUL
+                volatile double ry = r * y; volatile double om = 1.0 - y; y = ry * om;
+#else
+                y = __dmul_rn(__dmul_rn(r, y), __dsub_rn(1.0, y));
+#endif
+                tmp[j] = tmp[j] != (real)0. ? (real)(y - 0.5) : (real)0.;
+            }
+        }
+        c.sync();
+    } else {            // SY_SCANLINE
+        for (int j = c.tid; j < n; j += c.nthr) tmp[j] = table_sample(tab, M, n, j);
+        c.sync();
+    }
     const int K = E.ker_len, ctr = (K - 1) / 2;
     const real rate = (real)5.0 / (real)(K - 1);
     for (int j = c.tid; j < n; j += c.nthr) {
@@ -383,6 +414,7 @@ MS_DEV void synth_table_body(const SynthEvt* MS_RESTRICT evts, const real* MS_RE
             const int i = j + ctr - m;
             if (i >= 0 && i < n) acc += r_exp(-rate * (real)m) * tmp[i];
         }
+        if (E.mode == SY_CHAOS) acc *= (real)(n > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)j / (double)(n - 1)) : 1.0);   // hann after the smoothing
         out[j] = acc;
     }
 }

@@ -22,12 +22,12 @@ from .configs import BASIC_MODES
 DESIGN_SR_CAP = 30_000_000          # M:597, M:646
 IR_TAP_CAP = 8192                   # M:443
 
-MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET, MODE_IRFRAG, MODE_SCANLINE, MODE_SILENT = range(10)
+MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET, MODE_IRFRAG, MODE_SCANLINE, MODE_SILENT, MODE_CHAOS = range(11)
 WAVELET_FLOOR = 128                 # M:319
 _MODE_ID = {m: i for i, m in enumerate(BASIC_MODES)}
 
 _NEXT_ROW_FLAGS = ("res_bank_on", "wg_on", "event_feedback_on")
-_NEXT_ROW_MODES = ("Stick–slip friction", "Micro-chaos")
+_NEXT_ROW_MODES = ("Stick–slip friction",)
 
 
 # --------------------------------------------------------------------------- breakpoint lanes (M:452-482)
@@ -305,6 +305,8 @@ def plan_render(params) -> RenderPlan:
         mode, floor = (MODE_SILENT, 16) if (ir_audio is None or np.asarray(ir_audio).size < 32) else (MODE_IRFRAG, 64)
     elif gmode == "Image scanline":
         mode, floor = (MODE_SILENT if img_gray is None else MODE_SCANLINE), 64
+    elif gmode == "Micro-chaos":
+        mode, floor = MODE_CHAOS, 64
     elif gmode in _MODE_ID:
         mode = _MODE_ID[gmode]
         dust_density, tilt = float(params["dust_density"]), float(params["noise_tilt"])
@@ -363,6 +365,10 @@ def plan_render(params) -> RenderPlan:
             _plan_ir_fragment(ev, ir_audio)
         elif mode == MODE_SCANLINE:
             _plan_scanline(ev, img_gray)
+        elif mode == MODE_CHAOS:               # M:303-315: r, gate, y0 = (seed % 10000) / 10000 ride in the mode constants
+            ev.f_over_sr, ev.ring_decay = float(params["chaos_r"]), float(params["chaos_gate"])
+            ev.env_decay = (int(ev.seed) % 10000) / 10000.0
+            ev.ker_len, ev.fade = 48, 0
         elif mode in (MODE_NOISE, MODE_SKEW):
             ev.tilt = tilt_spec_op(n, sr_evt, tilt)
             T = max(1e-6, micro_s * (0.25 if mode == MODE_NOISE else 0.2))

@@ -170,6 +170,9 @@ def pack_chunk(plans) -> Tables:
                 if ev.mode == P.MODE_SCANLINE:
                     aux2 = pool_n                                     # windowed, unsmoothed line
                     pool_n += ev.n
+            elif ev.mode == P.MODE_CHAOS:
+                aux2 = pool_n                                         # gated logistic-map samples before the smoothing
+                pool_n += ev.n
             elif ev.mode in (P.MODE_NOISE, P.MODE_SKEW):
                 raw, tilted = pool_n, pool_n + ev.n
                 pool_n += 2 * ev.n
@@ -180,7 +183,7 @@ def pack_chunk(plans) -> Tables:
             tail = (ev.fade, ev.sigma)
             inv_fade = 1.0 / ev.fade if ev.fade > 0 else 0.0
             sy1[e] = common + (ev.mode,) + tail + (out1, ev.f_over_sr, inv_fade, ev.ring_decay, ev.env_decay,
-                                                     dust_b, dust_c, ev.ker_len, aux2 if ev.mode == P.MODE_SCANLINE else 0,
+                                                     dust_b, dust_c, ev.ker_len, aux2 if ev.mode in (P.MODE_SCANLINE, P.MODE_CHAOS) else 0,
                                                      atom_b, atom_c, 0)
             sy2[e] = common + (mode2,) + tail + (micro, ev.f_over_sr, inv_fade, ev.ring_decay, ev.env_decay,
                                                   0, 0, ev.ker_len, aux2, 0, 0, 0)
@@ -361,7 +364,7 @@ def merge_chunks(chunks) -> Tables:
     for c in chunks:
         _shift(c.sy1, ("out",), pool_b)
         if c.sy1.size and pool_b:
-            c.sy1["aux"] += np.where(c.sy1["mode"] == P.MODE_SCANLINE, pool_b, 0)
+            c.sy1["aux"] += np.where((c.sy1["mode"] == P.MODE_SCANLINE) | (c.sy1["mode"] == P.MODE_CHAOS), pool_b, 0)
         _shift(c.sy1, ("dust_begin",), dust_b)
         _shift(c.sy1, ("atom_begin",), atom_b)
         if c.imprint.size:

@@ -125,7 +125,7 @@ typedef struct {
 /* ---- transient synthesis: gen_basic (main_v2.py:219-269).  One record per event; the array lives in
  *      DEVICE memory.  The PCG64 state is numpy's `PCG64(seed).state` right after seeding. */
 enum { MS_SY_GAUSS = 0, MS_SY_DUST = 1, MS_SY_NOISE = 2, MS_SY_SKEW = 3, MS_SY_RES = 4, MS_SY_PLAIN = 5, MS_SY_WAVELET = 6,
-       MS_SY_IRFRAG = 7, MS_SY_SCANLINE = 8, MS_SY_SILENT = 9 };
+       MS_SY_IRFRAG = 7, MS_SY_SCANLINE = 8, MS_SY_SILENT = 9, MS_SY_CHAOS = 10 };
 typedef struct {
     uint64_t s_hi, s_lo, i_hi, i_lo;
     int32_t n, mode;
@@ -153,6 +153,8 @@ typedef struct { double f0_over_sr, inv_sigma, phase, weight; } ms_wavelet_atom;
  * a short host-chosen table (dust_val[dust_begin .. +dust_count]) stretched to n samples by linear interpolation
  * under a Hann window, then peak-normalised to 0.9 (IR fragment) or smoothed by exp(-linspace(0,5,ker_len))
  * (scanline; `aux` = n samples of scratch in the pool).  One CTA per event. */
+/* MS_SY_CHAOS (gen_micro_chaos, main_v2.py:303-315) also runs in ms_synth_table: f_over_sr = r, ring_decay = gate,
+ * env_decay = y0 = (seed % 10000) / 10000, the PCG64 state as for the normal modes, `aux` = n samples of scratch. */
 /* ms_synth_table_f32 / ms_synth_table_f64: declared below by MS_DECLARE_API */
 /* MS_SY_WAVELET events: sum of shifted Gaussian-windowed cosines under a Hann window (float64 phase) */
 /* ms_synth_wavelet_f32 / ms_synth_wavelet_f64: declared below by MS_DECLARE_API */

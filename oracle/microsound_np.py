@@ -504,11 +504,25 @@ def image_scanline(img_gray, gen_sr, micro_ms, seed):
     return np.convolve(x, np.exp(-np.linspace(0, 5, 48)), mode="same")
 
 
+def micro_chaos(gen_sr, micro_ms, seed, r, gate):
+    """M:303-315 -- a logistic map sampled through a random gate (one uniform draw per sample), smoothed ("same") by
+    exp(-linspace(0, 5, 48)) and Hann-windowed.  The map is iterated in Python floats: (r * y) * (1.0 - y)."""
+    rng = np.random.default_rng(int(seed))
+    n = grain_length(gen_sr, micro_ms, floor=64)
+    x = np.zeros(n, dtype=np.float64)
+    y = (int(seed) % 10000) / 10000.0
+    for i in range(n):
+        y = r * y * (1.0 - y)
+        if rng.random() < gate:
+            x[i] = y - 0.5
+    return np.convolve(x, np.exp(-np.linspace(0, 5, 48)), mode="same") * raised_cosine_window(n)
+
+
 def generator_floor(mode, params):
     """Minimum grain length of each generator (M:221, 273, 319, 337-338, 352)."""
     if mode == "Wavelet atoms":
         return WAVELET_FLOOR
-    if mode == "Image scanline":
+    if mode in ("Image scanline", "Micro-chaos"):
         return 64
     if mode == "IR fragment":
         ir = params.get("_ir_audio")
@@ -620,7 +634,7 @@ def render(params, progress=None, taps=None, jitter=None):
         if params[flag]:
             raise NotImplementedError(f"oracle: '{flag}' is a SURVEY 8(f) 'next' row, not restated yet")
     mode = params["gen_mode"]
-    if mode in ("Stick–slip friction", "Micro-chaos"):
+    if mode in ("Stick–slip friction",):
         raise NotImplementedError(f"oracle: generator '{mode}' is a SURVEY 8(f) 'next' row")
     plan = plan_events(params)
     base_sr, out_n = plan["base_sr"], plan["out_n"]
@@ -640,6 +654,8 @@ def render(params, progress=None, taps=None, jitter=None):
         elif mode == "Crackle / corona":
             g = crackle(ev["gen_sr"], micro_ms, seed + i, float(params["crackle_alpha"]), float(params["crackle_density"]),
                         int(params["crackle_kernel"]))
+        elif mode == "Micro-chaos":
+            g = micro_chaos(ev["gen_sr"], micro_ms, seed + i, float(params["chaos_r"]), float(params["chaos_gate"]))
         elif mode == "IR fragment":
             g = ir_fragment(params.get("_ir_audio"), ev["gen_sr"], micro_ms, seed + i)
         elif mode == "Image scanline":

@@ -267,6 +267,12 @@ PRESET_LIKE = {
     "ghost_formants": dict(gen_mode="Noise burst", micro_ms=1.1, noise_tilt=-6.0, cep_warp_on=True, cep_factor=1.45,
                            partial_stretch=0.92, event_process="Poisson", grains_per_sec=12, bp_cutoff="0:16000, 6:9000, 12:6000",
                            er_cloud_on=True, er_taps=260, er_max_ms=42),
+    "chaotic_dustfield": dict(gen_mode="Micro-chaos", micro_ms=0.9, chaos_r=3.97, chaos_gate=0.42, event_process="Poisson",
+                              grains_per_sec=9, bp_density="0:6, 3:14, 5:28, 9:10", nl_warp_on=True, nl_warp_power=1.6,
+                              bandlimit_out_hz=14000, er_taps=180, er_max_ms=38),
+    "elliptical_insect_hum": dict(gen_mode="Micro-chaos", micro_ms=1.4, chaos_r=3.91, chaos_gate=0.22,
+                                  unfold_mode="Multi-band unfold", mb_u1=34, mb_u2=22, mb_u3=14, event_process="Poisson",
+                                  grains_per_sec=8, nl_warp_on=True, nl_warp_power=1.2, er_taps=210, er_max_ms=36),
     "soft_ellipse_memory": dict(gen_mode="Noise burst", micro_ms=2.2, noise_tilt=-8.0, event_process="Poisson",
                                 grains_per_sec=6, spectral_imprint_on=True, spectral_imprint_amt=0.25,
                                 spectral_imprint_smooth=0.97, partial_stretch=0.95, bp_cutoff="0:14000, 12:9000, 24:6000",

@@ -159,9 +159,12 @@ def test_partial_lock(emul, kw):
                                 dict(gen_mode="IR fragment", _ir_audio=configs.synth_ir(0.25, 48000, 11, channels=1)),
                                 dict(gen_mode="IR fragment"),                                     # no IR loaded: silence
                                 dict(gen_mode="Image scanline", _img_gray=np.random.default_rng(5).integers(0, 256, (40, 300)).astype(np.uint8)),
-                                dict(gen_mode="Image scanline")])
+                                dict(gen_mode="Image scanline"),
+                                dict(gen_mode="Micro-chaos"),
+                                dict(gen_mode="Micro-chaos", chaos_r=3.99, chaos_gate=0.9, micro_ms=3.0, seed=20000)])
 def test_next_row_generators(emul, kw):
-    """gen_crackle (main_v2.py:271-281), gen_ir_fragment (:333-348), gen_image_scanline (:350-362)."""
+    """gen_crackle (main_v2.py:271-281), gen_ir_fragment (:333-348), gen_image_scanline (:350-362), gen_micro_chaos
+    (:303-315; the logistic map must stay bit-identical over thousands of iterations)."""
     p = configs.with_defaults(event_process="Poisson", out_dur_s=0.6, grains_per_sec=20.0, er_cloud_on=False, **kw)
     K.check_render(emul, p, "f64")
 

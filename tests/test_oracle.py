@@ -154,7 +154,8 @@ def test_wavelet_grain_shorter_than_its_atoms_fails_like_the_reference():
                                   "soft_ellipse_memory", "micro_carillon", "oval_glass_orbit", "glass_harmonic_arc",
                                   "01_corona_glass_fog", "corona_memory_glass", "melodic_dust_chime", "oval_room_trace",
                                   "room_as_particle", "image_grain_hallucination", "closed_curve_air",
-                                  "drifting_mode_fragments", "ghost_formants", "corona_glass_fog", "chaotic_dustfield"])
+                                  "drifting_mode_fragments", "ghost_formants", "corona_glass_fog", "chaotic_dustfield",
+                                  "elliptical_insect_hum", "orbital_friction_loop"])
 def test_oracle_matches_reference_on_shipped_presets(name):
     """The shipped presets that need only accelerated rows, merged over the factory defaults the way on_load_preset
     does (main_v2.py:1286-1291), first 3 s."""
@@ -163,7 +164,7 @@ def test_oracle_matches_reference_on_shipped_presets(name):
     path = os.path.join(ref_loader.REFERENCE_ROOT, "microsound_0.2.1", "presets", name + ".json")
     p = configs.with_defaults(json.load(open(path)))
     p["out_dur_s"] = 3.0
-    if name == "chaotic_dustfield":                  # generator not restated: both sides must say so, not guess
+    if name == "orbital_friction_loop":              # generator not restated: both sides must say so, not guess
         with pytest.raises(NotImplementedError):
             O.render(p)
         return

@@ -68,7 +68,7 @@ def test_missing_key_raises_keyerror_like_reference():
 
 def test_unsupported_rows_fail_loudly():
     with pytest.raises(NotImplementedError):
-        P.plan_render(configs.with_defaults(gen_mode="Micro-chaos"))
+        P.plan_render(configs.with_defaults(gen_mode="Stick–slip friction"))
     with pytest.raises(NotImplementedError):
         P.plan_render(configs.with_defaults(res_bank_on=True))
     P.plan_render(configs.with_defaults(partial_lock_on=True, nl_warp_on=True))
