@@ -45,6 +45,15 @@ class SynthEvt(C.Structure):
                 ("atom_begin", C.c_int64), ("atom_count", C.c_int32), ("_pad", C.c_int32)]
 
 
+class ResMode(C.Structure):
+    _fields_ = [("f_over_sr", C.c_double), ("phase", C.c_double), ("weight", C.c_double)]
+
+
+class ResEvt(C.Structure):
+    _fields_ = [("src", C.c_int64), ("dst", C.c_int64), ("n", C.c_int32), ("mode_begin", C.c_int32),
+                ("mode_count", C.c_int32), ("_pad", C.c_int32), ("decay", C.c_double)]
+
+
 class PlockEvt(C.Structure):
     _fields_ = [("z", C.c_int64), ("scratch", C.c_int64), ("n", C.c_int32), ("top_n", C.c_int32), ("neigh", C.c_int32),
                 ("_pad", C.c_int32), ("factor", C.c_double), ("pre", SpecOp)]
@@ -112,6 +121,7 @@ _STAGES = {
     "ms_spectral_z_table": (_I, [_P, _P, C.POINTER(C.c_size_t)]),
     "ms_imprint": (_I, [_P, _P, _I, _I, _P, _P]),
     "ms_partial_lock": (_I, [_P, _I, _P, _P, _P]),
+    "ms_resonator": (_I, [_P, _I, _P, _P, _P]),
     "ms_cepstral": (_I, [_I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "ms_spectral_destroy": (None, [_P]),
     "ms_fft_pair_forward": (_I, [_P, _P, _I, _P, _P, _Z, _P]),

@@ -330,3 +330,37 @@ MS_DEV void cepstral_body(const CepEvt* MS_RESTRICT evts, cpx* z1, cpx* z2, cons
         z1[E.z1 + i] = mag > 0.0 ? mk((real)(g * ((double)x.x / mag)), (real)(g * ((double)x.y / mag))) : mk((real)g, (real)0.);
     }
 }
+
+// ---- resonator bank (resonator_bank, main_v2.py:369-384) ------------------------------------------------------------
+// One CTA per grain: pass 1 writes the bank (sum of decaying sinusoids, float64 phase) to dst and takes its peak,
+// pass 2 overwrites dst with 0.55 x + 0.45 (bank / peak) sign(x).
+typedef ms_res_evt ResEvt;
+typedef ms_res_mode ResMode;
+MS_DEV void resonator_body(const ResEvt* MS_RESTRICT evts, const ResMode* MS_RESTRICT modes, real* pool, const Ctx& c) {
+    const ResEvt E = evts[c.bx];
+    const real* x = pool + E.src;
+    real* y = pool + E.dst;
+    const ResMode* Mo = modes + E.mode_begin;
+    real* red = (real*)c.smem;
+    real mx = (real)0.;
+    for (int j = c.tid; j < E.n; j += c.nthr) {
+        double acc = 0.0;
+        for (int k = 0; k < E.mode_count; ++k) {
+            double cyc = (double)j * Mo[k].f_over_sr;
+            cyc -= floor(cyc);
+            acc += Mo[k].weight * sin(6.283185307179586476925286766559 * cyc + Mo[k].phase);
+        }
+        const real v = (real)(acc * exp(-(double)j * E.decay));
+        y[j] = v;
+        mx = r_max(mx, r_abs(v));
+    }
+    red[c.tid] = mx;
+    c.sync();
+    for (int s = c.nthr >> 1; s > 0; s >>= 1) { if (c.tid < s) red[c.tid] = r_max(red[c.tid], red[c.tid + s]); c.sync(); }
+    const real inv = (real)1.0 / r_max((real)1e-12, red[0]);
+    for (int j = c.tid; j < E.n; j += c.nthr) {
+        const real xv = x[j];
+        const real sg = xv > (real)0. ? (real)1. : (xv < (real)0. ? (real)-1. : (real)0.);
+        y[j] = (real)0.55 * xv + (real)0.45 * (y[j] * inv) * sg;
+    }
+}

@@ -251,6 +251,15 @@ class BatchRenderer:
         self.tilt_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.tilt), self.pool, self.pool)
         self.grain_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.grain), self.pool, self.pool)
         self.rot_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.rot), self.mono, self.mono)
+        # resonator bank (time domain) and the multiband unfold that follows it
+        self.n_res = 0
+        self.post_stage = None
+        if t.res is not None and len(t.res[0]):
+            rows, decay, modes = t.res
+            ev = np.zeros(len(rows), np.dtype(_abi.ResEvt))
+            ev["src"], ev["dst"], ev["n"], ev["mode_begin"], ev["mode_count"], ev["decay"] = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4], decay
+            self.d_res_evt, self.d_res_modes, self.n_res = dev.upload(ev), dev.upload(np.ascontiguousarray(modes)), len(rows)
+            self.post_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.post_grain), self.pool, self.pool)
         # cepstral warp: three stages of single-signal jobs around the elementwise steps of ms_cepstral
         self.cep_stages = None
         if t.cep is not None and len(t.cep[0]):
@@ -392,6 +401,10 @@ class BatchRenderer:
                 _check(dev, lib.ms_partial_lock(dev.ptr(self.d_plock_evt), self.n_plock, zptr, dev.ptr(self.plock_scratch), st))
                 self.plock_stage.inverse()
                 mark("partial_lock")
+            if self.n_res:
+                _check(dev, lib.ms_resonator(dev.ptr(self.d_res_evt), self.n_res, dev.ptr(self.d_res_modes), dev.ptr(self.pool), st))
+                self.post_stage.run()
+                mark("resonator_bank")
             if self.imprint_stage is not None:
                 self.imprint_stage.forward()
                 zptr = C.c_void_p(dev.ptr(self.imprint_stage.ws).value + self.imprint_zbase)
@@ -435,7 +448,7 @@ class BatchRenderer:
         return m
 
     def close(self):
-        for s in (self.tilt_stage, self.grain_stage, self.rot_stage, self.imprint_stage, self.plock_stage) + tuple(self.cep_stages or ()):
+        for s in (self.tilt_stage, self.grain_stage, self.rot_stage, self.imprint_stage, self.plock_stage, self.post_stage) + tuple(self.cep_stages or ()):
             if s is not None:
                 s.close()
         if self.fir_handle:

@@ -26,7 +26,7 @@ MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET
 WAVELET_FLOOR = 128                 # M:319
 _MODE_ID = {m: i for i, m in enumerate(BASIC_MODES)}
 
-_NEXT_ROW_FLAGS = ("res_bank_on", "wg_on", "event_feedback_on")
+_NEXT_ROW_FLAGS = ("wg_on", "event_feedback_on")
 _NEXT_ROW_MODES = ("Stick–slip friction",)
 
 
@@ -160,7 +160,7 @@ def bin_spacing(n, sr):
     return 1.0 / (n * (1.0 / sr))
 
 
-def grain_spec_op(params, gen_sr, n, cutoff_gen, stretch, pre=True, post=True, keep=False):
+def grain_spec_op(params, gen_sr, n, cutoff_gen, stretch, pre=True, post=True, keep=False, mb=True):
     """Spectral operator of one event: lowpass_fft -> fft_warp_power -> fft_partial_stretch -> unfold_multiband
     (M:690-727), or None when every stage is an identity (unless `keep`).  `pre` / `post` select the stages before
     (low-pass, warp) and after (stretch, multiband) the point where partial_lock_stretch sits."""
@@ -172,6 +172,8 @@ def grain_spec_op(params, gen_sr, n, cutoff_gen, stretch, pre=True, post=True, k
         params = dict(params, bandlimit_on=False, nl_warp_on=False)
     if not post:
         params, stretch = dict(params, unfold_mode="Classic reinterpret"), 1.0
+    if not mb:
+        params = dict(params, unfold_mode="Classic reinterpret")
     if params["bandlimit_on"] and n >= 8:
         op.lp_on = 1
         op.lp = lowpass_edge(gen_sr, cutoff_gen, float(params["bandlimit_roll_hz"]))
@@ -222,6 +224,8 @@ class EventPlan:
     spec: Optional[object] = None           # _abi.SpecOp or None
     plock: Optional[tuple] = None           # (factor, top_n, neigh, pre-operator) when partial_lock_stretch is active
     cep: Optional[tuple] = None             # (factor, pre-operator) when cepstral_warp is active
+    res: Optional[tuple] = None             # (modes float64 [K, 3] = f/sr, phase, weight ; decay per sample) for resonator_bank
+    spec_b: Optional[object] = None         # multiband operator applied AFTER the resonator bank
     tilt: Optional[object] = None           # _abi.SpecOp for the tilted-noise modes
     dust_pos: Optional[np.ndarray] = None   # sorted unique impulse positions (int32)
     dust_val: Optional[np.ndarray] = None   # float64 values (last write wins, M:243)
@@ -337,23 +341,29 @@ def plan_render(params) -> RenderPlan:
                 ev.offset = int(rng.integers(0, max(1, min(max_off, n))))
             ev.length = max(0, min(out_n - ev.start, n - ev.offset))
             ev.placed = ev.length > 0
+        res_on = bool(params["res_bank_on"]) and n >= 32                 # M:372
+        mb_here = not res_on                                             # the multiband unfold follows the resonator (M:719-727)
         if params["cep_warp_on"] and n >= 64:
             # M:696-697: cepstral_warp sits between low-pass / power warp and the stretch; its three elementwise steps
             # run between transforms of their own, the stage's inverse applies stretch + multiband
             if params["partial_lock_on"] and not abs(ev.stretch - 1.0) < 1e-9:
                 raise NotImplementedError("microsound_b200: cep_warp_on together with an active partial lock is not on the accelerated path yet")
             ev.cep = (float(params["cep_factor"]), grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, post=False, keep=True))
-            ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0 if params["partial_lock_on"] else ev.stretch, pre=False, keep=True)
+            ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0 if params["partial_lock_on"] else ev.stretch, pre=False,
+                                    keep=True, mb=mb_here)
         elif params["partial_lock_on"]:
             # M:699-702: partial_lock_stretch REPLACES fft_partial_stretch; it is the identity for n < 64 or a factor of 1
             if n >= 64 and not abs(ev.stretch - 1.0) < 1e-9:
                 ev.plock = (ev.stretch, int(params["pl_top_n"]), int(params["pl_neigh"]),
                             grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, post=False, keep=True))
-                ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, pre=False, keep=True)
+                ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, pre=False, keep=True, mb=mb_here)
             else:
-                ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0)
+                ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, mb=mb_here)
         else:
-            ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, ev.stretch)
+            ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, ev.stretch, mb=mb_here)
+        if res_on:
+            ev.res = _plan_resonator(params, seed + i, sr_evt)
+            ev.spec_b = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, pre=False)       # multiband only, or None
         ev.fade = max(8, int(0.01 * n))
         if mode == MODE_GAUSS:
             ev.sigma = max(1, int(0.0025 * n))
@@ -455,6 +465,20 @@ def _plan_wavelet(ev, micro_ms, base_hz, count, spread):
         sigma = max(1e-9, sigma_ms / 1000.0)
         atoms[k] = (f0 / ev.gen_sr, 1.0 / (sigma * ev.gen_sr), phase, 1.0 / (1 + k * 0.6))
     ev.atoms, ev.atom_shift = atoms, shifts
+
+
+def _plan_resonator(params, seed, sr):
+    """Scalar draws of resonator_bank (M:370, 377-380)."""
+    rng = np.random.default_rng(int(seed) + 321)
+    modes = int(max(1, int(params["res_modes"])))
+    f_min, f_max = float(params["res_fmin"]), float(params["res_fmax"])
+    rows = np.zeros((modes, 3), dtype=np.float64)
+    for k in range(modes):
+        f = f_min * ((f_max / max(1.0, f_min)) ** (k / max(1, modes - 1)))
+        f *= 2.0 ** rng.uniform(-0.02, 0.02)
+        rows[k] = (f / sr, rng.uniform(0, 2 * np.pi), 1.0 / (1 + k * 0.35))
+    tau = max(1e-6, float(params["res_decay_ms"]) / 1000.0)
+    return rows, 1.0 / (tau * sr)
 
 
 def _plan_crackle(ev, alpha, density, kernel):

@@ -90,6 +90,8 @@ class Tables:
     dust_val: np.ndarray = None
     atoms: np.ndarray = None        # wavelet atoms, float64 [N, 4]
     atom_shift: np.ndarray = None   # int32 [N]
+    res: tuple = None               # (rows int64 [N, 5] = src, dst, n, mode_begin, mode_count ; decay [N] ; modes float64 [M, 3])
+    post_grain: tuple = None        # spectral items applied after the resonator bank (multiband): (n, src, dst, ops)
     cep: tuple = None               # (rows int64 [N, 3] = src, dst, n ; factor [N] ; pre ops [N, B] ; post ops [N, B])
     plock: tuple = None             # (rows int64 [N, 5] = src, dst, n, top_n, neigh ; factor [N] ; pre ops [N, B] ; post ops [N, B])
     imprint: np.ndarray = None      # rows per imprinted event, in event order per render: render, pool_in, pool_out, n
@@ -125,6 +127,8 @@ def pack_chunk(plans) -> Tables:
     imprint_rows, imprint_par = [], np.full((R, 2), np.nan)
     pl_rows, pl_factor, pl_pre, pl_post = [], [], [], []
     cp_rows, cp_factor, cp_pre, cp_post = [], [], [], []
+    rs_rows, rs_decay, rs_modes, n_modes = [], [], [], 0
+    post_grain = _Items()
     tap_off, tap_gain, n_taps = [], [], 0
     irs, ir_index, n_ir = [], {}, 0
     pool_n = mono_n = h_total = max_h = 0
@@ -211,6 +215,20 @@ def pack_chunk(plans) -> Tables:
                 grain.add(ev.n, micro, g_at, ev.spec)
                 alg["grain_spectral"] += 2 * ev.n * (int(ev.spec.lp_on) + int(ev.spec.stretch_on) + (1 if ev.spec.n_bands else 0)
                                                      + (1 if ev.spec.warp_exp else 0))
+            if ev.res is not None:
+                r_at = pool_n                      # the resonator reads the grain so far and writes a new one
+                pool_n += ev.n
+                rs_rows.append((g_at, r_at, ev.n, n_modes, len(ev.res[0])))
+                rs_decay.append(ev.res[1])
+                rs_modes.append(ev.res[0])
+                n_modes += len(ev.res[0])
+                g_at = r_at
+                if ev.spec_b is not None:
+                    b_at = pool_n
+                    pool_n += ev.n
+                    post_grain.add(ev.n, g_at, b_at, ev.spec_b)
+                    alg["grain_spectral"] += 2 * ev.n
+                    g_at = b_at
             last[r] = (micro, g_at, ev.n)
             if rp.imprint is not None and ev.n >= 64 and rp.imprint[0] > 0:         # M:570: short grains / amount <= 0 pass through
                 src = g_at
@@ -328,6 +346,9 @@ def pack_chunk(plans) -> Tables:
     t.plock = (np.asarray(pl_rows, np.int64).reshape(-1, 5), np.asarray(pl_factor, np.float64),
                np.frombuffer(b"".join(pl_pre), np.uint8).reshape(npl, _SPEC_OP_BYTES) if npl else np.zeros((0, _SPEC_OP_BYTES), np.uint8),
                np.frombuffer(b"".join(pl_post), np.uint8).reshape(npl, _SPEC_OP_BYTES) if npl else np.zeros((0, _SPEC_OP_BYTES), np.uint8))
+    t.res = (np.asarray(rs_rows, np.int64).reshape(-1, 5), np.asarray(rs_decay, np.float64),
+             np.concatenate(rs_modes) if rs_modes else np.zeros((0, 3)))
+    t.post_grain = post_grain.arrays()
     ncp = len(cp_rows)
     t.cep = (np.asarray(cp_rows, np.int64).reshape(-1, 3), np.asarray(cp_factor, np.float64),
              np.frombuffer(b"".join(cp_pre), np.uint8).reshape(ncp, _SPEC_OP_BYTES) if ncp else np.zeros((0, _SPEC_OP_BYTES), np.uint8),
@@ -357,7 +378,8 @@ def merge_chunks(chunks) -> Tables:
     pool_b = mono_b = frame_b = h_b = tap_b = ir_b = dust_b = olae_b = env_b = atom_b = render_b = 0
     parts = {k: [] for k in ("sy1", "sy2", "ola_r", "env_reps", "ola_e", "fir", "post", "tap_off", "tap_gain", "irs", "dust_pos", "dust_val",
                              "atoms", "atom_shift", "imprint", "imprint_par", "odd", "out_at", "out_n", "y_at", "last", "srs")}
-    items = {k: [[], [], [], []] for k in ("tilt", "grain", "rot")}
+    items = {k: [[], [], [], []] for k in ("tilt", "grain", "rot", "post_grain")}
+    rs_parts, mode_b = [[], [], []], 0
     pl_parts = [[], [], [], []]
     cp_parts = [[], [], [], []]
     alg = {}
@@ -398,7 +420,13 @@ def merge_chunks(chunks) -> Tables:
             c.last[:, 0:2] += np.where(c.last[:, 0:2] >= 0, pool_b, 0)
         for k in parts:
             parts[k].append(getattr(c, k))
-        for k, base in (("tilt", pool_b), ("grain", pool_b), ("rot", mono_b)):
+        if c.res[0].size:
+            c.res[0][:, 0:2] += pool_b
+            c.res[0][:, 3] += mode_b
+        for i in range(3):
+            rs_parts[i].append(c.res[i])
+        mode_b += len(c.res[2])
+        for k, base in (("tilt", pool_b), ("grain", pool_b), ("rot", mono_b), ("post_grain", pool_b)):
             n, s, d, ops = getattr(c, k)
             items[k][0].append(n)
             items[k][1].append(s + base)
@@ -424,6 +452,7 @@ def merge_chunks(chunks) -> Tables:
     for k in items:
         setattr(m, k, tuple(np.concatenate(x) for x in items[k]))
     m.plock = tuple(np.concatenate(x) for x in pl_parts)
+    m.res = tuple(np.concatenate(x) for x in rs_parts)
     m.cep = tuple(np.concatenate(x) for x in cp_parts)
     m.pool_n, m.mono_n, m.frames, m.h_total, m.alg, m.env_n = pool_b, mono_b, frame_b, h_b, alg, env_b
     return m

@@ -91,6 +91,15 @@ typedef struct {
 typedef struct { int64_t z; int32_t n, _pad; } ms_imprint_evt;               /* z: offset of the grain's spectrum, complex elements */
 typedef struct { int32_t ev_begin, ev_end; double amount, smooth; } ms_imprint_render;
 /* ms_imprint_f32 / ms_imprint_f64: declared below by MS_DECLARE_API */
+/* resonator_bank (main_v2.py:369-384) on time-domain grains: dst = 0.55 src + 0.45 bank sign(src), bank = the
+ * peak-normalised sum of decaying sinusoids whose frequencies / phases the host drew.  One CTA per grain. */
+typedef struct { double f_over_sr, phase, weight; } ms_res_mode;
+typedef struct {
+    int64_t src, dst;        /* pool offsets */
+    int32_t n, mode_begin, mode_count, _pad;
+    double decay;            /* 1 / (tau * sr): env[j] = exp(-j * decay) */
+} ms_res_evt;
+/* ms_resonator_f32 / ms_resonator_f64: declared below by MS_DECLARE_API */
 /* partial_lock_stretch (main_v2.py:130-148) on the spectrum of one grain (single-signal job, after
  * ms_spectral_forward): W = low-pass / power warp of the grain's spectrum (`pre`), the top_n strongest bins of W
  * (DC excluded) are moved to round(k * factor) with a triangular spread over +-neigh bins on top of 0.12 W, and the
@@ -230,6 +239,7 @@ typedef struct {
     int ms_spectral_forward##SFX(void* handle, void* stream); \
     int ms_spectral_inverse##SFX(void* handle, void* stream); \
     int ms_spectral_z_table##SFX(void* handle, int64_t* host_z_offsets, size_t* z_base_bytes); \
+    int ms_resonator##SFX(const ms_res_evt* dev_evts, int n_evts, const ms_res_mode* dev_modes, REAL* pool, void* stream); \
     int ms_partial_lock##SFX(const ms_plock_evt* dev_evts, int n_evts, REAL* z_base, REAL* scratch, void* stream); \
     int ms_cepstral##SFX(int step, const ms_cep_evt* dev_evts, int n_evts, int max_n, REAL* z1_base, REAL* z2_base, \
     REAL* z3_base, REAL* scratch, void* stream); \

@@ -192,6 +192,33 @@ def cepstrum_warp(x, factor):
     return np.fft.irfft(mag * np.exp(1j * np.angle(spec)), n=n)
 
 
+def resonator_modes(seed, modes, f_min, f_max):
+    """Scalar draws of resonator_bank (M:370, 377-380): per mode a log-spaced frequency detuned by 2**U(-.02, .02),
+    a phase in [0, 2 pi) and the weight 1 / (1 + 0.35 k)."""
+    rng = np.random.default_rng(int(seed) + 321)
+    rows = []
+    for k in range(int(max(1, modes))):
+        f = float(f_min) * ((float(f_max) / max(1.0, float(f_min))) ** (k / max(1, modes - 1)))
+        f *= 2.0 ** rng.uniform(-0.02, 0.02)
+        rows.append((f, rng.uniform(0, 2 * np.pi), 1.0 / (1 + k * 0.35)))
+    return rows
+
+
+def resonator_bank(x, sr, modes, f_min, f_max, decay_ms, seed):
+    """M:369-384 -- a bank of decaying sinusoids, peak-normalised, mixed in with the SIGN of the input:
+    0.55 x + 0.45 bank sign(x).  (Where x is rounding noise its sign is too: see rounding_noise_floor.)"""
+    n = len(x)
+    if n < 32:
+        return x
+    t = np.arange(n, dtype=np.float64) / sr
+    env = np.exp(-t / max(1e-6, decay_ms / 1000.0))
+    bank = np.zeros_like(x)
+    for f, ph, w in resonator_modes(seed, modes, f_min, f_max):
+        bank += w * np.sin(2 * np.pi * f * t + ph) * env
+    bank = bank / max(1e-12, np.max(np.abs(bank)))
+    return 0.55 * x + 0.45 * (x * 0.0 + bank) * np.sign(x)
+
+
 def multiband_unfold(x, gen_sr, bands_out_hz, unfolds, roll_hz):
     """M:492-500 -- sum of band-passed copies, band edges scaled by each band's unfold."""
     acc = None
@@ -554,8 +581,9 @@ class ImprintMemory:
 def rounding_noise_floor(params, reference_audio=None):
     """max-abs change of the rendered audio under a 1e-15 relative perturbation of the grains entering the cepstral
     warp / the spectral imprint: the part of the reference's output that is decided by float64 rounding noise
-    (0.0 when neither is on)."""
-    if not (params["spectral_imprint_on"] or params["cep_warp_on"]):
+    (0.0 when none is on).  resonator_bank multiplies by np.sign(x): where the grain has decayed below its own
+    rounding noise the sign -- and with it 45 % of the output there -- is noise."""
+    if not (params["spectral_imprint_on"] or params["cep_warp_on"] or params["res_bank_on"]):
         return 0.0
     a = reference_audio if reference_audio is not None else render(params)[0]
     b = render(params, jitter=1e-15)[0]
@@ -566,7 +594,7 @@ imprint_noise_floor = rounding_noise_floor
 
 
 # --------------------------------------------------------------------------- render
-_UNSUPPORTED_FLAGS = ( "res_bank_on", "wg_on",
+_UNSUPPORTED_FLAGS = ("wg_on",
                       "event_feedback_on")
 
 
@@ -679,6 +707,11 @@ def render(params, progress=None, taps=None, jitter=None):
             g = partial_lock(g, ev["stretch"], int(params["pl_top_n"]), int(params["pl_neigh"]))
         else:
             g = spectrum_stretch(g, ev["stretch"])
+        if params["res_bank_on"]:                                                 # M:704-710
+            if jitter:
+                g = g + jitter * np.max(np.abs(g)) * np.random.default_rng(333 + i).standard_normal(g.size)
+            g = resonator_bank(g, ev["gen_sr"], int(params["res_modes"]), float(params["res_fmin"]), float(params["res_fmax"]),
+                               float(params["res_decay_ms"]), seed + i)
         if params["unfold_mode"] != "Classic reinterpret":
             b1, b2, b3 = float(params["mb_b1"]), float(params["mb_b2"]), float(params["mb_b3"])
             g = multiband_unfold(g, ev["gen_sr"], [(0, b1), (b1, b2), (b2, b3)],

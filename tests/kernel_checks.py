@@ -273,6 +273,14 @@ PRESET_LIKE = {
     "elliptical_insect_hum": dict(gen_mode="Micro-chaos", micro_ms=1.4, chaos_r=3.91, chaos_gate=0.22,
                                   unfold_mode="Multi-band unfold", mb_u1=34, mb_u2=22, mb_u3=14, event_process="Poisson",
                                   grains_per_sec=8, nl_warp_on=True, nl_warp_power=1.2, er_taps=210, er_max_ms=36),
+    "infra_mechanical_choir": dict(gen_mode="Resonant strike", micro_ms=3.5, ring_hz=420, ring_decay_ms=90, res_bank_on=True,
+                                   res_modes=36, res_fmin=90, res_fmax=4200, res_decay_ms=160, partial_lock_on=True,
+                                   partial_stretch=0.88, event_process="Clustered", grains_per_sec=8, cluster_spread_ms=40,
+                                   bp_unfold="0:18, 6:40, 14:22"),
+    "infra_tone_lattice": dict(gen_mode="Resonant strike", micro_ms=2.8, ring_hz=180, ring_decay_ms=120, res_bank_on=True,
+                               res_fmin=90, res_fmax=1800, res_decay_ms=220, partial_lock_on=True, partial_stretch=1.02,
+                               event_process="Poisson", grains_per_sec=6, spectral_imprint_on=True, spectral_imprint_amt=0.22,
+                               er_taps=300, er_max_ms=60),
     "soft_ellipse_memory": dict(gen_mode="Noise burst", micro_ms=2.2, noise_tilt=-8.0, event_process="Poisson",
                                 grains_per_sec=6, spectral_imprint_on=True, spectral_imprint_amt=0.25,
                                 spectral_imprint_smooth=0.97, partial_stretch=0.95, bp_cutoff="0:14000, 12:9000, 24:6000",

@@ -186,3 +186,14 @@ def test_cepstral_warp(emul, kw):
         assert err < 1e-6
     else:
         assert O.rounding_noise_floor(p) > 1e-3          # the reference itself moves by this much under a 1e-15 jitter
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(unfold_mode="Multi-band unfold", partial_stretch=1.2),
+                                dict(partial_lock_on=True, partial_stretch=0.88, res_modes=36, res_fmin=90, res_fmax=4200,
+                                     res_decay_ms=160, micro_ms=3.5),
+                                dict(gen_mode="Wavelet atoms", nl_warp_on=True, unfold_mode="Multi-band unfold", spectral_imprint_on=True)])
+def test_resonator_bank(emul, kw):
+    """resonator_bank (main_v2.py:369-384) between the stretch / partial lock and the multiband unfold."""
+    base = dict(event_process="Poisson", out_dur_s=0.6, grains_per_sec=20.0, er_cloud_on=False, res_bank_on=True, gen_mode="Resonant strike")
+    base.update(kw)
+    assert K.check_render(emul, configs.with_defaults(base), "f64") < 1e-6

@@ -155,7 +155,8 @@ def test_wavelet_grain_shorter_than_its_atoms_fails_like_the_reference():
                                   "01_corona_glass_fog", "corona_memory_glass", "melodic_dust_chime", "oval_room_trace",
                                   "room_as_particle", "image_grain_hallucination", "closed_curve_air",
                                   "drifting_mode_fragments", "ghost_formants", "corona_glass_fog", "chaotic_dustfield",
-                                  "elliptical_insect_hum", "orbital_friction_loop"])
+                                  "elliptical_insect_hum", "infra_mechanical_choir",
+                                  "infra_tone_lattice", "03_wavelet_ice_bloom", "orbital_friction_loop"])
 def test_oracle_matches_reference_on_shipped_presets(name):
     """The shipped presets that need only accelerated rows, merged over the factory defaults the way on_load_preset
     does (main_v2.py:1286-1291), first 3 s."""

@@ -70,7 +70,7 @@ def test_unsupported_rows_fail_loudly():
     with pytest.raises(NotImplementedError):
         P.plan_render(configs.with_defaults(gen_mode="Stick–slip friction"))
     with pytest.raises(NotImplementedError):
-        P.plan_render(configs.with_defaults(res_bank_on=True))
+        P.plan_render(configs.with_defaults(wg_on=True))
     P.plan_render(configs.with_defaults(partial_lock_on=True, nl_warp_on=True))
     P.plan_render(configs.with_defaults(gen_mode="Wavelet atoms"))          # accelerated since
     P.plan_render(configs.with_defaults(spectral_imprint_on=True))
