@@ -55,3 +55,31 @@ def gather_frames(local, frames_per_rank, dist, rank, world, dst=0):
         return [b[:2 * f] for b, f in zip(bufs, frames_per_rank)]
     dist.gather(local, gather_list=None, dst=dst)
     return None
+
+
+class SlicedGather:
+    """Gather of per-rank rendered buffers that overlaps with rendering: every rank cuts its renders into `slices`
+    equal parts; as soon as slice k has been rendered its buffer is gathered on rank `dst` (NCCL runs the collective
+    on its own stream) while slice k+1 renders.  Receive buffers are allocated once."""
+
+    def __init__(self, frames_per_slice, dist, rank, world, device, dst=0):
+        import torch
+        self.dist, self.rank, self.world, self.dst = dist, rank, world, dst
+        self.frames = list(frames_per_slice)
+        self.recv = None
+        if rank == dst:
+            self.recv = [[torch.empty(2 * f, dtype=torch.float32, device=device) for _ in range(world)] for f in self.frames]
+        self.pending = []
+
+    def start(self, k, local):
+        """local: this rank's 1-D float32 buffer of slice k (2 * frames[k] values on every rank)."""
+        if local.numel() != 2 * self.frames[k]:
+            raise ValueError("slice buffers must have the same size on every rank")
+        w = self.dist.gather(local, gather_list=self.recv[k] if self.rank == self.dst else None, dst=self.dst, async_op=True)
+        self.pending.append(w)
+
+    def finish(self):
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+        return self.recv

@@ -62,7 +62,14 @@ def _worker(rank, world, port, n_items, q):
     local = torch.from_numpy(np.asarray(br.out).copy())
     frames = [sum(int(round(_sweep(i)["out_dur_s"] * 48000)) for i in parallel.partition(n_items, world, r)) for r in range(world)]
     got = parallel.gather_frames(local, frames, dist, rank, world)
+    # the overlapped form bench.py uses: equal slices per rank, gathered asynchronously one by one
+    sg = parallel.SlicedGather([1000, 500], dist, rank, world, torch.device("cpu"))
+    parts = [torch.full((2000,), float(rank + 1)), torch.full((1000,), float(10 * (rank + 1)))]
+    for k, part in enumerate(parts):
+        sg.start(k, part)
+    recv = sg.finish()
     if rank == 0:
+        assert [float(recv[0][r][0]) for r in range(world)] == [1.0, 2.0] and [float(recv[1][r][-1]) for r in range(world)] == [10.0, 20.0]
         q.put([g.numpy().copy() for g in got])
     dist.barrier()
     dist.destroy_process_group()
