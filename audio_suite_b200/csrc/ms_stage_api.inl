@@ -27,8 +27,11 @@ template <int STEP> struct CepstralK { static constexpr int MAXT = 256;
 struct ImprintK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const ImprintEvt* e, const ImprintRender* r, cpx* z, const Ctx& c) { imprint_body(e, r, z, c); } };
+#ifndef MS_OLA_MINB
+#define MS_OLA_MINB 1
+#endif
 struct OlaK { static constexpr int MAXT = OLA_NTHR;
-    static constexpr int MINB = 1;
+    static constexpr int MINB = MS_OLA_MINB;
     static MS_DEV void run(const OlaRender* r, const OlaEvt* e, const real* pool, const real* env, real* mono, const Ctx& c) { ola_adsr_body(r, e, pool, env, mono, c); } };
 struct AdsrTableK { static constexpr int MAXT = OLA_NTHR;
     static constexpr int MINB = 1;

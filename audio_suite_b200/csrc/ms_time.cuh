@@ -14,7 +14,7 @@ typedef ms_ola_render OlaRender;
 typedef ms_ola_evt OlaEvt;
 
 
-MS_DEV real adsr_gain(const OlaRender& R, int i) {
+MS_DEV real adsr_gain(const OlaRender& R, int i) {      // (kept inline: an out-of-line call was measured slower, 1.56 -> 2.05 ms)
     // Evaluated in the working precision: an error relative to a loud sample is still an error relative
     // to the peak, and the FIR gain + soft clip downstream turn 1e-7 of that into 1e-5 (precision).
     const real S = (real)R.S, curve = (real)R.curve;
