@@ -45,6 +45,15 @@ class SynthEvt(C.Structure):
                 ("atom_begin", C.c_int64), ("atom_count", C.c_int32), ("_pad", C.c_int32)]
 
 
+class WgLine(C.Structure):
+    _fields_ = [("d", C.c_int32), ("_pad", C.c_int32), ("g", C.c_double), ("mix", C.c_double)]
+
+
+class WgEvt(C.Structure):
+    _fields_ = [("src", C.c_int64), ("dst", C.c_int64), ("tmp", C.c_int64), ("n", C.c_int32), ("line_begin", C.c_int32),
+                ("line_count", C.c_int32), ("_pad", C.c_int32)]
+
+
 class ResMode(C.Structure):
     _fields_ = [("f_over_sr", C.c_double), ("phase", C.c_double), ("weight", C.c_double)]
 
@@ -122,6 +131,7 @@ _STAGES = {
     "ms_imprint": (_I, [_P, _P, _I, _I, _P, _P]),
     "ms_partial_lock": (_I, [_P, _I, _P, _P, _P]),
     "ms_resonator": (_I, [_P, _I, _P, _P, _P]),
+    "ms_waveguide": (_I, [_P, _I, _P, _P, _P]),
     "ms_cepstral": (_I, [_I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "ms_spectral_destroy": (None, [_P]),
     "ms_fft_pair_forward": (_I, [_P, _P, _I, _P, _P, _Z, _P]),

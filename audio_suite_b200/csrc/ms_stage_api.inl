@@ -15,6 +15,9 @@ struct SynthTableK { static constexpr int MAXT = 256;
 struct SynthWaveletK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const SynthEvt* e, const WaveletAtom* a, const int* sh, real* pool, const Ctx& c) { synth_wavelet_body(e, a, sh, pool, c); } };
+struct WaveguideK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const WgEvt* e, const WgLine* l, real* pool, const Ctx& c) { waveguide_body(e, l, pool, c); } };
 struct ResonatorK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const ResEvt* e, const ResMode* m, real* pool, const Ctx& c) { resonator_body(e, m, pool, c); } };
@@ -85,6 +88,13 @@ extern "C" int MS_API(ms_synth_table)(const ms_synth_evt* evts, int n, const rea
 extern "C" int MS_API(ms_synth_wavelet)(const ms_synth_evt* evts, int n, const ms_wavelet_atom* atoms, const int32_t* shifts,
                                 real* pool, void* stream) {
     MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthWaveletK>(mk_dim(64, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, atoms, (const int*)shifts, pool)) return -1; })
+    return 0;
+}
+extern "C" int MS_API(ms_waveguide)(const ms_wg_evt* evts, int n, const ms_wg_line* lines, real* pool, void* stream) {
+    for (int x0 = 0; x0 < n; x0 += 1 << 20) {
+        const int cnt = std::min(1 << 20, n - x0);
+        if (ms_launch<WaveguideK>(mk_dim((unsigned)cnt, 1), 256, 0, (ms_stream_t)stream, evts + x0, lines, pool)) return -1;
+    }
     return 0;
 }
 extern "C" int MS_API(ms_resonator)(const ms_res_evt* evts, int n, const ms_res_mode* modes, real* pool, void* stream) {

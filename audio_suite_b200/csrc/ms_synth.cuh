@@ -10,7 +10,7 @@
 // shared staging buffer in stream order; the mode's closed-form terms (sine with float64 phase,
 // exponentials, fades) are applied on the way out with coalesced stores.
 
-enum { SY_GAUSS = 0, SY_DUST = 1, SY_NOISE = 2, SY_SKEW = 3, SY_RES = 4, SY_PLAIN = 5, SY_WAVELET = 6, SY_IRFRAG = 7, SY_SCANLINE = 8, SY_SILENT = 9, SY_CHAOS = 10 };
+enum { SY_GAUSS = 0, SY_DUST = 1, SY_NOISE = 2, SY_SKEW = 3, SY_RES = 4, SY_PLAIN = 5, SY_WAVELET = 6, SY_IRFRAG = 7, SY_SCANLINE = 8, SY_SILENT = 9, SY_CHAOS = 10, SY_STICK = 11 };
 
 #define SY_C 8            // words per thread per round
 #define SY_NTHR 256
@@ -372,6 +372,40 @@ MS_DEV void synth_table_body(const SynthEvt* MS_RESTRICT evts, const real* MS_RE
         return;
     }
     real* tmp = pool + E.aux;
+    if (E.mode == SY_STICK) {
+        // gen_stick_slip (main_v2.py:283-301): tmp holds the event's normals (one per sample, both states draw one).
+        // The state machine is walked by one thread in the reference's float64 operation order, no fused multiply-add.
+        if (c.tid == 0) {
+            const double threshold = E.f_over_sr, build = E.ring_decay, decay = E.env_decay, noise = E.inv_fade;
+            double force = 0.0;
+            bool sticking = true;
+            for (int j = 0; j < n; ++j) {
+                const double z = (double)tmp[j];
+                double x = 0.0;
+                if (sticking) {
+#ifdef MS_HOST_EMUL
+                    volatile double t1 = z * noise; volatile double t2 = t1 + 0.2; volatile double t3 = build * t2; force = force + t3;
+#else
+                    force = __dadd_rn(force, __dmul_rn(build, __dadd_rn(__dmul_rn(z, noise), 0.2)));
+#endif
+                    if (fabs(force) > threshold) sticking = false;
+                } else {
+#ifdef MS_HOST_EMUL
+                    volatile double t1 = 0.25 * z; x = force + t1; volatile double t2 = force * decay; force = t2;
+#else
+                    x = __dadd_rn(force, __dmul_rn(0.25, z));
+                    force = __dmul_rn(force, decay);
+#endif
+                    if (fabs(force) < 0.02) { sticking = true; force = 0.0; }
+                }
+                out[j] = (real)x;
+            }
+        }
+        c.sync();
+        for (int j = c.tid; j < n; j += c.nthr)
+            out[j] *= (real)(n > 1 ? 0.5 - 0.5 * cospi(2.0 * (double)j / (double)(n - 1)) : 1.0);
+        return;
+    }
     if (E.mode == SY_CHAOS) {
         // gen_micro_chaos (main_v2.py:303-315).  The gate draws (one uniform per sample: (word >> 11) * 2^-53 < gate) are
         // position-independent, so every thread jumps the 128-bit LCG to its own samples; the logistic map itself is a

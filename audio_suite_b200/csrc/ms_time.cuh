@@ -364,3 +364,34 @@ MS_DEV void resonator_body(const ResEvt* MS_RESTRICT evts, const ResMode* MS_RES
         y[j] = (real)0.55 * xv + (real)0.45 * (y[j] * inv) * sg;
     }
 }
+
+// ---- waveguide (waveguide_splinters, main_v2.py:386-402) ---------------------------------------------------------------
+// One CTA per grain, lines one after the other.  Within a line v[t] = y[t] + g v[t - d] couples only samples d apart:
+// a thread owns a residue r < d and walks t = r, r + d, ... (d is 0.4..8 ms at the design rate, so the chains are short).
+typedef ms_wg_evt WgEvt;
+typedef ms_wg_line WgLine;
+MS_DEV void waveguide_body(const WgEvt* MS_RESTRICT evts, const WgLine* MS_RESTRICT lines, real* pool, const Ctx& c) {
+    const WgEvt E = evts[c.bx];
+    const real* x = pool + E.src;
+    real* y = pool + E.dst;
+    const int n = E.n;
+    if (E.src != E.dst) {
+        for (int j = c.tid; j < n; j += c.nthr) y[j] = x[j];
+        c.sync();
+    }
+    for (int l = 0; l < E.line_count; ++l) {
+        const WgLine Ln = lines[E.line_begin + l];
+        const int d = Ln.d;
+        const real g = (real)Ln.g, mix = (real)Ln.mix, dry = (real)1.0 - (real)Ln.mix;
+        const int chains = d < n ? d : n;
+        for (int r = c.tid; r < chains; r += c.nthr) {
+            real v = (real)0.;
+            for (int t = r; t < n; t += d) {
+                const real yt = y[t];
+                v = yt + g * v;                           // v[t - d] of the same chain (0 before the first sample)
+                y[t] = dry * yt + mix * v;
+            }
+        }
+        c.sync();
+    }
+}

@@ -228,6 +228,11 @@ class BatchRenderer:
         tilt = t.sy2[(t.sy2["mode"] == P.MODE_NOISE) | (t.sy2["mode"] == P.MODE_SKEW)]
         self.n_dust_evt, self.n_tilt_evt = len(dust), len(tilt)
         normal = sy1[(sy1["mode"] != P.MODE_DUST) & (sy1["mode"] < P.MODE_WAVELET)]      # the modes that draw normals
+        stick = sy1[sy1["mode"] == P.MODE_STICK]
+        if len(stick):                            # stick-slip: its normals (one per sample) go to the scratch at `aux` first
+            pre = stick.copy()
+            pre["out"] = stick["aux"]
+            normal = np.concatenate([normal, pre])
         tab = sy1[sy1["mode"] > P.MODE_WAVELET]                                           # IR fragment / scan line / silence
         self.n_tab_evt = len(tab)
         self.d_sy_tab = dev.upload(tab) if self.n_tab_evt else None
@@ -251,15 +256,23 @@ class BatchRenderer:
         self.tilt_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.tilt), self.pool, self.pool)
         self.grain_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.grain), self.pool, self.pool)
         self.rot_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.rot), self.mono, self.mono)
-        # resonator bank (time domain) and the multiband unfold that follows it
-        self.n_res = 0
+        # resonator bank / waveguide (time domain) and the multiband unfold that follows them
+        self.n_res = self.n_wg = 0
         self.post_stage = None
+        if t.wg is not None and len(t.wg[0]):
+            rows, lines = t.wg
+            ev = np.zeros(len(rows), np.dtype(_abi.WgEvt))
+            ev["src"], ev["dst"], ev["n"], ev["line_begin"], ev["line_count"] = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4]
+            ln = np.zeros(len(lines), np.dtype(_abi.WgLine))
+            ln["d"], ln["g"], ln["mix"] = lines[:, 0].astype(np.int64), lines[:, 1], lines[:, 2]
+            self.d_wg_evt, self.d_wg_lines, self.n_wg = dev.upload(ev), dev.upload(ln), len(rows)
+        if t.post_grain is not None and len(t.post_grain[0]):
+            self.post_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.post_grain), self.pool, self.pool)
         if t.res is not None and len(t.res[0]):
             rows, decay, modes = t.res
             ev = np.zeros(len(rows), np.dtype(_abi.ResEvt))
             ev["src"], ev["dst"], ev["n"], ev["mode_begin"], ev["mode_count"], ev["decay"] = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4], decay
             self.d_res_evt, self.d_res_modes, self.n_res = dev.upload(ev), dev.upload(np.ascontiguousarray(modes)), len(rows)
-            self.post_stage = _SpectralStage(dev, self.api, T.pair_jobs(t.post_grain), self.pool, self.pool)
         # cepstral warp: three stages of single-signal jobs around the elementwise steps of ms_cepstral
         self.cep_stages = None
         if t.cep is not None and len(t.cep[0]):
@@ -403,8 +416,12 @@ class BatchRenderer:
                 mark("partial_lock")
             if self.n_res:
                 _check(dev, lib.ms_resonator(dev.ptr(self.d_res_evt), self.n_res, dev.ptr(self.d_res_modes), dev.ptr(self.pool), st))
-                self.post_stage.run()
-                mark("resonator_bank")
+            if self.n_wg:
+                _check(dev, lib.ms_waveguide(dev.ptr(self.d_wg_evt), self.n_wg, dev.ptr(self.d_wg_lines), dev.ptr(self.pool), st))
+            if self.n_res or self.n_wg:
+                if self.post_stage is not None:
+                    self.post_stage.run()
+                mark("resonator_waveguide")
             if self.imprint_stage is not None:
                 self.imprint_stage.forward()
                 zptr = C.c_void_p(dev.ptr(self.imprint_stage.ws).value + self.imprint_zbase)

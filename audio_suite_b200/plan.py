@@ -22,12 +22,12 @@ from .configs import BASIC_MODES
 DESIGN_SR_CAP = 30_000_000          # M:597, M:646
 IR_TAP_CAP = 8192                   # M:443
 
-MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET, MODE_IRFRAG, MODE_SCANLINE, MODE_SILENT, MODE_CHAOS = range(11)
+MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET, MODE_IRFRAG, MODE_SCANLINE, MODE_SILENT, MODE_CHAOS, MODE_STICK = range(12)
 WAVELET_FLOOR = 128                 # M:319
 _MODE_ID = {m: i for i, m in enumerate(BASIC_MODES)}
 
-_NEXT_ROW_FLAGS = ("wg_on", "event_feedback_on")
-_NEXT_ROW_MODES = ("Stick–slip friction",)
+_NEXT_ROW_FLAGS = ("event_feedback_on",)
+_NEXT_ROW_MODES = ()
 
 
 # --------------------------------------------------------------------------- breakpoint lanes (M:452-482)
@@ -224,6 +224,8 @@ class EventPlan:
     spec: Optional[object] = None           # _abi.SpecOp or None
     plock: Optional[tuple] = None           # (factor, top_n, neigh, pre-operator) when partial_lock_stretch is active
     cep: Optional[tuple] = None             # (factor, pre-operator) when cepstral_warp is active
+    stick_noise: float = 0.0
+    wg: Optional[np.ndarray] = None         # waveguide lines: float64 [L, 3] = delay in samples, loop gain, mix
     res: Optional[tuple] = None             # (modes float64 [K, 3] = f/sr, phase, weight ; decay per sample) for resonator_bank
     spec_b: Optional[object] = None         # multiband operator applied AFTER the resonator bank
     tilt: Optional[object] = None           # _abi.SpecOp for the tilted-noise modes
@@ -311,6 +313,8 @@ def plan_render(params) -> RenderPlan:
         mode, floor = (MODE_SILENT if img_gray is None else MODE_SCANLINE), 64
     elif gmode == "Micro-chaos":
         mode, floor = MODE_CHAOS, 64
+    elif gmode == "Stick–slip friction":
+        mode, floor = MODE_STICK, 64
     elif gmode in _MODE_ID:
         mode = _MODE_ID[gmode]
         dust_density, tilt = float(params["dust_density"]), float(params["noise_tilt"])
@@ -342,7 +346,8 @@ def plan_render(params) -> RenderPlan:
             ev.length = max(0, min(out_n - ev.start, n - ev.offset))
             ev.placed = ev.length > 0
         res_on = bool(params["res_bank_on"]) and n >= 32                 # M:372
-        mb_here = not res_on                                             # the multiband unfold follows the resonator (M:719-727)
+        wg_on = bool(params["wg_on"]) and n >= 64                        # M:389
+        mb_here = not (res_on or wg_on)                                  # the multiband unfold follows them (M:719-727)
         if params["cep_warp_on"] and n >= 64:
             # M:696-697: cepstral_warp sits between low-pass / power warp and the stretch; its three elementwise steps
             # run between transforms of their own, the stage's inverse applies stretch + multiband
@@ -363,6 +368,9 @@ def plan_render(params) -> RenderPlan:
             ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, ev.stretch, mb=mb_here)
         if res_on:
             ev.res = _plan_resonator(params, seed + i, sr_evt)
+        if wg_on:
+            ev.wg = _plan_waveguide(params, seed + i, sr_evt)
+        if res_on or wg_on:
             ev.spec_b = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, pre=False)       # multiband only, or None
         ev.fade = max(8, int(0.01 * n))
         if mode == MODE_GAUSS:
@@ -375,6 +383,10 @@ def plan_render(params) -> RenderPlan:
             _plan_ir_fragment(ev, ir_audio)
         elif mode == MODE_SCANLINE:
             _plan_scanline(ev, img_gray)
+        elif mode == MODE_STICK:               # M:283-301: threshold, build, decay, noise ride in the mode constants
+            ev.f_over_sr, ev.ring_decay = float(params["ss_threshold"]), float(params["ss_build"])
+            ev.env_decay, ev.stick_noise = float(params["ss_decay"]), float(params["ss_noise"])
+            ev.fade = 0
         elif mode == MODE_CHAOS:               # M:303-315: r, gate, y0 = (seed % 10000) / 10000 ride in the mode constants
             ev.f_over_sr, ev.ring_decay = float(params["chaos_r"]), float(params["chaos_gate"])
             ev.env_decay = (int(ev.seed) % 10000) / 10000.0
@@ -479,6 +491,19 @@ def _plan_resonator(params, seed, sr):
         rows[k] = (f / sr, rng.uniform(0, 2 * np.pi), 1.0 / (1 + k * 0.35))
     tau = max(1e-6, float(params["res_decay_ms"]) / 1000.0)
     return rows, 1.0 / (tau * sr)
+
+
+def _plan_waveguide(params, seed, sr):
+    """Scalar draws of waveguide_splinters (M:387, 391-396)."""
+    rng = np.random.default_rng(int(seed) + 777)
+    lines = int(max(1, int(params["wg_lines"])))
+    max_ms, fb = float(params["wg_max_ms"]), float(params["wg_fb"])
+    rows = np.zeros((lines, 3), dtype=np.float64)
+    for k in range(lines):
+        d = int(max(1, round((rng.uniform(0.4, max_ms) / 1000.0) * sr)))
+        g = fb * rng.uniform(0.6, 0.98)
+        rows[k] = (d, g, rng.uniform(0.15, 0.45))
+    return rows
 
 
 def _plan_crackle(ev, alpha, density, kernel):

@@ -90,6 +90,7 @@ class Tables:
     dust_val: np.ndarray = None
     atoms: np.ndarray = None        # wavelet atoms, float64 [N, 4]
     atom_shift: np.ndarray = None   # int32 [N]
+    wg: tuple = None                # (rows int64 [N, 5] = src, dst, n, line_begin, line_count ; lines float64 [L, 3])
     res: tuple = None               # (rows int64 [N, 5] = src, dst, n, mode_begin, mode_count ; decay [N] ; modes float64 [M, 3])
     post_grain: tuple = None        # spectral items applied after the resonator bank (multiband): (n, src, dst, ops)
     cep: tuple = None               # (rows int64 [N, 3] = src, dst, n ; factor [N] ; pre ops [N, B] ; post ops [N, B])
@@ -128,6 +129,7 @@ def pack_chunk(plans) -> Tables:
     pl_rows, pl_factor, pl_pre, pl_post = [], [], [], []
     cp_rows, cp_factor, cp_pre, cp_post = [], [], [], []
     rs_rows, rs_decay, rs_modes, n_modes = [], [], [], 0
+    wg_rows, wg_lines, n_lines = [], [], 0
     post_grain = _Items()
     tap_off, tap_gain, n_taps = [], [], 0
     irs, ir_index, n_ir = [], {}, 0
@@ -174,8 +176,8 @@ def pack_chunk(plans) -> Tables:
                 if ev.mode == P.MODE_SCANLINE:
                     aux2 = pool_n                                     # windowed, unsmoothed line
                     pool_n += ev.n
-            elif ev.mode == P.MODE_CHAOS:
-                aux2 = pool_n                                         # gated logistic-map samples before the smoothing
+            elif ev.mode in (P.MODE_CHAOS, P.MODE_STICK):
+                aux2 = pool_n                                         # gated logistic-map samples / the event's normals
                 pool_n += ev.n
             elif ev.mode in (P.MODE_NOISE, P.MODE_SKEW):
                 raw, tilted = pool_n, pool_n + ev.n
@@ -185,9 +187,9 @@ def pack_chunk(plans) -> Tables:
                 alg["tilt_spectral"] += 2 * ev.n
             common = (s_hi, s_lo, i_hi, i_lo, ev.n)
             tail = (ev.fade, ev.sigma)
-            inv_fade = 1.0 / ev.fade if ev.fade > 0 else 0.0
+            inv_fade = 1.0 / ev.fade if ev.fade > 0 else (ev.stick_noise if ev.mode == P.MODE_STICK else 0.0)
             sy1[e] = common + (ev.mode,) + tail + (out1, ev.f_over_sr, inv_fade, ev.ring_decay, ev.env_decay,
-                                                     dust_b, dust_c, ev.ker_len, aux2 if ev.mode in (P.MODE_SCANLINE, P.MODE_CHAOS) else 0,
+                                                     dust_b, dust_c, ev.ker_len, aux2 if ev.mode in (P.MODE_SCANLINE, P.MODE_CHAOS, P.MODE_STICK) else 0,
                                                      atom_b, atom_c, 0)
             sy2[e] = common + (mode2,) + tail + (micro, ev.f_over_sr, inv_fade, ev.ring_decay, ev.env_decay,
                                                   0, 0, ev.ker_len, aux2, 0, 0, 0)
@@ -223,6 +225,14 @@ def pack_chunk(plans) -> Tables:
                 rs_modes.append(ev.res[0])
                 n_modes += len(ev.res[0])
                 g_at = r_at
+            if ev.wg is not None:
+                w_at = pool_n                      # the combs run in place on a copy of the grain so far
+                pool_n += ev.n
+                wg_rows.append((g_at, w_at, ev.n, n_lines, len(ev.wg)))
+                wg_lines.append(ev.wg)
+                n_lines += len(ev.wg)
+                g_at = w_at
+            if ev.res is not None or ev.wg is not None:
                 if ev.spec_b is not None:
                     b_at = pool_n
                     pool_n += ev.n
@@ -348,6 +358,7 @@ def pack_chunk(plans) -> Tables:
                np.frombuffer(b"".join(pl_post), np.uint8).reshape(npl, _SPEC_OP_BYTES) if npl else np.zeros((0, _SPEC_OP_BYTES), np.uint8))
     t.res = (np.asarray(rs_rows, np.int64).reshape(-1, 5), np.asarray(rs_decay, np.float64),
              np.concatenate(rs_modes) if rs_modes else np.zeros((0, 3)))
+    t.wg = (np.asarray(wg_rows, np.int64).reshape(-1, 5), np.concatenate(wg_lines) if wg_lines else np.zeros((0, 3)))
     t.post_grain = post_grain.arrays()
     ncp = len(cp_rows)
     t.cep = (np.asarray(cp_rows, np.int64).reshape(-1, 3), np.asarray(cp_factor, np.float64),
@@ -380,13 +391,14 @@ def merge_chunks(chunks) -> Tables:
                              "atoms", "atom_shift", "imprint", "imprint_par", "odd", "out_at", "out_n", "y_at", "last", "srs")}
     items = {k: [[], [], [], []] for k in ("tilt", "grain", "rot", "post_grain")}
     rs_parts, mode_b = [[], [], []], 0
+    wg_parts, line_b = [[], []], 0
     pl_parts = [[], [], [], []]
     cp_parts = [[], [], [], []]
     alg = {}
     for c in chunks:
         _shift(c.sy1, ("out",), pool_b)
         if c.sy1.size and pool_b:
-            c.sy1["aux"] += np.where((c.sy1["mode"] == P.MODE_SCANLINE) | (c.sy1["mode"] == P.MODE_CHAOS), pool_b, 0)
+            c.sy1["aux"] += np.where((c.sy1["mode"] == P.MODE_SCANLINE) | (c.sy1["mode"] == P.MODE_CHAOS) | (c.sy1["mode"] == P.MODE_STICK), pool_b, 0)
         _shift(c.sy1, ("dust_begin",), dust_b)
         _shift(c.sy1, ("atom_begin",), atom_b)
         if c.imprint.size:
@@ -426,6 +438,12 @@ def merge_chunks(chunks) -> Tables:
         for i in range(3):
             rs_parts[i].append(c.res[i])
         mode_b += len(c.res[2])
+        if c.wg[0].size:
+            c.wg[0][:, 0:2] += pool_b
+            c.wg[0][:, 3] += line_b
+        wg_parts[0].append(c.wg[0])
+        wg_parts[1].append(c.wg[1])
+        line_b += len(c.wg[1])
         for k, base in (("tilt", pool_b), ("grain", pool_b), ("rot", mono_b), ("post_grain", pool_b)):
             n, s, d, ops = getattr(c, k)
             items[k][0].append(n)
@@ -453,6 +471,7 @@ def merge_chunks(chunks) -> Tables:
         setattr(m, k, tuple(np.concatenate(x) for x in items[k]))
     m.plock = tuple(np.concatenate(x) for x in pl_parts)
     m.res = tuple(np.concatenate(x) for x in rs_parts)
+    m.wg = tuple(np.concatenate(x) for x in wg_parts)
     m.cep = tuple(np.concatenate(x) for x in cp_parts)
     m.pool_n, m.mono_n, m.frames, m.h_total, m.alg, m.env_n = pool_b, mono_b, frame_b, h_b, alg, env_b
     return m

@@ -100,6 +100,11 @@ typedef struct {
     double decay;            /* 1 / (tau * sr): env[j] = exp(-j * decay) */
 } ms_res_evt;
 /* ms_resonator_f32 / ms_resonator_f64: declared below by MS_DECLARE_API */
+/* waveguide_splinters (main_v2.py:386-402) on time-domain grains: a cascade of feedback combs, per line
+ * v[t] = y[t] + g v[t - d], y[t] <- (1 - mix) y[t] + mix v[t].  dst may equal src.  One CTA per grain. */
+typedef struct { int32_t d, _pad; double g, mix; } ms_wg_line;
+typedef struct { int64_t src, dst, tmp; int32_t n, line_begin, line_count, _pad; } ms_wg_evt;   /* tmp: n REALs of scratch */
+/* ms_waveguide_f32 / ms_waveguide_f64: declared below by MS_DECLARE_API */
 /* partial_lock_stretch (main_v2.py:130-148) on the spectrum of one grain (single-signal job, after
  * ms_spectral_forward): W = low-pass / power warp of the grain's spectrum (`pre`), the top_n strongest bins of W
  * (DC excluded) are moved to round(k * factor) with a triangular spread over +-neigh bins on top of 0.12 W, and the
@@ -134,7 +139,7 @@ typedef struct {
 /* ---- transient synthesis: gen_basic (main_v2.py:219-269).  One record per event; the array lives in
  *      DEVICE memory.  The PCG64 state is numpy's `PCG64(seed).state` right after seeding. */
 enum { MS_SY_GAUSS = 0, MS_SY_DUST = 1, MS_SY_NOISE = 2, MS_SY_SKEW = 3, MS_SY_RES = 4, MS_SY_PLAIN = 5, MS_SY_WAVELET = 6,
-       MS_SY_IRFRAG = 7, MS_SY_SCANLINE = 8, MS_SY_SILENT = 9, MS_SY_CHAOS = 10 };
+       MS_SY_IRFRAG = 7, MS_SY_SCANLINE = 8, MS_SY_SILENT = 9, MS_SY_CHAOS = 10, MS_SY_STICK = 11 };
 typedef struct {
     uint64_t s_hi, s_lo, i_hi, i_lo;
     int32_t n, mode;
@@ -164,6 +169,9 @@ typedef struct { double f0_over_sr, inv_sigma, phase, weight; } ms_wavelet_atom;
  * (scanline; `aux` = n samples of scratch in the pool).  One CTA per event. */
 /* MS_SY_CHAOS (gen_micro_chaos, main_v2.py:303-315) also runs in ms_synth_table: f_over_sr = r, ring_decay = gate,
  * env_decay = y0 = (seed % 10000) / 10000, the PCG64 state as for the normal modes, `aux` = n samples of scratch. */
+/* MS_SY_STICK (gen_stick_slip, main_v2.py:283-301): ms_synth_normal first leaves the event's n raw normals at `aux`
+ * (the model draws exactly one per sample), ms_synth_table then walks the two-state friction model sequentially with
+ * the reference's float64 operation order: f_over_sr = threshold, ring_decay = build, env_decay = decay, inv_fade = noise. */
 /* ms_synth_table_f32 / ms_synth_table_f64: declared below by MS_DECLARE_API */
 /* MS_SY_WAVELET events: sum of shifted Gaussian-windowed cosines under a Hann window (float64 phase) */
 /* ms_synth_wavelet_f32 / ms_synth_wavelet_f64: declared below by MS_DECLARE_API */
@@ -239,6 +247,7 @@ typedef struct {
     int ms_spectral_forward##SFX(void* handle, void* stream); \
     int ms_spectral_inverse##SFX(void* handle, void* stream); \
     int ms_spectral_z_table##SFX(void* handle, int64_t* host_z_offsets, size_t* z_base_bytes); \
+    int ms_waveguide##SFX(const ms_wg_evt* dev_evts, int n_evts, const ms_wg_line* dev_lines, REAL* pool, void* stream); \
     int ms_resonator##SFX(const ms_res_evt* dev_evts, int n_evts, const ms_res_mode* dev_modes, REAL* pool, void* stream); \
     int ms_partial_lock##SFX(const ms_plock_evt* dev_evts, int n_evts, REAL* z_base, REAL* scratch, void* stream); \
     int ms_cepstral##SFX(int step, const ms_cep_evt* dev_evts, int n_evts, int max_n, REAL* z1_base, REAL* z2_base, \

@@ -219,6 +219,31 @@ def resonator_bank(x, sr, modes, f_min, f_max, decay_ms, seed):
     return 0.55 * x + 0.45 * (x * 0.0 + bank) * np.sign(x)
 
 
+def waveguide_lines(seed, sr, lines, max_ms, feedback):
+    """Scalar draws of waveguide_splinters (M:387, 391-396): per line the delay in samples, the loop gain and the mix."""
+    rng = np.random.default_rng(int(seed) + 777)
+    rows = []
+    for _ in range(int(max(1, lines))):
+        d = int(max(1, round((rng.uniform(0.4, max_ms) / 1000.0) * sr)))
+        g = feedback * rng.uniform(0.6, 0.98)
+        rows.append((d, g, rng.uniform(0.15, 0.45)))
+    return rows
+
+
+def waveguide(x, sr, lines, max_ms, feedback, seed):
+    """M:386-402 -- a cascade of feedback comb filters: per line v[t] = y[t] + g v[t - d], y[t] <- (1 - mix) y[t] + mix v[t]."""
+    n = len(x)
+    if n < 64:
+        return x
+    y = x.copy()
+    for d, g, mix in waveguide_lines(seed, sr, lines, max_ms, feedback):
+        v = y.copy()
+        for t in range(d, n):
+            v[t] = y[t] + g * v[t - d]
+        y = (1.0 - mix) * y + mix * v
+    return y
+
+
 def multiband_unfold(x, gen_sr, bands_out_hz, unfolds, roll_hz):
     """M:492-500 -- sum of band-passed copies, band edges scaled by each band's unfold."""
     acc = None
@@ -545,11 +570,33 @@ def micro_chaos(gen_sr, micro_ms, seed, r, gate):
     return np.convolve(x, np.exp(-np.linspace(0, 5, 48)), mode="same") * raised_cosine_window(n)
 
 
+def stick_slip(gen_sr, micro_ms, seed, threshold, build, decay, noise):
+    """M:283-301 -- a two-state friction model driven by one normal draw per sample: while sticking the force builds
+    up (output 0) until it exceeds the threshold; while slipping the output is the force plus noise and the force
+    decays until it falls under 0.02.  Hann-windowed."""
+    rng = np.random.default_rng(int(seed))
+    n = grain_length(gen_sr, micro_ms, floor=64)
+    x = np.zeros(n, dtype=np.float64)
+    sticking, force = True, 0.0
+    for i in range(n):
+        z = rng.standard_normal()
+        if sticking:
+            force += build * (z * noise + 0.2)
+            if abs(force) > threshold:
+                sticking = False
+        else:
+            x[i] = force + 0.25 * z
+            force *= decay
+            if abs(force) < 0.02:
+                sticking, force = True, 0.0
+    return x * raised_cosine_window(n)
+
+
 def generator_floor(mode, params):
     """Minimum grain length of each generator (M:221, 273, 319, 337-338, 352)."""
     if mode == "Wavelet atoms":
         return WAVELET_FLOOR
-    if mode in ("Image scanline", "Micro-chaos"):
+    if mode in ("Image scanline", "Micro-chaos", "Stick–slip friction"):
         return 64
     if mode == "IR fragment":
         ir = params.get("_ir_audio")
@@ -594,8 +641,7 @@ imprint_noise_floor = rounding_noise_floor
 
 
 # --------------------------------------------------------------------------- render
-_UNSUPPORTED_FLAGS = ("wg_on",
-                      "event_feedback_on")
+_UNSUPPORTED_FLAGS = ("event_feedback_on",)
 
 
 def design_rate(base_sr, unfold):
@@ -662,8 +708,6 @@ def render(params, progress=None, taps=None, jitter=None):
         if params[flag]:
             raise NotImplementedError(f"oracle: '{flag}' is a SURVEY 8(f) 'next' row, not restated yet")
     mode = params["gen_mode"]
-    if mode in ("Stick–slip friction",):
-        raise NotImplementedError(f"oracle: generator '{mode}' is a SURVEY 8(f) 'next' row")
     plan = plan_events(params)
     base_sr, out_n = plan["base_sr"], plan["out_n"]
     if progress:
@@ -682,6 +726,9 @@ def render(params, progress=None, taps=None, jitter=None):
         elif mode == "Crackle / corona":
             g = crackle(ev["gen_sr"], micro_ms, seed + i, float(params["crackle_alpha"]), float(params["crackle_density"]),
                         int(params["crackle_kernel"]))
+        elif mode == "Stick–slip friction":
+            g = stick_slip(ev["gen_sr"], micro_ms, seed + i, float(params["ss_threshold"]), float(params["ss_build"]),
+                           float(params["ss_decay"]), float(params["ss_noise"]))
         elif mode == "Micro-chaos":
             g = micro_chaos(ev["gen_sr"], micro_ms, seed + i, float(params["chaos_r"]), float(params["chaos_gate"]))
         elif mode == "IR fragment":
@@ -712,6 +759,8 @@ def render(params, progress=None, taps=None, jitter=None):
                 g = g + jitter * np.max(np.abs(g)) * np.random.default_rng(333 + i).standard_normal(g.size)
             g = resonator_bank(g, ev["gen_sr"], int(params["res_modes"]), float(params["res_fmin"]), float(params["res_fmax"]),
                                float(params["res_decay_ms"]), seed + i)
+        if params["wg_on"]:                                                       # M:712-717
+            g = waveguide(g, ev["gen_sr"], int(params["wg_lines"]), float(params["wg_max_ms"]), float(params["wg_fb"]), seed + i)
         if params["unfold_mode"] != "Classic reinterpret":
             b1, b2, b3 = float(params["mb_b1"]), float(params["mb_b2"]), float(params["mb_b3"])
             g = multiband_unfold(g, ev["gen_sr"], [(0, b1), (b1, b2), (b2, b3)],

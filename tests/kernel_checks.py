@@ -281,6 +281,13 @@ PRESET_LIKE = {
                                res_fmin=90, res_fmax=1800, res_decay_ms=220, partial_lock_on=True, partial_stretch=1.02,
                                event_process="Poisson", grains_per_sec=6, spectral_imprint_on=True, spectral_imprint_amt=0.22,
                                er_taps=300, er_max_ms=60),
+    "friction_lattice": dict(gen_mode="Stick–slip friction", micro_ms=2.4, ss_threshold=0.85, ss_build=0.08, ss_decay=0.72,
+                             ss_noise=0.06, wg_on=True, wg_lines=14, wg_max_ms=6.5, wg_fb=0.78, partial_stretch=1.18,
+                             partial_lock_on=True, event_process="Clustered", grains_per_sec=22, cluster_size=8,
+                             cluster_spread_ms=18, er_cloud_on=False, stereo_width=0.35),
+    "orbital_friction_loop": dict(gen_mode="Stick–slip friction", micro_ms=3.2, ss_threshold=0.55, ss_build=0.035, ss_decay=0.88,
+                                  ss_noise=0.04, wg_on=True, wg_lines=6, wg_max_ms=5.5, wg_fb=0.6, event_process="Poisson",
+                                  grains_per_sec=5, partial_stretch=1.03, er_cloud_on=False),
     "soft_ellipse_memory": dict(gen_mode="Noise burst", micro_ms=2.2, noise_tilt=-8.0, event_process="Poisson",
                                 grains_per_sec=6, spectral_imprint_on=True, spectral_imprint_amt=0.25,
                                 spectral_imprint_smooth=0.97, partial_stretch=0.95, bp_cutoff="0:14000, 12:9000, 24:6000",

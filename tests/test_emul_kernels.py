@@ -161,7 +161,9 @@ def test_partial_lock(emul, kw):
                                 dict(gen_mode="Image scanline", _img_gray=np.random.default_rng(5).integers(0, 256, (40, 300)).astype(np.uint8)),
                                 dict(gen_mode="Image scanline"),
                                 dict(gen_mode="Micro-chaos"),
-                                dict(gen_mode="Micro-chaos", chaos_r=3.99, chaos_gate=0.9, micro_ms=3.0, seed=20000)])
+                                dict(gen_mode="Micro-chaos", chaos_r=3.99, chaos_gate=0.9, micro_ms=3.0, seed=20000),
+                                dict(gen_mode="Stick–slip friction"),
+                                dict(gen_mode="Stick–slip friction", ss_threshold=0.5, ss_build=0.2, ss_decay=0.9, ss_noise=0.3, micro_ms=3.0)])
 def test_next_row_generators(emul, kw):
     """gen_crackle (main_v2.py:271-281), gen_ir_fragment (:333-348), gen_image_scanline (:350-362), gen_micro_chaos
     (:303-315; the logistic map must stay bit-identical over thousands of iterations)."""
@@ -195,5 +197,15 @@ def test_cepstral_warp(emul, kw):
 def test_resonator_bank(emul, kw):
     """resonator_bank (main_v2.py:369-384) between the stretch / partial lock and the multiband unfold."""
     base = dict(event_process="Poisson", out_dur_s=0.6, grains_per_sec=20.0, er_cloud_on=False, res_bank_on=True, gen_mode="Resonant strike")
+    base.update(kw)
+    assert K.check_render(emul, configs.with_defaults(base), "f64") < 1e-6
+
+
+@pytest.mark.parametrize("kw", [dict(gen_mode="Resonant strike", wg_max_ms=1.0),
+                                dict(res_bank_on=True, unfold_mode="Multi-band unfold", gen_mode="Stick–slip friction", wg_lines=12,
+                                     wg_max_ms=0.6, partial_lock_on=True, partial_stretch=1.1)])
+def test_waveguide(emul, kw):
+    """waveguide_splinters (main_v2.py:386-402): feedback combs walked chain by chain (samples d apart)."""
+    base = dict(event_process="Poisson", out_dur_s=0.6, grains_per_sec=20.0, er_cloud_on=False, wg_on=True)
     base.update(kw)
     assert K.check_render(emul, configs.with_defaults(base), "f64") < 1e-6

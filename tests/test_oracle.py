@@ -156,7 +156,8 @@ def test_wavelet_grain_shorter_than_its_atoms_fails_like_the_reference():
                                   "room_as_particle", "image_grain_hallucination", "closed_curve_air",
                                   "drifting_mode_fragments", "ghost_formants", "corona_glass_fog", "chaotic_dustfield",
                                   "elliptical_insect_hum", "infra_mechanical_choir",
-                                  "infra_tone_lattice", "03_wavelet_ice_bloom", "orbital_friction_loop"])
+                                  "infra_tone_lattice", "03_wavelet_ice_bloom", "orbital_friction_loop",
+                                  "02_friction_lattice", "friction_lattice", "wavelet_mist"])
 def test_oracle_matches_reference_on_shipped_presets(name):
     """The shipped presets that need only accelerated rows, merged over the factory defaults the way on_load_preset
     does (main_v2.py:1286-1291), first 3 s."""
@@ -165,7 +166,7 @@ def test_oracle_matches_reference_on_shipped_presets(name):
     path = os.path.join(ref_loader.REFERENCE_ROOT, "microsound_0.2.1", "presets", name + ".json")
     p = configs.with_defaults(json.load(open(path)))
     p["out_dur_s"] = 3.0
-    if name == "orbital_friction_loop":              # generator not restated: both sides must say so, not guess
+    if name == "wavelet_mist":                       # event feedback not restated: both sides must say so, not guess
         with pytest.raises(NotImplementedError):
             O.render(p)
         return
