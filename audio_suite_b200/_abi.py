@@ -45,6 +45,15 @@ class SynthEvt(C.Structure):
                 ("atom_begin", C.c_int64), ("atom_count", C.c_int32), ("_pad", C.c_int32)]
 
 
+class FeedbackEvt(C.Structure):
+    _fields_ = [("cur", C.c_int64), ("prev", C.c_int64), ("dst", C.c_int64), ("n_cur", C.c_int32), ("n_prev", C.c_int32),
+                ("fb", C.c_double)]
+
+
+class ImprintStepEvt(C.Structure):
+    _fields_ = [("z", C.c_int64), ("n", C.c_int32), ("slot", C.c_int32), ("amount", C.c_double), ("smooth", C.c_double)]
+
+
 class WgLine(C.Structure):
     _fields_ = [("d", C.c_int32), ("_pad", C.c_int32), ("g", C.c_double), ("mix", C.c_double)]
 
@@ -132,6 +141,8 @@ _STAGES = {
     "ms_partial_lock": (_I, [_P, _I, _P, _P, _P]),
     "ms_resonator": (_I, [_P, _I, _P, _P, _P]),
     "ms_waveguide": (_I, [_P, _I, _P, _P, _P]),
+    "ms_feedback": (_I, [_P, _I, _I, _P, _P]),
+    "ms_imprint_step": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "ms_cepstral": (_I, [_I, _P, _I, _I, _P, _P, _P, _P, _P]),
     "ms_spectral_destroy": (None, [_P]),
     "ms_fft_pair_forward": (_I, [_P, _P, _I, _P, _P, _Z, _P]),

@@ -15,6 +15,15 @@ struct SynthTableK { static constexpr int MAXT = 256;
 struct SynthWaveletK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const SynthEvt* e, const WaveletAtom* a, const int* sh, real* pool, const Ctx& c) { synth_wavelet_body(e, a, sh, pool, c); } };
+struct FeedbackK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const FeedbackEvt* e, real* pool, const Ctx& c) { feedback_body(e, pool, c); } };
+struct ImprintStepK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const ImprintStepEvt* e, cpx* z, real* mem, const int* pb, int mb, const Ctx& c) { imprint_step_body(e, z, mem, pb, mb, c); } };
+struct ImprintCommitK { static constexpr int MAXT = 256;
+    static constexpr int MINB = 1;
+    static MS_DEV void run(const ImprintStepEvt* e, int n, int* pb, const Ctx& c) { imprint_commit_body(e, n, pb, c); } };
 struct WaveguideK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const WgEvt* e, const WgLine* l, real* pool, const Ctx& c) { waveguide_body(e, l, pool, c); } };
@@ -89,6 +98,18 @@ extern "C" int MS_API(ms_synth_wavelet)(const ms_synth_evt* evts, int n, const m
                                 real* pool, void* stream) {
     MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthWaveletK>(mk_dim(64, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, atoms, (const int*)shifts, pool)) return -1; })
     return 0;
+}
+extern "C" int MS_API(ms_feedback)(const ms_feedback_evt* evts, int n, int max_n, real* pool, void* stream) {
+    const unsigned gx = (unsigned)((max_n + 255) / 256);
+    MS_FOR_Y_CHUNKS(n, { if (ms_launch<FeedbackK>(mk_dim(gx, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, pool)) return -1; })
+    return 0;
+}
+extern "C" int MS_API(ms_imprint_step)(const ms_imprint_step_evt* evts, int n, int max_bins, real* z_base, real* mem, int32_t* prev_bins,
+                               void* stream) {
+    const unsigned gx = (unsigned)((max_bins + 255) / 256);
+    MS_FOR_Y_CHUNKS(n, { if (ms_launch<ImprintStepK>(mk_dim(gx, (unsigned)_yc), 256, 0, (ms_stream_t)stream, evts + _y0, (cpx*)z_base, mem,
+                                                     (const int*)prev_bins, max_bins)) return -1; })
+    return ms_launch<ImprintCommitK>(mk_dim(64, 1), 256, 0, (ms_stream_t)stream, evts, n, (int*)prev_bins);
 }
 extern "C" int MS_API(ms_waveguide)(const ms_wg_evt* evts, int n, const ms_wg_line* lines, real* pool, void* stream) {
     for (int x0 = 0; x0 < n; x0 += 1 << 20) {

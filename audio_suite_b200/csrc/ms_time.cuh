@@ -395,3 +395,36 @@ MS_DEV void waveguide_body(const WgEvt* MS_RESTRICT evts, const WgLine* MS_RESTR
         c.sync();
     }
 }
+
+// ---- event feedback (main_v2.py:731-734) and the one-grain step of the spectral imprint that goes with it ----------------
+typedef ms_feedback_evt FeedbackEvt;
+typedef ms_imprint_step_evt ImprintStepEvt;
+MS_DEV void feedback_body(const FeedbackEvt* MS_RESTRICT evts, real* pool, const Ctx& c) {
+    const FeedbackEvt E = evts[c.by];
+    const int j = c.bx * c.nthr + c.tid;
+    if (j >= E.n_cur) return;
+    const real cur = pool[E.cur + j];
+    const real fb = (real)E.fb;
+    pool[E.dst + j] = j < E.n_prev ? ((real)1.0 - fb) * cur + fb * pool[E.prev + j] : cur;
+}
+// mem: max_bins reals per render slot; prev_bins: spectrum length of the slot's previous imprinted grain (-1: none).
+// prev_bins is updated by a second tiny launch (imprint_commit_body) so that every thread of this one sees the old value.
+MS_DEV void imprint_step_body(const ImprintStepEvt* MS_RESTRICT evts, cpx* zbase, real* mem, const int* MS_RESTRICT prev_bins,
+                              int max_bins, const Ctx& c) {
+    const ImprintStepEvt E = evts[c.by];
+    const int bins = E.n / 2 + 1;
+    const int k = c.bx * c.nthr + c.tid;
+    if (k >= bins) return;
+    cpx* Z = zbase + E.z;
+    real* m = mem + (long long)E.slot * max_bins;
+    const cpx X = Z[k];
+    const real mag = (real)hypot((double)X.x, (double)X.y);
+    const real amount = (real)E.amount, smooth = (real)E.smooth;
+    const real mm = (prev_bins[E.slot] != bins) ? mag : smooth * m[k] + ((real)1.0 - smooth) * mag;
+    m[k] = mm;
+    const real mag2 = ((real)1.0 - amount) * mag + amount * mm;
+    Z[k] = mag > (real)0. ? c_scale(X, mag2 / mag) : mk(mag2, (real)0.);
+}
+MS_DEV void imprint_commit_body(const ImprintStepEvt* MS_RESTRICT evts, int n_evts, int* prev_bins, const Ctx& c) {
+    for (int e = c.bx * c.nthr + c.tid; e < n_evts; e += c.nthr * 64) prev_bins[evts[e].slot] = evts[e].n / 2 + 1;
+}

@@ -331,6 +331,37 @@ class BatchRenderer:
             self.d_plock_evt, self.n_plock = dev.upload(ev), len(rows)
             self.plock_scratch = dev.empty(int(scr[-1]), real)
             self.plock_zbase = zbase
+        # event feedback (+ imprint): the events of a render depend on each other, so they are processed rank by rank
+        # (rank e of all renders together): feedback kernel, then -- with the imprint on -- forward / one-grain step /
+        # inverse on a spectral stage of that rank's grains
+        self.seq_ranks = []
+        if t.seq is not None and len(t.seq):
+            sq = t.seq
+            renders = np.unique(sq[:, 0].astype(np.int64))
+            slot_of = {int(rr): i for i, rr in enumerate(renders)}
+            self.seq_max_bins = int(sq[:, 7].max()) // 2 + 1
+            self.seq_mem = dev.zeros(len(renders) * self.seq_max_bins, real)
+            self.seq_prev_bins = dev.zeros(len(renders), np.int32)
+            for e in np.unique(sq[:, 1].astype(np.int64)):
+                rows = sq[sq[:, 1] == e]
+                fbr = rows[rows[:, 5] >= 0]
+                item = {"n_fb": len(fbr), "n_imp": 0}
+                if len(fbr):
+                    ev = np.zeros(len(fbr), np.dtype(_abi.FeedbackEvt))
+                    ev["cur"], ev["prev"], ev["dst"], ev["n_cur"], ev["n_prev"], ev["fb"] = fbr[:, 2], fbr[:, 3], fbr[:, 5], fbr[:, 7], fbr[:, 4], fbr[:, 8]
+                    item["d_fb"], item["fb_max_n"] = dev.upload(ev), int(fbr[:, 7].max())
+                imr = rows[rows[:, 6] >= 0]
+                if len(imr):
+                    src = np.where(imr[:, 5] >= 0, imr[:, 5], imr[:, 2]).astype(np.int64)        # the fed-back grain, or the grain itself at rank 0
+                    jobs = np.zeros(len(imr), np.dtype(_abi.SpecJob))
+                    jobs["n"], jobs["in_a"], jobs["out_a"], jobs["in_b"], jobs["out_b"] = imr[:, 7].astype(np.int64), src, imr[:, 6].astype(np.int64), -1, -1
+                    stg = _SpectralStage(dev, self.api, jobs, self.pool, self.pool)
+                    zbase, zoffs = stg.z_table()
+                    iv = np.zeros(len(imr), np.dtype(_abi.ImprintStepEvt))
+                    iv["z"], iv["n"], iv["amount"], iv["smooth"] = zoffs, imr[:, 7].astype(np.int64), imr[:, 9], imr[:, 10]
+                    iv["slot"] = [slot_of[int(rr)] for rr in imr[:, 0]]
+                    item.update(n_imp=len(imr), stage=stg, zbase=zbase, d_imp=dev.upload(iv))
+                self.seq_ranks.append(item)
         # spectral imprint: single-signal jobs (Z = the grain's DFT), forward -> per-render moving average -> inverse
         self.imprint_stage, self.n_imprint_renders = None, 0
         if len(t.imprint):
@@ -422,6 +453,19 @@ class BatchRenderer:
                 if self.post_stage is not None:
                     self.post_stage.run()
                 mark("resonator_waveguide")
+            if self.seq_ranks:
+                self.seq_prev_bins.fill_(-1) if hasattr(self.seq_prev_bins, "fill_") else self.seq_prev_bins.fill(-1)
+                for item in self.seq_ranks:
+                    if item["n_fb"]:
+                        _check(dev, lib.ms_feedback(dev.ptr(item["d_fb"]), item["n_fb"], item["fb_max_n"], dev.ptr(self.pool), st))
+                    if item["n_imp"]:
+                        stg = item["stage"]
+                        stg.forward()
+                        zptr = C.c_void_p(dev.ptr(stg.ws).value + item["zbase"])
+                        _check(dev, lib.ms_imprint_step(dev.ptr(item["d_imp"]), item["n_imp"], self.seq_max_bins, zptr,
+                                                        dev.ptr(self.seq_mem), dev.ptr(self.seq_prev_bins), st))
+                        stg.inverse()
+                mark("event_feedback")
             if self.imprint_stage is not None:
                 self.imprint_stage.forward()
                 zptr = C.c_void_p(dev.ptr(self.imprint_stage.ws).value + self.imprint_zbase)
@@ -465,7 +509,8 @@ class BatchRenderer:
         return m
 
     def close(self):
-        for s in (self.tilt_stage, self.grain_stage, self.rot_stage, self.imprint_stage, self.plock_stage, self.post_stage) + tuple(self.cep_stages or ()):
+        for s in (self.tilt_stage, self.grain_stage, self.rot_stage, self.imprint_stage, self.plock_stage, self.post_stage) + \
+                tuple(self.cep_stages or ()) + tuple(it["stage"] for it in getattr(self, "seq_ranks", []) if it["n_imp"]):
             if s is not None:
                 s.close()
         if self.fir_handle:

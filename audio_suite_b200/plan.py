@@ -26,7 +26,7 @@ MODE_GAUSS, MODE_DUST, MODE_NOISE, MODE_SKEW, MODE_RES, MODE_PLAIN, MODE_WAVELET
 WAVELET_FLOOR = 128                 # M:319
 _MODE_ID = {m: i for i, m in enumerate(BASIC_MODES)}
 
-_NEXT_ROW_FLAGS = ("event_feedback_on",)
+_NEXT_ROW_FLAGS = ()
 _NEXT_ROW_MODES = ()
 
 
@@ -251,6 +251,7 @@ class RenderPlan:
     events: List[EventPlan] = field(default_factory=list)
     adsr: tuple = (0, 0, 0, 1.0, 1.0)       # A, D, R samples, sustain, curve
     imprint: Optional[tuple] = None         # (amount, smooth) when SpectralImprint is active (M:625, 736-738)
+    feedback: Optional[float] = None        # event_feedback_amt when event feedback is on (M:731-734)
     er_offs: Optional[np.ndarray] = None    # int32 tap delays (0 < off < out_n)
     er_gains: Optional[np.ndarray] = None   # float64
     ir: Optional[np.ndarray] = None         # float64 mono taps (<= 8192) or None
@@ -408,6 +409,8 @@ def plan_render(params) -> RenderPlan:
     r = max(0, int(round(base_sr * float(params["env_r"]) / 1000.0)))
     rp.adsr = (a, d, r, float(min(max(float(params["env_s"]), 0.0), 1.0)), float(max(1e-6, float(params["env_curve"]))))
 
+    if params["event_feedback_on"]:
+        rp.feedback = float(params["event_feedback_amt"])
     if params["spectral_imprint_on"]:
         rp.imprint = (float(params["spectral_imprint_amt"]), float(params["spectral_imprint_smooth"]))
     if params["er_cloud_on"]:

@@ -90,6 +90,8 @@ class Tables:
     dust_val: np.ndarray = None
     atoms: np.ndarray = None        # wavelet atoms, float64 [N, 4]
     atom_shift: np.ndarray = None   # int32 [N]
+    seq: np.ndarray = None          # event-sequential tail (renders with event feedback), rows float64:
+                                    # render, rank, cur, prev (-1: none), n_prev, fb_dst (-1), imp_dst (-1), n, fb, amount, smooth
     wg: tuple = None                # (rows int64 [N, 5] = src, dst, n, line_begin, line_count ; lines float64 [L, 3])
     res: tuple = None               # (rows int64 [N, 5] = src, dst, n, mode_begin, mode_count ; decay [N] ; modes float64 [M, 3])
     post_grain: tuple = None        # spectral items applied after the resonator bank (multiband): (n, src, dst, ops)
@@ -130,6 +132,7 @@ def pack_chunk(plans) -> Tables:
     cp_rows, cp_factor, cp_pre, cp_post = [], [], [], []
     rs_rows, rs_decay, rs_modes, n_modes = [], [], [], 0
     wg_rows, wg_lines, n_lines = [], [], 0
+    seq_rows = []
     post_grain = _Items()
     tap_off, tap_gain, n_taps = [], [], 0
     irs, ir_index, n_ir = [], {}, 0
@@ -149,6 +152,7 @@ def pack_chunk(plans) -> Tables:
         ev_begin = len(ola_e)
         max_len = 0
         x_begin, x_end = n, 0
+        prev_final, prev_n, rank = -1, 0, 0
         for ev in rp.events:
             st = np.random.PCG64(ev.seed).state["state"]
             s_hi, s_lo = st["state"] >> 64, st["state"] & 0xFFFFFFFFFFFFFFFF
@@ -240,7 +244,22 @@ def pack_chunk(plans) -> Tables:
                     alg["grain_spectral"] += 2 * ev.n
                     g_at = b_at
             last[r] = (micro, g_at, ev.n)
-            if rp.imprint is not None and ev.n >= 64 and rp.imprint[0] > 0:         # M:570: short grains / amount <= 0 pass through
+            if rp.feedback is not None:
+                # M:731-740: feedback from the previous event's FINAL grain, then the imprint, rank by rank
+                cur, fb_dst, imp_dst = g_at, -1, -1
+                if prev_final >= 0:
+                    fb_dst = pool_n
+                    pool_n += ev.n
+                    g_at = fb_dst
+                imp_on = rp.imprint is not None and ev.n >= 64 and rp.imprint[0] > 0
+                if imp_on:
+                    imp_dst = pool_n
+                    pool_n += ev.n
+                    g_at = imp_dst
+                seq_rows.append((r, rank, cur, prev_final, prev_n, fb_dst, imp_dst, ev.n, rp.feedback,
+                                 rp.imprint[0] if imp_on else 0.0, rp.imprint[1] if imp_on else 0.0))
+                prev_final, prev_n, rank = g_at, ev.n, rank + 1
+            elif rp.imprint is not None and ev.n >= 64 and rp.imprint[0] > 0:         # M:570: short grains / amount <= 0 pass through
                 src = g_at
                 g_at = pool_n                      # imprinted grain (grain_last keeps the grain before it, M:729)
                 pool_n += ev.n
@@ -358,6 +377,7 @@ def pack_chunk(plans) -> Tables:
                np.frombuffer(b"".join(pl_post), np.uint8).reshape(npl, _SPEC_OP_BYTES) if npl else np.zeros((0, _SPEC_OP_BYTES), np.uint8))
     t.res = (np.asarray(rs_rows, np.int64).reshape(-1, 5), np.asarray(rs_decay, np.float64),
              np.concatenate(rs_modes) if rs_modes else np.zeros((0, 3)))
+    t.seq = np.asarray(seq_rows, np.float64).reshape(-1, 11)
     t.wg = (np.asarray(wg_rows, np.int64).reshape(-1, 5), np.concatenate(wg_lines) if wg_lines else np.zeros((0, 3)))
     t.post_grain = post_grain.arrays()
     ncp = len(cp_rows)
@@ -388,7 +408,7 @@ def merge_chunks(chunks) -> Tables:
     m = Tables()
     pool_b = mono_b = frame_b = h_b = tap_b = ir_b = dust_b = olae_b = env_b = atom_b = render_b = 0
     parts = {k: [] for k in ("sy1", "sy2", "ola_r", "env_reps", "ola_e", "fir", "post", "tap_off", "tap_gain", "irs", "dust_pos", "dust_val",
-                             "atoms", "atom_shift", "imprint", "imprint_par", "odd", "out_at", "out_n", "y_at", "last", "srs")}
+                             "atoms", "atom_shift", "imprint", "imprint_par", "seq", "odd", "out_at", "out_n", "y_at", "last", "srs")}
     items = {k: [[], [], [], []] for k in ("tilt", "grain", "rot", "post_grain")}
     rs_parts, mode_b = [[], [], []], 0
     wg_parts, line_b = [[], []], 0
@@ -404,6 +424,10 @@ def merge_chunks(chunks) -> Tables:
         if c.imprint.size:
             c.imprint[:, 0] += render_b
             c.imprint[:, 1:3] += pool_b
+        if c.seq.size:
+            c.seq[:, 0] += render_b
+            for col in (2, 3, 5, 6):
+                c.seq[:, col] += np.where(c.seq[:, col] >= 0, pool_b, 0)
         if c.plock[0].size:
             c.plock[0][:, 0:2] += pool_b
         if c.cep[0].size:

@@ -91,6 +91,13 @@ typedef struct {
 typedef struct { int64_t z; int32_t n, _pad; } ms_imprint_evt;               /* z: offset of the grain's spectrum, complex elements */
 typedef struct { int32_t ev_begin, ev_end; double amount, smooth; } ms_imprint_render;
 /* ms_imprint_f32 / ms_imprint_f64: declared below by MS_DECLARE_API */
+/* Event feedback (main_v2.py:731-734): dst = (1 - fb) cur + fb prev over the first min(n_cur, n_prev) samples, cur beyond.
+ * prev is the PREVIOUS event's final grain of the same render, so the events of a render are processed rank by rank
+ * (the host launches rank e of all renders together).  With the spectral imprint on, ms_imprint_step advances the
+ * per-render moving average by exactly one grain (state: `mem`, max_bins REALs per render slot; prev_bins per slot). */
+typedef struct { int64_t cur, prev, dst; int32_t n_cur, n_prev; double fb; } ms_feedback_evt;
+typedef struct { int64_t z; int32_t n, slot; double amount, smooth; } ms_imprint_step_evt;
+/* ms_feedback_f32/_f64, ms_imprint_step_f32/_f64: declared below by MS_DECLARE_API */
 /* resonator_bank (main_v2.py:369-384) on time-domain grains: dst = 0.55 src + 0.45 bank sign(src), bank = the
  * peak-normalised sum of decaying sinusoids whose frequencies / phases the host drew.  One CTA per grain. */
 typedef struct { double f_over_sr, phase, weight; } ms_res_mode;
@@ -247,6 +254,9 @@ typedef struct {
     int ms_spectral_forward##SFX(void* handle, void* stream); \
     int ms_spectral_inverse##SFX(void* handle, void* stream); \
     int ms_spectral_z_table##SFX(void* handle, int64_t* host_z_offsets, size_t* z_base_bytes); \
+    int ms_feedback##SFX(const ms_feedback_evt* dev_evts, int n_evts, int max_n, REAL* pool, void* stream); \
+    int ms_imprint_step##SFX(const ms_imprint_step_evt* dev_evts, int n_evts, int max_bins, REAL* z_base, REAL* mem, \
+    int32_t* prev_bins, void* stream); \
     int ms_waveguide##SFX(const ms_wg_evt* dev_evts, int n_evts, const ms_wg_line* dev_lines, REAL* pool, void* stream); \
     int ms_resonator##SFX(const ms_res_evt* dev_evts, int n_evts, const ms_res_mode* dev_modes, REAL* pool, void* stream); \
     int ms_partial_lock##SFX(const ms_plock_evt* dev_evts, int n_evts, REAL* z_base, REAL* scratch, void* stream); \

@@ -641,7 +641,7 @@ imprint_noise_floor = rounding_noise_floor
 
 
 # --------------------------------------------------------------------------- render
-_UNSUPPORTED_FLAGS = ("event_feedback_on",)
+_UNSUPPORTED_FLAGS = ()
 
 
 def design_rate(base_sr, unfold):
@@ -718,6 +718,7 @@ def render(params, progress=None, taps=None, jitter=None):
     micro_ms = float(params["micro_ms"])
     n_evt = len(plan["events"])
     imprint = ImprintMemory() if params["spectral_imprint_on"] else None          # M:625
+    previous = None                                                               # M:626: last event's grain, as placed
     for ev in plan["events"]:
         i = ev["index"]
         if mode == "Wavelet atoms":
@@ -767,10 +768,15 @@ def render(params, progress=None, taps=None, jitter=None):
                                  [float(params["mb_u1"]), float(params["mb_u2"]), float(params["mb_u3"])],
                                  float(params["mb_roll"]))
         grain_last = g.copy()
+        if params["event_feedback_on"] and previous is not None:                  # M:731-734
+            fb = float(params["event_feedback_amt"])
+            m = min(len(g), len(previous))
+            g[:m] = (1.0 - fb) * g[:m] + fb * previous[:m]
         if imprint is not None:                                                   # M:736-738 (after grain_last)
             if jitter:
                 g = g + jitter * np.max(np.abs(g)) * np.random.default_rng(777 + i).standard_normal(g.size)
             g = imprint.apply(g, float(params["spectral_imprint_amt"]), float(params["spectral_imprint_smooth"]))
+        previous = g.copy()                                                       # M:740 (before the placement test)
         if ev["placed"]:
             a, o, ln = ev["start"], ev["offset"], ev["length"]
             mix[a:a + ln] += ev["amp"] * g[o:o + ln]

@@ -288,6 +288,18 @@ PRESET_LIKE = {
     "orbital_friction_loop": dict(gen_mode="Stick–slip friction", micro_ms=3.2, ss_threshold=0.55, ss_build=0.035, ss_decay=0.88,
                                   ss_noise=0.04, wg_on=True, wg_lines=6, wg_max_ms=5.5, wg_fb=0.6, event_process="Poisson",
                                   grains_per_sec=5, partial_stretch=1.03, er_cloud_on=False),
+    "wavelet_mist": dict(out_dur_s=12.0, time_unfold=30.0, sat_drive=1.05, stereo_width=0.75, gen_mode="Wavelet atoms", micro_ms=1.6,
+                         seed=33009, noise_tilt=-5.0, wav_base_hz=1700.0, wav_count=14, wav_spread=1.1,
+                         unfold_mode="Multi-band unfold", partial_stretch=0.92, nl_warp_on=True, nl_warp_power=1.35,
+                         cep_warp_on=True, cep_factor=1.35, mb_b1=1800.0, mb_b2=7000.0, mb_u1=55.0, mb_u2=28.0, mb_u3=10.0,
+                         mb_roll=2500.0, bandlimit_out_hz=17500.0, bandlimit_roll_hz=3200.0, event_process="Poisson",
+                         grains_per_sec=14.0, max_grains=5500, grain_amp_rand=0.25, grain_offset_max_ms=120.0,
+                         bp_density="0:10, 5:18, 12:12", bp_unfold="0:45, 6:22, 12:35", bp_cutoff="0:16000, 7:11000, 12:17500",
+                         bp_stretch="0:0.85, 12:0.95", res_bank_on=True, res_modes=30, res_fmin=90.0, res_fmax=9000.0,
+                         res_decay_ms=110.0, event_feedback_on=True, event_feedback_amt=0.22, spectral_imprint_on=True,
+                         spectral_imprint_amt=0.25, spectral_imprint_smooth=0.94, er_taps=520, er_max_ms=60.0,
+                         space_ir_on=True, space_ir_max_samps=16000, env_a=80.0, env_d=450.0, env_s=0.7, env_r=3800.0,
+                         env_curve=1.6),
     "soft_ellipse_memory": dict(gen_mode="Noise burst", micro_ms=2.2, noise_tilt=-8.0, event_process="Poisson",
                                 grains_per_sec=6, spectral_imprint_on=True, spectral_imprint_amt=0.25,
                                 spectral_imprint_smooth=0.97, partial_stretch=0.95, bp_cutoff="0:14000, 12:9000, 24:6000",

@@ -131,7 +131,9 @@ def test_render_preset_rows_wavelet_atoms_and_imprint(cuda_dev, name):
                                 dict(res_bank_on=True, partial_lock_on=True, partial_stretch=0.9, unfold_mode="Multi-band unfold"),
                                 dict(gen_mode="Micro-chaos", nl_warp_on=True, res_bank_on=True, spectral_imprint_on=True),
                                 dict(gen_mode="Stick–slip friction", wg_on=True, wg_lines=14, wg_max_ms=1.5, partial_lock_on=True,
-                                     partial_stretch=1.18)])
+                                     partial_stretch=1.18),
+                                dict(event_feedback_on=True, event_feedback_amt=0.5, spectral_imprint_on=True, bandlimit_on=False,
+                                     bp_unfold="0:60,1.5:45,3:60", gen_mode="Wavelet atoms")])
 def test_render_spectral_extras(cuda_dev, kw):
     """SURVEY 8(f) rank 1 rows on the GPU: power warp, partial lock, imprint, combined, several events per render."""
     base = dict(event_process="Poisson", out_dur_s=3.0, grains_per_sec=25.0, time_unfold=60.0, micro_ms=3.0,

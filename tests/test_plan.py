@@ -67,8 +67,7 @@ def test_missing_key_raises_keyerror_like_reference():
 
 
 def test_unsupported_rows_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        P.plan_render(configs.with_defaults(event_feedback_on=True))
+    P.plan_render(configs.with_defaults(event_feedback_on=True, spectral_imprint_on=True, event_process="Poisson"))
     with pytest.raises(NotImplementedError):
         P.plan_render(configs.with_defaults(cep_warp_on=True, partial_lock_on=True, partial_stretch=1.2))
     P.plan_render(configs.with_defaults(gen_mode="Stick–slip friction", wg_on=True, res_bank_on=True, cep_warp_on=True))
