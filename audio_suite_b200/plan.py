@@ -223,7 +223,7 @@ class EventPlan:
     placed: bool = False
     spec: Optional[object] = None           # _abi.SpecOp or None
     plock: Optional[tuple] = None           # (factor, top_n, neigh, pre-operator) when partial_lock_stretch is active
-    cep: Optional[tuple] = None             # (factor, pre-operator) when cepstral_warp is active
+    cep: Optional[tuple] = None             # (factor, pre-operator, operator of its last inverse) when cepstral_warp is active
     stick_noise: float = 0.0
     wg: Optional[np.ndarray] = None         # waveguide lines: float64 [L, 3] = delay in samples, loop gain, mix
     res: Optional[tuple] = None             # (modes float64 [K, 3] = f/sr, phase, weight ; decay per sample) for resonator_bank
@@ -351,12 +351,19 @@ def plan_render(params) -> RenderPlan:
         mb_here = not (res_on or wg_on)                                  # the multiband unfold follows them (M:719-727)
         if params["cep_warp_on"] and n >= 64:
             # M:696-697: cepstral_warp sits between low-pass / power warp and the stretch; its three elementwise steps
-            # run between transforms of their own, the stage's inverse applies stretch + multiband
-            if params["partial_lock_on"] and not abs(ev.stretch - 1.0) < 1e-9:
-                raise NotImplementedError("microsound_b200: cep_warp_on together with an active partial lock is not on the accelerated path yet")
-            ev.cep = (float(params["cep_factor"]), grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, post=False, keep=True))
-            ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0 if params["partial_lock_on"] else ev.stretch, pre=False,
-                                    keep=True, mb=mb_here)
+            # run between transforms of their own, the stage's inverse applies what follows (stretch + multiband) --
+            # unless an active partial lock follows: then the inverse is plain and the lock stage takes over from there
+            pl_active = bool(params["partial_lock_on"]) and not abs(ev.stretch - 1.0) < 1e-9
+            pre = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, post=False, keep=True)
+            if pl_active:
+                ident = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, pre=False, post=False, keep=True)
+                ev.cep = (float(params["cep_factor"]), pre, ident)
+                ev.plock = (ev.stretch, int(params["pl_top_n"]), int(params["pl_neigh"]), ident)
+                ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0, pre=False, keep=True, mb=mb_here)
+            else:
+                ev.spec = grain_spec_op(params, sr_evt, n, ev.cutoff_gen, 1.0 if params["partial_lock_on"] else ev.stretch, pre=False,
+                                        keep=True, mb=mb_here)
+                ev.cep = (float(params["cep_factor"]), pre, ev.spec)
         elif params["partial_lock_on"]:
             # M:699-702: partial_lock_stretch REPLACES fft_partial_stretch; it is the identity for n < 64 or a factor of 1
             if n >= 64 and not abs(ev.stretch - 1.0) < 1e-9:

@@ -204,18 +204,19 @@ def pack_chunk(plans) -> Tables:
                 cp_rows.append((micro, g_at, ev.n))
                 cp_factor.append(ev.cep[0])
                 cp_pre.append(bytes(ev.cep[1]))
-                cp_post.append(bytes(ev.spec))
+                cp_post.append(bytes(ev.cep[2]))
                 alg["grain_spectral"] += 2 * ev.n * (1 + int(ev.cep[1].lp_on) + (1 if ev.cep[1].warp_exp else 0)
-                                                     + int(ev.spec.stretch_on) + (1 if ev.spec.n_bands else 0))
-            elif ev.plock is not None:
+                                                     + int(ev.cep[2].stretch_on) + (1 if ev.cep[2].n_bands else 0))
+            if ev.plock is not None:
+                pl_src = g_at                      # the raw transient, or the cepstrally warped grain
                 g_at = pool_n
                 pool_n += ev.n
-                pl_rows.append((micro, g_at, ev.n, ev.plock[1], ev.plock[2]))
+                pl_rows.append((pl_src, g_at, ev.n, ev.plock[1], ev.plock[2]))
                 pl_factor.append(ev.plock[0])
                 pl_pre.append(bytes(ev.plock[3]))
                 pl_post.append(bytes(ev.spec))
                 alg["grain_spectral"] += 2 * ev.n * (1 + int(ev.plock[3].lp_on) + (1 if ev.plock[3].warp_exp else 0) + (1 if ev.spec.n_bands else 0))
-            elif ev.spec is not None:
+            elif ev.cep is None and ev.spec is not None:
                 g_at = pool_n
                 pool_n += ev.n
                 grain.add(ev.n, micro, g_at, ev.spec)

@@ -175,6 +175,8 @@ def test_next_row_generators(emul, kw):
                                      partial_stretch=1.3),
                                 dict(cep_factor=0.8, gen_mode="Gaussian click", bp_unfold="0:25,0.6:25.013"),
                                 dict(cep_factor=1.2, gen_mode="Wavelet atoms", partial_lock_on=True),
+                                dict(cep_factor=1.1, partial_lock_on=True, partial_stretch=0.8, unfold_mode="Multi-band unfold",
+                                     res_bank_on=True, nl_warp_on=True),
                                 dict(cep_factor=1.25, gen_mode="Noise burst", bandlimit_on=True)])
 def test_cepstral_warp(emul, kw):
     """cepstral_warp (main_v2.py:150-163) as forward / log / inverse / resample / forward / exp / inverse.  Without the
