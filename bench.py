@@ -175,8 +175,6 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = engine.CudaDevice(local)
@@ -288,7 +286,7 @@ def run_ours(args):
     h2d = d2h = 0
     e2e_ms = []
     host_out = torch.empty(2 * len(mine) * FRAMES_PER_RENDER, dtype=torch.float32).pin_memory()
-    E2E_WARM = 2      # untimed: the first call starts the planning workers, the second sizes the per-slot device arenas
+    E2E_WARM = 3      # untimed: the first call starts the planning workers, the second sizes the per-slot device arenas, the third settles the allocator
     for s in range(E2E_WARM + args.e2e_steps if args.e2e_steps > 0 else 0):
         barrier()
         t0 = time.perf_counter()
@@ -371,10 +369,27 @@ def run_ours(args):
 
 def main():
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # rank 0 prints ONE JSON line on stdout and nothing else: libraries that write to file descriptor 1 (NCCL's version
+    # banner) are sent to stderr while the bench runs; the saved descriptor gets the JSON line at the end
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    import builtins
+    _print = builtins.print
+
+    def _json_print(*a, **k):
+        k.setdefault("file", real_stdout)
+        _print(*a, **k)
+        real_stdout.flush()
+    builtins.print = _json_print
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        builtins.print = _print
 
 
 if __name__ == "__main__":

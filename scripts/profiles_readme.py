@@ -2,21 +2,21 @@
 import io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
-d = json.load(open(os.path.join(P, "bench_r01g_n1.json")))
-r = json.load(open(os.path.join(P, "bench_r01g_reference_arm.json")))
+d = json.load(open(os.path.join(P, "bench_r01i_n1.json")))
+r = json.load(open(os.path.join(P, "bench_r01i_reference_arm.json")))
 o = io.StringIO()
 w = lambda *a: print(*a, file=o)
 w("# profiles/ — round 1 measurements (B200, sm_100a, CUDA 12.9, driver 580)\n")
 w("All runs: `gpurun` on one fresh B200 box; timed numbers come from `bench.py` (CUDA events, no profiler);")
 w("ncu numbers are cold-cache/serialised and are used for *shares* and counters only.  Regenerate this file with")
 w("`python scripts/profiles_readme.py`.\n")
-w("## 1. bench.py, C5 sweep (4096 renders x 96000 stereo frames, f64), N=1 (`bench_r01g_n1.json`)\n")
+w("## 1. bench.py, C5 sweep (4096 renders x 96000 stereo frames, f64), N=1 (`bench_r01i_n1.json`)\n")
 e = d["e2e"]
 w("* `value` (plan resident in HBM): **%.3e samples/s** (%.1f ms/step), %d kernel launches/step, SM clock %s MHz, throttle reasons %s" % (
     d["value"], d["ms_per_step"], d["gpu_launches"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"]))
 w("* `e2e` (host dicts -> pinned host float32 audio, `render_batch`): **%.3e samples/s** (%.1f ms/step mean of %s; H2D %.1f MB, D2H %.2f GB)" % (
     e["value"], e["ms_per_step"], e.get("ms_each_rank0"), e["h2d_bytes_per_step"] / 1e6, e["d2h_bytes_per_step"] / 1e9))
-w("* `cpu_baseline` (oracle port, 1 core): %.3e samples/s;  `--impl reference` (oracle port, %d cores, `bench_r01g_reference_arm.json`): %.3e samples/s" % (
+w("* `cpu_baseline` (oracle port, 1 core): %.3e samples/s;  `--impl reference` (oracle port, %d cores, `bench_r01i_reference_arm.json`): %.3e samples/s" % (
     d["cpu_baseline"]["value"], r["cpu_baseline"]["cores"], r["value"]))
 w("* e2e / reference-arm = **%.0fx**;  value / reference-arm = %.0fx" % (e["value"] / r["value"], d["value"] / r["value"]))
 w("* round history of the same metric (ms/step, kernels | e2e): first GPU run 84.9 | 252 -> session start 67.2 | 226 -> now %.1f | %.0f\n" % (d["ms_per_step"], min(e.get("ms_each_rank0", [e["ms_per_step"]]))))
@@ -34,11 +34,19 @@ w("| # kernel | ms |\n|---|---|")
 for k, v in d["kernels_ms"].items():
     w("| %s | %.3f |" % (k, v))
 w("")
-w("2 GPUs (`torchrun`, NCCL gather of rendered buffers inside the step; commit before the static FFT tiles): 31.3 ms/step, 2.51e10 samples/s (1.81x of that commit's N=1, 56.7 ms); e2e 105.7 ms.  File: `bench_r01f_n2_raw.txt`.\n")
+w("### 1 / 2 / 4 / 8 GPUs (`torchrun`, one rank per GPU, NCCL gather of the rendered buffers to rank 0 inside the step; strong scaling, 4096 renders)\n")
+w("| N | ms/step | samples/s | speed-up | e2e ms/step | e2e samples/s |\n|---|---|---|---|---|---|")
+base = None
+for n in (1, 2, 4, 8):
+    x = json.load(open(os.path.join(P, "bench_r01i_n%d.json" % n)))
+    base = base or x["value"]
+    w("| %d | %.2f | %.3e | %.2fx | %.1f | %.3e |" % (n, x["ms_per_step"], x["value"], x["value"] / base, x["e2e"]["ms_per_step"], x["e2e"]["value"]))
+w("")
+w("At N = 8 a rank renders its 512 renders in about 5.9 ms and rank 0 then receives 2.75 GB over NVLink (about 4.6 ms): the gather, not the kernels, bounds the step.  Cutting every rank's share into four slices whose gather overlaps the next slice's rendering was measured slower (12.0 ms, `bench_r01h_n8_sliced4.json`: the slices get launch-bound), so it stays optional (`--slices`).  End to end the multi-GPU runs are bound by host planning (0.27 ms of Python per render, 32 cores on the 8-GPU box).\n")
 w("C4 (long-form render, 57.6 M frames, 1222 events of 300000 samples): kernels 31 ms (synth 6.4, grain spectral 21.1, OLA 0.8, FIR 2.0, post 0.8), `render()` end to end 0.48 s; the reference took 244 s on one core of the build container (`tests/golden/c4_full.npz`).\n")
-w("## 2. ncu launch list of one step, 512-render slab (`launches_r01g_512renders.csv`)\n")
+w("## 2. ncu launch list of one step, 512-render slab (`launches_r01i_512renders.csv`)\n")
 w("`ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,... --clock-control none` around the timed step of `bench.py --renders 512`.\n")
-out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summarise.py"), os.path.join(P, "launches_r01g_512renders.csv"), "512"],
+out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summarise.py"), os.path.join(P, "launches_r01i_512renders.csv"), "512"],
                      capture_output=True, text=True).stdout
 w(out)
 w("Stage shares under ncu agree with the CUDA-event stage table above (spectral stages 48 %, FIR 28 %, synth 11 %, post 10 %, OLA 3 %).  `ncu_traffic.json` holds the per-stage DRAM bytes per render that `bench.py` scales into `roofline.traffic`.\n")
