@@ -50,7 +50,15 @@ out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summari
                      capture_output=True, text=True).stdout
 w(out)
 w("Stage shares under ncu agree with the CUDA-event stage table above (spectral stages 48 %, FIR 28 %, synth 11 %, post 10 %, OLA 3 %).  `ncu_traffic.json` holds the per-stage DRAM bytes per render that `bench.py` scales into `roofline.traffic`.\n")
-w("## 3. Earlier captures kept for the record\n")
+w("## 3. `ncu --set full` counters of the key kernels, current build (`ncu_full_r01i_key_kernels.csv`, 512-render slab)\n")
+rows = list(__import__("csv").reader(open(os.path.join(P, "ncu_full_r01i_key_kernels.csv"))))
+w("| " + " | ".join(c[:28] for c in rows[0]) + " |")
+w("|" + "---|" * len(rows[0]))
+for r in rows[1:]:
+    w("| " + " | ".join((c if i == 0 else (c[:8] if c.replace(".", "").isdigit() else c)) for i, c in enumerate(r)) + " |")
+w("")
+w("Reading: the static in-place FFT tiles (ColsK<..., 256>, ColsK<7, 0, 1, 8>, RowsK<0, 1, 0, 8>) now keep 58-61 % of the warp slots busy (24-30 % before this round's occupancy work), 5 CTAs/SM limited equally by registers (48) and shared memory; the FP64 pipe is 17-35 % busy and the issue slots 31-55 %, so they are still latency-bound on shared-memory round trips rather than on a pipe or on DRAM (29-32 % of DRAM throughput for the FIR kernels).  OlaK runs at 35 % DRAM throughput with 44 % of the warp slots (64 registers: 4 CTAs/SM).  PostMaxK has 32 % of its shared-memory wavefronts in bank conflicts (the de-interleaving stores), the next thing to fix there.  SynthNormalK is integer/FP64-issue bound (DRAM 2.6 %), as designed.\n")
+w("## 4. Earlier captures kept for the record\n")
 w("* `ncu_full_raw_r01c_512renders.csv`: `ncu --set full` raw metrics of every kernel of a step at build r01c (first FFT engine): FFT tile kernels 24-30 % of warp slots active, fp64 pipe 6-18 %, issue 30-45 % — latency-bound; that reading drove the occupancy work of this round (register caps, in-place static tiles).")
 w("* `launches_r01b_512renders.csv`, `bench_r01_*.json`: first measurements of the round (84.9 ms/step, e2e 252 ms, reference arm on 16 cores).")
 w("* Source-level stall samples of the FIR rows kernel and the inverse Bluestein columns kernel (ncu `--set full --import-source on`, build r01e): long-scoreboard stalls on twiddle / job-descriptor loads dominated (52 % / 46 % of samples); integer address arithmetic was 70 % of issued instructions.  Fixes that followed: job descriptor staged in shared memory, magic-number divisions, static tile geometry.")
