@@ -161,7 +161,7 @@ extern "C" int MS_API(ms_post)(const ms_post_render* renders, int n_renders, int
                        float* out, void* stream) {
     const unsigned gx = (unsigned)((max_n + OLA_TILE - 1) / OLA_TILE);
     if (ms_memset(maxbits, 0, sizeof(uint64_t) * (size_t)n_renders, (ms_stream_t)stream)) return -1;
-    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, (2 * POST_PAR + POST_NC + 1 + OLA_NTHR + OLA_TILE) * sizeof(real), (ms_stream_t)stream,
+    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, (2 * POST_PAR + POST_NC + 1 + OLA_NTHR + OLA_TILE + OLA_TILE / 8 + 8) * sizeof(real), (ms_stream_t)stream,
                                    renders + _y0, mono, (unsigned long long*)maxbits + _y0)) return -1; })
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostWriteK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream,
                                    renders + _y0, (const real*)mono, (const unsigned long long*)maxbits + _y0, (float2*)out)) return -1; })

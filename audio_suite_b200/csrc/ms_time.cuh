@@ -145,12 +145,12 @@ MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, uns
                 a0 += ck * x0; a1 += ck * x1; a2 += ck * x2; a3 += ck * x3;
                 x0 = x1; x1 = x2; x2 = x3;
             }
-            const int j0 = 8 * t + par;
+            const int j0 = 9 * t + par;                  // slot of output j = 8t + par + 2q is j + (j >> 3): stride 9, conflict-free
             res[j0] = a0; res[j0 + 2] = a1; res[j0 + 4] = a2; res[j0 + 6] = a3;
         }
         c.sync();
         for (int j = c.tid; j < len; j += c.nthr) {
-            const real r = res[j];
+            const real r = res[j + (j >> 3)];
             mono[R.rbuf + t0 + j] = r;
             m = r_max(m, r_max(r_abs(r), r_abs(y[t0 + j])));
         }
