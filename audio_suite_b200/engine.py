@@ -544,7 +544,32 @@ def render(params, progress=None, device=None, precision="auto"):
     return audio, meta
 
 
-def render_batch(params_list, device=None, precision="auto", host_out=None, chunk=512, depth=3, workers=None, piece=32):
+def _prefetch(gen, depth=2):
+    """Runs a generator in a helper thread, `depth` items ahead: the parent's pipe reads / unpickling / merging of
+    slice k+1 (tables.plan_stream) overlap its table uploads and kernel launches for slice k."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=depth)
+    end = object()
+
+    def pump():
+        try:
+            for item in gen:
+                q.put(item)
+            q.put(end)
+        except BaseException as e:          # re-raised in the consumer
+            q.put(e)
+    threading.Thread(target=pump, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is end:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+
+
+def render_batch(params_list, device=None, precision="auto", host_out=None, chunk=512, depth=3, workers=None, piece=32, ramp=True):
     """Independent renders (the reference's batch loop, main_v2.py:1578-1593) streamed through the GPU.
 
     The batch is cut into slices of `chunk` renders.  Worker processes plan slice k+1 (numpy Generators,
@@ -555,6 +580,8 @@ def render_batch(params_list, device=None, precision="auto", host_out=None, chun
     from collections import deque
     from . import tables as T
     dev = device or CudaDevice()
+    if isinstance(chunk, int) and ramp and len(params_list) >= 4 * chunk:
+        chunk = [max(piece, chunk // 4), max(piece, chunk // 2), chunk]      # short first slices: the drain starts early
     if not hasattr(dev, "torch"):                   # host emulator device (tests): one slice after the other
         outs = []
         for tb in T.plan_stream(params_list, chunk, workers=workers or 1, piece=piece):
@@ -577,7 +604,7 @@ def render_batch(params_list, device=None, precision="auto", host_out=None, chun
     trace = [] if _os.environ.get("MS_TRACE") else None
     t_start = t_prev = _time.perf_counter()
     k = 0
-    for tb in T.plan_stream(params_list, chunk, workers=workers, piece=piece):
+    for tb in _prefetch(T.plan_stream(params_list, chunk, workers=workers, piece=piece)):
         t_got = _time.perf_counter()
         dev.slot_begin(k % (depth + 1))        # the previous user of this slot has retired (see below)
         try:

@@ -10,6 +10,11 @@ import sys
 
 
 def main():
+    import os
+    try:                                             # planning yields the cores to the parent's launches / copies when asked to
+        os.nice(int(os.environ.get("MS_PLAN_NICE", "0")))
+    except Exception:
+        pass
     from audio_suite_b200 import plan as P, tables as T
     inp, out = sys.stdin.buffer, sys.stdout.buffer
     while True:

@@ -702,19 +702,25 @@ def plan_stream(params_list, chunk, workers=None, piece=32):
     packed, while the workers carry on with the later ones -- the caller renders slice k meanwhile."""
     n = len(params_list)
     workers = default_workers() if workers is None else workers
+    # slice boundaries; `chunk` may be a list of sizes (the last one repeats): a short first slice starts the GPU and
+    # the device->host drain early
+    sizes = list(chunk) if isinstance(chunk, (list, tuple)) else [int(chunk)]
+    cuts, a = [], 0
+    while a < n:
+        c = max(1, int(sizes[min(len(cuts), len(sizes) - 1)]))
+        cuts.append((a, min(n, a + c)))
+        a += c
     if workers <= 1:
-        for a in range(0, n, chunk):
-            yield pack_chunk([P.plan_render(p) for p in params_list[a:a + chunk]])
+        for a, b in cuts:
+            yield pack_chunk([P.plan_render(p) for p in params_list[a:b]])
         return
     bounds = []
-    for a in range(0, n, chunk):
-        b = min(n, a + chunk)
+    for a, b in cuts:
         bounds.append([(i, min(b, i + piece)) for i in range(a, b, piece)])
     flat = [ab for bs in bounds for ab in bs]
-    # Static round-robin assignment, no threads in the parent: piece i belongs to worker i % W.  Every worker
-    # first gets its piece of the first slice, then ONE message with all of its remaining pieces, and answers
-    # piece by piece; the parent reads the answers in piece order straight from the pipes (1 MiB pipes let a
-    # worker run a few pieces ahead).  Impulse responses are slimmed before pickling (P._slim_params).
+    # Static round-robin assignment, no threads in the parent: piece i belongs to worker i % W and is answered in
+    # order; the parent reads the answers in piece order straight from the pipes (1 MiB pipes let a worker run a
+    # few pieces ahead).  Impulse responses are slimmed before pickling (P._slim_params).
     import pickle
     import struct
     pool = _pool(workers)
@@ -741,15 +747,24 @@ def plan_stream(params_list, chunk, workers=None, piece=32):
             raise payload
         return payload
     try:
-        for w in range(min(W, len(flat))):
-            send(w, slim(w))
-        for w in range(W):
-            rest = [slim(i) for i in range(w + W, len(flat), W)]
-            if rest:
-                send(w, {"pieces": rest})
+        # Requests go out piece by piece, round-robin (piece i -> worker i % W), always a few slices AHEAD of what is
+        # being read: pickling 4096 parameter dicts costs ~30 ms of the parent's time, which would otherwise sit in
+        # front of the first slice and leave the later workers idle while the earlier ones get their lists.
+        sent = 0
+
+        def send_until(limit):
+            nonlocal sent
+            while sent < min(limit, len(flat)):
+                send(sent % W, slim(sent))
+                sent += 1
         k = 0
+        per_slice = max(len(bs) for bs in bounds)
         for bs in bounds:
-            parts = [recv((k + t) % W) for t in range(len(bs))]
+            send_until(k + len(bs) + max(2 * W, 2 * per_slice))       # this slice plus two rounds / two slices of lookahead
+            parts = []
+            for t in range(len(bs)):
+                parts.append(recv((k + t) % W))
+                send_until(k + t + 1 + max(2 * W, 2 * per_slice))
             k += len(bs)
             yield merge_chunks(parts)
     except BaseException:
