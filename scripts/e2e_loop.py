@@ -7,7 +7,7 @@ dev = engine.CudaDevice(0)
 ir = configs.synth_ir(5.0, 48000, 303)
 params = [configs.c5_params(i, shared_ir=ir) for i in range(R)]
 host = torch.empty(2 * R * 96000, dtype=torch.float32).pin_memory()
-for kw in (dict(chunk=512, workers=14, piece=32), dict(chunk=512, workers=14, piece=64), dict(chunk=512, workers=14, piece=128), dict(chunk=1024, workers=14, piece=128), dict(chunk=512, workers=14, piece=64, ramp=False)):
+for kw in (dict(chunk=512), dict(chunk=512, ramp=False), dict(chunk=512, workers=12)):
     ts = []
     for rep in range(6):
         torch.cuda.synchronize(); t0 = time.perf_counter()
