@@ -43,6 +43,13 @@ for n in (1, 2, 4, 8):
     w("| %d | %.2f | %.3e | %.2fx | %.1f | %.3e |" % (n, x["ms_per_step"], x["value"], x["value"] / base, x["e2e"]["ms_per_step"], x["e2e"]["value"]))
 w("")
 w("At N = 8 a rank renders its 512 renders in about 5.9 ms and rank 0 then receives 2.75 GB over NVLink (about 4.6 ms): the gather, not the kernels, bounds the step.  Cutting every rank's share into four slices whose gather overlaps the next slice's rendering was measured slower (12.0 ms, `bench_r01h_n8_sliced4.json`: the slices get launch-bound), so it stays optional (`--slices`).  End to end the multi-GPU runs are bound by host planning (0.27 ms of Python per render, 32 cores on the 8-GPU box).\n")
+sc = json.load(open(os.path.join(P, "small_configs_r01j.json")))
+w("### Single renders (configs 1-3: launch-latency-bound, a few hundred KB of data each; `small_configs_r01j.json`)\n")
+w("| config | render() ms | kernels only ms | numpy on one host core ms | max-abs vs numpy |\n|---|---|---|---|---|")
+for r_ in sc["rows"]:
+    w("| %s | %.2f | %.3f | %.2f | %.1e |" % (r_["config"], r_["render_ms"], r_["kernels_only_ms"], r_["numpy_ms"], r_["max_abs"]))
+w("")
+w("The smallest case (C1b, 7680 samples) is faster in numpy (0.56 ms) than through the GPU path (0.90 ms: planning, ten launches, one D2H): these sizes are below one kernel launch's worth of HBM time (SURVEY H5).\n")
 w("C4 (long-form render, 57.6 M frames, 1222 events of 300000 samples): kernels 31 ms (synth 6.4, grain spectral 21.1, OLA 0.8, FIR 2.0, post 0.8), `render()` end to end 0.48 s; the reference took 244 s on one core of the build container (`tests/golden/c4_full.npz`).\n")
 w("## 2. ncu launch list of one step, 512-render slab (`launches_r01i_512renders.csv`)\n")
 w("`ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,... --clock-control none` around the timed step of `bench.py --renders 512`.\n")
