@@ -79,7 +79,7 @@ extern "C" int MS_API(ms_synth_tilt_finish)(const ms_synth_evt* evts, int n, rea
     return 0;
 }
 extern "C" int MS_API(ms_synth_dust)(const ms_synth_evt* evts, int n, const int32_t* dpos, const real* dval, real* pool, void* stream) {
-    MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthDustK>(mk_dim(64, (unsigned)_yc), 256, DUST_KER_MAX * sizeof(real), (ms_stream_t)stream, evts + _y0, (const int*)dpos, dval, pool)) return -1; })
+    MS_FOR_Y_CHUNKS(n, { if (ms_launch<SynthDustK>(mk_dim(DUST_CTAS, (unsigned)_yc), 256, DUST_KER_MAX * sizeof(real) + DUST_STAGE_MAX * (sizeof(real) + sizeof(int)), (ms_stream_t)stream, evts + _y0, (const int*)dpos, dval, pool)) return -1; })
     return 0;
 }
 extern "C" int MS_API(ms_adsr_tables)(const ms_ola_render* reps, int n_tables, int max_out_n, real* envpool, void* stream) {

@@ -276,6 +276,13 @@ MS_DEV void synth_tilt_finish_body(const SynthEvt* MS_RESTRICT evts, real* MS_RE
 // ker is tabulated once per CTA in shared memory (K <= 0.01 n entries), so an output costs one table lookup
 // per impulse in reach instead of one exp().  Events longer than the table fall back to exp().
 #define DUST_KER_MAX 4096
+#define DUST_STAGE_MAX 1024
+#define DUST_CTAS 16
+// grid = (DUST_CTAS, events): CTA bx owns the contiguous outputs [bx * span, (bx + 1) * span), span = ceil(n / DUST_CTAS)
+// (16 CTAs per event: every CTA tabulates the kernel once, so fewer, longer chunks amortise those K exponentials).  The impulses
+// that can reach them (positions in (first + ctr - K, last + ctr]) are found with two binary searches and staged in
+// shared memory together with the kernel table, so an output costs a short search in shared memory plus one
+// multiply-add per impulse in reach.  (More than DUST_STAGE_MAX impulses in reach: read them from global memory.)
 MS_DEV void synth_dust_body(const SynthEvt* MS_RESTRICT evts, const int* MS_RESTRICT dpos, const real* MS_RESTRICT dval,
                             real* MS_RESTRICT pool, const Ctx& c) {
     const SynthEvt E = evts[c.by];
@@ -285,21 +292,43 @@ MS_DEV void synth_dust_body(const SynthEvt* MS_RESTRICT evts, const int* MS_REST
     real* out = pool + E.out;
     const int K = E.ker_len, ctr = (K - 1) / 2;
     const real rate = (real)6.0 / (real)(K - 1);
+    const int span = (E.n + DUST_CTAS - 1) / DUST_CTAS;
+    const int j0 = c.bx * span, j1 = (j0 + span) < E.n ? (j0 + span) : E.n;
+    if (j0 >= E.n) return;
     real* ker = (real*)c.smem;
+    real* sval = ker + DUST_KER_MAX;
+    int* spos = (int*)(sval + DUST_STAGE_MAX);
     const int tab = K <= DUST_KER_MAX;
-    if (tab) {
-        for (int d = c.tid; d < K; d += c.nthr) ker[d] = r_exp(-rate * (real)d);
-        c.sync();
-    }
-    for (int j = c.bx * c.nthr + c.tid; j < E.n; j += c.nthr * 64) {
+    if (tab) for (int d = c.tid; d < K; d += c.nthr) ker[d] = r_exp(-rate * (real)d);
+    // impulses with  j0 + ctr - K < p <= j1 - 1 + ctr
+    int lo = 0, hi_i = E.dust_count;
+    while (lo < hi_i) { const int mid = (lo + hi_i) >> 1; if (__ldg(&pos[mid]) > j0 + ctr - K) hi_i = mid; else lo = mid + 1; }
+    const int q0 = lo;
+    lo = q0; hi_i = E.dust_count;
+    while (lo < hi_i) { const int mid = (lo + hi_i) >> 1; if (__ldg(&pos[mid]) > j1 - 1 + ctr) hi_i = mid; else lo = mid + 1; }
+    const int q1 = lo, cnt = q1 - q0;
+    const int staged = cnt <= DUST_STAGE_MAX;
+    if (staged) for (int q = c.tid; q < cnt; q += c.nthr) { spos[q] = __ldg(&pos[q0 + q]); sval[q] = __ldg(&val[q0 + q]); }
+    c.sync();
+    for (int j = j0 + c.tid; j < j1; j += c.nthr) {
         const int hi = j + ctr;            // impulses p with hi-K < p <= hi contribute ker[hi-p]
-        int lo_i = 0, hi_i = E.dust_count; // first index with pos > hi - K
-        while (lo_i < hi_i) { const int mid = (lo_i + hi_i) >> 1; if (__ldg(&pos[mid]) > hi - K) hi_i = mid; else lo_i = mid + 1; }
         real acc = (real)0.;
-        for (int q = lo_i; q < E.dust_count; ++q) {
-            const int p = __ldg(&pos[q]);
-            if (p > hi) break;
-            acc += __ldg(&val[q]) * (tab ? ker[hi - p] : r_exp(-rate * (real)(hi - p)));
+        if (staged) {
+            int a = 0, b = cnt;            // first staged impulse with pos > hi - K
+            while (a < b) { const int mid = (a + b) >> 1; if (spos[mid] > hi - K) b = mid; else a = mid + 1; }
+            for (int q = a; q < cnt; ++q) {
+                const int p = spos[q];
+                if (p > hi) break;
+                acc += sval[q] * (tab ? ker[hi - p] : r_exp(-rate * (real)(hi - p)));
+            }
+        } else {
+            int a = q0, b = q1;
+            while (a < b) { const int mid = (a + b) >> 1; if (__ldg(&pos[mid]) > hi - K) b = mid; else a = mid + 1; }
+            for (int q = a; q < q1; ++q) {
+                const int p = __ldg(&pos[q]);
+                if (p > hi) break;
+                acc += __ldg(&val[q]) * (tab ? ker[hi - p] : r_exp(-rate * (real)(hi - p)));
+            }
         }
         out[j] = acc * fade_gain(j, E.n, E.fade, E.inv_fade);
     }
