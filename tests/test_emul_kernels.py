@@ -107,6 +107,9 @@ def test_pooled_planning_matches_in_process(emul, monkeypatch):
     ps[3]["base_sr"], ps[3]["out_dur_s"] = 44100, 0.05003          # odd length -> FFT rotation path
     one = engine.render_batch(ps, device=emul)
     streamed = engine.render_batch(ps, device=emul, chunk=5, workers=3, piece=2)     # slices of 5 = pieces of 2+2+1, 2
+    ramped = engine.render_batch(ps, device=emul, chunk=[1, 2, 3], workers=2, piece=2)  # slice schedule 1, 2, 3, 3: short first slices
+    for a, c in zip(one, ramped):
+        assert a.shape == c.shape and np.max(np.abs(a.astype(np.float64) - c.astype(np.float64))) < 1e-6
     monkeypatch.setenv("MS_PLAN_MIN_BATCH", "2")
     monkeypatch.setenv("MS_PLAN_WORKERS", "3")
     br = engine.BatchRenderer(ps, device=emul)                                       # plan_and_pack through the pool

@@ -84,7 +84,7 @@ def test_streamed_batch_equals_one_launch_sequence(cuda_dev):
     import torch
     ps = [configs.c5_params(i) for i in range(200, 296)]
     host = torch.empty(2 * 96 * 96000, dtype=torch.float32).pin_memory()
-    outs = engine.render_batch(ps, device=cuda_dev, host_out=host, chunk=40, piece=16, depth=2)
+    outs = engine.render_batch(ps, device=cuda_dev, host_out=host, chunk=[8, 16, 40], piece=16, depth=2)      # ramped slices
     br = engine.BatchRenderer(ps, device=cuda_dev)
     br.run()
     for r in (0, 39, 40, 79, 80, 95):
