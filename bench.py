@@ -67,24 +67,56 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.polled, self.alive, self.mx = None, [], False, 0.0
 
     def start(self):
+        """NVML polled every 5 ms from a thread (a 10 ms step at N=8 still gets samples); nvidia-smi -lms as fallback."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(int(self.index))
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.alive = True
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = (("hw_slowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))
+        while self.alive:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.polled.append((time.time(), sm, [name for name, b in bits if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
+        self.alive = False
         if self.proc:
             self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, reasons = [], self.mx, set()
+        for t, mhz, names in self.polled:
+            if t0 <= t <= t1:
+                sm.append(mhz)
+                reasons.update(names)
         for t, line in self.rows:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
@@ -99,7 +131,7 @@ class ClockSampler:
             except ValueError:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml 5 ms poll" if self.nvml else "nvidia-smi -lms 20"}
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
