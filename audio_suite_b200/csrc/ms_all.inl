@@ -17,6 +17,7 @@ MS_DEV cpx c_zero() { return mk((real)0, (real)0); }
 #include "ms_fft_api.inl"
 #include "ms_synth.cuh"
 #include "ms_time.cuh"
+#include "ms_fir_fused.cuh"
 #include "ms_stage_api.inl"
 }  // namespace MS_NS
 #undef MS_API

@@ -1,0 +1,310 @@
+// ms_fir_fused.cuh -- the FIR stage (early_reflection_cloud + convolve_ir_short, main_v2.py:409-421, 438-445) for
+// 65536-point overlap-save blocks, as three phases over ONE 65536-point complex scratch block per unit:
+//
+//   P1  columns:  x (two real blocks as re / im) -> 256-point FFTs over n1 -> twiddle W^(k1 n2)        -> S[n2][k1]
+//   P2  rows:     S[.][k1] -> FFT over n2 -> * H[k1][k2] -> swap -> FFT -> twiddle W^(k1 n2') -> back to S[n2'][k1]
+//                 with H[k1][k2] = IRspec[k1][k2] * (1 + E[k1 + 256 k2]) composed IN the tile: the reflection taps are
+//                 folded modulo 256 with the modulation W^(off k1) and one more 256-point FFT gives row k1 of E
+//   P3  columns:  S[n2][.] -> FFT over k1 -> valid outputs of both blocks (exact zeros outside the live range)
+//
+// Every 256-point FFT is WARP-LOCAL: a lane holds x[lane + 32 q] (q < 8) in registers, radix 8 . 8 . 4, two
+// exchanges through the warp's own shared-memory row with __syncwarp only; the first pass reads its input and the
+// last pass leaves its output in registers in the SAME layout (index lane + 32 m), so two transforms chain without
+// touching shared memory and global loads / stores on the contiguous side go straight from / to registers
+// (512 contiguous bytes per warp instruction).  The strided side of each phase goes through a transposing tile in
+// shared memory (8 vectors x 256) so that global accesses are 64- / 128-byte segments.
+//
+// On the GPU the three phases run inside ONE persistent kernel launched as thread-block clusters: the CTAs of a
+// cluster share a unit, split the 32 tiles of each phase and meet at the hardware cluster barrier between phases;
+// the scratch block is 1 MB per CLUSTER (not per unit), is rewritten for every unit and therefore lives in the
+// 126 MB L2 -- x is read from HBM once and y written once.  The same phase bodies are also launchable one phase per
+// kernel (scratch per unit): that is what the CPU block emulator runs, and the A/B baseline on the GPU.
+
+#ifdef MS_HOST_EMUL
+#define MS_LDCG(p) (*(p))
+#else
+#define MS_LDCG(p) __ldcg(p)
+#endif
+
+#define FF_N 256                       // both factors of the 65536-point block
+#define FF_TILE 8                      // vectors (columns or rows) per tile = warps per CTA
+#define FF_NTHR (32 * FF_TILE)
+#define FF_TILES (FF_N / FF_TILE)      // tiles per phase
+#define FF_RS ((ms_pad(FF_N) + 1) | 1) // row stride of a tile in shared memory (odd: conflict-free transposes)
+
+struct FirUnit {
+    const real* in; real* out;        // the render's mono input / output planes
+    const cpx* filt;                  // IR spectrum / B in [k1][k2] layout
+    long long p0_a, p0_b;             // first input sample of block a / b (may be negative)
+    int has_b, ols_n, ols_skip;       // ols_skip = taps - 1: leading outputs of a block that are discarded
+    int live_lo, live_hi;             // outputs outside [live_lo, live_hi) are exactly zero (input support + taps)
+    int tap_res;                      // >= 0: offset of this render's 257 residue pointers; < 0: no reflection taps
+    int _pad0, _pad1;
+};
+struct FirTables {
+    const cpx* tw;                    // w_256^i
+    const cpx* twM_hi; const cpx* twM_lo;   // W_65536^(1024 i), W_65536^i (i < 1024)
+    const int* res_ptr;               // per render with taps: 257 offsets into the residue-sorted tap arrays
+    const int* tap_off; const real* tap_gain;     // residue-sorted taps
+};
+
+// ---- warp-local 256-point forward FFT ---------------------------------------------------------------------
+// in: v[q] = x[lane + 32 q];  out: v[m] = X[lane + 32 m].  sw: the warp's shared-memory row (FF_RS entries).
+// The caller guarantees that nobody else touches sw and that the warp is converged.
+MS_DEV void warp_fft256(cpx* v, cpx* sw, const cpx* MS_RESTRICT tw, int lane, const Ctx& c) {
+    Bfly<8>::run(v);                                        // pass 1: Ns = 1, no twiddles; output q of butterfly j -> 8 j + q
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sw[ms_pad(lane * 8 + q)] = v[q];
+    c.syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
+    c.syncwarp();
+    {                                                       // pass 2: Ns = 8, twiddle w_64^(q k) = w_256^(4 q k)
+        const int k = lane & 7;
+        const cpx w1 = __ldg(&tw[4 * k]), w2 = __ldg(&tw[8 * k]), w4 = __ldg(&tw[16 * k]);
+        const cpx w3 = c_mul(w1, w2);
+        v[1] = c_mul(v[1], w1); v[2] = c_mul(v[2], w2); v[3] = c_mul(v[3], w3); v[4] = c_mul(v[4], w4);
+        v[5] = c_mul(v[5], c_mul(w4, w1)); v[6] = c_mul(v[6], c_mul(w4, w2)); v[7] = c_mul(v[7], c_mul(w4, w3));
+        Bfly<8>::run(v);
+        const int base = (lane - k) * 8 + k;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sw[ms_pad(base + 8 * q)] = v[q];
+    }
+    c.syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
+    c.syncwarp();
+    {                                                       // pass 3: Ns = 64, radix 4; butterflies j = lane (even m) and lane + 32 (odd m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = lane + 32 * h;
+            const cpx w1 = __ldg(&tw[j]), w2 = __ldg(&tw[2 * j]);
+            const cpx w3 = c_mul(w1, w2);
+            cpx a[4] = {v[h], c_mul(v[2 + h], w1), c_mul(v[4 + h], w2), c_mul(v[6 + h], w3)};
+            Bfly<4>::run(a);
+            v[h] = a[0]; v[2 + h] = a[1]; v[4 + h] = a[2]; v[6 + h] = a[3];      // X[j + 64 q] -> m = 2 q + h
+        }
+    }
+}
+// v[m] *= W_65536^(a (lane + 32 m)):  base W^(a lane), step W^(32 a), powers by a depth-4 product tree
+MS_DEV void twiddle_row(cpx* v, const FirTables& T, int a, int lane) {
+    const cpx base = tw2level(T.twM_hi, T.twM_lo, (unsigned)(a * lane) & 65535u);
+    const cpx st1 = tw2level(T.twM_hi, T.twM_lo, (unsigned)(32 * a) & 65535u);
+    const cpx st2 = c_mul(st1, st1);
+    cpx t0 = base, t1 = c_mul(base, st1);
+    v[0] = c_mul(v[0], t0); v[1] = c_mul(v[1], t1);
+#pragma unroll
+    for (int m = 2; m < 8; m += 2) {
+        t0 = c_mul(t0, st2); t1 = c_mul(t1, st2);
+        v[m] = c_mul(v[m], t0); v[m + 1] = c_mul(v[m + 1], t1);
+    }
+}
+
+// ---- phase 1: forward columns -----------------------------------------------------------------------------
+MS_DEV void fir_p1_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, const Ctx& c) {
+    cpx* s = (cpx*)c.smem;
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+    const int c0 = tile * FF_TILE;
+#pragma unroll
+    for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
+        const int e = c.tid + FF_NTHR * i, n1 = e >> 3, cc = e & 7;
+        const long long idx = (long long)n1 * FF_N + c0 + cc;
+        const long long pa = U.p0_a + idx, pb = U.p0_b + idx;
+        const real a = (pa >= 0 && pa < U.ols_n) ? __ldg(&U.in[pa]) : (real)0.;
+        const real b = (U.has_b && pb >= 0 && pb < U.ols_n) ? __ldg(&U.in[pb]) : (real)0.;
+        s[cc * FF_RS + ms_pad(n1)] = mk(a, b);
+    }
+    c.sync();
+    cpx v[8];
+    cpx* sw = s + warp * FF_RS;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
+    c.syncwarp();
+    warp_fft256(v, sw, T.tw, lane, c);
+    const int n2 = c0 + warp;
+    twiddle_row(v, T, n2, lane);                            // W^(k1 n2), k1 = lane + 32 m
+    cpx* dst = S + (size_t)n2 * FF_N + lane;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) dst[32 * m] = v[m];
+    c.sync();                                               // the next tile refills the transposing buffer
+}
+
+// ---- phase 2: rows (forward, filter, inverse) ---------------------------------------------------------------
+MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, const Ctx& c) {
+    cpx* sB = (cpx*)c.smem;                                 // transposing tile + exchange rows
+    cpx* sA = sB + FF_TILE * FF_RS;                         // filter rows H[k1][.]
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+    const int r0 = tile * FF_TILE, k1 = r0 + warp;
+    const int taps = U.tap_res >= 0;
+    cpx v[8];
+    if (taps) {
+        // E[k1 + 256 k2] = FFT_256 over r of F[r] = sum over taps with off = r (mod 256) of g W_65536^(off k1).
+        // Thread r owns residue r for the eight rows of the tile: W^(off k1) steps by W^off from one row to the next.
+        // (four rows at a time: eight complex accumulators next to the twiddles do not fit the register budget)
+        const int* rp = T.res_ptr + U.tap_res;
+        const int r = c.tid;
+        const int t_begin = __ldg(&rp[r]), t_end = __ldg(&rp[r + 1]);
+#pragma unroll 1
+        for (int half = 0; half < FF_TILE; half += 4) {
+            cpx acc[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) acc[w] = c_zero();
+            for (int t = t_begin; t < t_end; ++t) {
+                const unsigned off = (unsigned)__ldg(&T.tap_off[t]);
+                const real g = __ldg(&T.tap_gain[t]);
+                cpx tw = tw2level(T.twM_hi, T.twM_lo, (off * (unsigned)(r0 + half)) & 65535u);
+                const cpx st = tw2level(T.twM_hi, T.twM_lo, off & 65535u);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    acc[w] = mk(acc[w].x + g * tw.x, acc[w].y + g * tw.y);
+                    if (w < 3) tw = c_mul(tw, st);
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w) sA[(half + w) * FF_RS + ms_pad(r)] = acc[w];
+        }
+        c.sync();
+        cpx* swA = sA + warp * FF_RS;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = swA[ms_pad(lane + 32 * q)];
+        c.syncwarp();
+        warp_fft256(v, swA, T.tw, lane, c);
+        const cpx* f = U.filt + (size_t)k1 * FF_N + lane;
+        c.syncwarp();
+#pragma unroll
+        for (int m = 0; m < 8; ++m) swA[ms_pad(lane + 32 * m)] = c_mul(__ldg(&f[32 * m]), mk(v[m].x + (real)1.0, v[m].y));
+        c.syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
+        const int e = c.tid + FF_NTHR * i, n2 = e >> 3, rr = e & 7;
+        sB[rr * FF_RS + ms_pad(n2)] = MS_LDCG(&S[(size_t)n2 * FF_N + r0 + rr]);
+    }
+    c.sync();
+    cpx* sw = sB + warp * FF_RS;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
+    c.syncwarp();
+    warp_fft256(v, sw, T.tw, lane, c);                      // v[m] = Z[k1][k2 = lane + 32 m]
+    if (taps) {
+        const cpx* swA = sA + warp * FF_RS;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = c_swap(c_mul(v[m], swA[ms_pad(lane + 32 * m)]));
+    } else {
+        const cpx* f = U.filt + (size_t)k1 * FF_N + lane;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = c_swap(c_mul(v[m], __ldg(&f[32 * m])));
+    }
+    c.syncwarp();
+    warp_fft256(v, sw, T.tw, lane, c);                      // inverse over k2 (swapped domain): index n2' = lane + 32 m
+    twiddle_row(v, T, k1, lane);
+    c.syncwarp();
+#pragma unroll
+    for (int m = 0; m < 8; ++m) sw[ms_pad(lane + 32 * m)] = v[m];
+    c.sync();
+#pragma unroll
+    for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
+        const int e = c.tid + FF_NTHR * i, n2 = e >> 3, rr = e & 7;
+        S[(size_t)n2 * FF_N + r0 + rr] = sB[rr * FF_RS + ms_pad(n2)];
+    }
+    c.sync();
+}
+
+// ---- phase 3: inverse columns, valid outputs ------------------------------------------------------------------
+MS_DEV void fir_p3_tile(const FirUnit& U, const FirTables& T, const cpx* S, int tile, const Ctx& c) {
+    cpx* s = (cpx*)c.smem;
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+    const int c0 = tile * FF_TILE;
+    cpx v[8];
+    const cpx* src = S + (size_t)(c0 + warp) * FF_N + lane;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = MS_LDCG(&src[32 * q]);
+    cpx* sw = s + warp * FF_RS;
+    warp_fft256(v, sw, T.tw, lane, c);                      // v[m]: sample n1 = lane + 32 m of column c0 + warp (swapped domain)
+    c.syncwarp();
+#pragma unroll
+    for (int m = 0; m < 8; ++m) sw[ms_pad(lane + 32 * m)] = v[m];
+    c.sync();
+#pragma unroll
+    for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
+        const int e = c.tid + FF_NTHR * i, n1 = e >> 3, cc = e & 7;
+        const int idx = n1 * FF_N + c0 + cc;
+        if (idx < U.ols_skip) continue;
+        const cpx val = s[cc * FF_RS + ms_pad(n1)];
+        const long long qa = U.p0_a + idx, qb = U.p0_b + idx;
+        if (qa < U.ols_n) U.out[qa] = (qa >= U.live_lo && qa < U.live_hi) ? val.y : (real)0;       // un-swap: re of the inverse
+        if (U.has_b && qb < U.ols_n) U.out[qb] = (qb >= U.live_lo && qb < U.live_hi) ? val.x : (real)0;
+    }
+    c.sync();
+}
+
+// ---- one phase per launch: grid = (FF_TILES, units); scratch block u belongs to unit u -----------------------------
+MS_DEV void fir_phase_body(int phase, const FirUnit* MS_RESTRICT units, FirTables T, cpx* scratch, const Ctx& c) {
+    const FirUnit& U = units[c.by];
+    cpx* S = scratch + (size_t)c.by * (FF_N * FF_N);
+    if (phase == 1) fir_p1_tile(U, T, S, c.bx, c);
+    else if (phase == 2) fir_p2_tile(U, T, S, c.bx, c);
+    else fir_p3_tile(U, T, S, c.bx, c);
+}
+
+// ---- reflection taps sorted by residue (off mod 256), once per plan ------------------------------------------------
+// One CTA of 256 threads per render with taps: thread r counts and then copies the taps of residue r in tap order
+// (deterministic, no atomics); res_ptr gets the 257 segment boundaries (absolute positions in the sorted arrays).
+struct FirSortJob { int tap_begin, tap_end, res_at, _pad; };
+MS_DEV void fir_sort_taps_body(const FirSortJob* MS_RESTRICT jobs, const int* MS_RESTRICT tap_off, const real* MS_RESTRICT tap_gain,
+                               int* res_ptr, int* soff, real* sgain, const Ctx& c) {
+    const FirSortJob J = jobs[c.by];
+    int* cnt = (int*)c.smem;                                // 257
+    const int r = c.tid;
+    int n = 0;
+    for (int t = J.tap_begin; t < J.tap_end; ++t) {
+        const int off = __ldg(&tap_off[t]);
+        if (off >= 0 && off < FF_N * FF_N && (off & 255) == r) ++n;
+    }
+    cnt[r] = n;
+    c.sync();
+    if (r == 0) {
+        int acc = J.tap_begin;
+        for (int i = 0; i < 256; ++i) { const int k = cnt[i]; cnt[i] = acc; acc += k; }
+        cnt[256] = acc;
+    }
+    c.sync();
+    int at = cnt[r];
+    res_ptr[J.res_at + r] = at;
+    if (r == 0) res_ptr[J.res_at + 256] = cnt[256];
+    for (int t = J.tap_begin; t < J.tap_end; ++t) {
+        const int off = __ldg(&tap_off[t]);
+        if (off >= 0 && off < FF_N * FF_N && (off & 255) == r) { soff[at] = off; sgain[at] = __ldg(&tap_gain[t]); ++at; }
+    }
+}
+
+#ifndef MS_HOST_EMUL
+// ---- persistent cluster kernel ------------------------------------------------------------------------------------------
+// grid = clusters * CL CTAs of FF_NTHR threads; cluster k takes units k, k + clusters, ...; its CTAs split the 32 tiles
+// of each phase (tile = rank, rank + CL, ...: the SAME tiles in P1 and P3, so a CTA only overwrites scratch columns it
+// has itself finished reading) and meet at the cluster barrier between phases.  Scratch: 65536 complex per cluster.
+MS_DEV void ff_cluster_sync() {
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+MS_DEV unsigned ff_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+MS_DEV unsigned ff_cluster_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+MS_DEV unsigned ff_nclusters() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+template <int CL>
+__global__ void __launch_bounds__(FF_NTHR, 3) fir_cluster_kernel(const FirUnit* __restrict__ units, int n_units, FirTables T, cpx* scratch) {
+    extern __shared__ float4 ms_dyn_smem[];
+    Ctx c;
+    c.tid = threadIdx.x; c.nthr = blockDim.x; c.bx = blockIdx.x; c.by = 0;
+    c.smem = (char*)ms_dyn_smem;
+    const int rank = (int)ff_cluster_rank(), cid = (int)ff_cluster_id(), ncl = (int)ff_nclusters();
+    cpx* S = scratch + (size_t)cid * (FF_N * FF_N);
+    for (int u = cid; u < n_units; u += ncl) {
+        const FirUnit& U = units[u];
+        for (int t = rank; t < FF_TILES; t += CL) fir_p1_tile(U, T, S, t, c);
+        ff_cluster_sync();
+        for (int t = rank; t < FF_TILES; t += CL) fir_p2_tile(U, T, S, t, c);
+        ff_cluster_sync();
+        for (int t = rank; t < FF_TILES; t += CL) fir_p3_tile(U, T, S, t, c);
+    }
+}
+#endif

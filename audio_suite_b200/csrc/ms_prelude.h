@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <utility>
 #include <string.h>
+#include <stdlib.h>
 #ifdef MS_HOST_EMUL
 #define MS_POPC(x) __builtin_popcount(x)
 #else

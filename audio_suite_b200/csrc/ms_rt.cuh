@@ -33,6 +33,9 @@
       int tid, nthr, bx, by;
       char* smem;
       void sync() const { msemu::yield_barrier(); }
+      // warp-level barrier: the emulator has no warps, so this is a block barrier.  That is only equivalent when every
+      // warp of the block executes the same number of them between two block barriers -- true for every kernel here.
+      void syncwarp() const { msemu::yield_barrier(); }
   };
 #else
   #include <cuda_runtime.h>
@@ -44,6 +47,7 @@
       int tid, nthr, bx, by;
       char* smem;
       __device__ __forceinline__ void sync() const { __syncthreads(); }
+      __device__ __forceinline__ void syncwarp() const { __syncwarp(); }
   };
 #endif
 

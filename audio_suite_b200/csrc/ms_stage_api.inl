@@ -172,51 +172,89 @@ extern "C" int MS_API(ms_roll)(const real* src, real* dst, int n, int shift, voi
 }
 
 // ---- FIR by overlap-save ----------------------------------------------------------------------------------
-static int ols_block_len(int h_len) {
+static int ols_block_len(int h_len, int out_n) {
     if (h_len <= 3072) return 8192;
     int B = 32768;
     while (B < 4 * h_len && B < (1 << 20)) B <<= 1;
+    // 65536-point blocks have the fused kernel (ms_fir_fused.cuh) and waste less on overlap; 32768 stays only where
+    // the whole output fits in one transform of two blocks
+    if (B == 32768 && (out_n + (B - h_len)) / (B - h_len + 1) > 2) B = 65536;
     return B;
 }
-// Plan: (1) at create time, the spectrum of every distinct impulse response (FFT_B(ir)/B, scrambled [k1][k2]
-// layout); (2) per run and per render with reflection taps: scatter the taps into a dense vector, transform it
-// and compose the render's filter spectrum IRspec * (1 + FFT(e)); (3) overlap-save with two blocks per transform.
+// How the 65536-point blocks run (ms_fir_fused.cuh):  0 = legacy five-kernel sequence through the spectral engine,
+// 1 = fused phases, one launch per phase (scratch per unit), 4 / 8 / 16 = fused phases inside one persistent kernel of
+// thread-block clusters of that many CTAs (scratch per cluster, L2-resident).  Development switch: MS_FIR_MODE.
+static int fir_mode() {
+#ifdef MS_HOST_EMUL
+    const char* e = getenv("MS_FIR_MODE");
+    return (e && atoi(e) == 0) ? 0 : 1;                     // the block emulator has no clusters
+#else
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("MS_FIR_MODE"); mode = e ? atoi(e) : 8; if (mode != 0 && mode != 1 && mode != 4 && mode != 16) mode = 8; }
+    return mode;
+#endif
+}
+struct FirP1K { static constexpr int MAXT = FF_NTHR; static constexpr int MINB = 4;
+    static MS_DEV void run(const FirUnit* u, FirTables T, cpx* s, const Ctx& c) { fir_phase_body(1, u, T, s, c); } };
+struct FirP2K { static constexpr int MAXT = FF_NTHR; static constexpr int MINB = 3;
+    static MS_DEV void run(const FirUnit* u, FirTables T, cpx* s, const Ctx& c) { fir_phase_body(2, u, T, s, c); } };
+struct FirP3K { static constexpr int MAXT = FF_NTHR; static constexpr int MINB = 4;
+    static MS_DEV void run(const FirUnit* u, FirTables T, cpx* s, const Ctx& c) { fir_phase_body(3, u, T, s, c); } };
+struct FirSortK { static constexpr int MAXT = 256; static constexpr int MINB = 1;
+    static MS_DEV void run(const FirSortJob* j, const int* to, const real* tg, int* rp, int* so, real* sg, const Ctx& c) { fir_sort_taps_body(j, to, tg, rp, so, sg, c); } };
+static const size_t FF_SMEM1 = sizeof(cpx) * (size_t)FF_TILE * FF_RS;       // one transposing tile
+static const size_t FF_SMEM2 = 2 * FF_SMEM1;                                  // + the filter rows of phase 2
+
+// Plan: (1) at create time, the spectrum of every distinct impulse response (FFT_B(ir)/B, [k1][k2] layout) and the
+// reflection taps of the fused renders sorted by residue; (2) legacy renders, per run: scatter the taps into a dense
+// vector, transform it and compose the render's filter spectrum IRspec * (1 + FFT(e)); (3) overlap-save with two blocks
+// per transform: fused units (65536-point blocks) or legacy jobs.
 struct FirPlan {
     std::vector<FftJob> ijobs, hjobs, cjobs;
     FftJob *ijobs_dev, *hjobs_dev, *cjobs_dev;
     std::vector<ErJob> ejobs; ErJob* ejobs_dev;
     const int* tap_off; const real* tap_gain; real* ebase;
+    std::vector<FirUnit> units; FirUnit* units_dev;
+    FirTables ft; cpx* scratch; int n_scratch;           // n_scratch: 65536-point scratch blocks available
 };
 struct FirLayout {
     size_t ijobs_off, hjobs_off, cjobs_off, ejobs_off, ebuf_off, ispec_off, hspec_off, work_off, total;
-    std::vector<size_t> hspec_at, e_at; std::vector<int> B, ispec_of; std::vector<std::pair<long long, std::pair<int, int>>> irs;
-    int ncj, nh;
+    size_t units_off, sort_off, res_off, soff_off, sgain_off, scratch_off;
+    std::vector<size_t> hspec_at, e_at; std::vector<int> B, ispec_of, fused; std::vector<std::pair<long long, std::pair<int, int>>> irs;
+    int ncj, nh, n_units, n_sort, n_scratch, n_taps;
 };
+static int fir_max_clusters(int cl) { return std::max(1, (148 * 3) / cl); }      // resident clusters at three CTAs per SM
 
 static int fir_layout(const ms_fir_render* r, int n, FirLayout& L) {
-    L.hspec_at.assign(n, 0); L.e_at.assign(n, 0); L.B.resize(n); L.ispec_of.resize(n); L.irs.clear();
-    size_t hs = 0, wk = 0, is = 0, eb = 0; int ncj = 0, nh = 0;
+    L.hspec_at.assign(n, 0); L.e_at.assign(n, 0); L.B.resize(n); L.ispec_of.resize(n); L.fused.assign(n, 0); L.irs.clear();
+    size_t hs = 0, wk = 0, is = 0, eb = 0; int ncj = 0, nh = 0, nu = 0, ns = 0, nt = 0;
+    const int mode = fir_mode();
     for (int i = 0; i < n; ++i) {
-        const int B = ols_block_len(r[i].h_len);
+        const int B = ols_block_len(r[i].h_len, r[i].out_n);
         if (r[i].h_len < 1 || r[i].h_len > B / 2 || r[i].ir_len < 1) MS_FAIL("fir: %d taps unsupported", r[i].h_len);
         L.B[i] = B;
+        L.fused[i] = (mode != 0 && B == FF_N * FF_N) ? 1 : 0;
         const std::pair<long long, std::pair<int, int>> key(r[i].ir, std::make_pair(r[i].ir_len, B));
         int found = -1;
         for (size_t k = 0; k < L.irs.size(); ++k) if (L.irs[k] == key) { found = (int)k; break; }
         if (found < 0) { found = (int)L.irs.size(); L.irs.push_back(key); is += (size_t)B; }
         L.ispec_of[i] = found;
-        if (r[i].tap_end > r[i].tap_begin) {
+        const bool has_taps = r[i].tap_end > r[i].tap_begin;
+        nt = std::max(nt, r[i].tap_end);
+        const int hop = B - r[i].h_len + 1;
+        const int nblk = (r[i].out_n + hop - 1) / hop;
+        const int nj = (nblk + 1) / 2;
+        if (L.fused[i]) { nu += nj; if (has_taps) ++ns; continue; }
+        if (has_taps) {
             L.hspec_at[i] = hs; hs += (size_t)B;
             L.e_at[i] = eb; eb += (size_t)(r[i].h_len - r[i].ir_len + 1);
             ++nh;
         }
-        const int hop = B - r[i].h_len + 1;
-        const int nblk = (r[i].out_n + hop - 1) / hop;
-        const int nj = (nblk + 1) / 2;
         ncj += nj;
         if (B > MS_SMALL_MAX) wk += (size_t)B * (size_t)nj;
     }
-    L.ncj = ncj; L.nh = nh;
+    L.ncj = ncj; L.nh = nh; L.n_units = nu; L.n_sort = ns; L.n_taps = nt;
+    L.n_scratch = nu == 0 ? 0 : (mode == 1 ? nu : std::min(nu, fir_max_clusters(mode)));
     L.ijobs_off = 0;
     L.hjobs_off = ms_align256(sizeof(FftJob) * L.irs.size());
     L.cjobs_off = L.hjobs_off + ms_align256(sizeof(FftJob) * (size_t)nh);
@@ -225,7 +263,13 @@ static int fir_layout(const ms_fir_render* r, int n, FirLayout& L) {
     L.ispec_off = L.ebuf_off + ms_align256(sizeof(real) * eb);
     L.hspec_off = L.ispec_off + ms_align256(sizeof(cpx) * is);
     L.work_off = L.hspec_off + ms_align256(sizeof(cpx) * hs);
-    L.total = L.work_off + ms_align256(sizeof(cpx) * wk);
+    L.units_off = L.work_off + ms_align256(sizeof(cpx) * wk);
+    L.sort_off = L.units_off + ms_align256(sizeof(FirUnit) * (size_t)nu);
+    L.res_off = L.sort_off + ms_align256(sizeof(FirSortJob) * (size_t)ns);
+    L.soff_off = L.res_off + ms_align256(sizeof(int) * 257 * (size_t)ns);
+    L.sgain_off = L.soff_off + ms_align256(sizeof(int) * (size_t)(ns ? nt : 0));
+    L.scratch_off = L.sgain_off + ms_align256(sizeof(real) * (size_t)(ns ? nt : 0));
+    L.total = L.scratch_off + ms_align256(sizeof(cpx) * (size_t)L.n_scratch * (FF_N * FF_N));
     return 0;
 }
 extern "C" size_t MS_API(ms_fir_workspace_bytes)(const ms_fir_render* r, int n) {
@@ -239,7 +283,7 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
     *handle = nullptr;
     ms_stream_t st = (ms_stream_t)stream;
     FirPlan* P = new FirPlan();
-    P->ijobs_dev = P->hjobs_dev = P->cjobs_dev = nullptr; P->ejobs_dev = nullptr;
+    P->ijobs_dev = P->hjobs_dev = P->cjobs_dev = nullptr; P->ejobs_dev = nullptr; P->units_dev = nullptr; P->scratch = nullptr; P->n_scratch = 0;
     if (n <= 0) { *handle = P; return 0; }
     FirLayout L;
     if (fir_layout(r, n, L)) { delete P; return -1; }
@@ -266,11 +310,39 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
     for (int i = 0; i < n; ++i) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (L.B[a] > MS_SMALL_MAX) < (L.B[b] > MS_SMALL_MAX); });
     size_t wk = 0;
+    std::vector<FirSortJob> sorts;
     for (int oi = 0; oi < n; ++oi) {
         const int i = order[oi];
         FftJob G; memset(&G, 0, sizeof G);
         if (FftEngine::get().prepare(G, L.B[i], st)) { delete P; return -1; }
         const cpx* filt = ispec + ispec_at[L.ispec_of[i]];
+        const int hop = L.B[i] - r[i].h_len + 1;
+        const int nblk = (r[i].out_n + hop - 1) / hop;
+        const int nj = (nblk + 1) / 2;
+        const int live_hi = (int)std::min<long long>(r[i].out_n, (long long)r[i].x_end + r[i].h_len - 1);
+        if (L.fused[i]) {
+            if (G.F1 != FF_N || G.F2 != FF_N) { delete P; MS_FAIL("fir: internal: 65536 is not planned as 256 x 256"); }
+            P->ft.tw = G.tw1; P->ft.twM_hi = G.twM_hi; P->ft.twM_lo = G.twM_lo;
+            int res_at = -1;
+            if (r[i].tap_end > r[i].tap_begin) {
+                FirSortJob sj; sj.tap_begin = r[i].tap_begin; sj.tap_end = r[i].tap_end; sj.res_at = 257 * (int)sorts.size(); sj._pad = 0;
+                res_at = sj.res_at;
+                sorts.push_back(sj);
+            }
+            for (int j = 0; j < nj; ++j) {
+                FirUnit U; memset(&U, 0, sizeof U);
+                const int bb = j + nj;                         // pair block j with block j + nj of the same render
+                U.in = mono_in + r[i].x; U.out = mono_out + r[i].y; U.filt = filt;
+                U.p0_a = (long long)j * hop - (r[i].h_len - 1);
+                U.has_b = bb < nblk;
+                U.p0_b = U.has_b ? (long long)bb * hop - (r[i].h_len - 1) : 0;
+                U.ols_n = r[i].out_n; U.ols_skip = r[i].h_len - 1;
+                U.live_lo = r[i].x_begin; U.live_hi = live_hi;
+                U.tap_res = res_at;
+                P->units.push_back(U);
+            }
+            continue;
+        }
         if (r[i].tap_end > r[i].tap_begin) {
             FftJob H = G;
             ErJob E; E.e = (long long)L.e_at[i]; E.elen = r[i].h_len - r[i].ir_len + 1; E.tap_begin = r[i].tap_begin; E.tap_end = r[i].tap_end;
@@ -279,9 +351,6 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
             P->hjobs.push_back(H);
             filt = hspec + L.hspec_at[i];
         }
-        const int hop = L.B[i] - r[i].h_len + 1;
-        const int nblk = (r[i].out_n + hop - 1) / hop;
-        const int nj = (nblk + 1) / 2;
         for (int j = 0; j < nj; ++j) {
             FftJob J = G;
             const int ba = j, bb = j + nj;                 // pair block j with block j + nj of the same render
@@ -290,7 +359,7 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
             if (bb < nblk) { J.in_b = J.in_a; J.out_b = J.out_a; J.p0_b = (long long)bb * hop - (r[i].h_len - 1); }
             J.ols_n = r[i].out_n; J.ols_skip = r[i].h_len - 1;
             J.live_lo = r[i].x_begin;
-            J.live_hi = (int)std::min<long long>(r[i].out_n, (long long)r[i].x_end + r[i].h_len - 1);
+            J.live_hi = live_hi;
             J.bspec = filt;
             if (L.B[i] > MS_SMALL_MAX) { J.work = work + wk; wk += (size_t)L.B[i]; }
             P->cjobs.push_back(J);
@@ -307,16 +376,82 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
         if (ms_h2d(P->hjobs_dev, P->hjobs.data(), sizeof(FftJob) * P->hjobs.size(), st)) { delete P; return -1; }
         if (ms_h2d(P->ejobs_dev, P->ejobs.data(), sizeof(ErJob) * P->ejobs.size(), st)) { delete P; return -1; }
     }
-    if (ms_h2d(P->cjobs_dev, P->cjobs.data(), sizeof(FftJob) * P->cjobs.size(), st)) { delete P; return -1; }
+    if (!P->cjobs.empty() && ms_h2d(P->cjobs_dev, P->cjobs.data(), sizeof(FftJob) * P->cjobs.size(), st)) { delete P; return -1; }
     if (FftEngine::get().filter_spectrum(P->ijobs, P->ijobs_dev, st)) { delete P; return -1; }      // once per plan
+    if (!P->units.empty()) {
+        P->units_dev = (FirUnit*)(base + L.units_off);
+        P->scratch = (cpx*)(base + L.scratch_off);
+        P->n_scratch = L.n_scratch;
+        int* res_ptr = (int*)(base + L.res_off);
+        int* soff = (int*)(base + L.soff_off);
+        real* sgain = (real*)(base + L.sgain_off);
+        P->ft.res_ptr = res_ptr; P->ft.tap_off = soff; P->ft.tap_gain = sgain;
+        if (ms_h2d(P->units_dev, P->units.data(), sizeof(FirUnit) * P->units.size(), st)) { delete P; return -1; }
+        if (!sorts.empty()) {                                  // residue-sorted copies of the taps: table building, once per plan
+            FirSortJob* sj = (FirSortJob*)(base + L.sort_off);
+            if (ms_h2d(sj, sorts.data(), sizeof(FirSortJob) * sorts.size(), st)) { delete P; return -1; }
+            for (size_t y0 = 0; y0 < sorts.size(); y0 += 32768) {
+                const unsigned yc = (unsigned)std::min<size_t>(32768, sorts.size() - y0);
+                if (ms_launch<FirSortK>(mk_dim(1, yc), 256, 257 * sizeof(int), st, (const FirSortJob*)(sj + y0), P->tap_off, P->tap_gain,
+                                        res_ptr, soff, sgain)) { delete P; return -1; }
+            }
+        }
+    }
     *handle = P;
+    return 0;
+}
+#ifndef MS_HOST_EMUL
+template <int CL>
+static int fir_launch_cluster(FirPlan* P, ms_stream_t st) {
+    static int max_clusters = -1;
+    auto kern = fir_cluster_kernel<CL>;
+    if (max_clusters < 0) {
+        MS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM2));
+        if (CL > 8) MS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t q; memset(&q, 0, sizeof q);
+        q.gridDim = dim3(CL * fir_max_clusters(CL), 1, 1); q.blockDim = dim3(FF_NTHR, 1, 1); q.dynamicSmemBytes = FF_SMEM2;
+        cudaLaunchAttribute a[1]; a[0].id = cudaLaunchAttributeClusterDimension; a[0].val.clusterDim.x = CL; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+        q.attrs = a; q.numAttrs = 1;
+        int nc = 0;
+        MS_CUDA_OK(cudaOccupancyMaxActiveClusters(&nc, kern, &q));
+        if (nc < 1) MS_FAIL("fir: clusters of %d CTAs cannot be scheduled on this device", CL);
+        max_clusters = nc;
+    }
+    const int ncl = std::min(std::min(max_clusters, P->n_scratch), (int)P->units.size());
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(CL * ncl), 1, 1); cfg.blockDim = dim3(FF_NTHR, 1, 1); cfg.dynamicSmemBytes = FF_SMEM2; cfg.stream = st;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, (const FirUnit*)P->units_dev, (int)P->units.size(), P->ft, P->scratch));
+    ++ms_launch_counter();
+    if (ms_launch_hook()) ms_launch_hook()(CL == 4 ? "K = fir_cluster_kernel<4>;" : CL == 8 ? "K = fir_cluster_kernel<8>;" : "K = fir_cluster_kernel<16>;", (void*)st);
+    return 0;
+}
+#endif
+static int fir_run_fused(FirPlan* P, ms_stream_t st) {
+    const int mode = fir_mode();
+#ifndef MS_HOST_EMUL
+    if (mode == 4) return fir_launch_cluster<4>(P, st);
+    if (mode == 8) return fir_launch_cluster<8>(P, st);
+    if (mode == 16) return fir_launch_cluster<16>(P, st);
+#endif
+    (void)mode;
+    for (size_t y0 = 0; y0 < P->units.size(); y0 += 32768) {
+        const unsigned yc = (unsigned)std::min<size_t>(32768, P->units.size() - y0);
+        const FirUnit* u = P->units_dev + y0;
+        cpx* sc = P->scratch + y0 * (size_t)(FF_N * FF_N);
+        if (ms_launch<FirP1K>(mk_dim(FF_TILES, yc), FF_NTHR, FF_SMEM1, st, u, P->ft, sc)) return -1;
+        if (ms_launch<FirP2K>(mk_dim(FF_TILES, yc), FF_NTHR, FF_SMEM2, st, u, P->ft, sc)) return -1;
+        if (ms_launch<FirP3K>(mk_dim(FF_TILES, yc), FF_NTHR, FF_SMEM1, st, u, P->ft, sc)) return -1;
+    }
     return 0;
 }
 extern "C" int MS_API(ms_fir_run)(void* handle, void* stream) {
     FirPlan* P = (FirPlan*)handle;
     if (!P) MS_FAIL("ms_fir_run: null handle");
-    if (P->cjobs.empty()) return 0;
     ms_stream_t st = (ms_stream_t)stream;
+    if (!P->units.empty() && fir_run_fused(P, st)) return -1;
+    if (P->cjobs.empty()) return 0;
     if (!P->hjobs.empty()) {
         for (size_t y0 = 0; y0 < P->ejobs.size(); y0 += 32768) {
             const unsigned yc = (unsigned)std::min<size_t>(32768, P->ejobs.size() - y0);

@@ -34,9 +34,18 @@ class CudaDevice:
             raise RuntimeError("audio_suite_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.torch = torch
         self.index = torch.cuda.current_device() if index is None else int(index)
+        # the library allocates its twiddle / chirp tables with cudaMalloc on the CURRENT device and caches them per
+        # process, so a process drives exactly one GPU (one process per GPU, as torchrun launches them)
+        owner = CudaDevice._owner
+        if owner is not None and owner != self.index:
+            raise RuntimeError(f"audio_suite_b200: this process already renders on cuda:{owner}; use one process per GPU")
+        CudaDevice._owner = self.index
+        torch.cuda.set_device(self.index)
         self.dev = torch.device("cuda", self.index)
         self.lib = _abi.lib()
         self.uploaded = 0
+
+    _owner = None
 
     def stream_ptr(self):
         return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
@@ -535,7 +544,7 @@ def render(params, progress=None, device=None, precision="auto"):
         n_evt = len(rp.events)
         for ev in rp.events:
             if ev.placed and ev.index % 50 == 0:
-                progress(int(5 + 70 * (ev.index / max(1, n_evt))), f"Events {ev.index}/{n_evt}")
+                progress(int(5 + 70 * (ev.index / max(1, n_evt))), f"Events {ev.index}/{n_evt}  {ev.note}".strip())      # M:758
     audio = br.output(0).astype(np.float64)
     meta = br.meta(0)
     br.close()

@@ -50,8 +50,8 @@ def _parse_breakpoints(text):
         part = part.strip()
         if not part or ":" not in part:
             continue
+        t, v = part.split(":")               # "a:b:c" raises ValueError like the reference (M:461 is outside its try)
         try:
-            t, v = part.split(":")
             pts.append((float(t.strip()), float(v.strip())))
         except Exception:
             continue
@@ -225,6 +225,7 @@ class EventPlan:
     plock: Optional[tuple] = None           # (factor, top_n, neigh, pre-operator) when partial_lock_stretch is active
     cep: Optional[tuple] = None             # (factor, pre-operator, operator of its last inverse) when cepstral_warp is active
     stick_noise: float = 0.0
+    note: str = ""                          # generator note carried by the progress message (M:651, 682-684, 758)
     wg: Optional[np.ndarray] = None         # waveguide lines: float64 [L, 3] = delay in samples, loop gain, mix
     res: Optional[tuple] = None             # (modes float64 [K, 3] = f/sr, phase, weight ; decay per sample) for resonator_bank
     spec_b: Optional[object] = None         # multiband operator applied AFTER the resonator bank
@@ -303,15 +304,24 @@ def plan_render(params) -> RenderPlan:
     gmode = params["gen_mode"]
     dust_density = tilt = ring_hz = ring_decay_ms = 0.0
     ir_audio, img_gray = params.get("_ir_audio"), params.get("_img_gray")
+    digest = params.get("_ir_digest")          # pooled batches ship the IR pre-digested (digest_params) instead of `_ir_audio`
+    frag_src = None
     floor = 16
+    note = ""
     if gmode == "Wavelet atoms":
         mode, floor = MODE_WAVELET, WAVELET_FLOOR
     elif gmode == "Crackle / corona":
         mode = MODE_DUST                       # same device kernel as the dust mode: sparse impulses * exp kernel, no fades
     elif gmode == "IR fragment":               # M:335-337: silence of gen_basic's length when no IR is loaded
-        mode, floor = (MODE_SILENT, 16) if (ir_audio is None or np.asarray(ir_audio).size < 32) else (MODE_IRFRAG, 64)
+        if digest is not None:
+            frag_src = digest["frag"]
+        elif ir_audio is not None and np.asarray(ir_audio).size >= 32:                # M:335
+            frag_src = _mono64(ir_audio)
+        mode, floor = (MODE_SILENT, 16) if frag_src is None else (MODE_IRFRAG, 64)
+        note = "No IR loaded" if frag_src is None else "IR fragment"                  # M:336, 348
     elif gmode == "Image scanline":
         mode, floor = (MODE_SILENT if img_gray is None else MODE_SCANLINE), 64
+        note = "No image loaded" if img_gray is None else ""                          # M:354 (else: the scan line, per event)
     elif gmode == "Micro-chaos":
         mode, floor = MODE_CHAOS, 64
     elif gmode == "Stick–slip friction":
@@ -340,7 +350,7 @@ def plan_render(params) -> RenderPlan:
         sr_evt = design_rate(base_sr, ufac)
         n = grain_length(sr_evt, micro_ms, floor)
         ev = EventPlan(index=i, t0=t0, amp=float(amp), ufac=ufac, gen_sr=sr_evt, n=n, seed=seed + i, mode=mode,
-                       cutoff_gen=cutoff_out * ufac, stretch=float(stretch), start=int(round(t0 * base_sr)))
+                       cutoff_gen=cutoff_out * ufac, stretch=float(stretch), start=int(round(t0 * base_sr)), note=note)
         if ev.start < out_n:
             if offset_on and max_off > 0:
                 ev.offset = int(rng.integers(0, max(1, min(max_off, n))))
@@ -388,7 +398,7 @@ def plan_render(params) -> RenderPlan:
         elif mode == MODE_DUST:
             _plan_dust(ev, dust_density)
         elif mode == MODE_IRFRAG:
-            _plan_ir_fragment(ev, ir_audio)
+            _plan_ir_fragment(ev, frag_src)
         elif mode == MODE_SCANLINE:
             _plan_scanline(ev, img_gray)
         elif mode == MODE_STICK:               # M:283-301: threshold, build, decay, noise ride in the mode constants
@@ -424,9 +434,11 @@ def plan_render(params) -> RenderPlan:
         offs, gains = reflection_taps(base_sr, int(params["er_taps"]), float(params["er_max_ms"]), seed)
         keep = (offs > 0) & (offs < out_n)
         rp.er_offs, rp.er_gains = offs[keep].astype(np.int32), gains[keep]
-    ir = params.get("_ir_audio")
-    if params["space_ir_on"] and ir is not None:
-        rp.ir = _ir_taps(ir, int(params["space_ir_max_samps"]))
+    if params["space_ir_on"]:
+        if digest is not None:
+            rp.ir = digest["taps"]
+        elif ir_audio is not None:
+            rp.ir = _ir_taps(ir_audio, int(params["space_ir_max_samps"]))
     if params["stereo_on"] and out_n >= 64:   # M:426: shorter outputs are duplicated
         w = float(min(max(float(params["stereo_width"]), 0.0), 1.0))
         rp.stereo_on = True
@@ -546,10 +558,10 @@ def _mono64(ir):
     return hit[1]
 
 
-def _plan_ir_fragment(ev, ir_audio):
-    """gen_ir_fragment (M:333-348): the host draws the start and hands the 256-sample piece to the device."""
+def _plan_ir_fragment(ev, src):
+    """gen_ir_fragment (M:333-348): the host draws the start and hands the 256-sample piece of the mono mix `src`
+    (float64, full length) to the device."""
     rng = np.random.default_rng(int(ev.seed))
-    src = _mono64(ir_audio)
     start = int(rng.integers(0, max(1, src.size - 256)))
     ev.table = np.ascontiguousarray(src[start:start + 256])
 
@@ -558,7 +570,9 @@ def _plan_scanline(ev, img_gray):
     """gen_image_scanline (M:350-362): the host draws the row and centres it; the device resamples and smooths."""
     rng = np.random.default_rng(int(ev.seed))
     h, w = img_gray.shape
-    row = img_gray[int(rng.integers(0, h)), :].astype(np.float64) / 255.0
+    y = int(rng.integers(0, h))
+    ev.note = f"Image line y={y}"                                                   # M:362
+    row = img_gray[y, :].astype(np.float64) / 255.0
     ev.table = (row - row.mean()) * 2.0
     ev.ker_len = 48
 
@@ -581,30 +595,21 @@ def _plan_dust(ev, density):
 
 
 # --------------------------------------------------------------------------- batch planning
-_IR_CACHE = {}
-
-
 def _slim_params(p):
-    """Copy of a parameter dict whose impulse response is already reduced to what the planner keeps:
-    the mono mix of the first 8192 rows (M:441-443).  Planning the copy gives the identical plan."""
+    """Copy of a parameter dict for the planning workers: the impulse response is replaced by what the planner
+    keeps of it -- `_ir_digest = {"taps": convolve_ir_short's view (M:439-443: float64 mono mix of the first
+    min(space_ir_max_samps, 8192) rows, None when that slice has fewer than 8 values), "frag": gen_ir_fragment's
+    source (M:335-340: the float64 mono mix of the WHOLE response, None when it has fewer than 32 values)}` -- so a
+    multi-second stereo IR is not pickled per render and both size tests are made on the original array.  The
+    digests are cached per IR object, so renders sharing an IR share the arrays (one pickle memo entry per piece)."""
     ir = p.get("_ir_audio")
-    if ir is None:
+    if ir is None or "_ir_digest" in p:
         return p
     q = dict(p)
-    a = np.asarray(ir)
-    if a[:int(p["space_ir_max_samps"])].size < 8:          # M:439 is evaluated on the full (2-D) slice
-        q["_ir_audio"] = None
-        return q
-    key = (id(ir), a.shape)
-    hit = _IR_CACHE.get(key)
-    if hit is None or hit[0] is not ir:
-        h = a[:IR_TAP_CAP].astype(np.float64)
-        if h.ndim > 1:
-            h = h.mean(axis=1)
-        if len(_IR_CACHE) > 64:
-            _IR_CACHE.clear()
-        _IR_CACHE[key] = hit = (ir, h)
-    q["_ir_audio"] = hit[1]
-    if hit[1].size < 8:                                    # keep the planner's own size test true
-        q["_ir_audio"] = np.concatenate([hit[1], np.zeros(8 - hit[1].size)]) if False else hit[1]
+    q["_ir_audio"] = None
+    frag = None
+    if p["gen_mode"] == "IR fragment" and np.asarray(ir).size >= 32:
+        frag = _mono64(ir)
+    taps = _ir_taps(ir, int(p["space_ir_max_samps"])) if p["space_ir_on"] else None
+    q["_ir_digest"] = {"taps": taps, "frag": frag}
     return q

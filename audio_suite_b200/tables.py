@@ -269,9 +269,9 @@ def pack_chunk(plans) -> Tables:
             if ev.placed:
                 ola_e.append((g_at + ev.offset, ev.start, ev.length, ev.amp))
                 max_len = max(max_len, ev.length)
-                # grain[0] is exactly 0 (fade-in starts at 0, main_v2.py:267): with no offset the first placed
-                # sample is an exact zero
-                x_begin = min(x_begin, ev.start + (1 if ev.offset == 0 else 0))
+                # (no "grain[0] == 0" shortcut here: that holds for a raw gen_basic transient only, not after the
+                #  band-limit / stretch / multiband operators or for the generators without a fade-in)
+                x_begin = min(x_begin, ev.start)
                 x_end = max(x_end, ev.start + ev.length)
                 alg["overlap_add"] += ev.length
             e += 1
@@ -718,9 +718,9 @@ def plan_stream(params_list, chunk, workers=None, piece=32):
     for a, b in cuts:
         bounds.append([(i, min(b, i + piece)) for i in range(a, b, piece)])
     flat = [ab for bs in bounds for ab in bs]
-    # Static round-robin assignment, no threads in the parent: piece i belongs to worker i % W and is answered in
-    # order; the parent reads the answers in piece order straight from the pipes (1 MiB pipes let a worker run a
-    # few pieces ahead).  Impulse responses are slimmed before pickling (P._slim_params).
+    # Static round-robin assignment: piece i belongs to worker i % W and is answered in order; the parent reads the
+    # answers in piece order straight from the pipes (1 MiB pipes let a worker run a few pieces ahead).  Impulse
+    # responses are digested before pickling (P._slim_params).
     import pickle
     import struct
     pool = _pool(workers)
@@ -746,29 +746,35 @@ def plan_stream(params_list, chunk, workers=None, piece=32):
         if status != "ok":
             raise payload
         return payload
-    try:
-        # Requests go out piece by piece, round-robin (piece i -> worker i % W), always a few slices AHEAD of what is
-        # being read: pickling 4096 parameter dicts costs ~30 ms of the parent's time, which would otherwise sit in
-        # front of the first slice and leave the later workers idle while the earlier ones get their lists.
-        sent = 0
+    # Requests go out piece by piece, round-robin (piece i -> worker i % W), from a FEEDER THREAD: the thread that
+    # reads the answers never blocks on a write.  (Writing from the reading thread can deadlock: a request larger than
+    # the free space of a worker's stdin pipe blocks the parent while that worker is itself blocked writing an answer
+    # nobody reads -- reproduced with 4 MB `_img_gray` arrays per piece.)  Every piece below the one being read has been
+    # consumed, so the worker that owns it can always finish it: the pipeline cannot stall for good.
+    import threading
+    feed_err = []
 
-        def send_until(limit):
-            nonlocal sent
-            while sent < min(limit, len(flat)):
-                send(sent % W, slim(sent))
-                sent += 1
+    def feed():
+        try:
+            for i in range(len(flat)):
+                send(i % W, slim(i))
+        except BaseException as e:          # a closed pool (abandoned generator) ends the feeder quietly;
+            feed_err.append(e)              # anything else (e.g. an unpicklable parameter) must not leave the reader waiting
+            if not isinstance(e, (BrokenPipeError, ValueError, OSError)):
+                shutdown_pool()
+    feeder = threading.Thread(target=feed, daemon=True)
+    feeder.start()
+    try:
         k = 0
-        per_slice = max(len(bs) for bs in bounds)
         for bs in bounds:
-            send_until(k + len(bs) + max(2 * W, 2 * per_slice))       # this slice plus two rounds / two slices of lookahead
-            parts = []
-            for t in range(len(bs)):
-                parts.append(recv((k + t) % W))
-                send_until(k + t + 1 + max(2 * W, 2 * per_slice))
+            parts = [recv((k + t) % W) for t in range(len(bs))]
             k += len(bs)
             yield merge_chunks(parts)
-    except BaseException:
+        feeder.join()
+    except BaseException as e:
         shutdown_pool()          # pipes may hold unread answers: start from fresh workers next time
+        if feed_err and not isinstance(feed_err[0], (BrokenPipeError, ValueError, OSError)) and isinstance(e, RuntimeError):
+            raise feed_err[0]
         raise
 
 

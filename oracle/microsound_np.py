@@ -331,14 +331,15 @@ def stereo_diffuse(x, sr, width):
 
 # --------------------------------------------------------------------------- breakpoints / events
 def parse_lane(text):
-    """M:452-467 -- 't:v, t:v' -> sorted [(t, v)]; malformed parts are skipped silently."""
+    """M:452-467 -- 't:v, t:v' -> sorted [(t, v)]; parts without ':' or with unparsable numbers are skipped silently,
+    a part with more than one ':' raises ValueError (the unpacking at M:461 sits outside the reference's try)."""
     pts = []
     for part in (text or "").strip().split(","):
         part = part.strip()
         if not part or ":" not in part:
             continue
+        t, v = part.split(":")
         try:
-            t, v = part.split(":")          # more than one ':' raises -> (reference: bare except) skip
             pts.append((float(t.strip()), float(v.strip())))
         except Exception:
             continue
@@ -542,18 +543,22 @@ def ir_fragment(ir_audio, gen_sr, micro_ms, seed):
     return peak_normalize(x, 0.9)
 
 
-def image_scanline(img_gray, gen_sr, micro_ms, seed):
+def image_scanline(img_gray, gen_sr, micro_ms, seed, with_note=False):
     """M:350-362 -- one random row of the loaded grey image, centred, stretched to the grain length, Hann-windowed
-    and smoothed by exp(-linspace(0, 5, 48)); silence when no image is loaded."""
+    and smoothed by exp(-linspace(0, 5, 48)); silence when no image is loaded.  `with_note`: also return the
+    progress note the reference hands back (M:354, 362)."""
     rng = np.random.default_rng(int(seed))
     n = grain_length(gen_sr, micro_ms, floor=64)
     if img_gray is None:
-        return np.zeros(n, dtype=np.float64)
+        x = np.zeros(n, dtype=np.float64)
+        return (x, "No image loaded") if with_note else x
     h, w = img_gray.shape
-    row = img_gray[int(rng.integers(0, h)), :].astype(np.float64) / 255.0
+    y = int(rng.integers(0, h))
+    row = img_gray[y, :].astype(np.float64) / 255.0
     row = (row - row.mean()) * 2.0
     x = np.interp(np.linspace(0, 1, n), np.linspace(0, 1, w), row) * raised_cosine_window(n)
-    return np.convolve(x, np.exp(-np.linspace(0, 5, 48)), mode="same")
+    x = np.convolve(x, np.exp(-np.linspace(0, 5, 48)), mode="same")
+    return (x, f"Image line y={y}") if with_note else x
 
 
 def micro_chaos(gen_sr, micro_ms, seed, r, gate):
@@ -721,6 +726,7 @@ def render(params, progress=None, taps=None, jitter=None):
     previous = None                                                               # M:626: last event's grain, as placed
     for ev in plan["events"]:
         i = ev["index"]
+        note = ""                                                                 # M:651
         if mode == "Wavelet atoms":
             g = wavelet_atoms(ev["gen_sr"], micro_ms, seed + i, float(params["wav_base_hz"]), int(params["wav_count"]),
                               float(params["wav_spread"]))
@@ -733,9 +739,11 @@ def render(params, progress=None, taps=None, jitter=None):
         elif mode == "Micro-chaos":
             g = micro_chaos(ev["gen_sr"], micro_ms, seed + i, float(params["chaos_r"]), float(params["chaos_gate"]))
         elif mode == "IR fragment":
-            g = ir_fragment(params.get("_ir_audio"), ev["gen_sr"], micro_ms, seed + i)
+            ir_a = params.get("_ir_audio")
+            g = ir_fragment(ir_a, ev["gen_sr"], micro_ms, seed + i)
+            note = "No IR loaded" if (ir_a is None or ir_a.size < 32) else "IR fragment"       # M:336, 348
         elif mode == "Image scanline":
-            g = image_scanline(params.get("_img_gray"), ev["gen_sr"], micro_ms, seed + i)
+            g, note = image_scanline(params.get("_img_gray"), ev["gen_sr"], micro_ms, seed + i, with_note=True)
         elif mode in BASIC_MODES:
             g = basic_transient(ev["gen_sr"], micro_ms, seed + i, mode, float(params["dust_density"]),
                                 float(params["noise_tilt"]), float(params["ring_hz"]),
@@ -781,7 +789,7 @@ def render(params, progress=None, taps=None, jitter=None):
             a, o, ln = ev["start"], ev["offset"], ev["length"]
             mix[a:a + ln] += ev["amp"] * g[o:o + ln]
         if progress and ev["placed"] and i % 50 == 0:       # M:757 sits after the `continue` at M:744
-            progress(int(5 + 70 * (i / max(1, n_evt))), f"Events {i}/{n_evt}")
+            progress(int(5 + 70 * (i / max(1, n_evt))), f"Events {i}/{n_evt}  {note}".strip())      # M:758
     mix *= adsr_envelope(out_n, base_sr, float(params["env_a"]), float(params["env_d"]),
                          float(params["env_s"]), float(params["env_r"]), float(params["env_curve"]))
     if taps is not None:
