@@ -31,6 +31,7 @@
 #define FF_NTHR (32 * FF_TILE)
 #define FF_TILES (FF_N / FF_TILE)      // tiles per phase
 #define FF_RS ((ms_pad(FF_N) + 1) | 1) // row stride of a tile in shared memory (odd: conflict-free transposes)
+#define FF_RES_STRIDE (257 + 256)       // ints per render in the residue table
 
 struct FirUnit {
     const real* in; real* out;        // the render's mono input / output planes
@@ -38,13 +39,13 @@ struct FirUnit {
     long long p0_a, p0_b;             // first input sample of block a / b (may be negative)
     int has_b, ols_n, ols_skip;       // ols_skip = taps - 1: leading outputs of a block that are discarded
     int live_lo, live_hi;             // outputs outside [live_lo, live_hi) are exactly zero (input support + taps)
-    int tap_res;                      // >= 0: offset of this render's 257 residue pointers; < 0: no reflection taps
+    int tap_res;                      // >= 0: offset of this render's residue table (257 segment pointers + 256 owners); < 0: no reflection taps
     int _pad0, _pad1;
 };
 struct FirTables {
     const cpx* tw;                    // w_256^i
     const cpx* twM_hi; const cpx* twM_lo;   // W_65536^(1024 i), W_65536^i (i < 1024)
-    const int* res_ptr;               // per render with taps: 257 offsets into the residue-sorted tap arrays
+    const int* res_ptr;               // per render with taps: 257 offsets into the residue-sorted tap arrays, then the 256 residues by descending count
     const int* tap_off; const real* tap_gain;     // residue-sorted taps
 };
 
@@ -130,74 +131,95 @@ MS_DEV void fir_p1_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
 }
 
 // ---- phase 2: rows (forward, filter, inverse) ---------------------------------------------------------------
+// The reflection taps are real, so E is Hermitian: E[65536 - k] = conj E[k], i.e. row 256 - k1 is row k1 reversed and
+// conjugated (E[256 - k1][k2] = conj E[k1][255 - k2]).  A tile therefore holds four rows k1 = 4 t + 1 .. 4 t + 4 and
+// their partners 256 - k1: the fold and the extra FFT run for four rows only.  Rows 0 and 128 are their own partners:
+// in tile 31 (k1 = 125 .. 128) the warp that would get row 128 a second time takes row 0, with a fifth folded row.
+// Warps 0-3 transform the folded rows while warps 4-7 fetch the tile, so the two latencies overlap inside the CTA.
+#define FF_EROWS 5
 MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, const Ctx& c) {
     cpx* sB = (cpx*)c.smem;                                 // transposing tile + exchange rows
-    cpx* sA = sB + FF_TILE * FF_RS;                         // filter rows H[k1][.]
+    cpx* sE = sB + FF_TILE * FF_RS;                         // E rows (natural order k2): four + row 0 in the last tile
     const int lane = c.tid & 31, warp = c.tid >> 5;
-    const int r0 = tile * FF_TILE, k1 = r0 + warp;
+    const int k_lo = 4 * tile + 1;
+    const int last = tile == FF_TILES - 1;
+    int row, erow, rev;
+    if (warp < 4) { row = k_lo + warp; erow = warp; rev = 0; }
+    else { row = FF_N - (k_lo + warp - 4); erow = warp - 4; rev = 1; }
+    if (last && warp == 7) { row = 0; erow = 4; rev = 0; }
     const int taps = U.tap_res >= 0;
     cpx v[8];
     if (taps) {
-        // E[k1 + 256 k2] = FFT_256 over r of F[r] = sum over taps with off = r (mod 256) of g W_65536^(off k1).
-        // Thread r owns residue r for the eight rows of the tile: W^(off k1) steps by W^off from one row to the next.
-        // (four rows at a time: eight complex accumulators next to the twiddles do not fit the register budget)
+        // fold: F[k1][r] = sum over taps with off = r (mod 256) of g W_65536^(off k1); a thread owns one residue for the
+        // tile's four rows (W^(off k1) steps by W^off from row to row).  Residues are handed out by descending tap count
+        // (perm), so the lanes of a warp run the same number of iterations.
         const int* rp = T.res_ptr + U.tap_res;
-        const int r = c.tid;
+        const int r = __ldg(&rp[257 + c.tid]);
         const int t_begin = __ldg(&rp[r]), t_end = __ldg(&rp[r + 1]);
-#pragma unroll 1
-        for (int half = 0; half < FF_TILE; half += 4) {
-            cpx acc[4];
+        cpx acc[4];
+        real f0 = (real)0.;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) acc[w] = c_zero();
-            for (int t = t_begin; t < t_end; ++t) {
-                const unsigned off = (unsigned)__ldg(&T.tap_off[t]);
-                const real g = __ldg(&T.tap_gain[t]);
-                cpx tw = tw2level(T.twM_hi, T.twM_lo, (off * (unsigned)(r0 + half)) & 65535u);
-                const cpx st = tw2level(T.twM_hi, T.twM_lo, off & 65535u);
+        for (int w = 0; w < 4; ++w) acc[w] = c_zero();
+        for (int t = t_begin; t < t_end; ++t) {
+            const unsigned off = (unsigned)__ldg(&T.tap_off[t]);
+            const real g = __ldg(&T.tap_gain[t]);
+            cpx tw = tw2level(T.twM_hi, T.twM_lo, (off * (unsigned)k_lo) & 65535u);
+            const cpx st = tw2level(T.twM_hi, T.twM_lo, off & 65535u);
+            f0 += g;
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    acc[w] = mk(acc[w].x + g * tw.x, acc[w].y + g * tw.y);
-                    if (w < 3) tw = c_mul(tw, st);
-                }
+            for (int w = 0; w < 4; ++w) {
+                acc[w] = mk(acc[w].x + g * tw.x, acc[w].y + g * tw.y);
+                if (w < 3) tw = c_mul(tw, st);
             }
-#pragma unroll
-            for (int w = 0; w < 4; ++w) sA[(half + w) * FF_RS + ms_pad(r)] = acc[w];
         }
+#pragma unroll
+        for (int w = 0; w < 4; ++w) sE[w * FF_RS + ms_pad(r)] = acc[w];
+        if (last) sE[4 * FF_RS + ms_pad(r)] = mk(f0, (real)0.);
         c.sync();
-        cpx* swA = sA + warp * FF_RS;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = swA[ms_pad(lane + 32 * q)];
-        c.syncwarp();
-        warp_fft256(v, swA, T.tw, lane, c);
-        const cpx* f = U.filt + (size_t)k1 * FF_N + lane;
-        c.syncwarp();
-#pragma unroll
-        for (int m = 0; m < 8; ++m) swA[ms_pad(lane + 32 * m)] = c_mul(__ldg(&f[32 * m]), mk(v[m].x + (real)1.0, v[m].y));
-        c.syncwarp();
     }
+    if (!taps || warp >= 4) {
+        // the tile: S[n2][rows of the tile] -> sB[row slot][n2]   (warps 4-7 when the others are busy with E)
+        const int nthr = taps ? FF_NTHR / 2 : FF_NTHR, t0 = taps ? c.tid - FF_NTHR / 2 : c.tid;
+        for (int e = t0; e < FF_N * FF_TILE; e += nthr) {
+            const int n2 = e >> 3, rr = e & 7;
+            int rw = rr < 4 ? k_lo + rr : FF_N - (k_lo + rr - 4);
+            if (last && rr == 7) rw = 0;
+            sB[rr * FF_RS + ms_pad(n2)] = MS_LDCG(&S[(size_t)n2 * FF_N + rw]);
+        }
+    }
+    if (taps && (warp < 4 || (last && warp == 7))) {
+        cpx* swE = sE + erow * FF_RS;
 #pragma unroll
-    for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
-        const int e = c.tid + FF_NTHR * i, n2 = e >> 3, rr = e & 7;
-        sB[rr * FF_RS + ms_pad(n2)] = MS_LDCG(&S[(size_t)n2 * FF_N + r0 + rr]);
+        for (int q = 0; q < 8; ++q) v[q] = swE[ms_pad(lane + 32 * q)];
+        c.syncwarp();
+        warp_fft256(v, swE, T.tw, lane, c);                 // v[m] = E[row][k2 = lane + 32 m]
+        c.syncwarp();
+#pragma unroll
+        for (int m = 0; m < 8; ++m) swE[ms_pad(lane + 32 * m)] = v[m];
     }
     c.sync();
     cpx* sw = sB + warp * FF_RS;
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
     c.syncwarp();
-    warp_fft256(v, sw, T.tw, lane, c);                      // v[m] = Z[k1][k2 = lane + 32 m]
-    if (taps) {
-        const cpx* swA = sA + warp * FF_RS;
+    warp_fft256(v, sw, T.tw, lane, c);                      // v[m] = Z[row][k2 = lane + 32 m]
+    {
+        const cpx* f = U.filt + (size_t)row * FF_N + lane;
+        const cpx* swE = sE + erow * FF_RS;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = c_swap(c_mul(v[m], swA[ms_pad(lane + 32 * m)]));
-    } else {
-        const cpx* f = U.filt + (size_t)k1 * FF_N + lane;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = c_swap(c_mul(v[m], __ldg(&f[32 * m])));
+        for (int m = 0; m < 8; ++m) {
+            cpx h = __ldg(&f[32 * m]);
+            if (taps) {
+                const int k2 = lane + 32 * m;
+                const cpx e = rev ? c_conj(swE[ms_pad(FF_N - 1 - k2)]) : swE[ms_pad(k2)];
+                h = c_mul(h, mk(e.x + (real)1.0, e.y));
+            }
+            v[m] = c_swap(c_mul(v[m], h));
+        }
     }
     c.syncwarp();
     warp_fft256(v, sw, T.tw, lane, c);                      // inverse over k2 (swapped domain): index n2' = lane + 32 m
-    twiddle_row(v, T, k1, lane);
+    twiddle_row(v, T, row, lane);
     c.syncwarp();
 #pragma unroll
     for (int m = 0; m < 8; ++m) sw[ms_pad(lane + 32 * m)] = v[m];
@@ -205,7 +227,9 @@ MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
 #pragma unroll
     for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
         const int e = c.tid + FF_NTHR * i, n2 = e >> 3, rr = e & 7;
-        S[(size_t)n2 * FF_N + r0 + rr] = sB[rr * FF_RS + ms_pad(n2)];
+        int rw = rr < 4 ? k_lo + rr : FF_N - (k_lo + rr - 4);
+        if (last && rr == 7) rw = 0;
+        S[(size_t)n2 * FF_N + rw] = sB[rr * FF_RS + ms_pad(n2)];
     }
     c.sync();
 }
@@ -254,7 +278,7 @@ struct FirSortJob { int tap_begin, tap_end, res_at, _pad; };
 MS_DEV void fir_sort_taps_body(const FirSortJob* MS_RESTRICT jobs, const int* MS_RESTRICT tap_off, const real* MS_RESTRICT tap_gain,
                                int* res_ptr, int* soff, real* sgain, const Ctx& c) {
     const FirSortJob J = jobs[c.by];
-    int* cnt = (int*)c.smem;                                // 257
+    int* cnt = (int*)c.smem;                                // 257 segment starts + 256 counts
     const int r = c.tid;
     int n = 0;
     for (int t = J.tap_begin; t < J.tap_end; ++t) {
@@ -272,6 +296,14 @@ MS_DEV void fir_sort_taps_body(const FirSortJob* MS_RESTRICT jobs, const int* MS
     int at = cnt[r];
     res_ptr[J.res_at + r] = at;
     if (r == 0) res_ptr[J.res_at + 256] = cnt[256];
+    // residues by descending tap count (ties by index): thread t of the fold owns residue perm[t], so the lanes of a
+    // warp see (nearly) equal loop counts
+    int* cn = cnt + 257;
+    cn[r] = n;
+    c.sync();
+    int rank = 0;
+    for (int i = 0; i < 256; ++i) { const int k = cn[i]; rank += (k > n || (k == n && i < r)) ? 1 : 0; }
+    res_ptr[J.res_at + 257 + rank] = r;
     for (int t = J.tap_begin; t < J.tap_end; ++t) {
         const int off = __ldg(&tap_off[t]);
         if (off >= 0 && off < FF_N * FF_N && (off & 255) == r) { soff[at] = off; sgain[at] = __ldg(&tap_gain[t]); ++at; }

@@ -28,14 +28,13 @@
   static inline int __ldg(const int* p) { return *p; }
   static inline float __fmaf_rn(float a, float b, float c) { return std::fma(a, b, c); }
   static inline double cospi(double a) { return std::cos(M_PI * a); }
-  namespace msemu { void yield_barrier(); }
+  namespace msemu { void yield_barrier(); void yield_warp_barrier(); }
   struct Ctx {
       int tid, nthr, bx, by;
       char* smem;
       void sync() const { msemu::yield_barrier(); }
-      // warp-level barrier: the emulator has no warps, so this is a block barrier.  That is only equivalent when every
-      // warp of the block executes the same number of them between two block barriers -- true for every kernel here.
-      void syncwarp() const { msemu::yield_barrier(); }
+      // warp-level barrier among the 32 fibres of a warp (counting barrier in the emulator's scheduler)
+      void syncwarp() const { msemu::yield_warp_barrier(); }
   };
 #else
   #include <cuda_runtime.h>

@@ -58,7 +58,7 @@ struct PostMaxK { static constexpr int MAXT = OLA_NTHR;
     static constexpr int MINB = MS_POSTMAX_MINB;
     static MS_DEV void run(const PostRender* r, real* mono, unsigned long long* mb, const Ctx& c) { post_max_body(r, mono, mb, c); } };
 struct PostWriteK { static constexpr int MAXT = OLA_NTHR;
-    static constexpr int MINB = 1;
+    static constexpr int MINB = MS_POSTMAX_MINB;
     static MS_DEV void run(const PostRender* r, const real* mono, const unsigned long long* mb, float2* out, const Ctx& c) { post_write_body(r, mono, mb, out, c); } };
 struct RollK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
@@ -163,7 +163,7 @@ extern "C" int MS_API(ms_post)(const ms_post_render* renders, int n_renders, int
     if (ms_memset(maxbits, 0, sizeof(uint64_t) * (size_t)n_renders, (ms_stream_t)stream)) return -1;
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, (2 * POST_PAR + POST_NC + 1 + OLA_NTHR + OLA_TILE + OLA_TILE / 8 + 8) * sizeof(real), (ms_stream_t)stream,
                                    renders + _y0, mono, (unsigned long long*)maxbits + _y0)) return -1; })
-    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostWriteK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream,
+    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostWriteK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, (2 * POST_PAR + POST_NC + 1 + OLA_NTHR + OLA_TILE + OLA_TILE / 8 + 8) * sizeof(real), (ms_stream_t)stream,
                                    renders + _y0, (const real*)mono, (const unsigned long long*)maxbits + _y0, (float2*)out)) return -1; })
     return 0;
 }
@@ -190,7 +190,10 @@ static int fir_mode() {
     return (e && atoi(e) == 0) ? 0 : 1;                     // the block emulator has no clusters
 #else
     static int mode = -1;
-    if (mode < 0) { const char* e = getenv("MS_FIR_MODE"); mode = e ? atoi(e) : 8; if (mode != 0 && mode != 1 && mode != 4 && mode != 16) mode = 8; }
+    // default 1: measured on B200 (C5 sweep, f64) the one-launch-per-phase form wins -- 10.2 ms against 12.9 / 13.7 / 14.9 ms
+    // for clusters of 4 / 8 / 16 (legacy 15.3 ms): the phases are latency-bound, not DRAM-bound, and a cluster keeps all
+    // its CTAs in the same phase at three CTAs per SM, while separate launches run P1 / P3 at four
+    if (mode < 0) { const char* e = getenv("MS_FIR_MODE"); mode = e ? atoi(e) : 1; if (mode != 0 && mode != 4 && mode != 8 && mode != 16) mode = 1; }
     return mode;
 #endif
 }
@@ -203,7 +206,7 @@ struct FirP3K { static constexpr int MAXT = FF_NTHR; static constexpr int MINB =
 struct FirSortK { static constexpr int MAXT = 256; static constexpr int MINB = 1;
     static MS_DEV void run(const FirSortJob* j, const int* to, const real* tg, int* rp, int* so, real* sg, const Ctx& c) { fir_sort_taps_body(j, to, tg, rp, so, sg, c); } };
 static const size_t FF_SMEM1 = sizeof(cpx) * (size_t)FF_TILE * FF_RS;       // one transposing tile
-static const size_t FF_SMEM2 = 2 * FF_SMEM1;                                  // + the filter rows of phase 2
+static const size_t FF_SMEM2 = sizeof(cpx) * (size_t)(FF_TILE + FF_EROWS) * FF_RS;   // + the reflection-spectrum rows of phase 2
 
 // Plan: (1) at create time, the spectrum of every distinct impulse response (FFT_B(ir)/B, [k1][k2] layout) and the
 // reflection taps of the fused renders sorted by residue; (2) legacy renders, per run: scatter the taps into a dense
@@ -266,7 +269,7 @@ static int fir_layout(const ms_fir_render* r, int n, FirLayout& L) {
     L.units_off = L.work_off + ms_align256(sizeof(cpx) * wk);
     L.sort_off = L.units_off + ms_align256(sizeof(FirUnit) * (size_t)nu);
     L.res_off = L.sort_off + ms_align256(sizeof(FirSortJob) * (size_t)ns);
-    L.soff_off = L.res_off + ms_align256(sizeof(int) * 257 * (size_t)ns);
+    L.soff_off = L.res_off + ms_align256(sizeof(int) * FF_RES_STRIDE * (size_t)ns);
     L.sgain_off = L.soff_off + ms_align256(sizeof(int) * (size_t)(ns ? nt : 0));
     L.scratch_off = L.sgain_off + ms_align256(sizeof(real) * (size_t)(ns ? nt : 0));
     L.total = L.scratch_off + ms_align256(sizeof(cpx) * (size_t)L.n_scratch * (FF_N * FF_N));
@@ -325,7 +328,7 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
             P->ft.tw = G.tw1; P->ft.twM_hi = G.twM_hi; P->ft.twM_lo = G.twM_lo;
             int res_at = -1;
             if (r[i].tap_end > r[i].tap_begin) {
-                FirSortJob sj; sj.tap_begin = r[i].tap_begin; sj.tap_end = r[i].tap_end; sj.res_at = 257 * (int)sorts.size(); sj._pad = 0;
+                FirSortJob sj; sj.tap_begin = r[i].tap_begin; sj.tap_end = r[i].tap_end; sj.res_at = FF_RES_STRIDE * (int)sorts.size(); sj._pad = 0;
                 res_at = sj.res_at;
                 sorts.push_back(sj);
             }
@@ -392,7 +395,7 @@ extern "C" int MS_API(ms_fir_create)(const ms_fir_render* r, int n, const real* 
             if (ms_h2d(sj, sorts.data(), sizeof(FirSortJob) * sorts.size(), st)) { delete P; return -1; }
             for (size_t y0 = 0; y0 < sorts.size(); y0 += 32768) {
                 const unsigned yc = (unsigned)std::min<size_t>(32768, sorts.size() - y0);
-                if (ms_launch<FirSortK>(mk_dim(1, yc), 256, 257 * sizeof(int), st, (const FirSortJob*)(sj + y0), P->tap_off, P->tap_gain,
+                if (ms_launch<FirSortK>(mk_dim(1, yc), 256, (257 + 256) * sizeof(int), st, (const FirSortJob*)(sj + y0), P->tap_off, P->tap_gain,
                                         res_ptr, soff, sgain)) { delete P; return -1; }
             }
         }

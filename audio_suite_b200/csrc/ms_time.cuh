@@ -101,9 +101,68 @@ MS_DEV int wrap_idx(long long i, int n) { long long r = i % n; if (r < 0) r += n
 // the clipped value is stored as float32, so tanh is evaluated in float32 (argument rounded once: 6e-8 relative)
 MS_DEV real soft_clip(real v, real drive, real inv_t) { return drive > (real)0. ? (real)tanhf((float)(v * drive)) * inv_t : v; }
 
+// The right channel of an even-length render over one tile: R[i] = sum_m J_m y[(i + dr + 2 m) mod n] (25 Bessel taps at
+// even lags).  The tile's input window (1024 + 4K samples, circular) is staged in shared memory de-interleaved into
+// its even and odd samples (each parity is a dense 25-tap FIR of its own), every four samples skewed by one slot so
+// that threads working on quads of outputs hit distinct banks; results land in `res` (slot of output j: j + (j >> 3)).
+// Both passes call it: recomputing the taps in pass 2 is cheaper than a write + read of the right channel through HBM
+// (40 N -> 24 N bytes per render).
+MS_DEV void post_right_tile(const PostRender& R, const real* MS_RESTRICT y, int t0, int len, real* win, real* coef, real* res, const Ctx& c) {
+    const int n = R.n;
+    const int W = len + 4 * POST_K;
+    const int w0 = wrap_idx((long long)t0 + R.dr - 2 * POST_K, n);          // one 64-bit modulo per thread
+    for (int j = c.tid; j < W; j += c.nthr) {
+        const int mm = j >> 1;
+        int idx = w0 + j;
+        if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }                  // second wrap only for n < tile
+        win[(j & 1) * POST_PAR + mm + (mm >> 2)] = y[idx];
+    }
+    for (int j = c.tid; j < POST_NC; j += c.nthr) coef[j] = (real)R.coef[j];
+    c.sync();
+    // thread -> parity (warp-uniform) and a quad of consecutive outputs of that parity: 28 loads per 4 outputs
+    for (int u = c.tid; u < OLA_TILE / 4; u += c.nthr) {
+        const int par = u / (OLA_TILE / 8), t = u - par * (OLA_TILE / 8);
+        if (8 * t + par >= len) continue;
+        const real* w = win + par * POST_PAR + 5 * t;     // slot of sample m0 = 4t: 4t + t
+        real a0 = (real)0., a1 = (real)0., a2 = (real)0., a3 = (real)0.;
+        real x0 = w[0], x1 = w[1], x2 = w[2];
+#pragma unroll
+        for (int k = 0; k < POST_NC; ++k) {
+            const real x3 = w[(k + 3) + ((k + 3) >> 2)];
+            const real ck = coef[k];
+            a0 += ck * x0; a1 += ck * x1; a2 += ck * x2; a3 += ck * x3;
+            x0 = x1; x1 = x2; x2 = x3;
+        }
+        const int j0 = 9 * t + par;                  // slot of output j = 8t + par + 2q is j + (j >> 3): stride 9, conflict-free
+        res[j0] = a0; res[j0 + 2] = a1; res[j0 + 4] = a2; res[j0 + 6] = a3;
+    }
+    c.sync();
+}
+// block-wide maximum of non-negative values: warp shuffles, then one value per warp through shared memory
+MS_DEV real block_max(real m, real* red, const Ctx& c) {
+#ifdef MS_HOST_EMUL
+    red[c.tid] = m;
+    c.sync();
+    for (int s = c.nthr >> 1; s > 0; s >>= 1) {
+        if (c.tid < s) red[c.tid] = r_max(red[c.tid], red[c.tid + s]);
+        c.sync();
+    }
+    const real r = red[0];
+    c.sync();
+    return r;
+#else
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = r_max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((c.tid & 31) == 0) red[c.tid >> 5] = m;
+    c.sync();
+    real r = (c.tid & 31) < (c.nthr >> 5) ? red[c.tid & 31] : (real)0.;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r = r_max(r, __shfl_xor_sync(0xffffffffu, r, o));
+    c.sync();
+    return r;
+#endif
+}
 // pass 1: per-render max(|L|, |R|) before the clip (tanh is monotonic, so the clipped max follows).
-// stereo_mode 1 also materialises the right channel at rbuf so that pass 2 does not redo the 25 taps.
-// The tile's input window (1024 + 4K samples, circular) and the taps are staged in shared memory.
 MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, unsigned long long* MS_RESTRICT maxbits, const Ctx& c) {
     const PostRender& R = renders[c.by];
     const int n = R.n, mode = R.stereo_mode;
@@ -111,9 +170,6 @@ MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, uns
     if (t0 >= n) return;
     const int t1 = (t0 + OLA_TILE) < n ? (t0 + OLA_TILE) : n;
     const real* y = mono + R.y;
-    // shared memory: the tile's input window (1024 + 4K samples, circular) de-interleaved into its even and odd
-    // samples (the Bessel taps sit at even lags, so each parity is a dense 25-tap FIR of its own), every four
-    // samples skewed by one slot so that threads working on quads of outputs hit distinct banks.
     real* win = (real*)c.smem;                       // 2 * POST_PAR
     real* coef = win + 2 * POST_PAR;                  // POST_NC (+1)
     real* red = coef + POST_NC + 1;                  // nthr
@@ -121,53 +177,17 @@ MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, uns
     const int len = t1 - t0;
     real m = (real)0.;
     if (mode == 1) {
-        const int W = len + 4 * POST_K;
-        const int w0 = wrap_idx((long long)t0 + R.dr - 2 * POST_K, n);          // one 64-bit modulo per thread
-        for (int j = c.tid; j < W; j += c.nthr) {
-            const int mm = j >> 1;
-            int idx = w0 + j;
-            if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }                  // second wrap only for n < tile
-            win[(j & 1) * POST_PAR + mm + (mm >> 2)] = y[idx];
-        }
-        for (int j = c.tid; j < POST_NC; j += c.nthr) coef[j] = (real)R.coef[j];
-        c.sync();
-        // thread -> parity (warp-uniform) and a quad of consecutive outputs of that parity: 28 loads per 4 outputs
-        for (int u = c.tid; u < OLA_TILE / 4; u += c.nthr) {
-            const int par = u / (OLA_TILE / 8), t = u - par * (OLA_TILE / 8);
-            if (8 * t + par >= len) continue;
-            const real* w = win + par * POST_PAR + 5 * t;     // slot of sample m0 = 4t: 4t + t
-            real a0 = (real)0., a1 = (real)0., a2 = (real)0., a3 = (real)0.;
-            real x0 = w[0], x1 = w[1], x2 = w[2];
-#pragma unroll
-            for (int k = 0; k < POST_NC; ++k) {
-                const real x3 = w[(k + 3) + ((k + 3) >> 2)];
-                const real ck = coef[k];
-                a0 += ck * x0; a1 += ck * x1; a2 += ck * x2; a3 += ck * x3;
-                x0 = x1; x1 = x2; x2 = x3;
-            }
-            const int j0 = 9 * t + par;                  // slot of output j = 8t + par + 2q is j + (j >> 3): stride 9, conflict-free
-            res[j0] = a0; res[j0 + 2] = a1; res[j0 + 4] = a2; res[j0 + 6] = a3;
-        }
-        c.sync();
-        for (int j = c.tid; j < len; j += c.nthr) {
-            const real r = res[j + (j >> 3)];
-            mono[R.rbuf + t0 + j] = r;
-            m = r_max(m, r_max(r_abs(r), r_abs(y[t0 + j])));
-        }
+        post_right_tile(R, y, t0, len, win, coef, res, c);
+        for (int j = c.tid; j < len; j += c.nthr) m = r_max(m, r_max(r_abs(res[j + (j >> 3)]), r_abs(y[t0 + j])));
     } else {
         for (int i = t0 + c.tid; i < t1; i += c.nthr) {
             m = r_max(m, r_abs(y[i]));
             if (mode == 2) m = r_max(m, r_abs(mono[R.rbuf + i]));
         }
     }
-    red[c.tid] = m;
-    c.sync();
-    for (int s = c.nthr >> 1; s > 0; s >>= 1) {
-        if (c.tid < s) red[c.tid] = r_max(red[c.tid], red[c.tid + s]);
-        c.sync();
-    }
+    m = block_max(m, red, c);
     if (c.tid == 0) {
-        union { double f; unsigned long long u; } cv; cv.f = (double)red[0];
+        union { double f; unsigned long long u; } cv; cv.f = (double)m;
 #ifdef MS_HOST_EMUL
         if (cv.u > maxbits[c.by]) maxbits[c.by] = cv.u;
 #else
@@ -178,21 +198,27 @@ MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, uns
 // pass 2: write interleaved stereo, clipped and scaled to the requested peak
 MS_DEV void post_write_body(const PostRender* MS_RESTRICT renders, const real* MS_RESTRICT mono, const unsigned long long* MS_RESTRICT maxbits,
                             float2* MS_RESTRICT out, const Ctx& c) {
-    const PostRender R = renders[c.by];
+    const PostRender& R = renders[c.by];
     const int t0 = c.bx * OLA_TILE;
     if (t0 >= R.n) return;
     const int t1 = (t0 + OLA_TILE) < R.n ? (t0 + OLA_TILE) : R.n;
     const real* y = mono + R.y;
+    real* win = (real*)c.smem;
+    real* coef = win + 2 * POST_PAR;
+    real* res = coef + POST_NC + 1 + OLA_NTHR;
+    const int mode = R.stereo_mode;
+    if (mode == 1) post_right_tile(R, y, t0, t1 - t0, win, coef, res, c);
     union { double f; unsigned long long u; } cv; cv.u = maxbits[c.by];
     const real drive = (real)R.drive, inv_t = (real)R.inv_tanh_drive;
     const real top = soft_clip((real)cv.f, drive, inv_t);
     const real scale = top > (real)0. ? (real)R.peak / top : (real)1.0;
     float2* o = out + R.out;
-    const int dlm = R.stereo_mode ? wrap_idx((long long)R.dl, R.n) : 0;          // left channel = roll(y, dl)
+    const int dlm = mode ? wrap_idx((long long)R.dl, R.n) : 0;          // left channel = roll(y, dl)
     for (int i = t0 + c.tid; i < t1; i += c.nthr) {
         int li = i - dlm; if (li < 0) li += R.n;
         const real l = y[li];
-        const real r = R.stereo_mode ? mono[R.rbuf + i] : y[i];
+        const int j = i - t0;
+        const real r = mode == 1 ? res[j + (j >> 3)] : (mode == 2 ? mono[R.rbuf + i] : y[i]);
         o[i] = make_float2((float)(soft_clip(l, drive, inv_t) * scale), (float)(soft_clip(r, drive, inv_t) * scale));
     }
 }

@@ -282,6 +282,7 @@ class BatchRenderer:
             ev = np.zeros(len(rows), np.dtype(_abi.ResEvt))
             ev["src"], ev["dst"], ev["n"], ev["mode_begin"], ev["mode_count"], ev["decay"] = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3], rows[:, 4], decay
             self.d_res_evt, self.d_res_modes, self.n_res = dev.upload(ev), dev.upload(np.ascontiguousarray(modes)), len(rows)
+            self.h_res_evt = ev
         # cepstral warp: three stages of single-signal jobs around the elementwise steps of ms_cepstral
         self.cep_stages = None
         if t.cep is not None and len(t.cep[0]):
@@ -318,6 +319,7 @@ class BatchRenderer:
             p0 = ev.dtype.fields["pre"][1]
             rawe[:, p0:p0 + pre.shape[1]] = pre
             self.d_cep_evt, self.n_cep, self.cep_max_n, self.cep_zb = dev.upload(ev), N, int(n.max()), zb
+            self.h_cep_evt = ev
         # partial lock: single-signal jobs from the event's raw transient; low-pass / warp are evaluated by the
         # lock kernel on the forward spectrum, the inverse applies what follows it (multiband)
         self.plock_stage = None
@@ -369,7 +371,7 @@ class BatchRenderer:
                     iv = np.zeros(len(imr), np.dtype(_abi.ImprintStepEvt))
                     iv["z"], iv["n"], iv["amount"], iv["smooth"] = zoffs, imr[:, 7].astype(np.int64), imr[:, 9], imr[:, 10]
                     iv["slot"] = [slot_of[int(rr)] for rr in imr[:, 0]]
-                    item.update(n_imp=len(imr), stage=stg, zbase=zbase, d_imp=dev.upload(iv))
+                    item.update(n_imp=len(imr), stage=stg, zbase=zbase, d_imp=dev.upload(iv), h_imp=iv)
                 self.seq_ranks.append(item)
         # spectral imprint: single-signal jobs (Z = the grain's DFT), forward -> per-render moving average -> inverse
         self.imprint_stage, self.n_imprint_renders = None, 0
@@ -388,6 +390,7 @@ class BatchRenderer:
             rr["ev_begin"], rr["ev_end"] = first, last
             rr["amount"], rr["smooth"] = t.imprint_par[renders, 0], t.imprint_par[renders, 1]
             self.d_imp_evt, self.d_imp_render = dev.upload(ev), dev.upload(rr)
+            self.h_imp_evt, self.h_imp_render = ev, rr
             self.n_imprint_renders = len(renders)
             self.imprint_max_bins = int(rows[:, 3].max()) // 2 + 1
             self.imprint_zbase = zbase
@@ -411,12 +414,16 @@ class BatchRenderer:
             print("  _upload: " + " ".join("%s %.1f" % (n, 1e3 * v) for n, v in _tr), flush=True)
 
     # ---- execution -------------------------------------------------------------------------------------
-    def run(self, mark=None):
+    def run(self, mark=None, probe=None):
         """Launch the whole kernel sequence on the current stream.  `mark(name)` (optional) is called
-        after each stage has been enqueued (bench.py records a CUDA event there)."""
+        after each stage has been enqueued (bench.py records a CUDA event there).  `probe(name, item)` (tests only)
+        is called around the stages whose output the reference itself does not determine to rounding (cepstral warp,
+        spectral imprint, resonator sign): the stage-level parity tests read the device buffers there and feed the
+        oracle the SAME input (tests/kernel_checks.py: check_stages)."""
         dev, lib = self.dev, self.api
         st = dev.stream_ptr()
         mark = mark or (lambda name: None)
+        probe = probe or (lambda name, item=None: None)
         if self.n_evt:
             if self.n_normal_evt:
                 _check(dev, lib.ms_synth_normal(dev.ptr(self.d_sy1), self.n_normal_evt, dev.ptr(self.pool), st))
@@ -442,10 +449,12 @@ class BatchRenderer:
                 args = (dev.ptr(self.d_cep_evt), self.n_cep, self.cep_max_n, zp[0], zp[1], zp[2], dev.ptr(self.cep_scratch), st)
                 s1.forward()
                 _check(dev, lib.ms_cepstral(0, *args))
+                probe("cep_x")
                 s2.inverse()
                 _check(dev, lib.ms_cepstral(1, *args))
                 s3.forward()
                 _check(dev, lib.ms_cepstral(2, *args))
+                probe("cep_y")
                 s1.inverse()
                 mark("cepstral_warp")
             if self.plock_stage is not None:
@@ -455,7 +464,10 @@ class BatchRenderer:
                 self.plock_stage.inverse()
                 mark("partial_lock")
             if self.n_res:
+                probe("res_x")
                 _check(dev, lib.ms_resonator(dev.ptr(self.d_res_evt), self.n_res, dev.ptr(self.d_res_modes), dev.ptr(self.pool), st))
+            if self.n_res:
+                probe("res_y")
             if self.n_wg:
                 _check(dev, lib.ms_waveguide(dev.ptr(self.d_wg_evt), self.n_wg, dev.ptr(self.d_wg_lines), dev.ptr(self.pool), st))
             if self.n_res or self.n_wg:
@@ -471,15 +483,19 @@ class BatchRenderer:
                         stg = item["stage"]
                         stg.forward()
                         zptr = C.c_void_p(dev.ptr(stg.ws).value + item["zbase"])
+                        probe("seq_imprint_x", item)
                         _check(dev, lib.ms_imprint_step(dev.ptr(item["d_imp"]), item["n_imp"], self.seq_max_bins, zptr,
                                                         dev.ptr(self.seq_mem), dev.ptr(self.seq_prev_bins), st))
+                        probe("seq_imprint_y", item)
                         stg.inverse()
                 mark("event_feedback")
             if self.imprint_stage is not None:
                 self.imprint_stage.forward()
                 zptr = C.c_void_p(dev.ptr(self.imprint_stage.ws).value + self.imprint_zbase)
+                probe("imprint_x")
                 _check(dev, lib.ms_imprint(dev.ptr(self.d_imp_evt), dev.ptr(self.d_imp_render), self.n_imprint_renders,
                                            self.imprint_max_bins, zptr, st))
+                probe("imprint_y")
                 self.imprint_stage.inverse()
                 mark("spectral_imprint")
         if self.n_env:

@@ -33,6 +33,59 @@ def load_preset(source, ir_audio=None, img_gray=None):
     return p
 
 
+def read_wav(path):
+    """(float64 samples [frames] or [frames, channels], sample rate) of a RIFF/WAVE file: PCM 8/16/24/32 bit scaled to
+    [-1, 1) the way soundfile's default float64 read does (value / 2^(bits-1)), or IEEE float 32/64.  soundfile is not
+    a dependency here."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:4] != b"RIFF" or raw[8:12] != b"WAVE":
+        raise ValueError(f"{path}: not a RIFF/WAVE file")
+    at, fmt, data = 12, None, None
+    while at + 8 <= len(raw):
+        tag, size = raw[at:at + 4], struct.unpack("<I", raw[at + 4:at + 8])[0]
+        body = raw[at + 8:at + 8 + size]
+        if tag == b"fmt ":
+            fmt = struct.unpack("<HHIIHH", body[:16])
+            if fmt[0] == 0xFFFE and len(body) >= 26:            # WAVE_FORMAT_EXTENSIBLE: the sub-format's first two bytes
+                fmt = (struct.unpack("<H", body[24:26])[0],) + fmt[1:]
+        elif tag == b"data":
+            data = body
+        at += 8 + size + (size & 1)
+    if fmt is None or data is None:
+        raise ValueError(f"{path}: missing fmt or data chunk")
+    kind, ch, sr, _, _, bits = fmt
+    if kind == 3:
+        a = np.frombuffer(data, dtype="<f4" if bits == 32 else "<f8").astype(np.float64)
+    elif kind == 1 and bits == 8:
+        a = (np.frombuffer(data, dtype=np.uint8).astype(np.float64) - 128.0) / 128.0
+    elif kind == 1 and bits == 16:
+        a = np.frombuffer(data, dtype="<i2").astype(np.float64) / 32768.0
+    elif kind == 1 and bits == 24:
+        b = np.frombuffer(data[:len(data) // 3 * 3], dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+        v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+        a = np.where(v >= 1 << 23, v - (1 << 24), v).astype(np.float64) / float(1 << 23)
+    elif kind == 1 and bits == 32:
+        a = np.frombuffer(data, dtype="<i4").astype(np.float64) / 2147483648.0
+    else:
+        raise ValueError(f"{path}: unsupported WAVE format {kind}/{bits} bit")
+    if ch > 1:
+        a = a[:a.size // ch * ch].reshape(-1, ch)
+    return a, int(sr)
+
+
+def load_ir_wav(path):
+    """What on_load_ir hands to render() as `_ir_audio` (main_v2.py:1401-1413): the file as float64, the mean over
+    its channels, normalised to a 0.9 peak (normalize, main_v2.py:26-29: untouched when silent).  The file's sample
+    rate is ignored, as in the reference (it is only displayed there)."""
+    a, _ = read_wav(path)
+    a = a.astype(np.float64)
+    if a.ndim > 1:
+        a = a.mean(axis=1)
+    m = float(np.max(np.abs(a))) if a.size else 0.0
+    return a if m <= 0 else a * (0.9 / m)
+
+
 def parse_list(text, cast=float):
     """Comma-separated list of the batch dialog; entries that do not parse are dropped (main_v2.py:1553-1562)."""
     out = []

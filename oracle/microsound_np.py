@@ -185,11 +185,18 @@ def cepstrum_warp(x, factor):
     if n < 64:
         return x
     spec = np.fft.rfft(x)
+    mag = cepstrum_warp_magnitudes(spec, n, factor)
+    return np.fft.irfft(mag * np.exp(1j * np.angle(spec)), n=n)
+
+
+def cepstrum_warp_magnitudes(spec, n, factor):
+    """M:154-161 on a given rfft spectrum: the new magnitudes exp(Re rfft(warped cepstrum)).  Split out so the
+    stage-level parity tests can hand the oracle the SAME spectrum the device kernels saw: in bins the band-limit has
+    emptied, |X| is rounding noise next to the +1e-12, so log|X| there differs between any two FFTs by ~1e-4."""
     cep = np.fft.irfft(np.log(np.abs(spec) + 1e-12), n=n)
     t = np.arange(n, dtype=np.float64)
     warped = np.interp(t / max(1e-12, float(factor)), t, cep, left=0.0, right=0.0)
-    mag = np.exp(np.fft.rfft(warped).real)
-    return np.fft.irfft(mag * np.exp(1j * np.angle(spec)), n=n)
+    return np.exp(np.fft.rfft(warped).real)
 
 
 def resonator_modes(seed, modes, f_min, f_max):
@@ -621,13 +628,16 @@ class ImprintMemory:
         if n < 64 or amount <= 0:
             return x
         spec = np.fft.rfft(x)
-        mag = np.abs(spec)
+        blended = self.blend(np.abs(spec), amount, smooth)
+        return np.fft.irfft(blended * np.exp(1j * np.angle(spec)), n=n)
+
+    def blend(self, mag, amount, smooth):
+        """M:575-579 on given magnitudes: advance the moving average by one grain and return the blended magnitudes."""
         if self.mem is None or self.mem.size != mag.size:
             self.mem = mag.copy()
         else:
             self.mem = smooth * self.mem + (1.0 - smooth) * mag
-        blended = (1.0 - amount) * mag + amount * self.mem
-        return np.fft.irfft(blended * np.exp(1j * np.angle(spec)), n=n)
+        return (1.0 - amount) * mag + amount * self.mem
 
 
 def rounding_noise_floor(params, reference_audio=None):

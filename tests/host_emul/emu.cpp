@@ -22,7 +22,31 @@ static void trampoline() {
     g_done[g_cur] = 1;
     swapcontext(&g_ctx[g_cur], &g_main);
 }
-void yield_barrier() { swapcontext(&g_ctx[g_cur], &g_main); }
+// Counting barriers: a fibre that arrives waits (yielding) until its barrier's generation changes.  Block barriers
+// expect every fibre that has not exited; warp barriers the live fibres of the warp (32 consecutive thread ids), so
+// warps may execute different numbers of warp-level barriers between two block barriers (warp-specialised kernels).
+static int g_blk_cnt = 0; static unsigned g_blk_gen = 0;
+static std::vector<int> g_warp_cnt; static std::vector<unsigned> g_warp_gen;
+static int live_in(int lo, int hi) { int n = 0; for (int t = lo; t < hi && t < g_n; ++t) n += g_done[t] ? 0 : 1; return n; }
+void yield_barrier() {
+    const unsigned gen = g_blk_gen;
+    ++g_blk_cnt;
+    for (;;) {
+        if (g_blk_gen != gen) return;
+        if (g_blk_cnt >= live_in(0, g_n)) { g_blk_cnt = 0; ++g_blk_gen; return; }
+        swapcontext(&g_ctx[g_cur], &g_main);
+    }
+}
+void yield_warp_barrier() {
+    const int w = g_cur >> 5;
+    const unsigned gen = g_warp_gen[w];
+    ++g_warp_cnt[w];
+    for (;;) {
+        if (g_warp_gen[w] != gen) return;
+        if (g_warp_cnt[w] >= live_in(32 * w, 32 * w + 32)) { g_warp_cnt[w] = 0; ++g_warp_gen[w]; return; }
+        swapcontext(&g_ctx[g_cur], &g_main);
+    }
+}
 
 void run(MsDim grid, int block, size_t smem, const std::function<void(const Ctx&)>& body) {
     std::vector<char> shared(smem + 64);
@@ -31,6 +55,7 @@ void run(MsDim grid, int block, size_t smem, const std::function<void(const Ctx&
     for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
         g_ctx.assign(block, ucontext_t());
         g_done.assign(block, 0);
+        g_blk_cnt = 0; g_warp_cnt.assign((block + 31) / 32, 0); g_warp_gen.assign((block + 31) / 32, 0);
         g_tmpl.nthr = block; g_tmpl.bx = (int)bx; g_tmpl.by = (int)by; g_tmpl.smem = shared.data();
         for (int t = 0; t < block; ++t) {
             getcontext(&g_ctx[t]);

@@ -196,15 +196,25 @@ def reference_noise_floor(params, taps):
     return 8.0 * np.finfo(np.float64).eps * float(np.max(np.abs(taps["after_ir"]))) * float(params["sat_drive"])
 
 
-def check_render(dev, params, precision="auto"):
+VACUOUS = 0.05          # 4 x floor above this: the end-to-end tolerance cannot fail on a +-0.98 output
+
+
+def check_render(dev, params, precision="auto", floor=None):
     taps = {}
     err, rms_db, gm, mm = render_error(dev, params, precision, taps)
-    # spectral imprint keeps the phase of bins that hold only rounding noise: that share of the reference's own
-    # output is not reproducible by any other FFT (oracle.imprint_noise_floor measures it by a 1e-15 jitter)
-    floor = O.rounding_noise_floor(params)
+    # cepstral warp / spectral imprint / resonator sign keep the phase of bins that hold only rounding noise: that share
+    # of the reference's own output is not reproducible by any other FFT (oracle.rounding_noise_floor measures it by a
+    # 1e-15 jitter).  Where that makes the end-to-end tolerance vacuous the stages themselves are verified on the
+    # device's own input (check_stages) -- no silent pass.
+    floor = O.rounding_noise_floor(params) if floor is None else floor
     assert err < MAX_ABS_TOL + reference_noise_floor(params, taps) + 4.0 * floor, (err, floor)
     assert rms_db < RMS_DB_TOL or floor > 1e-6, rms_db
     assert (gm < 2e-6 or floor > 1e-6) and mm < 2e-6, (gm, mm)
+    if floor > 1e-6:
+        staged = check_stages(dev, params)
+        print("rounding-noise floor %.3e (4 x floor %s the vacuous bound %.2f): stage-level checks %s" % (
+            floor, ">" if 4.0 * floor > VACUOUS else "<=", VACUOUS, staged))
+        assert staged, "ill-conditioned render with no stage-level coverage"
     return err
 
 
@@ -307,3 +317,98 @@ PRESET_LIKE = {
 }
 
 
+
+
+# ---- stage-level parity where the reference's own output is decided by rounding noise -------------------------------------
+# cepstral_warp (main_v2.py:150-163) and SpectralImprint (565-581) keep the PHASE of every bin and give it a new
+# magnitude; resonator_bank (369-384) multiplies by sign(x).  After a band-limit (every shipped cepstral preset has one)
+# the emptied bins hold ~1e-16 of rounding noise whose phase / sign no other FFT reproduces, so a time-domain comparison
+# of the whole render cannot fail there (oracle.rounding_noise_floor up to 1.9 on a +-0.98 output).  What IS determined
+# is each stage as a function of ITS input: these checks read the device buffers around the stage (engine.run's probe
+# hook), hand the oracle the SAME input and compare magnitudes in every bin and phases where the input is above 1e-9 of
+# its peak, at 1e-9.
+STAGE_TOL = 1e-9
+
+
+def _ws_complex(dev, stage, zbase, z_off, n):
+    raw = np.asarray(dev.download(stage.ws, int(zbase) + 16 * int(z_off), 16 * int(n)))
+    return raw.view(np.complex128).copy()
+
+
+def _phase_close(y, x, tol):
+    big = np.abs(x) > 1e-9 * max(1e-300, float(np.max(np.abs(x))))
+    if not np.any(big):
+        return 0.0
+    ok = big & (np.abs(y) > 0)
+    return float(np.max(np.abs(y[ok] / np.abs(y[ok]) - x[ok] / np.abs(x[ok])))) if np.any(ok) else 0.0
+
+
+def check_stages(dev, params):
+    """Runs one render (float64) with probes around the ill-conditioned stages and checks each against the oracle on
+    the device's own input.  Returns the names of the stages it verified."""
+    br = engine.BatchRenderer([params], device=dev, precision="f64")
+    rp = br.plans[0]
+    seen, hold = [], {}
+
+    def spectra(stage, zbase, evs, zname="z"):
+        return [_ws_complex(dev, stage, zbase, e[zname], e["n"]) for e in evs]
+
+    def probe(name, item=None):
+        dev.synchronize()
+        if name == "cep_x":
+            ev = br.h_cep_evt
+            scr = np.asarray(dev.download(br.cep_scratch, 0, br.cep_scratch.shape[0] if hasattr(br.cep_scratch, "shape") else len(br.cep_scratch)))
+            hold["cep_x"] = [scr[int(e["xp"]):int(e["xp"]) + 2 * (int(e["n"]) // 2 + 1)].view(np.complex128).copy() for e in ev]
+        elif name == "cep_y":
+            ev = br.h_cep_evt
+            ys = spectra(br.cep_stages[0], br.cep_zb[0], ev, "z1")
+            for e, x, y in zip(ev, hold["cep_x"], ys):
+                n = int(e["n"]); bins = n // 2 + 1
+                want = O.cepstrum_warp_magnitudes(x, n, float(e["factor"]))
+                got = np.abs(y[:bins])
+                assert np.max(np.abs(got - want) / want) < STAGE_TOL, ("cepstral magnitudes", n, float(np.max(np.abs(got - want) / want)))
+                assert _phase_close(y[:bins], x, STAGE_TOL) < STAGE_TOL, ("cepstral phases", n)
+            seen.append("cepstral_warp[%d]" % len(ev))
+        elif name == "imprint_x":
+            hold["imp_x"] = spectra(br.imprint_stage, br.imprint_zbase, br.h_imp_evt)
+        elif name == "imprint_y":
+            ys = spectra(br.imprint_stage, br.imprint_zbase, br.h_imp_evt)
+            for r in br.h_imp_render:
+                mem = O.ImprintMemory()
+                for k in range(int(r["ev_begin"]), int(r["ev_end"])):
+                    n = int(br.h_imp_evt[k]["n"]); bins = n // 2 + 1
+                    x, y = hold["imp_x"][k][:bins], ys[k][:bins]
+                    want = mem.blend(np.abs(x), float(r["amount"]), float(r["smooth"]))
+                    sc = max(1e-300, float(np.max(want)))
+                    assert np.max(np.abs(np.abs(y) - want)) / sc < STAGE_TOL, ("imprint magnitudes", k)
+                    assert _phase_close(y, x, STAGE_TOL) < STAGE_TOL, ("imprint phases", k)
+            seen.append("spectral_imprint[%d]" % len(ys))
+        elif name == "seq_imprint_x":
+            hold["seq_x"] = spectra(item["stage"], item["zbase"], item["h_imp"])
+        elif name == "seq_imprint_y":
+            ys = spectra(item["stage"], item["zbase"], item["h_imp"])
+            mems = hold.setdefault("seq_mem", {})
+            for e, x, y in zip(item["h_imp"], hold["seq_x"], ys):
+                n = int(e["n"]); bins = n // 2 + 1
+                mem = mems.setdefault(int(e["slot"]), O.ImprintMemory())
+                want = mem.blend(np.abs(x[:bins]), float(e["amount"]), float(e["smooth"]))
+                sc = max(1e-300, float(np.max(want)))
+                assert np.max(np.abs(np.abs(y[:bins]) - want)) / sc < STAGE_TOL, ("imprint step magnitudes", n)
+                assert _phase_close(y[:bins], x[:bins], STAGE_TOL) < STAGE_TOL, ("imprint step phases", n)
+            seen.append("imprint_step")
+        elif name == "res_x":
+            hold["res_x"] = [np.asarray(dev.download(br.pool, int(e["src"]), int(e["n"]))).astype(np.float64) for e in br.h_res_evt]
+        elif name == "res_y":
+            evs = [ev for ev in rp.events if ev.res is not None]
+            assert len(evs) == len(br.h_res_evt)
+            for e, pe, x in zip(br.h_res_evt, evs, hold["res_x"]):
+                y = np.asarray(dev.download(br.pool, int(e["dst"]), int(e["n"]))).astype(np.float64)
+                want = O.resonator_bank(x, pe.gen_sr, int(params["res_modes"]), float(params["res_fmin"]), float(params["res_fmax"]),
+                                        float(params["res_decay_ms"]), pe.seed)
+                sc = max(1e-300, float(np.max(np.abs(want))))
+                assert np.max(np.abs(y - want)) / sc < STAGE_TOL, ("resonator bank", int(e["n"]), float(np.max(np.abs(y - want)) / sc))
+            seen.append("resonator_bank[%d]" % len(evs))
+    br.run(probe=probe)
+    dev.synchronize()
+    br.close()
+    return seen
