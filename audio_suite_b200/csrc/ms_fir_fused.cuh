@@ -135,7 +135,8 @@ MS_DEV void fir_p1_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
 // conjugated (E[256 - k1][k2] = conj E[k1][255 - k2]).  A tile therefore holds four rows k1 = 4 t + 1 .. 4 t + 4 and
 // their partners 256 - k1: the fold and the extra FFT run for four rows only.  Rows 0 and 128 are their own partners:
 // in tile 31 (k1 = 125 .. 128) the warp that would get row 128 a second time takes row 0, with a fifth folded row.
-// Warps 0-3 transform the folded rows while warps 4-7 fetch the tile, so the two latencies overlap inside the CTA.
+// Warps 0-3 transform the folded rows before their own row; warps 4-7 go straight to theirs and meet them at the barrier
+// in front of the filter product.  (Letting warps 4-7 fetch the whole tile meanwhile was measured slower: 6.0 -> 6.5 ms.)
 #define FF_EROWS 5
 MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, const Ctx& c) {
     cpx* sB = (cpx*)c.smem;                                 // transposing tile + exchange rows
@@ -175,19 +176,18 @@ MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
 #pragma unroll
         for (int w = 0; w < 4; ++w) sE[w * FF_RS + ms_pad(r)] = acc[w];
         if (last) sE[4 * FF_RS + ms_pad(r)] = mk(f0, (real)0.);
-        c.sync();
     }
-    if (!taps || warp >= 4) {
-        // the tile: S[n2][rows of the tile] -> sB[row slot][n2]   (warps 4-7 when the others are busy with E)
-        const int nthr = taps ? FF_NTHR / 2 : FF_NTHR, t0 = taps ? c.tid - FF_NTHR / 2 : c.tid;
-        for (int e = t0; e < FF_N * FF_TILE; e += nthr) {
-            const int n2 = e >> 3, rr = e & 7;
+    {   // the tile: S[n2][rows of the tile] -> sB[row slot][n2]
+#pragma unroll
+        for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
+            const int e = c.tid + FF_NTHR * i, n2 = e >> 3, rr = e & 7;
             int rw = rr < 4 ? k_lo + rr : FF_N - (k_lo + rr - 4);
             if (last && rr == 7) rw = 0;
             sB[rr * FF_RS + ms_pad(n2)] = MS_LDCG(&S[(size_t)n2 * FF_N + rw]);
         }
     }
-    if (taps && (warp < 4 || (last && warp == 7))) {
+    c.sync();
+    if (taps && (warp < 4 || (last && warp == 7))) {        // the warps that own an E row transform it first
         cpx* swE = sE + erow * FF_RS;
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = swE[ms_pad(lane + 32 * q)];
@@ -197,12 +197,12 @@ MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
 #pragma unroll
         for (int m = 0; m < 8; ++m) swE[ms_pad(lane + 32 * m)] = v[m];
     }
-    c.sync();
     cpx* sw = sB + warp * FF_RS;
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
     c.syncwarp();
     warp_fft256(v, sw, T.tw, lane, c);                      // v[m] = Z[row][k2 = lane + 32 m]
+    if (taps) c.sync();                                     // every E row is in place
     {
         const cpx* f = U.filt + (size_t)row * FF_N + lane;
         const cpx* swE = sE + erow * FF_RS;

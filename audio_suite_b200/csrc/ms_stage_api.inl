@@ -58,7 +58,7 @@ struct PostMaxK { static constexpr int MAXT = OLA_NTHR;
     static constexpr int MINB = MS_POSTMAX_MINB;
     static MS_DEV void run(const PostRender* r, real* mono, unsigned long long* mb, const Ctx& c) { post_max_body(r, mono, mb, c); } };
 struct PostWriteK { static constexpr int MAXT = OLA_NTHR;
-    static constexpr int MINB = MS_POSTMAX_MINB;
+    static constexpr int MINB = 1;
     static MS_DEV void run(const PostRender* r, const real* mono, const unsigned long long* mb, float2* out, const Ctx& c) { post_write_body(r, mono, mb, out, c); } };
 struct RollK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
@@ -163,7 +163,7 @@ extern "C" int MS_API(ms_post)(const ms_post_render* renders, int n_renders, int
     if (ms_memset(maxbits, 0, sizeof(uint64_t) * (size_t)n_renders, (ms_stream_t)stream)) return -1;
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostMaxK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, (2 * POST_PAR + POST_NC + 1 + OLA_NTHR + OLA_TILE + OLA_TILE / 8 + 8) * sizeof(real), (ms_stream_t)stream,
                                    renders + _y0, mono, (unsigned long long*)maxbits + _y0)) return -1; })
-    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostWriteK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, (2 * POST_PAR + POST_NC + 1 + OLA_NTHR + OLA_TILE + OLA_TILE / 8 + 8) * sizeof(real), (ms_stream_t)stream,
+    MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<PostWriteK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream,
                                    renders + _y0, (const real*)mono, (const unsigned long long*)maxbits + _y0, (float2*)out)) return -1; })
     return 0;
 }

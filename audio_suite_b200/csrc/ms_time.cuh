@@ -105,8 +105,9 @@ MS_DEV real soft_clip(real v, real drive, real inv_t) { return drive > (real)0. 
 // even lags).  The tile's input window (1024 + 4K samples, circular) is staged in shared memory de-interleaved into
 // its even and odd samples (each parity is a dense 25-tap FIR of its own), every four samples skewed by one slot so
 // that threads working on quads of outputs hit distinct banks; results land in `res` (slot of output j: j + (j >> 3)).
-// Both passes call it: recomputing the taps in pass 2 is cheaper than a write + read of the right channel through HBM
-// (40 N -> 24 N bytes per render).
+// Pass 1 keeps the result at rbuf for pass 2.  (Recomputing the taps in pass 2 instead -- 40 N -> 24 N bytes of HBM
+// traffic per render -- was measured SLOWER on B200: max pass 2.66 -> 2.40 ms but write pass 2.18 -> 3.00 ms.  These
+// passes are bound by the per-tile latency chain (stage, barrier, taps, barrier), not by bandwidth.)
 MS_DEV void post_right_tile(const PostRender& R, const real* MS_RESTRICT y, int t0, int len, real* win, real* coef, real* res, const Ctx& c) {
     const int n = R.n;
     const int W = len + 4 * POST_K;
@@ -178,7 +179,11 @@ MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, uns
     real m = (real)0.;
     if (mode == 1) {
         post_right_tile(R, y, t0, len, win, coef, res, c);
-        for (int j = c.tid; j < len; j += c.nthr) m = r_max(m, r_max(r_abs(res[j + (j >> 3)]), r_abs(y[t0 + j])));
+        for (int j = c.tid; j < len; j += c.nthr) {
+            const real r = res[j + (j >> 3)];
+            mono[R.rbuf + t0 + j] = r;
+            m = r_max(m, r_max(r_abs(r), r_abs(y[t0 + j])));
+        }
     } else {
         for (int i = t0 + c.tid; i < t1; i += c.nthr) {
             m = r_max(m, r_abs(y[i]));
@@ -203,11 +208,7 @@ MS_DEV void post_write_body(const PostRender* MS_RESTRICT renders, const real* M
     if (t0 >= R.n) return;
     const int t1 = (t0 + OLA_TILE) < R.n ? (t0 + OLA_TILE) : R.n;
     const real* y = mono + R.y;
-    real* win = (real*)c.smem;
-    real* coef = win + 2 * POST_PAR;
-    real* res = coef + POST_NC + 1 + OLA_NTHR;
     const int mode = R.stereo_mode;
-    if (mode == 1) post_right_tile(R, y, t0, t1 - t0, win, coef, res, c);
     union { double f; unsigned long long u; } cv; cv.u = maxbits[c.by];
     const real drive = (real)R.drive, inv_t = (real)R.inv_tanh_drive;
     const real top = soft_clip((real)cv.f, drive, inv_t);
@@ -217,8 +218,7 @@ MS_DEV void post_write_body(const PostRender* MS_RESTRICT renders, const real* M
     for (int i = t0 + c.tid; i < t1; i += c.nthr) {
         int li = i - dlm; if (li < 0) li += R.n;
         const real l = y[li];
-        const int j = i - t0;
-        const real r = mode == 1 ? res[j + (j >> 3)] : (mode == 2 ? mono[R.rbuf + i] : y[i]);
+        const real r = mode ? mono[R.rbuf + i] : y[i];
         o[i] = make_float2((float)(soft_clip(l, drive, inv_t) * scale), (float)(soft_clip(r, drive, inv_t) * scale));
     }
 }

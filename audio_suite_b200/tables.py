@@ -337,7 +337,8 @@ def pack_chunk(plans) -> Tables:
         if rp.stereo_on:
             dl, dr = rp.stereo_dl, rp.stereo_dr
             if n % 2 == 0:
-                mode, coef, rbuf = 1, bessel_coeffs(rp.stereo_theta), 0       # right channel: 25 taps, evaluated by both post passes
+                mode, coef, rbuf = 1, bessel_coeffs(rp.stereo_theta), 2 * plane + extra     # right channel, written by the max pass
+                extra += n
             else:
                 mode, rbuf = 2, 2 * plane + extra + n                                        # [rolled copy | right channel]
                 odd.append((y, 2 * plane + extra, n, dr))
