@@ -87,9 +87,18 @@ MS_DEV void warp_fft256(cpx* v, cpx* sw, const cpx* MS_RESTRICT tw, int lane, co
         }
     }
 }
-// v[m] *= W_65536^(a (lane + 32 m)):  base W^(a lane), step W^(32 a), powers by a depth-4 product tree
+// W_65536^e = exp(-2 pi i e / 65536) from the unit itself (sincospi of an exactly representable argument).  Profiling
+// (ncu, B200) showed these kernels bound by LSU wavefronts, not by the FP64 pipe: a table lookup at a per-lane address
+// costs up to 32 wavefronts per warp instruction, ~45 FP64 instructions cost a third of that in SM time.
+MS_DEV cpx w65536(unsigned e) {
+    real sn, cs;
+    r_sincospi((real)(e & 65535u) * (real)(1.0 / 32768.0), &sn, &cs);
+    return mk(cs, -sn);
+}
+// v[m] *= W_65536^(a (lane + 32 m)):  base W^(a lane) per lane, step W^(32 a) (warp-uniform: one broadcast lookup),
+// powers by a depth-4 product tree
 MS_DEV void twiddle_row(cpx* v, const FirTables& T, int a, int lane) {
-    const cpx base = tw2level(T.twM_hi, T.twM_lo, (unsigned)(a * lane) & 65535u);
+    const cpx base = w65536((unsigned)(a * lane));
     const cpx st1 = tw2level(T.twM_hi, T.twM_lo, (unsigned)(32 * a) & 65535u);
     const cpx st2 = c_mul(st1, st1);
     cpx t0 = base, t1 = c_mul(base, st1);
@@ -138,6 +147,34 @@ MS_DEV void fir_p1_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
 // Warps 0-3 transform the folded rows before their own row; warps 4-7 go straight to theirs and meet them at the barrier
 // in front of the filter product.  (Letting warps 4-7 fetch the whole tile meanwhile was measured slower: 6.0 -> 6.5 ms.)
 #define FF_EROWS 5
+// fold: F[k1][r] = sum over taps with off = r (mod 256) of g W_65536^(off k1); a thread owns one residue for the tile's
+// four rows (W^(off k1) steps by W^off from row to row).  Residues are handed out by descending tap count (perm), so
+// the lanes of a warp run the same number of iterations.  Out of line: its registers (two sincospi per tap) stay out
+// of the transform code's allocation.
+MS_DEV_NOINLINE void fir_fold_taps(const int* MS_RESTRICT rp, const int* MS_RESTRICT tap_off, const real* MS_RESTRICT tap_gain,
+                                   cpx* sE, int k_lo, int last, int tid) {
+    const int r = __ldg(&rp[257 + tid]);
+    const int t_begin = __ldg(&rp[r]), t_end = __ldg(&rp[r + 1]);
+    cpx acc[4];
+    real f0 = (real)0.;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) acc[w] = c_zero();
+    for (int t = t_begin; t < t_end; ++t) {
+        const unsigned off = (unsigned)__ldg(&tap_off[t]);
+        const real g = __ldg(&tap_gain[t]);
+        cpx tw = w65536(off * (unsigned)k_lo);
+        const cpx st = w65536(off);
+        f0 += g;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            acc[w] = mk(acc[w].x + g * tw.x, acc[w].y + g * tw.y);
+            if (w < 3) tw = c_mul(tw, st);
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) sE[w * FF_RS + ms_pad(r)] = acc[w];
+    if (last) sE[4 * FF_RS + ms_pad(r)] = mk(f0, (real)0.);
+}
 MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, const Ctx& c) {
     cpx* sB = (cpx*)c.smem;                                 // transposing tile + exchange rows
     cpx* sE = sB + FF_TILE * FF_RS;                         // E rows (natural order k2): four + row 0 in the last tile
@@ -150,33 +187,7 @@ MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
     if (last && warp == 7) { row = 0; erow = 4; rev = 0; }
     const int taps = U.tap_res >= 0;
     cpx v[8];
-    if (taps) {
-        // fold: F[k1][r] = sum over taps with off = r (mod 256) of g W_65536^(off k1); a thread owns one residue for the
-        // tile's four rows (W^(off k1) steps by W^off from row to row).  Residues are handed out by descending tap count
-        // (perm), so the lanes of a warp run the same number of iterations.
-        const int* rp = T.res_ptr + U.tap_res;
-        const int r = __ldg(&rp[257 + c.tid]);
-        const int t_begin = __ldg(&rp[r]), t_end = __ldg(&rp[r + 1]);
-        cpx acc[4];
-        real f0 = (real)0.;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) acc[w] = c_zero();
-        for (int t = t_begin; t < t_end; ++t) {
-            const unsigned off = (unsigned)__ldg(&T.tap_off[t]);
-            const real g = __ldg(&T.tap_gain[t]);
-            cpx tw = tw2level(T.twM_hi, T.twM_lo, (off * (unsigned)k_lo) & 65535u);
-            const cpx st = tw2level(T.twM_hi, T.twM_lo, off & 65535u);
-            f0 += g;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                acc[w] = mk(acc[w].x + g * tw.x, acc[w].y + g * tw.y);
-                if (w < 3) tw = c_mul(tw, st);
-            }
-        }
-#pragma unroll
-        for (int w = 0; w < 4; ++w) sE[w * FF_RS + ms_pad(r)] = acc[w];
-        if (last) sE[4 * FF_RS + ms_pad(r)] = mk(f0, (real)0.);
-    }
+    if (taps) fir_fold_taps(T.res_ptr + U.tap_res, T.tap_off, T.tap_gain, sE, k_lo, last, c.tid);
     {   // the tile: S[n2][rows of the tile] -> sB[row slot][n2]
 #pragma unroll
         for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
