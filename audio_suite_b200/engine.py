@@ -515,6 +515,33 @@ class BatchRenderer:
                                 dev.ptr(self.maxbits), dev.ptr(self.out), st))
         mark("post")
 
+    # ---- CUDA graph ------------------------------------------------------------------------------------
+    def capture(self):
+        """Capture the launch sequence of run() into a CUDA graph (the ~50 launches of a step become one graph launch:
+        small slices stop being launch-bound).  The tables are resident and nothing in run() allocates or synchronises,
+        so the sequence is capturable once it has run eagerly (kernel attributes and library tables are then in place)."""
+        torch = self.dev.torch
+        self.run()
+        self.dev.synchronize()
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(self.dev.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev.dev))
+        n0 = self.dev.lib.ms_launch_count()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                self.run()
+        torch.cuda.current_stream(self.dev.dev).wait_stream(side)
+        self.graph, self.graph_launches = g, int(self.dev.lib.ms_launch_count() - n0)      # kernel nodes one replay launches
+        return g
+
+    graph, graph_launches = None, 0
+
+    def replay(self):
+        """run() through the captured graph (capture() first)."""
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+
     # ---- results ---------------------------------------------------------------------------------------
     def output(self, r):
         """float32 [out_n, 2] of render r (host copy)."""
@@ -552,8 +579,8 @@ class BatchRenderer:
 def render(params, progress=None, device=None, precision="auto"):
     """Drop-in for reference render() (main_v2.py:588-792)."""
     br = BatchRenderer([params], device=device, precision=precision)
-    rp = br.plans[0]
     if progress:
+        rp = br.plans[0] if br.plans else P.plan_render(params)        # (the native planner keeps no per-event records)
         progress(0, f"Output SR {rp.base_sr} Hz | Design SR {rp.design_sr_base} Hz")
     br.run()
     if progress:

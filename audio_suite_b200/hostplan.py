@@ -213,3 +213,25 @@ def plan_chunk(params_list):
     t.pool_n, t.mono_n, t.frames, t.h_total, t.max_h, t.max_out_n, t.env_n = (int(v) for v in sc[:7])
     t.alg = dict(zip(("synth", "tilt_spectral", "grain_spectral", "overlap_add", "fir_in", "fir_taps", "post"), (int(v) for v in sc[7:])))
     return t
+
+
+_POOL = None
+
+
+def plan_slice(params_list, threads=None):
+    """plan_chunk over a slice, split across a few threads (the native call releases the GIL; marshalling does not) and
+    merged with tables.merge_chunks -- the same relocation the worker-process path uses."""
+    from . import tables as T
+    n = len(params_list)
+    if threads is None:
+        threads = int(os.environ.get("MS_PLAN_THREADS", "0")) or max(1, min(8, (len(os.sched_getaffinity(0)) - 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    parts = max(1, min(threads, n // 64))
+    if parts <= 1:
+        return plan_chunk(params_list)
+    global _POOL
+    if _POOL is None or _POOL._max_workers < parts:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=max(parts, 8), thread_name_prefix="ms-hostplan")
+    cuts = [n * i // parts for i in range(parts + 1)]
+    subs = list(_POOL.map(plan_chunk, [params_list[a:b] for a, b in zip(cuts[:-1], cuts[1:])]))
+    return T.merge_chunks(subs)

@@ -32,6 +32,27 @@ def balanced_partition(costs, world: int):
     return [sorted(o) for o in owners]
 
 
+def balanced_equal_partition(costs, world: int):
+    """Equal COUNTS per rank (so the rendered slabs gather as equal-shape buffers), near-equal cost: renders sorted by
+    cost are dealt to the ranks in snake order.  Returns a list of sorted index lists; the counts differ by at most one."""
+    order = np.argsort(-np.asarray(costs, dtype=np.float64), kind="stable").tolist()
+    owners = [[] for _ in range(world)]
+    for k, i in enumerate(order):
+        rnd, pos = divmod(k, world)
+        owners[pos if rnd % 2 == 0 else world - 1 - pos].append(i)
+    return [sorted(o) for o in owners]
+
+
+def param_cost(p):
+    """Cost estimate of one render from its parameters alone (no planning): the per-output-frame tail plus, per expected
+    event, the grain's FFT work.  Used to balance a sweep over the ranks before anything is planned."""
+    base_sr = float(p["base_sr"])
+    out_n = max(1.0, float(p["out_dur_s"]) * base_sr)
+    n = max(16.0, base_sr * max(1.0, float(p["time_unfold"])) * float(p["micro_ms"]) / 1000.0)
+    events = 1.0 if p["event_process"] == "Single" else max(1.0, min(float(p["max_grains"]), float(p["grains_per_sec"]) * float(p["out_dur_s"])))
+    return 56.0 * out_n + events * n * (20.0 + 8.0 * float(np.log2(max(2.0, n))))
+
+
 def render_cost(plan):
     c = 56.0 * plan.out_n
     for ev in plan.events:

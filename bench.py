@@ -43,9 +43,10 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=48, help="renders timed for cpu_baseline (rank 0, N=1)")
     ap.add_argument("--chunk", type=int, default=512, help="renders per streamed slice of the end-to-end run")
-    ap.add_argument("--slices", type=int, default=1,
-                    help="N>1: parts per rank whose gather overlaps the next part's rendering (measured on 8 B200: 4 slices "
-                         "12.0 ms/step vs 10.5 ms unsliced -- the parts get launch-bound -- so the default is 1)")
+    ap.add_argument("--slices", type=int, default=0,
+                    help="N>1: parts per rank whose gather overlaps the next part's rendering; each part replays a CUDA graph of "
+                         "its launch sequence, so small parts are not launch-bound.  0 = auto (1 at N=1, 4 at N>1)")
+    ap.add_argument("--no-graph", action="store_true", help="N>1: launch the parts eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather of rendered buffers (N>1)")
     return ap.parse_args()
 
@@ -210,10 +211,20 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = engine.CudaDevice(local)
-    mine = list(parallel.partition(args.renders, world, rank))
-    frames_per_rank = [len(parallel.partition(args.renders, world, r)) * FRAMES_PER_RENDER for r in range(world)]
     ir = configs.synth_ir(5.0, 48000, 303)
-    params = [configs.c5_params(i, shared_ir=ir) for i in mine]
+    if world > 1:
+        # equal counts per rank (equal-shape slabs for the gather), near-equal predicted cost: every rank derives the same
+        # partition from the parameters alone (parallel.param_cost), no communication
+        everything = [configs.c5_params(i, shared_ir=ir) for i in range(args.renders)]
+        owners = parallel.balanced_equal_partition([parallel.param_cost(p) for p in everything], world)
+        mine = owners[rank]
+        frames_per_rank = [len(o) * FRAMES_PER_RENDER for o in owners]
+        params = [everything[i] for i in mine]
+        del everything
+    else:
+        mine = list(range(args.renders))
+        frames_per_rank = [len(mine) * FRAMES_PER_RENDER]
+        params = [configs.c5_params(i, shared_ir=ir) for i in mine]
 
     def barrier():
         if world > 1:
@@ -223,18 +234,26 @@ def run_ours(args):
     # ---- device-resident plan: kernels only.  With several ranks every rank renders its share in `--slices` parts
     #      and the NCCL gather of part k runs while part k+1 renders (parallel.SlicedGather).
     gather = world > 1 and not args.no_gather
-    slices = args.slices if (gather and len(mine) % args.slices == 0 and len(set(frames_per_rank)) == 1) else 1
+    want = args.slices if args.slices > 0 else (4 if world > 1 else 1)
+    slices = want if (gather and len(mine) % want == 0 and len(set(frames_per_rank)) == 1) else 1
+    use_graph = world > 1 and not args.no_graph
     per = len(mine) // slices
     brs = [engine.BatchRenderer(params[k * per:(k + 1) * per], device=dev, precision=args.precision) for k in range(slices)]
     br = brs[0]
     sg = parallel.SlicedGather([per * FRAMES_PER_RENDER] * slices, dist, rank, world, dev.dev) if gather else None
+    if use_graph:
+        for b in brs:
+            b.capture()
 
-    def step(mark=None):
+    def step(mark=None, with_gather=True):
         for k, b in enumerate(brs):
-            b.run(mark)
-            if sg is not None:
+            if use_graph and mark is None:
+                b.replay()
+            else:
+                b.run(mark)
+            if sg is not None and with_gather:
                 sg.start(k, b.outputs_device())
-        if sg is not None:
+        if sg is not None and with_gather:
             sg.finish()
 
     for _ in range(max(3, args.warmup)):
@@ -261,13 +280,45 @@ def run_ours(args):
             ev.record()
             evs.append(ev)
             names.append(name)
-        step(mark)
-        stage_names, _ = names, stage_ev.append(evs)
+        if use_graph:
+            step()                      # graph replays: no per-stage events inside the timed region (taken below, untimed)
+        else:
+            step(mark)
+            stage_names, _ = names, stage_ev.append(evs)
     e1.record()
     barrier()
     torch.cuda.profiler.stop()
     wall1 = time.time()
+    render_only_ms = None
+    if use_graph or gather:
+        # the same steps without the gather (render only), and one eager pass for the per-stage events: both untimed extras
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for s in range(args.steps):
+            step(with_gather=False)
+        r1.record()
+        barrier()
+        t = torch.tensor([r0.elapsed_time(r1) / args.steps], dtype=torch.float64, device=dev.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        render_only_ms = float(t.item())
+        if use_graph:
+            evs = [torch.cuda.Event(enable_timing=True)]
+            evs[0].record()
+            names = []
+
+            def mark(name, evs=evs, names=names):
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                evs.append(ev)
+                names.append(name)
+            for b in brs:
+                b.run(mark)
+            torch.cuda.synchronize()
+            stage_names, stage_ev = names, [evs]
     launches = (dev.lib.ms_launch_count() - launches0) // args.steps
+    if use_graph:
+        launches = sum(b.graph_launches for b in brs)          # kernel nodes replayed per step (the library counter only sees captures)
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], dtype=torch.float64, device=dev.dev)
     if world > 1:
@@ -277,7 +328,7 @@ def run_ours(args):
     stage_ms = {}
     for evs in stage_ev:
         for name, a, b in zip(stage_names, evs[:-1], evs[1:]):
-            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / args.steps
+            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / len(stage_ev)
 
     # ---- individual kernels of one step: the library calls a hook after every launch, a CUDA event is recorded
     #      there (on the launching stream), consecutive events bracket one kernel.  Separate untimed steps, so
@@ -369,7 +420,11 @@ def run_ours(args):
                 "dtype": br.precision, "data": "synthetic",
                 "config": workload_config(args, {"precision_rule": "auto = f64 (engine.choose_precision)" if args.precision == "auto" else args.precision,
                                                  "gather": ("NCCL gather of rendered buffers to rank 0 inside the step, %d slices per rank, "
-                                                            "slice k gathered while slice k+1 renders" % slices) if gather else "none"}),
+                                                            "slice k gathered while slice k+1 renders; %s" % (
+                                                                slices, "each slice replays a CUDA graph of its launch sequence" if use_graph else "eager launches")) if gather else "none",
+                                                 "partition": "equal counts, cost-balanced by parameters (parallel.balanced_equal_partition)" if world > 1 else "single rank",
+                                                 "e2e_note": "at N>1 every rank drains its own shard to its own pinned host buffer: the end-to-end result stays sharded on the host (no gather)" if world > 1 else "single rank"}),
+                "ms_per_step_render_only": render_only_ms,
                 "frames_per_s": value / 2.0,
                 "gpu_launches": int(launches),
                 "clocks": clocks,

@@ -412,3 +412,43 @@ def check_stages(dev, params):
     dev.synchronize()
     br.close()
     return seen
+
+
+# ---- the 27 shipped presets, from the fixture the unmodified reference wrote (oracle/make_golden_presets.py) ----------------
+def preset_fixture():
+    """{name: (params, audio[::step] float32, step, rounding-noise floor, [(pct, msg), ...])} for every shipped preset:
+    parameters exactly as on_load_preset merges them (main_v2.py:1286-1291), 2 s renders of the reference."""
+    import json
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "presets.npz"))
+    out = {}
+    for name in json.loads(str(g["names"])):
+        p = json.loads(str(g["params_" + name]))
+        p["_ir_audio"], p["_img_gray"] = None, None
+        ir = str(g["ir_of_" + name])
+        if ir:
+            p["_ir_audio"] = np.array(g["ir_" + ir])
+        if p["gen_mode"] == "Image scanline":
+            p["_img_gray"] = np.array(g["img_gray"])
+        out[name] = (p, np.array(g["audio_" + name]), int(g["step"]), float(g["floor_" + name]),
+                     [tuple(x) for x in json.loads(str(g["progress_" + name]))])
+    return out
+
+
+def check_preset(dev, name, fixture=None):
+    """One shipped preset through render(): audio against the reference's, progress messages identical, and -- where
+    the reference's own output is decided by rounding noise -- the stage-level checks on the device's own input."""
+    p, want, step, floor, msgs = (fixture or preset_fixture())[name]
+    seen = []
+    out, meta = engine.render(p, progress=lambda pct, msg: seen.append((int(pct), str(msg))), device=dev)
+    assert seen == msgs, (name, seen[:3], msgs[:3])
+    assert out.shape[0] == int(round(p["out_dur_s"] * p["base_sr"])) and meta["out_sr"] == int(p["base_sr"])
+    err = float(np.max(np.abs(out[::step] - want.astype(np.float64))))
+    assert err < MAX_ABS_TOL + 1e-7 + 4.0 * floor, (name, err, floor)          # 1e-7: the fixture stores float32
+    staged = []
+    if floor > 1e-6:
+        staged = check_stages(dev, p)
+        assert staged, name
+    print("preset %-28s max-abs %.2e  floor %.2e  stage checks %s" % (name, err, floor, staged or "-"))
+    return err

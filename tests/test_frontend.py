@@ -48,3 +48,51 @@ def test_batch_render_through_the_engine(emul, tmp_path):
     assert len(out) == 4 and seen[-1] == (4, 4)
     assert all(os.path.getsize(p) == 12 + 8 + 16 + 12 + 8 + 2400 * 2 * 4 for _, p in out)
     assert out[0][0] == "ms_seed5_unf20_st1_48000Hzpwav"
+
+
+def test_ir_loader_follows_on_load_ir(tmp_path):
+    """frontend.load_ir_wav = on_load_ir (main_v2.py:1401-1413): float64, mean over channels, normalise to 0.9, rate
+    ignored; PCM 16 / 24 / 32 bit and float32 files; the shipped IRs give what the reference's rule gives."""
+    import wave
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-0.5, 0.5, (300, 2))
+    frontend.write_wav_float32(str(tmp_path / "f.wav"), x, 44100)
+    a, sr = frontend.read_wav(str(tmp_path / "f.wav"))
+    assert sr == 44100 and np.array_equal(a, x.astype(np.float32).astype(np.float64))
+    ir = frontend.load_ir_wav(str(tmp_path / "f.wav"))
+    mono = x.astype(np.float32).astype(np.float64).mean(axis=1)
+    assert ir.ndim == 1 and np.allclose(ir, mono * (0.9 / np.max(np.abs(mono))), rtol=0, atol=1e-15) and abs(np.max(np.abs(ir)) - 0.9) < 1e-12
+    q = np.round(x[:, 0] * 32767).astype("<i2")
+    with wave.open(str(tmp_path / "p16.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(48000); w.writeframes(q.tobytes())
+    a, _ = frontend.read_wav(str(tmp_path / "p16.wav"))
+    assert np.array_equal(a, q.astype(np.float64) / 32768.0)
+    q24 = np.round(x[:, 0] * (2 ** 23 - 1)).astype(np.int32)
+    raw = b"".join(int(v & 0xFFFFFF).to_bytes(3, "little") for v in q24)
+    with wave.open(str(tmp_path / "p24.wav"), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(3); w.setframerate(48000); w.writeframes(raw)
+    a, _ = frontend.read_wav(str(tmp_path / "p24.wav"))
+    assert np.array_equal(a, q24.astype(np.float64) / float(2 ** 23))
+    from oracle import ref_loader
+    if ref_loader.available():
+        import glob
+        ref = ref_loader.load()
+        for f in glob.glob(os.path.join(ref_loader.REFERENCE_ROOT, "microsound_0.2.1", "irs", "*.wav")):
+            with wave.open(f, "rb") as w:
+                s = np.frombuffer(w.readframes(w.getnframes()), "<i2").astype(np.float64) / 32768.0
+                s = s.reshape(-1, w.getnchannels()).mean(axis=1) if w.getnchannels() > 1 else s
+            assert np.array_equal(frontend.load_ir_wav(f), ref.normalize(s, 0.9)), f
+
+
+def test_shipped_preset_files_merge_like_on_load_preset():
+    from oracle import ref_loader
+    import glob
+    import json
+    if not ref_loader.available():
+        return
+    files = sorted(glob.glob(os.path.join(ref_loader.REFERENCE_ROOT, "microsound_0.2.1", "presets", "*.json")))
+    assert len(files) == 27
+    for f in files:
+        p = frontend.load_preset(f)
+        raw = json.load(open(f))
+        assert all(p[k] == v for k, v in raw.items()) and set(configs.FACTORY_DEFAULTS) <= set(p)

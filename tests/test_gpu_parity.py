@@ -209,7 +209,7 @@ def test_full_size_c4_against_the_reference(cuda_dev):
     windows, the channel sums and the peak."""
     p = configs.canonical("C4")
     br = engine.BatchRenderer([p], device=cuda_dev)
-    assert len(br.plans[0].events) == 1222 and br.plans[0].out_n == 57_600_000
+    assert br.n_evt == 1222 and int(br.tables.out_n[0]) == 57_600_000
     br.run()
     out = br.outputs_device().view(-1, 2)
     assert bool(out.isfinite().all())
@@ -231,3 +231,58 @@ def test_full_size_c4_against_the_reference(cuda_dev):
     meta = br.meta(0)
     assert meta["design_sr_base"] == int(g["design_sr_base"]) == 30_000_000
     br.close()
+
+
+# ---- round 2: the shipped presets from the real files, the regimes the verdict found untested ------------------------------
+_PRESETS = None
+
+
+def _presets():
+    global _PRESETS
+    if _PRESETS is None:
+        _PRESETS = K.preset_fixture()
+    return _PRESETS
+
+
+@pytest.mark.parametrize("name", sorted(K.preset_fixture()))
+def test_shipped_preset_from_the_reference_fixture(cuda_dev, name):
+    """All 27 microsound_0.2.1/presets/*.json (merged over the factory defaults, shipped IRs via on_load_ir's rule)
+    against 2 s renders of the unmodified reference: audio, progress messages (incl. the 'IR fragment' / 'Image line y=..'
+    notes, main_v2.py:758) and, for the seven presets whose output the reference itself does not determine to rounding,
+    every ill-conditioned stage on the device's own input."""
+    K.check_preset(cuda_dev, name, _presets())
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(gen_mode="Crackle / corona"), dict(gen_mode="Noise burst", bandlimit_roll_hz=0.0),
+                                dict(gen_mode="Micro-chaos", space_ir_on=True, _ir_audio=configs.synth_ir(0.2, 48000, 3))])
+def test_first_placed_sample_survives_the_fir_stage(cuda_dev, kw):
+    """with no grain offset the first placed sample is NOT an exact zero after band-limit / stretch or for the
+    generators without a fade-in; the FIR stage must not blank it (support starts at the event's start)."""
+    p = configs.with_defaults(dict(event_process="Poisson", grain_offset_on=False, er_cloud_on=True, out_dur_s=1.5, grains_per_sec=12.0), **kw)
+    K.check_render(cuda_dev, p, "auto")
+
+
+def test_frontend_batch_render_writes_what_the_reference_renders(cuda_dev, tmp_path):
+    """SURVEY 8(f) rank 3 on the GPU: the batch dialog's sweep (main_v2.py:1578-1593) over a shipped-preset-like base with
+    a loaded IR; every WAV is read back and compared with the oracle's render of the same parameters."""
+    from audio_suite_b200 import frontend
+    ir_path = tmp_path / "ir.wav"
+    frontend.write_wav_float32(str(ir_path), configs.synth_ir(0.2, 48000, 9, channels=2), 44100)
+    base = frontend.load_preset(dict(gen_mode="Resonant strike", event_process="Poisson", out_dur_s=1.0, grains_per_sec=9.0,
+                                     space_ir_on=True), ir_audio=frontend.load_ir_wav(str(ir_path)))
+    written = frontend.batch_render(base, [1001, 1002], [15.0, 22.5], [0.9, 1.2], str(tmp_path / "out"), device=cuda_dev)
+    assert len(written) == 8 and written[0][0] == "ms_seed1001_unf15_st0p9_48000Hzpwav"
+    for (name, path), p in zip(written, frontend.batch_params(base, [1001, 1002], [15.0, 22.5], [0.9, 1.2])):
+        audio, sr = frontend.read_wav(path)
+        ref, _ = O.render(p)
+        assert sr == 48000 and audio.shape == ref.shape
+        assert np.max(np.abs(audio - ref)) < K.MAX_ABS_TOL, name
+
+
+def test_native_and_python_planner_render_the_same_audio(cuda_dev, monkeypatch):
+    ps = [configs.c5_params(i) for i in range(300, 308)]
+    a = engine.render_batch(ps, device=cuda_dev)
+    monkeypatch.setenv("MS_PLAN_PYTHON", "1")
+    b = engine.render_batch(ps, device=cuda_dev)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)

@@ -98,3 +98,43 @@ def test_bessel_taps_reproduce_the_rotation_filter():
         K = (len(c) - 1) // 2
         got = sum(c[K + m] * np.roll(x, -(dr + 2 * m)) for m in range(-K, K + 1))
         assert np.max(np.abs(got - want)) < 1e-12
+
+
+# ---- round 2 ---------------------------------------------------------------------------------------------------------------
+def test_malformed_lane_raises_like_the_reference():
+    """'a:b:c' makes the reference's `t, v = part.split(":")` raise ValueError (main_v2.py:461 sits outside its try)."""
+    from oracle import ref_loader
+    for fn in (P.parse_breakpoints, O.parse_lane) + ((ref_loader.load().parse_breakpoints,) if ref_loader.available() else ()):
+        with pytest.raises(ValueError):
+            fn("0:1:2, 3:4")
+        assert list(fn("0:1, x:2, 3, 4:5")) == [(0.0, 1.0), (4.0, 5.0)]
+
+
+def test_pooled_planning_keeps_the_whole_ir_for_the_fragment_generator():
+    """ADVICE r1 (plan.py _slim_params): gen_ir_fragment draws its 256-sample piece from the WHOLE mono mix, not from the
+    8192 taps the convolution keeps; a 2-D IR of 4..7 rows passes the reference's size >= 8 test (rows x channels)."""
+    from audio_suite_b200 import tables as T
+    ir = configs.synth_ir(1.0, 48000, 21)                       # 48000 x 2
+    for kw in (dict(gen_mode="IR fragment", space_ir_on=True), dict(gen_mode="IR fragment", space_ir_max_samps=0, space_ir_on=True),
+               dict(gen_mode="Gaussian click", space_ir_on=True, _ir_audio=np.ones((5, 2))), dict(gen_mode="IR fragment", _ir_audio=np.ones((5, 2)))):
+        p = configs.with_defaults(dict(event_process="Poisson", out_dur_s=0.5, _ir_audio=ir), **kw)
+        a = T.pack_chunk([P.plan_render(p)])
+        b = T.pack_chunk([P.plan_render(P._slim_params(p))])
+        for name in ("sy1", "ola_e", "fir", "dust_val", "irs", "tap_gain"):
+            x, y = getattr(a, name), getattr(b, name)
+            assert x.shape == y.shape and x.tobytes() == y.tobytes(), (kw, name)
+
+
+def test_streamed_planning_does_not_deadlock_on_large_requests():
+    """ADVICE r1 (tables.py plan_stream): requests larger than the pipe (a 4 MB `_img_gray` per piece) used to block the
+    parent on a write while the worker blocked on its answer.  Requests now leave from a feeder thread."""
+    import threading
+    from audio_suite_b200 import tables as T
+    img = np.random.default_rng(3).integers(0, 256, (2048, 2048)).astype(np.uint8)
+    ps = [configs.with_defaults(gen_mode="Image scanline", seed=i, out_dur_s=0.05, _img_gray=img) for i in range(96)]
+    got = []
+    th = threading.Thread(target=lambda: got.extend(T.plan_stream(ps, 32, workers=2, piece=16)), daemon=True)
+    th.start()
+    th.join(120)
+    T.shutdown_pool()
+    assert not th.is_alive() and len(got) == 3 and sum(len(t.post) for t in got) == 96
