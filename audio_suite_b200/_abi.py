@@ -160,6 +160,7 @@ _STAGES = {
     "ms_fir_destroy": (None, [_P]),
     "ms_post": (_I, [_P, _I, _I, _P, _P, _P, _P]),
     "ms_roll": (_I, [_P, _P, _I, _I, _P]),
+    "ms_polyphase_decimate": (_I, [_P, C.c_int64, _I, _I, _P, _I, _I, _P, C.c_int64, _P]),
 }
 PRECISIONS = ("f32", "f64")
 

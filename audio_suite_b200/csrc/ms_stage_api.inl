@@ -171,6 +171,22 @@ extern "C" int MS_API(ms_roll)(const real* src, real* dst, int n, int shift, voi
     return ms_launch<RollK>(mk_dim(64, 1), 256, 0, (ms_stream_t)stream, src, dst, n, shift);
 }
 
+// ---- EXTENSION: polyphase decimation (see ms_time.cuh; not on the reference's path) -----------------------------------
+struct DecimateK { static constexpr int MAXT = DEC_NTHR; static constexpr int MINB = 1;
+    static MS_DEV void run(const real* x, long long xs, int n, const real* h, int taps, int q, real* y, long long ys, int n_out, const Ctx& c) {
+        decimate_body(x, xs, n, h, taps, q, y, ys, n_out, c); } };
+extern "C" int MS_API(ms_polyphase_decimate)(const real* x, int64_t x_stride, int n, int n_signals, const real* h, int taps, int q,
+                                             real* y, int64_t y_stride, void* stream) {
+    if (taps < 1 || taps > DEC_TAPS_MAX || q < 1 || n < 0) MS_FAIL("ms_polyphase_decimate: unsupported taps %d / factor %d", taps, q);
+    const int n_out = n + taps - 1 <= 0 ? 0 : (n + taps - 1 + q - 1) / q;
+    if (n_out == 0 || n_signals <= 0) return 0;
+    const size_t smem = sizeof(real) * ((size_t)taps + (size_t)(DEC_OUT - 1) * q + taps + DEC_NTHR);
+    if (smem > 200 * 1024) MS_FAIL("ms_polyphase_decimate: window of %zu bytes does not fit shared memory (factor %d, %d taps)", smem, q, taps);
+    MS_FOR_Y_CHUNKS(n_signals, { if (ms_launch<DecimateK>(mk_dim((unsigned)((n_out + DEC_OUT - 1) / DEC_OUT), (unsigned)_yc), DEC_NTHR, smem, (ms_stream_t)stream,
+                                    x + (long long)_y0 * x_stride, (long long)x_stride, n, h, taps, q, y + (long long)_y0 * y_stride, (long long)y_stride, n_out)) return -1; })
+    return 0;
+}
+
 // ---- FIR by overlap-save ----------------------------------------------------------------------------------
 static int ols_block_len(int h_len, int out_n) {
     if (h_len <= 3072) return 8192;

@@ -454,3 +454,60 @@ MS_DEV void imprint_step_body(const ImprintStepEvt* MS_RESTRICT evts, cpx* zbase
 MS_DEV void imprint_commit_body(const ImprintStepEvt* MS_RESTRICT evts, int n_evts, int* prev_bins, const Ctx& c) {
     for (int e = c.bx * c.nthr + c.tid; e < n_evts; e += c.nthr * 64) prev_bins[evts[e].slot] = evts[e].n / 2 + 1;
 }
+
+// ---- EXTENSION (no reference counterpart): band-limited polyphase decimation ---------------------------------
+// Nothing in render() decimates -- the rate change is a relabel (main_v2.py:489-490) and the band-limit is lowpass_fft
+// (main_v2.py:39-59) -- so this stage is OFF the parity path; it exists because north_star names it, and is checked
+// against scipy.signal.upfirdn / resample_poly in float64 ("parity unpinned by the reference").
+//   y[m] = sum_k h[k] x[m q - k]   (upfirdn(h, x, up = 1, down = q): zero-extended input, m < ceil((n + taps - 1) / q))
+// i.e. only the q-th outputs of the FIR are ever formed (the polyphase identity), never the full-rate signal.
+// grid = (ceil(n_out / DEC_OUT), signals), DEC_NTHR threads.  The taps and the tile's input window live in shared
+// memory; a warp forms one output at a time: its lanes stride over the taps (conflict-free: consecutive lanes read
+// consecutive taps and consecutive input samples) and the 32 partial sums are reduced with warp shuffles.
+#define DEC_NTHR 256
+#define DEC_OUT 256                  // outputs per CTA
+#define DEC_TAPS_MAX 4096
+MS_DEV real warp_sum(real v, real* scratch, const Ctx& c) {
+#ifdef MS_HOST_EMUL
+    scratch[c.tid] = v;
+    c.syncwarp();
+    real s = (real)0.;
+    const int w0 = c.tid & ~31;
+    for (int i = 0; i < 32; ++i) s += scratch[w0 + (i ^ 0)];      // same value in every lane, like the xor butterfly
+    c.syncwarp();
+    return s;
+#else
+    (void)scratch; (void)c;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+#endif
+}
+MS_DEV void decimate_body(const real* MS_RESTRICT x, long long x_stride, int n, const real* MS_RESTRICT h, int taps, int q,
+                          real* MS_RESTRICT y, long long y_stride, int n_out, const Ctx& c) {
+    real* sh = (real*)c.smem;                        // taps
+    real* sx = sh + taps;                            // window: (DEC_OUT - 1) q + taps samples, oldest first
+    real* scratch = sx + (DEC_OUT - 1) * q + taps;   // emulator only
+    const real* xs = x + (long long)c.by * x_stride;
+    real* ys = y + (long long)c.by * y_stride;
+    const int m0 = c.bx * DEC_OUT;
+    if (m0 >= n_out) return;
+    const int mcnt = (n_out - m0) < DEC_OUT ? (n_out - m0) : DEC_OUT;
+    const long long first = (long long)m0 * q - (taps - 1);              // input index of window slot 0
+    const int wlen = (mcnt - 1) * q + taps;
+    for (int i = c.tid; i < taps; i += c.nthr) sh[i] = __ldg(&h[i]);
+    for (int i = c.tid; i < wlen; i += c.nthr) {
+        const long long j = first + i;
+        sx[i] = (j >= 0 && j < n) ? __ldg(&xs[j]) : (real)0.;
+    }
+    c.sync();
+    const int lane = c.tid & 31, warp = c.tid >> 5, nwarps = c.nthr >> 5;
+    for (int mm = warp; mm < mcnt; mm += nwarps) {
+        // x[m q - k] sits at window slot (m - m0) q + taps - 1 - k
+        const real* w = sx + mm * q + taps - 1;
+        real acc = (real)0.;
+        for (int k = lane; k < taps; k += 32) acc += sh[k] * w[-k];
+        acc = warp_sum(acc, scratch, c);
+        if (lane == 0) ys[m0 + mm] = acc;
+    }
+}

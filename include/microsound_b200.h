@@ -241,6 +241,13 @@ typedef struct {
 /* ms_post_f32 / ms_post_f64: declared below by MS_DECLARE_API */
 /* ms_roll_f32 / ms_roll_f64: declared below by MS_DECLARE_API */
 
+/* ---- EXTENSION, not on the reference's path: band-limited polyphase decimation.  render() never decimates:
+ *      the rate change is a relabel (main_v2.py:489-490), the band-limit is lowpass_fft (main_v2.py:39-59).  This stage
+ *      exists because the task statement names it; its oracle is scipy.signal.upfirdn / resample_poly in float64, and it
+ *      is "parity unpinned" by the reference.  y[s][m] = sum_k h[k] x[s][m q - k] (zero-extended), m < ceil((n + taps - 1) / q);
+ *      taps <= 4096; x_stride / y_stride: elements between consecutive signals. ---- */
+/* ms_polyphase_decimate_f32 / ms_polyphase_decimate_f64: declared below by MS_DECLARE_API */
+
 /* ---- entry points.  Every stage exists in two precisions with identical signatures except for the
  *      element type of the signal buffers: suffix _f32 (float) and _f64 (double).  The interleaved stereo
  *      output of ms_post is float in both. ---- */
@@ -286,7 +293,9 @@ typedef struct {
     void ms_fir_destroy##SFX(void* handle); \
     int ms_post##SFX(const ms_post_render* dev_renders, int n_renders, int max_n, REAL* mono, uint64_t* maxbits, \
     float* out, void* stream); \
-    int ms_roll##SFX(const REAL* src, REAL* dst, int n, int shift, void* stream);
+    int ms_roll##SFX(const REAL* src, REAL* dst, int n, int shift, void* stream); \
+    int ms_polyphase_decimate##SFX(const REAL* x, int64_t x_stride, int n, int n_signals, const REAL* h, int taps, int q, \
+    REAL* y, int64_t y_stride, void* stream);
 MS_DECLARE_API(_f32, float)
 MS_DECLARE_API(_f64, double)
 
