@@ -411,7 +411,8 @@ class BatchRenderer:
                                                dev.ptr(self.fir_ws), need, dev.stream_ptr(), C.byref(self.fir_handle)))
         _mark("fir_create")
         if _tr is not None:
-            print("  _upload: " + " ".join("%s %.1f" % (n, 1e3 * v) for n, v in _tr), flush=True)
+            import sys as _sys
+            print("  _upload: " + " ".join("%s %.1f" % (n, 1e3 * v) for n, v in _tr), file=_sys.stderr, flush=True)
 
     # ---- execution -------------------------------------------------------------------------------------
     def run(self, mark=None, probe=None):
@@ -707,6 +708,7 @@ def _render_batch(params_list, device=None, precision="auto", host_out=None, chu
         old.close()
     render_batch.last_h2d_bytes = h2d
     if trace is not None:
-        print("\n".join(trace) + "\n  drained at t=%.1f ms" % (1e3 * (_time.perf_counter() - t_start)), flush=True)
+        import sys as _sys
+        print("\n".join(trace) + "\n  drained at t=%.1f ms" % (1e3 * (_time.perf_counter() - t_start)), file=_sys.stderr, flush=True)
     flat = host_out.numpy()
     return [flat[a:a + 2 * n].reshape(n, 2) for a, n in views]

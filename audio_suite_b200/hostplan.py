@@ -83,7 +83,7 @@ _NUM = ("base_sr", "out_dur_s", "time_unfold", "peak", "sat_drive", "stereo_on",
 _NUM_COL = [FIELDS.index(k) for k in _NUM]
 _INT_COL = [FIELDS.index(k) for k in ("base_sr", "seed", "max_grains", "er_taps")]           # int(params[k]) in the reference
 _BOOL_COL = [FIELDS.index(k) for k in ("stereo_on", "nl_warp_on", "bandlimit_on", "grain_offset_on", "er_cloud_on", "space_ir_on")]
-_get_num = None
+_get_num = _get_side = None
 _CLASSIC = "Classic reinterpret"
 
 
@@ -91,9 +91,12 @@ def _marshal(params_list):
     """Parameter dicts -> float64 rows in FIELDS order plus the side tables (lanes, impulse responses, Bessel taps)."""
     import operator
     from . import tables as T
-    global _get_num
+    global _get_num, _get_side
     if _get_num is None:
         _get_num = operator.itemgetter(*_NUM)
+
+        _get_side = operator.itemgetter("gen_mode", "unfold_mode", "event_process", "bp_density", "bp_unfold", "bp_cutoff",
+                                        "bp_stretch", "space_ir_on", "space_ir_max_samps")
     R = len(params_list)
     rows = np.zeros((R, len(FIELDS)), np.float64)
     try:
@@ -116,31 +119,36 @@ def _marshal(params_list):
                 i = lane_of[text] = float(len(lanes))
                 lanes.append(pts)
         return i
-    side = np.zeros((R, 9), np.float64)
+    # the non-numeric fields: one small tuple per render; a sweep repeats the same strings / IR object, so the converted
+    # values are memoised per distinct tuple (arrays enter by id(); the objects themselves are kept alive by `params_list`)
+    uniq, uniq_of, idx = [], {}, []
+    widths = rows[:, 6].tolist()
+    gs = _get_side
     for r, p in enumerate(params_list):
-        ir_id = -1.0
-        if p["space_ir_on"]:
-            dig = p.get("_ir_digest")
-            if dig is not None:
-                taps = dig["taps"]
-            else:
-                ir = p.get("_ir_audio")
-                taps = P._ir_taps(ir, int(p["space_ir_max_samps"])) if ir is not None else None
-            if taps is not None:
-                k = ir_of.get(id(taps))
-                if k is None or irs[k] is not taps:
-                    k = ir_of[id(taps)] = len(irs)
-                    irs.append(taps)
-                ir_id = float(k)
-        w = rows[r, 6]
-        theta = (0.0 if w < 0.0 else 1.0 if w > 1.0 else float(w)) * 0.9
-        b = bess_of.get(theta)
-        if b is None:
-            b = bess_of[theta] = float(len(bess))
-            bess.append(T.bessel_coeffs(theta))
-        side[r] = (_MODE[p["gen_mode"]], 0.0 if p["unfold_mode"] == _CLASSIC else 1.0, _PROCESS[p["event_process"]],
-                   lane_id(p["bp_density"]), lane_id(p["bp_unfold"]), lane_id(p["bp_cutoff"]), lane_id(p["bp_stretch"]), ir_id, b)
-    rows[:, _SIDE_COL] = side
+        ir, dig = p.get("_ir_audio"), p.get("_ir_digest")
+        key = gs(p) + (id(ir), id(dig), widths[r])
+        k = uniq_of.get(key)
+        if k is None:
+            gen_mode, unfold_mode, process, l0, l1, l2, l3, ir_on, max_samps, _, _, w = key
+            ir_id = -1.0
+            if ir_on:
+                taps = dig["taps"] if dig is not None else (P._ir_taps(ir, int(max_samps)) if ir is not None else None)
+                if taps is not None:
+                    j = ir_of.get(id(taps))
+                    if j is None or irs[j] is not taps:
+                        j = ir_of[id(taps)] = len(irs)
+                        irs.append(taps)
+                    ir_id = float(j)
+            theta = (0.0 if w < 0.0 else 1.0 if w > 1.0 else float(w)) * 0.9
+            b = bess_of.get(theta)
+            if b is None:
+                b = bess_of[theta] = float(len(bess))
+                bess.append(T.bessel_coeffs(theta))
+            k = uniq_of[key] = len(uniq)
+            uniq.append((_MODE[gen_mode], 0.0 if unfold_mode == _CLASSIC else 1.0, _PROCESS[process],
+                         lane_id(l0), lane_id(l1), lane_id(l2), lane_id(l3), ir_id, b))
+        idx.append(k)
+    rows[:, _SIDE_COL] = np.array(uniq, dtype=np.float64).reshape(len(uniq), 9)[np.array(idx, dtype=np.intp)]
     lane_ptr = np.zeros(len(lanes) + 1, np.int64)
     for i, pts in enumerate(lanes):
         lane_ptr[i + 1] = lane_ptr[i] + len(pts)

@@ -716,6 +716,16 @@ def plan_stream(params_list, chunk, workers=None, piece=32):
     from . import hostplan
     native = [hostplan.lib() is not None and not os.environ.get("MS_PLAN_PYTHON") and all(hostplan.supported(p) for p in params_list[a:b])
               for a, b in cuts]
+    if all(native) and len(cuts) > 1 and workers > 1:
+        # whole slices are planned ahead by a few threads (slice-level parallelism: marshalling holds the GIL for ~5 us per
+        # render, the native call releases it) and handed over in order; nothing is merged or pickled
+        from concurrent.futures import ThreadPoolExecutor
+        nthr = int(os.environ.get("MS_PLAN_THREADS", "0")) or max(1, min(4, workers))
+        with ThreadPoolExecutor(max_workers=nthr, thread_name_prefix="ms-hostplan") as ex:
+            futs = [ex.submit(hostplan.plan_chunk, params_list[a:b]) for a, b in cuts]
+            for f in futs:
+                yield f.result()
+        return
     if workers <= 1 or all(native):
         for (a, b), nat in zip(cuts, native):
             yield hostplan.plan_slice(params_list[a:b]) if nat else pack_chunk([P.plan_render(p) for p in params_list[a:b]])
