@@ -106,7 +106,12 @@ struct Pcg64 {
     }
 };
 
-static inline double py_round(double x) { return nearbyint(x); }          // Python round(): half to even
+// Python round(): half to even.  In the default rounding mode adding and subtracting 1.5 * 2^52 rounds |x| < 2^51 to the
+// nearest integer, ties to even, exactly like nearbyint() -- without the libm call (this runs per reflection tap).
+static inline double py_round(double x) {
+    if (fabs(x) < 2251799813685248.0) { volatile double t = x + 6755399441055744.0; return t - 6755399441055744.0; }
+    return nearbyint(x);
+}
 static inline double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 enum { F_base_sr, F_out_dur_s, F_time_unfold, F_peak, F_sat_drive, F_stereo_on, F_stereo_width, F_mode, F_micro_ms, F_seed,

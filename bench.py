@@ -47,6 +47,7 @@ def parse():
                     help="N>1: parts per rank whose gather overlaps the next part's rendering; each part replays a CUDA graph of "
                          "its launch sequence, so small parts are not launch-bound.  0 = auto (1 at N=1, 4 at N>1)")
     ap.add_argument("--no-graph", action="store_true", help="N>1: launch the parts eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-pipeline", action="store_true", help="N>1: wait for each pass's gather before the next pass starts")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather of rendered buffers (N>1)")
     return ap.parse_args()
 
@@ -234,18 +235,35 @@ def run_ours(args):
     # ---- device-resident plan: kernels only.  With several ranks every rank renders its share in `--slices` parts
     #      and the NCCL gather of part k runs while part k+1 renders (parallel.SlicedGather).
     gather = world > 1 and not args.no_gather
-    want = args.slices if args.slices > 0 else (4 if world > 1 else 1)
-    slices = want if (gather and len(mine) % want == 0 and len(set(frames_per_rank)) == 1) else 1
-    use_graph = world > 1 and not args.no_graph
+    equal = len(set(frames_per_rank)) == 1
+    want = args.slices if args.slices > 0 else 1
+    slices = want if (gather and len(mine) % want == 0 and equal) else 1
+    # default at N>1: ONE part per rank, eager launches, and the gather of pass k overlapping pass k+1 (two output buffers,
+    # parallel.PipelinedGather).  --slices S > 1: S parts per rank, each a CUDA-graph replay, the gather of part k overlapping
+    # part k+1 of the SAME pass (parallel.SlicedGather) -- measured slower: parts render less efficiently than the whole.
+    pipelined = gather and slices == 1 and equal and not args.no_pipeline
+    use_graph = world > 1 and slices > 1 and not args.no_graph
     per = len(mine) // slices
     brs = [engine.BatchRenderer(params[k * per:(k + 1) * per], device=dev, precision=args.precision) for k in range(slices)]
     br = brs[0]
-    sg = parallel.SlicedGather([per * FRAMES_PER_RENDER] * slices, dist, rank, world, dev.dev) if gather else None
+    sg = pg = None
+    if pipelined:
+        pg = parallel.PipelinedGather(len(mine) * FRAMES_PER_RENDER, dist, rank, world, dev.dev)
+        outs = [br.out, torch.empty_like(br.out)]
+    elif gather:
+        sg = parallel.SlicedGather([per * FRAMES_PER_RENDER] * slices, dist, rank, world, dev.dev)
     if use_graph:
         for b in brs:
             b.capture()
 
     def step(mark=None, with_gather=True):
+        if pg is not None:
+            if with_gather:
+                br.out = outs[pg.slot()]            # the buffer whose previous gather has completed
+            br.run(mark)
+            if with_gather:
+                pg.start(br.outputs_device())
+            return
         for k, b in enumerate(brs):
             if use_graph and mark is None:
                 b.replay()
@@ -256,8 +274,13 @@ def run_ours(args):
         if sg is not None and with_gather:
             sg.finish()
 
+    def drain():
+        if pg is not None:
+            pg.finish()
+
     for _ in range(max(3, args.warmup)):
         step()
+    drain()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -285,6 +308,7 @@ def run_ours(args):
         else:
             step(mark)
             stage_names, _ = names, stage_ev.append(evs)
+    drain()                             # the last pass's gather completes inside the timed region
     e1.record()
     barrier()
     torch.cuda.profiler.stop()
@@ -419,9 +443,11 @@ def run_ours(args):
                 "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": br.precision, "data": "synthetic",
                 "config": workload_config(args, {"precision_rule": "auto = f64 (engine.choose_precision)" if args.precision == "auto" else args.precision,
-                                                 "gather": ("NCCL gather of rendered buffers to rank 0 inside the step, %d slices per rank, "
-                                                            "slice k gathered while slice k+1 renders; %s" % (
-                                                                slices, "each slice replays a CUDA graph of its launch sequence" if use_graph else "eager launches")) if gather else "none",
+                                                 "gather": ("NCCL gather of the rendered buffers to rank 0 inside the timed region; pass k is gathered while pass k+1 "
+                                                            "renders into a second output buffer, the last gather completes before the closing event" if pipelined else
+                                                            ("NCCL gather of rendered buffers to rank 0 inside the step, %d slices per rank, "
+                                                             "slice k gathered while slice k+1 renders; %s" % (
+                                                                 slices, "each slice replays a CUDA graph of its launch sequence" if use_graph else "eager launches"))) if gather else "none",
                                                  "partition": "equal counts, cost-balanced by parameters (parallel.balanced_equal_partition)" if world > 1 else "single rank",
                                                  "e2e_note": "at N>1 every rank drains its own shard to its own pinned host buffer: the end-to-end result stays sharded on the host (no gather)" if world > 1 else "single rank"}),
                 "ms_per_step_render_only": render_only_ms,

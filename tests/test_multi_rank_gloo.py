@@ -29,6 +29,16 @@ def test_balanced_partition_is_a_partition():
     assert max(loads) - min(loads) < 10.0
 
 
+def test_balanced_equal_partition_keeps_counts_equal():
+    costs = np.random.default_rng(1).uniform(1, 10, 4096)
+    owners = parallel.balanced_equal_partition(costs, 8)
+    assert sorted(sum(owners, [])) == list(range(4096)) and {len(o) for o in owners} == {512}
+    loads = [sum(costs[i] for i in o) for o in owners]
+    assert (max(loads) - min(loads)) / np.mean(loads) < 0.01
+    from audio_suite_b200 import configs
+    assert parallel.param_cost(configs.c5_params(3)) > 0
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -68,8 +78,21 @@ def _worker(rank, world, port, n_items, q):
     for k, part in enumerate(parts):
         sg.start(k, part)
     recv = sg.finish()
+    # the default at N>1: pass k is gathered while pass k+1 renders into the other output buffer
+    pg = parallel.PipelinedGather(300, dist, rank, world, torch.device("cpu"))
+    bufs = [torch.zeros(600), torch.zeros(600)]
+    seen = []
+    for k in range(5):
+        s_ = pg.slot()
+        if rank == 0 and k >= 2:
+            seen.append([float(pg.recv[s_][r][0]) for r in range(world)])       # pass k-2, complete before its buffer is reused
+        bufs[s_].fill_(float(100 * k + rank))
+        pg.start(bufs[s_])
+    recv2 = pg.finish()
     if rank == 0:
         assert [float(recv[0][r][0]) for r in range(world)] == [1.0, 2.0] and [float(recv[1][r][-1]) for r in range(world)] == [10.0, 20.0]
+        assert seen == [[0.0, 1.0], [100.0, 101.0], [200.0, 201.0]]
+        assert [float(recv2[0][r][0]) for r in range(world)] == [400.0, 401.0] and [float(recv2[1][r][0]) for r in range(world)] == [300.0, 301.0]
         q.put([g.numpy().copy() for g in got])
     dist.barrier()
     dist.destroy_process_group()
