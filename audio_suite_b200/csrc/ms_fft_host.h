@@ -21,6 +21,14 @@ template <int LD, int ST, int TWID, int SQ = 0, int SB = 0> struct ColsK {
     static constexpr int MINB = SB ? MS_SB_MINB : (SQ && sizeof(real) == 8) ? MS_SQ_MINB : MS_FFT_MINB;   // 2 x 512: <= 64 registers
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_body<LD, ST, TWID, SQ, SB>(jobs, c); }
 };
+#ifndef MS_WB_MINB
+#define MS_WB_MINB 4
+#endif
+template <int LD, int ST, int TWID> struct ColsWarpK {              // in-tile Bluestein, B1 = 256, warp-local transforms
+    static constexpr int MAXT = 256;
+    static constexpr int MINB = MS_WB_MINB;
+    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_warp_body<LD, ST, TWID>(jobs, c); }
+};
 template <int LD, int MODE, int ST, int SQ = 0> struct RowsK {
     static constexpr int MAXT = (SQ && sizeof(real) == 8) ? 256 : 512;
     static constexpr int MINB = (SQ && sizeof(real) == 8) ? MS_SQ_MINB : MS_FFT_MINB;
@@ -282,11 +290,15 @@ private:
         const size_t smem = MS_JOB_SMEM + sizeof(cpx) * (size_t)(MS_SB_TILE + MS_SB_TILE / 8 + 4);
         switch (sb) {
             case 1: return L<ColsK<LD, ST, TWID, 0, 128>>(gx, gy, 256, smem, st, jd);
-            case 2: return L<ColsK<LD, ST, TWID, 0, 256>>(gx, gy, 256, smem, st, jd);
+            case 2:
+                if (sb_warp()) return L<ColsWarpK<LD, ST, TWID>>(gx, gy, 256, MS_JOB_SMEM + sizeof(cpx) * (size_t)(8 * WB_RS), st, jd);
+                return L<ColsK<LD, ST, TWID, 0, 256>>(gx, gy, 256, smem, st, jd);
             case 3: return L<ColsK<LD, ST, TWID, 0, 512>>(gx, gy, 256, smem, st, jd);
             default: return L<ColsK<LD, ST, TWID, 0, 1024>>(gx, gy, 256, smem, st, jd);
         }
     }
+    // development switch MS_SB_WARP=0: the block-wide B1 = 256 kernel instead of the warp-local one
+    static bool sb_warp() { static int v = -1; if (v < 0) { const char* e = getenv("MS_SB_WARP"); v = (e && e[0] == '0') ? 0 : 1; } return v != 0; }
     template <int LD, int MODE, int ST, int SQ = 0>
     static int launch_rows(int ept, unsigned gx, unsigned gy, int nthr, size_t smem, ms_stream_t st, const FftJob* jd) {
         return L<RowsK<LD, MODE, ST, SQ>>(gx, gy, nthr, smem, st, jd);

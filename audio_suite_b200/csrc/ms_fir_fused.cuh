@@ -49,44 +49,6 @@ struct FirTables {
     const int* tap_off; const real* tap_gain;     // residue-sorted taps
 };
 
-// ---- warp-local 256-point forward FFT ---------------------------------------------------------------------
-// in: v[q] = x[lane + 32 q];  out: v[m] = X[lane + 32 m].  sw: the warp's shared-memory row (FF_RS entries).
-// The caller guarantees that nobody else touches sw and that the warp is converged.
-MS_DEV void warp_fft256(cpx* v, cpx* sw, const cpx* MS_RESTRICT tw, int lane, const Ctx& c) {
-    Bfly<8>::run(v);                                        // pass 1: Ns = 1, no twiddles; output q of butterfly j -> 8 j + q
-#pragma unroll
-    for (int q = 0; q < 8; ++q) sw[ms_pad(lane * 8 + q)] = v[q];
-    c.syncwarp();
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
-    c.syncwarp();
-    {                                                       // pass 2: Ns = 8, twiddle w_64^(q k) = w_256^(4 q k)
-        const int k = lane & 7;
-        const cpx w1 = __ldg(&tw[4 * k]), w2 = __ldg(&tw[8 * k]), w4 = __ldg(&tw[16 * k]);
-        const cpx w3 = c_mul(w1, w2);
-        v[1] = c_mul(v[1], w1); v[2] = c_mul(v[2], w2); v[3] = c_mul(v[3], w3); v[4] = c_mul(v[4], w4);
-        v[5] = c_mul(v[5], c_mul(w4, w1)); v[6] = c_mul(v[6], c_mul(w4, w2)); v[7] = c_mul(v[7], c_mul(w4, w3));
-        Bfly<8>::run(v);
-        const int base = (lane - k) * 8 + k;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) sw[ms_pad(base + 8 * q)] = v[q];
-    }
-    c.syncwarp();
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
-    c.syncwarp();
-    {                                                       // pass 3: Ns = 64, radix 4; butterflies j = lane (even m) and lane + 32 (odd m)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = lane + 32 * h;
-            const cpx w1 = __ldg(&tw[j]), w2 = __ldg(&tw[2 * j]);
-            const cpx w3 = c_mul(w1, w2);
-            cpx a[4] = {v[h], c_mul(v[2 + h], w1), c_mul(v[4 + h], w2), c_mul(v[6 + h], w3)};
-            Bfly<4>::run(a);
-            v[h] = a[0]; v[2 + h] = a[1]; v[4 + h] = a[2]; v[6 + h] = a[3];      // X[j + 64 q] -> m = 2 q + h
-        }
-    }
-}
 // W_65536^e = exp(-2 pi i e / 65536) from the unit itself (sincospi of an exactly representable argument).  Profiling
 // (ncu, B200) showed these kernels bound by LSU wavefronts, not by the FP64 pipe: a table lookup at a per-lane address
 // costs up to 32 wavefronts per warp instruction, ~45 FP64 instructions cost a third of that in SM time.
