@@ -281,6 +281,11 @@ MS_DEV void job_store(const FftJob& J, int idx, cpx v) {
     }
 }
 
+// Load functors that are plain memory loads: the tile-fill loops issue them in batches of four BEFORE the first dependent
+// shared-memory store (ncu on B200: with load and store in one loop body every STS waited out its own LDG -- the compiler
+// cannot hoist a global load over a store through a pointer it cannot prove disjoint).
+template <int LD> struct LdPlain { static constexpr bool v = (LD == LD_WORK || LD == LD_CPX || LD == LD_PAIR || LD == LD_OLS || LD == LD_REALPAD); };
+
 // The job descriptor (geometry, radix plans, table pointers, spectral operators: ~1 KB) is staged in shared
 // memory by the CTA: every later field access is a shared-memory load instead of a global one.
 #define MS_JOB_SMEM ((sizeof(FftJob) + 15) / 16 * 16)
@@ -305,12 +310,28 @@ MS_DEV void fft_cols_bluestein_static(const FftJob& J, const Ctx& c) {
     cpx* s = (cpx*)(c.smem + MS_JOB_SMEM);
     TileGeom g; g.cnt = T; g.vs = 1; g.es = T; g.colmajor = 1;
     constexpr int all = MS_SB_TILE;
+    if (LdPlain<LD>::v) {
+        for (int e0 = c.tid; e0 < all; e0 += 4 * c.nthr) {
+            cpx ld[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * c.nthr, i = e / T, v = e - i * T;
+                ld[u] = (e < all && i < F1) ? job_load<LD>(J, i * F2 + col0 + v) : c_zero();
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * c.nthr, i = e / T, v = e - i * T;
+                if (e < all) s[tile_addr(g, v, i)] = i < F1 ? c_mul(ld[u], __ldg(&J.b1_chirp[i])) : c_zero();
+            }
+        }
+    } else {
 #pragma unroll 2
-    for (int e = c.tid; e < all; e += c.nthr) {
-        const int i = e / T, v = e - i * T;
-        cpx val = c_zero();
-        if (i < F1) val = c_mul(job_load<LD>(J, i * F2 + col0 + v), __ldg(&J.b1_chirp[i]));
-        s[tile_addr(g, v, i)] = val;
+        for (int e = c.tid; e < all; e += c.nthr) {
+            const int i = e / T, v = e - i * T;
+            cpx val = c_zero();
+            if (i < F1) val = c_mul(job_load<LD>(J, i * F2 + col0 + v), __ldg(&J.b1_chirp[i]));
+            s[tile_addr(g, v, i)] = val;
+        }
     }
     c.sync();
     tile_fft_pow2<1, SB ? SB : 128, T>(s, g, J.twb, c);
@@ -346,12 +367,26 @@ MS_DEV void fft_cols_bluestein_warp256(const FftJob& J, const Ctx& c) {
     const int lane = c.tid & 31, warp = c.tid >> 5;
     // rows 0 .. 127 may hold data (F1 <= 128), rows 128 .. 255 are the zero padding of the convolution.  The load functor of
     // the inverse (the whole spectral operator) is NOT unrolled: four inlined copies spill.
+    if (LD == LD_PAIR || LD == LD_WORK || LD == LD_CPX) {
+        cpx ld[4];                                              // plain loads: all in flight before the first store
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = c.tid + 256 * i, row = e >> 3, v = e & 7;
+            ld[i] = row < F1 ? job_load<LD>(J, row * F2 + col0 + v) : c_zero();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = c.tid + 256 * i, row = e >> 3, v = e & 7;
+            s[v * WB_RS + ms_pad(row)] = row < F1 ? c_mul(ld[i], __ldg(&J.b1_chirp[row])) : c_zero();
+        }
+    } else {
 #pragma unroll 1
-    for (int i = 0; i < 4; ++i) {
-        const int e = c.tid + 256 * i, row = e >> 3, v = e & 7;
-        cpx val = c_zero();
-        if (row < F1) val = c_mul(job_load<LD>(J, row * F2 + col0 + v), __ldg(&J.b1_chirp[row]));
-        s[v * WB_RS + ms_pad(row)] = val;
+        for (int i = 0; i < 4; ++i) {
+            const int e = c.tid + 256 * i, row = e >> 3, v = e & 7;
+            cpx val = c_zero();
+            if (row < F1) val = c_mul(job_load<LD>(J, row * F2 + col0 + v), __ldg(&J.b1_chirp[row]));
+            s[v * WB_RS + ms_pad(row)] = val;
+        }
     }
 #pragma unroll
     for (int i = 4; i < 8; ++i) {
@@ -436,10 +471,26 @@ MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
         }
         return;
     }
+    if (LdPlain<LD>::v) {
+        for (int e0 = c.tid; e0 < total; e0 += 4 * c.nthr) {
+            cpx ld[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * c.nthr, i = ms_fastdiv(e, mgc), v = e - i * cnt;
+                ld[u] = e < total ? job_load<LD>(J, i * F2 + col0 + v) : c_zero();
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * c.nthr, i = ms_fastdiv(e, mgc), v = e - i * cnt;
+                if (e < total) s[tile_addr(g, v, i)] = ld[u];
+            }
+        }
+    } else {
 #pragma unroll 4
-    for (int e = c.tid; e < total; e += c.nthr) {
-        const int i = ms_fastdiv(e, mgc), v = e - i * cnt;
-        s[tile_addr(g, v, i)] = job_load<LD>(J, i * F2 + col0 + v);
+        for (int e = c.tid; e < total; e += c.nthr) {
+            const int i = ms_fastdiv(e, mgc), v = e - i * cnt;
+            s[tile_addr(g, v, i)] = job_load<LD>(J, i * F2 + col0 + v);
+        }
     }
     c.sync();
     s = SQ ? tile_fft_256<1, SQ ? SQ : 1>(s, g, J.tw1, c) : tile_fft<1>(s, s2, g, J.p1, J.tw1, c);
@@ -466,10 +517,26 @@ MS_DEV void fft_rows_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
     cpx* s2 = s + (G * g.vs + 2);                                 // (unused by the static in-place tiles)
     const int total = F2 * cnt;
     const unsigned mgF = SQ ? ms_magic_c(256) : J.p2.mg_F, mgc = SQ ? ms_magic_c(SQ ? SQ : 1) : ms_magic_dev(cnt);
+    if (LdPlain<LD>::v) {
+        for (int e0 = c.tid; e0 < total; e0 += 4 * c.nthr) {
+            cpx ld[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * c.nthr, r = ms_fastdiv(e, mgF), i = e - r * F2;
+                ld[u] = e < total ? job_load<LD>(J, (row0 + r) * F2 + i) : c_zero();
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * c.nthr, r = ms_fastdiv(e, mgF), i = e - r * F2;
+                if (e < total) s[tile_addr(g, r, i)] = ld[u];
+            }
+        }
+    } else {
 #pragma unroll 4
-    for (int e = c.tid; e < total; e += c.nthr) {
-        const int r = ms_fastdiv(e, mgF), i = e - r * F2;
-        s[tile_addr(g, r, i)] = job_load<LD>(J, (row0 + r) * F2 + i);
+        for (int e = c.tid; e < total; e += c.nthr) {
+            const int r = ms_fastdiv(e, mgF), i = e - r * F2;
+            s[tile_addr(g, r, i)] = job_load<LD>(J, (row0 + r) * F2 + i);
+        }
     }
     c.sync();
     s = SQ ? tile_fft_256<0, SQ ? SQ : 1>(s, g, J.tw2, c) : tile_fft<0>(s, s2, g, J.p2, J.tw2, c);

@@ -77,14 +77,25 @@ MS_DEV void fir_p1_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
     cpx* s = (cpx*)c.smem;
     const int lane = c.tid & 31, warp = c.tid >> 5;
     const int c0 = tile * FF_TILE;
+    {
+        // all sixteen loads are issued before the first dependent store (ncu: with load and store in one loop body every
+        // STS waited out its own LDG -- half of this kernel's stall samples)
+        cpx ld[FF_N * FF_TILE / FF_NTHR];
+        const real* in = U.in;
+        const long long pa0 = U.p0_a + c0, pb0 = U.p0_b + c0, nn = U.ols_n;
+        const int has_b = U.has_b;
 #pragma unroll
-    for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
-        const int e = c.tid + FF_NTHR * i, n1 = e >> 3, cc = e & 7;
-        const long long idx = (long long)n1 * FF_N + c0 + cc;
-        const long long pa = U.p0_a + idx, pb = U.p0_b + idx;
-        const real a = (pa >= 0 && pa < U.ols_n) ? __ldg(&U.in[pa]) : (real)0.;
-        const real b = (U.has_b && pb >= 0 && pb < U.ols_n) ? __ldg(&U.in[pb]) : (real)0.;
-        s[cc * FF_RS + ms_pad(n1)] = mk(a, b);
+        for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
+            const int e = c.tid + FF_NTHR * i, n1 = e >> 3, cc = e & 7;
+            const long long pa = pa0 + (long long)n1 * FF_N + cc, pb = pb0 + (long long)n1 * FF_N + cc;
+            ld[i].x = (pa >= 0 && pa < nn) ? __ldg(&in[pa]) : (real)0.;
+            ld[i].y = (has_b && pb >= 0 && pb < nn) ? __ldg(&in[pb]) : (real)0.;
+        }
+#pragma unroll
+        for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
+            const int e = c.tid + FF_NTHR * i, n1 = e >> 3, cc = e & 7;
+            s[cc * FF_RS + ms_pad(n1)] = ld[i];
+        }
     }
     c.sync();
     cpx v[8];
@@ -150,14 +161,15 @@ MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
     const int taps = U.tap_res >= 0;
     cpx v[8];
     if (taps) fir_fold_taps(T.res_ptr + U.tap_res, T.tap_off, T.tap_gain, sE, k_lo, last, c.tid);
-    {   // the tile: S[n2][rows of the tile] -> sB[row slot][n2]
+    {   // the tile: S[n2][rows of the tile] -> sB[row slot][n2]   (all loads in flight before the first store)
+        const int rr = c.tid & 7;
+        int rw = rr < 4 ? k_lo + rr : FF_N - (k_lo + rr - 4);
+        if (last && rr == 7) rw = 0;
+        const cpx* src = S + (size_t)(c.tid >> 3) * FF_N + rw;
 #pragma unroll
-        for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
-            const int e = c.tid + FF_NTHR * i, n2 = e >> 3, rr = e & 7;
-            int rw = rr < 4 ? k_lo + rr : FF_N - (k_lo + rr - 4);
-            if (last && rr == 7) rw = 0;
-            sB[rr * FF_RS + ms_pad(n2)] = MS_LDCG(&S[(size_t)n2 * FF_N + rw]);
-        }
+        for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) v[i] = MS_LDCG(&src[(size_t)(FF_NTHR / 8) * FF_N * i]);
+#pragma unroll
+        for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) sB[rr * FF_RS + ms_pad((c.tid >> 3) + (FF_NTHR / 8) * i)] = v[i];
     }
     c.sync();
     if (taps && (warp < 4 || (last && warp == 7))) {        // the warps that own an E row transform it first

@@ -112,11 +112,23 @@ MS_DEV void post_right_tile(const PostRender& R, const real* MS_RESTRICT y, int 
     const int n = R.n;
     const int W = len + 4 * POST_K;
     const int w0 = wrap_idx((long long)t0 + R.dr - 2 * POST_K, n);          // one 64-bit modulo per thread
-    for (int j = c.tid; j < W; j += c.nthr) {
-        const int mm = j >> 1;
-        int idx = w0 + j;
-        if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }                  // second wrap only for n < tile
-        win[(j & 1) * POST_PAR + mm + (mm >> 2)] = y[idx];
+    {
+        // every load of the window is issued before the first store (ncu: one loop body per sample made each STS wait
+        // out its own LDG)
+        constexpr int NQ = (OLA_TILE + 4 * POST_K + OLA_NTHR - 1) / OLA_NTHR;
+        real tmp[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int j = c.tid + OLA_NTHR * q;
+            int idx = w0 + j;
+            if (idx >= n) { idx -= n; if (idx >= n) idx %= n; }              // second wrap only for n < tile
+            tmp[q] = j < W ? y[idx] : (real)0.;
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int j = c.tid + OLA_NTHR * q, mm = j >> 1;
+            if (j < W) win[(j & 1) * POST_PAR + mm + (mm >> 2)] = tmp[q];
+        }
     }
     for (int j = c.tid; j < POST_NC; j += c.nthr) coef[j] = (real)R.coef[j];
     c.sync();
@@ -179,10 +191,17 @@ MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, uns
     real m = (real)0.;
     if (mode == 1) {
         post_right_tile(R, y, t0, len, win, coef, res, c);
-        for (int j = c.tid; j < len; j += c.nthr) {
-            const real r = res[j + (j >> 3)];
-            mono[R.rbuf + t0 + j] = r;
-            m = r_max(m, r_max(r_abs(r), r_abs(y[t0 + j])));
+        real yv[OLA_TILE / OLA_NTHR];
+#pragma unroll
+        for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) { const int j = c.tid + OLA_NTHR * q; yv[q] = j < len ? y[t0 + j] : (real)0.; }
+#pragma unroll
+        for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) {
+            const int j = c.tid + OLA_NTHR * q;
+            if (j < len) {
+                const real r = res[j + (j >> 3)];
+                mono[R.rbuf + t0 + j] = r;
+                m = r_max(m, r_max(r_abs(r), r_abs(yv[q])));
+            }
         }
     } else {
         for (int i = t0 + c.tid; i < t1; i += c.nthr) {
@@ -215,11 +234,19 @@ MS_DEV void post_write_body(const PostRender* MS_RESTRICT renders, const real* M
     const real scale = top > (real)0. ? (real)R.peak / top : (real)1.0;
     float2* o = out + R.out;
     const int dlm = mode ? wrap_idx((long long)R.dl, R.n) : 0;          // left channel = roll(y, dl)
-    for (int i = t0 + c.tid; i < t1; i += c.nthr) {
+    real lv[OLA_TILE / OLA_NTHR], rv[OLA_TILE / OLA_NTHR];
+    const real* rsrc = mode ? mono + R.rbuf : y;
+#pragma unroll
+    for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) {
+        const int i = t0 + c.tid + OLA_NTHR * q;
         int li = i - dlm; if (li < 0) li += R.n;
-        const real l = y[li];
-        const real r = mode ? mono[R.rbuf + i] : y[i];
-        o[i] = make_float2((float)(soft_clip(l, drive, inv_t) * scale), (float)(soft_clip(r, drive, inv_t) * scale));
+        lv[q] = i < t1 ? y[li] : (real)0.;
+        rv[q] = i < t1 ? rsrc[i] : (real)0.;
+    }
+#pragma unroll
+    for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) {
+        const int i = t0 + c.tid + OLA_NTHR * q;
+        if (i < t1) o[i] = make_float2((float)(soft_clip(lv[q], drive, inv_t) * scale), (float)(soft_clip(rv[q], drive, inv_t) * scale));
     }
 }
 // circular shift used by the odd-length stereo path: dst[i] = src[(i + shift) mod n]

@@ -650,8 +650,9 @@ def _render_batch(params_list, device=None, precision="auto", host_out=None, chu
         # short first slices: the GPU and the drain start early; short LAST slices: what is left after the host has enqueued
         # its last slice (that slice's kernels + its device->host copy) is short too
         n, c = len(params_list), int(chunk)
-        head = [max(piece, c // 16), max(piece, c // 8), max(piece, c // 4), max(piece, c // 2)]
-        tail = [max(piece, c // 2), max(piece, c // 4), max(piece, c // 8), max(piece, c // 8)]
+        # (a finer ramp -- 32, 64, 128, 256 ... -- was measured slower: 99 ms against 92 ms; every slice costs ~1 ms of host work)
+        head = [max(piece, c // 4), max(piece, c // 2)]
+        tail = [max(piece, c // 2), max(piece, c // 4), max(piece, c // 4)]
         body = max(0, n - sum(head) - sum(tail))
         chunk = head + [c] * (body // c) + ([body % c] if body % c else []) + tail
     if not hasattr(dev, "torch"):                   # host emulator device (tests): one slice after the other
