@@ -128,7 +128,7 @@ extern "C" int MS_API(ms_resonator)(const ms_res_evt* evts, int n, const ms_res_
 extern "C" int MS_API(ms_partial_lock)(const ms_plock_evt* evts, int n, real* z_base, real* scratch, void* stream) {
     for (int x0 = 0; x0 < n; x0 += 1 << 20) {
         const int cnt = std::min(1 << 20, n - x0);
-        if (ms_launch<PartialLockK>(mk_dim((unsigned)cnt, 1), PLOCK_NTHR, PLOCK_NTHR * sizeof(int), (ms_stream_t)stream,
+        if (ms_launch<PartialLockK>(mk_dim((unsigned)cnt, 1), PLOCK_NTHR, (PLOCK_NTHR + 1 + 2 * PLOCK_SEL_MAX) * sizeof(int), (ms_stream_t)stream,
                                     evts + x0, (cpx*)z_base, scratch)) return -1;
     }
     return 0;

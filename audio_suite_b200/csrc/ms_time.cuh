@@ -83,15 +83,18 @@ MS_DEV void er_scatter_body(const ErJob* MS_RESTRICT jobs, const int* MS_RESTRIC
     real* e = ebase + J.e;
     for (int i = c.tid; i < J.elen; i += c.nthr) e[i] = (real)0.;
     c.sync();
+    // Several taps may share a delay.  No atomics: the FIRST tap of a delay sums every later tap of that delay in tap
+    // order and writes the sum, so the result does not depend on the thread schedule (O(taps^2) compares per render,
+    // taps <= 4096; the tap table is L1-resident).
     for (int t = J.tap_begin + c.tid; t < J.tap_end; t += c.nthr) {
-        const int off = tap_off[t];
-        if (off >= 0 && off < J.elen) {
-#ifdef MS_HOST_EMUL
-            e[off] += tap_gain[t];
-#else
-            atomicAdd(&e[off], tap_gain[t]);        // several taps may share a delay
-#endif
-        }
+        const int off = __ldg(&tap_off[t]);
+        if (off < 0 || off >= J.elen) continue;
+        bool first = true;
+        for (int u = J.tap_begin; u < t; ++u) if (__ldg(&tap_off[u]) == off) { first = false; break; }
+        if (!first) continue;
+        real sum = __ldg(&tap_gain[t]);
+        for (int u = t + 1; u < J.tap_end; ++u) if (__ldg(&tap_off[u]) == off) sum += __ldg(&tap_gain[u]);
+        e[off] = sum;
     }
 }
 
@@ -288,6 +291,7 @@ MS_DEV void imprint_body(const ImprintEvt* MS_RESTRICT evts, const ImprintRender
 // W[k] * (1 - |d| / (neigh + 1)) at round-half-even(k * factor) + d; (4) Y replaces the spectrum's bins 0..n/2.
 typedef ms_plock_evt PlockEvt;
 #define PLOCK_NTHR 256
+#define PLOCK_SEL_MAX 1024               // selected bins kept (pl_top_n is at most 200 in the reference's UI; exact ties may add a few)
 MS_DEV int plock_block_sum(int v, int* red, const Ctx& c) {
     red[c.tid] = v;
     c.sync();
@@ -324,27 +328,45 @@ MS_DEV void partial_lock_body(const PlockEvt* MS_RESTRICT evts, cpx* zbase, real
         if (plock_block_sum(cnt, red, c) >= want) lo = mid; else hi = mid;
     }
     union { unsigned long long u; double d; } th; th.u = lo;
-    for (int k = c.tid; k < bins; k += c.nthr) Z[k] = c_scale(W[k], (real)0.12);
+    // The selected bins in ascending k, compacted into shared memory (a thread owns a contiguous chunk of bins; an
+    // exclusive scan of the chunk counts gives its slot), then a GATHER: every output bin adds the selected bins that
+    // land within +-neigh of it, in k order.  No atomics, the result does not depend on the thread schedule.
+    int* sel_k2 = red + PLOCK_NTHR + 1;                       // PLOCK_SEL_MAX target bins (round-half-even(k * factor))
+    int* sel_k = sel_k2 + PLOCK_SEL_MAX;                      // ... and their source bins
+    const int chunk = (bins - 1 + c.nthr - 1) / c.nthr;
+    const int k_lo = 1 + c.tid * chunk, k_hi = (k_lo + chunk) < bins ? (k_lo + chunk) : bins;
+    int mine = 0;
+    if (want > 0) for (int k = k_lo; k < k_hi; ++k) mine += ((double)M[k] >= th.d) ? 1 : 0;
+    red[c.tid] = mine;
     c.sync();
-    if (want > 0) {
-        const int nb = E.neigh;
-        const real inv = (real)1.0 / (real)(nb + 1);
-        for (int k = 1 + c.tid; k < bins; k += c.nthr) {
+    if (c.tid == 0) { int acc = 0; for (int i = 0; i < c.nthr; ++i) { const int v = red[i]; red[i] = acc; acc += v; } red[c.nthr] = acc; }
+    c.sync();
+    const int n_sel = red[c.nthr] < PLOCK_SEL_MAX ? red[c.nthr] : PLOCK_SEL_MAX;
+    {
+        int at = red[c.tid];
+        if (want > 0) for (int k = k_lo; k < k_hi; ++k) {
             if ((double)M[k] < th.d) continue;
-            const int k2 = (int)rint((double)k * E.factor);                 // Python round(): half to even
-            if (k2 < 1 || k2 >= bins) continue;
-            const cpx x = W[k];
-            for (int d = -nb; d <= nb; ++d) {
-                const int kk = k2 + d;
-                if (kk < 1 || kk >= bins) continue;
-                const real w = (real)1.0 - (real)(d < 0 ? -d : d) * inv;
-#ifdef MS_HOST_EMUL
-                Z[kk].x += x.x * w; Z[kk].y += x.y * w;
-#else
-                atomicAdd(&Z[kk].x, x.x * w); atomicAdd(&Z[kk].y, x.y * w);    // several strong bins may land on one
-#endif
+            if (at < PLOCK_SEL_MAX) { sel_k[at] = k; sel_k2[at] = (int)rint((double)k * E.factor); }     // Python round(): half to even
+            ++at;
+        }
+    }
+    c.sync();
+    const int nb = E.neigh;
+    const real inv = (real)1.0 / (real)(nb + 1);
+    for (int kk = c.tid; kk < bins; kk += c.nthr) {
+        cpx y = c_scale(W[kk], (real)0.12);
+        if (kk >= 1) {
+            for (int i = 0; i < n_sel; ++i) {
+                const int k2 = sel_k2[i];
+                int d = kk - k2;
+                if (d < 0) d = -d;
+                if (d > nb || k2 < 1 || k2 >= bins) continue;
+                const real w = (real)1.0 - (real)d * inv;
+                const cpx x = W[sel_k[i]];
+                y.x += x.x * w; y.y += x.y * w;
             }
         }
+        Z[kk] = y;
     }
 }
 

@@ -49,6 +49,10 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="N>1: launch the parts eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-pipeline", action="store_true", help="N>1: wait for each pass's gather before the next pass starts")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather of rendered buffers (N>1)")
+    ap.add_argument("--config", default="C5", choices=["C1", "C1b", "C2", "C3", "C4", "C5"],
+                    help="C5 (default) is the metric's workload; C1..C4 time ONE render of that BASELINE.json config: the kernel "
+                         "sequence with the plan resident (value), render() from the parameter dict to the float64 result (e2e) "
+                         "and the numpy port on one host core (cpu_baseline) -- single GPU only")
     return ap.parse_args()
 
 
@@ -480,6 +484,90 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_single_config(args):
+    """One render of C1 / C1b / C2 / C3 / C4 (launch-latency-bound except C4): same JSON contract, N = 1."""
+    import torch
+    from audio_suite_b200 import configs, engine
+    from oracle import microsound_np as O
+    torch.cuda.set_device(0)
+    dev = engine.CudaDevice(0)
+    p = configs.canonical(args.config)
+    br = engine.BatchRenderer([p], device=dev, precision=args.precision)
+    frames = int(br.tables.frames)
+    for _ in range(max(3, args.warmup)):
+        br.run()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.2)
+    launches0 = dev.lib.ms_launch_count()
+    wall0 = time.time()
+    names, per_step = [], []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        evs = [torch.cuda.Event(enable_timing=True)]
+        evs[0].record()
+        names = []
+
+        def mark(name, evs=evs, names=names):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            evs.append(ev)
+            names.append(name)
+        br.run(mark)
+        per_step.append((names, evs))
+    e1.record()
+    torch.cuda.synchronize()
+    wall1 = time.time()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (dev.lib.ms_launch_count() - launches0) // args.steps
+    clocks = sampler.stop(wall0, wall1)
+    stage_ms = {}
+    for names, evs in per_step:
+        for name, a, b in zip(names, evs[:-1], evs[1:]):
+            stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / args.steps
+    alg = algorithmic_bytes(br)
+    br.close()
+    lat = []
+    for s in range(3 + max(1, args.e2e_steps)):
+        t0 = time.perf_counter()
+        out, meta = engine.render(p, device=dev, precision=args.precision)
+        if s >= 3:
+            lat.append((time.perf_counter() - t0) * 1e3)
+    reps = 1 if args.config == "C4" else 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ref, _ = O.render(p)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+    err = float(np.max(np.abs(out[::7] - ref[::7])))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom = max(stage_ms, key=stage_ms.get)
+    ach = alg.get(dom, 0) / 1e9 / (stage_ms[dom] * 1e-3)
+    total = 2.0 * frames
+    e2e_ms = float(np.mean(lat))
+    line = {"metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": br.precision, "data": "synthetic",
+            "config": {"workload": "%s: one render of BASELINE.json's config (SURVEY.md Appendix D), %d stereo frames" % (args.config, frames),
+                       "l2": "working set %s the 126 MB L2" % ("exceeds" if args.config == "C4" else "fits: these single renders are launch-latency-bound, not bandwidth-bound")},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": {"value": total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": len(lat), "warmup": 3,
+                    "h2d_bytes_per_step": int(br.h2d_bytes), "d2h_bytes_per_step": int(frames * 2 * 4),
+                    "includes": "render(params): planning, table upload, kernels, device->host copy, float64 (out_n, 2) result + meta"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                         "traffic": None, "algorithmic_bytes": alg.get(dom, 0), "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"},
+            "stages": {k: {"ms": round(v, 4), "algorithmic_GB": round(alg.get(k, 0) / 1e9, 4)} for k, v in stage_ms.items()},
+            "cpu_baseline": {"value": total / (cpu_ms * 1e-3), "unit": UNIT, "cores": 1, "kind": "port", "ms": cpu_ms,
+                             "sample": "the same single render, oracle/microsound_np.py, one core"},
+            "max_abs_vs_oracle": err}
+    print(json.dumps(line))
+
+
 def main():
     args = parse()
     # rank 0 prints ONE JSON line on stdout and nothing else: libraries that write to file descriptor 1 (NCCL's version
@@ -499,6 +587,8 @@ def main():
     try:
         if args.impl == "reference":
             run_reference(args)
+        elif args.config != "C5":
+            run_single_config(args)
         else:
             run_ours(args)
     finally:

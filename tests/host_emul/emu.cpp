@@ -6,6 +6,8 @@
 #include <ucontext.h>
 #include <vector>
 #include <stdexcept>
+#include <cstdlib>
+#include <utility>
 
 namespace msemu {
 static ucontext_t g_main;
@@ -64,9 +66,19 @@ void run(MsDim grid, int block, size_t smem, const std::function<void(const Ctx&
             g_ctx[t].uc_link = &g_main;
             makecontext(&g_ctx[t], trampoline, 0);
         }
+        // MS_EMUL_SHUFFLE=<seed>: every sweep visits the fibres in a fresh pseudo-random order.  A kernel whose result depends
+        // on which thread runs first between two barriers (a shared-memory race) then gives different results under
+        // different seeds -- the stand-in for compute-sanitizer's racecheck, which is closed on the GPU pool
+        // (tests/test_emul_kernels.py::test_results_do_not_depend_on_the_thread_schedule).
+        static const char* shuf = getenv("MS_EMUL_SHUFFLE");
+        static unsigned long long rs = shuf ? strtoull(shuf, nullptr, 10) * 2654435761ull + 88172645463325252ull : 0ull;
+        std::vector<int> order(block);
+        for (int t = 0; t < block; ++t) order[t] = t;
         for (;;) {      // one sweep = one barrier interval
             int alive = 0, finished = 0;
-            for (int t = 0; t < block; ++t) {
+            if (shuf) for (int t = block - 1; t > 0; --t) { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; std::swap(order[t], order[(int)(rs % (unsigned long long)(t + 1))]); }
+            for (int ti = 0; ti < block; ++ti) {
+                const int t = order[ti];
                 if (g_done[t]) { ++finished; continue; }
                 g_cur = t;
                 swapcontext(&g_main, &g_ctx[t]);

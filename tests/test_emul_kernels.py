@@ -271,3 +271,49 @@ def test_shipped_presets_from_the_reference_fixture(emul, name):
         K.check_render(emul, p, "f64")
         return
     K.check_preset(emul, name, fx)
+
+
+def test_results_do_not_depend_on_the_thread_schedule():
+    """Race check without compute-sanitizer (closed on the GPU pool, profiles/r02_compute_sanitizer_closed.log): the block
+    emulator visits the fibres of a block in a fresh pseudo-random order between every two barriers (MS_EMUL_SHUFFLE); a
+    shared-memory race -- a read that is not separated from a write by a barrier -- changes the result with the order.
+    Covers the warp-local FFTs and the fused FIR phases, the block-wide in-place passes, in-tile and global Bluestein, the
+    post passes, overlap-add, every generator; bitwise equality across schedules."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, hashlib
+sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+from emul_device import EmulDevice
+from audio_suite_b200 import configs, engine
+dev = EmulDevice()
+W = configs.with_defaults
+ir = configs.synth_ir(0.05, 48000, 3)
+ps = [configs.canonical("C1b")]
+p = configs.c5_params(3); p["out_dur_s"] = 0.3; ps.append(p)
+for mode in configs.BASIC_MODES:
+    ps.append(W(gen_mode=mode, event_process="Poisson", out_dur_s=0.2, grains_per_sec=25.0, time_unfold=40.0, micro_ms=2.0, partial_stretch=1.7,
+                space_ir_on=True, _ir_audio=ir))
+ps.append(W(event_process="Clustered", out_dur_s=0.10003, base_sr=44100, grains_per_sec=30.0, bp_unfold="0:20, 0.1:33.3", unfold_mode="Multi-band unfold"))
+ps.append(W(cep_warp_on=True, bandlimit_on=False, res_bank_on=True, wg_on=True, wg_max_ms=1.0, event_feedback_on=True, spectral_imprint_on=True,
+            event_process="Poisson", out_dur_s=0.2, grains_per_sec=25.0, micro_ms=2.0, gen_mode="Micro-chaos"))
+ps.append(W(partial_lock_on=True, partial_stretch=1.3, pl_top_n=60, pl_neigh=9, event_process="Poisson", out_dur_s=0.2, grains_per_sec=25.0,
+            gen_mode="Resonant strike", er_taps=2000))              # lock: compaction + gather; cloud: many taps sharing a delay
+h = hashlib.sha256()
+for p in ps:
+    out, meta = engine.render(p, device=dev, precision="f64")
+    h.update(out.tobytes()); h.update(meta["grain_last"].tobytes())
+print(h.hexdigest())
+'''
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = code % (root, os.path.join(root, "tests"), os.path.join(root, "tests", "host_emul"))
+    digests = []
+    for seed in (None, "1", "2", "12345"):
+        env = dict(os.environ)
+        env.pop("MS_EMUL_SHUFFLE", None)
+        if seed:
+            env["MS_EMUL_SHUFFLE"] = seed
+        digests.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])
+    assert len(set(digests)) == 1, digests
