@@ -33,11 +33,11 @@ def stage_of(launches):
             continue
         elif "AdsrTableK" in n or "OlaK" in n:
             stage = "overlap_add"
-        elif "ErScatterK" in n:
+        elif "ErScatterK" in n or "FirP1K" in n or "FirP2K" in n or "FirP3K" in n or "fir_cluster_kernel" in n:
             stage = "fir_overlap_save"
         elif "PostMaxK" in n or "PostWriteK" in n or "RollK" in n:
             stage = "post"
-        elif "ColsK" in n or "RowsK" in n:
+        elif "ColsK" in n or "RowsK" in n or "ColsWarpK" in n:
             if stage == "synth":
                 stage = "tilt_spectral" if fft_before_tilt else "grain_spectral"
             elif stage == "tilt_spectral" and not fft_before_tilt:
