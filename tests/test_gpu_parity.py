@@ -286,3 +286,22 @@ def test_native_and_python_planner_render_the_same_audio(cuda_dev, monkeypatch):
     b = engine.render_batch(ps, device=cuda_dev)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+def test_render_plan_cache_recomputes_identical_audio(cuda_dev):
+    """render() keeps the planned renderer of unchanged settings and replays its launch sequence as a CUDA graph; the audio is
+    recomputed, identical to a render planned from scratch, and a changed parameter or an IR edited in place is a miss."""
+    engine.clear_render_cache()
+    ir = configs.synth_ir(0.2, 48000, 3)
+    p = configs.with_defaults(event_process="Poisson", out_dur_s=0.5, space_ir_on=True, _ir_audio=ir)
+    fresh, _ = engine.render(p, device=cuda_dev, cache=False)
+    outs = [engine.render(p, device=cuda_dev)[0] for _ in range(4)]            # miss, hit (captures), replay, replay
+    for o in outs:
+        assert np.array_equal(o, fresh)
+    q = dict(p, seed=p["seed"] + 1)
+    assert not np.array_equal(engine.render(q, device=cuda_dev)[0], fresh)
+    ir[::7] *= 0.5                                                              # edited in place: must not be served from the cache
+    changed, _ = engine.render(p, device=cuda_dev)
+    ref, _ = O.render(p)
+    assert np.max(np.abs(changed - ref)) < K.MAX_ABS_TOL and not np.array_equal(changed, fresh)
+    engine.clear_render_cache()
