@@ -586,13 +586,7 @@ _RENDER_CACHE = {}
 _CACHE_ENTRIES, _CACHE_MAX_FRAMES = 8, 4_000_000
 
 
-def _array_key(a):
-    if a is None:
-        return None
-    a = np.asarray(a)
-    flat = a.reshape(-1)
-    step = max(1, flat.size // 64)
-    return (id(a), a.shape, str(a.dtype), float(np.sum(flat[::step], dtype=np.float64)), float(flat[-1]) if flat.size else 0.0)
+_array_key = P.array_signature
 
 
 def _cache_key(params, dev, precision):

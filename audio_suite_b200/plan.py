@@ -453,10 +453,22 @@ def plan_render(params) -> RenderPlan:
 _TAPS_CACHE = {}
 
 
+def array_signature(a):
+    """Cheap identity-and-content key of an array-valued parameter (`_ir_audio`, `_img_gray`) for the planner's caches:
+    the object, its shape / dtype, and a checksum over 64 strided samples plus the last one -- so an array edited IN PLACE
+    between two renders is seen as new (the reference keeps no caches: whatever the array holds at call time is used)."""
+    if a is None:
+        return None
+    a = np.asarray(a)
+    flat = a.reshape(-1)
+    step = max(1, flat.size // 64)
+    return (id(a), a.shape, a.dtype.str, float(np.sum(flat[::step], dtype=np.float64)), float(flat[-1]) if flat.size else 0.0)
+
+
 def _ir_taps(ir, max_samps):
     """convolve_ir_short's view of the IR (M:438-443): None if the slice has fewer than 8 values, else the
     float64 mono mix of its first 8192 rows.  Cached per IR object: a sweep shares one IR."""
-    key = (id(ir), max_samps)
+    key = (array_signature(ir), max_samps)
     hit = _TAPS_CACHE.get(key)
     if hit is not None and hit[0] is ir:
         return hit[1]
@@ -547,14 +559,15 @@ _MONO_CACHE = {}
 
 
 def _mono64(ir):
-    hit = _MONO_CACHE.get(id(ir))
+    key = array_signature(ir)
+    hit = _MONO_CACHE.get(key)
     if hit is None or hit[0] is not ir:
         src = np.asarray(ir).astype(np.float64)
         if src.ndim > 1:
             src = src.mean(axis=1)
         if len(_MONO_CACHE) > 16:
             _MONO_CACHE.clear()
-        _MONO_CACHE[id(ir)] = hit = (ir, src)
+        _MONO_CACHE[key] = hit = (ir, src)
     return hit[1]
 
 
