@@ -114,66 +114,71 @@ MS_DEV void fir_p1_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
 
 // ---- phase 2: rows (forward, filter, inverse) ---------------------------------------------------------------
 // The reflection taps are real, so E is Hermitian: E[65536 - k] = conj E[k], i.e. row 256 - k1 is row k1 reversed and
-// conjugated (E[256 - k1][k2] = conj E[k1][255 - k2]).  A tile therefore holds four rows k1 = 4 t + 1 .. 4 t + 4 and
-// their partners 256 - k1: the fold and the extra FFT run for four rows only.  Rows 0 and 128 are their own partners:
-// in tile 31 (k1 = 125 .. 128) the warp that would get row 128 a second time takes row 0, with a fifth folded row.
-// Warps 0-3 transform the folded rows before their own row; warps 4-7 go straight to theirs and meet them at the barrier
-// in front of the filter product.  (Letting warps 4-7 fetch the whole tile meanwhile was measured slower: 6.0 -> 6.5 ms.)
-#define FF_EROWS 5
+// conjugated (E[256 - k1][k2] = conj E[k1][255 - k2]).  A CTA therefore takes SIXTEEN rows in two passes of eight: pass A
+// the rows k1 = 8 t + 1 .. 8 t + 8 (every warp folds nothing twice: the fold and the extra FFT run once per PAIR), pass B
+// their partners 256 - k1 = 248 - 8 t .. 255 - 8 t, which reuse the E rows of pass A reversed and conjugated.  Every warp
+// does the same work (one E transform + two row transforms in pass A, two row transforms in pass B), so nobody idles
+// at the barriers (ncu on the previous form -- four rows + four partners per tile, warps 0-3 owning the E rows -- showed
+// 18 % of the stall samples at the barrier where warps 4-7 waited for them), and both tile fetches are eight contiguous
+// rows = full 128-byte segments.  Rows 0 and 128 are their own partners: in the last tile (k1 = 121 .. 128) pass B would
+// meet row 128 again; that slot takes row 0 instead, whose E row is folded (no modulation: W^0) into the slot row 128's E
+// occupied -- nobody needs that one in pass B.
+#define FF_EROWS 8
+#define FF_TILES2 (FF_N / 16)          // CTAs per unit in phase 2
 // fold: F[k1][r] = sum over taps with off = r (mod 256) of g W_65536^(off k1); a thread owns one residue for the tile's
-// four rows (W^(off k1) steps by W^off from row to row).  Residues are handed out by descending tap count (perm), so
-// the lanes of a warp run the same number of iterations.  Out of line: its registers (two sincospi per tap) stay out
-// of the transform code's allocation.
+// eight rows, four at a time (W^(off k1) steps by W^off from row to row).  Residues are handed out by descending tap
+// count (perm), so the lanes of a warp run the same number of iterations.  Out of line: its registers (two sincospi per
+// tap) stay out of the transform code's allocation.
 MS_DEV_NOINLINE void fir_fold_taps(const int* MS_RESTRICT rp, const int* MS_RESTRICT tap_off, const real* MS_RESTRICT tap_gain,
-                                   cpx* sE, int k_lo, int last, int tid) {
+                                   cpx* sE, int k_first, int tid) {
     const int r = __ldg(&rp[257 + tid]);
     const int t_begin = __ldg(&rp[r]), t_end = __ldg(&rp[r + 1]);
-    cpx acc[4];
-    real f0 = (real)0.;
+#pragma unroll 1
+    for (int half = 0; half < FF_EROWS; half += 4) {
+        cpx acc[4];
 #pragma unroll
-    for (int w = 0; w < 4; ++w) acc[w] = c_zero();
-    for (int t = t_begin; t < t_end; ++t) {
-        const unsigned off = (unsigned)__ldg(&tap_off[t]);
-        const real g = __ldg(&tap_gain[t]);
-        cpx tw = w65536(off * (unsigned)k_lo);
-        const cpx st = w65536(off);
-        f0 += g;
+        for (int w = 0; w < 4; ++w) acc[w] = c_zero();
+        for (int t = t_begin; t < t_end; ++t) {
+            const unsigned off = (unsigned)__ldg(&tap_off[t]);
+            const real g = __ldg(&tap_gain[t]);
+            cpx tw = w65536(off * (unsigned)(k_first + half));
+            const cpx st = w65536(off);
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            acc[w] = mk(acc[w].x + g * tw.x, acc[w].y + g * tw.y);
-            if (w < 3) tw = c_mul(tw, st);
+            for (int w = 0; w < 4; ++w) {
+                acc[w] = mk(acc[w].x + g * tw.x, acc[w].y + g * tw.y);
+                if (w < 3) tw = c_mul(tw, st);
+            }
         }
-    }
 #pragma unroll
-    for (int w = 0; w < 4; ++w) sE[w * FF_RS + ms_pad(r)] = acc[w];
-    if (last) sE[4 * FF_RS + ms_pad(r)] = mk(f0, (real)0.);
+        for (int w = 0; w < 4; ++w) sE[(half + w) * FF_RS + ms_pad(r)] = acc[w];
+    }
 }
-MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, const Ctx& c) {
-    cpx* sB = (cpx*)c.smem;                                 // transposing tile + exchange rows
-    cpx* sE = sB + FF_TILE * FF_RS;                         // E rows (natural order k2): four + row 0 in the last tile
-    const int lane = c.tid & 31, warp = c.tid >> 5;
-    const int k_lo = 4 * tile + 1;
-    const int last = tile == FF_TILES - 1;
-    int row, erow, rev;
-    if (warp < 4) { row = k_lo + warp; erow = warp; rev = 0; }
-    else { row = FF_N - (k_lo + warp - 4); erow = warp - 4; rev = 1; }
-    if (last && warp == 7) { row = 0; erow = 4; rev = 0; }
-    const int taps = U.tap_res >= 0;
+// the unmodulated fold of row 0 (k1 = 0: F[r] = sum of the gains of residue r), into one E row
+MS_DEV_NOINLINE void fir_fold_row0(const int* MS_RESTRICT rp, const real* MS_RESTRICT tap_gain, cpx* row, int tid) {
+    const int r = __ldg(&rp[257 + tid]);
+    real f0 = (real)0.;
+    for (int t = __ldg(&rp[r]); t < __ldg(&rp[r + 1]); ++t) f0 += __ldg(&tap_gain[t]);
+    row[ms_pad(r)] = mk(f0, (real)0.);
+}
+// one pass of eight rows: fetch, FFT, * H, swap, FFT, twiddle, back.  row0 + slot = global row of tile slot `slot`
+// (slot_zero >= 0: that slot holds row 0 instead); this warp works on slot `my`, whose filter row is IRspec[row] *
+// (1 + E) with E = sE[erow] (rev: reversed and conjugated); own_e: the warp first transforms its E row in place.
+MS_DEV void fir_p2_pass(const FirUnit& U, const FirTables& T, cpx* S, cpx* sB, cpx* sE, int row0, int slot_zero, int my, int erow, int rev,
+                        int own_e, int taps, const Ctx& c) {
+    const int lane = c.tid & 31;
     cpx v[8];
-    if (taps) fir_fold_taps(T.res_ptr + U.tap_res, T.tap_off, T.tap_gain, sE, k_lo, last, c.tid);
-    {   // the tile: S[n2][rows of the tile] -> sB[row slot][n2]   (all loads in flight before the first store)
+    {   // the tile: S[n2][rows of the pass] -> sB[slot][n2]   (all loads in flight before the first store)
         const int rr = c.tid & 7;
-        int rw = rr < 4 ? k_lo + rr : FF_N - (k_lo + rr - 4);
-        if (last && rr == 7) rw = 0;
+        const int rw = rr == slot_zero ? 0 : row0 + rr;
         const cpx* src = S + (size_t)(c.tid >> 3) * FF_N + rw;
 #pragma unroll
         for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) v[i] = MS_LDCG(&src[(size_t)(FF_NTHR / 8) * FF_N * i]);
 #pragma unroll
         for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) sB[rr * FF_RS + ms_pad((c.tid >> 3) + (FF_NTHR / 8) * i)] = v[i];
     }
-    c.sync();
-    if (taps && (warp < 4 || (last && warp == 7))) {        // the warps that own an E row transform it first
-        cpx* swE = sE + erow * FF_RS;
+    c.sync();                                               // the tile and the folded rows are in place
+    cpx* swE = sE + erow * FF_RS;
+    if (taps && own_e) {                                    // the warp's own E row, in place (only its owner touches it from here on)
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = swE[ms_pad(lane + 32 * q)];
         c.syncwarp();
@@ -181,16 +186,16 @@ MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
         c.syncwarp();
 #pragma unroll
         for (int m = 0; m < 8; ++m) swE[ms_pad(lane + 32 * m)] = v[m];
+        c.syncwarp();
     }
-    cpx* sw = sB + warp * FF_RS;
+    const int row = my == slot_zero ? 0 : row0 + my;
+    cpx* sw = sB + my * FF_RS;
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
     c.syncwarp();
     warp_fft256(v, sw, T.tw, lane, c);                      // v[m] = Z[row][k2 = lane + 32 m]
-    if (taps) c.sync();                                     // every E row is in place
     {
         const cpx* f = U.filt + (size_t)row * FF_N + lane;
-        const cpx* swE = sE + erow * FF_RS;
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             cpx h = __ldg(&f[32 * m]);
@@ -209,14 +214,30 @@ MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, 
 #pragma unroll
     for (int m = 0; m < 8; ++m) sw[ms_pad(lane + 32 * m)] = v[m];
     c.sync();
+    {
+        const int rr = c.tid & 7;
+        const int rw = rr == slot_zero ? 0 : row0 + rr;
+        cpx* dst = S + (size_t)(c.tid >> 3) * FF_N + rw;
 #pragma unroll
-    for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) {
-        const int e = c.tid + FF_NTHR * i, n2 = e >> 3, rr = e & 7;
-        int rw = rr < 4 ? k_lo + rr : FF_N - (k_lo + rr - 4);
-        if (last && rr == 7) rw = 0;
-        S[(size_t)n2 * FF_N + rw] = sB[rr * FF_RS + ms_pad(n2)];
+        for (int i = 0; i < FF_N * FF_TILE / FF_NTHR; ++i) dst[(size_t)(FF_NTHR / 8) * FF_N * i] = sB[rr * FF_RS + ms_pad((c.tid >> 3) + (FF_NTHR / 8) * i)];
     }
     c.sync();
+}
+MS_DEV void fir_p2_tile(const FirUnit& U, const FirTables& T, cpx* S, int tile, const Ctx& c) {
+    cpx* sB = (cpx*)c.smem;                                 // transposing tile + exchange rows
+    cpx* sE = sB + FF_TILE * FF_RS;                         // E rows of pass A (natural order k2)
+    const int warp = c.tid >> 5;
+    const int k_first = 8 * tile + 1;
+    const int last = tile == FF_TILES2 - 1;                 // k1 = 121 .. 128
+    const int taps = U.tap_res >= 0;
+    if (taps) { fir_fold_taps(T.res_ptr + U.tap_res, T.tap_off, T.tap_gain, sE, k_first, c.tid); }
+    // pass A: rows k_first + w, each warp its own E row
+    fir_p2_pass(U, T, S, sB, sE, k_first, -1, warp, warp, 0, 1, taps, c);
+    // pass B: partners 256 - (k_first + w) = rowB0 + (7 - w); in the last tile slot 0 (row 128 again) takes row 0
+    const int rowB0 = FF_N - (k_first + 7);
+    if (taps && last) { fir_fold_row0(T.res_ptr + U.tap_res, T.tap_gain, sE + 7 * FF_RS, c.tid); }
+    const int slot = 7 - warp;
+    fir_p2_pass(U, T, S, sB, sE, rowB0, last ? 0 : -1, slot, warp, (last && warp == 7) ? 0 : 1, (last && warp == 7) ? 1 : 0, taps, c);
 }
 
 // ---- phase 3: inverse columns, valid outputs ------------------------------------------------------------------
@@ -319,7 +340,7 @@ __global__ void __launch_bounds__(FF_NTHR, 3) fir_cluster_kernel(const FirUnit* 
         const FirUnit& U = units[u];
         for (int t = rank; t < FF_TILES; t += CL) fir_p1_tile(U, T, S, t, c);
         ff_cluster_sync();
-        for (int t = rank; t < FF_TILES; t += CL) fir_p2_tile(U, T, S, t, c);
+        for (int t = rank; t < FF_TILES2; t += CL) fir_p2_tile(U, T, S, t, c);
         ff_cluster_sync();
         for (int t = rank; t < FF_TILES; t += CL) fir_p3_tile(U, T, S, t, c);
     }

@@ -460,7 +460,7 @@ static int fir_run_fused(FirPlan* P, ms_stream_t st) {
         const FirUnit* u = P->units_dev + y0;
         cpx* sc = P->scratch + y0 * (size_t)(FF_N * FF_N);
         if (ms_launch<FirP1K>(mk_dim(FF_TILES, yc), FF_NTHR, FF_SMEM1, st, u, P->ft, sc)) return -1;
-        if (ms_launch<FirP2K>(mk_dim(FF_TILES, yc), FF_NTHR, FF_SMEM2, st, u, P->ft, sc)) return -1;
+        if (ms_launch<FirP2K>(mk_dim(FF_TILES2, yc), FF_NTHR, FF_SMEM2, st, u, P->ft, sc)) return -1;
         if (ms_launch<FirP3K>(mk_dim(FF_TILES, yc), FF_NTHR, FF_SMEM1, st, u, P->ft, sc)) return -1;
     }
     return 0;

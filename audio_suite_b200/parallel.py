@@ -113,12 +113,19 @@ class PipelinedGather:
     base preset -- then cost max(render, gather) per pass instead of their sum, without cutting the batch into slices
     (measured on B200: slices render less efficiently -- 20.3 ms unsliced vs 23.6 ms in four slices at N = 2)."""
 
-    def __init__(self, frames, dist, rank, world, device, dst=0, depth=2):
+    def __init__(self, frames, dist, rank, world, device, dst=0, depth=2, collective="gather"):
+        """collective: "gather" (NCCL point-to-point receives on rank `dst`) or "all_gather" (every rank ends up with every
+        slab -- more traffic in total, but it runs on NCCL's ring / NVLS all-gather path instead of seven concurrent
+        point-to-point streams into one GPU)."""
         import torch
         self.dist, self.rank, self.world, self.dst, self.depth = dist, rank, world, dst, depth
         self.frames = int(frames)
+        self.collective = collective
         self.recv = None
-        if rank == dst:
+        if collective == "all_gather":
+            self.full = [torch.empty(world * 2 * self.frames, dtype=torch.float32, device=device) for _ in range(depth)]
+            self.recv = [list(f.view(world, 2 * self.frames).unbind(0)) for f in self.full]
+        elif rank == dst:
             self.recv = [[torch.empty(2 * self.frames, dtype=torch.float32, device=device) for _ in range(world)] for _ in range(depth)]
         self.work = [None] * depth
         self.k = 0
@@ -136,7 +143,10 @@ class PipelinedGather:
         if local.numel() != 2 * self.frames:
             raise ValueError("buffers must have the same size on every rank")
         s = self.k % self.depth
-        self.work[s] = self.dist.gather(local, gather_list=self.recv[s] if self.rank == self.dst else None, dst=self.dst, async_op=True)
+        if self.collective == "all_gather":
+            self.work[s] = self.dist.all_gather_into_tensor(self.full[s], local, async_op=True)
+        else:
+            self.work[s] = self.dist.gather(local, gather_list=self.recv[s] if self.rank == self.dst else None, dst=self.dst, async_op=True)
         self.k += 1
 
     def finish(self):

@@ -48,6 +48,8 @@ def parse():
                          "its launch sequence, so small parts are not launch-bound.  0 = auto (1 at N=1, 4 at N>1)")
     ap.add_argument("--no-graph", action="store_true", help="N>1: launch the parts eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-pipeline", action="store_true", help="N>1: wait for each pass's gather before the next pass starts")
+    ap.add_argument("--collective", default="gather", choices=["gather", "all_gather"],
+                    help="N>1: how the rendered buffers reach rank 0 (parallel.PipelinedGather)")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather of rendered buffers (N>1)")
     ap.add_argument("--config", default="C5", choices=["C1", "C1b", "C2", "C3", "C4", "C5"],
                     help="C5 (default) is the metric's workload; C1..C4 time ONE render of that BASELINE.json config: the kernel "
@@ -252,7 +254,7 @@ def run_ours(args):
     br = brs[0]
     sg = pg = None
     if pipelined:
-        pg = parallel.PipelinedGather(len(mine) * FRAMES_PER_RENDER, dist, rank, world, dev.dev)
+        pg = parallel.PipelinedGather(len(mine) * FRAMES_PER_RENDER, dist, rank, world, dev.dev, collective=args.collective)
         outs = [br.out, torch.empty_like(br.out)]
     elif gather:
         sg = parallel.SlicedGather([per * FRAMES_PER_RENDER] * slices, dist, rank, world, dev.dev)
@@ -447,6 +449,7 @@ def run_ours(args):
                 "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": br.precision, "data": "synthetic",
                 "config": workload_config(args, {"precision_rule": "auto = f64 (engine.choose_precision)" if args.precision == "auto" else args.precision,
+                                                 "collective": args.collective if gather else None,
                                                  "gather": ("NCCL gather of the rendered buffers to rank 0 inside the timed region; pass k is gathered while pass k+1 "
                                                             "renders into a second output buffer, the last gather completes before the closing event" if pipelined else
                                                             ("NCCL gather of rendered buffers to rank 0 inside the step, %d slices per rank, "
