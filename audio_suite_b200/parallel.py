@@ -106,6 +106,16 @@ class SlicedGather:
         return self.recv
 
 
+class _EventWork:
+    """wait(): the current stream waits for the recorded event (the interface of a c10d Work as PipelinedGather uses it)."""
+
+    def __init__(self, ev):
+        self.ev = ev
+
+    def wait(self):
+        self.ev.wait()
+
+
 class PipelinedGather:
     """Gather of per-rank rendered buffers that overlaps with the NEXT pass over the batch: the ranks render pass k+1 into
     the other of two output buffers while NCCL collects pass k on rank `dst` (the collective runs on NCCL's own stream
@@ -125,6 +135,19 @@ class PipelinedGather:
         if collective == "all_gather":
             self.full = [torch.empty(world * 2 * self.frames, dtype=torch.float32, device=device) for _ in range(depth)]
             self.recv = [list(f.view(world, 2 * self.frames).unbind(0)) for f in self.full]
+        elif collective == "peer_copy":
+            # Rank `dst`'s receive slabs live in symmetric memory that every rank maps; a rank stores its slab with ONE
+            # device-to-device copy over NVLink (copy engines: no SMs taken from the rendering kernels, unlike NCCL's
+            # send / receive kernels), bracketed by the symmetric-memory barrier on a side stream.
+            import torch.distributed._symmetric_memory as symm
+            n = depth * world * 2 * self.frames
+            self._sym = symm.empty(n, dtype=torch.float32, device=device)
+            self._hdl = symm.rendezvous(self._sym, dist.group.WORLD)
+            self._remote = self._hdl.get_buffer(dst, (depth, world, 2 * self.frames), torch.float32)
+            self._side = torch.cuda.Stream(device=device)
+            self._torch = torch
+            if rank == dst:
+                self.recv = [list(self._sym.view(depth, world, 2 * self.frames)[d].unbind(0)) for d in range(depth)]
         elif rank == dst:
             self.recv = [[torch.empty(2 * self.frames, dtype=torch.float32, device=device) for _ in range(world)] for _ in range(depth)]
         self.work = [None] * depth
@@ -145,6 +168,16 @@ class PipelinedGather:
         s = self.k % self.depth
         if self.collective == "all_gather":
             self.work[s] = self.dist.all_gather_into_tensor(self.full[s], local, async_op=True)
+        elif self.collective == "peer_copy":
+            torch = self._torch
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                self._hdl.barrier(channel=0)          # rank dst has let go of slot s (its consumer ran before this call)
+                self._remote[s, self.rank].copy_(local, non_blocking=True)
+                self._hdl.barrier(channel=1)          # every rank's store has landed
+                ev = torch.cuda.Event()
+                ev.record()
+            self.work[s] = _EventWork(ev)
         else:
             self.work[s] = self.dist.gather(local, gather_list=self.recv[s] if self.rank == self.dst else None, dst=self.dst, async_op=True)
         self.k += 1

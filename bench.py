@@ -48,7 +48,7 @@ def parse():
                          "its launch sequence, so small parts are not launch-bound.  0 = auto (1 at N=1, 4 at N>1)")
     ap.add_argument("--no-graph", action="store_true", help="N>1: launch the parts eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-pipeline", action="store_true", help="N>1: wait for each pass's gather before the next pass starts")
-    ap.add_argument("--collective", default="gather", choices=["gather", "all_gather"],
+    ap.add_argument("--collective", default="gather", choices=["gather", "all_gather", "peer_copy"],
                     help="N>1: how the rendered buffers reach rank 0 (parallel.PipelinedGather)")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather of rendered buffers (N>1)")
     ap.add_argument("--config", default="C5", choices=["C1", "C1b", "C2", "C3", "C4", "C5"],
