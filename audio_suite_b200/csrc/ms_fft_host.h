@@ -34,6 +34,11 @@ template <int LD, int MODE, int ST, int SQ = 0> struct RowsK {
     static constexpr int MINB = (SQ && sizeof(real) == 8) ? MS_SQ_MINB : MS_FFT_MINB;
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_rows_body<LD, MODE, ST, SQ>(jobs, c); }
 };
+struct SpecOpK {                                                    // spectral operators, elementwise, in front of the inverse
+    static constexpr int MAXT = SPECOP_NTHR;
+    static constexpr int MINB = 4;
+    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { spec_op_body(jobs, c); }
+};
 // tile width of the static 256 x 256 kernels: what plan_direct picks for 65536 points in this precision
 static const int MS_SQ = (sizeof(real) == 4 ? 8192 : 4096) / 2 / 256;
 struct GenChirpK {
@@ -297,6 +302,8 @@ private:
             default: return L<ColsK<LD, ST, TWID, 0, 1024>>(gx, gy, 256, smem, st, jd);
         }
     }
+    // development switch MS_SPEC_PASS=0: the operators inside the load functor of the inverse columns (round 1 form)
+    static bool spec_pass() { static int v = -1; if (v < 0) { const char* e = getenv("MS_SPEC_PASS"); v = (e && e[0] == '0') ? 0 : 1; } return v != 0; }
     // development switch MS_SB_WARP=0: the block-wide B1 = 256 kernel instead of the warp-local one
     static bool sb_warp() { static int v = -1; if (v < 0) { const char* e = getenv("MS_SB_WARP"); v = (e && e[0] == '0') ? 0 : 1; } return v != 0; }
     template <int LD, int MODE, int ST, int SQ = 0>
@@ -392,6 +399,16 @@ private:
                     rc = sb ? launch_cols_sb<LD_PAIR, ST_WORK, 1>(sb, C.gx, gy, st, jd)
                             : launch_cols<LD_PAIR, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
                     if (!rc) rc = launch_rows<LD_WORK, MODE_NAT, ST_Z>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
+                } else if (spec_pass()) {
+                    // operators in their own elementwise pass (Z -> work), then the inverse in place in `work`: a columns
+                    // tile reads exactly the positions it writes back
+                    int nmax = 0;
+                    for (size_t i = b; i < e; ++i) nmax = std::max(nmax, jobs[i].n);
+                    const unsigned gxo = (unsigned)((nmax / 2 + 1 + SPECOP_NTHR * SPECOP_PER - 1) / (SPECOP_NTHR * SPECOP_PER));
+                    rc = L<SpecOpK>(gxo, gy, SPECOP_NTHR, MS_JOB_SMEM, st, jd);
+                    if (!rc) rc = sb ? launch_cols_sb<LD_WORK, ST_WORK, 1>(sb, C.gx, gy, st, jd)
+                                     : launch_cols<LD_WORK, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    if (!rc) rc = launch_rows<LD_WORK, MODE_NAT, ST_PAIR>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
                 } else {
                     rc = sb ? launch_cols_sb<LD_SPEC, ST_WORK, 1>(sb, C.gx, gy, st, jd)
                             : launch_cols<LD_SPEC, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);

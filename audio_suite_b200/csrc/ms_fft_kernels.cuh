@@ -297,6 +297,30 @@ MS_DEV const FftJob& stage_job(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
     return *(const FftJob*)c.smem;
 }
 
+// ---- spectral operator pass ---------------------------------------------------------------------------
+// swap(Y[k]) for every natural k in [0, n) into `work`, in front of a plain-load inverse (two-pass lengths).  A thread owns
+// folded bins kk and writes both k = kk and k = n - kk: consecutive threads gather at consecutive bins (the stretch /
+// warp gathers of a warp fall into a few sectors), where the columns tile of the inverse would gather F1 rows F2 apart.
+#define SPECOP_NTHR 256
+#define SPECOP_PER 4
+MS_DEV void spec_op_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
+    const FftJob& J = stage_job(jobs, c);
+    const int n = J.n, kmax = n >> 1;
+    const int kk0 = c.bx * (SPECOP_NTHR * SPECOP_PER) + c.tid;
+    if (c.bx * (SPECOP_NTHR * SPECOP_PER) > kmax) return;
+    const int paired = J.in_b != nullptr;
+#pragma unroll 2
+    for (int u = 0; u < SPECOP_PER; ++u) {
+        const int kk = kk0 + u * SPECOP_NTHR;
+        if (kk > kmax) break;
+        cpx ya = op_value(J.op[0], J.Z, n, kk, 0, paired);
+        cpx yb = paired ? op_value(J.op[1], J.Z, n, kk, 1, paired) : c_zero();
+        if (kk == 0 || (!(n & 1) && kk == kmax)) { ya.y = (real)0.; yb.y = (real)0.; }
+        J.work[kk] = mk(ya.y + yb.x, ya.x - yb.y);                                  // swap(Y[kk])
+        if (kk != 0 && kk != n - kk) J.work[n - kk] = mk(yb.x - ya.y, ya.x + yb.y);   // swap(Y[n - kk]): both spectra conjugated
+    }
+}
+
 // ---- columns kernel --------------------------------------------------------------------------------
 // SQ != 0: static geometry F1 = F2 = 256, T = G = SQ, plain mixed radix (the 65536-point transforms of the FIR stage)
 // SB != 0: in-tile Bluestein with static convolution length B1 = SB and T = MS_SB_TILE / SB full columns, in place

@@ -48,8 +48,10 @@ def parse():
                          "its launch sequence, so small parts are not launch-bound.  0 = auto (1 at N=1, 4 at N>1)")
     ap.add_argument("--no-graph", action="store_true", help="N>1: launch the parts eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-pipeline", action="store_true", help="N>1: wait for each pass's gather before the next pass starts")
-    ap.add_argument("--collective", default="gather", choices=["gather", "all_gather", "peer_copy"],
-                    help="N>1: how the rendered buffers reach rank 0 (parallel.PipelinedGather)")
+    ap.add_argument("--collective", default="peer_copy", choices=["gather", "all_gather", "peer_copy"],
+                    help="N>1: how the rendered buffers reach rank 0 (parallel.PipelinedGather): peer_copy = every rank stores its slab "
+                         "into rank 0's symmetric-memory buffer over NVLink with the copy engines (falls back to the NCCL gather, and "
+                         "says so in config, if symmetric memory cannot be set up); gather / all_gather = NCCL")
     ap.add_argument("--no-gather", action="store_true", help="skip the NCCL gather of rendered buffers (N>1)")
     ap.add_argument("--config", default="C5", choices=["C1", "C1b", "C2", "C3", "C4", "C5"],
                     help="C5 (default) is the metric's workload; C1..C4 time ONE render of that BASELINE.json config: the kernel "
@@ -254,7 +256,21 @@ def run_ours(args):
     br = brs[0]
     sg = pg = None
     if pipelined:
-        pg = parallel.PipelinedGather(len(mine) * FRAMES_PER_RENDER, dist, rank, world, dev.dev, collective=args.collective)
+        collective = args.collective
+        if collective == "peer_copy":
+            # all ranks must take the same branch: agree on whether symmetric memory came up everywhere
+            try:
+                pg = parallel.PipelinedGather(len(mine) * FRAMES_PER_RENDER, dist, rank, world, dev.dev, collective="peer_copy")
+                okflag = 1
+            except Exception as exc:                       # noqa: BLE001 -- reported, not hidden: config.collective says "gather"
+                print("rank %d: symmetric memory unavailable (%s); NCCL gather instead" % (rank, exc), file=sys.stderr)
+                pg, okflag = None, 0
+            t = torch.tensor([okflag], dtype=torch.int32, device=dev.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0:
+                collective, pg = "gather", None
+        if pg is None:
+            pg = parallel.PipelinedGather(len(mine) * FRAMES_PER_RENDER, dist, rank, world, dev.dev, collective=collective)
         outs = [br.out, torch.empty_like(br.out)]
     elif gather:
         sg = parallel.SlicedGather([per * FRAMES_PER_RENDER] * slices, dist, rank, world, dev.dev)
@@ -449,8 +465,10 @@ def run_ours(args):
                 "ms_per_step": ms_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": br.precision, "data": "synthetic",
                 "config": workload_config(args, {"precision_rule": "auto = f64 (engine.choose_precision)" if args.precision == "auto" else args.precision,
-                                                 "collective": args.collective if gather else None,
-                                                 "gather": ("NCCL gather of the rendered buffers to rank 0 inside the timed region; pass k is gathered while pass k+1 "
+                                                 "collective": (collective if pipelined else "gather") if gather else None,
+                                                 "gather": (("every rank stores its rendered buffer into rank 0's symmetric-memory receive slab over NVLink (copy engines, symmetric-memory "
+                                                             "barriers on a side stream)" if collective == "peer_copy" else "NCCL %s of the rendered buffers to rank 0" % collective) +
+                                                            " inside the timed region; pass k is gathered while pass k+1 "
                                                             "renders into a second output buffer, the last gather completes before the closing event" if pipelined else
                                                             ("NCCL gather of rendered buffers to rank 0 inside the step, %d slices per rank, "
                                                              "slice k gathered while slice k+1 renders; %s" % (
