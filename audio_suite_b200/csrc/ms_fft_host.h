@@ -154,6 +154,17 @@ private:
         return 0;
     }
 
+    // development switch MS_PLAN_W="c128,c256,c512,c1024,rows": per-element cost of the in-tile Bluestein columns by convolution
+    // length and of one radix-2 level of the rows pass (unset: the analytic cost)
+    static const double* mixed_weights() {
+        static double w[5] = {-1, 0, 0, 0, 0}; static int init = 0;
+        if (!init) {
+            init = 1;
+            const char* e = getenv("MS_PLAN_W");
+            if (e && sscanf(e, "%lf,%lf,%lf,%lf,%lf", &w[0], &w[1], &w[2], &w[3], &w[4]) != 5) w[0] = -1;
+        }
+        return w;
+    }
     static bool plan_direct(int n, FftJob& J) {
         if (!ms_is_smooth(n)) return false;
         J.M = n;
@@ -192,6 +203,12 @@ private:
             for (int t = f2; t > 1; t >>= 1) lg2 += 1;
             for (int t = b1; t > 1; t >>= 1) lgb += 1;
             double cost = lg2 + 2.0 * lgb * (double)b1 / (double)f1 + (T < 8 ? 16.0 / T : 0) + (G < 8 ? 16.0 / G : 0);
+            if (mixed_weights()[0] > 0) {
+                // measured form: padded elements per useful one times the per-element cost of that columns kernel
+                const double* w = mixed_weights();
+                const double cb = b1 <= 128 ? w[0] : b1 == 256 ? w[1] : b1 == 512 ? w[2] : b1 == 1024 ? w[3] : w[3] * (double)b1 / 1024.0;
+                cost = w[4] * lg2 + cb * (double)b1 / (double)f1 + (T < 8 ? 16.0 / T : 0) + (G < 8 ? 16.0 / G : 0);
+            }
             if (!best || cost < best_cost) { best = f2; best_cost = cost; }
         }
         if (!best) return false;

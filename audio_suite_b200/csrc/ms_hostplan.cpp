@@ -18,6 +18,8 @@
 #include <vector>
 #include <string>
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include "../../include/microsound_b200.h"
 #include "ms_zig_exp_tables.h"
 
@@ -193,21 +195,35 @@ static bool same_env(const EnvKey& k, const EnvKey& o) {
            k.inv_a == o.inv_a && k.inv_d == o.inv_d && k.inv_r == o.inv_r && k.S == o.S && k.curve == o.curve;
 }
 
-static int plan_chunk(Plan& P, const double* rows, int R, const Lanes& L, const int64_t* ir_len, const double* bessel, int n_coef) {
+// per-render scalars that the second (sequential) pass needs
+struct Scal {
+    std::vector<int64_t> mono_at, fir_of, st_dl, st_dr;
+    std::vector<int> stereo_on, bessel_id;
+    std::vector<double> st_theta, drive, peak;
+    void resize(size_t n) {
+        mono_at.resize(n); fir_of.assign(n, -1); st_dl.resize(n); st_dr.resize(n); stereo_on.resize(n); bessel_id.resize(n);
+        st_theta.resize(n); drive.resize(n); peak.resize(n);
+    }
+};
+// Renders [r0, r1) planned into P with every offset RELATIVE to the start of the range (pool, mono plane, event / tap / dust /
+// FIR record indices, filter pool); `fir.ir` holds the impulse response ID (-2: the unit impulse) until append_part()
+// resolves it.  Ranges are independent, so a slice is planned by several threads and appended in order.
+static int plan_range(Plan& P, Scal& SC, const double* rows, int r0, int r1, const Lanes& L, const int64_t* ir_len) {
+    const int R = r1 - r0;
     P.pool_n = P.mono_n = P.frames = P.h_total = P.max_h = P.max_out_n = P.env_n = P.n_ir = 0;
     memset(P.alg, 0, sizeof P.alg);
-    P.ola_r.resize(R); P.post.resize(R);
-    P.out_at.resize(R); P.out_n.resize(R); P.y_at.resize(R); P.last.assign(3 * (size_t)R, -1); P.srs.resize(2 * (size_t)R);
-    std::vector<int64_t> mono_at(R), fir_of(R, -1);
-    std::vector<int64_t> ir_at_of;                  // per entry of ir_order: offset in the irs pool
-    std::vector<EnvKey> envs;
-    std::vector<int> stereo_on(R); std::vector<int64_t> st_dl(R), st_dr(R); std::vector<double> st_theta(R), drive(R), peak(R);
-    std::vector<int> bessel_id(R);
-    int64_t delta_at = -1;
+    P.error_render = -1;
+    P.ola_r.resize(R);
+    P.out_n.resize(R); P.last.assign(3 * (size_t)R, -1); P.srs.resize(2 * (size_t)R);
+    SC.resize((size_t)R);
+    std::vector<int64_t>& mono_at = SC.mono_at; std::vector<int64_t>& fir_of = SC.fir_of;
+    std::vector<int>& stereo_on = SC.stereo_on; std::vector<int64_t>& st_dl = SC.st_dl; std::vector<int64_t>& st_dr = SC.st_dr;
+    std::vector<double>& st_theta = SC.st_theta; std::vector<double>& drive = SC.drive; std::vector<double>& peak = SC.peak;
+    std::vector<int>& bessel_id = SC.bessel_id;
     std::vector<double> times;
     std::vector<uint64_t> dbits; std::vector<int32_t> dlast; std::vector<double> dvals, er_dl, er_ga;
     for (int r = 0; r < R; ++r) {
-        const double* p = rows + (size_t)r * F_COUNT;
+        const double* p = rows + (size_t)(r0 + r) * F_COUNT;
         const long long base_sr = (long long)p[F_base_sr];
         const double out_dur = p[F_out_dur_s];
         long long out_n = (long long)py_round(out_dur * (double)base_sr);
@@ -240,7 +256,7 @@ static int plan_chunk(Plan& P, const double* rows, int R, const Lanes& L, const 
         const long long rel = std::max(0ll, (long long)py_round((double)base_sr * p[F_env_r] / 1000.0));
         const double S = clampd(p[F_env_s], 0.0, 1.0), curve = std::max(1e-6, p[F_env_curve]);
         const long long n_out = out_n;
-        if (a > n_out) { P.error = "adsr"; P.error_render = r; return -1; }
+        if (a > n_out) { P.error = "adsr"; P.error_render = r0 + r; return -1; }
         const long long d_end = d > 0 ? std::min(n_out, a + d) : a;
         const long long sus_end = std::max(d_end, n_out - rel);
         const int64_t ev_begin = (int64_t)P.ola_e.size();
@@ -364,21 +380,15 @@ static int plan_chunk(Plan& P, const double* rows, int R, const Lanes& L, const 
                 P.alg[3] += length;
             }
         }
-        // ---- envelope description (tables.pack_chunk) and sharing
-        EnvKey key; key.n = n_out; key.a = a; key.d_end = d_end; key.sus_end = sus_end; key.has_rel = (rel > 0 && n_out > sus_end) ? 1 : 0;
-        key.inv_a = a > 0 ? 1.0 / (double)a : 0.0; key.inv_d = d_end > a ? 1.0 / (double)(d_end - a) : 0.0;
-        key.inv_r = n_out - sus_end > 1 ? 1.0 / (double)(n_out - sus_end - 1) : 0.0; key.S = S; key.curve = curve;
-        {
-            size_t k = 0;
-            for (; k < envs.size(); ++k) if (same_env(envs[k], key)) break;
-            if (k == envs.size()) envs.push_back(key);
-            envs[k].members.push_back(r);
-        }
+        // ---- envelope description (tables.pack_chunk); sharing is decided over the whole slice (finish_plan)
+        const int64_t has_rel = (rel > 0 && n_out > sus_end) ? 1 : 0;
+        const double inv_a = a > 0 ? 1.0 / (double)a : 0.0, inv_d = d_end > a ? 1.0 / (double)(d_end - a) : 0.0;
+        const double inv_r = n_out - sus_end > 1 ? 1.0 / (double)(n_out - sus_end - 1) : 0.0;
         ms_ola_render& orr = P.ola_r[r];
         memset(&orr, 0, sizeof orr);
         orr.out = P.mono_n; orr.out_n = (int32_t)n_out; orr.ev_begin = (int32_t)ev_begin; orr.ev_end = (int32_t)P.ola_e.size(); orr.max_len = (int32_t)max_len;
-        orr.A = (int32_t)a; orr.D_end = (int32_t)d_end; orr.sus_end = (int32_t)sus_end; orr.has_release = (int32_t)key.has_rel;
-        orr.inv_A = key.inv_a; orr.inv_D = key.inv_d; orr.inv_R = key.inv_r; orr.S = S; orr.curve = curve; orr.env = -1;
+        orr.A = (int32_t)a; orr.D_end = (int32_t)d_end; orr.sus_end = (int32_t)sus_end; orr.has_release = (int32_t)has_rel;
+        orr.inv_A = inv_a; orr.inv_D = inv_d; orr.inv_R = inv_r; orr.S = S; orr.curve = curve; orr.env = -1;
         P.alg[3] += n_out;
         // ---- reflection cloud (main_v2.py:410-417) + impulse response -> one FIR
         int64_t t_begin = (int64_t)P.tap_off.size(), max_tap = 0; int has_er = 0;
@@ -400,20 +410,16 @@ static int plan_chunk(Plan& P, const double* rows, int R, const Lanes& L, const 
                 }
             }
             has_er = kept > 0;
-            if (kept > 4096) { P.error = "er_taps"; P.error_render = r; return -1; }
+            if (kept > 4096) { P.error = "er_taps"; P.error_render = r0 + r; return -1; }
         }
         const int ir_id = p[F_space_ir_on] != 0.0 ? (int)p[F_ir_id] : -1;
         if (has_er || ir_id >= 0) {
             int64_t ir_at, irl;
             if (ir_id >= 0) {
-                size_t k = 0;
-                for (; k < P.ir_order.size(); ++k) if (P.ir_order[k] == ir_id) break;
-                if (k == P.ir_order.size()) { P.ir_order.push_back(ir_id); ir_at_of.push_back(P.n_ir); P.n_ir += ir_len[ir_id]; }
-                ir_at = ir_at_of[k]; irl = ir_len[ir_id];
+                ir_at = ir_id; irl = ir_len[ir_id];
                 P.alg[4] += 2 * n_out; P.alg[5] += irl;
             } else {
-                if (delta_at < 0) { delta_at = P.n_ir; P.ir_order.push_back(-2); ir_at_of.push_back(P.n_ir); P.n_ir += 1; }
-                ir_at = delta_at; irl = 1;
+                ir_at = -2; irl = 1;
             }
             int64_t h_len = irl;
             if (has_er) { h_len = irl + max_tap; P.alg[4] += 2 * n_out; }
@@ -442,6 +448,66 @@ static int plan_chunk(Plan& P, const double* rows, int R, const Lanes& L, const 
         drive[r] = p[F_sat_drive]; peak[r] = p[F_peak]; bessel_id[r] = (int)p[F_bessel_id];
         P.out_n[r] = n_out;
     }
+    return 0;
+}
+
+template <class T> static void append(std::vector<T>& d, const std::vector<T>& s) { d.insert(d.end(), s.begin(), s.end()); }
+
+// Appends the range plan `Q` (relative offsets) to the slice plan `P`; returns the number of renders appended.
+static void append_part(Plan& P, Scal& S, const Plan& Q, const Scal& QS, std::vector<int64_t>& ir_at_of, int64_t& delta_at, const int64_t* ir_len) {
+    const int64_t pool_b = P.pool_n, mono_b = P.mono_n, ev_b = (int64_t)P.ola_e.size(), fir_b = (int64_t)P.fir.size();
+    const int64_t tap_b = (int64_t)P.tap_off.size(), dust_b = (int64_t)P.dust_pos.size(), h_b = P.h_total;
+    const size_t R = Q.ola_r.size();
+    for (size_t i = 0; i < Q.sy1.size(); ++i) {
+        ms_synth_evt s1 = Q.sy1[i], s2 = Q.sy2[i];
+        s1.out += pool_b; s2.out += pool_b;
+        if (s1.mode == MODE_DUST) s1.dust_begin += dust_b;
+        if (s2.mode != -1) s2.aux += pool_b;
+        P.sy1.push_back(s1); P.sy2.push_back(s2);
+    }
+    for (ms_ola_evt e : Q.ola_e) { e.grain += pool_b; P.ola_e.push_back(e); }
+    for (ms_ola_render o : Q.ola_r) { o.out += mono_b; o.ev_begin += (int32_t)ev_b; o.ev_end += (int32_t)ev_b; P.ola_r.push_back(o); }
+    for (ms_fir_render f : Q.fir) {
+        // impulse responses in order of first use; the unit impulse (reflections without an IR) is one more entry
+        const int64_t id = f.ir;
+        if (id >= 0) {
+            size_t k = 0;
+            for (; k < P.ir_order.size(); ++k) if (P.ir_order[k] == id) break;
+            if (k == P.ir_order.size()) { P.ir_order.push_back(id); ir_at_of.push_back(P.n_ir); P.n_ir += ir_len[id]; }
+            f.ir = ir_at_of[k];
+        } else {
+            if (delta_at < 0) { delta_at = P.n_ir; P.ir_order.push_back(-2); ir_at_of.push_back(P.n_ir); P.n_ir += 1; }
+            f.ir = delta_at;
+        }
+        f.h += h_b; f.tap_begin += (int32_t)tap_b; f.tap_end += (int32_t)tap_b; f.x += mono_b;
+        P.fir.push_back(f);
+    }
+    append(P.tap_off, Q.tap_off); append(P.tap_delay, Q.tap_delay); append(P.tap_raw, Q.tap_raw);
+    append(P.dust_pos, Q.dust_pos); append(P.dust_val, Q.dust_val);
+    for (Item it : Q.tilt) { it.src += pool_b; it.dst += pool_b; P.tilt.push_back(it); }
+    for (Item it : Q.grain) { it.src += pool_b; it.dst += pool_b; P.grain.push_back(it); }
+    for (size_t r = 0; r < R; ++r) {
+        for (int k = 0; k < 2; ++k) { const int64_t v = Q.last[3 * r + k]; P.last.push_back(v < 0 ? v : v + pool_b); }
+        P.last.push_back(Q.last[3 * r + 2]);
+        S.mono_at.push_back(QS.mono_at[r] + mono_b);
+        S.fir_of.push_back(QS.fir_of[r] < 0 ? -1 : QS.fir_of[r] + fir_b);
+    }
+    append(P.out_n, Q.out_n); append(P.srs, Q.srs);
+    append(S.stereo_on, QS.stereo_on); append(S.st_dl, QS.st_dl); append(S.st_dr, QS.st_dr); append(S.st_theta, QS.st_theta);
+    append(S.drive, QS.drive); append(S.peak, QS.peak); append(S.bessel_id, QS.bessel_id);
+    P.pool_n += Q.pool_n; P.mono_n += Q.mono_n; P.h_total += Q.h_total;
+    P.max_h = std::max(P.max_h, Q.max_h); P.max_out_n = std::max(P.max_out_n, Q.max_out_n);
+    for (int k = 0; k < 7; ++k) P.alg[k] += Q.alg[k];
+}
+
+// Output planes, post records, shared envelopes: the part of the plan that looks at the slice as a whole.
+static void finish_plan(Plan& P, const Scal& S, const double* bessel, int n_coef) {
+    const int R = (int)P.ola_r.size();
+    P.post.resize(R); P.out_at.resize(R); P.y_at.resize(R);
+    const std::vector<int64_t>& mono_at = S.mono_at; const std::vector<int64_t>& fir_of = S.fir_of;
+    const std::vector<int>& stereo_on = S.stereo_on; const std::vector<int64_t>& st_dl = S.st_dl; const std::vector<int64_t>& st_dr = S.st_dr;
+    const std::vector<double>& st_theta = S.st_theta; const std::vector<double>& drive = S.drive; const std::vector<double>& peak = S.peak;
+    const std::vector<int>& bessel_id = S.bessel_id;
     // ---- second pass: output planes, post records
     const int64_t plane = P.mono_n;
     int64_t extra = 0;
@@ -475,6 +541,16 @@ static int plan_chunk(Plan& P, const double* rows, int R, const Lanes& L, const 
         P.alg[6] += n;
     }
     // ---- envelopes shared by several renders are tabulated once
+    std::vector<EnvKey> envs;
+    for (int r = 0; r < R; ++r) {
+        const ms_ola_render& o = P.ola_r[(size_t)r];
+        EnvKey key; key.n = o.out_n; key.a = o.A; key.d_end = o.D_end; key.sus_end = o.sus_end; key.has_rel = o.has_release;
+        key.inv_a = o.inv_A; key.inv_d = o.inv_D; key.inv_r = o.inv_R; key.S = o.S; key.curve = o.curve;
+        size_t k = 0;
+        for (; k < envs.size(); ++k) if (same_env(envs[k], key)) break;
+        if (k == envs.size()) envs.push_back(key);
+        envs[k].members.push_back(r);
+    }
     for (size_t k = 0; k < envs.size(); ++k) {
         if (envs[k].members.size() < 2) continue;
         for (int m : envs[k].members) P.ola_r[(size_t)m].env = P.env_n;
@@ -482,6 +558,34 @@ static int plan_chunk(Plan& P, const double* rows, int R, const Lanes& L, const 
         P.env_n += envs[k].n;
     }
     P.mono_n = 2 * plane + extra;
+}
+
+// A slice in blocks of HP_BLOCK renders, the blocks handed out to `threads` threads and appended in order.
+static const int HP_BLOCK = 32;
+static int plan_chunk(Plan& P, const double* rows, int R, const Lanes& L, const int64_t* ir_len, const double* bessel, int n_coef, int threads) {
+    P.pool_n = P.mono_n = P.frames = P.h_total = P.max_h = P.max_out_n = P.env_n = P.n_ir = 0;
+    memset(P.alg, 0, sizeof P.alg);
+    const int nb = (R + HP_BLOCK - 1) / HP_BLOCK;
+    std::vector<Plan> parts((size_t)nb); std::vector<Scal> scal((size_t)nb);
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int b = next.fetch_add(1);
+            if (b >= nb) return;
+            plan_range(parts[(size_t)b], scal[(size_t)b], rows, b * HP_BLOCK, std::min(R, (b + 1) * HP_BLOCK), L, ir_len);
+        }
+    };
+    const int T = std::max(1, std::min(threads, nb));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(work);
+    work();
+    for (std::thread& t : pool) t.join();
+    Scal S; std::vector<int64_t> ir_at_of; int64_t delta_at = -1;
+    for (int b = 0; b < nb; ++b) {
+        if (parts[(size_t)b].error_render >= 0) { P.error = parts[(size_t)b].error; P.error_render = parts[(size_t)b].error_render; return -1; }
+        append_part(P, S, parts[(size_t)b], scal[(size_t)b], ir_at_of, delta_at, ir_len);
+    }
+    finish_plan(P, S, bessel, n_coef);
     return 0;
 }
 
@@ -507,11 +611,11 @@ void ms_hp_draws(int64_t seed, int kind, uint64_t high, int n, double* out) {
     }
 }
 void* ms_hp_plan(const double* rows, int n_renders, const int64_t* lane_ptr, const double* lane_t, const double* lane_v,
-                 const int64_t* ir_len, const double* bessel, int n_coef) {
+                 const int64_t* ir_len, const double* bessel, int n_coef, int threads) {
     Plan* P = new Plan();
     P->error_render = -1;
     Lanes L; L.ptr = lane_ptr; L.t = lane_t; L.v = lane_v;
-    plan_chunk(*P, rows, n_renders, L, ir_len, bessel, n_coef);
+    plan_chunk(*P, rows, n_renders, L, ir_len, bessel, n_coef, threads);
     return P;
 }
 const char* ms_hp_error(void* h, int* render) { Plan* P = (Plan*)h; *render = P->error_render; return P->error.c_str(); }

@@ -667,13 +667,24 @@ def render_batch(params_list, device=None, precision="auto", host_out=None, chun
     """See _render_batch.  The cyclic garbage collector is paused for the duration of the call: a full collection over a
     few thousand parameter dicts costs ~35 ms (measured: every fifth 100 ms sweep took 135 ms) and nothing here makes cycles."""
     import gc
+    import sys
     was = gc.isenabled()
     gc.disable()
+    # the launching thread shares the interpreter with the planning threads: with the default 5 ms switch interval every
+    # return from a ctypes / CUDA call could wait that long for the lock (measured: 5-7 ms per slice set-up instead of 2)
+    si = sys.getswitchinterval()
+    sys.setswitchinterval(1e-4)
     try:
         return _render_batch(params_list, device, precision, host_out, chunk, depth, workers, piece, ramp)
     finally:
+        sys.setswitchinterval(si)
         if was:
             gc.enable()
+
+
+def _os_env(name):
+    import os
+    return os.environ.get(name, "")
 
 
 def _render_batch(params_list, device=None, precision="auto", host_out=None, chunk=512, depth=3, workers=None, piece=32, ramp=True):
@@ -694,6 +705,9 @@ def _render_batch(params_list, device=None, precision="auto", host_out=None, chu
         # (a finer ramp -- 32, 64, 128, 256 ... -- was measured slower: 99 ms against 92 ms; every slice costs ~1 ms of host work)
         head = [max(piece, c // 4), max(piece, c // 2)]
         tail = [max(piece, c // 2), max(piece, c // 4), max(piece, c // 4)]
+        if _os_env("MS_RAMP"):                     # development switch: "head sizes / tail sizes", e.g. "64,128,256/256,128,64"
+            h_, t_ = _os_env("MS_RAMP").split("/")
+            head, tail = [int(x) for x in h_.split(",") if x], [int(x) for x in t_.split(",") if x]
         body = max(0, n - sum(head) - sum(tail))
         chunk = head + [c] * (body // c) + ([body % c] if body % c else []) + tail
     if not hasattr(dev, "torch"):                   # host emulator device (tests): one slice after the other

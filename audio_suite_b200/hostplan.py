@@ -43,7 +43,7 @@ def lib():
             l = C.CDLL(LIB_PATH)
             l.ms_hp_field_count.restype = C.c_int
             l.ms_hp_plan.restype = C.c_void_p
-            l.ms_hp_plan.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            l.ms_hp_plan.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
             l.ms_hp_error.restype = C.c_char_p
             l.ms_hp_error.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
             l.ms_hp_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -100,7 +100,15 @@ def _marshal(params_list):
     R = len(params_list)
     rows = np.zeros((R, len(FIELDS)), np.float64)
     try:
-        rows[:, _NUM_COL] = np.array([_get_num(p) for p in params_list], dtype=np.float64)
+        # (blocks of 64 with a GIL hand-over in between: a planning thread must not keep the launching thread waiting for
+        #  the ~3 ms a 512-render slice takes to convert)
+        import time as _time
+        num = []
+        for b in range(0, R, 64):
+            num += [_get_num(p) for p in params_list[b:b + 64]]
+            if b + 64 < R:
+                _time.sleep(0)
+        rows[:, _NUM_COL] = np.array(num, dtype=np.float64)
     except (TypeError, ValueError):          # numbers given as strings and the like: the reference's float() / int() accept them
         rows[:, _NUM_COL] = np.array([[float(p[k]) for k in _NUM] for p in params_list], dtype=np.float64)
     rows[:, _INT_COL] = np.trunc(rows[:, _INT_COL])
@@ -163,14 +171,24 @@ def _marshal(params_list):
 _SIDE_COL = [FIELDS.index(k) for k in ("gen_mode", "unfold_mode", "event_process", "bp_density", "bp_unfold", "bp_cutoff", "bp_stretch", "_ir", "_bessel")]
 
 
-def plan_chunk(params_list):
-    """Packed Tables (tables.Tables) of a list of supported renders -- what tables.pack_chunk(plan_render(p) ...) returns."""
+def default_threads():
+    """Native planning threads per slice: the cores this process may use, less two for the launching and the prefetching
+    thread, shared between the ranks of the node."""
+    t = int(os.environ.get("MS_PLAN_THREADS", "0"))
+    if t > 0:
+        return t
+    return max(1, min(8, (len(os.sched_getaffinity(0)) - 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+
+
+def plan_chunk(params_list, threads=1):
+    """Packed Tables (tables.Tables) of a list of supported renders -- what tables.pack_chunk(plan_render(p) ...) returns.
+    `threads`: the native call plans blocks of 32 renders on that many threads and appends them in order (same tables)."""
     from . import tables as T
     l = lib()
     R = len(params_list)
     rows, lane_ptr, lane_t, lane_v, irs, ir_len, btab = _marshal(params_list)
     h = l.ms_hp_plan(rows.ctypes.data, R, lane_ptr.ctypes.data, lane_t.ctypes.data, lane_v.ctypes.data, ir_len.ctypes.data,
-                     btab.ctypes.data, int(btab.shape[1]))
+                     btab.ctypes.data, int(btab.shape[1]), max(1, int(threads)))
     try:
         bad = C.c_int(-1)
         err = l.ms_hp_error(h, C.byref(bad))
@@ -223,23 +241,6 @@ def plan_chunk(params_list):
     return t
 
 
-_POOL = None
-
-
 def plan_slice(params_list, threads=None):
-    """plan_chunk over a slice, split across a few threads (the native call releases the GIL; marshalling does not) and
-    merged with tables.merge_chunks -- the same relocation the worker-process path uses."""
-    from . import tables as T
-    n = len(params_list)
-    if threads is None:
-        threads = int(os.environ.get("MS_PLAN_THREADS", "0")) or max(1, min(8, (len(os.sched_getaffinity(0)) - 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
-    parts = max(1, min(threads, n // 64))
-    if parts <= 1:
-        return plan_chunk(params_list)
-    global _POOL
-    if _POOL is None or _POOL._max_workers < parts:
-        from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=max(parts, 8), thread_name_prefix="ms-hostplan")
-    cuts = [n * i // parts for i in range(parts + 1)]
-    subs = list(_POOL.map(plan_chunk, [params_list[a:b] for a, b in zip(cuts[:-1], cuts[1:])]))
-    return T.merge_chunks(subs)
+    """plan_chunk with the default thread count (the native call splits the slice itself)."""
+    return plan_chunk(params_list, default_threads() if threads is None else threads)

@@ -717,12 +717,13 @@ def plan_stream(params_list, chunk, workers=None, piece=32):
     native = [hostplan.lib() is not None and not os.environ.get("MS_PLAN_PYTHON") and all(hostplan.supported(p) for p in params_list[a:b])
               for a, b in cuts]
     if all(native) and len(cuts) > 1 and workers > 1:
-        # whole slices are planned ahead by a few threads (slice-level parallelism: marshalling holds the GIL for ~5 us per
-        # render, the native call releases it) and handed over in order; nothing is merged or pickled
+        # two Python threads alternate over the slices (one converts the parameters of slice k+1 while the native call of
+        # slice k -- which releases the GIL and plans blocks of renders on its own threads -- runs); slices come out in order
         from concurrent.futures import ThreadPoolExecutor
-        nthr = int(os.environ.get("MS_PLAN_THREADS", "0")) or max(1, min(4, workers))
-        with ThreadPoolExecutor(max_workers=nthr, thread_name_prefix="ms-hostplan") as ex:
-            futs = [ex.submit(hostplan.plan_chunk, params_list[a:b]) for a, b in cuts]
+        nthr = hostplan.default_threads() if not os.environ.get("MS_PLAN_THREADS") else int(os.environ["MS_PLAN_THREADS"])
+        nthr = max(1, min(nthr, workers))
+        with ThreadPoolExecutor(max_workers=2, thread_name_prefix="ms-hostplan") as ex:
+            futs = [ex.submit(hostplan.plan_chunk, params_list[a:b], nthr) for a, b in cuts]
             for f in futs:
                 yield f.result()
         return
