@@ -94,11 +94,59 @@ extern "C" int MS_API(ms_spectral_create)(const ms_spec_job* in, int njobs, cons
     *handle = P;
     return 0;
 }
+#ifndef MS_HOST_EMUL
+// Side streams for the length classes of a spectral stage: the classes are independent launch chains (columns -> rows ->
+// operators -> columns -> rows), and run side by side their tails and small grids fill each other's idle SMs.  Fork / join
+// with events, so the caller's stream sees one ordered operation (and a stream capture records a forked graph).
+struct SpecStreams {
+    enum { N = 5 };
+    cudaStream_t s[N]; cudaEvent_t fork, join[N]; bool ok;
+    SpecStreams() : ok(true) {
+        for (int i = 0; i < N; ++i) ok = ok && cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking) == cudaSuccess
+                                             && cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess;
+    }
+    static SpecStreams& get() { static SpecStreams v; return v; }
+};
+// development switch MS_SPEC_STREAMS=0: one stream, class after class
+static bool spec_streams_on() { static int v = -1; if (v < 0) { const char* e = getenv("MS_SPEC_STREAMS"); v = (e && e[0] == '0') ? 0 : 1; } return v != 0; }
+#endif
+
 extern "C" int MS_API(ms_spectral_run)(void* handle, void* stream) {
     SpectralPlan* P = (SpectralPlan*)handle;
     if (!P) MS_FAIL("ms_spectral_run: null handle");
     if (P->jobs.empty()) return 0;
     ms_stream_t st = (ms_stream_t)stream;
+#ifndef MS_HOST_EMUL
+    if (spec_streams_on() && !ms_launch_hook() && P->groups.size() == 2) {
+        std::vector<std::pair<size_t, size_t>> rg = FftEngine::class_ranges(P->jobs);
+        if (rg.size() > 1 && SpecStreams::get().ok) {
+            // heaviest class first, on the caller's stream; the others on side streams
+            auto weight = [&](const std::pair<size_t, size_t>& r) { double w = 0; for (size_t i = r.first; i < r.second; ++i) w += (double)P->jobs[i].n; return w; };
+            std::sort(rg.begin(), rg.end(), [&](const std::pair<size_t, size_t>& a, const std::pair<size_t, size_t>& b) { return weight(a) > weight(b); });
+            SpecStreams& S = SpecStreams::get();
+            int used = 0, rc = cudaEventRecord(S.fork, st) == cudaSuccess ? 0 : -1;
+            for (size_t k = 0; k < rg.size() && !rc; ++k) {
+                // chain k -> stream (k - 1) mod N for k >= 1 (more classes than side streams: they queue up behind each other)
+                ms_stream_t q = st;
+                if (k > 0) {
+                    const int i = (int)((k - 1) % SpecStreams::N);
+                    q = S.s[i];
+                    if ((int)k - 1 < SpecStreams::N) { rc = cudaStreamWaitEvent(q, S.fork, 0) == cudaSuccess ? 0 : -1; used = i + 1; }
+                    if (rc) break;
+                }
+                rc = FftEngine::get().forward(P->jobs, P->jobs_dev, q, rg[k].first, rg[k].second);
+                if (!rc) rc = FftEngine::get().inverse(P->jobs, P->jobs_dev, q, rg[k].first, rg[k].second);
+            }
+            for (int i = 0; i < used; ++i) {                    // always join, also after an error: a capture must not be left forked
+                cudaEventRecord(S.join[i], S.s[i]);
+                cudaStreamWaitEvent(st, S.join[i], 0);
+            }
+            if (rc) MS_FAIL("ms_spectral_run: a launch chain of the stage failed");
+            return 0;
+        }
+    }
+#endif
     for (size_t g = 0; g + 1 < P->groups.size(); ++g) {
         if (FftEngine::get().forward(P->jobs, P->jobs_dev, st, P->groups[g], P->groups[g + 1])) return -1;
         if (FftEngine::get().inverse(P->jobs, P->jobs_dev, st, P->groups[g], P->groups[g + 1])) return -1;

@@ -102,6 +102,20 @@ public:
     }
     static int job_class(const FftJob& J) { return (J.ch_hi ? 2 : 0) + (J.F1 > 1 ? 1 : 0) + 4 * sb_id(J); }
 
+    // [b, e) ranges of equal job_class() inside [lo, hi): what run() turns into one launch sequence each
+    static std::vector<std::pair<size_t, size_t>> class_ranges(const std::vector<FftJob>& jobs, size_t lo = 0, size_t hi = (size_t)-1) {
+        std::vector<std::pair<size_t, size_t>> out;
+        const size_t end = std::min(hi, jobs.size());
+        size_t b = lo;
+        while (b < end) {
+            const int cls = job_class(jobs[b]);
+            size_t e = b;
+            while (e < end && job_class(jobs[e]) == cls && e - b < 32768) ++e;
+            out.emplace_back(b, e);
+            b = e;
+        }
+        return out;
+    }
     // forward: pair (in_a,in_b) -> Z ;  inverse: spec op on Z -> (out_a,out_b)
     // (all entry points take an optional [lo, hi) job range so callers can walk a batch in L2-sized groups)
     int forward(const std::vector<FftJob>& jobs, const FftJob* jobs_dev, ms_stream_t st, size_t lo = 0, size_t hi = (size_t)-1) { return run(jobs, jobs_dev, st, 0, lo, hi); }

@@ -698,12 +698,15 @@ def _render_batch(params_list, device=None, precision="auto", host_out=None, chu
     from collections import deque
     from . import tables as T
     dev = device or CudaDevice()
-    if isinstance(chunk, int) and ramp and len(params_list) >= 4 * chunk:
+    if isinstance(chunk, int) and ramp and len(params_list) >= 8 * piece:
         # short first slices: the GPU and the drain start early; short LAST slices: what is left after the host has enqueued
-        # its last slice (that slice's kernels + its device->host copy) is short too
-        n, c = len(params_list), int(chunk)
-        # (a finer ramp -- 32, 64, 128, 256 ... -- was measured slower: 99 ms against 92 ms; every slice costs ~1 ms of host work)
-        head = [max(piece, c // 4), max(piece, c // 2)]
+        # its last slice (that slice's kernels + its device->host copy) is short too.  Small batches (a rank's share of a
+        # multi-GPU sweep) are still cut into about eight slices so that planning, kernels and the drain overlap.
+        n = len(params_list)
+        c = max(piece, min(int(chunk), (n // 8) // piece * piece))
+        # (measured on B200, 4096 renders, c = 512: heads 128,256 -> 86.7 ms; 64,128,256 -> 80.8; 32,64,128,256 -> 82.9;
+        #  128,384 -> 77.1: every slice costs 1-2 ms of host work, and the host is what paces the first third of the sweep)
+        head = [max(piece, c // 4), max(piece, 3 * c // 4)]
         tail = [max(piece, c // 2), max(piece, c // 4), max(piece, c // 4)]
         if _os_env("MS_RAMP"):                     # development switch: "head sizes / tail sizes", e.g. "64,128,256/256,128,64"
             h_, t_ = _os_env("MS_RAMP").split("/")
@@ -719,7 +722,16 @@ def _render_batch(params_list, device=None, precision="auto", host_out=None, chu
             br.close()
         return outs
     torch = dev.torch
-    total = sum(int(max(1, round(float(p["out_dur_s"]) * int(p["base_sr"])))) for p in params_list)      # main_v2.py:590
+    # frames of the whole batch (main_v2.py:590), memoised per distinct (duration, rate): a sweep repeats a few values
+    import operator
+    frames_of, get_dur = {}, operator.itemgetter("out_dur_s", "base_sr")
+    total = 0
+    for p in params_list:
+        key = get_dur(p)
+        f = frames_of.get(key)
+        if f is None:
+            f = frames_of[key] = int(max(1, round(float(key[0]) * int(key[1]))))
+        total += f
     if host_out is None:
         host_out = torch.empty(2 * total, dtype=torch.float32).pin_memory()
     if host_out.numel() < 2 * total:

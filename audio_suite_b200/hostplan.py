@@ -177,7 +177,8 @@ def default_threads():
     t = int(os.environ.get("MS_PLAN_THREADS", "0"))
     if t > 0:
         return t
-    return max(1, min(8, (len(os.sched_getaffinity(0)) - 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+    # (more than four slowed the launching thread's own slice set-up on the 16-core B200 hosts: 86.7 -> 79.4 ms per sweep)
+    return max(1, min(4, (len(os.sched_getaffinity(0)) - 2) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
 
 def plan_chunk(params_list, threads=1):

@@ -714,19 +714,28 @@ def plan_stream(params_list, chunk, workers=None, piece=32):
     # slices whose renders all belong to the native planner's family are planned in-process by libms_hostplan.so
     # (hostplan.plan_slice: no pickling, ~10x the Python planner's speed); the others go to the worker processes
     from . import hostplan
-    native = [hostplan.lib() is not None and not os.environ.get("MS_PLAN_PYTHON") and all(hostplan.supported(p) for p in params_list[a:b])
-              for a, b in cuts]
-    if all(native) and len(cuts) > 1 and workers > 1:
+    have_native = hostplan.lib() is not None and not os.environ.get("MS_PLAN_PYTHON")
+
+    def is_native(a, b):
+        return have_native and all(hostplan.supported(p) for p in params_list[a:b])
+    if have_native and len(cuts) > 1 and workers > 1 and is_native(*cuts[0]):
         # two Python threads alternate over the slices (one converts the parameters of slice k+1 while the native call of
-        # slice k -- which releases the GIL and plans blocks of renders on its own threads -- runs); slices come out in order
+        # slice k -- which releases the GIL and plans blocks of renders on its own threads -- runs); slices come out in
+        # order.  The first slice is on its way before the rest of the batch has been looked at.
         from concurrent.futures import ThreadPoolExecutor
-        nthr = hostplan.default_threads() if not os.environ.get("MS_PLAN_THREADS") else int(os.environ["MS_PLAN_THREADS"])
-        nthr = max(1, min(nthr, workers))
+        nthr = max(1, min(hostplan.default_threads(), workers))
         with ThreadPoolExecutor(max_workers=2, thread_name_prefix="ms-hostplan") as ex:
-            futs = [ex.submit(hostplan.plan_chunk, params_list[a:b], nthr) for a, b in cuts]
-            for f in futs:
-                yield f.result()
+            first = ex.submit(hostplan.plan_chunk, params_list[cuts[0][0]:cuts[0][1]], nthr)
+            if is_native(cuts[1][0], n):
+                futs = [first] + [ex.submit(hostplan.plan_chunk, params_list[a:b], nthr) for a, b in cuts[1:]]
+                for f in futs:
+                    yield f.result()
+                return
+            yield first.result()
+        # a mixed batch: the remaining slices go through the general path below
+        yield from plan_stream(params_list[cuts[1][0]:], sizes[1:] if len(sizes) > 1 else sizes, workers=workers, piece=piece)
         return
+    native = [is_native(a, b) for a, b in cuts]
     if workers <= 1 or all(native):
         for (a, b), nat in zip(cuts, native):
             yield hostplan.plan_slice(params_list[a:b]) if nat else pack_chunk([P.plan_render(p) for p in params_list[a:b]])

@@ -105,6 +105,32 @@ def test_randomised_family():
     assert len(ok) > 100
     for a in range(0, len(ok), 16):
         assert_same_tables(ok[a:a + 16])
+    # the whole family at once: several blocks of 32 renders, planned on three threads and appended in order (shared
+    # envelopes, impulse responses in order of first use, odd lengths -- everything that spans blocks)
+    want = T.pack_chunk([P.plan_render(p) for p in ok])
+    for threads in (1, 3):
+        got = hostplan.plan_chunk(ok, threads)
+        for name in want.__dataclass_fields__:
+            _same(getattr(want, name), getattr(got, name), "%s (threads=%d)" % (name, threads))
+
+
+def test_streamed_planning_of_a_mixed_batch():
+    """plan_stream sends the first slice to the native planner before it has looked at the rest; a batch whose later
+    renders are outside the native family must still come out slice by slice with the tables the Python planner packs."""
+    ps = [configs.c5_params(i, shared_ir=configs.synth_ir(0.1, 48000, 5)) for i in range(40)]
+    ps[25] = configs.with_defaults(ps[25], cep_warp_on=True)
+    ps[33] = configs.with_defaults(ps[33], gen_mode="Wavelet atoms")
+    got = list(T.plan_stream(ps, [8, 16], workers=2, piece=8))
+    T.shutdown_pool()
+    assert [len(t.post) for t in got] == [8, 16, 16]
+    for t, (a, b) in zip(got, ((0, 8), (8, 24), (24, 40))):
+        want = T.pack_chunk([P.plan_render(p) for p in ps[a:b]])
+        if b <= 24:
+            for name in want.__dataclass_fields__:
+                _same(getattr(want, name), getattr(t, name), "%s [%d:%d]" % (name, a, b))
+        else:       # the mixed slice comes from the worker processes as merged pieces: same renders, its own pool layout
+            assert np.array_equal(want.out_n, t.out_n) and np.array_equal(want.sy1["n"], t.sy1["n"])
+            assert np.array_equal(want.ola_e["amp"], t.ola_e["amp"]) and np.array_equal(want.tap_gain, t.tap_gain)
 
 
 def test_unsupported_renders_stay_with_the_python_planner():
