@@ -696,7 +696,9 @@ def _render_batch(params_list, device=None, precision="auto", host_out=None, chu
     [out_n, 2] arrays, one per render, in order -- views into `host_out` (a pinned 1-D float32 torch tensor
     of at least 2 * total frames) when it is given, else into a pinned buffer allocated here."""
     from collections import deque
+    import os as _os, time as _time
     from . import tables as T
+    t_start = t_prev = _time.perf_counter()
     dev = device or CudaDevice()
     if isinstance(chunk, int) and ramp and len(params_list) >= 8 * piece:
         # short first slices: the GPU and the drain start early; short LAST slices: what is left after the host has enqueued
@@ -740,9 +742,9 @@ def _render_batch(params_list, device=None, precision="auto", host_out=None, chu
     copy = torch.cuda.Stream(dev.dev)
     live, views, at = deque(), [], 0
     h2d = 0
-    import os as _os, time as _time
     trace = [] if _os.environ.get("MS_TRACE") else None
-    t_start = t_prev = _time.perf_counter()
+    if trace is not None:
+        trace.append("  set-up before the first slice is asked for: %.1f ms" % (1e3 * (_time.perf_counter() - t_start)))
     k = 0
     for tb in _prefetch(T.plan_stream(params_list, chunk, workers=workers, piece=piece)):
         t_got = _time.perf_counter()

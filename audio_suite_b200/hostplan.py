@@ -84,6 +84,10 @@ _NUM_COL = [FIELDS.index(k) for k in _NUM]
 _INT_COL = [FIELDS.index(k) for k in ("base_sr", "seed", "max_grains", "er_taps")]           # int(params[k]) in the reference
 _BOOL_COL = [FIELDS.index(k) for k in ("stereo_on", "nl_warp_on", "bandlimit_on", "grain_offset_on", "er_cloud_on", "space_ir_on")]
 _get_num = _get_side = None
+
+
+class Unsupported(Exception):
+    """A render of the list is outside the native planner's family (`supported()` is False for it); args[0] = its index."""
 _CLASSIC = "Classic reinterpret"
 
 
@@ -93,7 +97,7 @@ def _marshal(params_list):
     from . import tables as T
     global _get_num, _get_side
     if _get_num is None:
-        _get_num = operator.itemgetter(*_NUM)
+        _get_num = operator.itemgetter(*(_NUM + _OFF_FLAGS))     # the flags ride along: the support check costs no second pass
 
         _get_side = operator.itemgetter("gen_mode", "unfold_mode", "event_process", "bp_density", "bp_unfold", "bp_cutoff",
                                         "bp_stretch", "space_ir_on", "space_ir_max_samps")
@@ -108,8 +112,15 @@ def _marshal(params_list):
             num += [_get_num(p) for p in params_list[b:b + 64]]
             if b + 64 < R:
                 _time.sleep(0)
-        rows[:, _NUM_COL] = np.array(num, dtype=np.float64)
+        num = np.array(num, dtype=np.float64).reshape(R, len(_NUM) + len(_OFF_FLAGS))
+        rows[:, _NUM_COL] = num[:, :len(_NUM)]
+        bad = np.flatnonzero((num[:, len(_NUM):] != 0.0).any(axis=1) | (num[:, _NUM.index("seed")] < 0))
+        if bad.size:
+            raise Unsupported(int(bad[0]))
     except (TypeError, ValueError):          # numbers given as strings and the like: the reference's float() / int() accept them
+        for r, p in enumerate(params_list):
+            if not supported(p):
+                raise Unsupported(r)
         rows[:, _NUM_COL] = np.array([[float(p[k]) for k in _NUM] for p in params_list], dtype=np.float64)
     rows[:, _INT_COL] = np.trunc(rows[:, _INT_COL])
     rows[:, _BOOL_COL] = rows[:, _BOOL_COL] != 0.0
@@ -153,6 +164,8 @@ def _marshal(params_list):
                 b = bess_of[theta] = float(len(bess))
                 bess.append(T.bessel_coeffs(theta))
             k = uniq_of[key] = len(uniq)
+            if gen_mode not in _MODE or process not in _PROCESS:
+                raise Unsupported(r)
             uniq.append((_MODE[gen_mode], 0.0 if unfold_mode == _CLASSIC else 1.0, _PROCESS[process],
                          lane_id(l0), lane_id(l1), lane_id(l2), lane_id(l3), ir_id, b))
         idx.append(k)

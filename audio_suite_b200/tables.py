@@ -719,21 +719,28 @@ def plan_stream(params_list, chunk, workers=None, piece=32):
     def is_native(a, b):
         return have_native and all(hostplan.supported(p) for p in params_list[a:b])
     if have_native and len(cuts) > 1 and workers > 1 and is_native(*cuts[0]):
-        # two Python threads alternate over the slices (one converts the parameters of slice k+1 while the native call of
-        # slice k -- which releases the GIL and plans blocks of renders on its own threads -- runs); slices come out in
-        # order.  The first slice is on its way before the rest of the batch has been looked at.
+        # Optimistic native path: the first slice is planned before anything else is looked at; then two Python threads
+        # alternate over the remaining slices (one converts the parameters of slice k+1 while the native call of slice k --
+        # which releases the GIL and plans blocks of renders on its own threads -- runs).  Slices come out in order.  The
+        # conversion itself notices a render outside the native family (hostplan.Unsupported): from that slice on the
+        # batch goes through the general path below.
         from concurrent.futures import ThreadPoolExecutor
         nthr = max(1, min(hostplan.default_threads(), workers))
+        yield hostplan.plan_chunk(params_list[cuts[0][0]:cuts[0][1]], nthr)
+        rest = None
         with ThreadPoolExecutor(max_workers=2, thread_name_prefix="ms-hostplan") as ex:
-            first = ex.submit(hostplan.plan_chunk, params_list[cuts[0][0]:cuts[0][1]], nthr)
-            if is_native(cuts[1][0], n):
-                futs = [first] + [ex.submit(hostplan.plan_chunk, params_list[a:b], nthr) for a, b in cuts[1:]]
-                for f in futs:
-                    yield f.result()
-                return
-            yield first.result()
-        # a mixed batch: the remaining slices go through the general path below
-        yield from plan_stream(params_list[cuts[1][0]:], sizes[1:] if len(sizes) > 1 else sizes, workers=workers, piece=piece)
+            futs = [ex.submit(hostplan.plan_chunk, params_list[a:b], nthr) for a, b in cuts[1:]]
+            for k, f in enumerate(futs):
+                try:
+                    tb = f.result()
+                except hostplan.Unsupported:
+                    for g in futs[k + 1:]:
+                        g.cancel()
+                    rest = k + 1
+                    break
+                yield tb
+        if rest is not None:
+            yield from plan_stream(params_list[cuts[rest][0]:], sizes[rest:] if len(sizes) > rest else sizes[-1:], workers=workers, piece=piece)
         return
     native = [is_native(a, b) for a, b in cuts]
     if workers <= 1 or all(native):

@@ -137,4 +137,9 @@ def test_unsupported_renders_stay_with_the_python_planner():
     for kw in (dict(gen_mode="Wavelet atoms"), dict(event_process="Hawkes"), dict(cep_warp_on=True), dict(spectral_imprint_on=True),
                dict(res_bank_on=True), dict(gen_mode="no such generator")):
         assert not hostplan.supported(configs.with_defaults(kw))
+        with pytest.raises(hostplan.Unsupported) as e:            # the conversion notices it too (no second pass over the batch)
+            hostplan.plan_chunk([configs.with_defaults(), configs.with_defaults(kw)])
+        assert e.value.args[0] == 1
+    with pytest.raises(hostplan.Unsupported):
+        hostplan.plan_chunk([configs.with_defaults(seed=-5)])
     assert hostplan.supported(configs.with_defaults())
