@@ -67,7 +67,47 @@ struct RollK { static constexpr int MAXT = 256;
 static inline MsDim mk_dim(unsigned x, unsigned y) { MsDim d; d.x = x; d.y = y; return d; }
 #define MS_FOR_Y_CHUNKS(total, body) for (int _y0 = 0; _y0 < (total); _y0 += 32768) { const int _yc = std::min(32768, (total) - _y0); body }
 
+#ifndef MS_HOST_EMUL
+template <int CL>
+static int synth_launch_cluster(const ms_synth_evt* evts, int n, real* pool, ms_stream_t st) {
+    auto kern = synth_normal_cluster_kernel<CL>;
+    static bool configured = false;
+    if (!configured) {
+        MS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SynthSmem)));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(CL * n), 1, 1); cfg.blockDim = dim3(SY_NTHR, 1, 1); cfg.dynamicSmemBytes = sizeof(SynthSmem); cfg.stream = st;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    MS_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, (const SynthEvt*)evts, pool));
+    ++ms_launch_counter();
+    if (ms_launch_hook()) ms_launch_hook()(CL == 2 ? "K = synth_normal_cluster_kernel<2>;" : CL == 4 ? "K = synth_normal_cluster_kernel<4>;" : "K = synth_normal_cluster_kernel<8>;", (void*)st);
+    return 0;
+}
+// CTAs per event: small batches spread every event over a thread-block cluster (development switch MS_SYNTH_CLUSTER=1|2|4|8
+// forces a size; 1 = always one CTA per event)
+static int synth_cluster_size(int n_events) {
+    const char* e = getenv("MS_SYNTH_CLUSTER");            // (read per call: the tests switch it between launches)
+    const int forced = e ? atoi(e) : 0;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+    static int slots = 0;                                   // CTAs of this kernel the device holds at once
+    if (!slots) { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); slots = 4 * sms; }
+    if (n_events * 8 <= slots) return 8;
+    if (n_events * 4 <= 3 * slots) return 4;
+    if (n_events * 2 <= 3 * slots) return 2;
+    return 1;
+}
+#endif
 extern "C" int MS_API(ms_synth_normal)(const ms_synth_evt* evts, int n, real* pool, void* stream) {
+#ifndef MS_HOST_EMUL
+    if (n > 0 && n < (1 << 20)) {
+        const int cl = synth_cluster_size(n);
+        if (cl == 8) return synth_launch_cluster<8>(evts, n, pool, (ms_stream_t)stream);
+        if (cl == 4) return synth_launch_cluster<4>(evts, n, pool, (ms_stream_t)stream);
+        if (cl == 2) return synth_launch_cluster<2>(evts, n, pool, (ms_stream_t)stream);
+    }
+#endif
     for (int x0 = 0; x0 < n; x0 += 1 << 20) {
         const int cnt = std::min(1 << 20, n - x0);
         if (ms_launch<SynthNormalK>(mk_dim((unsigned)cnt, 1), SY_NTHR, sizeof(SynthSmem), (ms_stream_t)stream, evts + x0, pool)) return -1;

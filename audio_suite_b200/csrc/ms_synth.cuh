@@ -136,6 +136,7 @@ struct SynthSmem {
     int scan[2][SY_NTHR];                   // prefix sums of the per-thread output counts
     int flag[3];                            // "some thread changed its start state" (rotating, see below)
     int carry_state, _pad;
+    int xend, xtotal;                       // cluster form: end state of this CTA's last run / its count of normals, read by the peers
 };
 MS_DEV unsigned long long sy_word(const SynthSmem* S, int p) {   // p in [-1, SY_W)
     if (p < 0) return S->words[0];
@@ -267,6 +268,109 @@ MS_DEV void synth_normal_body(const SynthEvt* MS_RESTRICT evts, real* MS_RESTRIC
         c.sync();
     }
 }
+
+#ifndef MS_HOST_EMUL
+// ---- cluster form: CL CTAs share one event ---------------------------------------------------------------------------
+// For small batches (a rank's share of a multi-GPU sweep, a single render) one CTA per event leaves most SMs idle and
+// the longest event sets the kernel's duration.  Here a thread-block cluster walks an event together: in every round CTA
+// `rank` takes the words [rank * SY_W, (rank + 1) * SY_W) of the cluster's CL * SY_W, and the two things a CTA needs from
+// its left neighbour -- the ziggurat state its first run starts in, and how many normals the CTAs before it produced --
+// are read from the neighbour's shared memory (DSMEM: mapa + ld.shared::cluster) between hardware cluster barriers.
+// Same words, same state machine, same output order as synth_normal_body: bit-identical output.
+MS_DEV void sy_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+MS_DEV unsigned sy_cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+MS_DEV int sy_ld_peer(const int* p, unsigned rank) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    unsigned ra; int v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(ra) : "memory");
+    return v;
+}
+template <int CL>
+__global__ void __launch_bounds__(SY_NTHR, 4) synth_normal_cluster_kernel(const SynthEvt* __restrict__ evts, real* __restrict__ pool) {
+    extern __shared__ float4 ms_dyn_smem[];
+    const int tid = threadIdx.x;
+    const unsigned rank = sy_cluster_rank();
+    const SynthEvt E = evts[blockIdx.x / CL];
+    if (E.mode == SY_DUST) return;                          // (the whole cluster leaves)
+    SynthSmem* S = (SynthSmem*)ms_dyn_smem;
+    for (int i = tid; i < 256; i += SY_NTHR) {
+        S->ki[i] = MS_ZIG_KI[i];
+        union { unsigned long long u; double d; } cv;
+        cv.u = MS_ZIG_WI_BITS[i]; S->wi[i] = cv.d;
+        cv.u = MS_ZIG_FI_BITS[i]; S->fi[i] = cv.d;
+    }
+    ZigTables T; T.ki = S->ki; T.wi = S->wi; T.fi = S->fi;
+    u128 inc; inc.hi = E.i_hi; inc.lo = E.i_lo;
+    u128 st; st.hi = E.s_hi; st.lo = E.s_lo;
+    u128 jm, jp;
+    pcg_jump_consts(inc, (unsigned long long)(rank * SY_W + tid * SY_C), &jm, &jp);
+    st = u128_add(u128_mul(st, jm), jp);
+    pcg_jump_consts(inc, (unsigned long long)(CL * SY_W - SY_C), &jm, &jp);
+    real* out = pool + E.out;
+    int out_base = 0;
+    int carry = ZS_S0;                                      // state the cluster's round starts in (used by rank 0, thread 0)
+    __syncthreads();
+    const int max_rounds = (int)((2ll * E.n) / (CL * SY_W)) + 64;
+    for (int round = 0; round < max_rounds && out_base < E.n; ++round) {
+        if (tid == 0) { S->words[0] = pcg_output(st); S->flag[0] = 0; }
+        for (int i = 0; i < SY_C; ++i) { st = pcg_step(st, inc); S->words[1 + i * SY_NTHR + tid] = pcg_output(st); }
+        st = u128_add(u128_mul(st, jm), jp);
+        __syncthreads();
+        const int p0 = tid * SY_C;
+        const int first = (tid == 0 && rank == 0) ? carry : ZS_S0;
+        int start = first;
+        unsigned mask;
+        double vals[SY_C];
+        int end = zig_run(start, S, p0, T, vals, &mask);
+        for (int it = 0;; ++it) {
+            S->endst[tid] = end;
+            if (tid == SY_NTHR - 1) S->xend = end;
+            if (tid == 0) S->flag[(it + 1) % 3] = 0;
+            sy_cluster_sync();
+            int want;
+            if (tid == 0) want = rank == 0 ? first : sy_ld_peer(&S->xend, rank - 1);
+            else want = S->endst[tid - 1];
+            if (want != start) {
+                start = want;
+                end = zig_run(start, S, p0, T, vals, &mask);
+                S->flag[it % 3] = 1;
+            }
+            sy_cluster_sync();
+            int any = 0;
+#pragma unroll
+            for (int r = 0; r < CL; ++r) any |= sy_ld_peer(&S->flag[it % 3], (unsigned)r);
+            if (!any) break;
+        }
+        const int cnt = MS_POPC(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += o; }
+        if ((tid & 31) == 31) S->scan[0][tid >> 5] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SY_NTHR / 32; ++w) { const int t = S->scan[0][w]; if (w < (tid >> 5)) wbase += t; total += t; }
+        int my_off = wbase + incl - cnt;
+#pragma unroll
+        for (int i = 0; i < SY_C; ++i) if ((mask >> i) & 1u) S->stage[my_off++] = (real)vals[i];
+        if (tid == 0) S->xtotal = total;
+        sy_cluster_sync();                                  // (xend holds the final end state of the last run since the last iteration)
+        int before = 0, all = 0;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) { const int t = sy_ld_peer(&S->xtotal, (unsigned)r); if ((unsigned)r < rank) before += t; all += t; }
+        if (tid == 0 && rank == 0) carry = sy_ld_peer(&S->xend, CL - 1);
+        const int at = out_base + before;
+        int take = E.n - at;
+        take = take < 0 ? 0 : (take < total ? take : total);
+        for (int i = tid; i < take; i += SY_NTHR) out[at + i] = synth_sample(E, at + i, S->stage[i]);
+        out_base += all;
+        sy_cluster_sync();                                  // peers have read xend / xtotal; stage and words may be rewritten
+    }
+}
+#endif
 
 // Finalize for the tilted-noise modes (main_v2.py:246-255): one thread per sample.
 MS_DEV void synth_tilt_finish_body(const SynthEvt* MS_RESTRICT evts, real* MS_RESTRICT pool, const Ctx& c) {

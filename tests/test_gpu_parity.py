@@ -37,6 +37,32 @@ def test_normals_bit_exact(cuda_dev, precision):
                                                     (5, 2400000)])
 
 
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_cluster_synthesis_is_bit_identical(cuda_dev, precision, monkeypatch):
+    """Small batches spread every event over a thread-block cluster (2 / 4 / 8 CTAs exchanging the ziggurat state and their
+    counts through distributed shared memory): every size must write exactly what one CTA per event writes, and the
+    stream must still be numpy's."""
+    ps = [configs.c5_params(i) for i in (0, 2, 3, 5, 7, 11, 13, 100, 1000, 4095)]
+    ps = [dict(p, gen_mode=m) for p, m in zip(ps, ["Noise burst", "Gaussian click", "Resonant strike", "Skewed transient", "Noise burst"] * 2)]
+    pools = {}
+    for cl in (1, 2, 4, 8):
+        monkeypatch.setenv("MS_SYNTH_CLUSTER", str(cl))
+        br = engine.BatchRenderer(ps, device=cuda_dev, precision=precision)
+        br.pool.zero_()
+        import ctypes as C
+        lib, dev = br.api, br.dev
+        assert lib.ms_synth_normal(dev.ptr(br.d_sy1), br.n_normal_evt, dev.ptr(br.pool), dev.stream_ptr()) == 0
+        cuda_dev.synchronize()
+        pools[cl] = br.pool.cpu().numpy().copy()
+        br.close()
+    for cl in (2, 4, 8):
+        assert np.array_equal(pools[1], pools[cl]), cl
+    assert np.abs(pools[1]).max() > 0
+    for cl in (2, 8):
+        monkeypatch.setenv("MS_SYNTH_CLUSTER", str(cl))
+        K.check_normals_bit_exact(cuda_dev, precision, [(12345, 16), (7, 2049), (2026, 40000), (404, 300000)])
+
+
 @pytest.mark.parametrize("name", ["C1", "C1b", "C2"])
 @pytest.mark.parametrize("precision", ["f32", "f64"])
 def test_render_c1_c2(cuda_dev, name, precision):
