@@ -25,7 +25,7 @@ def stage_of(launches):
     fft_before_tilt = seen_tilt_finish
     for l in launches:
         n = l["name"]
-        if "SynthNormalK" in n or "SynthDustK" in n:
+        if "SynthNormalK" in n or "SynthDustK" in n or "synth_normal_cluster_kernel" in n:
             stage = "synth"
         elif "SynthTiltK" in n:
             out.append("tilt_spectral")
@@ -37,7 +37,7 @@ def stage_of(launches):
             stage = "fir_overlap_save"
         elif "PostMaxK" in n or "PostWriteK" in n or "RollK" in n:
             stage = "post"
-        elif "ColsK" in n or "RowsK" in n or "ColsWarpK" in n:
+        elif "ColsK" in n or "RowsK" in n or "ColsWarpK" in n or "SpecOpK" in n:
             if stage == "synth":
                 stage = "tilt_spectral" if fft_before_tilt else "grain_spectral"
             elif stage == "tilt_spectral" and not fft_before_tilt:
@@ -58,6 +58,8 @@ def main():
         t = l["gpu__time_duration.sum"]
         rd, wr = l.get("dram__bytes_read.sum", 0.0), l.get("dram__bytes_write.sum", 0.0)
         name = l["name"].replace("void ms_kernel<", "").split(", const")[0].replace("msd::", "").replace("msf::", "")
+        if name.startswith("void "):                         # kernels launched outside ms_launch (cluster kernels)
+            name = name[5:].split("(")[0]
         print("| %d | %s | %s | %s | %.3f | %.1f%% | %.1f | %.1f | %.0f |" % (i, name, s, l["grid"], t, 100 * t / tot, rd / 1e6, wr / 1e6,
                                                                        (rd + wr) / 1e9 / (t * 1e-3) if t else 0))
         d = per_stage.setdefault(s, {"ms": 0.0, "dram_bytes": 0.0, "launches": 0})
