@@ -152,17 +152,18 @@ MS_DEV void stockham_pass(const cpx* MS_RESTRICT src, cpx* MS_RESTRICT dst, cons
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = src[tile_addr(g, vec, j + q * per_vec)];
         if (k != 0) {
-            // powers of w = w_F^(k*tws): load w, w^2, w^4 (each rounded once), multiply the rest
+            // powers of w = w_F^(k*tws): column-major tiles load w, w^2, w^4 (broadcast loads, each rounded once); row tiles
+            // (a table address per lane) load w and square (see stockham_pass_ip)
             const cpx w1 = __ldg(&tw[k * tws]);
             if (R == 2) { v[1] = c_mul(v[1], w1); }
             else {
-                const cpx w2 = __ldg(&tw[2 * k * tws]);
+                const cpx w2 = CM ? __ldg(&tw[2 * k * tws]) : c_mul(w1, w1);
                 if (R == 3) { v[1] = c_mul(v[1], w1); v[2] = c_mul(v[2], w2); }
                 else {
                     const cpx w3 = c_mul(w1, w2);
                     if (R == 4) { v[1] = c_mul(v[1], w1); v[2] = c_mul(v[2], w2); v[3] = c_mul(v[3], w3); }
                     else {
-                        const cpx w4 = __ldg(&tw[4 * k * tws]);
+                        const cpx w4 = CM ? __ldg(&tw[4 * k * tws]) : c_mul(w2, w2);
                         v[1] = c_mul(v[1], w1); v[2] = c_mul(v[2], w2); v[3] = c_mul(v[3], w3); v[4] = c_mul(v[4], w4);
                         if (R == 8) {
                             v[5] = c_mul(v[5], c_mul(w4, w1)); v[6] = c_mul(v[6], c_mul(w4, w2)); v[7] = c_mul(v[7], c_mul(w4, w3));
@@ -231,17 +232,19 @@ MS_DEV void stockham_pass_ip(cpx* MS_RESTRICT buf, const TileGeom& g, int per_ve
 #pragma unroll
             for (int q = 0; q < R; ++q) v[u][q] = buf[tile_addr(g, vec, j + q * per_vec)];
             if (k != 0) {
-                // powers of w = w_F^(k*tws): load w, w^2, w^4 (each rounded once), multiply the rest
+                // powers of w = w_F^(k*tws).  Column-major tiles: the threads of a warp share a few k, the loads are
+                // broadcasts -- w, w^2, w^4 come from the table (each rounded once).  Row tiles: every lane has its own k,
+                // a lookup costs the L1 data pipe up to 32 sectors -- only w is loaded, the powers are squared.
                 const cpx w1 = __ldg(&tw[k * tws]);
                 if (R == 2) { v[u][1] = c_mul(v[u][1], w1); }
                 else {
-                    const cpx w2 = __ldg(&tw[2 * k * tws]);
+                    const cpx w2 = CM ? __ldg(&tw[2 * k * tws]) : c_mul(w1, w1);
                     if (R == 3) { v[u][1] = c_mul(v[u][1], w1); v[u][2] = c_mul(v[u][2], w2); }
                     else {
                         const cpx w3 = c_mul(w1, w2);
                         v[u][1] = c_mul(v[u][1], w1); v[u][2] = c_mul(v[u][2], w2); v[u][3] = c_mul(v[u][3], w3);
                         if (R > 4) {
-                            const cpx w4 = __ldg(&tw[4 * k * tws]);
+                            const cpx w4 = CM ? __ldg(&tw[4 * k * tws]) : c_mul(w2, w2);
                             v[u][4 % R] = c_mul(v[u][4 % R], w4);
                             if (R == 8) {
                                 v[u][5 % R] = c_mul(v[u][5 % R], c_mul(w4, w1)); v[u][6 % R] = c_mul(v[u][6 % R], c_mul(w4, w2));
@@ -315,7 +318,9 @@ MS_DEV void warp_fft256(cpx* v, cpx* sw, const cpx* MS_RESTRICT tw, int lane, co
     c.syncwarp();
     {                                                       // pass 2: Ns = 8, twiddle w_64^(q k) = w_256^(4 q k)
         const int k = lane & 7;
-        const cpx w1 = __ldg(&tw[4 * k]), w2 = __ldg(&tw[8 * k]), w4 = __ldg(&tw[16 * k]);
+        // (one table load; the other powers by squaring: ncu has these kernels at ~90 % of the L1 data pipe, and the seven
+        //  twiddle loads of a transform cost as many wavefronts as the transform's own data)
+        const cpx w1 = __ldg(&tw[4 * k]), w2 = c_mul(w1, w1), w4 = c_mul(w2, w2);
         const cpx w3 = c_mul(w1, w2);
         v[1] = c_mul(v[1], w1); v[2] = c_mul(v[2], w2); v[3] = c_mul(v[3], w3); v[4] = c_mul(v[4], w4);
         v[5] = c_mul(v[5], c_mul(w4, w1)); v[6] = c_mul(v[6], c_mul(w4, w2)); v[7] = c_mul(v[7], c_mul(w4, w3));
@@ -332,7 +337,7 @@ MS_DEV void warp_fft256(cpx* v, cpx* sw, const cpx* MS_RESTRICT tw, int lane, co
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int j = lane + 32 * h;
-            const cpx w1 = __ldg(&tw[j]), w2 = __ldg(&tw[2 * j]);
+            const cpx w1 = __ldg(&tw[j]), w2 = c_mul(w1, w1);
             const cpx w3 = c_mul(w1, w2);
             cpx a[4] = {v[h], c_mul(v[2 + h], w1), c_mul(v[4 + h], w2), c_mul(v[6 + h], w3)};
             Bfly<4>::run(a);

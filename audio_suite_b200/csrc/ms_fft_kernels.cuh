@@ -430,14 +430,24 @@ MS_DEV void fft_cols_bluestein_warp256(const FftJob& J, const Ctx& c) {
     warp_fft256(v, sw, J.twb, lane, c);
     c.syncwarp();
     const int col = col0 + warp;
+    // W_M^(k1 col), k1 = lane + 32 m:  W^(lane col) from sincospi (a table lookup at a per-lane address costs the L1 data pipe
+    // 32 sectors a request, and that pipe is what bounds this kernel), stepped by the warp-uniform W^(32 col)
+    cpx tb = mk((real)1., (real)0.), ts = tb;
+    if (TWID) {
+        real sn, cs;
+        r_sincospi((real)(2.0 * ((double)((unsigned)lane * (unsigned)col) / (double)J.M)), &sn, &cs);
+        tb = mk(cs, -sn);
+        ts = tw2level(J.twM_hi, J.twM_lo, (unsigned)(((long long)32 * col) % J.M));
+    }
 #pragma unroll
     for (int m = 0; m < 4; ++m) {                               // F1 <= 128: outputs k1 = lane + 32 m, m < 4
         const int k1 = lane + 32 * m;
         if (k1 < F1) {
             cpx val = c_mul(c_swap(v[m]), __ldg(&J.b1_chirp[k1]));
-            if (TWID) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)k1 * (unsigned)col));
+            if (TWID) val = c_mul(val, tb);
             sw[ms_pad(k1)] = val;
         }
+        if (TWID) tb = c_mul(tb, ts);
     }
     c.sync();
 #pragma unroll
