@@ -82,6 +82,13 @@ struct FftJob {
 MS_DEV cpx tw2level(const cpx* MS_RESTRICT hi, const cpx* MS_RESTRICT lo, unsigned e) {
     return c_mul(__ldg(&hi[e >> 10]), __ldg(&lo[e & 1023u]));
 }
+// W_M^e from sincospi (e < M): used where every lane needs its own exponent -- a table lookup at a per-lane address costs
+// the L1 data pipe up to 32 sectors a request, and that pipe (not DRAM, not FP64) is what bounds the FFT kernels.
+MS_DEV cpx tw_direct(unsigned e, int M) {
+    real sn, cs;
+    r_sincospi((real)(2.0 * ((double)e / (double)M)), &sn, &cs);
+    return mk(cs, -sn);
+}
 // chirp c[j] = exp(-i pi j^2 / n) = W_{2n}^(j^2 mod 2n)
 MS_DEV cpx chirp(const FftJob& J, int j) {
     const long long jj = (long long)j * (long long)j;
@@ -368,11 +375,19 @@ MS_DEV void fft_cols_bluestein_static(const FftJob& J, const Ctx& c) {
     c.sync();
     tile_fft_pow2<1, SB ? SB : 128, T>(s, g, J.twb, c);
     const int total = F1 * T;
+    // a thread keeps its column (256 threads, T | 256) and walks k1 in steps of 256 / T: W_M^(k1 col) starts from sincospi and
+    // is stepped by W_M^(col 256 / T) (T distinct values per warp: a cheap lookup)
+    cpx tw = mk((real)1., (real)0.), tstep = tw;
+    if (TWID) {
+        const unsigned col = (unsigned)(col0 + c.tid % T);
+        tw = tw_direct((unsigned)(c.tid / T) * col, J.M);
+        tstep = tw2level(J.twM_hi, J.twM_lo, (unsigned)(((long long)col * (c.nthr / T)) % J.M));
+    }
 #pragma unroll 2
     for (int e = c.tid; e < total; e += c.nthr) {
         const int k1 = e / T, v = e - k1 * T;
         cpx val = c_mul(c_swap(s[tile_addr(g, v, k1)]), __ldg(&J.b1_chirp[k1]));
-        if (TWID) val = c_mul(val, tw2level(J.twM_hi, J.twM_lo, (unsigned)k1 * (unsigned)(col0 + v)));
+        if (TWID) { val = c_mul(val, tw); tw = c_mul(tw, tstep); }
         job_store<ST>(J, k1 * F2 + col0 + v, val);
     }
 }
@@ -528,6 +543,20 @@ MS_DEV void fft_cols_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
     }
     c.sync();
     s = SQ ? tile_fft_256<1, SQ ? SQ : 1>(s, g, J.tw1, c) : tile_fft<1>(s, s2, g, J.p1, J.tw1, c);
+    if (TWID && c.nthr % cnt == 0) {
+        // the thread keeps its column: stepped twiddles as in the static Bluestein tiles
+        const int k10 = ms_fastdiv(c.tid, mgc);
+        const unsigned col = (unsigned)(col0 + c.tid - k10 * cnt);
+        cpx tw = tw_direct((unsigned)k10 * col, J.M);
+        const cpx tstep = tw2level(J.twM_hi, J.twM_lo, (unsigned)(((long long)col * (c.nthr / cnt)) % J.M));
+#pragma unroll 4
+        for (int e = c.tid; e < total; e += c.nthr) {
+            const int k1 = ms_fastdiv(e, mgc), v = e - k1 * cnt;
+            job_store<ST>(J, k1 * F2 + col0 + v, c_mul(s[tile_addr(g, v, k1)], tw));
+            tw = c_mul(tw, tstep);
+        }
+        return;
+    }
 #pragma unroll 4
     for (int e = c.tid; e < total; e += c.nthr) {
         const int k1 = ms_fastdiv(e, mgc), v = e - k1 * cnt;

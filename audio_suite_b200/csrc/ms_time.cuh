@@ -7,7 +7,7 @@
 #define POST_K MS_POST_K          // Bessel taps -K..K of the stereo rotation
 #define POST_NC (2 * POST_K + 1)
 #define POST_HALF (OLA_TILE / 2 + 2 * POST_K + 4)            // samples of one parity in a tile's window (+ quad slack)
-#define POST_PAR (POST_HALF + POST_HALF / 8 + 2)             // ... with the one-in-eight skew
+#define POST_PAR (POST_HALF + POST_HALF / 4 + 2)             // ... with the one-in-four skew
 
 // ---- overlap-add ("unfold" placement) + ADSR --------------------------------------------------------
 typedef ms_ola_render OlaRender;
@@ -130,40 +130,30 @@ MS_DEV void post_right_tile(const PostRender& R, const real* MS_RESTRICT y, int 
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             const int j = c.tid + OLA_NTHR * q, mm = j >> 1;
-            if (j < W) win[(j & 1) * POST_PAR + mm + (mm >> 3)] = tmp[q];
+            if (j < W) win[(j & 1) * POST_PAR + mm + (mm >> 2)] = tmp[q];
         }
     }
     for (int j = c.tid; j < POST_NC; j += c.nthr) coef[j] = (real)R.coef[j];
     c.sync();
-    // thread -> parity (warp-uniform) and EIGHT consecutive outputs of that parity: 32 window loads per 8 outputs, the
-    // coefficients two per (broadcast) load.  ncu had this kernel at 89 % of the L1 data pipe, two thirds of it these
-    // shared-memory loads; four outputs per thread took 28 + 25 loads per 4.  Slots: sample m of a parity at m + (m >> 3)
-    // (a thread's base 9 t: odd stride, conflict-free), output j at j + (j >> 4) (base 17 t).
-    for (int u = c.tid; u < OLA_TILE / 8; u += c.nthr) {
-        const int par = u / (OLA_TILE / 16), t = u - par * (OLA_TILE / 16);
-        if (16 * t + par >= len) continue;
-        const real* w = win + par * POST_PAR + 9 * t;
-        real a[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = (real)0.;
-        real x[8];
-#pragma unroll
-        for (int i = 0; i < 7; ++i) x[i] = w[i];                 // samples 8t .. 8t + 6 (no skew step inside the first eight)
+    // thread -> parity (warp-uniform) and a quad of consecutive outputs of that parity: 28 loads per 4 outputs
+    for (int u = c.tid; u < OLA_TILE / 4; u += c.nthr) {
+        const int par = u / (OLA_TILE / 8), t = u - par * (OLA_TILE / 8);
+        if (8 * t + par >= len) continue;
+        const real* w = win + par * POST_PAR + 5 * t;     // slot of sample m0 = 4t: 4t + t
+        real a0 = (real)0., a1 = (real)0., a2 = (real)0., a3 = (real)0.;
+        real x0 = w[0], x1 = w[1], x2 = w[2];
         struct alignas(2 * sizeof(real)) CoefPair { real a, b; };
-        const CoefPair* cp = (const CoefPair*)coef;              // (coef sits at an even offset and holds POST_NC + 1 entries)
+        const CoefPair* cp = (const CoefPair*)coef;          // two coefficients per (broadcast) load: coef sits at an even offset, POST_NC + 1 entries
 #pragma unroll
         for (int k = 0; k < POST_NC; ++k) {
-            x[7] = w[(k + 7) + ((k + 7) >> 3)];
+            const real x3 = w[(k + 3) + ((k + 3) >> 2)];
             const CoefPair pr = cp[k >> 1];
             const real ck = (k & 1) ? pr.b : pr.a;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] += ck * x[i];
-#pragma unroll
-            for (int i = 0; i < 7; ++i) x[i] = x[i + 1];
+            a0 += ck * x0; a1 += ck * x1; a2 += ck * x2; a3 += ck * x3;
+            x0 = x1; x1 = x2; x2 = x3;
         }
-        const int j0 = 17 * t + par;                 // output j = 16 t + par + 2 i at j + (j >> 4)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) res[j0 + 2 * i] = a[i];
+        const int j0 = 9 * t + par;                  // slot of output j = 8t + par + 2q is j + (j >> 3): stride 9, conflict-free
+        res[j0] = a0; res[j0 + 2] = a1; res[j0 + 4] = a2; res[j0 + 6] = a3;
     }
     c.sync();
 }
@@ -214,7 +204,7 @@ MS_DEV void post_max_body(const PostRender* MS_RESTRICT renders, real* mono, uns
         for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) {
             const int j = c.tid + OLA_NTHR * q;
             if (j < len) {
-                const real r = res[j + (j >> 4)];
+                const real r = res[j + (j >> 3)];
                 mono[R.rbuf + t0 + j] = r;
                 m = r_max(m, r_max(r_abs(r), r_abs(yv[q])));
             }
