@@ -345,3 +345,51 @@ MS_DEV void warp_fft256(cpx* v, cpx* sw, const cpx* MS_RESTRICT tw, int lane, co
         }
     }
 }
+
+// ---- warp-local 512-point forward FFT -----------------------------------------------------------------------
+// in: v[q] = x[lane + 32 q], q < 16;  out: v[m] = X[lane + 32 m].  Radix 8 . 8 . 8, two butterflies per lane and pass,
+// two exchanges through the warp's own shared-memory row (ms_pad(512) + 1 entries), __syncwarp only.
+MS_DEV void warp_fft512(cpx* v, cpx* sw, const cpx* MS_RESTRICT tw, int lane, const Ctx& c) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                           // pass 1: Ns = 1; butterfly j = lane + 32 h takes x[j + 64 q] = v[2 q + h]
+        cpx a[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) a[q] = v[2 * q + h];
+        Bfly<8>::run(a);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sw[ms_pad(8 * (lane + 32 * h) + q)] = a[q];
+    }
+    c.syncwarp();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
+    c.syncwarp();
+    {                                                       // pass 2: Ns = 8, twiddle w_64^(q k) = w_512^(8 q k), k = j mod 8 = lane mod 8
+        const int k = lane & 7;
+        const cpx w1 = __ldg(&tw[8 * k]), w2 = c_mul(w1, w1), w4 = c_mul(w2, w2);
+        const cpx w3 = c_mul(w1, w2), w5 = c_mul(w4, w1), w6 = c_mul(w4, w2), w7 = c_mul(w4, w3);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            cpx a[8] = {v[h], c_mul(v[2 + h], w1), c_mul(v[4 + h], w2), c_mul(v[6 + h], w3),
+                        c_mul(v[8 + h], w4), c_mul(v[10 + h], w5), c_mul(v[12 + h], w6), c_mul(v[14 + h], w7)};
+            Bfly<8>::run(a);
+            const int base = (lane + 32 * h - k) * 8 + k;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sw[ms_pad(base + 8 * q)] = a[q];
+        }
+    }
+    c.syncwarp();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
+    c.syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                           // pass 3: Ns = 64, k = j = lane + 32 h, twiddle w_512^(q j); X[j + 64 q] -> m = 2 q + h
+        const int j = lane + 32 * h;
+        const cpx w1 = __ldg(&tw[j]), w2 = c_mul(w1, w1), w4 = c_mul(w2, w2);
+        const cpx w3 = c_mul(w1, w2), w5 = c_mul(w4, w1), w6 = c_mul(w4, w2), w7 = c_mul(w4, w3);
+        cpx a[8] = {v[h], c_mul(v[2 + h], w1), c_mul(v[4 + h], w2), c_mul(v[6 + h], w3),
+                    c_mul(v[8 + h], w4), c_mul(v[10 + h], w5), c_mul(v[12 + h], w6), c_mul(v[14 + h], w7)};
+        Bfly<8>::run(a);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[2 * q + h] = a[q];
+    }
+}

@@ -29,6 +29,11 @@ template <int LD, int ST, int TWID> struct ColsWarpK {              // in-tile B
     static constexpr int MINB = MS_WB_MINB;
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_warp_body<LD, ST, TWID>(jobs, c); }
 };
+template <int LD, int ST, int TWID> struct ColsWarp512K {           // in-tile Bluestein, B1 = 512, warp-local transforms (16 values per lane)
+    static constexpr int MAXT = 256;
+    static constexpr int MINB = 2;
+    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_warp512_body<LD, ST, TWID>(jobs, c); }
+};
 template <int LD, int MODE, int ST, int SQ = 0> struct RowsK {
     static constexpr int MAXT = (SQ && sizeof(real) == 8) ? 256 : 512;
     static constexpr int MINB = (SQ && sizeof(real) == 8) ? MS_SQ_MINB : MS_FFT_MINB;
@@ -329,7 +334,9 @@ private:
             case 2:
                 if (sb_warp()) return L<ColsWarpK<LD, ST, TWID>>(gx, gy, 256, MS_JOB_SMEM + sizeof(cpx) * (size_t)(8 * WB_RS), st, jd);
                 return L<ColsK<LD, ST, TWID, 0, 256>>(gx, gy, 256, smem, st, jd);
-            case 3: return L<ColsK<LD, ST, TWID, 0, 512>>(gx, gy, 256, smem, st, jd);
+            case 3:
+                if (sb_warp() && LdPlain<LD>::v) return L<ColsWarp512K<LD, ST, TWID>>((gx + 1) / 2, gy, 256, MS_JOB_SMEM + sizeof(cpx) * (size_t)(8 * WB5_RS), st, jd);
+                return L<ColsK<LD, ST, TWID, 0, 512>>(gx, gy, 256, smem, st, jd);
             default: return L<ColsK<LD, ST, TWID, 0, 1024>>(gx, gy, 256, smem, st, jd);
         }
     }

@@ -427,16 +427,13 @@ MS_DEV void fft_cols_bluestein_warp256(const FftJob& J, const Ctx& c) {
             s[v * WB_RS + ms_pad(row)] = val;
         }
     }
-#pragma unroll
-    for (int i = 4; i < 8; ++i) {
-        const int e = c.tid + 256 * i;
-        s[(e & 7) * WB_RS + ms_pad(e >> 3)] = c_zero();
-    }
     c.sync();
     cpx v[8];
     cpx* sw = s + warp * WB_RS;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
+    for (int q = 0; q < 4; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
+#pragma unroll
+    for (int q = 4; q < 8; ++q) v[q] = c_zero();                // (the zero padding of the convolution never goes through shared memory)
     c.syncwarp();
     warp_fft256(v, sw, J.twb, lane, c);
 #pragma unroll
@@ -470,6 +467,73 @@ MS_DEV void fft_cols_bluestein_warp256(const FftJob& J, const Ctx& c) {
         const int e = c.tid + 256 * i, k1 = e >> 3, vv = e & 7;
         if (k1 < F1) job_store<ST>(J, k1 * F2 + col0 + vv, s[vv * WB_RS + ms_pad(k1)]);
     }
+}
+// B1 = 512 (F1 <= 256), same scheme with warp_fft512: eight columns per CTA, a lane holds sixteen values of its column.
+#define WB5_RS ((ms_pad(512) + 1) | 1)
+template <int LD, int ST, int TWID>
+MS_DEV void fft_cols_bluestein_warp512(const FftJob& J, const Ctx& c) {
+    const int F1 = J.F1, F2 = J.F2;
+    const int col0 = c.bx * 8;
+    if (col0 >= F2) return;
+    cpx* s = (cpx*)(c.smem + MS_JOB_SMEM);
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+    const int ncol = (F2 - col0) < 8 ? (F2 - col0) : 8;         // (the class guarantees 4 | F2 only: the last tile may hold four columns)
+    // rows 0 .. 255 may hold data, rows 256 .. 511 are the zero padding of the convolution (never staged: zeros in registers)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        cpx ld[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = c.tid + 256 * (4 * half + i), row = e >> 3, vv = e & 7;
+            ld[i] = (row < F1 && vv < ncol) ? job_load<LD>(J, row * F2 + col0 + vv) : c_zero();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = c.tid + 256 * (4 * half + i), row = e >> 3, vv = e & 7;
+            s[vv * WB5_RS + ms_pad(row)] = row < F1 ? c_mul(ld[i], __ldg(&J.b1_chirp[row])) : c_zero();
+        }
+    }
+    c.sync();
+    cpx v[16];
+    cpx* sw = s + warp * WB5_RS;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
+#pragma unroll
+    for (int q = 8; q < 16; ++q) v[q] = c_zero();
+    c.syncwarp();
+    warp_fft512(v, sw, J.twb, lane, c);
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = c_swap(c_mul(v[m], __ldg(&J.b1_spec[lane + 32 * m])));
+    c.syncwarp();
+    warp_fft512(v, sw, J.twb, lane, c);
+    c.syncwarp();
+    const int col = col0 + warp;
+    cpx tb = mk((real)1., (real)0.), ts = tb;
+    if (TWID) {
+        tb = tw_direct((unsigned)lane * (unsigned)col, J.M);
+        ts = tw2level(J.twM_hi, J.twM_lo, (unsigned)(((long long)32 * col) % J.M));
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {                               // F1 <= 256: outputs k1 = lane + 32 m, m < 8
+        const int k1 = lane + 32 * m;
+        if (k1 < F1) {
+            cpx val = c_mul(c_swap(v[m]), __ldg(&J.b1_chirp[k1]));
+            if (TWID) val = c_mul(val, tb);
+            sw[ms_pad(k1)] = val;
+        }
+        if (TWID) tb = c_mul(tb, ts);
+    }
+    c.sync();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = c.tid + 256 * i, k1 = e >> 3, vv = e & 7;
+        if (k1 < F1 && vv < ncol) job_store<ST>(J, k1 * F2 + col0 + vv, s[vv * WB5_RS + ms_pad(k1)]);
+    }
+}
+template <int LD, int ST, int TWID>
+MS_DEV void fft_cols_warp512_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
+    const FftJob& J = stage_job(jobs, c);
+    fft_cols_bluestein_warp512<LD, ST, TWID>(J, c);
 }
 template <int LD, int ST, int TWID>
 MS_DEV void fft_cols_warp_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
