@@ -173,10 +173,13 @@ private:
         return 0;
     }
 
-    // development switch MS_PLAN_W="c128,c256,c512,c1024,rows": per-element cost of the in-tile Bluestein columns by convolution
-    // length and of one radix-2 level of the rows pass (unset: the analytic cost)
+    // Per-element cost of the in-tile Bluestein columns by convolution length (<= 128, 256, 512, 1024) and of one radix-2
+    // level of the rows pass, relative to the warp-local 256 kernel.  Measured on B200 (C5 sweep, f64, per padded element):
+    // 128: 1.4, 256: 1.0, 512 (warp-local): 1.45, 1024 (block-wide tile): 2.45 -- so a longer convolution has to buy a much
+    // better padding ratio to be chosen (step 31.2 -> 30.8 ms against the analytic cost).  Development switch
+    // MS_PLAN_W="c128,c256,c512,c1024,rows" overrides; MS_PLAN_W=0 selects the analytic cost.
     static const double* mixed_weights() {
-        static double w[5] = {-1, 0, 0, 0, 0}; static int init = 0;
+        static double w[5] = {1.4, 1.0, 1.45, 2.45, 0.02}; static int init = 0;
         if (!init) {
             init = 1;
             const char* e = getenv("MS_PLAN_W");
