@@ -29,6 +29,11 @@ template <int LD, int ST, int TWID> struct ColsWarpK {              // in-tile B
     static constexpr int MINB = MS_WB_MINB;
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_warp_body<LD, ST, TWID>(jobs, c); }
 };
+template <int LD, int ST, int TWID> struct ColsWarpPlainK {         // plain columns of 256 rows, warp-local transform
+    static constexpr int MAXT = 256;
+    static constexpr int MINB = MS_WB_MINB;
+    static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_warp_plain_body<LD, ST, TWID>(jobs, c); }
+};
 template <int LD, int ST, int TWID> struct ColsWarp512K {           // in-tile Bluestein, B1 = 512, warp-local transforms (16 values per lane)
     static constexpr int MAXT = 256;
     static constexpr int MINB = 2;
@@ -102,6 +107,7 @@ public:
     // jobs_dev: device copy of `jobs` (same order).  Jobs must be sorted by job_class().
     // + 4 * static Bluestein id (1..4 for B1 = 128, 256, 512, 1024 with 2048-element tiles of full columns)
     static int sb_id(const FftJob& J) {
+        if (!J.B1 && !J.ch_hi && J.F1 == 256 && J.T == 8 && (J.n & (J.n - 1))) return 5;   // plain warp-local columns
         if (!J.B1 || J.ch_hi || J.T * J.B1 != MS_SB_TILE || J.F2 % J.T) return 0;
         return J.B1 == 128 ? 1 : J.B1 == 256 ? 2 : J.B1 == 512 ? 3 : J.B1 == 1024 ? 4 : 0;
     }
@@ -203,6 +209,14 @@ private:
         if (!best) return false;
         J.F1 = best; J.F2 = n / best;
         J.T = 16; J.G = 16;
+        // smooth n with 256 | n (not a power of two: those belong to the FIR stage's static kernels): columns of exactly 256
+        // rows run as one warp-local transform each -- a third of the generic tile's cost per element
+        if ((n & (n - 1)) && n % 256 == 0 && n / 256 >= 16 && n / 256 <= MS_TILE_MAX / 4) {
+            J.F1 = 256; J.F2 = n / 256; J.T = 8;
+            while (J.G > 4 && J.G * J.F2 > MS_TILE_MAX / 2) J.G /= 2;
+            while (J.G > 1 && J.G * J.F2 > MS_TILE_MAX) J.G /= 2;
+            return true;
+        }
         while (J.T > 4 && J.T * J.F1 > MS_TILE_MAX / 2) J.T /= 2;       // half tiles (<= 74 KB in f64): three CTAs per SM
         while (J.G > 4 && J.G * J.F2 > MS_TILE_MAX / 2) J.G /= 2;
         while (J.T > 1 && J.T * J.F1 > MS_TILE_MAX) J.T /= 2;
@@ -340,6 +354,9 @@ private:
             case 3:
                 if (sb_warp() && LdPlain<LD>::v) return L<ColsWarp512K<LD, ST, TWID>>((gx + 1) / 2, gy, 256, MS_JOB_SMEM + sizeof(cpx) * (size_t)(8 * WB5_RS), st, jd);
                 return L<ColsK<LD, ST, TWID, 0, 512>>(gx, gy, 256, smem, st, jd);
+            case 5:
+                if (LdPlain<LD>::v) return L<ColsWarpPlainK<LD, ST, TWID>>(gx, gy, 256, MS_JOB_SMEM + sizeof(cpx) * (size_t)(8 * WB_RS), st, jd);
+                return -1;
             default: return L<ColsK<LD, ST, TWID, 0, 1024>>(gx, gy, 256, smem, st, jd);
         }
     }
@@ -451,8 +468,8 @@ private:
                                      : launch_cols<LD_WORK, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
                     if (!rc) rc = launch_rows<LD_WORK, MODE_NAT, ST_PAIR>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
                 } else {
-                    rc = sb ? launch_cols_sb<LD_SPEC, ST_WORK, 1>(sb, C.gx, gy, st, jd)
-                            : launch_cols<LD_SPEC, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
+                    rc = (sb && sb != 5) ? launch_cols_sb<LD_SPEC, ST_WORK, 1>(sb, C.gx, gy, st, jd)
+                                         : launch_cols<LD_SPEC, ST_WORK, 1>(C.ept, C.gx, gy, C.nthr, C.smem, st, jd);
                     if (!rc) rc = launch_rows<LD_WORK, MODE_NAT, ST_PAIR>(R.ept, R.gx, gy, R.nthr, R.smem, st, jd);
                 }
             } else if (cls == 2) {

@@ -468,6 +468,60 @@ MS_DEV void fft_cols_bluestein_warp256(const FftJob& J, const Ctx& c) {
         if (k1 < F1) job_store<ST>(J, k1 * F2 + col0 + vv, s[vv * WB_RS + ms_pad(k1)]);
     }
 }
+// Plain columns of exactly 256 rows (smooth n with 256 | n): one warp-local transform per column, no convolution.
+template <int LD, int ST, int TWID>
+MS_DEV void fft_cols_warp_plain256(const FftJob& J, const Ctx& c) {
+    const int F2 = J.F2;
+    const int col0 = c.bx * 8;
+    if (col0 >= F2) return;
+    const int ncol = (F2 - col0) < 8 ? (F2 - col0) : 8;
+    cpx* s = (cpx*)(c.smem + MS_JOB_SMEM);
+    const int lane = c.tid & 31, warp = c.tid >> 5;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        cpx ld[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = c.tid + 256 * (4 * half + i);
+            ld[i] = (e & 7) < ncol ? job_load<LD>(J, (e >> 3) * F2 + col0 + (e & 7)) : c_zero();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = c.tid + 256 * (4 * half + i);
+            s[(e & 7) * WB_RS + ms_pad(e >> 3)] = ld[i];
+        }
+    }
+    c.sync();
+    cpx v[8];
+    cpx* sw = s + warp * WB_RS;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = sw[ms_pad(lane + 32 * q)];
+    c.syncwarp();
+    warp_fft256(v, sw, J.tw1, lane, c);
+    c.syncwarp();
+    const int col = col0 + warp;
+    cpx tb = mk((real)1., (real)0.), ts = tb;
+    if (TWID) {
+        tb = tw_direct((unsigned)lane * (unsigned)col, J.M);
+        ts = tw2level(J.twM_hi, J.twM_lo, (unsigned)(((long long)32 * col) % J.M));
+    }
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        sw[ms_pad(lane + 32 * m)] = TWID ? c_mul(v[m], tb) : v[m];
+        if (TWID) tb = c_mul(tb, ts);
+    }
+    c.sync();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = c.tid + 256 * i;
+        if ((e & 7) < ncol) job_store<ST>(J, (e >> 3) * F2 + col0 + (e & 7), s[(e & 7) * WB_RS + ms_pad(e >> 3)]);
+    }
+}
+template <int LD, int ST, int TWID>
+MS_DEV void fft_cols_warp_plain_body(const FftJob* MS_RESTRICT jobs, const Ctx& c) {
+    const FftJob& J = stage_job(jobs, c);
+    fft_cols_warp_plain256<LD, ST, TWID>(J, c);
+}
 // B1 = 512 (F1 <= 256), same scheme with warp_fft512: eight columns per CTA, a lane holds sixteen values of its column.
 #define WB5_RS ((ms_pad(512) + 1) | 1)
 template <int LD, int ST, int TWID>

@@ -11,7 +11,7 @@ from oracle import microsound_np as O
 @pytest.mark.parametrize("precision,tol", [("f32", 2e-6), ("f64", 1e-13)])
 def test_fft_direct_twopass_bluestein(emul, precision, tol):
     K.check_fft_lengths(emul, precision, [16, 60, 125, 243, 480, 1000, 7680, 8192, 17, 97, 1690, 3301, 4097,
-                                           9000, 12480, 20011, 51900, 83040], tol)   # 51900 = 173 * 300, 83040 = 173 * 480: in-tile Bluestein of 512
+                                           9000, 12480, 20011, 51900, 83040, 15360, 19200], tol)   # 51900 = 173 * 300, 83040 = 173 * 480: in-tile Bluestein of 512
 
 
 @pytest.mark.parametrize("precision,tol", [("f32", 3e-6), ("f64", 1e-12)])

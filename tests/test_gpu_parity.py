@@ -21,7 +21,7 @@ def test_native_library_is_the_cuda_build(cuda_dev):
 @pytest.mark.parametrize("precision,tol", [("f32", 2e-6), ("f64", 1e-13)])
 def test_fft_lengths(cuda_dev, precision, tol):
     K.check_fft_lengths(cuda_dev, precision, [16, 60, 125, 243, 480, 1000, 7680, 8192, 17, 97, 1690, 3301, 4097, 9000,
-                                               12480, 20011, 24000, 48000, 96000, 93600, 300000, 65536, 262144, 131101, 51900, 83040, 95520, 62880],
+                                               12480, 20011, 24000, 48000, 96000, 93600, 300000, 65536, 262144, 131101, 51900, 83040, 95520, 62880, 15360, 19200, 76800],
                         tol)
 
 
