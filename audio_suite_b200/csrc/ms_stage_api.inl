@@ -193,7 +193,7 @@ extern "C" int MS_API(ms_imprint)(const ms_imprint_evt* evts, const ms_imprint_r
 }
 extern "C" int MS_API(ms_overlap_add)(const ms_ola_render* renders, int n_renders, int max_out_n, const ms_ola_evt* evts,
                               const real* pool, const real* envpool, real* mono, void* stream) {
-    const unsigned gx = (unsigned)((max_out_n + OLA_TILE - 1) / OLA_TILE);
+    const unsigned gx = (unsigned)((max_out_n + OLA_ATILE - 1) / OLA_ATILE);
     MS_FOR_Y_CHUNKS(n_renders, { if (ms_launch<OlaK>(mk_dim(gx, (unsigned)_yc), OLA_NTHR, 0, (ms_stream_t)stream, renders + _y0, evts, pool, envpool, mono)) return -1; })
     return 0;
 }

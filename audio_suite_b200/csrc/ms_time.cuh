@@ -35,12 +35,16 @@ MS_DEV void adsr_table_body(const OlaRender* MS_RESTRICT reps, real* MS_RESTRICT
     for (int i = t0 + c.tid; i < t1; i += c.nthr) envpool[R.env + i] = adsr_gain(R, i);
 }
 
+// (the overlap-add tile is twice the post tile: the kernel is a chain of dependent global loads -- render record, event
+//  record, grain samples, envelope -- and ncu has it waiting on them (long scoreboard 18.6 warps per issue, 27 % issue slots):
+//  eight samples per thread halve the number of chains)
+#define OLA_ATILE (2 * OLA_TILE)
 MS_DEV void ola_adsr_body(const OlaRender* MS_RESTRICT renders, const OlaEvt* MS_RESTRICT evts,
                           const real* MS_RESTRICT pool, const real* MS_RESTRICT envpool, real* MS_RESTRICT mono, const Ctx& c) {
     const OlaRender R = renders[c.by];
-    const int t0 = c.bx * OLA_TILE;
+    const int t0 = c.bx * OLA_ATILE;
     if (t0 >= R.out_n) return;
-    const int t1 = (t0 + OLA_TILE) < R.out_n ? (t0 + OLA_TILE) : R.out_n;
+    const int t1 = (t0 + OLA_ATILE) < R.out_n ? (t0 + OLA_ATILE) : R.out_n;
     // candidates: start < t1 and start > t0 - max_len
     int lo = R.ev_begin, hi = R.ev_end;
     while (lo < hi) { const int m = (lo + hi) >> 1; if (evts[m].start >= t1) hi = m; else lo = m + 1; }
@@ -49,24 +53,24 @@ MS_DEV void ola_adsr_body(const OlaRender* MS_RESTRICT renders, const OlaEvt* MS
     while (lo < hi) { const int m = (lo + hi) >> 1; if (evts[m].start > t0 - R.max_len) hi = m; else lo = m + 1; }
     const int ea = lo;
     real* out = mono + R.out;
-    // every thread owns OLA_TILE / OLA_NTHR samples (i = t0 + tid + q * nthr) and keeps their sums in registers;
+    // every thread owns OLA_ATILE / OLA_NTHR samples (i = t0 + tid + q * nthr) and keeps their sums in registers;
     // events are the outer loop (one descriptor fetch per event, not per sample) and are added in event order,
     // so each output sample sees the same sequence of additions as out[start:start+L] += amp * g (main_v2.py:755)
-    real acc[OLA_TILE / OLA_NTHR];
+    real acc[OLA_ATILE / OLA_NTHR];
 #pragma unroll
-    for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) acc[q] = (real)0.;
+    for (int q = 0; q < OLA_ATILE / OLA_NTHR; ++q) acc[q] = (real)0.;
     for (int e = ea; e < eb; ++e) {
         const int st = __ldg(&evts[e].start), ln = __ldg(&evts[e].len);
         const real amp = (real)__ldg(&evts[e].amp);
         const real* g = pool + evts[e].grain;
 #pragma unroll
-        for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) {
+        for (int q = 0; q < OLA_ATILE / OLA_NTHR; ++q) {
             const int k = t0 + c.tid + q * OLA_NTHR - st;
             if (k >= 0 && k < ln) acc[q] += amp * __ldg(&g[k]);
         }
     }
 #pragma unroll
-    for (int q = 0; q < OLA_TILE / OLA_NTHR; ++q) {
+    for (int q = 0; q < OLA_ATILE / OLA_NTHR; ++q) {
         const int i = t0 + c.tid + q * OLA_NTHR;
         if (i < t1) out[i] = acc[q] * (R.env >= 0 ? __ldg(&envpool[R.env + i]) : adsr_gain(R, i));
     }

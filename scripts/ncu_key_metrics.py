@@ -3,9 +3,9 @@ usage: ncu_key_metrics.py raw.csv > table.md"""
 import csv
 import sys
 
-COLS = [("ms", "gpu__time_duration.sum", 1e-6),
+COLS = [("ms", "gpu__time_duration.sum", 1),
         ("regs", "launch__registers_per_thread", 1),
-        ("smem KB", "launch__shared_mem_per_block_dynamic", 1e-3),
+        ("smem KB", "launch__shared_mem_per_block_dynamic", 1),
         ("occ %", "sm__warps_active.avg.pct_of_peak_sustained_active", 1),
         ("issue %", "sm__inst_issued.avg.pct_of_peak_sustained_active", 1),
         ("LSU wavefronts %", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", 1),
@@ -17,26 +17,30 @@ COLS = [("ms", "gpu__time_duration.sum", 1e-6),
         ("smem conflicts / wavefront", None, 1),
         ("local ld+st wavefronts %", None, 1)]
 STALLS = "smsp__average_warps_issue_stalled_"
+STALL_END = "_per_issue_active.ratio"
 
 
 def main():
     rows = list(csv.reader(open(sys.argv[1])))
-    hdr, data = rows[0], rows[2:]
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    scale_of = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Kbyte/block": 1.0}
     ix = {}
     for i, h in enumerate(hdr):
         ix.setdefault(h, i)
         ix.setdefault(h.split(".", 2)[-1] if h.startswith(("SM_", "TPC.", "GPC.")) else h, i)
 
     def get(r, name, default=0.0):
+        """value in ms (times), bytes (sizes) or as reported (everything else)"""
         for k in (name, "TPC.TriageCompute." + name, "SM_A.TriageCompute." + name):
             if k in ix:
                 try:
-                    return float(r[ix[k]].replace(",", ""))
+                    return float(r[ix[k]].replace(",", "")) * scale_of.get(units[ix[k]], 1.0)
                 except ValueError:
                     return default
         return default
-    stall_cols = [(h[len(STALLS):].replace("_per_warp_active.pct", ""), i) for i, h in enumerate(hdr) if h.startswith(STALLS) and h.endswith("_per_warp_active.pct")]
-    print("| kernel | grid | " + " | ".join(c[0] for c in COLS) + " | top stall reasons (% of warp-cycles) |")
+    stall_cols = [(h[len(STALLS):-len(STALL_END)], i) for i, h in enumerate(hdr) if h.startswith(STALLS) and h.endswith(STALL_END)
+                  and "selected" not in h]
+    print("| kernel | grid | " + " | ".join(c[0] for c in COLS) + " | top stall reasons (warps stalled per issue cycle) |")
     print("|---|---|" + "---|" * (len(COLS) + 1))
     for r in data:
         name = r[ix["Kernel Name"]].replace("void ms_kernel<", "").split(", const")[0].replace("msd::", "").replace("msf::", "")
@@ -54,7 +58,7 @@ def main():
                 v = get(r, key) * scale
             vals.append("%.3f" % v if abs(v) < 10 else "%.1f" % v)
         st = sorted(((float(r[i].replace(",", "") or 0), n) for n, i in stall_cols), reverse=True)[:3]
-        print("| %s | %s | %s | %s |" % (name, r[ix["Grid Size"]], " | ".join(vals), ", ".join("%s %.0f" % (n, v) for v, n in st)))
+        print("| %s | %s | %s | %s |" % (name, r[ix["Grid Size"]], " | ".join(vals), ", ".join("%s %.2f" % (n, v) for v, n in st)))
 
 
 if __name__ == "__main__":
