@@ -35,10 +35,10 @@ MS_DEV void adsr_table_body(const OlaRender* MS_RESTRICT reps, real* MS_RESTRICT
     for (int i = t0 + c.tid; i < t1; i += c.nthr) envpool[R.env + i] = adsr_gain(R, i);
 }
 
-// (the overlap-add tile is twice the post tile: the kernel is a chain of dependent global loads -- render record, event
-//  record, grain samples, envelope -- and ncu has it waiting on them (long scoreboard 18.6 warps per issue, 27 % issue slots):
-//  eight samples per thread halve the number of chains)
-#define OLA_ATILE (2 * OLA_TILE)
+// (ncu has this kernel waiting on its chain of dependent global loads -- render record, event record, grain samples,
+//  envelope: long scoreboard 18.6 warps per issue, 27 % of the issue slots.  Tiles of 2048 samples, i.e. half as many
+//  chains, were measured SLOWER on B200: 1.52 -> 1.58 ms on the C5 sweep.)
+#define OLA_ATILE OLA_TILE
 MS_DEV void ola_adsr_body(const OlaRender* MS_RESTRICT renders, const OlaEvt* MS_RESTRICT evts,
                           const real* MS_RESTRICT pool, const real* MS_RESTRICT envpool, real* MS_RESTRICT mono, const Ctx& c) {
     const OlaRender R = renders[c.by];
