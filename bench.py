@@ -375,6 +375,9 @@ def run_ours(args):
     for evs in stage_ev:
         for name, a, b in zip(stage_names, evs[:-1], evs[1:]):
             stage_ms[name] = stage_ms.get(name, 0.0) + a.elapsed_time(b) / len(stage_ev)
+    if os.environ.get("MS_RANK_TIMES"):                 # every rank's own stage table (rank 0's goes into the JSON line)
+        print("rank %d: step %.3f ms own clock, stages %s, renders %d" % (
+            rank, ms, {k: round(v, 3) for k, v in stage_ms.items()}, len(mine)), file=sys.stderr, flush=True)
 
     # ---- individual kernels of one step: the library calls a hook after every launch, a CUDA event is recorded
     #      there (on the launching stream), consecutive events bracket one kernel.  Separate untimed steps, so

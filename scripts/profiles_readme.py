@@ -1,73 +1,101 @@
-"""Regenerates profiles/README.md from the artefacts committed beside it."""
-import io, json, os, subprocess, sys
+"""Regenerates profiles/README.md from the artefacts committed beside it (round 2)."""
+import io
+import json
+import os
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
-d = json.load(open(os.path.join(P, "bench_r01i_n1.json")))
-r = json.load(open(os.path.join(P, "bench_r01i_reference_arm.json")))
+load = lambda name: json.load(open(os.path.join(P, name)))
+d, r = load("r02_bench_n1.json"), load("r02_bench_ref.json")
+r1 = load("bench_r01i_n1.json")
 o = io.StringIO()
 w = lambda *a: print(*a, file=o)
-w("# profiles/ — round 1 measurements (B200, sm_100a, CUDA 12.9, driver 580)\n")
-w("All runs: `gpurun` on one fresh B200 box; timed numbers come from `bench.py` (CUDA events, no profiler);")
-w("ncu numbers are cold-cache/serialised and are used for *shares* and counters only.  Regenerate this file with")
-w("`python scripts/profiles_readme.py`.\n")
-w("## 1. bench.py, C5 sweep (4096 renders x 96000 stereo frames, f64), N=1 (`bench_r01i_n1.json`)\n")
+w("# profiles/ — round 2 measurements (B200, sm_100a, CUDA 12.9, driver 580)\n")
+w("All runs: `gpurun` on fresh B200 boxes; timed numbers come from `bench.py` (CUDA events, no profiler); ncu numbers are")
+w("cold-cache / serialised and are used for *shares* and counters only.  Regenerate this file with `python scripts/profiles_readme.py`.")
+w("Round-1 artefacts (`*_r01*`) are kept for the history; everything named `r02_*` is the final build of round 2.\n")
+w("## 1. bench.py, C5 sweep (4096 renders x 96000 stereo frames, f64), N = 1 (`r02_bench_n1.json`, `r02_bench_ref.json`)\n")
 e = d["e2e"]
-w("* `value` (plan resident in HBM): **%.3e samples/s** (%.1f ms/step), %d kernel launches/step, SM clock %s MHz, throttle reasons %s" % (
+w("* `value` (plan resident in HBM): **%.3e samples/s** (%.2f ms/step), %d kernel launches/step, SM clock %s MHz, throttle reasons %s" % (
     d["value"], d["ms_per_step"], d["gpu_launches"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"]))
-w("* `e2e` (host dicts -> pinned host float32 audio, `render_batch`): **%.3e samples/s** (%.1f ms/step mean of %s; H2D %.1f MB, D2H %.2f GB)" % (
+w("* `e2e` (host dicts -> pinned host float32 audio, `render_batch`): **%.3e samples/s** (%.1f ms/step, runs %s; H2D %.1f MB, D2H %.2f GB)" % (
     e["value"], e["ms_per_step"], e.get("ms_each_rank0"), e["h2d_bytes_per_step"] / 1e6, e["d2h_bytes_per_step"] / 1e9))
-w("* `cpu_baseline` (oracle port, 1 core): %.3e samples/s;  `--impl reference` (oracle port, %d cores, `bench_r01i_reference_arm.json`): %.3e samples/s" % (
+w("* `cpu_baseline` (oracle port, 1 core): %.3e samples/s;  `--impl reference` (oracle port, %d cores): %.3e samples/s" % (
     d["cpu_baseline"]["value"], r["cpu_baseline"]["cores"], r["value"]))
-w("* e2e / reference-arm = **%.0fx**;  value / reference-arm = %.0fx" % (e["value"] / r["value"], d["value"] / r["value"]))
-w("* round history of the same metric (ms/step, kernels | e2e): first GPU run 84.9 | 252 -> session start 67.2 | 226 -> now %.1f | %.0f\n" % (d["ms_per_step"], min(e.get("ms_each_rank0", [e["ms_per_step"]]))))
-w("| stage | ms | algorithmic GB | GB/s | fraction of measured HBM peak (%.1f GB/s) |" % d["roofline"]["peak"])
-w("|---|---|---|---|---|")
+w("* e2e / reference-arm = **%.0fx**;  value / reference-arm = %.0fx  (same box, back to back)" % (e["value"] / r["value"], d["value"] / r["value"]))
+w("* history of the same metric (ms/step, kernels | e2e): round 1 first run 84.9 | 252 -> round 1 final %.1f | %.0f -> round 2 final **%.2f | %.0f**\n" % (
+    r1["ms_per_step"], r1["e2e"]["ms_per_step"], d["ms_per_step"], e["ms_per_step"]))
+w("| stage | round 1 ms | round 2 ms | algorithmic GB | GB/s | fraction of measured HBM peak (%.1f GB/s) |" % d["roofline"]["peak"])
+w("|---|---|---|---|---|---|")
 for k, v in d["stages"].items():
-    w("| %s | %.2f | %.2f | %.1f | %.4f |" % (k, v["ms"], v["algorithmic_GB"], v["GBps"] or 0, v["frac_of_hbm"] or 0))
+    w("| %s | %.2f | **%.2f** | %.2f | %.1f | %.4f |" % (k, r1["stages"][k]["ms"], v["ms"], v["algorithmic_GB"], v["GBps"] or 0, v["frac_of_hbm"] or 0))
 w("")
 rf = d["roofline"]
-w("`roofline` of the dominant stage (%s): achieved %.1f GB/s of %.1f (frac %.4f); algorithmic bytes %.2f GB, measured DRAM traffic %.2f GB (%s)\n" % (
-    rf["kernel"], rf["achieved"], rf["peak"], rf["frac"], rf["algorithmic_bytes"] / 1e9, (rf["traffic"] or 0) / 1e9, rf["traffic_note"]))
-w("### Every launch of one step, timed live (CUDA event after each launch via `ms_set_launch_hook`)\n")
-w("Template arguments: `ColsK<LD, ST, TWID, SQ, SB>` / `RowsK<LD, MODE, ST, SQ>` (SQ: static 256x256 tile width, SB: static Bluestein length).\n")
+w("`roofline` of the dominant stage (%s): achieved %.1f GB/s of %.1f (frac %.4f); algorithmic bytes %.2f GB, measured DRAM traffic %.2f GB (%s).  "
+  "The HBM fraction is small because **no FFT-type kernel here is DRAM-bound: they run at 70-93 %% of the SM's L1 / shared-memory data pipe** "
+  "(section 3) -- that pipe, not HBM or the FP64 units, is the roofline these kernels sit under.\n" % (
+      rf["kernel"], rf["achieved"], rf["peak"], rf["frac"], rf["algorithmic_bytes"] / 1e9, (rf["traffic"] or 0) / 1e9, rf["traffic_note"]))
+w("### Every launch of one step, timed live (CUDA event after each launch via `ms_set_launch_hook`; the length classes of a spectral stage run one after the other in this mode)\n")
+w("`ColsWarpK / ColsWarp512K / ColsWarpPlainK<LD, ST, TWID>`: warp-local column transforms (in-tile Bluestein of 256 / 512, plain 256); "
+  "`ColsK<LD, ST, TWID, SQ, SB>` / `RowsK<LD, MODE, ST, SQ>`: block-wide tiles; `SpecOpK`: the spectral operators, elementwise.\n")
 w("| # kernel | ms |\n|---|---|")
 for k, v in d["kernels_ms"].items():
     w("| %s | %.3f |" % (k, v))
 w("")
-w("### 1 / 2 / 4 / 8 GPUs (`torchrun`, one rank per GPU, NCCL gather of the rendered buffers to rank 0 inside the step; strong scaling, 4096 renders)\n")
-w("| N | ms/step | samples/s | speed-up | e2e ms/step | e2e samples/s |\n|---|---|---|---|---|---|")
+w("### 1 / 2 / 4 / 8 GPUs (`torchrun`, one rank per GPU; strong scaling: 4096 renders in total; `r02_bench_n{1,2,4,8}.json`)\n")
+w("Every rank stores its rendered float32 buffer into rank 0's symmetric-memory receive slab over NVLink (copy engines) inside the timed region; "
+  "pass k is gathered while pass k+1 renders.\n")
+w("| N | ms/step | render only ms | samples/s | speed-up | efficiency | round 1 ms/step | e2e ms/step |\n|---|---|---|---|---|---|---|---|")
 base = None
 for n in (1, 2, 4, 8):
-    x = json.load(open(os.path.join(P, "bench_r01i_n%d.json" % n)))
+    x = load("r02_bench_n%d.json" % n)
+    y = load("bench_r01i_n%d.json" % n)
     base = base or x["value"]
-    w("| %d | %.2f | %.3e | %.2fx | %.1f | %.3e |" % (n, x["ms_per_step"], x["value"], x["value"] / base, x["e2e"]["ms_per_step"], x["e2e"]["value"]))
+    w("| %d | %.2f | %s | %.3e | %.2fx | %.3f | %.2f | %.1f |" % (
+        n, x["ms_per_step"], ("%.2f" % x["ms_per_step_render_only"]) if x.get("ms_per_step_render_only") else "-", x["value"], x["value"] / base,
+        x["value"] / base / n, y["ms_per_step"], x["e2e"]["ms_per_step"]))
 w("")
-w("At N = 8 a rank renders its 512 renders in about 5.9 ms and rank 0 then receives 2.75 GB over NVLink (about 4.6 ms): the gather, not the kernels, bounds the step.  Cutting every rank's share into four slices whose gather overlaps the next slice's rendering was measured slower (12.0 ms, `bench_r01h_n8_sliced4.json`: the slices get launch-bound), so it stays optional (`--slices`).  End to end the multi-GPU runs are bound by host planning (0.27 ms of Python per render, 32 cores on the 8-GPU box).\n")
-sc = json.load(open(os.path.join(P, "small_configs_r01j.json")))
-w("### Single renders (configs 1-3: launch-latency-bound, a few hundred KB of data each; `small_configs_r01j.json`)\n")
-w("| config | render() ms | kernels only ms | numpy on one host core ms | max-abs vs numpy |\n|---|---|---|---|---|")
-for r_ in sc["rows"]:
-    w("| %s | %.2f | %.3f | %.2f | %.1e |" % (r_["config"], r_["render_ms"], r_["kernels_only_ms"], r_["numpy_ms"], r_["max_abs"]))
+w("Where the 8-GPU step goes (per-rank CUDA events, `MS_RANK_TIMES=1`): a rank renders its 512 renders in 4.23-4.39 ms alone (the ideal share is 3.82 ms: "
+  "sixty launches over an eighth of the batch leave partial waves); with the gather in flight every rank's kernels take 0.45-0.5 ms longer and the "
+  "ranks are coupled pass by pass through the gather's barriers (5.0 ms).  NCCL's gather in place of the peer copies: 6.0 ms; without the overlap: 9.0 ms.  "
+  "End to end the multi-GPU runs are bound by the host: eight GPUs draining to pinned host memory at once get about 12 GB/s each "
+  "(~100 GB/s in total on these boxes, against 50 GB/s for one GPU alone), so 3.15 GB of audio cost ~32 ms whatever N >= 2 is.\n")
+w("### The other BASELINE.json configs, one render each (`r02_bench_C*.json`, `bench.py --config`)\n")
+w("| config | kernels ms (graph replay) | render() ms end to end | numpy oracle on one host core, samples/s | launches |\n|---|---|---|---|---|")
+for c in ("C1b", "C1", "C2", "C3", "C4"):
+    x = load("r02_bench_%s.json" % c)
+    w("| %s | %.3f | %.2f | %.3e | %s |" % (c, x["ms_per_step"], x["e2e"]["ms_per_step"], x["cpu_baseline"]["value"], x.get("gpu_launches")))
 w("")
-w("The smallest case (C1b, 7680 samples) is faster in numpy (0.56 ms) than through the GPU path (0.90 ms: planning, ten launches, one D2H): these sizes are below one kernel launch's worth of HBM time (SURVEY H5).\n")
-w("C4 (long-form render, 57.6 M frames, 1222 events of 300000 samples): kernels 31 ms (synth 6.4, grain spectral 21.1, OLA 0.8, FIR 2.0, post 0.8), `render()` end to end 0.48 s; the reference took 244 s on one core of the build container (`tests/golden/c4_full.npz`).\n")
-w("## 2. ncu launch list of one step, 512-render slab (`launches_r01i_512renders.csv`)\n")
-w("`ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,... --clock-control none` around the timed step of `bench.py --renders 512`.\n")
-out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summarise.py"), os.path.join(P, "launches_r01i_512renders.csv"), "512"],
-                     capture_output=True, text=True).stdout
-w(out)
-w("Stage shares under ncu agree with the CUDA-event stage table above (spectral stages 48 %, FIR 28 %, synth 11 %, post 10 %, OLA 3 %).  `ncu_traffic.json` holds the per-stage DRAM bytes per render that `bench.py` scales into `roofline.traffic`.\n")
-w("## 3. `ncu --set full` counters of the key kernels, current build (`ncu_full_r01i_key_kernels.csv`, 512-render slab)\n")
-rows = list(__import__("csv").reader(open(os.path.join(P, "ncu_full_r01i_key_kernels.csv"))))
-w("| " + " | ".join(c[:28] for c in rows[0]) + " |")
-w("|" + "---|" * len(rows[0]))
-for r in rows[1:]:
-    w("| " + " | ".join((c if i == 0 else (c[:8] if c.replace(".", "").isdigit() else c)) for i, c in enumerate(r)) + " |")
-w("")
-w("Reading: the static in-place FFT tiles (ColsK<..., 256>, ColsK<7, 0, 1, 8>, RowsK<0, 1, 0, 8>) now keep 58-61 % of the warp slots busy (24-30 % before this round's occupancy work), 5 CTAs/SM limited equally by registers (48) and shared memory; the FP64 pipe is 17-35 % busy and the issue slots 31-55 %, so they are still latency-bound on shared-memory round trips rather than on a pipe or on DRAM (29-32 % of DRAM throughput for the FIR kernels).  OlaK runs at 35 % DRAM throughput with 44 % of the warp slots (64 registers: 4 CTAs/SM).  PostMaxK has 32 % of its shared-memory wavefronts in bank conflicts (the de-interleaving stores), the next thing to fix there.  SynthNormalK is integer/FP64-issue bound (DRAM 2.6 %), as designed.\n")
-w("## 4. Earlier captures kept for the record\n")
-w("* `ncu_full_raw_r01c_512renders.csv`: `ncu --set full` raw metrics of every kernel of a step at build r01c (first FFT engine): FFT tile kernels 24-30 % of warp slots active, fp64 pipe 6-18 %, issue 30-45 % — latency-bound; that reading drove the occupancy work of this round (register caps, in-place static tiles).")
-w("* `launches_r01b_512renders.csv`, `bench_r01_*.json`: first measurements of the round (84.9 ms/step, e2e 252 ms, reference arm on 16 cores).")
-w("* Source-level stall samples of the FIR rows kernel and the inverse Bluestein columns kernel (ncu `--set full --import-source on`, build r01e): long-scoreboard stalls on twiddle / job-descriptor loads dominated (52 % / 46 % of samples); integer address arithmetic was 70 % of issued instructions.  Fixes that followed: job descriptor staged in shared memory, magic-number divisions, static tile geometry.")
+w("C1-C3 are launch-latency-sized (a few hundred KB of data); `render()` is dominated by Python (plan cache lookup, one D2H, the float64 copy the reference returns).  "
+  "C4 (57.6 M frames): 22 ms of kernels; `render()` spends the rest converting 461 MB of float32 into the float64 array the reference's signature promises.\n")
+w("## 2. ncu launch list of one step, 512-render slab (`launches_r02_512renders.csv`, table in `r02_launch_table.md`)\n")
+w("`ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none` around the timed step of "
+  "`bench.py --renders 512` (after the same command had exited 0 without ncu).  Stage shares under ncu:\n")
+nt = load("ncu_traffic.json")
+w("| stage | ncu share | ncu ms | bench share (N = 1, 4096 renders) | DRAM MB per render |\n|---|---|---|---|---|")
+tot = sum(v["ms"] for v in d["stages"].values())
+for k in d["stages"]:
+    w("| %s | %.3f | %.3f | %.3f | %.2f |" % (k, nt["ncu_share"][k], nt["ncu_ms"][k], d["stages"][k]["ms"] / tot, nt["dram_bytes_per_render"][k] / 1e6))
+w("\n(`ncu_traffic.json` holds the per-stage DRAM bytes per render that `bench.py` scales into `roofline.traffic`.)\n")
+w("## 3. `ncu --set full` of the kernels that carry the step, final build (`r02_ncu_key_metrics.md`, `r02_ncu_full_details.csv`)\n")
+w(open(os.path.join(P, "r02_ncu_key_metrics.md")).read())
+w("Reading (this is what drove the second half of round 2):\n")
+w("* **The FFT-type kernels are bound by the L1 / shared-memory data pipe** (`l1tex__data_pipe_lsu_wavefronts`): 87-93 % of its peak in FirP1K / FirP3K / PostMaxK, "
+  "70-77 % in ColsWarpK / FirP2K.  DRAM is at 5-54 %, the FP64 pipe at 4-23 %, issue slots at 33-52 %.  Shared-memory traffic is only about half of those wavefronts: "
+  "the other half are GLOBAL accesses, which this pipe moves at half the width of a shared-memory access -- and a table lookup at a per-lane address costs up to 32 sectors a request.")
+w("* Before that reading (capture `r2x`, same kernels): ColsWarpK 90 % of the pipe, FirP1K 91 %, FirP3K 93 %.  Cutting table lookups -- twiddle powers by squaring instead of "
+  "three loads, column twiddles stepped from one `sincospi` instead of two scattered loads per element -- took FirP1K 1.73 -> 1.49 ms, FirP2K 5.02 -> 4.12, FirP3K 1.88 -> 1.61, "
+  "ColsWarpK 1.22 -> 0.95 (C5 sweep, N = 1) without touching the arithmetic.")
+w("* ColsWarp512K (16 values per lane, 128 registers, two CTAs per SM) sits at 24 % occupancy and ~50 % of the pipe: latency-bound, still 27 % faster than the block-wide tile it replaced.")
+w("* OlaK waits on its chain of dependent global loads (long scoreboard 18.6 warps per issue); PostWriteK is the one kernel near DRAM (66 %).")
+w("* synth_normal_cluster_kernel: barrier stalls lead (4 cluster barriers per round) -- the price of spreading an event over four CTAs; it still cuts the small-batch synthesis from 0.59 to 0.40 ms.\n")
+w("## 4. SASS (`sass_r02_census.md`)\n")
+w("Opcode census + excerpts of the shipped library: `UCGABAR_ARV / UCGABAR_WAIT` + the `UPRMT` / `SR_SWINHI` / `LD.E` sequence of distributed-shared-memory loads in the cluster "
+  "synthesis kernel (default path for small batches), `WARPSYNC` instead of `BAR` inside the warp-local transforms, `SHFL` scans / reductions, no `ATOM` in the scatter kernels, no `UTMA*` / `*MMA`.\n")
+w("## 5. compute-sanitizer\n")
+w("`r02_compute_sanitizer_closed.log`: the pool refuses compute-sanitizer (exit 86).  The race check is the schedule-shuffling block emulator "
+  "(`tests/test_emul_kernels.py::test_results_do_not_depend_on_the_thread_schedule`) plus bitwise repeatability and the bit-identity of the cluster synthesis kernel against the one-CTA form on the GPU.\n")
+w("## 6. Round-1 artefacts kept for the record\n")
+w("`bench_r01*`, `launches_r01*`, `ncu_full_r01i_key_kernels.csv`, `ncu_full_raw_r01c_512renders.csv`, `small_configs_r01j.json`: see git history of this file for their description.")
 open(os.path.join(P, "README.md"), "w").write(o.getvalue())
-print(o.getvalue()[:1500])
+print(o.getvalue()[:3000])
