@@ -663,7 +663,7 @@ def _prefetch(gen, depth=2):
         yield item
 
 
-def render_batch(params_list, device=None, precision="auto", host_out=None, chunk=512, depth=3, workers=None, piece=32, ramp=True):
+def render_batch(params_list, device=None, precision="auto", host_out=None, chunk=384, depth=3, workers=None, piece=32, ramp=True):
     """See _render_batch.  The cyclic garbage collector is paused for the duration of the call: a full collection over a
     few thousand parameter dicts costs ~35 ms (measured: every fifth 100 ms sweep took 135 ms) and nothing here makes cycles."""
     import gc
@@ -673,7 +673,7 @@ def render_batch(params_list, device=None, precision="auto", host_out=None, chun
     # the launching thread shares the interpreter with the planning threads: with the default 5 ms switch interval every
     # return from a ctypes / CUDA call could wait that long for the lock (measured: 5-7 ms per slice set-up instead of 2)
     si = sys.getswitchinterval()
-    sys.setswitchinterval(1e-4)
+    sys.setswitchinterval(float(_os_env("MS_SWITCH") or 1e-4))
     try:
         return _render_batch(params_list, device, precision, host_out, chunk, depth, workers, piece, ramp)
     finally:
@@ -687,7 +687,7 @@ def _os_env(name):
     return os.environ.get(name, "")
 
 
-def _render_batch(params_list, device=None, precision="auto", host_out=None, chunk=512, depth=3, workers=None, piece=32, ramp=True):
+def _render_batch(params_list, device=None, precision="auto", host_out=None, chunk=384, depth=3, workers=None, piece=32, ramp=True):
     """Independent renders (the reference's batch loop, main_v2.py:1578-1593) streamed through the GPU.
 
     The batch is cut into slices of `chunk` renders.  Worker processes plan slice k+1 (numpy Generators,

@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--precision", default="auto", choices=["auto", "f32", "f64"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=48, help="renders timed for cpu_baseline (rank 0, N=1)")
-    ap.add_argument("--chunk", type=int, default=512, help="renders per streamed slice of the end-to-end run")
+    ap.add_argument("--chunk", type=int, default=384, help="renders per streamed slice of the end-to-end run (measured on B200, 4096 renders: "
+                                                           "256 -> 81.5 ms, 320 -> 74.5, 384 -> 74.8, 512 -> 78.5, 768 -> 79.0, 1024 -> 78.5)")
     ap.add_argument("--slices", type=int, default=0,
                     help="N>1: parts per rank whose gather overlaps the next part's rendering; each part replays a CUDA graph of "
                          "its launch sequence, so small parts are not launch-bound.  0 = auto (1 at N=1, 4 at N>1)")
