@@ -44,9 +44,12 @@ template <int LD, int MODE, int ST, int SQ = 0> struct RowsK {
     static constexpr int MINB = (SQ && sizeof(real) == 8) ? MS_SQ_MINB : MS_FFT_MINB;
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_rows_body<LD, MODE, ST, SQ>(jobs, c); }
 };
+#ifndef MS_SPECOP_MINB
+#define MS_SPECOP_MINB 6          // 40 registers (the cold operator branches spill): 1.98 -> 1.62 ms over the sweep; 7 and 8 were slower
+#endif
 struct SpecOpK {                                                    // spectral operators, elementwise, in front of the inverse
     static constexpr int MAXT = SPECOP_NTHR;
-    static constexpr int MINB = 4;
+    static constexpr int MINB = MS_SPECOP_MINB;
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { spec_op_body(jobs, c); }
 };
 // tile width of the static 256 x 256 kernels: what plan_direct picks for 65536 points in this precision

@@ -3,11 +3,19 @@
 struct SynthNormalK { static constexpr int MAXT = SY_NTHR;
     static constexpr int MINB = 4;
     static MS_DEV void run(const SynthEvt* e, real* pool, const Ctx& c) { synth_normal_body(e, pool, c); } };
+// (latency-bound elementwise kernels gain from residency, measured on the C5 sweep: SynthTiltK 0.59 -> 0.39 ms at eight CTAs
+//  per SM, SynthDustK 0.76 -> 0.54 at five; six and eight for the dust kernel were no better)
+#ifndef MS_TILT_MINB
+#define MS_TILT_MINB 8
+#endif
+#ifndef MS_DUST_MINB
+#define MS_DUST_MINB 5
+#endif
 struct SynthTiltK { static constexpr int MAXT = 256;
-    static constexpr int MINB = 1;
+    static constexpr int MINB = MS_TILT_MINB;
     static MS_DEV void run(const SynthEvt* e, real* pool, const Ctx& c) { synth_tilt_finish_body(e, pool, c); } };
 struct SynthDustK { static constexpr int MAXT = 256;
-    static constexpr int MINB = 1;
+    static constexpr int MINB = MS_DUST_MINB;
     static MS_DEV void run(const SynthEvt* e, const int* dp, const real* dv, real* pool, const Ctx& c) { synth_dust_body(e, dp, dv, pool, c); } };
 struct SynthTableK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
@@ -40,7 +48,7 @@ struct ImprintK { static constexpr int MAXT = 256;
     static constexpr int MINB = 1;
     static MS_DEV void run(const ImprintEvt* e, const ImprintRender* r, cpx* z, const Ctx& c) { imprint_body(e, r, z, c); } };
 #ifndef MS_OLA_MINB
-#define MS_OLA_MINB 1
+#define MS_OLA_MINB 8          // 32 registers, eight CTAs per SM: the kernel waits on dependent global loads (measured 1.54 -> 1.26 ms)
 #endif
 struct OlaK { static constexpr int MAXT = OLA_NTHR;
     static constexpr int MINB = MS_OLA_MINB;

@@ -9,7 +9,7 @@ cp $src/*.cu $src/*.cuh $src/*.h $src/*.inl $src/Makefile $out/csrc/
 cp /root/repo/include/*.h $out/include/
 sed -i 's#../../include/microsound_b200.h#../include/microsound_b200.h#' $out/csrc/ms_prelude.h
 sed -i 's#../../include/\*.h#../include/*.h#' $out/csrc/Makefile
-make -s -j4 -C $out/csrc EXTRA="$extra"
+make -s -j4 -C $out/csrc libmicrosound_b200.so EXTRA="$extra"
 cp $out/csrc/libmicrosound_b200.so $out/
 rm -rf $out/csrc $out/include
 ls -la $out
