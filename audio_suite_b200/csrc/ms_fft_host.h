@@ -34,9 +34,12 @@ template <int LD, int ST, int TWID> struct ColsWarpPlainK {         // plain col
     static constexpr int MINB = MS_WB_MINB;
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_warp_plain_body<LD, ST, TWID>(jobs, c); }
 };
+#ifndef MS_WB5_MINB
+#define MS_WB5_MINB 2
+#endif
 template <int LD, int ST, int TWID> struct ColsWarp512K {           // in-tile Bluestein, B1 = 512, warp-local transforms (16 values per lane)
     static constexpr int MAXT = 256;
-    static constexpr int MINB = 2;
+    static constexpr int MINB = MS_WB5_MINB;
     static MS_DEV void run(const FftJob* jobs, const Ctx& c) { fft_cols_warp512_body<LD, ST, TWID>(jobs, c); }
 };
 template <int LD, int MODE, int ST, int SQ = 0> struct RowsK {
