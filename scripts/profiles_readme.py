@@ -87,7 +87,9 @@ w("* Before that reading (capture `r2x`, same kernels): ColsWarpK 90 % of the pi
   "three loads, column twiddles stepped from one `sincospi` instead of two scattered loads per element -- took FirP1K 1.73 -> 1.49 ms, FirP2K 5.02 -> 4.12, FirP3K 1.88 -> 1.61, "
   "ColsWarpK 1.22 -> 0.95 (C5 sweep, N = 1) without touching the arithmetic.")
 w("* ColsWarp512K (16 values per lane, 128 registers, two CTAs per SM) sits at 24 % occupancy and ~50 % of the pipe: latency-bound, still 27 % faster than the block-wide tile it replaced.")
-w("* OlaK waits on its chain of dependent global loads (long scoreboard 18.6 warps per issue); PostWriteK is the one kernel near DRAM (66 %).")
+w("* OlaK waits on its chain of dependent global loads (long scoreboard 18.6 warps per issue at 64 registers / 44 % occupancy in this capture); "
+  "capping it at 32 registers afterwards (eight CTAs per SM) took it 1.54 -> 1.27 ms, and the same cap took SynthTiltK 0.59 -> 0.39, SynthDustK 0.76 -> 0.54 and "
+  "SpecOpK 1.98 -> 1.62 ms (the table above predates that change for these four kernels; `r02_bench_n1.json` has their final times).  PostWriteK is the one kernel near DRAM (66 %).")
 w("* synth_normal_cluster_kernel: barrier stalls lead (4 cluster barriers per round) -- the price of spreading an event over four CTAs; it still cuts the small-batch synthesis from 0.59 to 0.40 ms.\n")
 w("## 4. SASS (`sass_r02_census.md`)\n")
 w("Opcode census + excerpts of the shipped library: `UCGABAR_ARV / UCGABAR_WAIT` + the `UPRMT` / `SR_SWINHI` / `LD.E` sequence of distributed-shared-memory loads in the cluster "
