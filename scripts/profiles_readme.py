@@ -55,9 +55,9 @@ for n in (1, 2, 4, 8):
         n, x["ms_per_step"], ("%.2f" % x["ms_per_step_render_only"]) if x.get("ms_per_step_render_only") else "-", x["value"], x["value"] / base,
         x["value"] / base / n, y["ms_per_step"], x["e2e"]["ms_per_step"]))
 w("")
-w("Where the 8-GPU step goes (per-rank CUDA events, `MS_RANK_TIMES=1`): a rank renders its 512 renders in 4.23-4.39 ms alone (the ideal share is 3.82 ms: "
+w("Where the 8-GPU step goes (per-rank CUDA events, `MS_RANK_TIMES=1`): a rank renders its 512 renders in about 4.2-4.4 ms alone (the ideal share is 3.7 ms: "
   "sixty launches over an eighth of the batch leave partial waves); with the gather in flight every rank's kernels take 0.45-0.5 ms longer and the "
-  "ranks are coupled pass by pass through the gather's barriers (5.0 ms).  NCCL's gather in place of the peer copies: 6.0 ms; without the overlap: 9.0 ms.  "
+  "ranks are coupled pass by pass through the gather's barriers (4.9 ms).  NCCL's gather in place of the peer copies: 6.0 ms; without the overlap: 9.0 ms.  "
   "End to end the multi-GPU runs are bound by the host: eight GPUs draining to pinned host memory at once get about 12 GB/s each "
   "(~100 GB/s in total on these boxes, against 50 GB/s for one GPU alone), so 3.15 GB of audio cost ~32 ms whatever N >= 2 is.\n")
 w("### The other BASELINE.json configs, one render each (`r02_bench_C*.json`, `bench.py --config`)\n")
@@ -67,7 +67,7 @@ for c in ("C1b", "C1", "C2", "C3", "C4"):
     w("| %s | %.3f | %.2f | %.3e | %s |" % (c, x["ms_per_step"], x["e2e"]["ms_per_step"], x["cpu_baseline"]["value"], x.get("gpu_launches")))
 w("")
 w("C1-C3 are launch-latency-sized (a few hundred KB of data); `render()` is dominated by Python (plan cache lookup, one D2H, the float64 copy the reference returns).  "
-  "C4 (57.6 M frames): 22 ms of kernels; `render()` spends the rest converting 461 MB of float32 into the float64 array the reference's signature promises.\n")
+  "C4 (57.6 M frames): 21 ms of kernels; `render()` spends the rest bringing the 922 MB float64 array the reference's signature promises to pageable host memory.\n")
 w("## 2. ncu launch list of one step, 512-render slab (`launches_r02_512renders.csv`, table in `r02_launch_table.md`)\n")
 w("`ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none` around the timed step of "
   "`bench.py --renders 512` (after the same command had exited 0 without ncu).  Stage shares under ncu:\n")
