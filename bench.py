@@ -486,13 +486,15 @@ def run_ours(args):
                 "e2e": {"value": total_samples / (e2e_ms_max * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_max,
                         "steps": len(e2e_ms), "warmup": E2E_WARM, "ms_each_rank0": [round(x, 2) for x in e2e_ms],
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                        "includes": "host planning (numpy RNG draws, job tables), pinned H2D of tables, all kernels, D2H of float32 audio "
+                        "includes": "host planning (numpy's RNG streams restated natively, job tables), pinned H2D of tables, all kernels, D2H of float32 audio "
                                     "into pinned host memory; streamed in slices of %d renders so the three overlap" % args.chunk},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                              "frac": round(ach / peak, 4), "traffic": traffic, "traffic_note": traffic_note,
                              "algorithmic_bytes": alg.get(dom, 0), "launches": "see kernels_ms", "peak_source": peak_src,
                              "note": "stage = consecutive launches of one pipeline stage, CUDA events on the launch stream; "
-                                     "see profiles/ for the per-kernel ncu launch list"},
+                                     "see profiles/ for the per-kernel ncu launch list.  \"hbm\" is the tier's accounting; the "
+                                     "resource that binds the FFT-type kernels of these stages is the SM's L1 / shared-memory data pipe "
+                                     "(ncu l1tex__data_pipe_lsu_wavefronts at 70-93 % of peak, DRAM at 5-54 %: profiles/r02_ncu_key_metrics.md)"},
                 "stages": stages,
                 "kernels_ms": kernel_ms}
         if world == 1 and args.cpu_sample > 0:
