@@ -106,7 +106,7 @@ struct SpecStreams {
                                              && cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess;
     }
-    static SpecStreams& get() { static SpecStreams v; return v; }
+    static SpecStreams& get() { static thread_local SpecStreams v; return v; }     // (per host thread: the events are re-recorded by every call)
 };
 // development switch MS_SPEC_STREAMS=0: one stream, class after class
 static bool spec_streams_on() { static int v = -1; if (v < 0) { const char* e = getenv("MS_SPEC_STREAMS"); v = (e && e[0] == '0') ? 0 : 1; } return v != 0; }
